@@ -1,0 +1,143 @@
+/*
+ * ttb.h -- C-ABI of the B200 marginal ancestral-reconstruction engine (libttb.so).
+ *
+ * This is the drop-in boundary for ONE hot path of neherlab/treetime:
+ * TreeAnc._ml_anc_marginal (treetime/treeanc.py:762-932) and the branch-length /
+ * likelihood surface that consumes its messages (treeanc.py:1085-1146,1272-1360,
+ * gtr.py:816-963).  The reference has no FFI (it is pure Python/numpy); every entry
+ * point below names the reference code it replaces.  INTEGRATION.md shows the ctypes
+ * binding a TreeTime maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative TTB_E* code; ttb_last_error()
+ *    returns a thread-local description.  No C++ exception crosses the boundary.
+ *  - the caller owns every host buffer; the library owns device memory behind the handle.
+ *  - one handle = one GPU = one shard of the pattern axis.  Calls on a handle are
+ *    stream-ordered and not thread-safe.  Only ttb_fetch_* / ttb_results / ttb_sync block.
+ *  - nodes are numbered in the reference's preorder (tree.find_clades()), root = 0;
+ *    children are listed in `node.clades` order.
+ *  - host matrices handed in/out are row-major (L', q) like the reference's numpy arrays;
+ *    on the device messages are state-planar [node][state][pattern].
+ */
+#ifndef TTB_H
+#define TTB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ttb_engine* ttb_handle;
+
+enum {
+  TTB_OK = 0,
+  TTB_EINVAL = -1,   /* bad argument / call order */
+  TTB_ECUDA = -2,    /* CUDA runtime error (message has the CUDA string) */
+  TTB_ENOMEM = -3,   /* device allocation failed */
+  TTB_EUNSUPPORTED = -4 /* e.g. n_states without a compiled kernel */
+};
+
+/* which per-node array ttb_fetch_node returns */
+enum {
+  TTB_SUBTREE = 0,  /* node.marginal_subtree_LH   (treeanc.py:877)  */
+  TTB_OUTGROUP = 1, /* node.marginal_outgroup_LH  (treeanc.py:895-899) */
+  TTB_PROFILE = 2   /* node.marginal_profile      (treeanc.py:822-824,910-912) */
+};
+
+/* flags of ttb_marginal */
+enum {
+  TTB_RECONSTRUCT_TIPS = 1, /* reconstruct_tip_states=True (treeanc.py:900-903) */
+  TTB_LH_ONLY = 2           /* postorder + root only: the cost function of optimize_gtr_rate (treeanc.py:1685-1689) */
+};
+
+/* kinds of branch evaluated by ttb_branch_objective / ttb_branch_hamming */
+enum {
+  TTB_BRANCH = 0,      /* (pp, pc) = (outgroup_LH(n), subtree_LH(n))            treeanc.py:1122-1146 */
+  TTB_BRANCH_ROOT = 1  /* merged branch across a bifurcating root, n = first root child:
+                          pc = subtree(n1), pp = normalize(subtree(n2) * Pi)     treeanc.py:1317-1326 */
+};
+
+const char* ttb_last_error(void);
+int ttb_version(void);
+/* 1 if kernels for this alphabet size are compiled in (2..8 and 20..24) */
+int ttb_supports_n_states(int n_states);
+
+/* Create an engine on CUDA device `device` for an alphabet of n_states (gtr.n_states). */
+int ttb_create(ttb_handle* out, int device, int n_states);
+int ttb_destroy(ttb_handle h);
+/* Run on an externally owned stream (e.g. torch's current stream); NULL = engine's own stream. */
+int ttb_set_stream(ttb_handle h, void* cuda_stream);
+
+/* Tree topology (replaces the Bio.Phylo walk of treeanc.py:857,887).  parent[root] = -1.
+ * tip_row[n] = row of the tip-code matrix for terminal nodes, -1 for internal nodes.
+ * The level schedules (by height for the postorder, by depth for the preorder) are
+ * built inside. */
+int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int32_t* child_ptr,
+                 const int32_t* child_idx, const int32_t* tip_row);
+
+/* Compressed alignment shard (replaces seq2prof on the leaves, treeanc.py:846-853):
+ * tip_codes[n_tips][n_patterns] uint8 indices into code_profiles[n_codes][n_states]
+ * (the values of gtr.profile_map), multiplicity[n_patterns] = data.multiplicity(). */
+int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes, int32_t n_codes,
+                     const double* code_profiles, const double* multiplicity);
+
+/* Single-site GTR eigen-system (gtr.py:612-629): eigvals[q], v[q][q], v_inv[q][q], Pi[q], mu.
+ * gap_index = gtr.gap_index or -1 (used by the branch objective, gtr.py:954-959). */
+int ttb_set_gtr(ttb_handle h, const double* eigvals, const double* v, const double* v_inv,
+                const double* Pi, double mu, int32_t gap_index);
+
+/* Site-specific GTR (gtr_site_specific.py:312-371), arrays in the reference's layout for
+ * this shard's patterns: eigvals[q][L'], v[q][q][L'], v_inv[q][q][L'], Pi[q][L'], mu[L'];
+ * t_grid[n_grid] is the interpolation grid (:336-344); approximate != 0 selects the
+ * linear-in-t interpolated expQt for t*rate_scale < 10 (:367-371). */
+int ttb_set_gtr_site_specific(ttb_handle h, const double* eigvals, const double* v, const double* v_inv,
+                              const double* Pi, const double* mu, const double* t_grid, int32_t n_grid,
+                              double rate_scale, int32_t approximate, int32_t gap_index);
+
+/* t[n_nodes]: branch lengths as the GTR sees them, i.e. after _branch_length_to_gtr
+ * (treeanc.py:752-760).  t[root] is ignored. */
+int ttb_set_branch_lengths(ttb_handle h, const double* t);
+
+/* Enqueue one marginal reconstruction: batched expQt, level-ordered postorder, root,
+ * level-ordered preorder (treeanc.py:762-812), one CUDA graph launch.  Asynchronous. */
+int ttb_marginal(ttb_handle h, int32_t flags);
+/* Wait for the last ttb_marginal and return this shard's partial results:
+ * total_lh = sum_a LH_a * multiplicity_a (treeanc.py:828), n_diff = number of (node, pattern)
+ * state indices that changed w.r.t. the previous reconstruction (treeanc.py:925-926). */
+int ttb_results(ttb_handle h, double* total_lh, int64_t* n_diff);
+/* Device address of the double[2] {total_lh, n_diff} written by the last pass (for NCCL allreduce). */
+int ttb_results_device_ptr(ttb_handle h, void** dptr);
+int ttb_sync(ttb_handle h);
+
+/* tree.sequence_LH (treeanc.py:825-827): out[n_patterns]. */
+int ttb_fetch_site_lh(ttb_handle h, double* out);
+/* One per-node array, row-major out[n_patterns][n_states]. */
+int ttb_fetch_node(ttb_handle h, int32_t node, int32_t which, double* out);
+/* argmax state indices (alphabet[idx] = node._cseq, seq_utils.py:271) for `n` nodes:
+ * out[n][n_patterns].  Tips only after TTB_RECONSTRUCT_TIPS. */
+int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* out);
+
+/* Branch-length likelihood surface: f[e] = prob_t_profiles((pp,pc), multiplicity, t[e],
+ * return_log=True) (gtr.py:922-963) for the branch above nodes[e] (kind[e], may be NULL = all
+ * TTB_BRANCH), using the messages of the last ttb_marginal.  Partial sum over this shard. */
+int ttb_branch_objective(ttb_handle h, int32_t n_eval, const int32_t* nodes, const int32_t* kind,
+                         const double* t, double* f);
+/* num[e] = sum_a m_a (pp_a . pc_a) for the same branches; *den = sum_a m_a
+ * (hamming_distance = 1 - num/den, gtr.py:871-874). */
+int ttb_branch_hamming(ttb_handle h, int32_t n_eval, const int32_t* nodes, const int32_t* kind,
+                       double* num, double* den);
+
+/* Expected substitution statistics of infer_gtr(marginal=True) (treeanc.py:1556-1572):
+ * n_ij[q][q] and T_i[q] summed over this shard's patterns and all branches. */
+int ttb_mutation_counts(ttb_handle h, double* n_ij, double* T_i);
+
+/* Bytes of device memory currently held by the handle. */
+int ttb_device_bytes(ttb_handle h, int64_t* bytes);
+/* Kernel launches issued by the library since creation (bench.py's gpu_launches). */
+int ttb_launch_count(ttb_handle h, int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTB_H */

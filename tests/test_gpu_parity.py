@@ -1,0 +1,160 @@
+"""GPU parity: CUDA engine (through the C-ABI) vs the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+import flat_numpy as O
+import util
+from treetime_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+LH_RTOL = 1e-9      # BASELINE.json: total log-LH within 1e-9 relative (fp64)
+PROF_ATOL = 1e-6    # BASELINE.json: marginal profiles within 1e-6
+
+
+def compare_all(flat, g, eng, res, reconstruct_tips=False, every=1):
+    n_nodes = flat['parent'].shape[0]
+    site = eng.site_lh()
+    assert np.allclose(site, res.sequence_LH, rtol=1e-11, atol=1e-11)
+    worst = 0.0
+    for n in range(0, n_nodes, every):
+        tip = flat['tip_row'][n] >= 0
+        s = eng.node_array(n, 0)
+        worst = max(worst, np.abs(s - res.subtree_LH[n]).max())
+        o = eng.node_array(n, 1)
+        worst = max(worst, np.abs(o - res.outgroup_LH[n]).max())
+        if not tip or reconstruct_tips:
+            p = eng.node_array(n, 2)
+            worst = max(worst, np.abs(p - res.profile[n]).max())
+            idx = eng.seq_idx([n])[0]
+            bad = idx != res.seq_idx[n]
+            if bad.any():
+                assert util.tie_mask(res.profile[n])[bad].all(), 'argmax differs off ties at node %d' % n
+    assert worst < PROF_ATOL, worst
+    return worst
+
+
+@pytest.mark.parametrize('n_tips,L,seed', [(3, 64, 1), (50, 300, 2), (200, 1400, 3)])
+def test_nuc_binary(n_tips, L, seed):
+    tree = synth.random_tree(n_tips, seed=seed, mean_bl=0.01)
+    topo, flat, g = util.make_flat(tree, util.nuc_gtr(), L, seed, amb_frac=0.02)
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    tot, nd = eng.results()
+    res = O.marginal(flat, g)
+    assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+    assert nd == res.N_diff
+    w = compare_all(flat, g, eng, res, every=1 if n_tips <= 50 else 7)
+    # second pass: nothing changes
+    eng.marginal()
+    tot2, nd2 = eng.results()
+    assert tot2 == tot and nd2 == 0
+    print('nuc n=%d L\'=%d  relLH=%.2e  max|dprof|=%.2e' % (n_tips, flat['multiplicity'].shape[0],
+                                                         abs(tot - res.total_LH) / abs(res.total_LH), w))
+
+
+def test_polytomies_and_zero_branches():
+    tree = synth.random_tree(300, seed=4, mean_bl=0.005, polytomy_frac=0.5, zero_frac=0.3)
+    topo, flat, g = util.make_flat(tree, util.nuc_gtr(), 600, 4, amb_frac=0.01)
+    assert np.diff(flat['child_ptr']).max() > 4
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    tot, nd = eng.results()
+    res = O.marginal(flat, g)
+    assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+    compare_all(flat, g, eng, res, every=5)
+
+
+def test_star_tree_huge_polytomy():
+    """One node with 3000 children: exercises the power-of-two rescaling."""
+    from treetime_b200.tree import Node, Tree
+    rng = np.random.default_rng(7)
+    root = Node(clades=[Node(name='t%06d' % i, branch_length=float(b)) for i, b in enumerate(rng.exponential(0.3, 3000))])
+    tree = Tree(root)
+    topo, flat, g = util.make_flat(tree, util.nuc_gtr(), 200, 7)
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    tot, _ = eng.results()
+    res = O.marginal(flat, g)
+    assert np.isfinite(tot)
+    assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+    assert np.allclose(eng.site_lh(), res.sequence_LH, rtol=1e-11)
+
+
+def test_reconstruct_tip_states():
+    tree = synth.random_tree(40, seed=5, mean_bl=0.02)
+    topo, flat, g = util.make_flat(tree, util.nuc_gtr(), 250, 5, amb_frac=0.05)
+    eng = util.engine_for(flat, g)
+    eng.marginal(reconstruct_tips=True)
+    tot, nd = eng.results()
+    res = O.marginal(flat, g, reconstruct_tip_states=True)
+    assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+    assert nd == res.N_diff
+    compare_all(flat, g, eng, res, reconstruct_tips=True)
+
+
+@pytest.mark.parametrize('alphabet,q', [('nuc_nogap', 4), ('aa_nogap', 20), ('aa', 22)])
+def test_other_alphabets(alphabet, q):
+    gtr = util.random_gtr(alphabet, 11)
+    assert gtr.n_states == q
+    tree = synth.random_tree(60, seed=6, mean_bl=0.05)
+    topo, flat, g = util.make_flat(tree, gtr, 200, 6)
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    tot, nd = eng.results()
+    res = O.marginal(flat, g)
+    assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+    compare_all(flat, g, eng, res, every=3)
+
+
+def test_lh_only_and_new_rate():
+    """optimize_gtr_rate's cost function: postorder + root only, for several mu."""
+    tree = synth.random_tree(100, seed=8, mean_bl=0.01)
+    topo, flat, g = util.make_flat(tree, util.nuc_gtr(), 400, 8)
+    eng = util.engine_for(flat, g)
+    for mu in (0.5, 1.0, 2.0):
+        gg = dict(g); gg['mu'] = g['mu'] * mu
+        eng.set_gtr(gg)
+        eng.marginal(lh_only=True)
+        tot, _ = eng.results()
+        ref = O.sequence_LH_only(flat, gg)
+        assert abs(tot - ref.total_LH) <= LH_RTOL * abs(ref.total_LH)
+
+
+def test_branch_objective_hamming_counts():
+    tree = synth.random_tree(60, seed=9, mean_bl=0.02)
+    topo, flat, g = util.make_flat(tree, util.nuc_gtr(), 500, 9, amb_frac=0.02)
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    eng.results()
+    res = O.marginal(flat, g)
+    G = O.make_gtr(g)
+    nodes = np.arange(1, flat['parent'].shape[0], dtype=np.int32)
+    for tval in (1e-4, 0.01, 0.3):
+        f = eng.branch_objective(nodes, np.full(nodes.shape[0], tval))
+        ref = np.array([O.branch_objective(flat, g, res, n, tval) for n in nodes])
+        assert np.allclose(f, ref, rtol=1e-10, atol=1e-9), np.abs(f - ref).max()
+    num, den = eng.branch_hamming(nodes)
+    m = flat['multiplicity']
+    ref = np.array([np.sum(m * np.sum(res.outgroup_LH[n] * res.subtree_LH[n], axis=1)) for n in nodes])
+    assert np.allclose(num, ref, rtol=1e-12) and den == m.sum()
+    # merged root branch (treeanc.py:1317-1326)
+    n1 = flat['child_idx'][0]
+    pp, pc = O.root_branch_profiles(flat, g, res)
+    f = eng.branch_objective([n1], [0.05], kinds=[1])[0]
+    assert np.isclose(f, G.prob_t_profiles((pp, pc), m, 0.05, return_log=True), rtol=1e-10)
+    # substitution statistics (treeanc.py:1556-1572)
+    n_ij, T_i = eng.mutation_counts()
+    rn, rT = O.mutation_counts(flat, g, res)
+    assert np.allclose(n_ij, rn.sum(axis=-1), rtol=1e-10, atol=1e-12)
+    assert np.allclose(T_i, rT.sum(axis=-1), rtol=1e-10, atol=1e-12)
+
+
+def test_api_errors():
+    from treetime_b200.engine import Engine
+    from treetime_b200._lib import TTBError
+    with pytest.raises(TTBError):
+        Engine(9)            # no kernels for 9 states
+    eng = Engine(5)
+    with pytest.raises(TTBError):
+        eng.marginal()       # nothing set

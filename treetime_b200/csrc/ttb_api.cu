@@ -1,0 +1,693 @@
+// ttb_api.cu -- host side of libttb.so: the C-ABI of include/ttb.h, device memory,
+// level schedules and the CUDA-graph that covers one marginal reconstruction.
+#include "../../include/ttb.h"
+#include "ttb_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char buf_[512];                                                                         \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return fail(e_ == cudaErrorMemoryAllocation ? TTB_ENOMEM : TTB_ECUDA, buf_);            \
+    }                                                                                         \
+  } while (0)
+
+// Dispatch on the compile-time alphabet size.
+#define TTB_DISPATCH_Q(q, ...)                       \
+  switch (q) {                                       \
+    case 2: { constexpr int Q = 2; __VA_ARGS__; } break;   \
+    case 3: { constexpr int Q = 3; __VA_ARGS__; } break;   \
+    case 4: { constexpr int Q = 4; __VA_ARGS__; } break;   \
+    case 5: { constexpr int Q = 5; __VA_ARGS__; } break;   \
+    case 6: { constexpr int Q = 6; __VA_ARGS__; } break;   \
+    case 7: { constexpr int Q = 7; __VA_ARGS__; } break;   \
+    case 8: { constexpr int Q = 8; __VA_ARGS__; } break;   \
+    case 20: { constexpr int Q = 20; __VA_ARGS__; } break; \
+    case 21: { constexpr int Q = 21; __VA_ARGS__; } break; \
+    case 22: { constexpr int Q = 22; __VA_ARGS__; } break; \
+    default: break;                                  \
+  }
+
+bool q_supported(int q) { return (q >= 2 && q <= 8) || (q >= 20 && q <= 22); }
+
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (count == n && p) return 0;
+    release();
+    if (count == 0) return 0;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      cudaGetLastError();
+      char buf[256];
+      snprintf(buf, sizeof buf, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      return fail(TTB_ENOMEM, buf);
+    }
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+struct Level {
+  int begin, count;
+};
+
+}  // namespace
+
+struct ttb_engine {
+  int device = 0;
+  int q = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  // tree (host)
+  int n_nodes = 0, n_int = 0, n_tips = 0;
+  std::vector<int> parent, child_ptr, child_idx, tip_row, int_slot;
+  std::vector<int> post_nodes, pre_int_parents, pre_all_parents;
+  std::vector<Level> post_levels, pre_int_levels, pre_all_levels;
+  // device tree
+  DBuf<int> d_parent, d_child_ptr, d_child_idx, d_tip_row, d_int_slot, d_post_nodes, d_pre_int, d_pre_all;
+  // alignment
+  long long Lp = 0, ld = 0;
+  int n_codes = 0;
+  DBuf<uint8_t> d_codes;
+  DBuf<double> d_code_prof, d_mult;
+  DBuf<uint32_t> d_code_mask;
+  std::vector<double> h_mult;
+  // model
+  bool have_gtr = false, have_t = false;
+  double mu = 1.0;
+  int gap_index = -1;
+  DBuf<double> d_t, d_eig, d_v, d_vinv, d_Pi, d_mu;
+  // state
+  DBuf<double> d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
+  DBuf<uint8_t> d_idx, d_idxtip;
+  DBuf<unsigned long long> d_nd;
+  DBuf<int> d_enodes, d_ekinds;
+  DBuf<double> d_ets, d_eout;
+  double* h_results = nullptr;  // pinned {total, ndiff}
+  bool have_pass = false;       // a full (non LH-only) pass has completed
+  bool have_tip_pass = false;
+  bool first_full = true;       // no previous state indices to diff against
+  std::map<int, cudaGraphExec_t> graphs;
+  std::map<int, int> graph_kernels;
+  long long launches = 0;
+
+  int tiles() const { return (int)((Lp + TTB_BLOCK - 1) / TTB_BLOCK); }
+
+  void drop_graphs() {
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    graphs.clear();
+    graph_kernels.clear();
+  }
+
+  TtbDev dev() const {
+    TtbDev d;
+    d.q = q;
+    d.Lp = Lp;
+    d.ld = ld;
+    d.n_nodes = n_nodes;
+    d.n_int = n_int;
+    d.n_tips = n_tips;
+    d.n_codes = n_codes;
+    d.gap_index = gap_index;
+    d.parent = d_parent.p;
+    d.child_ptr = d_child_ptr.p;
+    d.child_idx = d_child_idx.p;
+    d.tip_row = d_tip_row.p;
+    d.int_slot = d_int_slot.p;
+    d.codes = d_codes.p;
+    d.code_prof = d_code_prof.p;
+    d.code_mask = d_code_mask.p;
+    d.mult = d_mult.p;
+    d.t = d_t.p;
+    d.eig = d_eig.p;
+    d.v = d_v.p;
+    d.vinv = d_vinv.p;
+    d.Pi = d_Pi.p;
+    d.mu = d_mu.p;
+    d.P = d_P.p;
+    d.S = d_S.p;
+    d.F = d_F.p;
+    d.M = d_M.p;
+    d.Mtip = d_Mtip.p;
+    d.idx = d_idx.p;
+    d.idxtip = d_idxtip.p;
+    d.LH = d_LH.p;
+    d.lh_partial = d_lh_partial.p;
+    d.nd_slots = d_nd.p;
+    d.results = d_results.p;
+    return d;
+  }
+};
+
+namespace {
+
+int use_device(ttb_handle h) {
+  if (!h) return fail(TTB_EINVAL, "null handle");
+  CK(cudaSetDevice(h->device));
+  return 0;
+}
+
+template <typename T>
+int upload(DBuf<T>& b, const T* src, size_t n, cudaStream_t s) {
+  int rc = b.alloc(n);
+  if (rc) return rc;
+  if (n) CK(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+// Group internal nodes into level lists.
+void build_levels(const std::vector<int>& key, const std::vector<char>& member, std::vector<int>& nodes,
+                  std::vector<Level>& levels) {
+  int maxk = -1;
+  for (size_t n = 0; n < key.size(); ++n)
+    if (member[n]) maxk = std::max(maxk, key[n]);
+  std::vector<int> count(maxk + 2, 0);
+  for (size_t n = 0; n < key.size(); ++n)
+    if (member[n]) count[key[n] + 1]++;
+  for (int k = 0; k <= maxk; ++k) count[k + 1] += count[k];
+  nodes.assign(count[maxk + 1], 0);
+  std::vector<int> fill(count.begin(), count.end() - 1);
+  for (size_t n = 0; n < key.size(); ++n)
+    if (member[n]) nodes[fill[key[n]]++] = (int)n;
+  levels.clear();
+  for (int k = 0; k <= maxk; ++k)
+    if (count[k + 1] > count[k]) levels.push_back({count[k], count[k + 1] - count[k]});
+}
+
+template <int Q>
+size_t level_smem(int n_codes) {
+  return Smem<Q>::bytes(n_codes);
+}
+
+// Enqueue every kernel of one pass on `s`; returns the number of kernels.
+int enqueue_pass(ttb_handle h, int flags, int count_diff, cudaStream_t s, int* n_kernels) {
+  const TtbDev d = h->dev();
+  const int tiles = h->tiles();
+  const bool lh_only = flags & TTB_LH_ONLY;
+  const bool tips = flags & TTB_RECONSTRUCT_TIPS;
+  int nk = 0;
+  TTB_DISPATCH_Q(h->q, {
+    const size_t smem = level_smem<Q>(h->n_codes);
+    const int nthr = h->n_nodes * Q;
+    expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
+    ++nk;
+    for (const Level& L : h->post_levels) {
+      post_level_kernel<Q><<<(unsigned)((long long)L.count * tiles), TTB_BLOCK, smem, s>>>(d, h->d_post_nodes.p + L.begin, tiles);
+      ++nk;
+    }
+    root_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d, lh_only ? 1 : 0);
+    ++nk;
+    if (!lh_only) {
+      zero_slots_kernel<<<4, 256, 0, s>>>(d);
+      ++nk;
+      if (tips) {
+        for (const Level& L : h->pre_all_levels) {
+          pre_level_kernel<Q, true><<<(unsigned)((long long)L.count * tiles), TTB_BLOCK, smem, s>>>(d, h->d_pre_all.p + L.begin, tiles, count_diff);
+          ++nk;
+        }
+      } else {
+        for (const Level& L : h->pre_int_levels) {
+          pre_level_kernel<Q, false><<<(unsigned)((long long)L.count * tiles), TTB_BLOCK, smem, s>>>(d, h->d_pre_int.p + L.begin, tiles, count_diff);
+          ++nk;
+        }
+      }
+    }
+    finish_kernel<<<1, 256, 0, s>>>(d, tiles);
+    ++nk;
+  });
+  *n_kernels = nk;
+  return 0;
+}
+
+int ensure_state(ttb_handle h, bool tips) {
+  const size_t q = h->q, ld = h->ld;
+  int rc;
+  if ((rc = h->d_P.alloc((size_t)h->n_nodes * q * q))) return rc;
+  if ((rc = h->d_S.alloc((size_t)h->n_int * q * ld))) return rc;
+  if ((rc = h->d_F.alloc((size_t)h->n_int * ld))) return rc;
+  if ((rc = h->d_LH.alloc(ld))) return rc;
+  if ((rc = h->d_lh_partial.alloc(h->tiles()))) return rc;
+  if ((rc = h->d_nd.alloc(1024))) return rc;
+  if ((rc = h->d_results.alloc(2))) return rc;
+  return 0;
+}
+
+int ensure_preorder_state(ttb_handle h, bool tips) {
+  const size_t q = h->q, ld = h->ld;
+  int rc;
+  if (!h->d_M.p) {
+    if ((rc = h->d_M.alloc((size_t)h->n_int * q * ld))) return rc;
+    if ((rc = h->d_idx.alloc((size_t)h->n_int * ld))) return rc;
+    CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), h->stream));
+    h->drop_graphs();
+  }
+  if (tips && !h->d_Mtip.p) {
+    if ((rc = h->d_Mtip.alloc((size_t)h->n_tips * q * ld))) return rc;
+    if ((rc = h->d_idxtip.alloc((size_t)h->n_tips * ld))) return rc;
+    CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), h->stream));
+    h->drop_graphs();
+  }
+  return 0;
+}
+
+int check_ready(ttb_handle h, bool need_pass) {
+  if (!h->n_nodes) return fail(TTB_EINVAL, "ttb_set_tree has not been called");
+  if (!h->Lp) return fail(TTB_EINVAL, "ttb_set_patterns has not been called");
+  if (!h->have_gtr) return fail(TTB_EINVAL, "ttb_set_gtr has not been called");
+  if (!h->have_t) return fail(TTB_EINVAL, "ttb_set_branch_lengths has not been called");
+  if (need_pass && !h->have_pass) return fail(TTB_EINVAL, "no marginal reconstruction has been run yet (call ttb_marginal first)");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ttb_last_error(void) { return g_err.c_str(); }
+int ttb_version(void) { return 100; }
+int ttb_supports_n_states(int n_states) { return q_supported(n_states) ? 1 : 0; }
+
+int ttb_create(ttb_handle* out, int device, int n_states) {
+  if (!out) return fail(TTB_EINVAL, "out is null");
+  if (!q_supported(n_states)) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "no kernels compiled for n_states=%d (supported: 2..8, 20..22)", n_states);
+    return fail(TTB_EUNSUPPORTED, buf);
+  }
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(TTB_EINVAL, "no such CUDA device");
+  CK(cudaSetDevice(device));
+  ttb_engine* h = new ttb_engine();
+  h->device = device;
+  h->q = n_states;
+  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CK(cudaMallocHost(&h->h_results, 2 * sizeof(double)));
+  *out = h;
+  return 0;
+}
+
+int ttb_destroy(ttb_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->drop_graphs();
+  DBuf<int>* ib[] = {&h->d_parent, &h->d_child_ptr, &h->d_child_idx, &h->d_tip_row, &h->d_int_slot, &h->d_post_nodes,
+                     &h->d_pre_int, &h->d_pre_all, &h->d_enodes, &h->d_ekinds};
+  for (auto* b : ib) b->release();
+  DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_P, &h->d_S,
+                        &h->d_F, &h->d_M, &h->d_Mtip, &h->d_LH, &h->d_lh_partial, &h->d_results, &h->d_stage,
+                        &h->d_partial, &h->d_ets, &h->d_eout};
+  for (auto* b : db) b->release();
+  h->d_codes.release();
+  h->d_code_mask.release();
+  h->d_idx.release();
+  h->d_idxtip.release();
+  h->d_nd.release();
+  if (h->h_results) cudaFreeHost(h->h_results);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+int ttb_set_stream(ttb_handle h, void* cuda_stream) {
+  if (int rc = use_device(h)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
+
+int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int32_t* child_ptr,
+                 const int32_t* child_idx, const int32_t* tip_row) {
+  if (int rc = use_device(h)) return rc;
+  if (n_nodes < 2 || !parent || !child_ptr || !child_idx || !tip_row) return fail(TTB_EINVAL, "ttb_set_tree: bad arguments");
+  if (parent[0] != -1) return fail(TTB_EINVAL, "ttb_set_tree: node 0 must be the root (parent -1)");
+  if (child_ptr[0] != 0 || child_ptr[n_nodes] != n_nodes - 1) return fail(TTB_EINVAL, "ttb_set_tree: child_ptr must cover n_nodes-1 children");
+  std::vector<int> height(n_nodes, 0), depth(n_nodes, 0), slot(n_nodes, -1);
+  int n_int = 0, n_tips = 0;
+  for (int n = 0; n < n_nodes; ++n) {
+    const int nc = child_ptr[n + 1] - child_ptr[n];
+    if (nc < 0) return fail(TTB_EINVAL, "ttb_set_tree: child_ptr not monotone");
+    if (n > 0 && (parent[n] < 0 || parent[n] >= n)) return fail(TTB_EINVAL, "ttb_set_tree: nodes must be in preorder (parent id < child id)");
+    if ((nc == 0) != (tip_row[n] >= 0)) return fail(TTB_EINVAL, "ttb_set_tree: tip_row must be >= 0 exactly for nodes without children");
+    if (nc == 0) {
+      if (tip_row[n] != n_tips) return fail(TTB_EINVAL, "ttb_set_tree: tip rows must be numbered in node order");
+      ++n_tips;
+    } else {
+      slot[n] = n_int++;
+    }
+    for (int k = child_ptr[n]; k < child_ptr[n + 1]; ++k) {
+      const int c = child_idx[k];
+      if (c <= n || c >= n_nodes || parent[c] != n) return fail(TTB_EINVAL, "ttb_set_tree: child_idx inconsistent with parent");
+    }
+    if (n > 0) depth[n] = depth[parent[n]] + 1;
+  }
+  for (int n = n_nodes - 1; n > 0; --n) height[parent[n]] = std::max(height[parent[n]], height[n] + 1);
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_nodes = n_nodes;
+  h->n_int = n_int;
+  h->n_tips = n_tips;
+  h->parent.assign(parent, parent + n_nodes);
+  h->child_ptr.assign(child_ptr, child_ptr + n_nodes + 1);
+  h->child_idx.assign(child_idx, child_idx + n_nodes - 1);
+  h->tip_row.assign(tip_row, tip_row + n_nodes);
+  h->int_slot = slot;
+  std::vector<char> is_int(n_nodes), has_int_child(n_nodes, 0);
+  for (int n = 0; n < n_nodes; ++n) is_int[n] = slot[n] >= 0;
+  for (int n = 1; n < n_nodes; ++n)
+    if (is_int[n]) has_int_child[parent[n]] = 1;
+  build_levels(height, is_int, h->post_nodes, h->post_levels);
+  build_levels(depth, has_int_child, h->pre_int_parents, h->pre_int_levels);
+  build_levels(depth, is_int, h->pre_all_parents, h->pre_all_levels);
+  cudaStream_t s = h->stream;
+  int rc;
+  if ((rc = upload(h->d_parent, h->parent.data(), h->parent.size(), s))) return rc;
+  if ((rc = upload(h->d_child_ptr, h->child_ptr.data(), h->child_ptr.size(), s))) return rc;
+  if ((rc = upload(h->d_child_idx, h->child_idx.data(), h->child_idx.size(), s))) return rc;
+  if ((rc = upload(h->d_tip_row, h->tip_row.data(), h->tip_row.size(), s))) return rc;
+  if ((rc = upload(h->d_int_slot, h->int_slot.data(), h->int_slot.size(), s))) return rc;
+  if ((rc = upload(h->d_post_nodes, h->post_nodes.data(), h->post_nodes.size(), s))) return rc;
+  if ((rc = upload(h->d_pre_int, h->pre_int_parents.data(), h->pre_int_parents.size(), s))) return rc;
+  if ((rc = upload(h->d_pre_all, h->pre_all_parents.data(), h->pre_all_parents.size(), s))) return rc;
+  CK(cudaStreamSynchronize(s));
+  // every per-node array is invalid now
+  h->d_P.release(); h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();
+  h->d_idx.release(); h->d_idxtip.release();
+  h->d_t.release();
+  h->have_t = false;
+  h->have_pass = h->have_tip_pass = false;
+  h->first_full = true;
+  h->drop_graphs();
+  return 0;
+}
+
+int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes, int32_t n_codes,
+                     const double* code_profiles, const double* multiplicity) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->n_nodes) return fail(TTB_EINVAL, "ttb_set_patterns: call ttb_set_tree first");
+  if (n_patterns <= 0 || !tip_codes || n_codes <= 0 || n_codes > 255 || !code_profiles || !multiplicity)
+    return fail(TTB_EINVAL, "ttb_set_patterns: bad arguments");
+  if (Smem<24>::bytes(n_codes) > 48 * 1024) return fail(TTB_EUNSUPPORTED, "ttb_set_patterns: too many distinct characters");
+  const long long Lp = n_patterns, ld = (Lp + 31) / 32 * 32;
+  CK(cudaStreamSynchronize(h->stream));
+  cudaStream_t s = h->stream;
+  int rc;
+  if ((rc = h->d_codes.alloc((size_t)h->n_tips * ld))) return rc;
+  CK(cudaMemsetAsync(h->d_codes.p, 0, h->d_codes.bytes(), s));
+  CK(cudaMemcpy2DAsync(h->d_codes.p, ld, tip_codes, Lp, Lp, h->n_tips, cudaMemcpyHostToDevice, s));
+  std::vector<uint32_t> mask(n_codes, 0);
+  for (int c = 0; c < n_codes; ++c)
+    for (int i = 0; i < h->q; ++i)
+      if (code_profiles[(size_t)c * h->q + i] != 0.0) mask[c] |= (1u << i);
+  if ((rc = upload(h->d_code_prof, code_profiles, (size_t)n_codes * h->q, s))) return rc;
+  if ((rc = upload(h->d_code_mask, mask.data(), mask.size(), s))) return rc;
+  if ((rc = h->d_mult.alloc(ld))) return rc;
+  CK(cudaMemsetAsync(h->d_mult.p, 0, h->d_mult.bytes(), s));
+  CK(cudaMemcpyAsync(h->d_mult.p, multiplicity, Lp * sizeof(double), cudaMemcpyHostToDevice, s));
+  h->h_mult.assign(multiplicity, multiplicity + Lp);
+  CK(cudaStreamSynchronize(s));
+  if (ld != h->ld || Lp != h->Lp) {
+    h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();
+    h->d_idx.release(); h->d_idxtip.release(); h->d_LH.release(); h->d_lh_partial.release();
+  }
+  h->Lp = Lp;
+  h->ld = ld;
+  h->n_codes = n_codes;
+  h->have_pass = h->have_tip_pass = false;
+  h->first_full = true;
+  h->drop_graphs();
+  return 0;
+}
+
+int ttb_set_gtr(ttb_handle h, const double* eigvals, const double* v, const double* v_inv, const double* Pi,
+                double mu, int32_t gap_index) {
+  if (int rc = use_device(h)) return rc;
+  if (!eigvals || !v || !v_inv || !Pi) return fail(TTB_EINVAL, "ttb_set_gtr: null argument");
+  const size_t q = h->q;
+  cudaStream_t s = h->stream;
+  int rc;
+  const bool realloc = !h->d_eig.p;
+  if ((rc = upload(h->d_eig, eigvals, q, s))) return rc;
+  if ((rc = upload(h->d_v, v, q * q, s))) return rc;
+  if ((rc = upload(h->d_vinv, v_inv, q * q, s))) return rc;
+  if ((rc = upload(h->d_Pi, Pi, q, s))) return rc;
+  if ((rc = upload(h->d_mu, &mu, 1, s))) return rc;
+  CK(cudaStreamSynchronize(s));
+  if (realloc) h->drop_graphs();
+  h->mu = mu;
+  h->gap_index = gap_index;
+  h->have_gtr = true;
+  return 0;
+}
+
+int ttb_set_gtr_site_specific(ttb_handle, const double*, const double*, const double*, const double*, const double*,
+                              const double*, int32_t, double, int32_t, int32_t) {
+  return fail(TTB_EUNSUPPORTED, "site-specific GTR models are not implemented in this build");
+}
+
+int ttb_set_branch_lengths(ttb_handle h, const double* t) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->n_nodes || !t) return fail(TTB_EINVAL, "ttb_set_branch_lengths: call ttb_set_tree first");
+  const bool realloc = !h->d_t.p;
+  if (int rc = h->d_t.alloc(h->n_nodes)) return rc;
+  // pageable source: the copy is staged before the call returns, so the caller may reuse `t`
+  CK(cudaMemcpyAsync(h->d_t.p, t, h->n_nodes * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (realloc) h->drop_graphs();
+  h->have_t = true;
+  return 0;
+}
+
+int ttb_marginal(ttb_handle h, int32_t flags) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, false)) return rc;
+  const bool lh_only = flags & TTB_LH_ONLY;
+  const bool tips = (flags & TTB_RECONSTRUCT_TIPS) && !lh_only;
+  flags = (lh_only ? TTB_LH_ONLY : 0) | (tips ? TTB_RECONSTRUCT_TIPS : 0);
+  const bool had_P = h->d_P.p != nullptr;
+  if (int rc = ensure_state(h, tips)) return rc;
+  if (!had_P) h->drop_graphs();
+  if (!lh_only)
+    if (int rc = ensure_preorder_state(h, tips)) return rc;
+  const int count_diff = lh_only ? 0 : 1;
+  const int key = flags;
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    // capture on the engine's own stream, replay on whatever stream is current
+    cudaGraph_t graph;
+    int nk = 0;
+    CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_pass(h, flags, count_diff, h->own_stream, &nk);
+    cudaError_t ce = cudaStreamEndCapture(h->own_stream, &graph);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(TTB_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec;
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    h->graphs[key] = exec;
+    h->graph_kernels[key] = nk;
+    it = h->graphs.find(key);
+  }
+  CK(cudaGraphLaunch(it->second, h->stream));
+  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  h->launches += h->graph_kernels[key];
+  if (!lh_only) {
+    h->have_pass = true;
+    h->have_tip_pass = tips;
+  }
+  return 0;
+}
+
+int ttb_results(ttb_handle h, double* total_lh, int64_t* n_diff) {
+  if (int rc = use_device(h)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  if (total_lh) *total_lh = h->h_results[0];
+  if (n_diff) *n_diff = (int64_t)h->h_results[1];
+  return 0;
+}
+
+int ttb_results_device_ptr(ttb_handle h, void** dptr) {
+  if (int rc = use_device(h)) return rc;
+  if (!dptr) return fail(TTB_EINVAL, "dptr is null");
+  if (int rc = h->d_results.alloc(2)) return rc;
+  *dptr = h->d_results.p;
+  return 0;
+}
+
+int ttb_sync(ttb_handle h) {
+  if (int rc = use_device(h)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ttb_fetch_site_lh(ttb_handle h, double* out) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->d_LH.p || !out) return fail(TTB_EINVAL, "ttb_fetch_site_lh: nothing computed yet");
+  CK(cudaMemcpyAsync(out, h->d_LH.p, h->Lp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ttb_fetch_node(ttb_handle h, int32_t node, int32_t which, double* out) {
+  if (int rc = use_device(h)) return rc;
+  if (node < 0 || node >= h->n_nodes || !out || which < 0 || which > 2) return fail(TTB_EINVAL, "ttb_fetch_node: bad arguments");
+  const bool tip = h->tip_row[node] >= 0;
+  if (which == TTB_SUBTREE) {
+    if (!tip && !h->d_S.p) return fail(TTB_EINVAL, "ttb_fetch_node: run ttb_marginal first");
+  } else {
+    if (int rc = check_ready(h, true)) return rc;
+    if (which == TTB_PROFILE && tip && !h->have_tip_pass)
+      return fail(TTB_EINVAL, "ttb_fetch_node: tip profiles exist only after TTB_RECONSTRUCT_TIPS");
+  }
+  if (int rc = h->d_stage.alloc((size_t)h->Lp * h->q)) return rc;
+  const TtbDev d = h->dev();
+  TTB_DISPATCH_Q(h->q, { fetch_node_kernel<Q><<<h->tiles(), TTB_BLOCK, 0, h->stream>>>(d, node, which, h->d_stage.p); });
+  h->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->d_stage.p, (size_t)h->Lp * h->q * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* out) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, true)) return rc;
+  if (n < 0 || (n && (!nodes || !out))) return fail(TTB_EINVAL, "ttb_fetch_seq_idx: bad arguments");
+  for (int k = 0; k < n; ++k) {
+    const int node = nodes[k];
+    if (node < 0 || node >= h->n_nodes) return fail(TTB_EINVAL, "ttb_fetch_seq_idx: bad node id");
+    const uint8_t* src;
+    if (h->tip_row[node] >= 0) {
+      if (!h->have_tip_pass) return fail(TTB_EINVAL, "ttb_fetch_seq_idx: tip states exist only after TTB_RECONSTRUCT_TIPS");
+      src = h->d_idxtip.p + (size_t)h->tip_row[node] * h->ld;
+    } else {
+      src = h->d_idx.p + (size_t)h->int_slot[node] * h->ld;
+    }
+    CK(cudaMemcpyAsync(out + (size_t)k * h->Lp, src, h->Lp, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int branch_eval(ttb_handle h, int32_t n_eval, const int32_t* nodes, const int32_t* kind, const double* t,
+                       int mode, double* out) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, true)) return rc;
+  if (n_eval < 0 || (n_eval && (!nodes || !out || (mode == 0 && !t)))) return fail(TTB_EINVAL, "branch evaluation: bad arguments");
+  if (n_eval == 0) return 0;
+  const bool root_bif = (h->child_ptr[1] - h->child_ptr[0]) == 2;
+  for (int e = 0; e < n_eval; ++e) {
+    if (nodes[e] <= 0 || nodes[e] >= h->n_nodes) return fail(TTB_EINVAL, "branch evaluation: node id out of range (the root has no branch)");
+    if (kind && kind[e] == TTB_BRANCH_ROOT && (!root_bif || h->parent[nodes[e]] != 0))
+      return fail(TTB_EINVAL, "branch evaluation: TTB_BRANCH_ROOT needs a child of a bifurcating root");
+  }
+  cudaStream_t s = h->stream;
+  int rc;
+  if ((rc = upload(h->d_enodes, nodes, (size_t)n_eval, s))) return rc;
+  if (kind) {
+    if ((rc = upload(h->d_ekinds, kind, (size_t)n_eval, s))) return rc;
+  }
+  if (mode == 0) {
+    if ((rc = upload(h->d_ets, t, (size_t)n_eval, s))) return rc;
+  }
+  // enough blocks per branch to fill the GPU without starving long alignments
+  int nb = (int)std::min<long long>(h->tiles(), std::max<long long>(1, (148LL * 16 + n_eval - 1) / n_eval));
+  nb = std::min(nb, 64);
+  if ((rc = h->d_partial.alloc((size_t)n_eval * nb))) return rc;
+  if ((rc = h->d_eout.alloc((size_t)n_eval))) return rc;
+  const TtbDev d = h->dev();
+  dim3 grid(n_eval, nb);
+  TTB_DISPATCH_Q(h->q, {
+    branch_eval_kernel<Q><<<grid, TTB_BLOCK, 0, s>>>(d, h->d_enodes.p, kind ? h->d_ekinds.p : nullptr, h->d_ets.p, mode, h->d_partial.p);
+  });
+  branch_reduce_kernel<<<(n_eval + 127) / 128, 128, 0, s>>>(h->d_partial.p, n_eval, nb, h->d_eout.p);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->d_eout.p, (size_t)n_eval * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int ttb_branch_objective(ttb_handle h, int32_t n_eval, const int32_t* nodes, const int32_t* kind, const double* t, double* f) {
+  return branch_eval(h, n_eval, nodes, kind, t, 0, f);
+}
+
+int ttb_branch_hamming(ttb_handle h, int32_t n_eval, const int32_t* nodes, const int32_t* kind, double* num, double* den) {
+  if (int rc = branch_eval(h, n_eval, nodes, kind, nullptr, 1, num)) return rc;
+  if (den) {
+    double s = 0.0;
+    for (double m : h->h_mult) s += m;
+    *den = s;
+  }
+  return 0;
+}
+
+int ttb_mutation_counts(ttb_handle h, double* n_ij, double* T_i) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, true)) return rc;
+  if (!n_ij || !T_i) return fail(TTB_EINVAL, "ttb_mutation_counts: null output");
+  const int q = h->q, width = q * q + q;
+  const int tiles = h->tiles();
+  int chunks = std::max(1, std::min(h->n_nodes - 1, (148 * 8 + tiles - 1) / tiles));
+  const int chunk = (h->n_nodes - 1 + chunks - 1) / chunks;
+  chunks = (h->n_nodes - 1 + chunk - 1) / chunk;
+  int rc;
+  if ((rc = h->d_partial.alloc((size_t)chunks * tiles * width))) return rc;
+  if ((rc = h->d_eout.alloc((size_t)width))) return rc;
+  const TtbDev d = h->dev();
+  dim3 grid(tiles, chunks);
+  TTB_DISPATCH_Q(h->q, { counts_kernel<Q><<<grid, TTB_BLOCK, 0, h->stream>>>(d, chunk, h->d_partial.p); });
+  counts_reduce_kernel<<<(width + 127) / 128, 128, 0, h->stream>>>(h->d_partial.p, chunks * tiles, width, h->d_eout.p);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  std::vector<double> tmp(width);
+  CK(cudaMemcpyAsync(tmp.data(), h->d_eout.p, width * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(n_ij, tmp.data(), sizeof(double) * q * q);
+  memcpy(T_i, tmp.data() + q * q, sizeof(double) * q);
+  return 0;
+}
+
+int ttb_device_bytes(ttb_handle h, int64_t* bytes) {
+  if (!h || !bytes) return fail(TTB_EINVAL, "null argument");
+  size_t b = h->d_codes.bytes() + h->d_code_prof.bytes() + h->d_mult.bytes() + h->d_code_mask.bytes() + h->d_t.bytes() +
+             h->d_P.bytes() + h->d_S.bytes() + h->d_F.bytes() + h->d_M.bytes() + h->d_Mtip.bytes() + h->d_LH.bytes() +
+             h->d_idx.bytes() + h->d_idxtip.bytes() + h->d_stage.bytes() + h->d_partial.bytes() + h->d_parent.bytes() * 5;
+  *bytes = (int64_t)b;
+  return 0;
+}
+
+int ttb_launch_count(ttb_handle h, int64_t* count) {
+  if (!h || !count) return fail(TTB_EINVAL, "null argument");
+  *count = h->launches;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+"""Python handle on one device engine (one GPU, one shard of the pattern axis)."""
+import ctypes
+import numpy as np
+from . import _lib
+
+SUBTREE, OUTGROUP, PROFILE = 0, 1, 2
+RECONSTRUCT_TIPS, LH_ONLY = 1, 2
+BRANCH, BRANCH_ROOT = 0, 1
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+def _up(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine(object):
+    """Owns a ttb_handle.  All array arguments are numpy (host) arrays."""
+
+    def __init__(self, n_states, device=0):
+        self.lib = _lib.load()
+        self.n_states = int(n_states)
+        self.device = int(device)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.ttb_create(ctypes.byref(h), self.device, self.n_states))
+        self.h = h
+        self.n_nodes = 0
+        self.n_patterns = 0
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.ttb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inputs ---------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        _lib.check(self.lib.ttb_set_stream(self.h, ctypes.c_void_p(int(cuda_stream) if cuda_stream else None)))
+
+    def set_tree(self, parent, child_ptr, child_idx, tip_row):
+        parent, child_ptr, child_idx, tip_row = _i32(parent), _i32(child_ptr), _i32(child_idx), _i32(tip_row)
+        _lib.check(self.lib.ttb_set_tree(self.h, parent.shape[0], _ip(parent), _ip(child_ptr), _ip(child_idx), _ip(tip_row)))
+        self.n_nodes = int(parent.shape[0])
+        self.tip_row = tip_row
+
+    def set_patterns(self, tip_codes, code_profiles, multiplicity):
+        tip_codes = np.ascontiguousarray(tip_codes, dtype=np.uint8)
+        code_profiles = _f64(code_profiles)
+        multiplicity = _f64(multiplicity)
+        if code_profiles.shape[1] != self.n_states:
+            raise ValueError('code_profiles must have n_states columns')
+        if tip_codes.shape[1] != multiplicity.shape[0]:
+            raise ValueError('tip_codes and multiplicity disagree on the number of patterns')
+        if tip_codes.size and int(tip_codes.max()) >= code_profiles.shape[0]:
+            raise ValueError('tip code out of range of code_profiles')
+        _lib.check(self.lib.ttb_set_patterns(self.h, tip_codes.shape[1], _up(tip_codes), code_profiles.shape[0],
+                                             _dp(code_profiles), _dp(multiplicity)))
+        self.n_patterns = int(tip_codes.shape[1])
+
+    def set_gtr(self, g):
+        """g: dict from flatten.gtr_arrays()."""
+        gap = -1 if g.get('gap_index') is None else int(g['gap_index'])
+        if g.get('site_specific', False):
+            ev, v, vi, Pi, mu = _f64(g['eigenvals']), _f64(g['v']), _f64(g['v_inv']), _f64(g['Pi']), _f64(g['mu'])
+            tg = _f64(g['t_grid'])
+            _lib.check(self.lib.ttb_set_gtr_site_specific(self.h, _dp(ev), _dp(v), _dp(vi), _dp(Pi), _dp(mu), _dp(tg),
+                                                          tg.shape[0], float(g['rate_scale']),
+                                                          1 if g.get('approximate', True) else 0, gap))
+        else:
+            ev, v, vi, Pi = _f64(g['eigenvals']), _f64(g['v']), _f64(g['v_inv']), _f64(g['Pi'])
+            if ev.shape[0] != self.n_states:
+                raise ValueError('GTR has %d states, engine was created for %d' % (ev.shape[0], self.n_states))
+            _lib.check(self.lib.ttb_set_gtr(self.h, _dp(ev), _dp(v), _dp(vi), _dp(Pi), float(g['mu']), gap))
+
+    def set_branch_lengths(self, t):
+        t = _f64(t)
+        if t.shape[0] != self.n_nodes:
+            raise ValueError('t must have one entry per node')
+        _lib.check(self.lib.ttb_set_branch_lengths(self.h, _dp(t)))
+
+    # -- the pass -------------------------------------------------------------
+    def marginal(self, reconstruct_tips=False, lh_only=False):
+        flags = (RECONSTRUCT_TIPS if reconstruct_tips else 0) | (LH_ONLY if lh_only else 0)
+        _lib.check(self.lib.ttb_marginal(self.h, flags))
+
+    def results(self):
+        tot = ctypes.c_double()
+        nd = ctypes.c_int64()
+        _lib.check(self.lib.ttb_results(self.h, ctypes.byref(tot), ctypes.byref(nd)))
+        return tot.value, nd.value
+
+    def results_device_ptr(self):
+        p = ctypes.c_void_p()
+        _lib.check(self.lib.ttb_results_device_ptr(self.h, ctypes.byref(p)))
+        return p.value
+
+    def sync(self):
+        _lib.check(self.lib.ttb_sync(self.h))
+
+    # -- outputs --------------------------------------------------------------
+    def site_lh(self):
+        out = np.empty(self.n_patterns, dtype=np.float64)
+        _lib.check(self.lib.ttb_fetch_site_lh(self.h, _dp(out)))
+        return out
+
+    def node_array(self, node, which):
+        out = np.empty((self.n_patterns, self.n_states), dtype=np.float64)
+        _lib.check(self.lib.ttb_fetch_node(self.h, int(node), int(which), _dp(out)))
+        return out
+
+    def seq_idx(self, nodes):
+        nodes = _i32(np.atleast_1d(nodes))
+        out = np.empty((nodes.shape[0], self.n_patterns), dtype=np.uint8)
+        _lib.check(self.lib.ttb_fetch_seq_idx(self.h, nodes.shape[0], _ip(nodes), _up(out)))
+        return out
+
+    def branch_objective(self, nodes, t, kinds=None):
+        nodes, t = _i32(nodes), _f64(t)
+        out = np.empty(nodes.shape[0], dtype=np.float64)
+        kp = None
+        if kinds is not None:
+            kinds = _i32(kinds)
+            kp = _ip(kinds)
+        _lib.check(self.lib.ttb_branch_objective(self.h, nodes.shape[0], _ip(nodes), kp, _dp(t), _dp(out)))
+        return out
+
+    def branch_hamming(self, nodes, kinds=None):
+        nodes = _i32(nodes)
+        num = np.empty(nodes.shape[0], dtype=np.float64)
+        den = ctypes.c_double()
+        kp = None
+        if kinds is not None:
+            kinds = _i32(kinds)
+            kp = _ip(kinds)
+        _lib.check(self.lib.ttb_branch_hamming(self.h, nodes.shape[0], _ip(nodes), kp, _dp(num), ctypes.byref(den)))
+        return num, den.value
+
+    def mutation_counts(self):
+        q = self.n_states
+        n_ij = np.empty((q, q), dtype=np.float64)
+        T_i = np.empty(q, dtype=np.float64)
+        _lib.check(self.lib.ttb_mutation_counts(self.h, _dp(n_ij), _dp(T_i)))
+        return n_ij, T_i
+
+    def device_bytes(self):
+        b = ctypes.c_int64()
+        _lib.check(self.lib.ttb_device_bytes(self.h, ctypes.byref(b)))
+        return b.value
+
+    def launch_count(self):
+        b = ctypes.c_int64()
+        _lib.check(self.lib.ttb_launch_count(self.h, ctypes.byref(b)))
+        return b.value

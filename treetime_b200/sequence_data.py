@@ -1,0 +1,221 @@
+"""Alignment container and pattern compression for the host side.
+
+Input boundary of the hot path: turns an alignment
+into the compressed pattern matrix the engine consumes.  Same semantics as the
+reference's SequenceData.make_compressed_alignment (sequence_data.py:325-464):
+  * columns are visited in order; a column that is constant -- possibly after
+    replacing the ambiguous character when exactly one other letter occurs
+    (:386-392) -- shares one pattern with all identical constant columns;
+  * every variable column gets a private pattern (:394-402);
+  * patterns are numbered by first occurrence; multiplicity = number of columns.
+Unlike the reference (a Python loop over columns building strings) the columns
+are classified with vectorised byte arithmetic on an (n_seq, L) uint8 matrix.
+"""
+import numpy as np
+
+
+def _to_bytes(seq, convert_upper=True):
+    """str / char array / bytes -> uint8 ASCII codes."""
+    if isinstance(seq, str):
+        b = np.frombuffer(seq.encode('ascii'), dtype=np.uint8)
+    elif isinstance(seq, (bytes, bytearray)):
+        b = np.frombuffer(bytes(seq), dtype=np.uint8)
+    else:
+        seq = np.asarray(seq)
+        if seq.dtype.kind == 'U':
+            b = seq.astype('U1').view(np.uint32).astype(np.uint8)
+        elif seq.dtype.kind == 'S':
+            b = seq.astype('S1').view(np.uint8)
+        elif seq.dtype == np.uint8:
+            b = seq
+        else:
+            raise TypeError('unsupported sequence type %r' % (seq.dtype,))
+    if convert_upper:
+        b = np.where((b >= 97) & (b <= 122), b - 32, b).astype(np.uint8)
+    return b
+
+
+def read_fasta(path):
+    names, seqs, cur = [], [], []
+    with open(path) as fh:
+        for line in fh:
+            line = line.strip()
+            if not line:
+                continue
+            if line[0] == '>':
+                if names:
+                    seqs.append(''.join(cur))
+                names.append(line[1:].split()[0])
+                cur = []
+            else:
+                cur.append(line)
+    if names:
+        seqs.append(''.join(cur))
+    return list(zip(names, seqs))
+
+
+class SequenceData(object):
+    """Holds the alignment as ASCII bytes and its compressed patterns.
+
+    aln : fasta file name, dict name -> sequence, or list of (name, sequence);
+          sequences may be str, numpy char arrays or uint8 ASCII arrays.
+    """
+
+    def __init__(self, aln, compress=True, convert_upper=True, fill_overhangs=True, ambiguous='N',
+                 sequence_length=None, logger=None):
+        self.logger = logger or (lambda *a, **k: None)
+        self.compress = compress
+        self.ambiguous = ambiguous
+        self.is_sparse = False
+        self.additional_constant_sites = 0
+        if isinstance(aln, str):
+            aln = read_fasta(aln)
+        if isinstance(aln, dict):
+            items = list(aln.items())
+        else:
+            items = [(getattr(r, 'id', None) or r[0], str(getattr(r, 'seq', None) or r[1])) if not isinstance(r, tuple) else r
+                     for r in aln]
+        if not items:
+            raise ValueError('SequenceData: empty alignment')
+        self.sequence_names = [k for k, _ in items]
+        rows = [_to_bytes(s, convert_upper) for _, s in items]
+        L = rows[0].shape[0]
+        if any(r.shape[0] != L for r in rows):
+            raise ValueError('SequenceData: sequences differ in length')
+        self.matrix = np.vstack(rows) if len(rows) > 1 else rows[0][None, :].copy()
+        if fill_overhangs and ambiguous is not None:
+            self._fill_overhangs(ord(ambiguous))
+        self.full_length = int(sequence_length) if sequence_length else L
+        if self.full_length < L:
+            raise AttributeError('SequenceData: specified sequence length is smaller than alignment length!')
+        self.additional_constant_sites = self.full_length - L
+        self._row = {k: i for i, k in enumerate(self.sequence_names)}
+        self.make_compressed_alignment()
+
+    def _fill_overhangs(self, amb):
+        """Leading/trailing gaps -> ambiguous (seq2array fill_overhangs, seq_utils.py:196-202)."""
+        A = self.matrix
+        nongap = A != ord('-')
+        any_ng = nongap.any(axis=1)
+        first = np.where(any_ng, nongap.argmax(axis=1), A.shape[1])
+        last = np.where(any_ng, A.shape[1] - 1 - nongap[:, ::-1].argmax(axis=1), -1)
+        pos = np.arange(A.shape[1])[None, :]
+        A[(pos < first[:, None]) | (pos > last[:, None])] = amb
+
+    @property
+    def aln(self):
+        return _AlnView(self)
+
+    @property
+    def compressed_length(self):
+        return self._compressed_length
+
+    def multiplicity(self, mask=None):
+        return self._multiplicity if mask is None else self._multiplicity * mask
+
+    def make_compressed_alignment(self):
+        A = self.matrix
+        n_seq, L = A.shape
+        if not self.compress:
+            self._multiplicity = np.ones(self.full_length, dtype=float)
+            self.full_to_compressed_sequence_map = np.arange(self.full_length)
+            self._compressed_length = self.full_length
+            self.compressed_matrix = A
+            self.pattern_first_position = np.arange(L)
+            self._finish()
+            return
+        amb = ord(self.ambiguous) if self.ambiguous is not None else 256
+        is_amb = A == amb
+        lo = np.where(is_amb, 255, A).min(axis=0)      # extrema over non-ambiguous entries
+        hi = np.where(is_amb, 0, A).max(axis=0)
+        all_amb = is_amb.all(axis=0)
+        # constant (possibly after replacing the ambiguous character by the single other letter)
+        const = (lo == hi) | all_amb
+        letter = np.where(all_amb, amb, lo).astype(np.uint8)
+        # pattern id by first occurrence: variable columns are private, constant ones keyed by letter
+        pid = np.empty(L, dtype=np.int64)
+        first_seen = {}
+        order = []
+        key = np.where(const, letter.astype(np.int64), -1 - np.arange(L))
+        uniq, first_idx, inverse = np.unique(key, return_index=True, return_inverse=True)
+        rank = np.argsort(np.argsort(first_idx))       # patterns ordered by first occurrence
+        pid = rank[inverse]
+        n_pat = uniq.shape[0]
+        first_pos = np.empty(n_pat, dtype=np.int64)
+        first_pos[rank] = first_idx
+        C = A[:, first_pos].copy()
+        cc = const[first_pos]
+        if cc.any():                                    # constant patterns: ambiguous replaced (:391)
+            C[:, cc] = letter[first_pos][cc][None, :]
+        mult = np.bincount(pid, minlength=n_pat).astype(float)
+        f2c = pid.copy()
+        if self.additional_constant_sites:
+            # extra constant columns distributed over the unambiguous states by composition (:417-441)
+            from .seq_utils import alphabets
+            likely = 'nuc' if np.isin(A, np.frombuffer(b'ACGT-N', dtype=np.uint8)).mean() > 0.9 else 'aa'
+            chars = [c for c in alphabets[likely + '_nogap'] if c not in (self.ambiguous, '-')]
+            counts = [(c, int((A == ord(c)).sum())) for c in chars]
+            total = sum(n for _, n in counts)
+            left = self.additional_constant_sites
+            extra_f2c = []
+            for k, (c, n) in enumerate(counts):
+                add = left if k == len(counts) - 1 else int(np.round(self.additional_constant_sites * n / total))
+                if add:
+                    hit = np.nonzero(cc & (C[0] == ord(c)) & (C == ord(c)).all(axis=0))[0]
+                    if hit.size:
+                        p = int(hit[0])
+                    else:
+                        p = C.shape[1]
+                        C = np.hstack([C, np.full((n_seq, 1), ord(c), dtype=np.uint8)])
+                        cc = np.append(cc, True)
+                        mult = np.append(mult, 0.0)
+                        first_pos = np.append(first_pos, L + len(extra_f2c))
+                    mult[p] += add
+                    extra_f2c.extend([p] * add)
+                    left -= add
+            f2c = np.concatenate([f2c, np.array(extra_f2c, dtype=np.int64)])
+        self._multiplicity = mult
+        self.full_to_compressed_sequence_map = f2c
+        self._compressed_length = int(mult.shape[0])
+        self.compressed_matrix = np.ascontiguousarray(C)
+        self.pattern_first_position = first_pos
+        self._finish()
+
+    def _finish(self):
+        self.compressed_alignment = _CompressedView(self)
+
+    def compressed_to_full_sequence(self, sequence, include_additional_constant_sites=False, as_string=False):
+        """Expand a compressed sequence (sequence_data.py:513-543)."""
+        L = self.full_length if include_additional_constant_sites else self.full_length - self.additional_constant_sites
+        tmp = np.asarray(sequence)[self.full_to_compressed_sequence_map[:L]]
+        return ''.join(tmp.astype('U')) if as_string else tmp
+
+
+class _CompressedView(object):
+    """dict-like view name -> compressed char array (like data.compressed_alignment)."""
+
+    def __init__(self, sd):
+        self._sd = sd
+
+    def __contains__(self, name):
+        return name in self._sd._row
+
+    def __getitem__(self, name):
+        return self._sd.compressed_matrix[self._sd._row[name]].view('S1').astype('U1')
+
+    def codes(self, name):
+        return self._sd.compressed_matrix[self._sd._row[name]]
+
+    def keys(self):
+        return self._sd.sequence_names
+
+    def __len__(self):
+        return len(self._sd.sequence_names)
+
+
+class _AlnView(_CompressedView):
+    def __getitem__(self, name):
+        return self._sd.matrix[self._sd._row[name]].view('S1').astype('U1')
+
+    def values(self):
+        return [self[k] for k in self.keys()]
