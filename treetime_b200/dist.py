@@ -1,0 +1,76 @@
+"""Pattern sharding across GPUs and the (tiny) collectives it needs.
+
+Alignment columns are conditionally independent given tree + model, so each rank
+owns a contiguous block of the compressed-pattern axis, the tree / branch lengths
+/ GTR are replicated, and the only data that ever crosses NVLink is
+  * the total log-likelihood and N_diff            (2 doubles per pass),
+  * per Brent iteration one vector of n_branches partial objective values,
+  * the q^2 + q substitution statistics when a GTR is inferred.
+One process per GPU; the collectives go through torch.distributed (NCCL on GPU,
+gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def shard_bounds(n_patterns, rank, world_size):
+    """Contiguous, balanced-by-count block [lo, hi) of the pattern axis for `rank`."""
+    base, rem = divmod(int(n_patterns), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class SingleComm(object):
+    """world_size = 1: every collective is the identity."""
+    rank, world_size = 0, 1
+
+    def allreduce_sum(self, x):
+        return np.asarray(x, dtype=np.float64)
+
+    def allgather(self, x, axis=0):
+        return np.asarray(x)
+
+    def barrier(self):
+        pass
+
+
+class TorchComm(object):
+    """Collectives over an initialised torch.distributed process group."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError('torch.distributed is not initialised')
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+        backend = dist.get_backend(group)
+        if device is None:
+            device = ('cuda:%d' % torch.cuda.current_device()) if backend == 'nccl' else 'cpu'
+        self.device = torch.device(device)
+
+    def allreduce_sum(self, x):
+        t = self.torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def allgather(self, x, axis=0):
+        """Concatenate per-rank arrays (possibly of different length along `axis`)."""
+        x = np.ascontiguousarray(x)
+        parts = [None] * self.world_size
+        self.dist.all_gather_object(parts, x, group=self.group)
+        return np.concatenate(parts, axis=axis)
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+def default_comm():
+    """TorchComm when torch.distributed is initialised with world_size > 1, else SingleComm."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return TorchComm()
+    except ImportError:
+        pass
+    return SingleComm()

@@ -235,3 +235,44 @@ class GTRSiteSpecific(GTR):
 
     def expQt(self, t):
         raise NotImplementedError('site-specific exp(Qt) is evaluated on the device')
+
+
+def infer_gtr_from_counts(nij, Ti, root_state, fixed_pi=None, pc=1.0, gap_limit=0.01, alphabet='nuc',
+                          prof_map=None, logger=None):
+    """Fit (mu, Pi, W) to the substitution statistics n_ij (changes j -> i), T_i
+    (time spent in state i) and the root state counts: the fixed-point iteration of
+    the reference's GTR.infer (gtr.py:491-599), consumer of the device-side counts
+    (csrc counts_kernel).  Host-only: q x q arithmetic."""
+    gtr = GTR(alphabet=alphabet, prof_map=prof_map, logger=logger)
+    nij = np.array(nij, dtype=float)
+    Ti = np.asarray(Ti, dtype=float)
+    root_state = np.asarray(root_state, dtype=float)
+    dp, Nit = 1e-5, 40
+    pc_mat = pc * np.ones_like(nij)
+    np.fill_diagonal(pc_mat, 0.0)
+    np.fill_diagonal(nij, 0.0)
+    pi_old = np.zeros_like(Ti)
+    pi = np.ones_like(Ti) if fixed_pi is None else np.array(fixed_pi, dtype=float)
+    pi /= pi.sum()
+    W_ij = np.ones_like(nij)
+    mu = (nij.sum() + pc) / (Ti.sum() + pc)
+    count = 0
+    while np.linalg.norm(pi_old - pi) > dp and count < Nit:
+        count += 1
+        pi_old = np.copy(pi)
+        W_ij = (nij + nij.T + 2 * pc_mat) / mu / (np.outer(pi, Ti) + np.outer(Ti, pi) + ttconf.TINY_NUMBER + 2 * pc_mat)
+        np.fill_diagonal(W_ij, 0)
+        W_ij = W_ij / avg_transition(W_ij, pi, gap_index=gtr.gap_index)
+        if fixed_pi is None:
+            pi = (np.sum(nij + pc_mat, axis=1) + root_state) / (
+                ttconf.TINY_NUMBER + mu * np.dot(W_ij, Ti) + root_state.sum() + np.sum(pc_mat, axis=1))
+            pi /= pi.sum()
+            mu = (nij.sum() + pc) / (np.sum(pi * (W_ij.dot(Ti))) + pc)
+        else:
+            mu = (nij.sum() + pc) / (np.sum(pi * (W_ij.dot(pi))) * Ti.sum() + pc)
+    if gtr.gap_index is not None:
+        # the reference resets the gap frequency to gap_limit unconditionally (gtr.py:584-596)
+        pi[gtr.gap_index] = gap_limit
+        pi /= pi.sum()
+    gtr.assign_rates(mu=mu, W=W_ij, pi=pi)
+    return gtr
