@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- marginal ancestral reconstruction throughput (branch x pattern updates/s).
+
+    python bench.py [--gpus N --steps K --warmup W] [--workload cfg3|cfg2|cfg1|cfg4|tiny]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # CPU arm: the oracle port of the reference's numpy path
+
+One step = one full `infer_ancestral_sequences(marginal=True)` pass (batched expQt, level-ordered
+postorder, root, level-ordered preorder, reductions) over one synthetic alignment shard.
+N > 1: one process per GPU, the tree/model replicated, every rank owns its own block of
+alignment columns (weak scaling: the per-GPU shard is fixed), the only collective is the
+all-reduce of {total log-LH, N_diff}.
+
+Prints ONE JSON line (rank 0).  `value` = updates/s with inputs resident in HBM, timed with CUDA
+events around the K steps (max over ranks); `e2e` = the same metric through the C-ABI with HOST
+buffers: per step the tip codes / branch lengths / model are copied host->device from pinned
+memory and the per-pattern LH, the totals and every reconstructed sequence are copied back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_tips, n_sites, alphabet, mean branch length, description)
+    'cfg3': (20000, 29903, 'nuc', 1.0 / 29903, '20k tips x 29,903-site SARS-CoV-2-shaped nucleotide alignment (BASELINE.json configs[2])'),
+    'cfg2': (2000, 10000, 'nuc', 5e-4, '2k tips x 10 kb nucleotide (BASELINE.json configs[1])'),
+    'cfg1': (200, 1400, 'nuc', 2e-3, '200-tip x 1.4 kb nucleotide (BASELINE.json configs[0])'),
+    'cfg4': (5000, 1000, 'aa_nogap', 1e-2, '5k tips x 1,000-site amino-acid alignment, 20-state model (BASELINE.json configs[3])'),
+    'tiny': (64, 500, 'nuc', 1e-2, 'smoke-sized'),
+}
+SURVEY_BYTES_PER_UPDATE = {5: 165.5, 4: 133.5, 20: 645.5, 22: 709.5}    # 4 q s + 0.5 s + 1.5
+
+
+def make_workload(name, seed):
+    from treetime_b200 import synth
+    from treetime_b200.gtr import GTR
+    n_tips, L, alphabet, mean_bl, _ = WORKLOADS[name]
+    if alphabet == 'nuc':
+        gtr = GTR.custom(pi=np.array([0.3, 0.2, 0.2, 0.29, 0.01]), W=np.ones((5, 5)), alphabet='nuc')
+    else:
+        gtr = GTR.random(alphabet=alphabet, rng=np.random.default_rng(1234))
+    tree = synth.random_tree(n_tips, seed=1, mean_bl=mean_bl)           # same tree on every rank
+    topo, flat, g = synth.make_flat_problem(tree, gtr, L, seed)         # rank-specific columns
+    return topo, flat, g
+
+
+def algorithmic_bytes(flat, q):
+    """Bytes the level kernels must move per pass under THIS design:
+    postorder: read (S,F) of internal children + 1-byte codes of tip children, write (S,F) per
+    internal node; preorder: read parent profile once per parent with an internal child, per
+    internal child read S, write profile, read+write the 1-byte state."""
+    Lp = flat['multiplicity'].shape[0]
+    n_nodes = flat['parent'].shape[0]
+    tip = flat['tip_row'] >= 0
+    n_tips = int(tip.sum())
+    n_int = n_nodes - n_tips
+    has_int_child = np.zeros(n_nodes, dtype=bool)
+    has_int_child[flat['parent'][1:][~tip[1:]]] = True
+    post = Lp * (n_int * (q + 1) * 8 + (n_int - 1) * (q + 1) * 8 + n_tips * 1)
+    pre = Lp * (int(has_int_child.sum()) * q * 8 + (n_int - 1) * (2 * q * 8 + 2))
+    return post, pre
+
+
+class ClockSampler(object):
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(workload):
+    """dram bytes per pass of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+def cpu_sample(flat, g, n_patterns):
+    """Bounded sample of the same workload for the CPU arm: the first n_patterns columns."""
+    n = min(n_patterns, flat['multiplicity'].shape[0])
+    s = dict(flat)
+    s['tip_codes'] = np.ascontiguousarray(flat['tip_codes'][:, :n])
+    s['multiplicity'] = flat['multiplicity'][:n].copy()
+    return s, n
+
+
+def run_cpu(flat, g, n_patterns, repeats):
+    """Time the oracle port (oracle/flat_numpy.py: the reference's per-node numpy calls)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import flat_numpy as O
+    s, n = cpu_sample(flat, g, n_patterns)
+    n_br = flat['parent'].shape[0] - 1
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        res = O.marginal(s, g)
+        times.append(time.perf_counter() - t0)
+    return n_br * n, times, res.total_LH
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
+    ap.add_argument('--cpu-patterns', type=int, default=0, help='patterns in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 0)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    n_tips, L, alphabet, mean_bl, desc = WORKLOADS[args.workload]
+
+    # ------------------------------------------------------------------ CPU (reference) arm
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        topo, flat, g = make_workload(args.workload, seed=1)
+        q = g['Pi'].shape[0]
+        n_br = flat['parent'].shape[0] - 1
+        total_steps = args.steps + args.warmup
+        n_pat = args.cpu_patterns or int(max(64, min(flat['multiplicity'].shape[0], 120.0 * 2.0e6 / (n_br * max(1, total_steps)))))
+        updates, times, _ = run_cpu(flat, g, n_pat, total_steps)
+        timed = times[args.warmup:]
+        ms = 1e3 * float(np.mean(timed))
+        val = updates / (ms / 1e3)
+        sample = 'first %d of %d compressed patterns of the same tree/alignment per step (cost is linear in patterns)' % (
+            min(n_pat, flat['multiplicity'].shape[0]), flat['multiplicity'].shape[0])
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'marginal ancestral reconstruction branch x pattern updates/s', 'value': val,
+            'unit': 'updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': '%s: %s' % (args.workload, desc), 'n_tips': n_tips, 'n_sites': L, 'n_states': q},
+            'cpu_baseline': {'value': val, 'unit': 'updates/s', 'cores': 1, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'note': 'oracle/flat_numpy.py: flat-array port of the reference numpy path (bit-identical to the '
+                    'reference on the build container); single-threaded like the reference',
+        }))
+        return 0
+
+    # ------------------------------------------------------------------ GPU arm
+    import torch
+    import torch.distributed as dist
+    from treetime_b200.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    topo, flat, g = make_workload(args.workload, seed=1 + rank)
+    q = g['Pi'].shape[0]
+    n_nodes = flat['parent'].shape[0]
+    n_br = n_nodes - 1
+    Lp = flat['multiplicity'].shape[0]
+    updates_local = n_br * Lp
+
+    stream = torch.cuda.current_stream()
+    eng = Engine(q, device=local_rank)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_tree(flat['parent'], flat['child_ptr'], flat['child_idx'], flat['tip_row'])
+    # pinned host staging for the e2e leg
+    codes_pin = torch.empty(flat['tip_codes'].shape, dtype=torch.uint8, pin_memory=True)
+    codes_pin.numpy()[...] = flat['tip_codes']
+    eng.set_patterns(codes_pin.numpy(), flat['code_profiles'], flat['multiplicity'])
+    eng.set_gtr(g)
+    eng.set_branch_lengths(flat['t'])
+
+    class _Dev(object):
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {'shape': (2,), 'typestr': '<f8', 'data': (ptr, False), 'version': 2}
+
+    def step():
+        eng.marginal()
+        if world > 1:
+            dist.all_reduce(res_t)
+
+    eng.marginal()
+    eng.sync()
+    res_t = torch.as_tensor(_Dev(eng.results_device_ptr()), device='cuda') if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    total_lh_local, _ = eng.results() if world == 1 else (float(res_t[0].item()), 0)
+
+    # per-phase device times (un-graphed pass, CUDA events between phases)
+    phases = eng.profile_marginal()
+    for _ in range(2):
+        ph = eng.profile_marginal()
+        phases = {k: (min(phases[k][0], ph[k][0]), ph[k][1]) for k in ph}
+
+    # ---- e2e: host buffers in, host results out, every step
+    e2e = None
+    if not args.no_e2e:
+        n_int = int((flat['tip_row'] < 0).sum())
+        seq_pin = torch.empty((n_int, Lp), dtype=torch.uint8, pin_memory=True)
+        seq_np = seq_pin.numpy()
+
+        def e2e_step():
+            eng.set_patterns(codes_pin.numpy(), flat['code_profiles'], flat['multiplicity'])
+            eng.set_gtr(g)
+            eng.set_branch_lengths(flat['t'])
+            eng.marginal()
+            if world > 1:
+                dist.all_reduce(res_t)
+            tot, nd = eng.results()
+            lh = eng.site_lh()
+            eng.all_seq_idx(out=seq_np)
+            return tot, lh
+
+        e2e_step()
+        barrier()
+        k_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / k_e2e
+        h2d = int(flat['tip_codes'].nbytes + flat['code_profiles'].nbytes + flat['multiplicity'].nbytes + flat['t'].nbytes
+                  + 8 * (2 * q * q + 2 * q + 1))
+        d2h = int(n_int * Lp + 8 * Lp + 16)
+        e2e = (e2e_s, h2d, d2h)
+
+    # ---- reduce over ranks: max time, summed work
+    ms_step = ms_total / args.steps
+    if world > 1:
+        tmax = torch.tensor([ms_step, e2e[0] if e2e else 0.0], device='cuda', dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = torch.tensor([float(updates_local)], device='cuda', dtype=torch.float64)
+        dist.all_reduce(tsum)
+        ms_step = float(tmax[0].item())
+        e2e_time = float(tmax[1].item())
+        updates_total = float(tsum[0].item())
+    else:
+        e2e_time = e2e[0] if e2e else 0.0
+        updates_total = float(updates_local)
+
+    if rank == 0:
+        value = updates_total / (ms_step / 1e3)
+        peak, peak_src = measured_peak()
+        post_b, pre_b = algorithmic_bytes(flat, q)
+        dom = 'preorder' if phases['preorder'][0] >= phases['postorder'][0] else 'postorder'
+        dom_bytes = pre_b if dom == 'preorder' else post_b
+        dom_ms, dom_launches = phases[dom]
+        achieved = dom_bytes / (dom_ms / 1e3) / 1e9
+        pass_ms = sum(v[0] for v in phases.values())
+        out = {
+            'metric': 'marginal ancestral reconstruction branch x pattern updates/s', 'value': value, 'unit': 'updates/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': '%s: %s' % (args.workload, desc), 'n_tips': n_tips, 'n_sites_per_gpu': L, 'n_states': q,
+                       'patterns_per_gpu': int(Lp), 'branches': int(n_br), 'updates_per_step': updates_total,
+                       'sharding': 'pattern blocks, tree replicated (%d rank%s)' % (world, 's' if world > 1 else ''),
+                       'l2': 'working set (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed' % (eng.device_bytes() / 1e9),
+                       'device_bytes_per_gpu': eng.device_bytes()},
+            'clocks': clocks,
+            'gpu_launches': int(launches),
+            'log_lh_rank0': total_lh_local,
+            'roofline': {
+                'bound': 'hbm', 'kernel': '%s_level_kernel<%d> (%d level launches per pass)' % ('pre' if dom == 'preorder' else 'post', q, dom_launches),
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
+                'algorithmic_bytes_per_pass': int(dom_bytes), 'kernel_ms_per_pass': dom_ms,
+                'traffic': ncu_traffic(args.workload),
+                'phases_ms': {k: v[0] for k, v in phases.items()}, 'phase_launches': {k: v[1] for k, v in phases.items()},
+                'whole_pass': {'algorithmic_bytes': int(post_b + pre_b), 'bytes_per_update': (post_b + pre_b) / float(updates_local),
+                               'achieved_gbs': (post_b + pre_b) / (pass_ms / 1e3) / 1e9,
+                               'frac': (post_b + pre_b) / (pass_ms / 1e3) / 1e9 / peak,
+                               'survey_bytes_per_update': SURVEY_BYTES_PER_UPDATE.get(q),
+                               'survey_frac': (SURVEY_BYTES_PER_UPDATE.get(q, 0) * updates_local / (pass_ms / 1e3) / 1e9 / peak)
+                               if q in SURVEY_BYTES_PER_UPDATE else None},
+            },
+        }
+        if e2e:
+            out['e2e'] = {'value': updates_total / e2e_time, 'unit': 'updates/s', 'ms_per_step': 1e3 * e2e_time,
+                          'h2d_bytes_per_step': e2e[1], 'd2h_bytes_per_step': e2e[2],
+                          'what': 'ttb_set_patterns/gtr/branch_lengths from pinned host memory + ttb_marginal + '
+                                  'ttb_results + ttb_fetch_site_lh + ttb_fetch_all_seq_idx, per rank'}
+        if not args.no_cpu_baseline and world >= 1:
+            n_pat = args.cpu_patterns or int(max(64, min(Lp, 20.0 * 2.0e6 / n_br)))
+            upd, times, cpu_lh = run_cpu(flat, g, n_pat, 1)
+            out['cpu_baseline'] = {'value': upd / times[0], 'unit': 'updates/s', 'cores': 1, 'kind': 'port',
+                                   'sample': 'one pass over the first %d of %d patterns (same tree, same model); '
+                                             'host has %d cores, the reference path is single-threaded numpy'
+                                             % (min(n_pat, Lp), Lp, os.cpu_count() or 0)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -118,6 +118,14 @@ int ttb_fetch_node(ttb_handle h, int32_t node, int32_t which, double* out);
  * out[n][n_patterns].  Tips only after TTB_RECONSTRUCT_TIPS. */
 int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* out);
 
+/* All internal nodes at once: out[n_internal][n_patterns], rows in node (preorder) order. */
+int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out);
+
+/* Same work as ttb_marginal but launched kernel by kernel with CUDA events between the
+ * phases (no graph): ms[4] = {expQt batch, postorder levels, root + reductions, preorder levels},
+ * launches[4] = kernels per phase.  Measurement aid for bench.py's roofline. Synchronous. */
+int ttb_profile_marginal(ttb_handle h, int32_t flags, double* ms, int32_t* launches);
+
 /* Branch-length likelihood surface: f[e] = prob_t_profiles((pp,pc), multiplicity, t[e],
  * return_log=True) (gtr.py:922-963) for the branch above nodes[e] (kind[e], may be NULL = all
  * TTB_BRANCH), using the messages of the last ttb_marginal.  Partial sum over this shard. */

@@ -11,11 +11,15 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libttb.so')
-SOURCES = [os.path.join(HERE, 'csrc', 'ttb_api.cu')]
-HEADERS = [os.path.join(HERE, 'csrc', 'ttb_kernels.cuh'), os.path.join(os.path.dirname(HERE), 'include', 'ttb.h')]
+CSRC = os.path.join(HERE, 'csrc')
+BUILD_DIR = os.path.join(HERE, 'build')
+Q_VALUES = (2, 3, 4, 5, 6, 7, 8, 20, 21, 22)      # alphabet sizes with compiled kernels
+SOURCES = [os.path.join(CSRC, 'ttb_api.cu'), os.path.join(CSRC, 'ttb_q.cu')]
+HEADERS = [os.path.join(CSRC, 'ttb_kernels.cuh'), os.path.join(CSRC, 'ttb_qops.h'),
+           os.path.join(os.path.dirname(HERE), 'include', 'ttb.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC']
 
 
 class TTBError(RuntimeError):
@@ -33,16 +37,33 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in SOURCES + HEADERS if os.path.exists(s))
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu -> treetime_b200/libttb.so for sm_100a."""
+def build(force=False, verbose=False, extra_flags=()):
+    """Compile csrc/*.cu -> treetime_b200/libttb.so for sm_100a (nvcc cross-compiles without
+    a GPU).  One object per alphabet size (ttb_q.cu with -DTTB_Q=q), built in parallel."""
     if not force and not needs_build():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH] + SOURCES
-    if verbose:
-        print(' '.join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
-    return LIB_PATH
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    jobs = [([nvcc] + NVCC_FLAGS + list(extra_flags) + ['-c', os.path.join(CSRC, 'ttb_api.cu'), '-o',
+                                                        os.path.join(BUILD_DIR, 'ttb_api.o')])]
+    for q in Q_VALUES:
+        jobs.append([nvcc] + NVCC_FLAGS + list(extra_flags) + ['-DTTB_Q=%d' % q, '-c', os.path.join(CSRC, 'ttb_q.cu'),
+                                                               '-o', os.path.join(BUILD_DIR, 'ttb_q%d.o' % q)])
+
+    def run(cmd):
+        if verbose:
+            print(' '.join(cmd), file=sys.stderr)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), r.stderr))
+        return r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        logs = list(ex.map(run, jobs))
+    objs = [j[-1] for j in jobs]
+    run([nvcc, '-shared', '-o', LIB_PATH] + objs)
+    return logs
 
 
 _lib = None
@@ -73,6 +94,8 @@ SIGNATURES = {
     'ttb_fetch_site_lh': ([_H, _c_dbl_p], ctypes.c_int),
     'ttb_fetch_node': ([_H, ctypes.c_int32, ctypes.c_int32, _c_dbl_p], ctypes.c_int),
     'ttb_fetch_seq_idx': ([_H, ctypes.c_int32, _c_int_p, _c_u8_p], ctypes.c_int),
+    'ttb_fetch_all_seq_idx': ([_H, _c_u8_p], ctypes.c_int),
+    'ttb_profile_marginal': ([_H, ctypes.c_int32, _c_dbl_p, _c_int_p], ctypes.c_int),
     'ttb_branch_objective': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_branch_hamming': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_mutation_counts': ([_H, _c_dbl_p, _c_dbl_p], ctypes.c_int),

@@ -1,7 +1,7 @@
 // ttb_api.cu -- host side of libttb.so: the C-ABI of include/ttb.h, device memory,
 // level schedules and the CUDA-graph that covers one marginal reconstruction.
 #include "../../include/ttb.h"
-#include "ttb_kernels.cuh"
+#include "ttb_qops.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -29,23 +29,20 @@ int fail(int code, const std::string& msg) {
     }                                                                                         \
   } while (0)
 
-// Dispatch on the compile-time alphabet size.
-#define TTB_DISPATCH_Q(q, ...)                       \
-  switch (q) {                                       \
-    case 2: { constexpr int Q = 2; __VA_ARGS__; } break;   \
-    case 3: { constexpr int Q = 3; __VA_ARGS__; } break;   \
-    case 4: { constexpr int Q = 4; __VA_ARGS__; } break;   \
-    case 5: { constexpr int Q = 5; __VA_ARGS__; } break;   \
-    case 6: { constexpr int Q = 6; __VA_ARGS__; } break;   \
-    case 7: { constexpr int Q = 7; __VA_ARGS__; } break;   \
-    case 8: { constexpr int Q = 8; __VA_ARGS__; } break;   \
-    case 20: { constexpr int Q = 20; __VA_ARGS__; } break; \
-    case 21: { constexpr int Q = 21; __VA_ARGS__; } break; \
-    case 22: { constexpr int Q = 22; __VA_ARGS__; } break; \
-    default: break;                                  \
+#define TTB_FOR_EACH_Q(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(20) X(21) X(22)
+#define TTB_DECL(qv) extern const TtbQOps ttb_qops_##qv;
+}  // namespace
+TTB_FOR_EACH_Q(TTB_DECL)
+const TtbQOps* ttb_qops(int q) {
+  switch (q) {
+#define TTB_CASE(qv) case qv: return &ttb_qops_##qv;
+    TTB_FOR_EACH_Q(TTB_CASE)
+    default: return nullptr;
   }
+}
+namespace {
 
-bool q_supported(int q) { return (q >= 2 && q <= 8) || (q >= 20 && q <= 22); }
+bool q_supported(int q) { return ttb_qops(q) != nullptr; }
 
 template <typename T>
 struct DBuf {
@@ -74,9 +71,7 @@ struct DBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
-struct Level {
-  int begin, count;
-};
+typedef TtbLevel Level;
 
 }  // namespace
 
@@ -201,48 +196,28 @@ void build_levels(const std::vector<int>& key, const std::vector<char>& member, 
     if (count[k + 1] > count[k]) levels.push_back({count[k], count[k + 1] - count[k]});
 }
 
-template <int Q>
-size_t level_smem(int n_codes) {
-  return Smem<Q>::bytes(n_codes);
-}
-
 // Enqueue every kernel of one pass on `s`; returns the number of kernels.
-int enqueue_pass(ttb_handle h, int flags, int count_diff, cudaStream_t s, int* n_kernels) {
-  const TtbDev d = h->dev();
-  const int tiles = h->tiles();
-  const bool lh_only = flags & TTB_LH_ONLY;
-  const bool tips = flags & TTB_RECONSTRUCT_TIPS;
-  int nk = 0;
-  TTB_DISPATCH_Q(h->q, {
-    const size_t smem = level_smem<Q>(h->n_codes);
-    const int nthr = h->n_nodes * Q;
-    expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
-    ++nk;
-    for (const Level& L : h->post_levels) {
-      post_level_kernel<Q><<<(unsigned)((long long)L.count * tiles), TTB_BLOCK, smem, s>>>(d, h->d_post_nodes.p + L.begin, tiles);
-      ++nk;
-    }
-    root_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d, lh_only ? 1 : 0);
-    ++nk;
-    if (!lh_only) {
-      zero_slots_kernel<<<4, 256, 0, s>>>(d);
-      ++nk;
-      if (tips) {
-        for (const Level& L : h->pre_all_levels) {
-          pre_level_kernel<Q, true><<<(unsigned)((long long)L.count * tiles), TTB_BLOCK, smem, s>>>(d, h->d_pre_all.p + L.begin, tiles, count_diff);
-          ++nk;
-        }
-      } else {
-        for (const Level& L : h->pre_int_levels) {
-          pre_level_kernel<Q, false><<<(unsigned)((long long)L.count * tiles), TTB_BLOCK, smem, s>>>(d, h->d_pre_int.p + L.begin, tiles, count_diff);
-          ++nk;
-        }
-      }
-    }
-    finish_kernel<<<1, 256, 0, s>>>(d, tiles);
-    ++nk;
-  });
-  *n_kernels = nk;
+int enqueue_pass(ttb_handle h, int flags, int count_diff, cudaStream_t s, int* n_kernels, cudaEvent_t* ev = nullptr,
+                 int* phase_kernels = nullptr) {
+  TtbPassPlan pl;
+  pl.d = h->dev();
+  pl.tiles = h->tiles();
+  pl.lh_only = flags & TTB_LH_ONLY;
+  pl.tips = flags & TTB_RECONSTRUCT_TIPS;
+  pl.count_diff = count_diff;
+  pl.d_post_nodes = h->d_post_nodes.p;
+  pl.post_levels = h->post_levels.data();
+  pl.n_post_levels = (int)h->post_levels.size();
+  if (pl.tips) {
+    pl.d_pre_nodes = h->d_pre_all.p;
+    pl.pre_levels = h->pre_all_levels.data();
+    pl.n_pre_levels = (int)h->pre_all_levels.size();
+  } else {
+    pl.d_pre_nodes = h->d_pre_int.p;
+    pl.pre_levels = h->pre_int_levels.data();
+    pl.n_pre_levels = (int)h->pre_int_levels.size();
+  }
+  *n_kernels = ttb_qops(h->q)->enqueue_pass(pl, s, ev, phase_kernels);
   return 0;
 }
 
@@ -415,7 +390,7 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
   if (!h->n_nodes) return fail(TTB_EINVAL, "ttb_set_patterns: call ttb_set_tree first");
   if (n_patterns <= 0 || !tip_codes || n_codes <= 0 || n_codes > 255 || !code_profiles || !multiplicity)
     return fail(TTB_EINVAL, "ttb_set_patterns: bad arguments");
-  if (Smem<24>::bytes(n_codes) > 48 * 1024) return fail(TTB_EUNSUPPORTED, "ttb_set_patterns: too many distinct characters");
+  if (Smem<22>::bytes(n_codes) > 48 * 1024) return fail(TTB_EUNSUPPORTED, "ttb_set_patterns: too many distinct characters");
   const long long Lp = n_patterns, ld = (Lp + 31) / 32 * 32;
   CK(cudaStreamSynchronize(h->stream));
   cudaStream_t s = h->stream;
@@ -437,13 +412,17 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
   if (ld != h->ld || Lp != h->Lp) {
     h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();
     h->d_idx.release(); h->d_idxtip.release(); h->d_LH.release(); h->d_lh_partial.release();
+    h->drop_graphs();
+  } else if (n_codes != h->n_codes) {
+    h->drop_graphs();  // n_codes is a kernel parameter
   }
+  if (h->d_idx.p) CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), s));  // new data: no previous states
+  if (h->d_idxtip.p) CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), s));
   h->Lp = Lp;
   h->ld = ld;
   h->n_codes = n_codes;
   h->have_pass = h->have_tip_pass = false;
   h->first_full = true;
-  h->drop_graphs();
   return 0;
 }
 
@@ -567,8 +546,7 @@ int ttb_fetch_node(ttb_handle h, int32_t node, int32_t which, double* out) {
       return fail(TTB_EINVAL, "ttb_fetch_node: tip profiles exist only after TTB_RECONSTRUCT_TIPS");
   }
   if (int rc = h->d_stage.alloc((size_t)h->Lp * h->q)) return rc;
-  const TtbDev d = h->dev();
-  TTB_DISPATCH_Q(h->q, { fetch_node_kernel<Q><<<h->tiles(), TTB_BLOCK, 0, h->stream>>>(d, node, which, h->d_stage.p); });
+  ttb_qops(h->q)->fetch_node(h->dev(), h->tiles(), node, which, h->d_stage.p, h->stream);
   h->launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, h->d_stage.p, (size_t)h->Lp * h->q * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -593,6 +571,51 @@ int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* ou
     CK(cudaMemcpyAsync(out + (size_t)k * h->Lp, src, h->Lp, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, true)) return rc;
+  if (!out) return fail(TTB_EINVAL, "ttb_fetch_all_seq_idx: null output");
+  CK(cudaMemcpy2DAsync(out, h->Lp, h->d_idx.p, h->ld, h->Lp, h->n_int, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ttb_profile_marginal(ttb_handle h, int32_t flags, double* ms, int32_t* launches) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, false)) return rc;
+  if (!ms || !launches) return fail(TTB_EINVAL, "ttb_profile_marginal: null output");
+  const bool lh_only = flags & TTB_LH_ONLY;
+  const bool tips = (flags & TTB_RECONSTRUCT_TIPS) && !lh_only;
+  flags = (lh_only ? TTB_LH_ONLY : 0) | (tips ? TTB_RECONSTRUCT_TIPS : 0);
+  const bool had_P = h->d_P.p != nullptr;
+  if (int rc = ensure_state(h, tips)) return rc;
+  if (!had_P) h->drop_graphs();
+  if (!lh_only)
+    if (int rc = ensure_preorder_state(h, tips)) return rc;
+  cudaEvent_t ev[6];
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  int nk = 0, pk[4] = {0, 0, 0, 0};
+  int rc = enqueue_pass(h, flags, lh_only ? 0 : 1, h->stream, &nk, ev, pk);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float f;
+  CK(cudaEventElapsedTime(&f, ev[0], ev[1])); ms[0] = f;
+  CK(cudaEventElapsedTime(&f, ev[1], ev[2])); ms[1] = f;
+  CK(cudaEventElapsedTime(&f, ev[2], ev[3])); ms[2] = f;
+  CK(cudaEventElapsedTime(&f, ev[4], ev[5])); ms[2] += f;
+  CK(cudaEventElapsedTime(&f, ev[3], ev[4])); ms[3] = f;
+  for (int i = 0; i < 4; ++i) launches[i] = pk[i];
+  for (auto& e : ev) cudaEventDestroy(e);
+  h->launches += nk;
+  if (!lh_only) {
+    h->have_pass = true;
+    h->have_tip_pass = tips;
+  }
   return 0;
 }
 
@@ -622,12 +645,8 @@ static int branch_eval(ttb_handle h, int32_t n_eval, const int32_t* nodes, const
   nb = std::min(nb, 64);
   if ((rc = h->d_partial.alloc((size_t)n_eval * nb))) return rc;
   if ((rc = h->d_eout.alloc((size_t)n_eval))) return rc;
-  const TtbDev d = h->dev();
-  dim3 grid(n_eval, nb);
-  TTB_DISPATCH_Q(h->q, {
-    branch_eval_kernel<Q><<<grid, TTB_BLOCK, 0, s>>>(d, h->d_enodes.p, kind ? h->d_ekinds.p : nullptr, h->d_ets.p, mode, h->d_partial.p);
-  });
-  branch_reduce_kernel<<<(n_eval + 127) / 128, 128, 0, s>>>(h->d_partial.p, n_eval, nb, h->d_eout.p);
+  ttb_qops(h->q)->branch_eval(h->dev(), n_eval, nb, h->d_enodes.p, kind ? h->d_ekinds.p : nullptr, h->d_ets.p, mode,
+                              h->d_partial.p, h->d_eout.p, s);
   h->launches += 2;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, h->d_eout.p, (size_t)n_eval * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -661,10 +680,7 @@ int ttb_mutation_counts(ttb_handle h, double* n_ij, double* T_i) {
   int rc;
   if ((rc = h->d_partial.alloc((size_t)chunks * tiles * width))) return rc;
   if ((rc = h->d_eout.alloc((size_t)width))) return rc;
-  const TtbDev d = h->dev();
-  dim3 grid(tiles, chunks);
-  TTB_DISPATCH_Q(h->q, { counts_kernel<Q><<<grid, TTB_BLOCK, 0, h->stream>>>(d, chunk, h->d_partial.p); });
-  counts_reduce_kernel<<<(width + 127) / 128, 128, 0, h->stream>>>(h->d_partial.p, chunks * tiles, width, h->d_eout.p);
+  ttb_qops(h->q)->counts(h->dev(), tiles, chunks, chunk, h->d_partial.p, h->d_eout.p, h->stream);
   h->launches += 2;
   CK(cudaGetLastError());
   std::vector<double> tmp(width);

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) root_kernel(TtbDev p, int lh_only) 
 }
 
 // Final deterministic reduction: total LH over tiles, N_diff over slots.
-__global__ void __launch_bounds__(256) finish_kernel(TtbDev p, int tiles) {
+static __global__ void __launch_bounds__(256) finish_kernel(TtbDev p, int tiles) {
   __shared__ double sred[256 / 32];
   double x = 0.0;
   for (int i = threadIdx.x; i < tiles; i += 256) x += p.lh_partial[i];
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) finish_kernel(TtbDev p, int tiles) {
   }
 }
 
-__global__ void zero_slots_kernel(TtbDev p) {
+static __global__ void zero_slots_kernel(TtbDev p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 1024) p.nd_slots[i] = 0ull;
 }
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) branch_eval_kernel(TtbDev p, const 
   if (threadIdx.x == 0) partial[(size_t)e * gridDim.y + blockIdx.y] = bs;
 }
 
-__global__ void branch_reduce_kernel(const double* __restrict__ partial, int n_eval, int nb, double* __restrict__ out) {
+static __global__ void branch_reduce_kernel(const double* __restrict__ partial, int n_eval, int nb, double* __restrict__ out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_eval) return;
   double s = 0.0;
@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) counts_kernel(TtbDev p, int chunk, 
   }
 }
 
-__global__ void counts_reduce_kernel(const double* __restrict__ partial, int n_part, int width, double* __restrict__ out) {
+static __global__ void counts_reduce_kernel(const double* __restrict__ partial, int n_part, int width, double* __restrict__ out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= width) return;
   double s = 0.0;

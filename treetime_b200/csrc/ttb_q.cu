@@ -1,0 +1,72 @@
+// ttb_q.cu -- instantiates the kernels for ONE alphabet size (-DTTB_Q=<q>) and exports
+// their launchers as a TtbQOps table.
+#include "ttb_qops.h"
+
+#ifndef TTB_Q
+#error "compile with -DTTB_Q=<n_states>"
+#endif
+
+namespace {
+constexpr int Q = TTB_Q;
+
+int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
+  const TtbDev& d = pl.d;
+  const int tiles = pl.tiles;
+  const size_t smem = Smem<Q>::bytes(d.n_codes);
+  int nk = 0;
+  if (ev) cudaEventRecord(ev[0], s);
+  const int nthr = d.n_nodes * Q;
+  expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
+  ++nk;
+  if (ev) { cudaEventRecord(ev[1], s); pk[0] = nk; }
+  for (int l = 0; l < pl.n_post_levels; ++l) {
+    const TtbLevel& L = pl.post_levels[l];
+    post_level_kernel<Q><<<(unsigned)((long long)L.count * tiles), TTB_BLOCK, smem, s>>>(d, pl.d_post_nodes + L.begin, tiles);
+    ++nk;
+  }
+  if (ev) { cudaEventRecord(ev[2], s); pk[1] = nk - pk[0]; }
+  root_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d, pl.lh_only ? 1 : 0);
+  ++nk;
+  if (!pl.lh_only) {
+    zero_slots_kernel<<<4, 256, 0, s>>>(d);
+    ++nk;
+  }
+  if (ev) { cudaEventRecord(ev[3], s); pk[2] = nk - pk[0] - pk[1]; }
+  if (!pl.lh_only) {
+    for (int l = 0; l < pl.n_pre_levels; ++l) {
+      const TtbLevel& L = pl.pre_levels[l];
+      const unsigned grid = (unsigned)((long long)L.count * tiles);
+      if (pl.tips)
+        pre_level_kernel<Q, true><<<grid, TTB_BLOCK, smem, s>>>(d, pl.d_pre_nodes + L.begin, tiles, pl.count_diff);
+      else
+        pre_level_kernel<Q, false><<<grid, TTB_BLOCK, smem, s>>>(d, pl.d_pre_nodes + L.begin, tiles, pl.count_diff);
+      ++nk;
+    }
+  }
+  if (ev) { cudaEventRecord(ev[4], s); pk[3] = nk - pk[0] - pk[1] - pk[2]; }
+  finish_kernel<<<1, 256, 0, s>>>(d, tiles);
+  ++nk;
+  if (ev) { cudaEventRecord(ev[5], s); pk[2] += 1; }
+  return nk;
+}
+
+void fetch_node_q(const TtbDev& d, int tiles, int node, int which, double* out, cudaStream_t s) {
+  fetch_node_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d, node, which, out);
+}
+
+void branch_eval_q(const TtbDev& d, int n_eval, int nb, const int* nodes, const int* kinds, const double* ts, int mode,
+                   double* partial, double* out, cudaStream_t s) {
+  branch_eval_kernel<Q><<<dim3(n_eval, nb), TTB_BLOCK, 0, s>>>(d, nodes, kinds, ts, mode, partial);
+  branch_reduce_kernel<<<(n_eval + 127) / 128, 128, 0, s>>>(partial, n_eval, nb, out);
+}
+
+void counts_q(const TtbDev& d, int tiles, int chunks, int chunk, double* partial, double* out, cudaStream_t s) {
+  counts_kernel<Q><<<dim3(tiles, chunks), TTB_BLOCK, 0, s>>>(d, chunk, partial);
+  const int width = Q * Q + Q;
+  counts_reduce_kernel<<<(width + 127) / 128, 128, 0, s>>>(partial, chunks * tiles, width, out);
+}
+}  // namespace
+
+#define TTB_CAT2(a, b) a##b
+#define TTB_CAT(a, b) TTB_CAT2(a, b)
+extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {enqueue_pass_q, fetch_node_q, branch_eval_q, counts_q};

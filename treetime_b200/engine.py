@@ -134,6 +134,22 @@ class Engine(object):
         _lib.check(self.lib.ttb_fetch_seq_idx(self.h, nodes.shape[0], _ip(nodes), _up(out)))
         return out
 
+    def all_seq_idx(self, out=None):
+        """State indices of all internal nodes, [n_internal, n_patterns] in node order."""
+        n_int = int((self.tip_row < 0).sum())
+        if out is None:
+            out = np.empty((n_int, self.n_patterns), dtype=np.uint8)
+        _lib.check(self.lib.ttb_fetch_all_seq_idx(self.h, _up(out)))
+        return out
+
+    def profile_marginal(self, reconstruct_tips=False, lh_only=False):
+        """Un-graphed pass with per-phase CUDA-event times: dict phase -> (ms, launches)."""
+        flags = (RECONSTRUCT_TIPS if reconstruct_tips else 0) | (LH_ONLY if lh_only else 0)
+        ms = np.zeros(4, dtype=np.float64)
+        nl = np.zeros(4, dtype=np.int32)
+        _lib.check(self.lib.ttb_profile_marginal(self.h, flags, _dp(ms), _ip(nl)))
+        return {k: (float(ms[i]), int(nl[i])) for i, k in enumerate(('expqt', 'postorder', 'root', 'preorder'))}
+
     def branch_objective(self, nodes, t, kinds=None):
         nodes, t = _i32(nodes), _f64(t)
         out = np.empty(nodes.shape[0], dtype=np.float64)

@@ -122,3 +122,49 @@ def sprinkle_ambiguous(aln_chars, frac, ambiguous_chars, seed=1):
         s[m] = amb[rng.integers(0, len(amb), size=int(m.sum()))]
         out[k] = s
     return out
+
+
+def flat_problem(tree, sd, gtr):
+    """tree + SequenceData + GTR -> (FlatTopology, flat dict, gtr dict): the arrays that cross
+    the C-ABI (include/ttb.h) and that the CPU oracle consumes.  Mirrors what
+    TreeAnc._sync_device uploads: ladderized child order (treeanc.py:456-457), branch lengths
+    floored at MIN_BRANCH_LENGTH * one_mutation (treeanc.py:752-760)."""
+    from . import config as ttconf
+    from .flatten import FlatTopology, code_table, gtr_arrays
+    tree.ladderize()
+    topo = FlatTopology(tree.root)
+    chars, lut, table = code_table(gtr.profile_map, gtr.n_states)
+    lut8 = np.full(256, 255, dtype=np.uint8)
+    for c, i in lut.items():
+        lut8[ord(c)] = i
+    rows = np.array([sd._row.get(topo.nodes[n].name, -1) for n in topo.tip_nodes])
+    codes = np.full((topo.n_tips, sd.compressed_length), len(chars), dtype=np.uint8)
+    have = rows >= 0
+    codes[have] = lut8[sd.compressed_matrix[rows[have]]]
+    if (codes == 255).any():
+        raise KeyError('alignment contains characters that are not in the profile map')
+    one_mutation = 1.0 / sd.full_length
+    floor = ttconf.MIN_BRANCH_LENGTH * one_mutation
+    t = np.array([max(floor, n.branch_length if n.branch_length else 0.0) for n in topo.nodes])
+    t[0] = max(floor, 0.001)
+    flat = topo.as_dict()
+    flat.update(tip_codes=codes, code_profiles=table, multiplicity=np.array(sd.multiplicity(), dtype=np.float64), t=t)
+    return topo, flat, gtr_arrays(gtr)
+
+
+def make_flat_problem(tree, gtr, L, seed, amb_frac=0.0, amb_chars='N-RY', compress=True, mu_sim=1.0):
+    """Simulate an alignment of length L down `tree` and flatten everything."""
+    from .sequence_data import SequenceData
+    Pi = gtr.Pi if np.ndim(gtr.Pi) == 1 else gtr.Pi.mean(axis=1)
+    idx = evolve_alignment(tree, L, Pi, gtr.W, mu=mu_sim, seed=seed)
+    ab = np.asarray(gtr.alphabet).astype('S1').view(np.uint8)
+    aln = {k: ab[v] for k, v in idx.items()}                      # ASCII bytes
+    if amb_frac:
+        amb = np.frombuffer(amb_chars.encode('ascii'), dtype=np.uint8)
+        rng = np.random.default_rng(seed + 1)
+        for k in sorted(aln):
+            s = aln[k]
+            m = rng.random(s.shape[0]) < amb_frac
+            s[m] = amb[rng.integers(0, len(amb), size=int(m.sum()))]
+    sd = SequenceData(aln, compress=compress, ambiguous=gtr.ambiguous)
+    return flat_problem(tree, sd, gtr)
