@@ -215,7 +215,8 @@ def main():
     Lp = flat['multiplicity'].shape[0]
     updates_local = n_br * Lp
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: events on it bracket the engine's work
+    torch.cuda.set_stream(stream)
     eng = Engine(q, device=local_rank)
     eng.set_stream(stream.cuda_stream)
     eng.set_tree(flat['parent'], flat['child_ptr'], flat['child_idx'], flat['tip_row'])

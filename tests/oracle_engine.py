@@ -1,0 +1,117 @@
+"""TEST-ONLY stand-in for treetime_b200.engine.Engine backed by the CPU oracle.
+
+Lets the host logic (TreeAnc mirror, lock-step Brent, pattern sharding, the
+TreeTime drop-in) be exercised without a GPU.  It is injected explicitly through
+`TreeAnc(..., engine_factory=oracle_engine.factory)`; nothing in treetime_b200/
+knows about it and the product path never falls back to it."""
+import numpy as np
+import flat_numpy as O
+
+
+class OracleEngine(object):
+    def __init__(self, n_states, device=0):
+        self.n_states = n_states
+        self.flat = {}
+        self.g = None
+        self.res = None
+        self.prev_idx = None
+        self.launches = 0
+
+    def set_stream(self, s):
+        pass
+
+    def set_tree(self, parent, child_ptr, child_idx, tip_row):
+        self.flat.update(parent=np.array(parent), child_ptr=np.array(child_ptr), child_idx=np.array(child_idx),
+                         tip_row=np.array(tip_row))
+        self.n_nodes = len(parent)
+        self.tip_row = np.array(tip_row)
+        self.res = None
+        self.prev_idx = None
+
+    def set_patterns(self, tip_codes, code_profiles, multiplicity):
+        self.flat.update(tip_codes=np.array(tip_codes), code_profiles=np.array(code_profiles, dtype=float),
+                         multiplicity=np.array(multiplicity, dtype=float))
+        self.n_patterns = tip_codes.shape[1]
+        self.res = None
+        self.prev_idx = None
+
+    def set_gtr(self, g):
+        self.g = dict(g)
+
+    def set_branch_lengths(self, t):
+        self.flat['t'] = np.array(t, dtype=float)
+
+    def marginal(self, reconstruct_tips=False, lh_only=False):
+        self.launches += 1
+        if lh_only:
+            r = O.sequence_LH_only(self.flat, self.g)
+            self._tot, self._nd = r.total_LH, 0
+            self._site = r.sequence_LH
+            return
+        self.t_pass = self.flat['t'].copy()
+        self.g_pass = dict(self.g)
+        r = O.marginal(self.flat, self.g, reconstruct_tip_states=reconstruct_tips, prev_seq_idx=self.prev_idx)
+        if self.prev_idx is None:
+            pass
+        self.res = r
+        self.prev_idx = list(r.seq_idx)
+        self._tot, self._nd, self._site = r.total_LH, r.N_diff, r.sequence_LH
+
+    def results(self):
+        return self._tot, self._nd
+
+    def sync(self):
+        pass
+
+    def site_lh(self):
+        return self._site.copy()
+
+    def node_array(self, node, which):
+        r = self.res
+        return np.array((r.subtree_LH, r.outgroup_LH, r.profile)[which][node])
+
+    def seq_idx(self, nodes):
+        return np.array([self.res.seq_idx[int(n)] for n in np.atleast_1d(nodes)], dtype=np.uint8)
+
+    def all_seq_idx(self, out=None):
+        rows = [self.res.seq_idx[n] for n in range(self.n_nodes) if self.tip_row[n] < 0]
+        return np.array(rows, dtype=np.uint8)
+
+    def _pair(self, n, kind):
+        if kind == 1:
+            return O.root_branch_profiles(self._pass_flat(), self.g_pass, self.res)
+        return self.res.outgroup_LH[n], self.res.subtree_LH[n]
+
+    def _pass_flat(self):
+        f = dict(self.flat)
+        f['t'] = self.t_pass
+        return f
+
+    def branch_objective(self, nodes, t, kinds=None):
+        G = O.make_gtr(self.g_pass)
+        kinds = np.zeros(len(nodes), dtype=int) if kinds is None else kinds
+        return np.array([G.prob_t_profiles(self._pair(int(n), int(k)), self.flat['multiplicity'], float(tt), return_log=True)
+                         for n, k, tt in zip(nodes, kinds, t)])
+
+    def branch_hamming(self, nodes, kinds=None):
+        kinds = np.zeros(len(nodes), dtype=int) if kinds is None else kinds
+        m = self.flat['multiplicity']
+        num = []
+        for n, k in zip(nodes, kinds):
+            pp, pc = self._pair(int(n), int(k))
+            num.append(np.sum(m * np.sum(pp * pc, axis=1)))
+        return np.array(num), m.sum()
+
+    def mutation_counts(self):
+        n_ija, T_ia = O.mutation_counts(self._pass_flat(), self.g_pass, self.res)
+        return n_ija.sum(axis=-1), T_ia.sum(axis=-1)
+
+    def launch_count(self):
+        return self.launches
+
+    def device_bytes(self):
+        return 0
+
+
+def factory(n_states, device):
+    return OracleEngine(n_states, device)
