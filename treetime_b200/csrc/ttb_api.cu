@@ -71,7 +71,19 @@ struct DBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
-typedef TtbLevel Level;
+// Level-ordered schedule of one traversal: chunks grouped by node, nodes grouped by level.
+struct Sched {
+  std::vector<TtbChunk> chunks;       // all levels, node-major
+  std::vector<int> node_chunk;        // first chunk of every scheduled node (+ sentinel), level-major
+  std::vector<int> level_node_begin;  // offsets into node_chunk per level (+ sentinel)
+  std::vector<int> group_ptr;         // built once the number of tiles is known
+  std::vector<TtbLevelLaunch> launches;
+  DBuf<TtbChunk> d_chunks;
+  DBuf<int> d_group_ptr;
+  void clear() {
+    chunks.clear(); node_chunk.clear(); level_node_begin.clear(); group_ptr.clear(); launches.clear();
+  }
+};
 
 }  // namespace
 
@@ -83,16 +95,17 @@ struct ttb_engine {
   // tree (host)
   int n_nodes = 0, n_int = 0, n_tips = 0;
   std::vector<int> parent, child_ptr, child_idx, tip_row, int_slot;
-  std::vector<int> post_nodes, pre_int_parents, pre_all_parents;
-  std::vector<Level> post_levels, pre_int_levels, pre_all_levels;
+  std::vector<int> tip_nodes;
+  Sched post, pre_int, pre_all;
+  int sched_tiles = -1;  // tiles the group pointers were built for
+  bool prepared = false;
   // device tree
-  DBuf<int> d_parent, d_child_ptr, d_child_idx, d_tip_row, d_int_slot, d_post_nodes, d_pre_int, d_pre_all;
+  DBuf<int> d_parent, d_child_ptr, d_child_idx, d_tip_row, d_int_slot, d_tip_nodes;
   // alignment
   long long Lp = 0, ld = 0;
   int n_codes = 0;
   DBuf<uint8_t> d_codes;
   DBuf<double> d_code_prof, d_mult;
-  DBuf<uint32_t> d_code_mask;
   std::vector<double> h_mult;
   // model
   bool have_gtr = false, have_t = false;
@@ -100,7 +113,7 @@ struct ttb_engine {
   int gap_index = -1;
   DBuf<double> d_t, d_eig, d_v, d_vinv, d_Pi, d_mu;
   // state
-  DBuf<double> d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
+  DBuf<double> d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
   DBuf<uint8_t> d_idx, d_idxtip;
   DBuf<unsigned long long> d_nd;
   DBuf<int> d_enodes, d_ekinds;
@@ -138,7 +151,6 @@ struct ttb_engine {
     d.int_slot = d_int_slot.p;
     d.codes = d_codes.p;
     d.code_prof = d_code_prof.p;
-    d.code_mask = d_code_mask.p;
     d.mult = d_mult.p;
     d.t = d_t.p;
     d.eig = d_eig.p;
@@ -146,6 +158,9 @@ struct ttb_engine {
     d.vinv = d_vinv.p;
     d.Pi = d_Pi.p;
     d.mu = d_mu.p;
+    d.pq = (q * q + 1) / 2 * 2;
+    d.tu_stride = (n_codes * q + 1) / 2 * 2;
+    d.TU = d_TU.p;
     d.P = d_P.p;
     d.S = d_S.p;
     d.F = d_F.p;
@@ -177,23 +192,71 @@ int upload(DBuf<T>& b, const T* src, size_t n, cudaStream_t s) {
   return 0;
 }
 
-// Group internal nodes into level lists.
-void build_levels(const std::vector<int>& key, const std::vector<char>& member, std::vector<int>& nodes,
-                  std::vector<Level>& levels) {
+// Build the chunk schedule of one traversal.  `key[n]` = level of node n (height for the
+// postorder, depth for the preorder), `member[n]` = node n is scheduled, `take(c)` = child c
+// takes part.  Levels are emitted in increasing key order for the preorder and increasing
+// height for the postorder (both = dependency order); nodes inside a level in id order.
+template <typename Take>
+void build_sched(ttb_handle h, const std::vector<int>& key, const std::vector<char>& member, bool out_is_node_slot,
+                 Take take, Sched& sc) {
+  sc.clear();
+  const int n_nodes = h->n_nodes;
   int maxk = -1;
-  for (size_t n = 0; n < key.size(); ++n)
+  for (int n = 0; n < n_nodes; ++n)
     if (member[n]) maxk = std::max(maxk, key[n]);
-  std::vector<int> count(maxk + 2, 0);
-  for (size_t n = 0; n < key.size(); ++n)
-    if (member[n]) count[key[n] + 1]++;
-  for (int k = 0; k <= maxk; ++k) count[k + 1] += count[k];
-  nodes.assign(count[maxk + 1], 0);
-  std::vector<int> fill(count.begin(), count.end() - 1);
-  for (size_t n = 0; n < key.size(); ++n)
-    if (member[n]) nodes[fill[key[n]]++] = (int)n;
-  levels.clear();
-  for (int k = 0; k <= maxk; ++k)
-    if (count[k + 1] > count[k]) levels.push_back({count[k], count[k + 1] - count[k]});
+  std::vector<std::vector<int>> by_level(maxk + 1);
+  for (int n = 0; n < n_nodes; ++n)
+    if (member[n]) by_level[key[n]].push_back(n);
+  sc.level_node_begin.push_back(0);
+  for (int k = 0; k <= maxk; ++k) {
+    if (by_level[k].empty()) continue;
+    for (int n : by_level[k]) {
+      sc.node_chunk.push_back((int)sc.chunks.size());
+      std::vector<int> kids;
+      for (int e = h->child_ptr[n]; e < h->child_ptr[n + 1]; ++e)
+        if (take(h->child_idx[e])) kids.push_back(h->child_idx[e]);
+      const int nk = (int)kids.size();
+      for (int c0 = 0; c0 < nk; c0 += TTB_CB) {
+        TtbChunk ch;
+        memset(&ch, 0, sizeof ch);
+        ch.out = h->int_slot[n];
+        const int nb = std::min(TTB_CB, nk - c0);
+        ch.flags = (c0 == 0 ? 1 : 0) | (c0 + TTB_CB >= nk ? 2 : 0) | (nb << 8);
+        for (int b = 0; b < nb; ++b) {
+          const int c = kids[c0 + b];
+          ch.src[b] = h->int_slot[c] >= 0 ? h->int_slot[c] : -1 - h->tip_row[c];
+          ch.cnode[b] = c;
+        }
+        sc.chunks.push_back(ch);
+      }
+    }
+    sc.level_node_begin.push_back((int)sc.node_chunk.size());
+  }
+  sc.node_chunk.push_back((int)sc.chunks.size());
+  (void)out_is_node_slot;
+}
+
+// Split every level into groups of consecutive nodes so that a launch has enough blocks to
+// fill the GPU but every block still pipelines over several chunks.
+void build_groups(Sched& sc, int tiles) {
+  sc.group_ptr.clear();
+  sc.launches.clear();
+  const long long target_blocks = 148LL * 32;
+  for (size_t l = 0; l + 1 < sc.level_node_begin.size(); ++l) {
+    const int nb = sc.level_node_begin[l], ne = sc.level_node_begin[l + 1];
+    const int n = ne - nb;
+    long long G = ((long long)n * tiles + target_blocks - 1) / target_blocks;
+    G = std::max(1LL, std::min(32LL, G));
+    TtbLevelLaunch L;
+    L.group_off = (int)sc.group_ptr.size();
+    L.n_groups = 0;
+    for (int i = nb; i < ne; i += (int)G) {
+      sc.group_ptr.push_back(sc.node_chunk[i]);
+      ++L.n_groups;
+    }
+    sc.group_ptr.push_back(sc.node_chunk[ne]);
+    sc.launches.push_back(L);
+  }
 }
 
 // Enqueue every kernel of one pass on `s`; returns the number of kernels.
@@ -205,18 +268,16 @@ int enqueue_pass(ttb_handle h, int flags, int count_diff, cudaStream_t s, int* n
   pl.lh_only = flags & TTB_LH_ONLY;
   pl.tips = flags & TTB_RECONSTRUCT_TIPS;
   pl.count_diff = count_diff;
-  pl.d_post_nodes = h->d_post_nodes.p;
-  pl.post_levels = h->post_levels.data();
-  pl.n_post_levels = (int)h->post_levels.size();
-  if (pl.tips) {
-    pl.d_pre_nodes = h->d_pre_all.p;
-    pl.pre_levels = h->pre_all_levels.data();
-    pl.n_pre_levels = (int)h->pre_all_levels.size();
-  } else {
-    pl.d_pre_nodes = h->d_pre_int.p;
-    pl.pre_levels = h->pre_int_levels.data();
-    pl.n_pre_levels = (int)h->pre_int_levels.size();
-  }
+  pl.d_tip_nodes = h->d_tip_nodes.p;
+  pl.d_post_chunks = h->post.d_chunks.p;
+  pl.d_post_group_ptr = h->post.d_group_ptr.p;
+  pl.post_levels = h->post.launches.data();
+  pl.n_post_levels = (int)h->post.launches.size();
+  const Sched& pre = pl.tips ? h->pre_all : h->pre_int;
+  pl.d_pre_chunks = pre.d_chunks.p;
+  pl.d_pre_group_ptr = pre.d_group_ptr.p;
+  pl.pre_levels = pre.launches.data();
+  pl.n_pre_levels = (int)pre.launches.size();
   *n_kernels = ttb_qops(h->q)->enqueue_pass(pl, s, ev, phase_kernels);
   return 0;
 }
@@ -224,7 +285,23 @@ int enqueue_pass(ttb_handle h, int flags, int count_diff, cudaStream_t s, int* n
 int ensure_state(ttb_handle h, bool tips) {
   const size_t q = h->q, ld = h->ld;
   int rc;
-  if ((rc = h->d_P.alloc((size_t)h->n_nodes * q * q))) return rc;
+  const size_t pq = (q * q + 1) / 2 * 2, tus = ((size_t)h->n_codes * q + 1) / 2 * 2;
+  if ((rc = h->d_P.alloc((size_t)h->n_nodes * pq))) return rc;
+  if ((rc = h->d_TU.alloc((size_t)h->n_tips * tus))) return rc;
+  if (h->sched_tiles != h->tiles()) {
+    for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all}) {
+      build_groups(*sc, h->tiles());
+      if ((rc = upload(sc->d_group_ptr, sc->group_ptr.data(), sc->group_ptr.size(), h->stream))) return rc;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->sched_tiles = h->tiles();
+    h->drop_graphs();
+  }
+  if (!h->prepared) {
+    const int e = ttb_qops(h->q)->prepare(h->dev());
+    if (e) return fail(TTB_ECUDA, std::string("cudaFuncSetAttribute(shared memory) failed: ") + cudaGetErrorString((cudaError_t)e));
+    h->prepared = true;
+  }
   if ((rc = h->d_S.alloc((size_t)h->n_int * q * ld))) return rc;
   if ((rc = h->d_F.alloc((size_t)h->n_int * ld))) return rc;
   if ((rc = h->d_LH.alloc(ld))) return rc;
@@ -295,15 +372,15 @@ int ttb_destroy(ttb_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   h->drop_graphs();
-  DBuf<int>* ib[] = {&h->d_parent, &h->d_child_ptr, &h->d_child_idx, &h->d_tip_row, &h->d_int_slot, &h->d_post_nodes,
-                     &h->d_pre_int, &h->d_pre_all, &h->d_enodes, &h->d_ekinds};
+  DBuf<int>* ib[] = {&h->d_parent, &h->d_child_ptr, &h->d_child_idx, &h->d_tip_row, &h->d_int_slot, &h->d_tip_nodes,
+                     &h->d_enodes, &h->d_ekinds, &h->post.d_group_ptr, &h->pre_int.d_group_ptr, &h->pre_all.d_group_ptr};
   for (auto* b : ib) b->release();
-  DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_P, &h->d_S,
+  DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_TU, &h->d_P, &h->d_S,
                         &h->d_F, &h->d_M, &h->d_Mtip, &h->d_LH, &h->d_lh_partial, &h->d_results, &h->d_stage,
                         &h->d_partial, &h->d_ets, &h->d_eout};
   for (auto* b : db) b->release();
   h->d_codes.release();
-  h->d_code_mask.release();
+  h->post.d_chunks.release(); h->pre_int.d_chunks.release(); h->pre_all.d_chunks.release();
   h->d_idx.release();
   h->d_idxtip.release();
   h->d_nd.release();
@@ -359,9 +436,13 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   for (int n = 0; n < n_nodes; ++n) is_int[n] = slot[n] >= 0;
   for (int n = 1; n < n_nodes; ++n)
     if (is_int[n]) has_int_child[parent[n]] = 1;
-  build_levels(height, is_int, h->post_nodes, h->post_levels);
-  build_levels(depth, has_int_child, h->pre_int_parents, h->pre_int_levels);
-  build_levels(depth, is_int, h->pre_all_parents, h->pre_all_levels);
+  h->tip_nodes.assign(n_tips, 0);
+  for (int n = 0; n < n_nodes; ++n)
+    if (tip_row[n] >= 0) h->tip_nodes[tip_row[n]] = n;
+  build_sched(h, height, is_int, true, [](int) { return true; }, h->post);
+  build_sched(h, depth, has_int_child, false, [&](int c) { return slot[c] >= 0; }, h->pre_int);
+  build_sched(h, depth, is_int, false, [](int) { return true; }, h->pre_all);
+  h->sched_tiles = -1;
   cudaStream_t s = h->stream;
   int rc;
   if ((rc = upload(h->d_parent, h->parent.data(), h->parent.size(), s))) return rc;
@@ -369,12 +450,12 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   if ((rc = upload(h->d_child_idx, h->child_idx.data(), h->child_idx.size(), s))) return rc;
   if ((rc = upload(h->d_tip_row, h->tip_row.data(), h->tip_row.size(), s))) return rc;
   if ((rc = upload(h->d_int_slot, h->int_slot.data(), h->int_slot.size(), s))) return rc;
-  if ((rc = upload(h->d_post_nodes, h->post_nodes.data(), h->post_nodes.size(), s))) return rc;
-  if ((rc = upload(h->d_pre_int, h->pre_int_parents.data(), h->pre_int_parents.size(), s))) return rc;
-  if ((rc = upload(h->d_pre_all, h->pre_all_parents.data(), h->pre_all_parents.size(), s))) return rc;
+  if ((rc = upload(h->d_tip_nodes, h->tip_nodes.data(), h->tip_nodes.size(), s))) return rc;
+  for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all})
+    if ((rc = upload(sc->d_chunks, sc->chunks.data(), sc->chunks.size(), s))) return rc;
   CK(cudaStreamSynchronize(s));
   // every per-node array is invalid now
-  h->d_P.release(); h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();
+  h->d_P.release(); h->d_TU.release(); h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();
   h->d_idx.release(); h->d_idxtip.release();
   h->d_t.release();
   h->have_t = false;
@@ -390,7 +471,7 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
   if (!h->n_nodes) return fail(TTB_EINVAL, "ttb_set_patterns: call ttb_set_tree first");
   if (n_patterns <= 0 || !tip_codes || n_codes <= 0 || n_codes > 255 || !code_profiles || !multiplicity)
     return fail(TTB_EINVAL, "ttb_set_patterns: bad arguments");
-  if (Smem<22>::bytes(n_codes) > 48 * 1024) return fail(TTB_EUNSUPPORTED, "ttb_set_patterns: too many distinct characters");
+  if ((size_t)n_codes * h->q * 8 > 16 * 1024) return fail(TTB_EUNSUPPORTED, "ttb_set_patterns: too many distinct characters for the tip tables");
   const long long Lp = n_patterns, ld = (Lp + 31) / 32 * 32;
   CK(cudaStreamSynchronize(h->stream));
   cudaStream_t s = h->stream;
@@ -398,12 +479,7 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
   if ((rc = h->d_codes.alloc((size_t)h->n_tips * ld))) return rc;
   CK(cudaMemsetAsync(h->d_codes.p, 0, h->d_codes.bytes(), s));
   CK(cudaMemcpy2DAsync(h->d_codes.p, ld, tip_codes, Lp, Lp, h->n_tips, cudaMemcpyHostToDevice, s));
-  std::vector<uint32_t> mask(n_codes, 0);
-  for (int c = 0; c < n_codes; ++c)
-    for (int i = 0; i < h->q; ++i)
-      if (code_profiles[(size_t)c * h->q + i] != 0.0) mask[c] |= (1u << i);
   if ((rc = upload(h->d_code_prof, code_profiles, (size_t)n_codes * h->q, s))) return rc;
-  if ((rc = upload(h->d_code_mask, mask.data(), mask.size(), s))) return rc;
   if ((rc = h->d_mult.alloc(ld))) return rc;
   CK(cudaMemsetAsync(h->d_mult.p, 0, h->d_mult.bytes(), s));
   CK(cudaMemcpyAsync(h->d_mult.p, multiplicity, Lp * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -414,6 +490,7 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
     h->d_idx.release(); h->d_idxtip.release(); h->d_LH.release(); h->d_lh_partial.release();
     h->drop_graphs();
   } else if (n_codes != h->n_codes) {
+    h->d_TU.release();
     h->drop_graphs();  // n_codes is a kernel parameter
   }
   if (h->d_idx.p) CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), s));  // new data: no previous states
@@ -693,7 +770,7 @@ int ttb_mutation_counts(ttb_handle h, double* n_ij, double* T_i) {
 
 int ttb_device_bytes(ttb_handle h, int64_t* bytes) {
   if (!h || !bytes) return fail(TTB_EINVAL, "null argument");
-  size_t b = h->d_codes.bytes() + h->d_code_prof.bytes() + h->d_mult.bytes() + h->d_code_mask.bytes() + h->d_t.bytes() +
+  size_t b = h->d_codes.bytes() + h->d_code_prof.bytes() + h->d_mult.bytes() + h->d_TU.bytes() + h->d_t.bytes() +
              h->d_P.bytes() + h->d_S.bytes() + h->d_F.bytes() + h->d_M.bytes() + h->d_Mtip.bytes() + h->d_LH.bytes() +
              h->d_idx.bytes() + h->d_idxtip.bytes() + h->d_stage.bytes() + h->d_partial.bytes() + h->d_parent.bytes() * 5;
   *bytes = (int64_t)b;

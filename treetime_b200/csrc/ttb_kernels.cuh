@@ -2,16 +2,21 @@
 //
 // Data layout in HBM (DESIGN.md "Layout"): every message array is STATE-PLANAR,
 //   A[slot][state][pattern]   (pattern stride = ld, a multiple of 32 doubles = 256 B)
-// so a warp that owns 32 consecutive patterns reads/writes q fully coalesced 256-byte
-// rows per node and no byte of padding ever crosses HBM (the 5->8 padded AoS layout would
-// move 60 % more bytes).  One thread = one alignment pattern; the q-state vectors live in
-// registers; the per-branch exp(Qt) matrices are staged in shared memory and read as
-// warp-wide broadcasts.
+// so the q values of 128 consecutive patterns of one node are q contiguous 1 KB rows and no
+// byte of padding ever crosses HBM (a 5->8 padded AoS layout would move 60 % more bytes).
 //
-// Arithmetic contract (reference lines cited per kernel): products
-// are taken in linear space with exact power-of-two rescaling instead of the reference's
-// sum of logs; one log per (internal node, pattern) survives.  This is the same function
-// up to fp64 rounding (measured: |dLH|/|LH| ~ 1e-15, profiles ~1e-16).
+// Level kernels (postorder / preorder) are TMA pipelines: a block owns one 128-pattern tile
+// and a run of nodes of the level; one warp issues `cp.async.bulk` (1-D TMA) copies of the
+// child rows, the child's exp(Qt) and the tip tables into a 3-stage shared-memory ring and
+// signals an mbarrier per stage (expect_tx / complete_tx); all four warps consume a stage
+// with one thread per pattern and the q-state vectors in registers, then the stage is handed
+// back with a __syncthreads().  Bytes in flight are decoupled from registers/occupancy, which
+// is what an HBM-bound fp64 kernel with ~100 registers of state needs.
+//
+// Arithmetic contract (reference lines cited per kernel): products are
+// taken in linear space with exact power-of-two rescaling instead of the reference's sum of
+// logs; one log per (internal node, pattern) survives.  Same function up to fp64 rounding
+// (measured: |dLH|/|LH| ~ 1e-16, profiles ~1e-13).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,7 +24,20 @@
 #define TTB_TINY 1e-12        // ttconf.TINY_NUMBER  (treetime/config.py:4)
 #define TTB_SUPERTINY 1e-24   // ttconf.SUPERTINY_NUMBER (treetime/config.py:5)
 #define TTB_BLOCK 128
-#define TTB_CB 4              // children whose exp(Qt) are staged per shared-memory batch
+#define TTB_TILE 128          // patterns per tile = threads per block: one 1 KB row per state
+#define TTB_CB 2              // children per pipeline chunk (binary nodes = one chunk)
+
+// One pipeline chunk of a level kernel: up to TTB_CB children of one node (32 bytes).
+//   postorder: out = slot of the node being computed; src[b] = slot of internal child b or
+//              -1 - tip_row for a tip child; cnode[b] = child node id (row of P).
+//   preorder : out = slot of the PARENT (profile source); src/cnode = children to reconstruct.
+struct TtbChunk {
+  int out;
+  int flags;  // bit0 first chunk of the node, bit1 last chunk, bits 8.. number of children
+  int src[TTB_CB];
+  int cnode[TTB_CB];
+  int pad[2];
+};
 
 struct TtbDev {
   int q;
@@ -36,7 +54,6 @@ struct TtbDev {
   // alignment
   const uint8_t* codes;       // [n_tips][ld]
   const double* code_prof;    // [n_codes][q]
-  const uint32_t* code_mask;  // bit i set <=> code_prof[code][i] != 0
   const double* mult;         // [ld]
   // model
   const double* t;       // [n_nodes]
@@ -46,7 +63,10 @@ struct TtbDev {
   const double* Pi;      // [q]
   const double* mu;      // [1] (device scalar so that a new rate does not invalidate the graph)
   // state
-  double* P;     // [n_nodes][q*q]  exp(Q t_c), P[i*q+j] = Prob(child=i | parent=j)
+  int pq;        // stride of one exp(Qt) matrix in doubles (q*q rounded up to even: 16-byte multiple for TMA)
+  int tu_stride; // stride of one tip table in doubles (n_codes*q rounded up to even)
+  double* TU;    // [n_tips][tu_stride]  tip message table: TU[code*q+j] = sum_i prof[code][i] P[i][j]
+  double* P;     // [n_nodes][pq]  exp(Q t_c), P[i*q+j] = Prob(child=i | parent=j)
   double* S;     // [n_int][q][ld]  marginal_subtree_LH
   double* F;     // [n_int][ld]     marginal_subtree_LH_prefactor
   double* M;     // [n_int][q][ld]  marginal_profile
@@ -58,6 +78,40 @@ struct TtbDev {
   unsigned long long* nd_slots;   // [1024]
   double* results;                // {total_lh, n_diff}
 };
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (global -> shared).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// cp.async.bulk: bytes must be a multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll
@@ -91,10 +145,9 @@ __global__ void expqt_kernel(TtbDev p) {
   if (gid >= p.n_nodes * Q) return;
   const int n = gid / Q, i = gid % Q;
   const double mt = p.mu[0] * p.t[n];
-  double ev[Q];
+  double ev[Q], e[Q];
 #pragma unroll
   for (int k = 0; k < Q; ++k) ev[k] = p.v[i * Q + k];
-  double e[Q];
 #pragma unroll
   for (int k = 0; k < Q; ++k) e[k] = exp(mt * p.eig[k]);
 #pragma unroll
@@ -102,118 +155,169 @@ __global__ void expqt_kernel(TtbDev p) {
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < Q; ++k) acc = fma(ev[k], e[k] * p.vinv[k * Q + j], acc);
-    p.P[(size_t)n * Q * Q + i * Q + j] = fmax(0.0, acc);
+    p.P[(size_t)n * p.pq + i * Q + j] = fmax(0.0, acc);
   }
 }
 
-// Shared-memory carve-up used by the level kernels.
+// Tip message tables: TU[row][code][j] = sum_i prof[code][i] * P_tip[i][j]  (seq2prof +
+// propagate_profile for a leaf, treeanc.py:846-853 + gtr.py:965-995).  One thread per
+// (tip, code, j); terms with prof == 0 are skipped, which is exact.
 template <int Q>
-struct Smem {
-  double* sP;        // [TTB_CB][Q*Q]
-  double* sprof;     // [n_codes][Q]
-  uint32_t* smask;   // [n_codes]
-  double* sred;      // [BLOCK/32]
-  __device__ Smem(unsigned char* base, int n_codes) {
-    sP = reinterpret_cast<double*>(base);
-    sprof = sP + TTB_CB * Q * Q;
-    sred = sprof + n_codes * Q;
-    smask = reinterpret_cast<uint32_t*>(sred + TTB_BLOCK / 32);
+__global__ void tip_table_kernel(TtbDev p, const int* __restrict__ tip_nodes) {
+  const int per = p.n_codes * Q;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)p.n_tips * per) return;
+  const int row = (int)(gid / per), r = (int)(gid % per);
+  const int code = r / Q, j = r % Q;
+  const double* P = p.P + (size_t)tip_nodes[row] * p.pq;
+  double u = 0.0;
+  for (int i = 0; i < Q; ++i) {
+    const double w = p.code_prof[code * Q + i];
+    if (w != 0.0) u = fma(w, P[i * Q + j], u);
   }
-  static size_t bytes(int n_codes) {
-    return sizeof(double) * (TTB_CB * Q * Q + (size_t)n_codes * Q + TTB_BLOCK / 32) + sizeof(uint32_t) * n_codes;
+  p.TU[(size_t)row * p.tu_stride + r] = u;
+}
+
+// ---------------------------------------------------------------------------------------
+// Shared-memory ring of the level kernels.
+// ---------------------------------------------------------------------------------------
+template <int Q>
+struct Pipe {
+  static constexpr int STAGES = (Q <= 8) ? 3 : 2;
+  // per-stage byte offsets (all multiples of 16)
+  int off_P, off_TU, off_codes, off_oidx, stage_bytes;
+  unsigned char* base;
+  uint64_t* bars;
+  __host__ __device__ static int stage_size(int rows, int pq, int tu_stride) {
+    return rows * TTB_TILE * 8 + TTB_CB * pq * 8 + TTB_CB * tu_stride * 8 + 2 * TTB_CB * TTB_TILE;
   }
+  __host__ static size_t smem_bytes(int rows, int pq, int tu_stride) {
+    return 64 + (size_t)STAGES * stage_size(rows, pq, tu_stride);
+  }
+  __device__ Pipe(unsigned char* smem, int rows, int pq, int tu_stride) {
+    bars = reinterpret_cast<uint64_t*>(smem);
+    base = smem + 64;
+    off_P = rows * TTB_TILE * 8;
+    off_TU = off_P + TTB_CB * pq * 8;
+    off_codes = off_TU + TTB_CB * tu_stride * 8;
+    off_oidx = off_codes + TTB_CB * TTB_TILE;
+    stage_bytes = off_oidx + TTB_CB * TTB_TILE;
+  }
+  __device__ double* rows(int s) const { return reinterpret_cast<double*>(base + (size_t)s * stage_bytes); }
+  __device__ double* P(int s) const { return reinterpret_cast<double*>(base + (size_t)s * stage_bytes + off_P); }
+  __device__ double* TU(int s) const { return reinterpret_cast<double*>(base + (size_t)s * stage_bytes + off_TU); }
+  __device__ uint8_t* codes(int s) const { return base + (size_t)s * stage_bytes + off_codes; }
+  __device__ uint8_t* oidx(int s) const { return base + (size_t)s * stage_bytes + off_oidx; }
 };
 
-template <int Q>
-__device__ __forceinline__ void load_code_tables(const TtbDev& p, Smem<Q>& sm) {
-  for (int k = threadIdx.x; k < p.n_codes * Q; k += blockDim.x) sm.sprof[k] = p.code_prof[k];
-  for (int k = threadIdx.x; k < p.n_codes; k += blockDim.x) sm.smask[k] = p.code_mask[k];
-}
-
-// Stage exp(Qt) of children [c0, c0+nb) of a node into shared memory.
-template <int Q>
-__device__ __forceinline__ void stage_P(const TtbDev& p, Smem<Q>& sm, int c0, int nb) {
-  __syncthreads();
-  for (int k = threadIdx.x; k < nb * Q * Q; k += blockDim.x) {
-    const int c = p.child_idx[c0 + k / (Q * Q)];
-    sm.sP[k] = p.P[(size_t)c * Q * Q + (k % (Q * Q))];
-  }
-  __syncthreads();
-}
-
-// Child -> parent message U[j] = sum_i S_c[i] P[i][j]  (gtr.propagate_profile, gtr.py:965-995,
-// without the log) and the child's subtree profile S_c (tips: the 0/1 ambiguity profile of the
-// pattern character, seq2prof, seq_utils.py:207-229; zero entries are skipped, which is exact).
-template <int Q, bool WANT_S>
-__device__ __forceinline__ void child_message(const TtbDev& p, const Smem<Q>& sm, const double* __restrict__ Pc,
-                                              int c, long long a, double (&U)[Q], double (&Sc)[Q]) {
-  const int row = p.tip_row[c];
-  if (row >= 0) {
-    const int code = p.codes[(size_t)row * p.ld + a];
-    uint32_t m = sm.smask[code];
-#pragma unroll
-    for (int j = 0; j < Q; ++j) U[j] = 0.0;
-    if (WANT_S) {
-#pragma unroll
-      for (int i = 0; i < Q; ++i) Sc[i] = sm.sprof[code * Q + i];
-    }
-    while (m) {
-      const int i = __ffs(m) - 1;
-      m &= m - 1;
-      const double w = sm.sprof[code * Q + i];
-#pragma unroll
-      for (int j = 0; j < Q; ++j) U[j] = fma(w, Pc[i * Q + j], U[j]);
-    }
-  } else {
-    const double* __restrict__ s = p.S + (size_t)p.int_slot[c] * Q * p.ld + a;
-    double sc[Q];
-#pragma unroll
-    for (int i = 0; i < Q; ++i) sc[i] = __ldg(s + (size_t)i * p.ld);
-#pragma unroll
-    for (int j = 0; j < Q; ++j) U[j] = sc[0] * Pc[j];
-#pragma unroll
-    for (int i = 1; i < Q; ++i) {
-#pragma unroll
-      for (int j = 0; j < Q; ++j) U[j] = fma(sc[i], Pc[i * Q + j], U[j]);
-    }
-    if (WANT_S) {
-#pragma unroll
-      for (int i = 0; i < Q; ++i) Sc[i] = sc[i];
-    }
-  }
+__device__ __forceinline__ TtbChunk load_chunk(const TtbChunk* __restrict__ c) {
+  const int4* q = reinterpret_cast<const int4*>(c);
+  const int4 a = __ldg(q), b = __ldg(q + 1);
+  TtbChunk r;
+  r.out = a.x; r.flags = a.y; r.src[0] = a.z; r.src[1] = a.w;
+  r.cnode[0] = b.x; r.cnode[1] = b.y; r.pad[0] = b.z; r.pad[1] = b.w;
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------
 // A3-A5: one postorder level.  Reference: postorder_traversal_marginal, treeanc.py:857-878 +
-// normalize_profile(log=True), seq_utils.py:279-307.  Block = (internal node, 128-pattern tile).
-//   X[j] = prod_c U_c[j];  Z = sum_j X[j];  S_n = X/Z;  F_n = sum_c F_c + log Z.
+// normalize_profile(log=True), seq_utils.py:279-307.
+//   X[j] = prod_c U_c[j],  U_c[j] = sum_i S_c[i] P_c[i][j]  (tips: table lookup)
+//   Z = sum_j X[j];  S_n = X/Z;  F_n = sum_c F_c + log Z.
 // Nodes with many children are rescaled by exact powers of two so the product cannot underflow.
+// Block = (run of nodes of the level given by group_ptr, one 128-pattern tile).
+// Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
 template <int Q>
-__global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const int* __restrict__ level_nodes, int tiles) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<Q> sm(smem_raw, p.n_codes);
-  const int node = level_nodes[blockIdx.x / tiles];
-  const long long a = (long long)(blockIdx.x % tiles) * TTB_BLOCK + threadIdx.x;
+__global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+                                                              const int* __restrict__ group_ptr, int tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int ST = Pipe<Q>::STAGES;
+  constexpr int RPC = Q + 1;  // rows per child
+  Pipe<Q> pipe(smem_raw, TTB_CB * RPC, p.pq, p.tu_stride);
+  const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
+  const long long a0 = (long long)tile * TTB_TILE;
+  const int cols = (int)min((long long)TTB_TILE, p.ld - a0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long a = a0 + tid;
   const bool act = a < p.Lp;
-  load_code_tables<Q>(p, sm);
+  if (tid == 0) {
+    for (int s = 0; s < ST; ++s) mbar_init(pipe.bars + s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int k) {  // executed by warp 0
+    const int s = (k - k0) % ST;
+    const TtbChunk c = load_chunk(chunks + k);
+    const int nch = c.flags >> 8;
+    uint32_t bytes = 0;
+    for (int b = 0; b < nch; ++b)
+      bytes += (c.src[b] >= 0) ? (uint32_t)(RPC * cols * 8 + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
+    if (lane == 0) mbar_arrive_expect_tx(pipe.bars + s, bytes);
+    __syncwarp();
+    for (int job = lane; job < nch * (RPC + 1); job += 32) {
+      const int b = job / (RPC + 1), r = job % (RPC + 1);
+      const int src = c.src[b];
+      if (src >= 0) {
+        if (r < Q)
+          tma_load_1d(pipe.rows(s) + (b * RPC + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, pipe.bars + s);
+        else if (r == Q)
+          tma_load_1d(pipe.rows(s) + (b * RPC + Q) * TTB_TILE, p.F + (size_t)src * p.ld + a0, cols * 8, pipe.bars + s);
+        else
+          tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode[b] * p.pq, p.pq * 8, pipe.bars + s);
+      } else {
+        const int row = -1 - src;
+        if (r == 0)
+          tma_load_1d(pipe.codes(s) + b * TTB_TILE, p.codes + (size_t)row * p.ld + a0, cols, pipe.bars + s);
+        else if (r == 1)
+          tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, pipe.bars + s);
+      }
+    }
+  };
+
+  if (warp == 0)
+    for (int k = k0; k < min(k1, k0 + ST - 1); ++k) issue(k);
+
   double X[Q];
-#pragma unroll
-  for (int j = 0; j < Q; ++j) X[j] = 1.0;
   double F = 0.0;
-  int scale = 0;  // X holds the true product times 2^(256*scale)
-  const int cb = p.child_ptr[node], ce = p.child_ptr[node + 1];
-  int seen = 0;
-  for (int c0 = cb; c0 < ce; c0 += TTB_CB) {
-    const int nb = min(TTB_CB, ce - c0);
-    stage_P<Q>(p, sm, c0, nb);
+  int scale = 0, seen = 0;
+  for (int k = k0; k < k1; ++k) {
+    if (warp == 0 && k + ST - 1 < k1) issue(k + ST - 1);
+    const int s = (k - k0) % ST;
+    const TtbChunk c = load_chunk(chunks + k);
+    mbar_wait(pipe.bars + s, ((k - k0) / ST) & 1);
+    if (c.flags & 1) {
+#pragma unroll
+      for (int j = 0; j < Q; ++j) X[j] = 1.0;
+      F = 0.0;
+      scale = 0;
+      seen = 0;
+    }
+    const int nch = c.flags >> 8;
     if (act) {
-      for (int b = 0; b < nb; ++b) {
-        const int c = p.child_idx[c0 + b];
-        double U[Q], dummy[Q];
-        child_message<Q, false>(p, sm, sm.sP + b * Q * Q, c, a, U, dummy);
-        const int slot = p.int_slot[c];
-        if (slot >= 0) F += __ldg(p.F + (size_t)slot * p.ld + a);
+      for (int b = 0; b < nch; ++b) {
+        double U[Q];
+        if (c.src[b] < 0) {
+          const int code = pipe.codes(s)[b * TTB_TILE + tid];
+          const double* tu = pipe.TU(s) + b * p.tu_stride + code * Q;
+#pragma unroll
+          for (int j = 0; j < Q; ++j) U[j] = tu[j];
+        } else {
+          const double* rows = pipe.rows(s) + (b * RPC) * TTB_TILE + tid;
+          const double* Pc = pipe.P(s) + b * p.pq;
+          double sc[Q];
+#pragma unroll
+          for (int i = 0; i < Q; ++i) sc[i] = rows[i * TTB_TILE];
+          F += rows[Q * TTB_TILE];
+#pragma unroll
+          for (int j = 0; j < Q; ++j) U[j] = sc[0] * Pc[j];
+#pragma unroll
+          for (int i = 1; i < Q; ++i)
+#pragma unroll
+            for (int j = 0; j < Q; ++j) U[j] = fma(sc[i], Pc[i * Q + j], U[j]);
+        }
 #pragma unroll
         for (int j = 0; j < Q; ++j) X[j] *= U[j];
         if (++seen > 2) {  // polytomy: keep the running product in range (exact scaling)
@@ -227,27 +331,19 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const i
           }
         }
       }
+      if (c.flags & 2) {
+        double Z = X[0];
+#pragma unroll
+        for (int j = 1; j < Q; ++j) Z += X[j];
+        const double inv = 1.0 / Z;
+        double* __restrict__ so = p.S + (size_t)c.out * Q * p.ld + a;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) so[(size_t)j * p.ld] = X[j] * inv;
+        p.F[(size_t)c.out * p.ld + a] = F + (log(Z) - scale * (256.0 * 0.693147180559945309417232121458));
+      }
     }
+    __syncthreads();  // stage s may be refilled
   }
-  if (act) {
-    double Z = X[0];
-#pragma unroll
-    for (int j = 1; j < Q; ++j) Z += X[j];
-    const double inv = 1.0 / Z;
-    const int slot = p.int_slot[node];
-    double* __restrict__ s = p.S + (size_t)slot * Q * p.ld + a;
-#pragma unroll
-    for (int j = 0; j < Q; ++j) s[(size_t)j * p.ld] = X[j] * inv;
-    p.F[(size_t)slot * p.ld + a] = F + (log(Z) - scale * (256.0 * 0.693147180559945309417232121458));
-  }
-}
-
-__device__ __forceinline__ int argmax_first(const double* x, int q) {
-  int best = 0;
-  double bv = x[0];
-  for (int i = 1; i < q; ++i)
-    if (x[i] > bv) { bv = x[i]; best = i; }
-  return best;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -351,42 +447,115 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // ---------------------------------------------------------------------------------------
 // A6-A7: one preorder level.  Reference: preorder_traversal_marginal, treeanc.py:887-930 +
 // GTR.evolve (gtr.py:997-1025) + prof2seq argmax (seq_utils.py:271).
-// Block = (parent p, 128-pattern tile); the parent's marginal profile is read once and
-// reused for all its children.  Per child c:
-//   O_c   ~ max(1e-12, profile_p) / U_c                     (outside message, not stored:
-//                                                            it is recomputed on demand by
-//                                                            fetch / branch kernels)
+// Block = (run of parents of the level, one 128-pattern tile); the parent's marginal profile is
+// fetched once (first chunk) and reused for all its children.  Per child c:
+//   O_c   ~ max(1e-12, profile_p) / U_c     (outside message; NOT stored: recomputed on demand
+//                                            by the fetch / branch kernels from resident data)
 //   msg_i = sum_j O_c[j] P_c[i][j];  profile_c = normalize(S_c * msg);  state = argmax.
-// Tips are skipped unless TIPS (reconstruct_tip_states).
+// Tips take part only with TIPS (reconstruct_tip_states).
+// Stage rows: [0, Q) parent profile, child b -> rows [Q + b*Q, Q + (b+1)*Q) = S_c.
 // ---------------------------------------------------------------------------------------
 template <int Q, bool TIPS>
-__global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const int* __restrict__ level_parents, int tiles,
-                                                             int count_diff) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<Q> sm(smem_raw, p.n_codes);
-  const int pn = level_parents[blockIdx.x / tiles];
-  const long long a = (long long)(blockIdx.x % tiles) * TTB_BLOCK + threadIdx.x;
+__global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+                                                             const int* __restrict__ group_ptr, int tiles, int count_diff) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int ST = Pipe<Q>::STAGES;
+  Pipe<Q> pipe(smem_raw, Q + TTB_CB * Q, p.pq, p.tu_stride);
+  const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
+  const long long a0 = (long long)tile * TTB_TILE;
+  const int cols = (int)min((long long)TTB_TILE, p.ld - a0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long a = a0 + tid;
   const bool act = a < p.Lp;
-  load_code_tables<Q>(p, sm);
-  double Mp[Q];
-  if (act) {
-    const double* __restrict__ m = p.M + (size_t)p.int_slot[pn] * Q * p.ld + a;
-#pragma unroll
-    for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, __ldg(m + (size_t)j * p.ld));
+  if (tid == 0) {
+    for (int s = 0; s < ST; ++s) mbar_init(pipe.bars + s, 1);
+    mbar_fence_init();
   }
+  __syncthreads();
+
+  auto issue = [&](int k) {  // executed by warp 0
+    const int s = (k - k0) % ST;
+    const TtbChunk c = load_chunk(chunks + k);
+    const int nch = c.flags >> 8;
+    const bool first = c.flags & 1;
+    uint32_t bytes = first ? (uint32_t)(Q * cols * 8) : 0u;
+    for (int b = 0; b < nch; ++b)
+      bytes += (c.src[b] >= 0) ? (uint32_t)(Q * cols * 8 + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
+    if (lane == 0) mbar_arrive_expect_tx(pipe.bars + s, bytes);
+    __syncwarp();
+    if (first)
+      for (int r = lane; r < Q; r += 32)
+        tma_load_1d(pipe.rows(s) + r * TTB_TILE, p.M + ((size_t)c.out * Q + r) * p.ld + a0, cols * 8, pipe.bars + s);
+    for (int job = lane; job < nch * (Q + 2); job += 32) {
+      const int b = job / (Q + 2), r = job % (Q + 2);
+      const int src = c.src[b];
+      if (r == Q + 1) {
+        tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode[b] * p.pq, p.pq * 8, pipe.bars + s);
+      } else if (src >= 0) {
+        if (r < Q)
+          tma_load_1d(pipe.rows(s) + (Q + b * Q + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, pipe.bars + s);
+        else
+          tma_load_1d(pipe.oidx(s) + b * TTB_TILE, p.idx + (size_t)src * p.ld + a0, cols, pipe.bars + s);
+      } else if (TIPS) {
+        const int row = -1 - src;
+        if (r == 0)
+          tma_load_1d(pipe.codes(s) + b * TTB_TILE, p.codes + (size_t)row * p.ld + a0, cols, pipe.bars + s);
+        else if (r == 1)
+          tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, pipe.bars + s);
+        else if (r == 2)
+          tma_load_1d(pipe.oidx(s) + b * TTB_TILE, p.idxtip + (size_t)row * p.ld + a0, cols, pipe.bars + s);
+      }
+    }
+  };
+
+  if (warp == 0)
+    for (int k = k0; k < min(k1, k0 + ST - 1); ++k) issue(k);
+
+  double Mp[Q];
   unsigned int ndiff = 0;
-  const int cb = p.child_ptr[pn], ce = p.child_ptr[pn + 1];
-  for (int c0 = cb; c0 < ce; c0 += TTB_CB) {
-    const int nb = min(TTB_CB, ce - c0);
-    stage_P<Q>(p, sm, c0, nb);
+  for (int k = k0; k < k1; ++k) {
+    if (warp == 0 && k + ST - 1 < k1) issue(k + ST - 1);
+    const int s = (k - k0) % ST;
+    const TtbChunk c = load_chunk(chunks + k);
+    mbar_wait(pipe.bars + s, ((k - k0) / ST) & 1);
+    const int nch = c.flags >> 8;
     if (act) {
-      for (int b = 0; b < nb; ++b) {
-        const int c = p.child_idx[c0 + b];
-        const int row = p.tip_row[c];
-        if (!TIPS && row >= 0) continue;
-        const double* Pc = sm.sP + b * Q * Q;
+      if (c.flags & 1) {
+        const double* m = pipe.rows(s) + tid;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, m[j * TTB_TILE]);
+      }
+      for (int b = 0; b < nch; ++b) {
+        const int src = c.src[b];
+        const double* Pc = pipe.P(s) + b * p.pq;
         double U[Q], Sc[Q], O[Q];
-        child_message<Q, true>(p, sm, Pc, c, a, U, Sc);
+        double* __restrict__ out;
+        uint8_t* ip;
+        if (TIPS && src < 0) {
+          const int row = -1 - src;
+          const int code = pipe.codes(s)[b * TTB_TILE + tid];
+          const double* tu = pipe.TU(s) + b * p.tu_stride + code * Q;
+#pragma unroll
+          for (int j = 0; j < Q; ++j) {
+            U[j] = tu[j];
+            Sc[j] = __ldg(p.code_prof + code * Q + j);
+          }
+          out = p.Mtip + (size_t)row * Q * p.ld + a;
+          ip = p.idxtip + (size_t)row * p.ld + a;
+        } else {
+          const double* rows = pipe.rows(s) + (Q + b * Q) * TTB_TILE + tid;
+#pragma unroll
+          for (int i = 0; i < Q; ++i) Sc[i] = rows[i * TTB_TILE];
+#pragma unroll
+          for (int j = 0; j < Q; ++j) U[j] = Sc[0] * Pc[j];
+#pragma unroll
+          for (int i = 1; i < Q; ++i)
+#pragma unroll
+            for (int j = 0; j < Q; ++j) U[j] = fma(Sc[i], Pc[i * Q + j], U[j]);
+          out = p.M + (size_t)src * Q * p.ld + a;
+          ip = p.idx + (size_t)src * p.ld + a;
+        }
         outgroup_message<Q>(Mp, U, O);
         double prof[Q];
         double z = 0.0;
@@ -399,16 +568,6 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const in
           z += prof[i];
         }
         const double inv = 1.0 / z;
-        double* __restrict__ out;
-        uint8_t* ip;
-        if (row >= 0) {
-          out = p.Mtip + (size_t)row * Q * p.ld + a;
-          ip = p.idxtip + (size_t)row * p.ld + a;
-        } else {
-          const int slot = p.int_slot[c];
-          out = p.M + (size_t)slot * Q * p.ld + a;
-          ip = p.idx + (size_t)slot * p.ld + a;
-        }
         int best = 0;
         double bv = -1.0;
 #pragma unroll
@@ -417,14 +576,15 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const in
           out[(size_t)i * p.ld] = x;
           if (x > bv) { bv = x; best = i; }
         }
-        if (count_diff) ndiff += (*ip != (uint8_t)best);
+        if (count_diff) ndiff += (pipe.oidx(s)[b * TTB_TILE + tid] != (uint8_t)best);
         *ip = (uint8_t)best;
       }
     }
+    __syncthreads();  // stage s may be refilled
   }
   if (count_diff) {
     ndiff = __reduce_add_sync(0xffffffffu, ndiff);
-    if ((threadIdx.x & 31) == 0 && ndiff) atomicAdd(p.nd_slots + (blockIdx.x & 1023), (unsigned long long)ndiff);
+    if (lane == 0 && ndiff) atomicAdd(p.nd_slots + (blockIdx.x & 1023), (unsigned long long)ndiff);
   }
 }
 
@@ -473,7 +633,7 @@ __device__ __forceinline__ void branch_profiles(const TtbDev& p, int n, int kind
   const double* m = p.M + (size_t)p.int_slot[up] * Q * p.ld + a;
 #pragma unroll
   for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, m[(size_t)j * p.ld]);
-  const double* Pc = p.P + (size_t)n * Q * Q;
+  const double* Pc = p.P + (size_t)n * p.pq;
 #pragma unroll
   for (int j = 0; j < Q; ++j) {
     double u = 0.0;
@@ -591,7 +751,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) counts_kernel(TtbDev p, int chunk, 
   const double m = act ? p.mult[a] : 0.0;
   for (int n = n0; n < n1; ++n) {
     __syncthreads();
-    for (int k = threadIdx.x; k < Q * Q; k += TTB_BLOCK) sPc[k] = p.P[(size_t)n * Q * Q + k] + TTB_SUPERTINY;
+    for (int k = threadIdx.x; k < Q * Q; k += TTB_BLOCK) sPc[k] = p.P[(size_t)n * p.pq + k] + TTB_SUPERTINY;
     __syncthreads();
     if (!act) continue;
     double pp[Q], pc[Q];

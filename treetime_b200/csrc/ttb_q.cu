@@ -9,19 +9,33 @@
 namespace {
 constexpr int Q = TTB_Q;
 
+size_t post_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(TTB_CB * (Q + 1), d.pq, d.tu_stride); }
+size_t pre_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(Q + TTB_CB * Q, d.pq, d.tu_stride); }
+
+int prepare_q(const TtbDev& d) {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(post_level_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d))) != cudaSuccess) return (int)e;
+  return 0;
+}
+
 int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
   const TtbDev& d = pl.d;
   const int tiles = pl.tiles;
-  const size_t smem = Smem<Q>::bytes(d.n_codes);
   int nk = 0;
   if (ev) cudaEventRecord(ev[0], s);
   const int nthr = d.n_nodes * Q;
   expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
-  ++nk;
+  const long long ntab = (long long)d.n_tips * d.n_codes * Q;
+  tip_table_kernel<Q><<<(unsigned)((ntab + 255) / 256), 256, 0, s>>>(d, pl.d_tip_nodes);
+  nk += 2;
   if (ev) { cudaEventRecord(ev[1], s); pk[0] = nk; }
+  const size_t psm = post_smem(d);
   for (int l = 0; l < pl.n_post_levels; ++l) {
-    const TtbLevel& L = pl.post_levels[l];
-    post_level_kernel<Q><<<(unsigned)((long long)L.count * tiles), TTB_BLOCK, smem, s>>>(d, pl.d_post_nodes + L.begin, tiles);
+    const TtbLevelLaunch& L = pl.post_levels[l];
+    post_level_kernel<Q><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, psm, s>>>(d, pl.d_post_chunks,
+                                                                                         pl.d_post_group_ptr + L.group_off, tiles);
     ++nk;
   }
   if (ev) { cudaEventRecord(ev[2], s); pk[1] = nk - pk[0]; }
@@ -33,13 +47,14 @@ int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   }
   if (ev) { cudaEventRecord(ev[3], s); pk[2] = nk - pk[0] - pk[1]; }
   if (!pl.lh_only) {
+    const size_t rsm = pre_smem(d);
     for (int l = 0; l < pl.n_pre_levels; ++l) {
-      const TtbLevel& L = pl.pre_levels[l];
-      const unsigned grid = (unsigned)((long long)L.count * tiles);
+      const TtbLevelLaunch& L = pl.pre_levels[l];
+      const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
       if (pl.tips)
-        pre_level_kernel<Q, true><<<grid, TTB_BLOCK, smem, s>>>(d, pl.d_pre_nodes + L.begin, tiles, pl.count_diff);
+        pre_level_kernel<Q, true><<<grid, TTB_BLOCK, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
       else
-        pre_level_kernel<Q, false><<<grid, TTB_BLOCK, smem, s>>>(d, pl.d_pre_nodes + L.begin, tiles, pl.count_diff);
+        pre_level_kernel<Q, false><<<grid, TTB_BLOCK, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
       ++nk;
     }
   }
@@ -69,4 +84,4 @@ void counts_q(const TtbDev& d, int tiles, int chunks, int chunk, double* partial
 
 #define TTB_CAT2(a, b) a##b
 #define TTB_CAT(a, b) TTB_CAT2(a, b)
-extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {enqueue_pass_q, fetch_node_q, branch_eval_q, counts_q};
+extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {prepare_q, enqueue_pass_q, fetch_node_q, branch_eval_q, counts_q};

@@ -5,24 +5,31 @@
 #include <cuda_runtime.h>
 #include "ttb_kernels.cuh"
 
-struct TtbLevel {
-  int begin, count;
+// One level launch: blocks = n_groups x tiles; group g covers chunks
+// [group_ptr[group_off + g], group_ptr[group_off + g + 1]).
+struct TtbLevelLaunch {
+  int group_off, n_groups;
 };
 
 struct TtbPassPlan {
   TtbDev d;
   int tiles;
-  const int* d_post_nodes;
-  const TtbLevel* post_levels;
+  const int* d_tip_nodes;          // tip row -> node id
+  const TtbChunk* d_post_chunks;
+  const int* d_post_group_ptr;
+  const TtbLevelLaunch* post_levels;
   int n_post_levels;
-  const int* d_pre_nodes;      // parents list matching `tips`
-  const TtbLevel* pre_levels;
+  const TtbChunk* d_pre_chunks;    // schedule matching `tips`
+  const int* d_pre_group_ptr;
+  const TtbLevelLaunch* pre_levels;
   int n_pre_levels;
   bool lh_only, tips;
   int count_diff;
 };
 
 struct TtbQOps {
+  // one-time per process: opt in to the dynamic shared memory the level kernels need; returns 0 or a cudaError
+  int (*prepare)(const TtbDev& d);
   // enqueue every kernel of one pass; optional events ev[6] bracket the phases; returns #kernels
   int (*enqueue_pass)(const TtbPassPlan& plan, cudaStream_t s, cudaEvent_t* ev, int* phase_kernels);
   void (*fetch_node)(const TtbDev& d, int tiles, int node, int which, double* out, cudaStream_t s);
