@@ -33,6 +33,10 @@ def sha(a):
 def gtr_params(gtr):
     d = dict(gtr_W=np.array(gtr.W), gtr_Pi=np.array(gtr.Pi), gtr_mu=np.array(gtr.mu), gtr_alphabet=np.array(gtr.alphabet),
              gtr_eigenvals=np.array(gtr.eigenvals), gtr_v=np.array(gtr.v), gtr_v_inv=np.array(gtr.v_inv))
+    chars = sorted(gtr.profile_map.keys())
+    d['gtr_prof_chars'] = np.array(chars)
+    d['gtr_prof_table'] = np.array([gtr.profile_map[c] for c in chars], dtype=float)
+    d['gtr_ambiguous'] = np.array(gtr.ambiguous if gtr.ambiguous is not None else '')
     if getattr(gtr, 'is_site_specific', False):
         d['gtr_rate_scale'] = np.array(gtr.rate_scale)
         d['gtr_approximate'] = np.array(gtr.approximate)
@@ -42,6 +46,7 @@ def gtr_params(gtr):
 def run_case(name, newick, aln, gtr, store_every=1, reconstruct_tips=False, optimize=False, infer_gtr=False,
              n_bl=6, compress=True, store_inputs=True, extra=None, cseq_as_idx=False):
     t0 = time.time()
+    pre = gtr_params(gtr)       # profile map / ambiguous as the user built the model (before extend_profile)
     tt = refenv.reference_treeanc(newick, aln, gtr, rng_seed=1, compress=compress)
     topo, flat, g = flatten_treeanc(tt)
     N1 = tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=reconstruct_tips)
@@ -51,6 +56,7 @@ def run_case(name, newick, aln, gtr, store_every=1, reconstruct_tips=False, opti
                total_LH=np.array(tt.tree.total_sequence_LH), reconstruct_tips=np.array(reconstruct_tips),
                compress=np.array(compress), t=flat['t'])
     out.update(gtr_params(tt.gtr))
+    out['gtr_prof_chars'] = pre['gtr_prof_chars']; out['gtr_prof_table'] = pre['gtr_prof_table']; out['gtr_ambiguous'] = pre['gtr_ambiguous']
     if store_inputs:
         out['newick'] = np.array(newick)
         out['aln_names'] = np.array(sorted(aln))

@@ -1,0 +1,142 @@
+"""GPU: the TreeAnc mirror on the real CUDA engine against golden vectors of the unmodified
+reference (tests/golden) -- the tests read like the reference's own (test/test_treetime.py)."""
+import numpy as np
+import pytest
+
+import golden_util as G
+from treetime_b200.treeanc import TreeAnc
+
+pytestmark = pytest.mark.gpu
+
+LH_RTOL = 1e-9       # BASELINE.json: total log-LH within 1e-9 relative (fp64)
+PROF_ATOL = 1e-6     # BASELINE.json: marginal profiles within 1e-6
+
+
+def gpu_from_golden(z, **kw):
+    return TreeAnc(tree=str(z['newick']), aln=G.alignment(z), gtr=G.model(z), rng_seed=1, **kw)
+
+
+def check(tt, z):
+    import util
+    tips = bool(z['reconstruct_tips'])
+    n1 = tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips)
+    assert n1 == int(z['N_diff_first'])
+    tot = float(z['total_LH'])
+    assert abs(tt.sequence_LH() - tot) <= LH_RTOL * abs(tot)
+    assert np.allclose(tt.tree.sequence_LH, z['sequence_LH'], rtol=1e-11, atol=1e-11)
+    nodes = list(tt.tree.find_clades())
+    worst = 0.0
+    for i in z['stored_nodes']:
+        n = nodes[i]
+        worst = max(worst, np.abs(n.marginal_subtree_LH - z['subtree_%d' % i]).max())
+        if i > 0:
+            worst = max(worst, np.abs(n.marginal_outgroup_LH - z['outgroup_%d' % i]).max())
+        if 'profile_%d' % i in z.files:
+            worst = max(worst, np.abs(n.marginal_profile - z['profile_%d' % i]).max())
+    assert worst < PROF_ATOL
+    for n, s in zip(nodes, z['cseq']):
+        c = n.cseq
+        if c is None:
+            assert str(s) == ''
+            continue
+        bad = np.array(list(str(s))) != c
+        if bad.any():       # identical except at exact ties
+            assert util.tie_mask(n.marginal_profile)[bad].all(), n.name
+    assert tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips) == int(z['N_diff_second'])
+    return nodes, worst
+
+
+@pytest.mark.parametrize('name', G.SMALL)
+def test_gpu_reconstruction_matches_reference_golden(name):
+    z = G.load(name)
+    tt = gpu_from_golden(z)
+    nodes, worst = check(tt, z)
+    for k, i in enumerate(z['bl_nodes']):
+        bl = tt.optimal_marginal_branch_length(nodes[i])
+        assert abs(bl - z['bl_opt'][k]) <= 1e-6 * z['bl_opt'][k] + 1e-12
+    print('%s: rel dLH=%.1e  max|dprofile|=%.1e' % (name, abs(tt.sequence_LH() - float(z['total_LH'])) / abs(float(z['total_LH'])), worst))
+
+
+def test_gpu_known_answer_lh_normalisation():
+    """The reference's own KAT (test/test_treetime.py:137-155): sum over all 4^3 patterns of exp(LH) = 1."""
+    z = G.load('kat3')
+    tt = gpu_from_golden(z)
+    tt.reconstruct_anc('ml', marginal=True, debug=True)
+    assert abs(np.exp(tt.tree.sequence_LH).sum() - 1.0) < 1e-6
+    assert abs(tt.tree.total_sequence_LH - (-495.7525153086474)) < 1e-9 * 495.75
+    tt.optimize_branch_len()
+
+
+@pytest.mark.parametrize('name', ['nuc40', 'poly70'])
+def test_gpu_optimize_tree_marginal(name):
+    z = G.load(name)
+    tt = gpu_from_golden(z)
+    tt.optimize_tree(branch_length_mode='marginal', max_iter=2, infer_gtr=False, prune_short=False)
+    bl = np.array([n.branch_length for n in tt.tree.find_clades()])
+    ref = z['opt_branch_length']
+    # Brent tolerance of the sweeps is 1e-2 / 1e-4 relative in s = sqrt(t): the iterates agree far tighter
+    assert np.allclose(bl[1:], ref[1:], rtol=1e-6, atol=1e-10), np.abs(bl[1:] - ref[1:]).max()
+    assert abs(tt.sequence_LH() - float(z['opt_total_LH'])) <= 1e-9 * abs(float(z['opt_total_LH']))
+
+
+def test_gpu_infer_gtr_and_rate():
+    z = G.load('nuc40')
+    tt = gpu_from_golden(z)
+    tt.optimize_tree(branch_length_mode='marginal', max_iter=2, infer_gtr=False, prune_short=False)
+    tt.infer_gtr(marginal=True)
+    assert np.allclose(tt.gtr.W, z['inferred_W'], rtol=1e-6) and np.allclose(tt.gtr.Pi, z['inferred_Pi'], rtol=1e-6)
+    tt.optimize_gtr_rate()
+    assert tt.gtr.mu > 0
+
+
+@pytest.mark.parametrize('name', G.BIG)
+def test_gpu_full_size_configs(name):
+    """BASELINE.json configs[0] and configs[1] at full size against the reference's output."""
+    z = G.load(name)
+    tree, aln, g, sha = G.regenerate_big(name)
+    assert sha == str(z['input_sha'])
+    tt = TreeAnc(tree=tree, aln=aln, gtr=g, rng_seed=1)
+    assert tt.infer_ancestral_sequences(marginal=True) == int(z['N_diff_first'])
+    tot = float(z['total_LH'])
+    assert abs(tt.sequence_LH() - tot) <= LH_RTOL * abs(tot)
+    assert np.allclose(tt.tree.sequence_LH, z['sequence_LH'], rtol=1e-11, atol=1e-10)
+    nodes = list(tt.tree.find_clades())
+    if 'cseq_idx' in z.files:
+        internal = [i for i, n in enumerate(nodes) if not n.is_terminal()]
+        idx = tt._engine.all_seq_idx()
+        ref = z['cseq_idx'][internal]
+        mism = int((idx != ref).sum())
+        assert mism <= 5, mism                 # only exact ties may differ
+        if mism:
+            import util
+            for r, c in zip(*np.nonzero(idx != ref)):
+                assert util.tie_mask(nodes[internal[r]].marginal_profile)[c]
+    else:
+        for n, s in zip(nodes, z['cseq']):
+            if not n.is_terminal():
+                assert ''.join(n.cseq) == str(s)
+    print('%s: rel dLH = %.2e' % (name, abs(tt.sequence_LH() - tot) / abs(tot)))
+
+
+def test_gpu_one_vs_two_engine_shards_agree():
+    """Pattern sharding on one GPU: two engines, half the patterns each, partial sums add up."""
+    import util
+    from treetime_b200 import synth
+    tree = synth.random_tree(80, seed=31, mean_bl=0.01)
+    topo, flat, g = util.make_flat(tree, util.nuc_gtr(), 700, 31, amb_frac=0.01)
+    full = util.engine_for(flat, g)
+    full.marginal()
+    tot, nd = full.results()
+    L = flat['multiplicity'].shape[0]
+    parts = []
+    for lo, hi in ((0, L // 2), (L // 2, L)):
+        f = dict(flat); f['tip_codes'] = np.ascontiguousarray(flat['tip_codes'][:, lo:hi]); f['multiplicity'] = flat['multiplicity'][lo:hi]
+        e = util.engine_for(f, g)
+        e.marginal()
+        parts.append((e, e.results()))
+    assert abs(sum(p[1][0] for p in parts) - tot) <= 1e-12 * abs(tot)
+    assert sum(p[1][1] for p in parts) == nd
+    n = int(flat['child_idx'][0])
+    whole = full.node_array(n, 1)
+    halves = np.vstack([p[0].node_array(n, 1) for p in parts])
+    assert np.array_equal(whole, halves)

@@ -1,0 +1,126 @@
+"""CPU: the TreeAnc mirror's host logic (flattening, N_diff rules, lazy node views, lock-step
+Brent, damping, GTR inference) with the oracle-backed test engine, checked against golden
+vectors from the unmodified reference -- and live against the reference when it is present."""
+import numpy as np
+import pytest
+
+import golden_util as G
+import oracle_engine
+from treetime_b200.treeanc import TreeAnc, MissingDataError, UnknownMethodError
+
+
+def mirror_from_golden(z, **kw):
+    return TreeAnc(tree=str(z['newick']), aln=G.alignment(z), gtr=G.model(z), rng_seed=1,
+                   engine_factory=oracle_engine.factory, **kw)
+
+
+def check_against_golden(tt, z, exact=True, prof_tol=0.0, lh_rtol=0.0):
+    tips = bool(z['reconstruct_tips'])
+    n1 = tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips)
+    assert n1 == int(z['N_diff_first'])
+    assert np.array_equal(tt.data.multiplicity(), z['multiplicity'])
+    assert np.allclose(tt.tree.sequence_LH, z['sequence_LH'], rtol=max(lh_rtol, 1e-15), atol=1e-12 if not exact else 0)
+    assert abs(tt.sequence_LH() - float(z['total_LH'])) <= max(lh_rtol, 1e-15) * abs(float(z['total_LH']))
+    nodes = list(tt.tree.find_clades())
+    assert [n.name for n in nodes] == [str(s) for s in z['node_names']]
+    for i in z['stored_nodes']:
+        n = nodes[i]
+        assert np.abs(n.marginal_subtree_LH - z['subtree_%d' % i]).max() <= prof_tol
+        if i > 0:
+            assert np.abs(n.marginal_outgroup_LH - z['outgroup_%d' % i]).max() <= prof_tol
+        if 'profile_%d' % i in z.files:
+            assert np.abs(n.marginal_profile - z['profile_%d' % i]).max() <= prof_tol
+    for n, s in zip(nodes, z['cseq']):
+        c = n.cseq
+        if c is None:
+            assert str(s) == ''
+        elif exact:
+            assert ''.join(c) == str(s)
+        else:
+            bad = np.array(list(str(s))) != c
+            if bad.any():
+                import util
+                assert util.tie_mask(n.marginal_profile)[bad].all()
+    assert tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips) == int(z['N_diff_second'])
+    return nodes
+
+
+@pytest.mark.parametrize('name', ['kat3', 'nuc40', 'nuc40_tips', 'poly70', 'aa16_jtt92', 'aa16_q22'])
+def test_mirror_reconstruction_matches_reference_golden(name):
+    z = G.load(name)
+    tt = mirror_from_golden(z)
+    nodes = check_against_golden(tt, z)
+    for k, i in enumerate(z['bl_nodes']):
+        bl = tt.optimal_marginal_branch_length(nodes[i])
+        assert abs(bl - z['bl_opt'][k]) <= 1e-9 * z['bl_opt'][k]
+        bl2 = tt.optimal_marginal_branch_length(nodes[i], tol=1e-2)
+        assert abs(bl2 - z['bl_opt_tol1e-2'][k]) <= 1e-9 * z['bl_opt_tol1e-2'][k]
+
+
+@pytest.mark.parametrize('name', ['nuc40', 'poly70'])
+def test_mirror_optimize_tree_marginal_matches_reference(name):
+    """optimize_tree(branch_length_mode='marginal', max_iter=2): batched lock-step Brent + damping +
+    the double update across a bifurcating root reproduce the reference's branch lengths."""
+    z = G.load(name)
+    tt = mirror_from_golden(z)
+    tt.optimize_tree(branch_length_mode='marginal', max_iter=2, infer_gtr=False, prune_short=False)
+    bl = np.array([n.branch_length for n in tt.tree.find_clades()])
+    assert np.allclose(bl[1:], z['opt_branch_length'][1:], rtol=1e-9, atol=1e-12)
+    assert abs(tt.sequence_LH() - float(z['opt_total_LH'])) <= 1e-11 * abs(float(z['opt_total_LH']))
+
+
+def test_mirror_infer_gtr_matches_reference():
+    z = G.load('nuc40')
+    tt = mirror_from_golden(z)
+    tt.optimize_tree(branch_length_mode='marginal', max_iter=2, infer_gtr=False, prune_short=False)
+    tt.infer_gtr(marginal=True)
+    assert np.allclose(tt.gtr.W, z['inferred_W'], rtol=1e-9) and np.allclose(tt.gtr.Pi, z['inferred_Pi'], rtol=1e-9)
+    assert np.isclose(tt.gtr.mu, float(z['inferred_mu']), rtol=1e-12)
+
+
+def test_mirror_big_config1_regenerated_inputs():
+    """BASELINE.json configs[0] at full size: inputs regenerated from seeds (checksum-pinned)."""
+    z = G.load('cfg1_200x1400')
+    tree, aln, g, sha = G.regenerate_big('cfg1')
+    assert sha == str(z['input_sha'])
+    tt = TreeAnc(tree=tree, aln=aln, gtr=g, rng_seed=1, engine_factory=oracle_engine.factory)
+    assert tt.infer_ancestral_sequences(marginal=True) == int(z['N_diff_first'])
+    assert np.allclose(tt.tree.sequence_LH, z['sequence_LH'], rtol=1e-13)
+    assert abs(tt.sequence_LH() - float(z['total_LH'])) < 1e-12 * abs(float(z['total_LH']))
+    for n, s in zip(tt.tree.find_clades(), z['cseq']):
+        if not n.is_terminal():
+            assert ''.join(n.cseq) == str(s)
+
+
+def test_error_behaviour_mirrors_reference():
+    z = G.load('nuc40')
+    tt = mirror_from_golden(z)
+    with pytest.raises(UnknownMethodError):
+        tt.infer_ancestral_sequences(method='nonsense', marginal=True)
+    with pytest.raises(UnknownMethodError):
+        tt.optimize_tree(branch_length_mode='nonsense')
+    with pytest.raises(Exception):
+        tt.marginal_branch_profile(tt.tree.root)
+    with pytest.raises(TypeError):
+        TreeAnc(tree=None, aln=G.alignment(z))
+    with pytest.raises(MissingDataError):
+        TreeAnc(tree='(A:0.1,B:0.2);', aln={'A': 'ACGT', 'B': 'ACGT'}, engine_factory=oracle_engine.factory)
+    # a tree whose tips are not in the alignment (treeanc.py:419-430)
+    with pytest.raises(MissingDataError):
+        TreeAnc(tree='((x:0.1,y:0.1):0.1,(z:0.1,w:0.2):0.1);', aln=G.alignment(z), engine_factory=oracle_engine.factory)
+    # sample_from_profile='root' consumes the host RNG like the reference (one uniform per pattern)
+    tt.infer_ancestral_sequences(marginal=True, sample_from_profile='root')
+    assert tt.tree.root.cseq.shape[0] == tt.data.compressed_length
+
+
+def test_reconstructed_alignment_and_mutations():
+    z = G.load('nuc40')
+    tt = mirror_from_golden(z)
+    aln = tt.get_reconstructed_alignment()
+    assert set(aln) == {str(s) for s in z['node_names']}
+    L = tt.data.full_length
+    assert all(len(s) == L for s in aln.values())
+    for n in tt.tree.find_clades():
+        if n.up is not None and not n.is_terminal():
+            for a, pos, d in n.mutations:
+                assert aln[n.up.name][pos] == a and aln[n.name][pos] == d and a != d

@@ -83,8 +83,13 @@ class SequenceData(object):
         if any(r.shape[0] != L for r in rows):
             raise ValueError('SequenceData: sequences differ in length')
         self.matrix = np.vstack(rows) if len(rows) > 1 else rows[0][None, :].copy()
-        if fill_overhangs and ambiguous is not None:
-            self._fill_overhangs(ord(ambiguous))
+        if fill_overhangs:
+            # with no ambiguous character the reference assigns None into a 'U1' array, which
+            # numpy stores as 'N' (seq_utils.py:196-202): reproduce that
+            self._fill_overhangs(ord(ambiguous) if ambiguous is not None else ord('N'))
+        if self.ambiguous is None:                      # sequence_data.py:322-323
+            nuc = np.isin(self.matrix, np.frombuffer(b'acgtACGT-N', dtype=np.uint8)).sum()
+            self.ambiguous = 'N' if nuc > 0.9 * self.matrix.size else 'X'
         self.full_length = int(sequence_length) if sequence_length else L
         if self.full_length < L:
             raise AttributeError('SequenceData: specified sequence length is smaller than alignment length!')
