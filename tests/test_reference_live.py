@@ -44,3 +44,128 @@ def test_mirror_live_against_reference_including_optimize_and_gtr():
     assert np.isclose(rt.sequence_LH(), mt.sequence_LH(), rtol=1e-12)
     rt.optimize_gtr_rate(); mt.optimize_gtr_rate()
     assert np.isclose(rt.gtr.mu, mt.gtr.mu, rtol=1e-9)
+
+
+def _pair(seed=33, n=30, L=300, **kw):
+    refenv.activate()
+    import oracle_engine
+    from treetime import GTR as RG, TreeAnc as RefTreeAnc
+    from treetime_b200 import synth
+    from treetime_b200.dropin import accelerate
+    from treetime_b200.gtr import GTR
+    pi = np.array([.3, .2, .2, .29, .01])
+    T = synth.random_tree(n, seed=seed, mean_bl=0.01)
+    g = GTR.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc')
+    idx = synth.evolve_alignment(T, L, g.Pi, g.W, seed=seed)
+    aln = synth.sprinkle_ambiguous({k: g.alphabet[v] for k, v in idx.items()}, 0.02, 'N-R', seed=3)
+    mk = lambda: RG.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc')  # noqa: E731
+    rt = refenv.reference_treeanc(T.to_newick(), aln, mk(), rng_seed=1, **kw)
+    # the drop-in: same constructor as the reference's TreeAnc, engine injected for the CPU test
+    from io import StringIO
+    from Bio import Phylo
+    from Bio.Align import MultipleSeqAlignment
+    from Bio.SeqRecord import SeqRecord
+    from Bio.Seq import Seq
+    B200TreeAnc = accelerate(RefTreeAnc)
+    dt = B200TreeAnc(tree=Phylo.read(StringIO(T.to_newick()), 'newick'),
+                     aln=MultipleSeqAlignment([SeqRecord(Seq(''.join(aln[k])), id=k, name=k, description='') for k in aln]),
+                     gtr=mk(), rng_seed=1, verbose=0, engine_factory=oracle_engine.factory, **kw)
+    return rt, dt
+
+
+def test_dropin_mixin_on_real_treeanc():
+    """class B200TreeAnc(B200MarginalMixin, treetime.TreeAnc): same answers as treetime.TreeAnc
+    through the reference's own accessors (lazy clade attributes)."""
+    rt, dt = _pair()
+    assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
+    assert dt._engine is not None and dt._b200_live              # the device path ran, not the fallback
+    assert rt.sequence_LH() == dt.sequence_LH() and np.array_equal(rt.tree.sequence_LH, dt.tree.sequence_LH)
+    assert rt.tree.sequence_marginal_LH == dt.tree.sequence_marginal_LH
+    for a, b in zip(rt.tree.find_clades(), dt.tree.find_clades()):
+        assert a.name == b.name
+        if not a.is_terminal():
+            assert np.array_equal(a.marginal_profile, b.marginal_profile)
+            assert (a.cseq == b.cseq).all() and a.mutations == b.mutations
+        if a.up is not None:
+            pa, pb = rt.marginal_branch_profile(a), dt.marginal_branch_profile(b)
+            assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
+    assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True) == 0
+    n = [c for c in dt.tree.find_clades()][7]
+    m = [c for c in rt.tree.find_clades()][7]
+    assert np.array_equal(rt.get_branch_mutation_matrix(m), dt.get_branch_mutation_matrix(n))
+    assert rt.optimal_marginal_branch_length(m) == dt.optimal_marginal_branch_length(n)
+    ra = rt.get_reconstructed_alignment(); da = dt.get_reconstructed_alignment()
+    assert [str(r.seq) for r in ra] == [str(r.seq) for r in da]
+    rt.optimize_tree(branch_length_mode='marginal', max_iter=2, infer_gtr=True, prune_short=True)
+    dt.optimize_tree(branch_length_mode='marginal', max_iter=2, infer_gtr=True, prune_short=True)
+    a = np.array([c.branch_length for c in rt.tree.find_clades()]); b = np.array([c.branch_length for c in dt.tree.find_clades()])
+    assert a.shape == b.shape and np.allclose(a[1:], b[1:], rtol=1e-9, atol=1e-14)
+    assert np.isclose(rt.sequence_LH(), dt.sequence_LH(), rtol=1e-12)
+    assert np.allclose(rt.gtr.W, dt.gtr.W, rtol=1e-9) and type(dt.gtr) is type(rt.gtr)
+    rt.optimize_gtr_rate(); dt.optimize_gtr_rate()
+    assert np.isclose(rt.gtr.mu, dt.gtr.mu, rtol=1e-9)
+
+
+def test_dropin_falls_back_to_reference_for_masks_and_joint():
+    rt, dt = _pair(seed=34)
+    # joint reconstruction is not on the device path: the reference code runs
+    assert rt.infer_ancestral_sequences(marginal=False) == dt.infer_ancestral_sequences(marginal=False)
+    # marginal after joint: N_diff is counted against the joint sequences
+    assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
+    # a per-branch mask (ARG mode) => reference implementation, identical numbers
+    L = rt.data.compressed_length
+    mask = np.ones(L); mask[::3] = 0
+    list(rt.tree.find_clades())[4].mask = mask
+    list(dt.tree.find_clades())[4].mask = mask
+    assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
+    assert not dt._b200_live
+    assert rt.sequence_LH() == dt.sequence_LH()
+    for a, b in zip(rt.tree.find_clades(), dt.tree.find_clades()):
+        if not a.is_terminal():
+            assert np.array_equal(a.marginal_profile, b.marginal_profile)
+
+
+def test_dropin_treetime_run_marginal():
+    """TreeTime.run(branch_length_mode='marginal') -- the production caller (test_treetime.py:310-363)
+    -- on top of the drop-in gives the reference's result."""
+    refenv.activate()
+    import oracle_engine
+    from io import StringIO
+    from Bio import Phylo
+    from Bio.Align import MultipleSeqAlignment
+    from Bio.SeqRecord import SeqRecord
+    from Bio.Seq import Seq
+    from treetime import GTR as RG, TreeTime
+    from treetime_b200 import synth
+    from treetime_b200.dropin import accelerate
+    from treetime_b200.gtr import GTR
+    pi = np.array([.3, .2, .2, .29, .01])
+    T = synth.random_tree(25, seed=41, mean_bl=0.004)
+    g = GTR.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc')
+    idx = synth.evolve_alignment(T, 500, g.Pi, g.W, seed=41)
+    aln = {k: g.alphabet[v] for k, v in idx.items()}
+    # sampling dates proportional to root-to-tip distance (a clock-like tree)
+    d2r = {}
+    stack = [(T.root, 0.0)]
+    while stack:
+        n, d = stack.pop()
+        if not n.clades:
+            d2r[n.name] = d
+        for c in n.clades:
+            stack.append((c, d + c.branch_length))
+    dates = {k: 2000.0 + v / 0.002 for k, v in d2r.items()}
+    mk = lambda: RG.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc')  # noqa: E731
+    mkaln = lambda: MultipleSeqAlignment([SeqRecord(Seq(''.join(aln[k])), id=k, name=k, description='') for k in aln])  # noqa: E731
+    mktree = lambda: Phylo.read(StringIO(T.to_newick()), 'newick')  # noqa: E731
+    kw = dict(root=None, infer_gtr=False, max_iter=1, branch_length_mode='marginal', time_marginal=False, resolve_polytomies=False)
+    ref = TreeTime(tree=mktree(), aln=mkaln(), gtr=mk(), dates=dates, verbose=0, rng_seed=1)
+    ref.run(**kw)
+    ours = accelerate(TreeTime)(tree=mktree(), aln=mkaln(), gtr=mk(), dates=dates, verbose=0, rng_seed=1,
+                                engine_factory=oracle_engine.factory)
+    ours.run(**kw)
+    assert ours._engine is not None and ours._engine.launch_count() > 0
+    for a, b in zip(ref.tree.find_clades(), ours.tree.find_clades()):
+        assert a.name == b.name
+        assert np.isclose(a.numdate, b.numdate, rtol=0, atol=1e-6)
+        assert np.isclose(a.branch_length, b.branch_length, rtol=1e-7, atol=1e-12)
+    assert np.isclose(ref.tree.sequence_marginal_LH, ours.tree.sequence_marginal_LH, rtol=1e-10)

@@ -1,0 +1,368 @@
+"""Device-side implementation of the marginal path, shared by the standalone TreeAnc mirror
+(treetime_b200.treeanc.TreeAnc) and the drop-in mixin for the real TreeTime
+(treetime_b200.dropin).  It only relies on the TreeAnc attribute surface both have:
+`tree`, `data` (compressed_alignment, multiplicity(), compressed_length, full_length), `gtr`,
+`_branch_length_to_gtr`, `logger`, `rng`, `one_mutation`, `sequence_reconstruction`,
+`reconstructed_tip_sequences`.
+"""
+import numpy as np
+
+from . import config as ttconf
+from .brent import brent_lockstep
+from .dist import default_comm, shard_bounds
+from .flatten import FlatTopology, code_table, encode_chars, gtr_arrays
+from .gtr import infer_gtr_from_counts
+from .seq_utils import prof2seq
+
+SUBTREE, OUTGROUP, PROFILE = 0, 1, 2
+
+
+class Unsupported(NotImplementedError):
+    """Raised for inputs the device path does not cover (masks, full sampling, ...)."""
+
+
+def _default_engine_factory(n_states, device):
+    from .engine import Engine          # raises if libttb.so is missing or there is no GPU
+    return Engine(n_states, device=device)
+
+
+class DeviceMarginalMixin(object):
+    def _init_device(self, device=0, comm=None, engine_factory=None):
+        self.device = device
+        self.comm = comm if comm is not None else default_comm()
+        self._engine_factory = engine_factory or _default_engine_factory
+        self._engine = None
+        self._topo = None
+        self._device_topology = None
+        self._device_patterns = False
+        self._device_data_id = None
+        self._cache = {}
+        self._seq_cache = {}
+
+    def _unsupported(self, why):
+        raise Unsupported(why)
+
+    _missing_data_error = RuntimeError      # overridden with the host package's MissingDataError
+
+    # -- device synchronisation -------------------------------------------------------------
+    def _flat(self):
+        if self._topo is None:
+            self._topo = FlatTopology(self.tree.root)
+            for i, n in enumerate(self._topo.nodes):
+                n._fid = i
+        return self._topo
+
+    def _shard(self):
+        return shard_bounds(self.data.compressed_length, self.comm.rank, self.comm.world_size)
+
+    def _tip_codes(self):
+        """uint8 codes [n_tips, L'] + (n_codes, q) table.  Works on treetime_b200.SequenceData
+        (compressed ASCII matrix, vectorised) and on the reference's SequenceData (dict name ->
+        numpy char array)."""
+        topo = self._flat()
+        chars, lut, table = code_table(self.gtr.profile_map, self.gtr.n_states)
+        lo, hi = self._shard()
+        codes = np.full((topo.n_tips, hi - lo), len(chars), dtype=np.uint8)     # default: missing = all ones
+        if hasattr(self.data, 'compressed_matrix'):
+            lut8 = np.full(256, 255, dtype=np.uint8)
+            for c, i in lut.items():
+                lut8[ord(c)] = i
+            rows = np.array([self.data._row.get(topo.nodes[n].name, -1) for n in topo.tip_nodes])
+            have = rows >= 0
+            codes[have] = lut8[self.data.compressed_matrix[rows[have], lo:hi]]
+        else:
+            ca = self.data.compressed_alignment
+            for n in topo.tip_nodes:
+                name = topo.nodes[n].name
+                if name in ca:
+                    codes[topo.tip_row[n]] = encode_chars(np.asarray(ca[name])[lo:hi], chars)
+        if (codes == 255).any():
+            raise KeyError('alignment contains characters that are not in the profile map')
+        return codes, table
+
+    def _sync_device(self):
+        """Bring the engine up to date with tree topology, patterns, model and branch lengths."""
+        topo = self._flat()
+        if self._engine is None:
+            self._engine = self._engine_factory(self.gtr.n_states, self.device)
+        eng = self._engine
+        sig = topo.signature()
+        if sig != self._device_topology:
+            eng.set_tree(topo.parent, topo.child_ptr, topo.child_idx, topo.tip_row)
+            self._device_topology = sig
+            self._device_patterns = False
+        data_id = (id(self.data), self.data.compressed_length, len(self.gtr.profile_map))
+        if data_id != self._device_data_id:
+            self._device_patterns = False
+        if not self._device_patterns:
+            self._device_data_id = data_id
+            codes, table = self._tip_codes()
+            lo, hi = self._shard()
+            eng.set_patterns(codes, table, self.data.multiplicity()[lo:hi])
+            self._device_patterns = True
+        g = gtr_arrays(self.gtr)
+        if g['site_specific']:
+            lo, hi = self._shard()
+            g = dict(g, eigenvals=g['eigenvals'][:, lo:hi], v=g['v'][:, :, lo:hi], v_inv=g['v_inv'][:, :, lo:hi],
+                     Pi=g['Pi'][:, lo:hi], mu=g['mu'][lo:hi], t_grid=self._t_grid())
+        tvec = np.array([self._branch_length_to_gtr(n) for n in topo.nodes], dtype=np.float64)
+        lam = np.max(g['eigenvals']) * np.max(g['mu'])
+        if lam * tvec[1:].max() > 10:
+            raise ValueError('Error in computing exp(Q * t): Q has positive eigenvalues or the branch length t is too large. '
+                             'This is most likely caused by incorrect input data.')     # gtr.py:1041-1047
+        eng.set_gtr(g)
+        eng.set_branch_lengths(tvec)
+        self._t_last = tvec
+        return eng
+
+    def _t_grid(self):
+        from .gtr import GTRSiteSpecific  # noqa: F401
+        rs = self.gtr.rate_scale
+        return (1.0 / rs) * np.concatenate((np.linspace(0, 0.1, 11)[:-1], np.linspace(0.1, 1, 21)[:-1],
+                                            np.linspace(1, 5, 21)[:-1], np.linspace(5, 10, 11)))
+
+    def _gather_patterns(self, x, axis=0):
+        return x if self.comm.world_size == 1 else self.comm.allgather(x, axis=axis)
+
+    def _node_array(self, node, which):
+        key = (node._fid, which)
+        if key not in self._cache:
+            if not self.sequence_reconstruction and not (which == SUBTREE and self._engine is not None):
+                raise AttributeError('marginal ancestral inference needs to be performed first!')
+            if which == PROFILE and node.is_terminal() and not self.reconstructed_tip_sequences:
+                raise AttributeError('tip profiles exist only after reconstruct_tip_states=True')
+            self._cache[key] = self._gather_patterns(self._engine.node_array(node._fid, which), axis=0)
+        return self._cache[key]
+
+    def _node_cseq(self, node):
+        if not self.sequence_reconstruction:
+            raise ValueError('Ancestral sequences are not yet inferred')
+        k = node._fid
+        if k not in self._seq_cache:
+            override = getattr(node, '_cseq_override', None)
+            if override is not None:
+                self._seq_cache[k] = override
+            else:
+                idx = self._gather_patterns(self._engine.seq_idx([k])[0], axis=0)
+                self._seq_cache[k] = self.gtr.alphabet[idx]
+        return self._seq_cache[k]
+
+    # -- ancestral reconstruction ---------------------------------------------------------
+    def _ml_anc_marginal(self, sample_from_profile=False, reconstruct_tip_states=False, debug=False, **kwargs):
+        """treeanc.py:762-812: postorder, root, preorder -- one graph launch on the device."""
+        self.logger('TreeAnc._ml_anc_marginal: type of reconstruction: Marginal', 2)
+        if sample_from_profile == 'root':
+            root_sample = True
+        elif isinstance(sample_from_profile, bool):
+            root_sample = sample_from_profile
+            if sample_from_profile:
+                self._unsupported("sampling every node from its profile is not provided; sample_from_profile='root' is")
+        else:
+            raise ValueError("sample_from_profile must be a bool or 'root'")
+        if any(getattr(n, 'mask', None) is not None for n in self._flat().nodes):
+            self._unsupported('per-branch masks (ARG mode) are not supported on the device path')
+        eng = self._sync_device()
+        topo = self._flat()
+        eng.marginal(reconstruct_tips=reconstruct_tip_states)
+        tot, nd = eng.results()
+        if self.comm.world_size > 1:
+            tot, nd = self.comm.allreduce_sum(np.array([tot, float(nd)]))
+        self._cache = {}
+        self._seq_cache = {}
+        self.tree.sequence_LH = self._gather_patterns(eng.site_lh())
+        self.tree.total_sequence_LH = float(tot)
+        self.tree.sequence_marginal_LH = self.tree.total_sequence_LH
+        n_rec = (topo.n_nodes - 1) if reconstruct_tip_states else (topo.n_nodes - topo.n_tips - 1)
+        if self.sequence_reconstruction:
+            N_diff = int(round(nd))
+        else:
+            N_diff = n_rec * self.data.compressed_length               # treeanc.py:927-928
+        root = self.tree.root
+        root._cseq_override = None
+        self.reconstructed_tip_sequences = reconstruct_tip_states
+        self.sequence_reconstruction = 'marginal'
+        if root_sample:                                                 # treeanc.py:831-838, host RNG
+            seq, _, _ = prof2seq(self._node_array(root, PROFILE), self.gtr, sample_from_prof=True, normalize=False, rng=self.rng)
+            root._cseq_override = seq
+        self.logger('TreeAnc._ml_anc_marginal: ...done', 3)
+        return N_diff
+
+    def sequence_LH(self, pos=None, full_sequence=False):
+        """treeanc.py:691-716."""
+        if not hasattr(self.tree, 'total_sequence_LH'):
+            self.logger('TreeAnc.sequence_LH: you need to run marginal ancestral inference first!', 1)
+            self.infer_ancestral_sequences(marginal=True)
+        if pos is not None:
+            cpos = self.data.full_to_compressed_sequence_map[pos] if full_sequence else pos
+            return self.tree.sequence_LH[cpos]
+        return self.tree.total_sequence_LH
+
+    # -- branch profiles / lengths ---------------------------------------------------------------
+    def marginal_branch_profile(self, node):
+        """treeanc.py:1122-1146: (pp, pc) = (outgroup_LH, subtree_LH) of the branch above `node`."""
+        if node.up is None:
+            raise Exception("Branch profiles can't be calculated for the root!")
+        if not self.sequence_reconstruction:
+            raise Exception('marginal ancestral inference needs to be performed first!')
+        return node.marginal_outgroup_LH, node.marginal_subtree_LH
+
+    def get_branch_mutation_matrix(self, node, full_sequence=False):
+        """treeanc.py:1085-1120 (host einsum on two fetched profiles; the summed statistics
+        used by infer_gtr are accumulated on the device instead)."""
+        pp, pc = self.marginal_branch_profile(node)
+        expQt = self.gtr.expQt(self._t_last[node._fid]) + ttconf.SUPERTINY_NUMBER
+        stack = np.einsum('ai,aj,ij->aij', pc, pp, expQt)
+        stack = stack / stack.sum(axis=2).sum(axis=1)[:, None, None]
+        return stack[self.data.full_to_compressed_sequence_map] if full_sequence else stack
+
+    def _optimal_branch_lengths(self, fids, kinds, tol):
+        """Batched GTR.optimal_t_compressed(profiles=True) (gtr.py:816-920) for many branches:
+        one lock-step Brent over s = sqrt(t) with the reference's bracket and penalty."""
+        eng = self._engine
+        fids = np.asarray(fids, dtype=np.int32)
+        kinds = np.asarray(kinds, dtype=np.int32)
+        num, _ = eng.branch_hamming(fids, kinds)
+        if self.comm.world_size > 1:
+            num = self.comm.allreduce_sum(num)
+        den = self.data.multiplicity().sum()
+        hamming = 1 - num / den
+
+        def neg_prob(idx, s):
+            f = eng.branch_objective(fids[idx], s ** 2, kinds[idx])
+            if self.comm.world_size > 1:
+                f = self.comm.allreduce_sum(f)
+            return -1.0 * f + np.exp(s ** 4 / 10000)
+
+        n = fids.shape[0]
+        smax = np.sqrt(ttconf.MAX_BRANCH_LENGTH)
+        with np.errstate(invalid='ignore'):
+            xb = np.sqrt(hamming)
+        opt = brent_lockstep(neg_prob, np.full(n, -smax), xb, np.full(n, smax), tol=tol)
+        new_len = opt['x'] ** 2
+        if (new_len > 0.9 * ttconf.MAX_BRANCH_LENGTH).any():
+            self.logger('WARNING: GTR.optimal_t_compressed -- The branch length seems to be very long!', 4, warn=True)
+        new_len = np.where(opt['success'], new_len, hamming)           # gtr.py:916-918
+        self._last_brent = opt
+        return new_len
+
+    def optimal_marginal_branch_length(self, node, tol=1e-10):
+        """treeanc.py:1272-1295."""
+        if node.up is None:
+            return self.one_mutation
+        if not self.sequence_reconstruction:
+            raise Exception('marginal ancestral inference needs to be performed first!')
+        return float(self._optimal_branch_lengths([node._fid], [0], tol)[0])
+
+    def optimize_tree_marginal(self, max_iter=10, infer_gtr=False, pc=1.0, damping=0.75, LHtol=0.1,
+                               site_specific_gtr=False, **kwargs):
+        """treeanc.py:1297-1360 with all branches of one sweep optimised in one batched Brent."""
+        self.infer_ancestral_sequences(marginal=True, **kwargs)
+        oldLH = self.sequence_LH()
+        self.logger('TreeAnc.optimize_tree_marginal: initial, LH=%1.2f, total branch_length %1.4f'
+                    % (oldLH, self.tree.total_branch_length()), 2)
+        for i in range(max_iter):
+            if infer_gtr:
+                self.infer_gtr(site_specific=site_specific_gtr, marginal=True, normalized_rate=True, pc=pc)
+                self.infer_ancestral_sequences(marginal=True, **kwargs)
+            old_bl = self.tree.total_branch_length()
+            tol = 1e-8 + 0.01 ** (i + 1)
+            topo = self._flat()
+            root = self.tree.root
+            root_bif = len(root.clades) == 2
+            fids, kinds = [], []
+            for n in topo.nodes[1:]:
+                if n.up is root and root_bif:
+                    continue
+                fids.append(n._fid)
+                kinds.append(0)
+            if root_bif:
+                fids.append(root.clades[0]._fid)
+                kinds.append(1)
+            new = self._optimal_branch_lengths(fids, kinds, tol)
+            d = damping ** (i + 1)
+            for k, fid in enumerate(fids[:len(fids) - (1 if root_bif else 0)]):
+                n = topo.nodes[fid]
+                n.branch_length = new[k] * (1 - d) + n.branch_length * d
+                n.mutation_length = n.branch_length
+            if root_bif:
+                # the reference runs this block once per root child (treeanc.py:1317-1339)
+                n1, n2 = root.clades
+                for _ in range(2):
+                    total_bl = n1.branch_length + n2.branch_length
+                    bl_ratio = n1.branch_length / total_bl
+                    update_val = new[-1] * (1 - d) + total_bl * d
+                    n1.branch_length = update_val * bl_ratio
+                    n2.branch_length = update_val * (1 - bl_ratio)
+                    n1.mutation_length = n1.branch_length
+                    n2.mutation_length = n2.branch_length
+            self.infer_ancestral_sequences(marginal=True, **kwargs)
+            LH = self.sequence_LH()
+            deltaLH = LH - oldLH
+            oldLH = LH
+            dbl = self.tree.total_branch_length() - old_bl
+            self.logger('TreeAnc.optimize_tree_marginal: iteration %d, LH=%1.2f (%1.2f), delta branch_length=%1.4f, '
+                        'total branch_length %1.4f' % (i, LH, deltaLH, dbl, self.tree.total_branch_length()), 2)
+            if deltaLH < LHtol:
+                self.logger('TreeAnc.optimize_tree_marginal: deltaLH=%f, stopping iteration.' % deltaLH, 1)
+                break
+        return ttconf.SUCCESS
+
+    # -- model inference -------------------------------------------------------------------------
+    def infer_gtr(self, marginal=False, site_specific=False, normalized_rate=True, fixed_pi=None, pc=5.0, **kwargs):
+        """treeanc.py:1500-1632, marginal branch: the n_ij / T_i accumulation over all branches
+        (:1556-1572) is one device kernel; GTR.infer (gtr.py:491-599) stays on the host."""
+        if site_specific:
+            self._unsupported('site-specific GTR inference is not provided on the device path')
+        if not marginal:
+            self._unsupported('joint-mode GTR inference is outside the B200 hot path')
+        if not self.ok:
+            raise self._missing_data_error('TreeAnc.infer_gtr: ERROR, sequences or tree are missing')
+        if self.sequence_reconstruction != 'marginal':
+            self._ml_anc_marginal(**kwargs)
+        n_ij, T_i = self._engine.mutation_counts()
+        if self.comm.world_size > 1:
+            red = self.comm.allreduce_sum(np.concatenate([n_ij.ravel(), T_i]))
+            q = self.gtr.n_states
+            n_ij, T_i = red[:q * q].reshape(q, q), red[q * q:]
+        root_cseq = self.tree.root.cseq
+        m = self.data.multiplicity()
+        root_state = np.array([np.sum((root_cseq == nuc) * m) for nuc in self.gtr.alphabet])
+        self._gtr = self._infer_gtr_from_counts(n_ij, T_i, root_state, fixed_pi, pc)
+        if normalized_rate:
+            self.logger('TreeAnc.infer_gtr: setting overall rate to 1.0...', 2)
+            self._gtr.mu = 1.0
+        return self._gtr
+
+    def _infer_gtr_from_counts(self, n_ij, T_i, root_state, fixed_pi, pc):
+        return infer_gtr_from_counts(n_ij, T_i, root_state, fixed_pi=fixed_pi, pc=pc, alphabet=self.gtr.alphabet,
+                                     prof_map=self.gtr.profile_map, logger=self.logger)
+
+    def optimize_gtr_rate(self):
+        """treeanc.py:1679-1708: Brent over sqrt(mu); each evaluation is the LH-only device pass."""
+        from scipy.optimize import minimize_scalar
+
+        def cost_func(sqrt_mu):
+            self.gtr.mu = sqrt_mu ** 2
+            eng = self._sync_device()
+            eng.marginal(lh_only=True)
+            tot, _ = eng.results()
+            if self.comm.world_size > 1:
+                tot = self.comm.allreduce_sum(np.array([tot]))[0]
+            self.tree.total_sequence_LH = float(tot)
+            return -float(tot)
+
+        old_mu = self.gtr.mu
+        try:
+            sol = minimize_scalar(cost_func, bracket=[0.01 * np.sqrt(old_mu), np.sqrt(old_mu), 100 * np.sqrt(old_mu)],
+                                  method='brent')
+        except Exception:
+            self.gtr.mu = old_mu
+            self.logger('treeanc:optimize_gtr_rate: optimization failed, continuing with previous mu', 1, warn=True)
+            return
+        if sol['success']:
+            self.gtr.mu = sol['x'] ** 2
+            self.logger('treeanc:optimize_gtr_rate: optimization successful. Overall rate estimated to be %f' % self.gtr.mu, 1)
+        else:
+            self.gtr.mu = old_mu
+            self.logger('treeanc:optimize_gtr_rate: optimization failed, continuing with previous mu', 1, warn=True)
+

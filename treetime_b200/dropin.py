@@ -1,0 +1,220 @@
+"""Drop-in for the REAL TreeTime: a mixin that puts the device implementation of the marginal
+path in front of `treetime.TreeAnc` in the MRO, so that `ClockTree` / `TreeTime.run` /
+`treetime ancestral --marginal` call it unchanged.
+
+    from treetime import TreeAnc, TreeTime
+    from treetime_b200.dropin import accelerate
+    B200TreeAnc = accelerate(TreeAnc)          # class B200TreeAnc(B200MarginalMixin, TreeAnc)
+    B200TreeTime = accelerate(TreeTime)
+    tt = B200TreeTime(tree=..., aln=..., gtr=..., dates=...)
+    tt.run(branch_length_mode='marginal', ...)
+
+What is overridden (reference lines in treeanc.py): `_ml_anc_marginal` (:762-812),
+`optimize_tree_marginal` (:1297-1360), `optimal_marginal_branch_length` (:1272-1295),
+`infer_gtr` marginal branch (:1500-1632), `optimize_gtr_rate` (:1679-1708).  Everything the
+device path does not cover -- per-branch masks (ARG), sampling all nodes from their profiles,
+site-specific models, alphabets without compiled kernels, joint / Fitch reconstruction --
+falls through to the reference's own implementation (`super()`).
+
+Per-node results stay on the device.  The reference reads them as plain attributes of the
+Bio.Phylo clades (`node.marginal_profile`, `node.marginal_subtree_LH`,
+`node.marginal_outgroup_LH`, `node._cseq`); a `__getattr__` hook installed on the clade class
+fetches them on first access and caches them on the node until the next pass.
+"""
+import numpy as np
+
+from .device_mixin import DeviceMarginalMixin, Unsupported, SUBTREE, OUTGROUP, PROFILE
+
+_LAZY = {'marginal_subtree_LH': SUBTREE, 'marginal_outgroup_LH': OUTGROUP, 'marginal_profile': PROFILE}
+_hooked = set()
+
+
+def _lazy_getattr(node, name):
+    """Called only when normal attribute lookup fails (so cached values and everything the
+    reference sets itself take precedence)."""
+    if name in _LAZY or name == '_cseq':
+        tt = node.__dict__.get('tt')
+        if tt is not None and getattr(tt, '_b200_live', False) and '_fid' in node.__dict__:
+            try:
+                if name == '_cseq':
+                    if node.is_terminal() and not tt.reconstructed_tip_sequences:
+                        raise AttributeError(name)
+                    val = tt._node_cseq(node)
+                else:
+                    val = tt._node_array(node, _LAZY[name])
+            except (ValueError, RuntimeError) as e:
+                raise AttributeError(str(e))
+            node.__dict__[name] = val
+            return val
+    raise AttributeError(name)
+
+
+def _install_hook(clade_cls):
+    if clade_cls in _hooked:
+        return
+    if '__getattr__' in clade_cls.__dict__:
+        prev = clade_cls.__dict__['__getattr__']
+
+        def chained(node, name, _prev=prev):
+            try:
+                return _lazy_getattr(node, name)
+            except AttributeError:
+                return _prev(node, name)
+        clade_cls.__getattr__ = chained
+    else:
+        clade_cls.__getattr__ = _lazy_getattr
+    _hooked.add(clade_cls)
+
+
+class B200MarginalMixin(DeviceMarginalMixin):
+    """Place before treetime.TreeAnc (or ClockTree / TreeTime) in the MRO."""
+
+    def __init__(self, *args, device=0, comm=None, engine_factory=None, **kwargs):
+        self._init_device(device=device, comm=comm, engine_factory=engine_factory)
+        self._b200_live = False
+        super(B200MarginalMixin, self).__init__(*args, **kwargs)
+
+    # -- topology changes invalidate the flattening (prepare_tree / reroot / resolve_polytomies) --
+    def _prepare_nodes(self):
+        super(B200MarginalMixin, self)._prepare_nodes()
+        self._drop_node_caches()
+        self._topo = None
+
+    def _flat(self):
+        """The reference edits `clades` lists in place (prune_short_branches, polytomy resolution)
+        without notifying anybody: re-validate the cached flattening against the live tree."""
+        topo = self._topo
+        if topo is not None:
+            ok = topo.nodes[0] is self.tree.root
+            if ok:
+                cp, ci, nodes = topo.child_ptr, topo.child_idx, topo.nodes
+                for i, n in enumerate(nodes):
+                    kids = n.clades
+                    b = cp[i]
+                    if len(kids) != cp[i + 1] - b or any(nodes[ci[b + k]] is not c for k, c in enumerate(kids)):
+                        ok = False
+                        break
+            if not ok:
+                self._drop_node_caches()
+                self._topo = None
+        return DeviceMarginalMixin._flat(self)
+
+    def _drop_node_caches(self):
+        self._b200_live = False
+        if self._topo is not None:
+            for n in self._topo.nodes:
+                d = n.__dict__
+                for k in ('marginal_subtree_LH', 'marginal_outgroup_LH', 'marginal_profile'):
+                    d.pop(k, None)
+        self._cache = {}
+        self._seq_cache = {}
+
+    def _device_ok(self):
+        from . import _lib
+        g = self.gtr
+        if getattr(g, 'is_site_specific', False):
+            return 'site-specific models run in the reference'
+        if self._engine is None and self._engine_factory.__module__ == 'treetime_b200.device_mixin':
+            if not _lib.load().ttb_supports_n_states(int(g.n_states)):
+                return 'no kernels for %d states' % g.n_states
+        if self.data.compressed_length < 1:
+            return 'empty alignment'
+        return None
+
+    # -- the pass ---------------------------------------------------------------------------
+    def _ml_anc_marginal(self, sample_from_profile=False, reconstruct_tip_states=False, debug=False, **kwargs):
+        why = self._device_ok()
+        if why is None and sample_from_profile is True:
+            why = 'sampling every node from its profile'
+        if why is None and any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
+            why = 'per-branch masks (ARG mode)'
+        if why is None:
+            try:
+                # N_diff against a previous reconstruction that did not come from the device (joint /
+                # Fitch / reference fallback) has to be counted on the host (treeanc.py:925-926)
+                prev_live = self._b200_live and self.sequence_reconstruction == 'marginal'
+                old = None
+                if self.sequence_reconstruction and not prev_live:
+                    old = {id(n): np.array(n.cseq) for n in self.tree.find_clades()
+                           if n.up is not None and n.cseq is not None and (reconstruct_tip_states or not n.is_terminal())}
+                self._drop_node_caches()
+                topo = self._flat()
+                _install_hook(type(self.tree.root))
+                # the reference keeps stale per-node arrays from an earlier (reference) pass: drop them
+                for n in topo.nodes:
+                    d = n.__dict__
+                    for k in ('marginal_subtree_LH', 'marginal_outgroup_LH', 'marginal_profile', '_cseq',
+                              'marginal_log_Lx', 'marginal_subtree_LH_prefactor', 'branch_state'):
+                        d.pop(k, None)
+                N_diff = DeviceMarginalMixin._ml_anc_marginal(self, sample_from_profile=sample_from_profile,
+                                                              reconstruct_tip_states=reconstruct_tip_states, debug=debug)
+                root = self.tree.root
+                if getattr(root, '_cseq_override', None) is not None:
+                    root.__dict__['_cseq'] = root._cseq_override
+                self._b200_live = True
+                if old is not None:
+                    N_diff = 0
+                    for n in topo.nodes[1:]:
+                        if reconstruct_tip_states or not n.is_terminal():
+                            N_diff += int((n.cseq != old[id(n)]).sum()) if id(n) in old else self.data.compressed_length
+                return N_diff
+            except Unsupported as e:
+                why = str(e)
+        self.logger('B200: falling back to the reference implementation (%s)' % why, 2)
+        if self._b200_live and self._topo is not None:
+            # the reference compares against node._cseq of the previous pass: bring them to the host
+            for n in self._topo.nodes:
+                if '_cseq' not in n.__dict__ and (self.reconstructed_tip_sequences or not n.is_terminal()):
+                    n.__dict__['_cseq'] = self._node_cseq(n)
+        self._drop_node_caches()
+        return super(DeviceMarginalMixin, self)._ml_anc_marginal(sample_from_profile=sample_from_profile,
+                                                               reconstruct_tip_states=reconstruct_tip_states,
+                                                               debug=debug, **kwargs)
+
+    # accessors: the reference's own versions work through the lazy node attributes
+    def sequence_LH(self, *args, **kwargs):
+        return super(DeviceMarginalMixin, self).sequence_LH(*args, **kwargs)
+
+    def marginal_branch_profile(self, node):
+        return super(DeviceMarginalMixin, self).marginal_branch_profile(node)
+
+    def get_branch_mutation_matrix(self, node, full_sequence=False):
+        return super(DeviceMarginalMixin, self).get_branch_mutation_matrix(node, full_sequence=full_sequence)
+
+    def optimize_tree_marginal(self, *args, **kwargs):
+        if self._device_ok() is None and not any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
+            try:
+                return DeviceMarginalMixin.optimize_tree_marginal(self, *args, **kwargs)
+            except Unsupported:
+                pass
+        return super(DeviceMarginalMixin, self).optimize_tree_marginal(*args, **kwargs)
+
+    def optimal_marginal_branch_length(self, node, tol=1e-10):
+        if self._b200_live and getattr(node, 'mask', None) is None:
+            return DeviceMarginalMixin.optimal_marginal_branch_length(self, node, tol=tol)
+        return super(DeviceMarginalMixin, self).optimal_marginal_branch_length(node, tol=tol)
+
+    def infer_gtr(self, marginal=False, site_specific=False, **kwargs):
+        if marginal and not site_specific and self._device_ok() is None:
+            try:
+                gtr = DeviceMarginalMixin.infer_gtr(self, marginal=True, site_specific=False, **kwargs)
+                return gtr
+            except Unsupported:
+                pass
+        return super(DeviceMarginalMixin, self).infer_gtr(marginal=marginal, site_specific=site_specific, **kwargs)
+
+    def _infer_gtr_from_counts(self, n_ij, T_i, root_state, fixed_pi, pc):
+        """Use the reference's own GTR.infer so that the resulting object is a reference GTR."""
+        from treetime.gtr import GTR
+        return GTR.infer(n_ij, T_i, root_state, fixed_pi=fixed_pi, pc=pc, alphabet=self.gtr.alphabet,
+                         logger=self.logger, prof_map=self.gtr.profile_map)
+
+    def optimize_gtr_rate(self):
+        if self._device_ok() is None and self._b200_live:
+            return DeviceMarginalMixin.optimize_gtr_rate(self)
+        return super(DeviceMarginalMixin, self).optimize_gtr_rate()
+
+
+def accelerate(base):
+    """Return `class B200<base>(B200MarginalMixin, base)`."""
+    return type('B200' + base.__name__, (B200MarginalMixin, base), {'__doc__': B200MarginalMixin.__doc__})
