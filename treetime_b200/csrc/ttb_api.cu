@@ -79,7 +79,7 @@ struct Sched {
   std::vector<int> group_ptr;         // built once the number of tiles is known
   std::vector<TtbLevelLaunch> launches;
   DBuf<TtbChunk> d_chunks;
-  DBuf<int> d_group_ptr;
+  DBuf<int> d_group_ptr, d_node_chunk;
   void clear() {
     chunks.clear(); node_chunk.clear(); level_node_begin.clear(); group_ptr.clear(); launches.clear();
   }
@@ -271,6 +271,8 @@ int enqueue_pass(ttb_handle h, int flags, int count_diff, cudaStream_t s, int* n
   pl.d_tip_nodes = h->d_tip_nodes.p;
   pl.d_post_chunks = h->post.d_chunks.p;
   pl.d_post_group_ptr = h->post.d_group_ptr.p;
+  pl.d_post_node_chunk = h->post.d_node_chunk.p;
+  pl.n_post_leaf_nodes = h->post.level_node_begin.size() > 1 ? h->post.level_node_begin[1] : 0;
   pl.post_levels = h->post.launches.data();
   pl.n_post_levels = (int)h->post.launches.size();
   const Sched& pre = pl.tips ? h->pre_all : h->pre_int;
@@ -373,7 +375,7 @@ int ttb_destroy(ttb_handle h) {
   cudaStreamSynchronize(h->stream);
   h->drop_graphs();
   DBuf<int>* ib[] = {&h->d_parent, &h->d_child_ptr, &h->d_child_idx, &h->d_tip_row, &h->d_int_slot, &h->d_tip_nodes,
-                     &h->d_enodes, &h->d_ekinds, &h->post.d_group_ptr, &h->pre_int.d_group_ptr, &h->pre_all.d_group_ptr};
+                     &h->d_enodes, &h->d_ekinds, &h->post.d_group_ptr, &h->pre_int.d_group_ptr, &h->pre_all.d_group_ptr, &h->post.d_node_chunk};
   for (auto* b : ib) b->release();
   DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_TU, &h->d_P, &h->d_S,
                         &h->d_F, &h->d_M, &h->d_Mtip, &h->d_LH, &h->d_lh_partial, &h->d_results, &h->d_stage,
@@ -453,6 +455,7 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   if ((rc = upload(h->d_tip_nodes, h->tip_nodes.data(), h->tip_nodes.size(), s))) return rc;
   for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all})
     if ((rc = upload(sc->d_chunks, sc->chunks.data(), sc->chunks.size(), s))) return rc;
+  if ((rc = upload(h->post.d_node_chunk, h->post.node_chunk.data(), h->post.node_chunk.size(), s))) return rc;
   CK(cudaStreamSynchronize(s));
   // every per-node array is invalid now
   h->d_P.release(); h->d_TU.release(); h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();

@@ -8,10 +8,11 @@
 // Level kernels (postorder / preorder) are TMA pipelines: a block owns one 128-pattern tile
 // and a run of nodes of the level; one warp issues `cp.async.bulk` (1-D TMA) copies of the
 // child rows, the child's exp(Qt) and the tip tables into a 3-stage shared-memory ring and
-// signals an mbarrier per stage (expect_tx / complete_tx); all four warps consume a stage
-// with one thread per pattern and the q-state vectors in registers, then the stage is handed
-// back with a __syncthreads().  Bytes in flight are decoupled from registers/occupancy, which
-// is what an HBM-bound fp64 kernel with ~100 registers of state needs.
+// signals a "full" mbarrier per stage (expect_tx / complete_tx); all four warps consume a stage
+// with one thread per pattern and the q-state vectors in registers, then every warp releases the
+// stage on an "empty" mbarrier the producer waits on -- no block-wide barrier in steady state.
+// Bytes in flight are decoupled from registers/occupancy, which is what an HBM-bound fp64
+// kernel with ~100 registers of state needs.
 //
 // Arithmetic contract (reference lines cited per kernel): products are
 // taken in linear space with exact power-of-two rescaling instead of the reference's sum of
@@ -90,6 +91,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -185,39 +189,69 @@ template <int Q>
 struct Pipe {
   static constexpr int STAGES = (Q <= 8) ? 3 : 2;
   // per-stage byte offsets (all multiples of 16)
-  int off_P, off_TU, off_codes, off_oidx, stage_bytes;
+  int off_P, off_TU, off_codes, off_oidx, off_desc, stage_bytes;
   unsigned char* base;
-  uint64_t* bars;
+  uint64_t* full;   // [STAGES] producer -> consumers (transaction barrier)
+  uint64_t* empty;  // [STAGES] consumers -> producer (one arrival per warp)
   __host__ __device__ static int stage_size(int rows, int pq, int tu_stride) {
-    return rows * TTB_TILE * 8 + TTB_CB * pq * 8 + TTB_CB * tu_stride * 8 + 2 * TTB_CB * TTB_TILE;
+    return rows * TTB_TILE * 8 + TTB_CB * pq * 8 + TTB_CB * tu_stride * 8 + 2 * TTB_CB * TTB_TILE + 32;
   }
   __host__ static size_t smem_bytes(int rows, int pq, int tu_stride) {
-    return 64 + (size_t)STAGES * stage_size(rows, pq, tu_stride);
+    return 128 + (size_t)STAGES * stage_size(rows, pq, tu_stride);
   }
   __device__ Pipe(unsigned char* smem, int rows, int pq, int tu_stride) {
-    bars = reinterpret_cast<uint64_t*>(smem);
-    base = smem + 64;
+    full = reinterpret_cast<uint64_t*>(smem);
+    empty = full + STAGES;
+    base = smem + 128;
     off_P = rows * TTB_TILE * 8;
     off_TU = off_P + TTB_CB * pq * 8;
     off_codes = off_TU + TTB_CB * tu_stride * 8;
     off_oidx = off_codes + TTB_CB * TTB_TILE;
-    stage_bytes = off_oidx + TTB_CB * TTB_TILE;
+    off_desc = off_oidx + TTB_CB * TTB_TILE;
+    stage_bytes = off_desc + 32;
+  }
+  __device__ void init() const {  // one thread
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, TTB_BLOCK / 32);
+    }
+    mbar_fence_init();
   }
   __device__ double* rows(int s) const { return reinterpret_cast<double*>(base + (size_t)s * stage_bytes); }
   __device__ double* P(int s) const { return reinterpret_cast<double*>(base + (size_t)s * stage_bytes + off_P); }
   __device__ double* TU(int s) const { return reinterpret_cast<double*>(base + (size_t)s * stage_bytes + off_TU); }
   __device__ uint8_t* codes(int s) const { return base + (size_t)s * stage_bytes + off_codes; }
   __device__ uint8_t* oidx(int s) const { return base + (size_t)s * stage_bytes + off_oidx; }
+  __device__ const int4* desc(int s) const { return reinterpret_cast<const int4*>(base + (size_t)s * stage_bytes + off_desc); }
+  // Producer side: the stage used by chunk number u (0-based within the block) is free once all
+  // consumer warps released its previous use.
+  __device__ void producer_acquire(int u) const {
+    if (u >= STAGES) mbar_wait(empty + u % STAGES, ((u / STAGES) - 1) & 1);
+  }
+  __device__ void consumer_wait(int u) const { mbar_wait(full + u % STAGES, (u / STAGES) & 1); }
+  __device__ void consumer_release(int u, int lane) const {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + u % STAGES);
+  }
 };
 
-__device__ __forceinline__ TtbChunk load_chunk(const TtbChunk* __restrict__ c) {
-  const int4* q = reinterpret_cast<const int4*>(c);
-  const int4 a = __ldg(q), b = __ldg(q + 1);
-  TtbChunk r;
-  r.out = a.x; r.flags = a.y; r.src[0] = a.z; r.src[1] = a.w;
-  r.cnode[0] = b.x; r.cnode[1] = b.y; r.pad[0] = b.z; r.pad[1] = b.w;
-  return r;
+// Chunk descriptor held in registers as scalars (no local-memory arrays).
+struct Chunk {
+  int out, flags, src0, src1, cnode0, cnode1;
+  __device__ __forceinline__ int nch() const { return flags >> 8; }
+  __device__ __forceinline__ int src(int b) const { return b ? src1 : src0; }
+  __device__ __forceinline__ int cnode(int b) const { return b ? cnode1 : cnode0; }
+};
+__device__ __forceinline__ Chunk chunk_from(const int4 a, const int4 b) {
+  Chunk c;
+  c.out = a.x; c.flags = a.y; c.src0 = a.z; c.src1 = a.w; c.cnode0 = b.x; c.cnode1 = b.y;
+  return c;
 }
+__device__ __forceinline__ Chunk load_chunk_global(const TtbChunk* __restrict__ c) {
+  const int4* q = reinterpret_cast<const int4*>(c);
+  return chunk_from(__ldg(q), __ldg(q + 1));
+}
+__device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_from(q[0], q[1]); }
 
 // ---------------------------------------------------------------------------------------
 // A3-A5: one postorder level.  Reference: postorder_traversal_marginal, treeanc.py:857-878 +
@@ -232,62 +266,64 @@ template <int Q>
 __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int ST = Pipe<Q>::STAGES;
   constexpr int RPC = Q + 1;  // rows per child
   Pipe<Q> pipe(smem_raw, TTB_CB * RPC, p.pq, p.tu_stride);
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
+  const int n_chunks = k1 - k0;
   const long long a0 = (long long)tile * TTB_TILE;
   const int cols = (int)min((long long)TTB_TILE, p.ld - a0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long a = a0 + tid;
   const bool act = a < p.Lp;
-  if (tid == 0) {
-    for (int s = 0; s < ST; ++s) mbar_init(pipe.bars + s, 1);
-    mbar_fence_init();
-  }
+  if (tid == 0) pipe.init();
   __syncthreads();
 
-  auto issue = [&](int k) {  // executed by warp 0
-    const int s = (k - k0) % ST;
-    const TtbChunk c = load_chunk(chunks + k);
-    const int nch = c.flags >> 8;
-    uint32_t bytes = 0;
+  auto issue = [&](int u) {  // executed by warp 0: fill the stage of chunk number u
+    const int s = u % Pipe<Q>::STAGES;
+    const Chunk c = load_chunk_global(chunks + k0 + u);
+    pipe.producer_acquire(u);
+    uint64_t* bar = pipe.full + s;
+    const int nch = c.nch();
+    uint32_t bytes = 32;
     for (int b = 0; b < nch; ++b)
-      bytes += (c.src[b] >= 0) ? (uint32_t)(RPC * cols * 8 + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
-    if (lane == 0) mbar_arrive_expect_tx(pipe.bars + s, bytes);
+      bytes += (c.src(b) >= 0) ? (uint32_t)(RPC * cols * 8 + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar, bytes);
+      tma_load_1d((void*)pipe.desc(s), chunks + k0 + u, 32, bar);
+    }
     __syncwarp();
     for (int job = lane; job < nch * (RPC + 1); job += 32) {
       const int b = job / (RPC + 1), r = job % (RPC + 1);
-      const int src = c.src[b];
+      const int src = c.src(b);
       if (src >= 0) {
         if (r < Q)
-          tma_load_1d(pipe.rows(s) + (b * RPC + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, pipe.bars + s);
+          tma_load_1d(pipe.rows(s) + (b * RPC + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, bar);
         else if (r == Q)
-          tma_load_1d(pipe.rows(s) + (b * RPC + Q) * TTB_TILE, p.F + (size_t)src * p.ld + a0, cols * 8, pipe.bars + s);
+          tma_load_1d(pipe.rows(s) + (b * RPC + Q) * TTB_TILE, p.F + (size_t)src * p.ld + a0, cols * 8, bar);
         else
-          tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode[b] * p.pq, p.pq * 8, pipe.bars + s);
+          tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
       } else {
         const int row = -1 - src;
         if (r == 0)
-          tma_load_1d(pipe.codes(s) + b * TTB_TILE, p.codes + (size_t)row * p.ld + a0, cols, pipe.bars + s);
+          tma_load_1d(pipe.codes(s) + b * TTB_TILE, p.codes + (size_t)row * p.ld + a0, cols, bar);
         else if (r == 1)
-          tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, pipe.bars + s);
+          tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, bar);
       }
     }
   };
 
   if (warp == 0)
-    for (int k = k0; k < min(k1, k0 + ST - 1); ++k) issue(k);
+    for (int u = 0; u < min(n_chunks, Pipe<Q>::STAGES - 1); ++u) issue(u);
 
   double X[Q];
   double F = 0.0;
   int scale = 0, seen = 0;
-  for (int k = k0; k < k1; ++k) {
-    if (warp == 0 && k + ST - 1 < k1) issue(k + ST - 1);
-    const int s = (k - k0) % ST;
-    const TtbChunk c = load_chunk(chunks + k);
-    mbar_wait(pipe.bars + s, ((k - k0) / ST) & 1);
+  for (int u = 0; u < n_chunks; ++u) {
+    if (warp == 0 && u + Pipe<Q>::STAGES - 1 < n_chunks) issue(u + Pipe<Q>::STAGES - 1);
+    const int s = u % Pipe<Q>::STAGES;
+    pipe.consumer_wait(u);
+    const Chunk c = load_chunk_smem(pipe.desc(s));
     if (c.flags & 1) {
 #pragma unroll
       for (int j = 0; j < Q; ++j) X[j] = 1.0;
@@ -295,11 +331,11 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
       scale = 0;
       seen = 0;
     }
-    const int nch = c.flags >> 8;
+    const int nch = c.nch();
     if (act) {
       for (int b = 0; b < nch; ++b) {
         double U[Q];
-        if (c.src[b] < 0) {
+        if (c.src(b) < 0) {
           const int code = pipe.codes(s)[b * TTB_TILE + tid];
           const double* tu = pipe.TU(s) + b * p.tu_stride + code * Q;
 #pragma unroll
@@ -331,19 +367,65 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
           }
         }
       }
-      if (c.flags & 2) {
-        double Z = X[0];
+    }
+    pipe.consumer_release(u, lane);  // all smem reads of this stage are done
+    if (act && (c.flags & 2)) {
+      double Z = X[0];
 #pragma unroll
-        for (int j = 1; j < Q; ++j) Z += X[j];
-        const double inv = 1.0 / Z;
-        double* __restrict__ so = p.S + (size_t)c.out * Q * p.ld + a;
+      for (int j = 1; j < Q; ++j) Z += X[j];
+      const double inv = 1.0 / Z;
+      double* __restrict__ so = p.S + (size_t)c.out * Q * p.ld + a;
 #pragma unroll
-        for (int j = 0; j < Q; ++j) so[(size_t)j * p.ld] = X[j] * inv;
-        p.F[(size_t)c.out * p.ld + a] = F + (log(Z) - scale * (256.0 * 0.693147180559945309417232121458));
+      for (int j = 0; j < Q; ++j) so[(size_t)j * p.ld] = X[j] * inv;
+      p.F[(size_t)c.out * p.ld + a] = F + (log(Z) - scale * (256.0 * 0.693147180559945309417232121458));
+    }
+  }
+}
+
+// Postorder level 1: every child is a tip, so there is nothing to stream in but one code byte
+// per (tip, pattern); the kernel is a pure write stream of (q+1) doubles per (node, pattern).
+// One thread per (node, pattern), tip tables read through L1.
+template <int Q>
+__global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+                                                                   const int* __restrict__ node_chunk, int tiles) {
+  const int node = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  const long long a = (long long)tile * TTB_TILE + threadIdx.x;
+  if (a >= p.Lp) return;
+  const int k0 = node_chunk[node], k1 = node_chunk[node + 1];
+  double X[Q];
+#pragma unroll
+  for (int j = 0; j < Q; ++j) X[j] = 1.0;
+  int scale = 0, seen = 0, out = 0;
+  for (int k = k0; k < k1; ++k) {
+    const Chunk c = load_chunk_global(chunks + k);
+    out = c.out;
+    const int nch = c.nch();
+    for (int b = 0; b < nch; ++b) {
+      const int row = -1 - c.src(b);
+      const int code = __ldg(p.codes + (size_t)row * p.ld + a);
+      const double* tu = p.TU + (size_t)row * p.tu_stride + code * Q;
+#pragma unroll
+      for (int j = 0; j < Q; ++j) X[j] *= __ldg(tu + j);
+      if (++seen > 2) {
+        double mx = X[0];
+#pragma unroll
+        for (int j = 1; j < Q; ++j) mx = fmax(mx, X[j]);
+        if (mx < 0x1p-256 && mx > 0.0) {
+#pragma unroll
+          for (int j = 0; j < Q; ++j) X[j] *= 0x1p+256;
+          ++scale;
+        }
       }
     }
-    __syncthreads();  // stage s may be refilled
   }
+  double Z = X[0];
+#pragma unroll
+  for (int j = 1; j < Q; ++j) Z += X[j];
+  const double inv = 1.0 / Z;
+  double* __restrict__ so = p.S + (size_t)out * Q * p.ld + a;
+#pragma unroll
+  for (int j = 0; j < Q; ++j) so[(size_t)j * p.ld] = X[j] * inv;
+  p.F[(size_t)out * p.ld + a] = log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -459,67 +541,69 @@ template <int Q, bool TIPS>
 __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int ST = Pipe<Q>::STAGES;
   Pipe<Q> pipe(smem_raw, Q + TTB_CB * Q, p.pq, p.tu_stride);
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
+  const int n_chunks = k1 - k0;
   const long long a0 = (long long)tile * TTB_TILE;
   const int cols = (int)min((long long)TTB_TILE, p.ld - a0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long a = a0 + tid;
   const bool act = a < p.Lp;
-  if (tid == 0) {
-    for (int s = 0; s < ST; ++s) mbar_init(pipe.bars + s, 1);
-    mbar_fence_init();
-  }
+  if (tid == 0) pipe.init();
   __syncthreads();
 
-  auto issue = [&](int k) {  // executed by warp 0
-    const int s = (k - k0) % ST;
-    const TtbChunk c = load_chunk(chunks + k);
-    const int nch = c.flags >> 8;
+  auto issue = [&](int u) {  // executed by warp 0
+    const int s = u % Pipe<Q>::STAGES;
+    const Chunk c = load_chunk_global(chunks + k0 + u);
+    pipe.producer_acquire(u);
+    uint64_t* bar = pipe.full + s;
+    const int nch = c.nch();
     const bool first = c.flags & 1;
-    uint32_t bytes = first ? (uint32_t)(Q * cols * 8) : 0u;
+    uint32_t bytes = 32 + (first ? (uint32_t)(Q * cols * 8) : 0u);
     for (int b = 0; b < nch; ++b)
-      bytes += (c.src[b] >= 0) ? (uint32_t)(Q * cols * 8 + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
-    if (lane == 0) mbar_arrive_expect_tx(pipe.bars + s, bytes);
+      bytes += (c.src(b) >= 0) ? (uint32_t)(Q * cols * 8 + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar, bytes);
+      tma_load_1d((void*)pipe.desc(s), chunks + k0 + u, 32, bar);
+    }
     __syncwarp();
     if (first)
       for (int r = lane; r < Q; r += 32)
-        tma_load_1d(pipe.rows(s) + r * TTB_TILE, p.M + ((size_t)c.out * Q + r) * p.ld + a0, cols * 8, pipe.bars + s);
+        tma_load_1d(pipe.rows(s) + r * TTB_TILE, p.M + ((size_t)c.out * Q + r) * p.ld + a0, cols * 8, bar);
     for (int job = lane; job < nch * (Q + 2); job += 32) {
       const int b = job / (Q + 2), r = job % (Q + 2);
-      const int src = c.src[b];
+      const int src = c.src(b);
       if (r == Q + 1) {
-        tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode[b] * p.pq, p.pq * 8, pipe.bars + s);
+        tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
       } else if (src >= 0) {
         if (r < Q)
-          tma_load_1d(pipe.rows(s) + (Q + b * Q + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, pipe.bars + s);
+          tma_load_1d(pipe.rows(s) + (Q + b * Q + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, bar);
         else
-          tma_load_1d(pipe.oidx(s) + b * TTB_TILE, p.idx + (size_t)src * p.ld + a0, cols, pipe.bars + s);
+          tma_load_1d(pipe.oidx(s) + b * TTB_TILE, p.idx + (size_t)src * p.ld + a0, cols, bar);
       } else if (TIPS) {
         const int row = -1 - src;
         if (r == 0)
-          tma_load_1d(pipe.codes(s) + b * TTB_TILE, p.codes + (size_t)row * p.ld + a0, cols, pipe.bars + s);
+          tma_load_1d(pipe.codes(s) + b * TTB_TILE, p.codes + (size_t)row * p.ld + a0, cols, bar);
         else if (r == 1)
-          tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, pipe.bars + s);
+          tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, bar);
         else if (r == 2)
-          tma_load_1d(pipe.oidx(s) + b * TTB_TILE, p.idxtip + (size_t)row * p.ld + a0, cols, pipe.bars + s);
+          tma_load_1d(pipe.oidx(s) + b * TTB_TILE, p.idxtip + (size_t)row * p.ld + a0, cols, bar);
       }
     }
   };
 
   if (warp == 0)
-    for (int k = k0; k < min(k1, k0 + ST - 1); ++k) issue(k);
+    for (int u = 0; u < min(n_chunks, Pipe<Q>::STAGES - 1); ++u) issue(u);
 
   double Mp[Q];
   unsigned int ndiff = 0;
-  for (int k = k0; k < k1; ++k) {
-    if (warp == 0 && k + ST - 1 < k1) issue(k + ST - 1);
-    const int s = (k - k0) % ST;
-    const TtbChunk c = load_chunk(chunks + k);
-    mbar_wait(pipe.bars + s, ((k - k0) / ST) & 1);
-    const int nch = c.flags >> 8;
+  for (int u = 0; u < n_chunks; ++u) {
+    if (warp == 0 && u + Pipe<Q>::STAGES - 1 < n_chunks) issue(u + Pipe<Q>::STAGES - 1);
+    const int s = u % Pipe<Q>::STAGES;
+    pipe.consumer_wait(u);
+    const Chunk c = load_chunk_smem(pipe.desc(s));
+    const int nch = c.nch();
     if (act) {
       if (c.flags & 1) {
         const double* m = pipe.rows(s) + tid;
@@ -527,7 +611,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
         for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, m[j * TTB_TILE]);
       }
       for (int b = 0; b < nch; ++b) {
-        const int src = c.src[b];
+        const int src = c.src(b);
         const double* Pc = pipe.P(s) + b * p.pq;
         double U[Q], Sc[Q], O[Q];
         double* __restrict__ out;
@@ -580,7 +664,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
         *ip = (uint8_t)best;
       }
     }
-    __syncthreads();  // stage s may be refilled
+    pipe.consumer_release(u, lane);
   }
   if (count_diff) {
     ndiff = __reduce_add_sync(0xffffffffu, ndiff);

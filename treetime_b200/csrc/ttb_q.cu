@@ -32,7 +32,11 @@ int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   nk += 2;
   if (ev) { cudaEventRecord(ev[1], s); pk[0] = nk; }
   const size_t psm = post_smem(d);
-  for (int l = 0; l < pl.n_post_levels; ++l) {
+  // level 1 (all children are tips) is a pure write stream: dedicated kernel, no pipeline
+  post_leaf_level_kernel<Q><<<(unsigned)((long long)pl.n_post_leaf_nodes * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_post_chunks,
+                                                                                                  pl.d_post_node_chunk, tiles);
+  ++nk;
+  for (int l = 1; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
     post_level_kernel<Q><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, psm, s>>>(d, pl.d_post_chunks,
                                                                                          pl.d_post_group_ptr + L.group_off, tiles);

@@ -16,6 +16,8 @@ struct TtbPassPlan {
   int tiles;
   const int* d_tip_nodes;          // tip row -> node id
   const TtbChunk* d_post_chunks;
+  const int* d_post_node_chunk;    // first chunk of every scheduled postorder node (+ sentinel)
+  int n_post_leaf_nodes;           // nodes of postorder level 1 (all children are tips)
   const int* d_post_group_ptr;
   const TtbLevelLaunch* post_levels;
   int n_post_levels;
