@@ -165,6 +165,7 @@ def main():
     ap.add_argument('--cpu-patterns', type=int, default=0, help='patterns in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--e2e-blocks', type=int, default=4, help='pattern blocks (engine handles / streams) of the e2e leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 0)
 
@@ -271,37 +272,70 @@ def main():
         ph = eng.profile_marginal()
         phases = {k: (min(phases[k][0], ph[k][0]), ph[k][1]) for k in ph}
 
-    # ---- e2e: host buffers in, host results out, every step
+    # ---- e2e: host buffers in, host results out, every step.
+    # The pattern axis is cut into E2E_BLOCKS column blocks, each with its own engine handle and
+    # stream (one handle = one pattern shard is the C-ABI's unit anyway), so the H2D copy of block
+    # k+1, the pass over block k and the D2H copy of block k-1 overlap on the two copy engines.
     e2e = None
     if not args.no_e2e:
         n_int = int((flat['tip_row'] < 0).sum())
-        seq_pin = torch.empty((n_int, Lp), dtype=torch.uint8, pin_memory=True)
-        seq_np = seq_pin.numpy()
+        nblk = max(1, min(args.e2e_blocks, Lp // 1024))
+        bounds = [(Lp * i) // nblk for i in range(nblk + 1)]
+        shards = []
+        for i in range(nblk):
+            lo, hi = bounds[i], bounds[i + 1]
+            e = Engine(q, device=local_rank)
+            e.set_tree(flat['parent'], flat['child_ptr'], flat['child_idx'], flat['tip_row'])
+            cp = torch.empty((flat['tip_codes'].shape[0], hi - lo), dtype=torch.uint8, pin_memory=True)
+            cp.numpy()[...] = flat['tip_codes'][:, lo:hi]
+            sp = torch.empty((n_int, hi - lo), dtype=torch.uint8, pin_memory=True)
+            lp = torch.empty(hi - lo, dtype=torch.float64, pin_memory=True)
+            shards.append((e, cp.numpy(), sp.numpy(), lp.numpy(), np.ascontiguousarray(flat['multiplicity'][lo:hi]), cp, sp, lp))
 
         def e2e_step():
-            eng.set_patterns(codes_pin.numpy(), flat['code_profiles'], flat['multiplicity'])
-            eng.set_gtr(g)
-            eng.set_branch_lengths(flat['t'])
-            eng.marginal()
+            for e, cp, sp, lp, m, *_ in shards:
+                e.set_patterns(cp, flat['code_profiles'], m)
+                e.set_gtr(g)
+                e.set_branch_lengths(flat['t'])
+                e.marginal()
+                e.enqueue_site_lh(lp)
+                e.enqueue_all_seq_idx(sp)
+            tot = 0.0
+            for e, *_ in shards:
+                t_, _ = e.results()          # waits for that block's stream (incl. its D2H copies)
+                tot += t_
             if world > 1:
-                dist.all_reduce(res_t)
-            tot, nd = eng.results()
-            lh = eng.site_lh()
-            eng.all_seq_idx(out=seq_np)
-            return tot, lh
+                tt_ = torch.tensor([tot], device='cuda', dtype=torch.float64)
+                dist.all_reduce(tt_)
+                tot = float(tt_.item())
+            return tot
 
+        tot_e2e = e2e_step()
         e2e_step()
         barrier()
         k_e2e = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            e2e_step()
+            tot_e2e = e2e_step()
         barrier()
         e2e_s = (time.perf_counter() - t0) / k_e2e
-        h2d = int(flat['tip_codes'].nbytes + flat['code_profiles'].nbytes + flat['multiplicity'].nbytes + flat['t'].nbytes
-                  + 8 * (2 * q * q + 2 * q + 1))
-        d2h = int(n_int * Lp + 8 * Lp + 16)
-        e2e = (e2e_s, h2d, d2h)
+        h2d = int(flat['tip_codes'].nbytes + nblk * (flat['code_profiles'].nbytes + flat['t'].nbytes + 8 * (2 * q * q + 2 * q + 1))
+                  + flat['multiplicity'].nbytes)
+        d2h = int(n_int * Lp + 8 * Lp + 16 * nblk)
+        # sanity: the blocked e2e result equals the resident pass
+        lh_check = abs(tot_e2e - (total_lh_local if world == 1 else float(res_t[0].item()))) / abs(tot_e2e)
+        # PCIe probe for context (pinned 256 MB each way)
+        pb = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+        db = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+        pe0, pe1, pe2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        db.copy_(pb, non_blocking=True); torch.cuda.synchronize()
+        pe0.record(); db.copy_(pb, non_blocking=True); pe1.record(); pb.copy_(db, non_blocking=True); pe2.record()
+        torch.cuda.synchronize()
+        pcie = (0.268435456 / (pe0.elapsed_time(pe1) / 1e3), 0.268435456 / (pe1.elapsed_time(pe2) / 1e3))
+        e2e = (e2e_s, h2d, d2h, nblk, lh_check, pcie)
+        for sh in shards:
+            sh[0].close()
+        del shards
 
     # ---- reduce over ranks: max time, summed work
     ms_step = ms_total / args.steps
@@ -355,8 +389,11 @@ def main():
         if e2e:
             out['e2e'] = {'value': updates_total / e2e_time, 'unit': 'updates/s', 'ms_per_step': 1e3 * e2e_time,
                           'h2d_bytes_per_step': e2e[1], 'd2h_bytes_per_step': e2e[2],
-                          'what': 'ttb_set_patterns/gtr/branch_lengths from pinned host memory + ttb_marginal + '
-                                  'ttb_results + ttb_fetch_site_lh + ttb_fetch_all_seq_idx, per rank'}
+                          'pattern_blocks': e2e[3], 'rel_lh_diff_vs_resident_pass': e2e[4],
+                          'pcie_probe_gbs': {'h2d': e2e[5][0], 'd2h': e2e[5][1]},
+                          'what': 'per step and per pattern block: ttb_set_patterns/gtr/branch_lengths from pinned host '
+                                  'memory, ttb_marginal, ttb_enqueue_fetch_site_lh + ttb_enqueue_fetch_all_seq_idx into '
+                                  'pinned host memory, ttb_results; blocks run on their own streams so copies overlap compute'}
         if not args.no_cpu_baseline and world >= 1:
             n_pat = args.cpu_patterns or int(max(64, min(Lp, 20.0 * 2.0e6 / n_br)))
             upd, times, cpu_lh = run_cpu(flat, g, n_pat, 1)

@@ -60,7 +60,7 @@ enum {
 
 const char* ttb_last_error(void);
 int ttb_version(void);
-/* 1 if kernels for this alphabet size are compiled in (2..8 and 20..24) */
+/* 1 if kernels for this alphabet size are compiled in (2..8 and 20..22) */
 int ttb_supports_n_states(int n_states);
 
 /* Create an engine on CUDA device `device` for an alphabet of n_states (gtr.n_states). */
@@ -120,6 +120,13 @@ int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* ou
 
 /* All internal nodes at once: out[n_internal][n_patterns], rows in node (preorder) order. */
 int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out);
+
+/* Stream-ordered variants without a host sync: the data is valid after ttb_sync / ttb_results.
+ * `out` should be page-locked memory (otherwise the driver stages and the call blocks).  With
+ * page-locked INPUT buffers ttb_set_patterns is asynchronous too (when sizes are unchanged): the
+ * caller must then leave them untouched until the next synchronising call. */
+int ttb_enqueue_fetch_site_lh(ttb_handle h, double* out);
+int ttb_enqueue_fetch_all_seq_idx(ttb_handle h, uint8_t* out);
 
 /* Same work as ttb_marginal but launched kernel by kernel with CUDA events between the
  * phases (no graph): ms[4] = {expQt batch, postorder levels, root + reductions, preorder levels},

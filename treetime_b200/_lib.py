@@ -95,6 +95,8 @@ SIGNATURES = {
     'ttb_fetch_node': ([_H, ctypes.c_int32, ctypes.c_int32, _c_dbl_p], ctypes.c_int),
     'ttb_fetch_seq_idx': ([_H, ctypes.c_int32, _c_int_p, _c_u8_p], ctypes.c_int),
     'ttb_fetch_all_seq_idx': ([_H, _c_u8_p], ctypes.c_int),
+    'ttb_enqueue_fetch_site_lh': ([_H, _c_dbl_p], ctypes.c_int),
+    'ttb_enqueue_fetch_all_seq_idx': ([_H, _c_u8_p], ctypes.c_int),
     'ttb_profile_marginal': ([_H, ctypes.c_int32, _c_dbl_p, _c_int_p], ctypes.c_int),
     'ttb_branch_objective': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_branch_hamming': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p], ctypes.c_int),

@@ -114,7 +114,7 @@ struct ttb_engine {
   DBuf<double> d_t, d_eig, d_v, d_vinv, d_Pi, d_mu;
   // state
   DBuf<double> d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
-  DBuf<uint8_t> d_idx, d_idxtip;
+  DBuf<uint8_t> d_idx, d_idxtip, d_bstage;   // d_bstage: packed byte staging for contiguous H2D / D2H
   DBuf<unsigned long long> d_nd;
   DBuf<int> d_enodes, d_ekinds;
   DBuf<double> d_ets, d_eout;
@@ -385,6 +385,7 @@ int ttb_destroy(ttb_handle h) {
   h->post.d_chunks.release(); h->pre_int.d_chunks.release(); h->pre_all.d_chunks.release();
   h->d_idx.release();
   h->d_idxtip.release();
+  h->d_bstage.release();
   h->d_nd.release();
   if (h->h_results) cudaFreeHost(h->h_results);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -476,18 +477,22 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
     return fail(TTB_EINVAL, "ttb_set_patterns: bad arguments");
   if ((size_t)n_codes * h->q * 8 > 16 * 1024) return fail(TTB_EUNSUPPORTED, "ttb_set_patterns: too many distinct characters for the tip tables");
   const long long Lp = n_patterns, ld = (Lp + 31) / 32 * 32;
-  CK(cudaStreamSynchronize(h->stream));
+  // same sizes as before: nothing is reallocated and the call is stream-ordered without host syncs
+  if (ld != h->ld || Lp != h->Lp || n_codes != h->n_codes) CK(cudaStreamSynchronize(h->stream));
   cudaStream_t s = h->stream;
   int rc;
   if ((rc = h->d_codes.alloc((size_t)h->n_tips * ld))) return rc;
-  CK(cudaMemsetAsync(h->d_codes.p, 0, h->d_codes.bytes(), s));
-  CK(cudaMemcpy2DAsync(h->d_codes.p, ld, tip_codes, Lp, Lp, h->n_tips, cudaMemcpyHostToDevice, s));
+  // one contiguous H2D copy into a packed staging buffer, re-pitched to the padded layout on the device
+  if ((rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)Lp))) return rc;
+  CK(cudaMemcpyAsync(h->d_bstage.p, tip_codes, (size_t)h->n_tips * Lp, cudaMemcpyHostToDevice, s));
+  pitch_bytes_kernel<<<148 * 8, 256, 0, s>>>(h->d_bstage.p, Lp, h->d_codes.p, ld, Lp, h->n_tips, 0);
+  h->launches += 1;
+  CK(cudaGetLastError());
   if ((rc = upload(h->d_code_prof, code_profiles, (size_t)n_codes * h->q, s))) return rc;
   if ((rc = h->d_mult.alloc(ld))) return rc;
   CK(cudaMemsetAsync(h->d_mult.p, 0, h->d_mult.bytes(), s));
   CK(cudaMemcpyAsync(h->d_mult.p, multiplicity, Lp * sizeof(double), cudaMemcpyHostToDevice, s));
   h->h_mult.assign(multiplicity, multiplicity + Lp);
-  CK(cudaStreamSynchronize(s));
   if (ld != h->ld || Lp != h->Lp) {
     h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();
     h->d_idx.release(); h->d_idxtip.release(); h->d_LH.release(); h->d_lh_partial.release();
@@ -518,8 +523,7 @@ int ttb_set_gtr(ttb_handle h, const double* eigvals, const double* v, const doub
   if ((rc = upload(h->d_v, v, q * q, s))) return rc;
   if ((rc = upload(h->d_vinv, v_inv, q * q, s))) return rc;
   if ((rc = upload(h->d_Pi, Pi, q, s))) return rc;
-  if ((rc = upload(h->d_mu, &mu, 1, s))) return rc;
-  CK(cudaStreamSynchronize(s));
+  if ((rc = upload(h->d_mu, &mu, 1, s))) return rc;   // pageable sources are staged before the call returns
   if (realloc) h->drop_graphs();
   h->mu = mu;
   h->gap_index = gap_index;
@@ -654,11 +658,34 @@ int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* ou
   return 0;
 }
 
+int ttb_enqueue_fetch_site_lh(ttb_handle h, double* out) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->d_LH.p || !out) return fail(TTB_EINVAL, "ttb_enqueue_fetch_site_lh: nothing computed yet");
+  CK(cudaMemcpyAsync(out, h->d_LH.p, h->Lp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+int ttb_enqueue_fetch_all_seq_idx(ttb_handle h, uint8_t* out) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, true)) return rc;
+  if (!out) return fail(TTB_EINVAL, "ttb_enqueue_fetch_all_seq_idx: null output");
+  if (int rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)h->Lp)) return rc;
+  pitch_bytes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_idx.p, h->ld, h->d_bstage.p, h->Lp, h->Lp, h->n_int, 0);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->d_bstage.p, (size_t)h->n_int * h->Lp, cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
 int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out) {
   if (int rc = use_device(h)) return rc;
   if (int rc = check_ready(h, true)) return rc;
   if (!out) return fail(TTB_EINVAL, "ttb_fetch_all_seq_idx: null output");
-  CK(cudaMemcpy2DAsync(out, h->Lp, h->d_idx.p, h->ld, h->Lp, h->n_int, cudaMemcpyDeviceToHost, h->stream));
+  if (int rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)h->Lp)) return rc;
+  pitch_bytes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_idx.p, h->ld, h->d_bstage.p, h->Lp, h->Lp, h->n_int, 0);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->d_bstage.p, (size_t)h->n_int * h->Lp, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }

@@ -489,6 +489,17 @@ static __global__ void __launch_bounds__(256) finish_kernel(TtbDev p, int tiles)
   }
 }
 
+// Re-pitch byte matrices between the host's packed [rows][Lp] layout and the device's padded
+// [rows][ld] layout, so that host<->device transfers are single contiguous copies.
+static __global__ void pitch_bytes_kernel(const uint8_t* __restrict__ src, long long src_ld, uint8_t* __restrict__ dst,
+                                          long long dst_ld, long long cols, long long rows, uint8_t fill) {
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const uint8_t* __restrict__ s = src + r * src_ld;
+    uint8_t* __restrict__ d = dst + r * dst_ld;
+    for (long long c = threadIdx.x; c < dst_ld; c += blockDim.x) d[c] = (c < cols) ? s[c] : fill;
+  }
+}
+
 static __global__ void zero_slots_kernel(TtbDev p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 1024) p.nd_slots[i] = 0ull;

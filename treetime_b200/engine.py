@@ -142,6 +142,14 @@ class Engine(object):
         _lib.check(self.lib.ttb_fetch_all_seq_idx(self.h, _up(out)))
         return out
 
+    def enqueue_site_lh(self, out):
+        """Stream-ordered D2H of tree.sequence_LH into `out` (pinned); valid after sync()."""
+        _lib.check(self.lib.ttb_enqueue_fetch_site_lh(self.h, _dp(out)))
+
+    def enqueue_all_seq_idx(self, out):
+        """Stream-ordered D2H of all internal state indices into `out` (pinned); valid after sync()."""
+        _lib.check(self.lib.ttb_enqueue_fetch_all_seq_idx(self.h, _up(out)))
+
     def profile_marginal(self, reconstruct_tips=False, lh_only=False):
         """Un-graphed pass with per-phase CUDA-event times: dict phase -> (ms, launches)."""
         flags = (RECONSTRUCT_TIPS if reconstruct_tips else 0) | (LH_ONLY if lh_only else 0)
