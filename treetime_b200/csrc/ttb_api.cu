@@ -216,12 +216,13 @@ void build_sched(ttb_handle h, const std::vector<int>& key, const std::vector<ch
       for (int e = h->child_ptr[n]; e < h->child_ptr[n + 1]; ++e)
         if (take(h->child_idx[e])) kids.push_back(h->child_idx[e]);
       const int nk = (int)kids.size();
-      for (int c0 = 0; c0 < nk; c0 += TTB_CB) {
+      const int CB = h->q <= 8 ? TTB_CB : 1;   // same rule as Pipe<Q>::CB
+      for (int c0 = 0; c0 < nk; c0 += CB) {
         TtbChunk ch;
         memset(&ch, 0, sizeof ch);
         ch.out = h->int_slot[n];
-        const int nb = std::min(TTB_CB, nk - c0);
-        ch.flags = (c0 == 0 ? 1 : 0) | (c0 + TTB_CB >= nk ? 2 : 0) | (nb << 8);
+        const int nb = std::min(CB, nk - c0);
+        ch.flags = (c0 == 0 ? 1 : 0) | (c0 + CB >= nk ? 2 : 0) | (nb << 8);
         for (int b = 0; b < nb; ++b) {
           const int c = kids[c0 + b];
           ch.src[b] = h->int_slot[c] >= 0 ? h->int_slot[c] : -1 - h->tip_row[c];

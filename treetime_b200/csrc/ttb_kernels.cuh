@@ -95,6 +95,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Orders this thread's generic-proxy shared-memory writes before later async-proxy (TMA) writes.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -188,13 +190,14 @@ __global__ void tip_table_kernel(TtbDev p, const int* __restrict__ tip_nodes) {
 template <int Q>
 struct Pipe {
   static constexpr int STAGES = (Q <= 8) ? 3 : 2;
+  static constexpr int CB = (Q <= 8) ? TTB_CB : 1;   // children per chunk (the host schedule uses the same rule)
   // per-stage byte offsets (all multiples of 16)
   int off_P, off_TU, off_codes, off_oidx, off_desc, stage_bytes;
   unsigned char* base;
   uint64_t* full;   // [STAGES] producer -> consumers (transaction barrier)
   uint64_t* empty;  // [STAGES] consumers -> producer (one arrival per warp)
   __host__ __device__ static int stage_size(int rows, int pq, int tu_stride) {
-    return rows * TTB_TILE * 8 + TTB_CB * pq * 8 + TTB_CB * tu_stride * 8 + 2 * TTB_CB * TTB_TILE + 32;
+    return rows * TTB_TILE * 8 + CB * pq * 8 + CB * tu_stride * 8 + 2 * CB * TTB_TILE + 32;
   }
   __host__ static size_t smem_bytes(int rows, int pq, int tu_stride) {
     return 128 + (size_t)STAGES * stage_size(rows, pq, tu_stride);
@@ -204,10 +207,10 @@ struct Pipe {
     empty = full + STAGES;
     base = smem + 128;
     off_P = rows * TTB_TILE * 8;
-    off_TU = off_P + TTB_CB * pq * 8;
-    off_codes = off_TU + TTB_CB * tu_stride * 8;
-    off_oidx = off_codes + TTB_CB * TTB_TILE;
-    off_desc = off_oidx + TTB_CB * TTB_TILE;
+    off_TU = off_P + CB * pq * 8;
+    off_codes = off_TU + CB * tu_stride * 8;
+    off_oidx = off_codes + CB * TTB_TILE;
+    off_desc = off_oidx + CB * TTB_TILE;
     stage_bytes = off_desc + 32;
   }
   __device__ void init() const {  // one thread
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
                                                               const int* __restrict__ group_ptr, int tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int RPC = Q + 1;  // rows per child
-  Pipe<Q> pipe(smem_raw, TTB_CB * RPC, p.pq, p.tu_stride);
+  Pipe<Q> pipe(smem_raw, Pipe<Q>::CB * RPC, p.pq, p.tu_stride);
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
   const int n_chunks = k1 - k0;
@@ -552,7 +555,7 @@ template <int Q, bool TIPS>
 __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Pipe<Q> pipe(smem_raw, Q + TTB_CB * Q, p.pq, p.tu_stride);
+  Pipe<Q> pipe(smem_raw, Q + Pipe<Q>::CB * Q, p.pq, p.tu_stride);
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
   const int n_chunks = k1 - k0;
@@ -624,57 +627,112 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
       for (int b = 0; b < nch; ++b) {
         const int src = c.src(b);
         const double* Pc = pipe.P(s) + b * p.pq;
-        double U[Q], Sc[Q], O[Q];
         double* __restrict__ out;
         uint8_t* ip;
         if (TIPS && src < 0) {
           const int row = -1 - src;
-          const int code = pipe.codes(s)[b * TTB_TILE + tid];
-          const double* tu = pipe.TU(s) + b * p.tu_stride + code * Q;
-#pragma unroll
-          for (int j = 0; j < Q; ++j) {
-            U[j] = tu[j];
-            Sc[j] = __ldg(p.code_prof + code * Q + j);
-          }
           out = p.Mtip + (size_t)row * Q * p.ld + a;
           ip = p.idxtip + (size_t)row * p.ld + a;
         } else {
-          const double* rows = pipe.rows(s) + (Q + b * Q) * TTB_TILE + tid;
-#pragma unroll
-          for (int i = 0; i < Q; ++i) Sc[i] = rows[i * TTB_TILE];
-#pragma unroll
-          for (int j = 0; j < Q; ++j) U[j] = Sc[0] * Pc[j];
-#pragma unroll
-          for (int i = 1; i < Q; ++i)
-#pragma unroll
-            for (int j = 0; j < Q; ++j) U[j] = fma(Sc[i], Pc[i * Q + j], U[j]);
           out = p.M + (size_t)src * Q * p.ld + a;
           ip = p.idx + (size_t)src * p.ld + a;
         }
-        outgroup_message<Q>(Mp, U, O);
-        double prof[Q];
-        double z = 0.0;
-#pragma unroll
-        for (int i = 0; i < Q; ++i) {
-          double msg = O[0] * Pc[i * Q];
-#pragma unroll
-          for (int j = 1; j < Q; ++j) msg = fma(O[j], Pc[i * Q + j], msg);
-          prof[i] = Sc[i] * msg;
-          z += prof[i];
-        }
-        const double inv = 1.0 / z;
         int best = 0;
-        double bv = -1.0;
+        if constexpr (Q <= 8) {
+          // small alphabets: every q-vector in registers
+          double U[Q], Sc[Q], O[Q];
+          if (TIPS && src < 0) {
+            const int code = pipe.codes(s)[b * TTB_TILE + tid];
+            const double* tu = pipe.TU(s) + b * p.tu_stride + code * Q;
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
-          const double x = prof[i] * inv;
-          out[(size_t)i * p.ld] = x;
-          if (x > bv) { bv = x; best = i; }
+            for (int j = 0; j < Q; ++j) {
+              U[j] = tu[j];
+              Sc[j] = __ldg(p.code_prof + code * Q + j);
+            }
+          } else {
+            const double* rows = pipe.rows(s) + (Q + b * Q) * TTB_TILE + tid;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) Sc[i] = rows[i * TTB_TILE];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) U[j] = Sc[0] * Pc[j];
+#pragma unroll
+            for (int i = 1; i < Q; ++i)
+#pragma unroll
+              for (int j = 0; j < Q; ++j) U[j] = fma(Sc[i], Pc[i * Q + j], U[j]);
+          }
+          outgroup_message<Q>(Mp, U, O);
+          double prof[Q];
+          double z = 0.0;
+#pragma unroll
+          for (int i = 0; i < Q; ++i) {
+            double msg = O[0] * Pc[i * Q];
+#pragma unroll
+            for (int j = 1; j < Q; ++j) msg = fma(O[j], Pc[i * Q + j], msg);
+            prof[i] = Sc[i] * msg;
+            z += prof[i];
+          }
+          const double inv = 1.0 / z;
+          double bv = -1.0;
+#pragma unroll
+          for (int i = 0; i < Q; ++i) {
+            const double x = prof[i] * inv;
+            out[(size_t)i * p.ld] = x;
+            if (x > bv) { bv = x; best = i; }
+          }
+        } else {
+          // large alphabets (amino acids): only the outside message lives in registers; the
+          // child's profile is streamed from this thread's private column of the stage and the
+          // unnormalised result is parked there until the normaliser is known
+          double* col = pipe.rows(s) + (Q + b * Q) * TTB_TILE + tid;
+          double O[Q];
+          if (TIPS && src < 0) {
+            const int code = pipe.codes(s)[b * TTB_TILE + tid];
+            const double* tu = pipe.TU(s) + b * p.tu_stride + code * Q;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) O[j] = tu[j];
+            for (int i = 0; i < Q; ++i) col[i * TTB_TILE] = __ldg(p.code_prof + code * Q + i);
+          } else {
+#pragma unroll
+            for (int j = 0; j < Q; ++j) O[j] = 0.0;
+#pragma unroll 2
+            for (int i = 0; i < Q; ++i) {
+              const double si = col[i * TTB_TILE];
+#pragma unroll
+              for (int j = 0; j < Q; ++j) O[j] = fma(si, Pc[i * Q + j], O[j]);
+            }
+          }
+          double z = 0.0;
+#pragma unroll
+          for (int j = 0; j < Q; ++j) {
+            O[j] = Mp[j] * (1.0 / O[j]);
+            z += O[j];
+          }
+          const double invz = 1.0 / z;
+#pragma unroll
+          for (int j = 0; j < Q; ++j) O[j] *= invz;
+          double z2 = 0.0;
+#pragma unroll 2
+          for (int i = 0; i < Q; ++i) {
+            double msg = 0.0;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) msg = fma(O[j], Pc[i * Q + j], msg);
+            const double pr = col[i * TTB_TILE] * msg;
+            col[i * TTB_TILE] = pr;
+            z2 += pr;
+          }
+          const double inv = 1.0 / z2;
+          double bv = -1.0;
+          for (int i = 0; i < Q; ++i) {
+            const double x = col[i * TTB_TILE] * inv;
+            out[(size_t)i * p.ld] = x;
+            if (x > bv) { bv = x; best = i; }
+          }
         }
         if (count_diff) ndiff += (pipe.oidx(s)[b * TTB_TILE + tid] != (uint8_t)best);
         *ip = (uint8_t)best;
       }
     }
+    if constexpr (Q > 8) fence_proxy_async_smem();  // the stage was written through the generic proxy
     pipe.consumer_release(u, lane);
   }
   if (count_diff) {

@@ -9,8 +9,8 @@
 namespace {
 constexpr int Q = TTB_Q;
 
-size_t post_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(TTB_CB * (Q + 1), d.pq, d.tu_stride); }
-size_t pre_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(Q + TTB_CB * Q, d.pq, d.tu_stride); }
+size_t post_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(Pipe<Q>::CB * (Q + 1), d.pq, d.tu_stride); }
+size_t pre_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(Q + Pipe<Q>::CB * Q, d.pq, d.tu_stride); }
 
 int prepare_q(const TtbDev& d) {
   cudaError_t e;
