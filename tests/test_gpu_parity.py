@@ -107,6 +107,35 @@ def test_other_alphabets(alphabet, q):
     compare_all(flat, g, eng, res, every=3)
 
 
+@pytest.mark.parametrize('approximate', [True, False])
+def test_site_specific_gtr(approximate):
+    """gtr_site_specific.py: per-site Pi/mu, interpolated (default) and exact exp(Qt)."""
+    from treetime_b200.gtr import GTRSiteSpecific
+    L = 300
+    gtr = GTRSiteSpecific.random(L=L, alphabet='nuc', rng=np.random.default_rng(17))
+    gtr.approximate = approximate
+    tree = synth.random_tree(40, seed=12, mean_bl=0.05)
+    topo, flat, g = util.make_flat(tree, gtr, L, 12, amb_frac=0.02, compress=False)
+    assert flat['multiplicity'].shape[0] == L and g['site_specific']
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    tot, nd = eng.results()
+    res = O.marginal(flat, g)
+    assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+    assert nd == res.N_diff
+    compare_all(flat, g, eng, res, every=2)
+    eng.marginal(reconstruct_tips=True)
+    res_t = O.marginal(flat, g, reconstruct_tip_states=True)
+    compare_all(flat, g, eng, res_t, reconstruct_tips=True, every=3)
+    # branch objective with the per-pattern matrices, below and above the interpolation range
+    nodes = np.arange(1, flat['parent'].shape[0], 3, dtype=np.int32)
+    for tval in (1e-3, 0.05, 0.7, 12.0 / g['rate_scale']):
+        f = eng.branch_objective(nodes, np.full(nodes.shape[0], tval))
+        ref = np.array([O.branch_objective(flat, g, res_t, n, tval) for n in nodes])
+        assert np.allclose(f, ref, rtol=1e-10, atol=1e-9), (tval, np.abs(f - ref).max())
+    print('site-specific approx=%s relLH=%.1e' % (approximate, abs(tot - res.total_LH) / abs(res.total_LH)))
+
+
 def test_lh_only_and_new_rate():
     """optimize_gtr_rate's cost function: postorder + root only, for several mu."""
     tree = synth.random_tree(100, seed=8, mean_bl=0.01)

@@ -57,6 +57,25 @@ def test_gpu_reconstruction_matches_reference_golden(name):
     print('%s: rel dLH=%.1e  max|dprofile|=%.1e' % (name, abs(tt.sequence_LH() - float(z['total_LH'])) / abs(float(z['total_LH'])), worst))
 
 
+def test_gpu_site_specific_golden():
+    """Site-specific model (reference default: interpolated expQt) against the reference's output."""
+    from treetime_b200.gtr import GTRSiteSpecific
+    z = G.load('sitespec20')
+    ab = [str(c) for c in z['gtr_alphabet']]
+    gtr = GTRSiteSpecific(seq_len=int(z['gtr_mu'].shape[0]), approximate=bool(z['gtr_approximate']), alphabet='nuc')
+    assert list(gtr.alphabet) == ab
+    gtr._W, gtr._Pi, gtr._mu = z['gtr_W'].copy(), z['gtr_Pi'].copy(), z['gtr_mu'].copy()
+    gtr.eigenvals, gtr.v, gtr.v_inv = z['gtr_eigenvals'].copy(), z['gtr_v'].copy(), z['gtr_v_inv'].copy()
+    gtr.rate_scale = float(z['gtr_rate_scale'])
+    tt = TreeAnc(tree=str(z['newick']), aln=G.alignment(z), gtr=gtr, rng_seed=1, compress=False)
+    nodes, worst = check(tt, z)
+    for k, i in enumerate(z['bl_nodes']):
+        bl = tt.optimal_marginal_branch_length(nodes[i])
+        assert abs(bl - z['bl_opt'][k]) <= 1e-6 * z['bl_opt'][k] + 1e-12
+    with pytest.raises(TypeError):
+        TreeAnc(tree=str(z['newick']), aln=G.alignment(z), gtr=gtr, compress=True)     # treeanc.py:186-187
+
+
 def test_gpu_known_answer_lh_normalisation():
     """The reference's own KAT (test/test_treetime.py:137-155): sum over all 4^3 patterns of exp(LH) = 1."""
     z = G.load('kat3')

@@ -112,6 +112,12 @@ struct ttb_engine {
   double mu = 1.0;
   int gap_index = -1;
   DBuf<double> d_t, d_eig, d_v, d_vinv, d_Pi, d_mu;
+  // site-specific model
+  bool site_specific = false;
+  DBuf<double> d_ss_eig, d_ss_mu, d_ss_V, d_ss_Vinv, d_ss_Pi, d_ss_tlo, d_ss_thi, d_ss_w, d_ss_grid;
+  std::vector<double> ss_grid, h_t;
+  double ss_tmax = 0.0;
+  bool ss_interp_dirty = true;
   // state
   DBuf<double> d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
   DBuf<uint8_t> d_idx, d_idxtip, d_bstage;   // d_bstage: packed byte staging for contiguous H2D / D2H
@@ -158,6 +164,11 @@ struct ttb_engine {
     d.vinv = d_vinv.p;
     d.Pi = d_Pi.p;
     d.mu = d_mu.p;
+    d.site_specific = site_specific ? 1 : 0;
+    d.ss_eig = d_ss_eig.p; d.ss_mu = d_ss_mu.p; d.ss_V = d_ss_V.p; d.ss_Vinv = d_ss_Vinv.p; d.ss_Pi = d_ss_Pi.p;
+    d.ss_tlo = d_ss_tlo.p; d.ss_thi = d_ss_thi.p; d.ss_w = d_ss_w.p; d.ss_grid = d_ss_grid.p;
+    d.ss_ngrid = (int)ss_grid.size();
+    d.ss_tmax = ss_tmax;
     d.pq = (q * q + 1) / 2 * 2;
     d.tu_stride = (n_codes * q + 1) / 2 * 2;
     d.TU = d_TU.p;
@@ -378,7 +389,8 @@ int ttb_destroy(ttb_handle h) {
   DBuf<int>* ib[] = {&h->d_parent, &h->d_child_ptr, &h->d_child_idx, &h->d_tip_row, &h->d_int_slot, &h->d_tip_nodes,
                      &h->d_enodes, &h->d_ekinds, &h->post.d_group_ptr, &h->pre_int.d_group_ptr, &h->pre_all.d_group_ptr, &h->post.d_node_chunk};
   for (auto* b : ib) b->release();
-  DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_TU, &h->d_P, &h->d_S,
+  DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_ss_eig, &h->d_ss_mu, &h->d_ss_V, &h->d_ss_Vinv, &h->d_ss_Pi,
+                        &h->d_ss_tlo, &h->d_ss_thi, &h->d_ss_w, &h->d_ss_grid, &h->d_TU, &h->d_P, &h->d_S,
                         &h->d_F, &h->d_M, &h->d_Mtip, &h->d_LH, &h->d_lh_partial, &h->d_results, &h->d_stage,
                         &h->d_partial, &h->d_ets, &h->d_eout};
   for (auto* b : db) b->release();
@@ -495,6 +507,7 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
   CK(cudaMemcpyAsync(h->d_mult.p, multiplicity, Lp * sizeof(double), cudaMemcpyHostToDevice, s));
   h->h_mult.assign(multiplicity, multiplicity + Lp);
   if (ld != h->ld || Lp != h->Lp) {
+    if (h->site_specific) { h->site_specific = false; h->have_gtr = false; }   // per-pattern model no longer matches
     h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();
     h->d_idx.release(); h->d_idxtip.release(); h->d_LH.release(); h->d_lh_partial.release();
     h->drop_graphs();
@@ -525,16 +538,82 @@ int ttb_set_gtr(ttb_handle h, const double* eigvals, const double* v, const doub
   if ((rc = upload(h->d_vinv, v_inv, q * q, s))) return rc;
   if ((rc = upload(h->d_Pi, Pi, q, s))) return rc;
   if ((rc = upload(h->d_mu, &mu, 1, s))) return rc;   // pageable sources are staged before the call returns
-  if (realloc) h->drop_graphs();
+  if (realloc || h->site_specific) h->drop_graphs();
+  h->site_specific = false;
   h->mu = mu;
   h->gap_index = gap_index;
   h->have_gtr = true;
   return 0;
 }
 
-int ttb_set_gtr_site_specific(ttb_handle, const double*, const double*, const double*, const double*, const double*,
-                              const double*, int32_t, double, int32_t, int32_t) {
-  return fail(TTB_EUNSUPPORTED, "site-specific GTR models are not implemented in this build");
+// Upload a [rows][Lp] host plane set into a [rows][ld] device buffer (zero padded).
+static int upload_planes(ttb_handle h, DBuf<double>& b, const double* src, size_t rows) {
+  if (int rc = b.alloc(rows * (size_t)h->ld)) return rc;
+  CK(cudaMemsetAsync(b.p, 0, b.bytes(), h->stream));
+  CK(cudaMemcpy2DAsync(b.p, h->ld * sizeof(double), src, h->Lp * sizeof(double), h->Lp * sizeof(double), rows,
+                       cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int ttb_set_gtr_site_specific(ttb_handle h, const double* eigvals, const double* v, const double* v_inv, const double* Pi,
+                              const double* mu, const double* t_grid, int32_t n_grid, double rate_scale,
+                              int32_t approximate, int32_t gap_index) {
+  if (int rc = use_device(h)) return rc;
+  if (!eigvals || !v || !v_inv || !Pi || !mu || !t_grid || n_grid < 2) return fail(TTB_EINVAL, "ttb_set_gtr_site_specific: bad arguments");
+  if (h->q > 8) return fail(TTB_EUNSUPPORTED, "site-specific models are compiled for alphabets of up to 8 states");
+  if (!h->Lp) return fail(TTB_EINVAL, "ttb_set_gtr_site_specific: call ttb_set_patterns first (the model is per pattern)");
+  const size_t q = h->q, L = (size_t)h->Lp;
+  // reference layout (gtr_site_specific.py:327-329): v[k][i][a] = V_a[i][k], v_inv[j][k][a] = Vinv_a[k][j];
+  // device planes: V at (i*q+k), Vinv at (k*q+j)  => transpose the two leading axes on the host
+  std::vector<double> V(q * q * L), Vi(q * q * L);
+  for (size_t i = 0; i < q; ++i)
+    for (size_t k = 0; k < q; ++k) {
+      memcpy(&V[(i * q + k) * L], &v[(k * q + i) * L], L * sizeof(double));
+      memcpy(&Vi[(k * q + i) * L], &v_inv[(i * q + k) * L], L * sizeof(double));
+    }
+  int rc;
+  if ((rc = upload_planes(h, h->d_ss_eig, eigvals, q))) return rc;
+  if ((rc = upload_planes(h, h->d_ss_mu, mu, 1))) return rc;
+  if ((rc = upload_planes(h, h->d_ss_V, V.data(), q * q))) return rc;
+  if ((rc = upload_planes(h, h->d_ss_Vinv, Vi.data(), q * q))) return rc;
+  if ((rc = upload_planes(h, h->d_ss_Pi, Pi, q))) return rc;
+  if ((rc = upload(h->d_ss_grid, t_grid, (size_t)n_grid, h->stream))) return rc;
+  CK(cudaStreamSynchronize(h->stream));   // V / Vi are locals
+  h->ss_grid.assign(t_grid, t_grid + n_grid);
+  h->ss_tmax = approximate ? 10.0 / rate_scale : 0.0;
+  h->ss_interp_dirty = true;
+  h->gap_index = gap_index;
+  h->site_specific = true;
+  h->have_gtr = true;
+  h->drop_graphs();
+  return 0;
+}
+
+// Bracket every branch length on the interpolation grid exactly like scipy's interp1d(kind='linear',
+// assume_sorted=True): idx = searchsorted(grid, t) clipped to [1, n-1]  (gtr_site_specific.py:345-348,367-371).
+static int update_ss_interp(ttb_handle h) {
+  if (!h->site_specific || !h->ss_interp_dirty) return 0;
+  const int n = h->n_nodes, ng = (int)h->ss_grid.size();
+  std::vector<double> tlo(n, 0.0), thi(n, 0.0), w(n, -1.0);
+  for (int i = 1; i < n; ++i) {
+    const double t = h->h_t[i];
+    if (h->ss_tmax > 0.0 && t < h->ss_tmax) {
+      int lo = (int)(std::lower_bound(h->ss_grid.begin(), h->ss_grid.end(), t) - h->ss_grid.begin());
+      lo = std::max(1, std::min(ng - 1, lo));
+      tlo[i] = h->ss_grid[lo - 1];
+      thi[i] = h->ss_grid[lo];
+      w[i] = (t - tlo[i]) / (thi[i] - tlo[i]);
+    }
+  }
+  const bool realloc = !h->d_ss_w.p;
+  int rc;
+  if ((rc = upload(h->d_ss_tlo, tlo.data(), (size_t)n, h->stream))) return rc;
+  if ((rc = upload(h->d_ss_thi, thi.data(), (size_t)n, h->stream))) return rc;
+  if ((rc = upload(h->d_ss_w, w.data(), (size_t)n, h->stream))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  if (realloc) h->drop_graphs();
+  h->ss_interp_dirty = false;
+  return 0;
 }
 
 int ttb_set_branch_lengths(ttb_handle h, const double* t) {
@@ -544,6 +623,8 @@ int ttb_set_branch_lengths(ttb_handle h, const double* t) {
   if (int rc = h->d_t.alloc(h->n_nodes)) return rc;
   // pageable source: the copy is staged before the call returns, so the caller may reuse `t`
   CK(cudaMemcpyAsync(h->d_t.p, t, h->n_nodes * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->h_t.assign(t, t + h->n_nodes);
+  h->ss_interp_dirty = true;
   if (realloc) h->drop_graphs();
   h->have_t = true;
   return 0;
@@ -560,6 +641,7 @@ int ttb_marginal(ttb_handle h, int32_t flags) {
   if (!had_P) h->drop_graphs();
   if (!lh_only)
     if (int rc = ensure_preorder_state(h, tips)) return rc;
+  if (int rc = update_ss_interp(h)) return rc;
   const int count_diff = lh_only ? 0 : 1;
   const int key = flags;
   auto it = h->graphs.find(key);
@@ -703,6 +785,7 @@ int ttb_profile_marginal(ttb_handle h, int32_t flags, double* ms, int32_t* launc
   if (!had_P) h->drop_graphs();
   if (!lh_only)
     if (int rc = ensure_preorder_state(h, tips)) return rc;
+  if (int rc = update_ss_interp(h)) return rc;
   cudaEvent_t ev[6];
   for (auto& e : ev) CK(cudaEventCreate(&e));
   int nk = 0, pk[4] = {0, 0, 0, 0};
@@ -780,6 +863,7 @@ int ttb_mutation_counts(ttb_handle h, double* n_ij, double* T_i) {
   if (int rc = use_device(h)) return rc;
   if (int rc = check_ready(h, true)) return rc;
   if (!n_ij || !T_i) return fail(TTB_EINVAL, "ttb_mutation_counts: null output");
+  if (h->site_specific) return fail(TTB_EUNSUPPORTED, "ttb_mutation_counts: per-site statistics of site-specific models are not implemented");
   const int q = h->q, width = q * q + q;
   const int tiles = h->tiles();
   int chunks = std::max(1, std::min(h->n_nodes - 1, (148 * 8 + tiles - 1) / tiles));

@@ -63,6 +63,19 @@ struct TtbDev {
   const double* vinv;    // [q][q]
   const double* Pi;      // [q]
   const double* mu;      // [1] (device scalar so that a new rate does not invalidate the graph)
+  // site-specific model (gtr_site_specific.py): per-pattern eigen-systems, pattern-contiguous planes
+  int site_specific;
+  const double* ss_eig;   // [q][ld]      eigenvalue k of pattern a at k*ld + a
+  const double* ss_mu;    // [ld]
+  const double* ss_V;     // [q*q][ld]    V_a[i][k]    at (i*q+k)*ld + a
+  const double* ss_Vinv;  // [q*q][ld]    Vinv_a[k][j] at (k*q+j)*ld + a
+  const double* ss_Pi;    // [q][ld]
+  const double* ss_tlo;   // [n_nodes] interpolation bracket of every branch length on the 61-point grid
+  const double* ss_thi;   // [n_nodes]
+  const double* ss_w;     // [n_nodes] (t - t_lo)/(t_hi - t_lo), or < 0: evaluate exp(Qt) exactly
+  const double* ss_grid;  // [ss_ngrid] the grid itself (branch objective at trial lengths)
+  int ss_ngrid;
+  double ss_tmax;         // interpolate while t < ss_tmax (= 10 / rate_scale), 0 = never
   // state
   int pq;        // stride of one exp(Qt) matrix in doubles (q*q rounded up to even: 16-byte multiple for TMA)
   int tu_stride; // stride of one tip table in doubles (n_codes*q rounded up to even)
@@ -185,6 +198,78 @@ __global__ void tip_table_kernel(TtbDev p, const int* __restrict__ tip_nodes) {
 }
 
 // ---------------------------------------------------------------------------------------
+// A9: site-specific GTR.  Reference: GTR_site_specific._expQt / expQt / propagate_profile /
+// evolve (gtr_site_specific.py:350-437).  Every pattern a has its own eigen-system, so
+//   expQt_a(t) = V_a diag(e_k) Vinv_a,  e_k = exp(lambda_k mu_a t)
+// and for t * rate_scale < 10 the reference interpolates the stacked matrices linearly on a
+// 61-point t-grid (:331-348,367-371); by linearity that is the same matrix with
+//   e_k = e_k(t_lo) + (e_k(t_hi) - e_k(t_lo)) * (t - t_lo)/(t_hi - t_lo).
+// The up-message is clamped at 1e-12 (:406), the matrix itself is not clamped.
+// Per-thread view: this thread's pattern column of the pattern-contiguous model planes.
+// ---------------------------------------------------------------------------------------
+template <int Q>
+struct SiteModel {
+  const double* V;
+  const double* Vi;
+  const double* lam;
+  double mu;
+  long long ld;
+  __device__ SiteModel(const TtbDev& p, long long a) : V(p.ss_V + a), Vi(p.ss_Vinv + a), lam(p.ss_eig + a), mu(p.ss_mu[a]), ld(p.ld) {}
+  __device__ __forceinline__ void efac_at(double t, double tlo, double thi, double w, double (&e)[Q]) const {
+    if (w < 0.0) {
+#pragma unroll
+      for (int k = 0; k < Q; ++k) e[k] = exp(t * mu * __ldg(lam + (size_t)k * ld));
+    } else {
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        const double l = mu * __ldg(lam + (size_t)k * ld);
+        const double elo = exp(tlo * l), ehi = exp(thi * l);
+        e[k] = elo + (ehi - elo) * w;
+      }
+    }
+  }
+  __device__ __forceinline__ void efac(const TtbDev& p, int node, double (&e)[Q]) const {
+    efac_at(p.t[node], p.ss_tlo[node], p.ss_thi[node], p.ss_w[node], e);
+  }
+  // child -> parent: U[j] = max(1e-12, sum_i S[i] P[i][j])
+  __device__ __forceinline__ void up(const double (&S)[Q], const double (&e)[Q], double (&U)[Q], bool clamp = true) const {
+    double wk[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < Q; ++i) acc = fma(S[i], __ldg(V + (size_t)(i * Q + k) * ld), acc);
+      wk[k] = acc * e[k];
+    }
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < Q; ++k) acc = fma(wk[k], __ldg(Vi + (size_t)(k * Q + j) * ld), acc);
+      U[j] = clamp ? fmax(TTB_TINY, acc) : acc;
+    }
+  }
+  // parent -> child: msg[i] = sum_j P[i][j] O[j]
+  __device__ __forceinline__ void down(const double (&O)[Q], const double (&e)[Q], double (&msg)[Q]) const {
+    double wk[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < Q; ++j) acc = fma(__ldg(Vi + (size_t)(k * Q + j) * ld), O[j], acc);
+      wk[k] = acc * e[k];
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < Q; ++k) acc = fma(__ldg(V + (size_t)(i * Q + k) * ld), wk[k], acc);
+      msg[i] = acc;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
 // Shared-memory ring of the level kernels.
 // ---------------------------------------------------------------------------------------
 template <int Q>
@@ -265,7 +350,7 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // Block = (run of nodes of the level given by group_ptr, one 128-pattern tile).
 // Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
-template <int Q>
+template <int Q, bool SS>
 __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -289,8 +374,12 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
     uint64_t* bar = pipe.full + s;
     const int nch = c.nch();
     uint32_t bytes = 32;
-    for (int b = 0; b < nch; ++b)
-      bytes += (c.src(b) >= 0) ? (uint32_t)(RPC * cols * 8 + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
+    for (int b = 0; b < nch; ++b) {
+      if (SS)  // site-specific: the transition matrices are per pattern, nothing per branch to stage
+        bytes += (c.src(b) >= 0) ? (uint32_t)(RPC * cols * 8) : (uint32_t)cols;
+      else
+        bytes += (c.src(b) >= 0) ? (uint32_t)(RPC * cols * 8 + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
+    }
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, bytes);
       tma_load_1d((void*)pipe.desc(s), chunks + k0 + u, 32, bar);
@@ -304,13 +393,13 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
           tma_load_1d(pipe.rows(s) + (b * RPC + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, bar);
         else if (r == Q)
           tma_load_1d(pipe.rows(s) + (b * RPC + Q) * TTB_TILE, p.F + (size_t)src * p.ld + a0, cols * 8, bar);
-        else
+        else if (!SS)
           tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
       } else {
         const int row = -1 - src;
         if (r == 0)
           tma_load_1d(pipe.codes(s) + b * TTB_TILE, p.codes + (size_t)row * p.ld + a0, cols, bar);
-        else if (r == 1)
+        else if (r == 1 && !SS)
           tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, bar);
       }
     }
@@ -338,7 +427,22 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
     if (act) {
       for (int b = 0; b < nch; ++b) {
         double U[Q];
-        if (c.src(b) < 0) {
+        if constexpr (SS) {
+          const SiteModel<Q> sm(p, a);
+          double sc[Q], e[Q];
+          if (c.src(b) < 0) {
+            const int code = pipe.codes(s)[b * TTB_TILE + tid];
+#pragma unroll
+            for (int i = 0; i < Q; ++i) sc[i] = __ldg(p.code_prof + code * Q + i);
+          } else {
+            const double* rows = pipe.rows(s) + (b * RPC) * TTB_TILE + tid;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) sc[i] = rows[i * TTB_TILE];
+            F += rows[Q * TTB_TILE];
+          }
+          sm.efac(p, c.cnode(b), e);
+          sm.up(sc, e, U);
+        } else if (c.src(b) < 0) {
           const int code = pipe.codes(s)[b * TTB_TILE + tid];
           const double* tu = pipe.TU(s) + b * p.tu_stride + code * Q;
 #pragma unroll
@@ -435,7 +539,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
 // A5': root.  Reference: total_LH_and_root_sequence, treeanc.py:814-838.
 //   profile_r = normalize(Pi * S_r);  LH_a = F_r + log Z_r;  partial sums of LH_a * m_a.
 // ---------------------------------------------------------------------------------------
-template <int Q>
+template <int Q, bool SS>
 __global__ void __launch_bounds__(TTB_BLOCK) root_kernel(TtbDev p, int lh_only) {
   __shared__ double sred[TTB_BLOCK / 32];
   const long long a = (long long)blockIdx.x * TTB_BLOCK + threadIdx.x;
@@ -447,7 +551,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) root_kernel(TtbDev p, int lh_only) 
     double Z = 0.0;
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-      R[j] = p.Pi[j] * s[(size_t)j * p.ld];
+      R[j] = (SS ? p.ss_Pi[(size_t)j * p.ld + a] : p.Pi[j]) * s[(size_t)j * p.ld];   // Pi.T at the root, treeanc.py:817-820
       Z += R[j];
     }
     const double lh = p.F[(size_t)slot * p.ld + a] + log(Z);
@@ -551,7 +655,7 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // Tips take part only with TIPS (reconstruct_tip_states).
 // Stage rows: [0, Q) parent profile, child b -> rows [Q + b*Q, Q + (b+1)*Q) = S_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool TIPS>
+template <int Q, bool TIPS, bool SS>
 __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -575,8 +679,12 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
     const int nch = c.nch();
     const bool first = c.flags & 1;
     uint32_t bytes = 32 + (first ? (uint32_t)(Q * cols * 8) : 0u);
-    for (int b = 0; b < nch; ++b)
-      bytes += (c.src(b) >= 0) ? (uint32_t)(Q * cols * 8 + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
+    for (int b = 0; b < nch; ++b) {
+      if (SS)
+        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * cols * 8 + cols) : (uint32_t)(2 * cols);
+      else
+        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * cols * 8 + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
+    }
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, bytes);
       tma_load_1d((void*)pipe.desc(s), chunks + k0 + u, 32, bar);
@@ -589,7 +697,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
       const int b = job / (Q + 2), r = job % (Q + 2);
       const int src = c.src(b);
       if (r == Q + 1) {
-        tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
+        if (!SS) tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
       } else if (src >= 0) {
         if (r < Q)
           tma_load_1d(pipe.rows(s) + (Q + b * Q + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, bar);
@@ -599,9 +707,9 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
         const int row = -1 - src;
         if (r == 0)
           tma_load_1d(pipe.codes(s) + b * TTB_TILE, p.codes + (size_t)row * p.ld + a0, cols, bar);
-        else if (r == 1)
-          tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, bar);
-        else if (r == 2)
+        else if (r == 1) {
+          if (!SS) tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, bar);
+        } else if (r == 2)
           tma_load_1d(pipe.oidx(s) + b * TTB_TILE, p.idxtip + (size_t)row * p.ld + a0, cols, bar);
       }
     }
@@ -638,7 +746,38 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
           ip = p.idx + (size_t)src * p.ld + a;
         }
         int best = 0;
-        if constexpr (Q <= 8) {
+        if constexpr (SS) {
+          // site-specific model: per-pattern eigen-system instead of a staged exp(Qt)
+          const SiteModel<Q> sm(p, a);
+          double U[Q], Sc[Q], O[Q], e[Q], msg[Q];
+          if (TIPS && src < 0) {
+            const int code = pipe.codes(s)[b * TTB_TILE + tid];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) Sc[j] = __ldg(p.code_prof + code * Q + j);
+          } else {
+            const double* rows = pipe.rows(s) + (Q + b * Q) * TTB_TILE + tid;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) Sc[i] = rows[i * TTB_TILE];
+          }
+          sm.efac(p, c.cnode(b), e);
+          sm.up(Sc, e, U);
+          outgroup_message<Q>(Mp, U, O);
+          sm.down(O, e, msg);
+          double z = 0.0;
+#pragma unroll
+          for (int i = 0; i < Q; ++i) {
+            msg[i] *= Sc[i];
+            z += msg[i];
+          }
+          const double inv = 1.0 / z;
+          double bv = -1.0;
+#pragma unroll
+          for (int i = 0; i < Q; ++i) {
+            const double x = msg[i] * inv;
+            out[(size_t)i * p.ld] = x;
+            if (x > bv) { bv = x; best = i; }
+          }
+        } else if constexpr (Q <= 8) {
           // small alphabets: every q-vector in registers
           double U[Q], Sc[Q], O[Q];
           if (TIPS && src < 0) {
@@ -761,7 +900,7 @@ __device__ __forceinline__ void node_subtree(const TtbDev& p, int n, long long a
 // (pp, pc) of the branch above node n from resident messages: pc = S_n, pp = O_n
 // (marginal_branch_profile, treeanc.py:1122-1146).  kind 1 = merged root branch
 // (treeanc.py:1317-1326): n = n1, pp = normalize(S_n2 * Pi).
-template <int Q>
+template <int Q, bool SS = false>
 __device__ __forceinline__ void branch_profiles(const TtbDev& p, int n, int kind, long long a, double (&pp)[Q], double (&pc)[Q]) {
   node_subtree<Q>(p, n, a, pc);
   if (kind == 1) {
@@ -773,7 +912,7 @@ __device__ __forceinline__ void branch_profiles(const TtbDev& p, int n, int kind
     double z = 0.0;
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-      pp[j] = s2[j] * p.Pi[j];
+      pp[j] = s2[j] * (SS ? p.ss_Pi[(size_t)j * p.ld + a] : p.Pi[j]);
       z += pp[j];
     }
     const double inv = 1.0 / z;
@@ -786,18 +925,25 @@ __device__ __forceinline__ void branch_profiles(const TtbDev& p, int n, int kind
   const double* m = p.M + (size_t)p.int_slot[up] * Q * p.ld + a;
 #pragma unroll
   for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, m[(size_t)j * p.ld]);
-  const double* Pc = p.P + (size_t)n * p.pq;
+  if constexpr (SS) {
+    const SiteModel<Q> sm(p, a);
+    double e[Q];
+    sm.efac(p, n, e);
+    sm.up(pc, e, U);
+  } else {
+    const double* Pc = p.P + (size_t)n * p.pq;
 #pragma unroll
-  for (int j = 0; j < Q; ++j) {
-    double u = 0.0;
+    for (int j = 0; j < Q; ++j) {
+      double u = 0.0;
 #pragma unroll
-    for (int i = 0; i < Q; ++i) u = fma(pc[i], Pc[i * Q + j], u);
-    U[j] = u;
+      for (int i = 0; i < Q; ++i) u = fma(pc[i], Pc[i * Q + j], u);
+      U[j] = u;
+    }
   }
   outgroup_message<Q>(Mp, U, pp);
 }
 
-template <int Q>
+template <int Q, bool SS>
 __global__ void __launch_bounds__(TTB_BLOCK) fetch_node_kernel(TtbDev p, int node, int which, double* __restrict__ out) {
   const long long a = (long long)blockIdx.x * TTB_BLOCK + threadIdx.x;
   if (a >= p.Lp) return;
@@ -807,9 +953,9 @@ __global__ void __launch_bounds__(TTB_BLOCK) fetch_node_kernel(TtbDev p, int nod
   } else if (which == 1) {
     if (node == 0) {
 #pragma unroll
-      for (int j = 0; j < Q; ++j) x[j] = p.Pi[j];
+      for (int j = 0; j < Q; ++j) x[j] = SS ? p.ss_Pi[(size_t)j * p.ld + a] : p.Pi[j];
     } else {
-      branch_profiles<Q>(p, node, 0, a, x, y);
+      branch_profiles<Q, SS>(p, node, 0, a, x, y);
     }
   } else {
     const int row = p.tip_row[node];
@@ -828,7 +974,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) fetch_node_kernel(TtbDev p, int nod
 // patterns; partial[e][b] is reduced in fixed order by branch_reduce_kernel.
 // mode 0: objective; mode 1: sum_a m_a (pp_a . pc_a)  (hamming numerator, gtr.py:871-874).
 // ---------------------------------------------------------------------------------------
-template <int Q>
+template <int Q, bool SS>
 __global__ void __launch_bounds__(TTB_BLOCK) branch_eval_kernel(TtbDev p, const int* __restrict__ nodes, const int* __restrict__ kinds,
                                                                const double* __restrict__ ts, int mode, double* __restrict__ partial) {
   __shared__ double sPt[Q * Q];
@@ -836,7 +982,24 @@ __global__ void __launch_bounds__(TTB_BLOCK) branch_eval_kernel(TtbDev p, const 
   const int e = blockIdx.x;
   const int node = nodes[e];
   const int kind = kinds ? kinds[e] : 0;
-  if (mode == 0) {
+  __shared__ double s_interp[3];   // site-specific: {t_lo, t_hi, w} of the trial length
+  if (SS && mode == 0 && threadIdx.x == 0) {
+    const double t = ts[e];
+    double tlo = 0.0, thi = 0.0, w = -1.0;
+    if (p.ss_tmax > 0.0 && t < p.ss_tmax) {   // expQt_interpolator(t), gtr_site_specific.py:367-371
+      int lo = 0, hi = p.ss_ngrid;              // searchsorted(grid, t, 'left') clipped to [1, n-1]
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (p.ss_grid[mid] < t) lo = mid + 1; else hi = mid;
+      }
+      lo = max(1, min(p.ss_ngrid - 1, lo));
+      tlo = p.ss_grid[lo - 1];
+      thi = p.ss_grid[lo];
+      w = (t - tlo) / (thi - tlo);
+    }
+    s_interp[0] = tlo; s_interp[1] = thi; s_interp[2] = w;
+  }
+  if (!SS && mode == 0) {
     const double mt = p.mu[0] * ts[e];
     for (int k = threadIdx.x; k < Q * Q; k += TTB_BLOCK) {
       const int i = k / Q, j = k % Q;
@@ -849,15 +1012,25 @@ __global__ void __launch_bounds__(TTB_BLOCK) branch_eval_kernel(TtbDev p, const 
   double acc = 0.0;
   for (long long a = (long long)blockIdx.y * TTB_BLOCK + threadIdx.x; a < p.Lp; a += (long long)gridDim.y * TTB_BLOCK) {
     double pp[Q], pc[Q];
-    branch_profiles<Q>(p, node, kind, a, pp, pc);
+    branch_profiles<Q, SS>(p, node, kind, a, pp, pc);
     if (mode == 0) {
       double g = 0.0;
+      if constexpr (SS) {
+        // einsum('ai,ija,aj->a', pc, expQt(t), pp), gtr.py:951-952, with the per-pattern matrix
+        const SiteModel<Q> sm(p, a);
+        double ek[Q], w[Q];
+        sm.efac_at(ts[e], s_interp[0], s_interp[1], s_interp[2], ek);
+        sm.down(pp, ek, w);
 #pragma unroll
-      for (int i = 0; i < Q; ++i) {
-        double w = 0.0;
+        for (int i = 0; i < Q; ++i) g = fma(pc[i], w[i], g);
+      } else {
 #pragma unroll
-        for (int j = 0; j < Q; ++j) w = fma(sPt[i * Q + j], pp[j], w);
-        g = fma(pc[i], w, g);
+        for (int i = 0; i < Q; ++i) {
+          double w = 0.0;
+#pragma unroll
+          for (int j = 0; j < Q; ++j) w = fma(sPt[i * Q + j], pp[j], w);
+          g = fma(pc[i], w, g);
+        }
       }
       double val = p.mult[a] * log(g + TTB_SUPERTINY);
       if (p.gap_index >= 0) val *= (1.0 - pp[p.gap_index]) * (1.0 - pc[p.gap_index]);

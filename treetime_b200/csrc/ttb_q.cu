@@ -12,38 +12,56 @@ constexpr int Q = TTB_Q;
 size_t post_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(Pipe<Q>::CB * (Q + 1), d.pq, d.tu_stride); }
 size_t pre_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(Q + Pipe<Q>::CB * Q, d.pq, d.tu_stride); }
 
-int prepare_q(const TtbDev& d) {
+constexpr bool HAS_SS = (Q <= 8);   // site-specific models: nucleotide-sized alphabets only
+
+template <bool SS>
+int prepare_t(const TtbDev& d) {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(post_level_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d))) != cudaSuccess) return (int)e;
-  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d))) != cudaSuccess) return (int)e;
-  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(post_level_kernel<Q, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d))) != cudaSuccess) return (int)e;
   return 0;
 }
 
-int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
+int prepare_q(const TtbDev& d) {
+  if (int e = prepare_t<false>(d)) return e;
+  if constexpr (HAS_SS) {
+    if (int e = prepare_t<true>(d)) return e;
+  }
+  return 0;
+}
+
+template <bool SS>
+int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
   const TtbDev& d = pl.d;
   const int tiles = pl.tiles;
   int nk = 0;
   if (ev) cudaEventRecord(ev[0], s);
-  const int nthr = d.n_nodes * Q;
-  expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
-  const long long ntab = (long long)d.n_tips * d.n_codes * Q;
-  tip_table_kernel<Q><<<(unsigned)((ntab + 255) / 256), 256, 0, s>>>(d, pl.d_tip_nodes);
-  nk += 2;
+  if (!SS) {
+    const int nthr = d.n_nodes * Q;
+    expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
+    const long long ntab = (long long)d.n_tips * d.n_codes * Q;
+    tip_table_kernel<Q><<<(unsigned)((ntab + 255) / 256), 256, 0, s>>>(d, pl.d_tip_nodes);
+    nk += 2;
+  }
   if (ev) { cudaEventRecord(ev[1], s); pk[0] = nk; }
   const size_t psm = post_smem(d);
-  // level 1 (all children are tips) is a pure write stream: dedicated kernel, no pipeline
-  post_leaf_level_kernel<Q><<<(unsigned)((long long)pl.n_post_leaf_nodes * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_post_chunks,
-                                                                                                  pl.d_post_node_chunk, tiles);
-  ++nk;
-  for (int l = 1; l < pl.n_post_levels; ++l) {
+  int l0 = 0;
+  if (!SS) {
+    // level 1 (all children are tips) is a pure write stream: dedicated kernel, no pipeline
+    post_leaf_level_kernel<Q><<<(unsigned)((long long)pl.n_post_leaf_nodes * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_post_chunks,
+                                                                                                    pl.d_post_node_chunk, tiles);
+    ++nk;
+    l0 = 1;
+  }
+  for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
-    post_level_kernel<Q><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, psm, s>>>(d, pl.d_post_chunks,
-                                                                                         pl.d_post_group_ptr + L.group_off, tiles);
+    post_level_kernel<Q, SS><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, psm, s>>>(d, pl.d_post_chunks,
+                                                                                             pl.d_post_group_ptr + L.group_off, tiles);
     ++nk;
   }
   if (ev) { cudaEventRecord(ev[2], s); pk[1] = nk - pk[0]; }
-  root_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d, pl.lh_only ? 1 : 0);
+  root_kernel<Q, SS><<<tiles, TTB_BLOCK, 0, s>>>(d, pl.lh_only ? 1 : 0);
   ++nk;
   if (!pl.lh_only) {
     zero_slots_kernel<<<4, 256, 0, s>>>(d);
@@ -56,9 +74,9 @@ int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
       const TtbLevelLaunch& L = pl.pre_levels[l];
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
       if (pl.tips)
-        pre_level_kernel<Q, true><<<grid, TTB_BLOCK, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
+        pre_level_kernel<Q, true, SS><<<grid, TTB_BLOCK, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
       else
-        pre_level_kernel<Q, false><<<grid, TTB_BLOCK, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
+        pre_level_kernel<Q, false, SS><<<grid, TTB_BLOCK, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
       ++nk;
     }
   }
@@ -69,13 +87,33 @@ int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   return nk;
 }
 
+int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
+  if constexpr (HAS_SS) {
+    if (pl.d.site_specific) return enqueue_pass_t<true>(pl, s, ev, pk);
+  }
+  return enqueue_pass_t<false>(pl, s, ev, pk);
+}
+
 void fetch_node_q(const TtbDev& d, int tiles, int node, int which, double* out, cudaStream_t s) {
-  fetch_node_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d, node, which, out);
+  if constexpr (HAS_SS) {
+    if (d.site_specific) {
+      fetch_node_kernel<Q, true><<<tiles, TTB_BLOCK, 0, s>>>(d, node, which, out);
+      return;
+    }
+  }
+  fetch_node_kernel<Q, false><<<tiles, TTB_BLOCK, 0, s>>>(d, node, which, out);
 }
 
 void branch_eval_q(const TtbDev& d, int n_eval, int nb, const int* nodes, const int* kinds, const double* ts, int mode,
                    double* partial, double* out, cudaStream_t s) {
-  branch_eval_kernel<Q><<<dim3(n_eval, nb), TTB_BLOCK, 0, s>>>(d, nodes, kinds, ts, mode, partial);
+  bool done = false;
+  if constexpr (HAS_SS) {
+    if (d.site_specific) {
+      branch_eval_kernel<Q, true><<<dim3(n_eval, nb), TTB_BLOCK, 0, s>>>(d, nodes, kinds, ts, mode, partial);
+      done = true;
+    }
+  }
+  if (!done) branch_eval_kernel<Q, false><<<dim3(n_eval, nb), TTB_BLOCK, 0, s>>>(d, nodes, kinds, ts, mode, partial);
   branch_reduce_kernel<<<(n_eval + 127) / 128, 128, 0, s>>>(partial, n_eval, nb, out);
 }
 

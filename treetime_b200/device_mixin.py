@@ -101,25 +101,28 @@ class DeviceMarginalMixin(object):
             eng.set_patterns(codes, table, self.data.multiplicity()[lo:hi])
             self._device_patterns = True
         g = gtr_arrays(self.gtr)
+        upload_model = True
         if g['site_specific']:
             lo, hi = self._shard()
             g = dict(g, eigenvals=g['eigenvals'][:, lo:hi], v=g['v'][:, :, lo:hi], v_inv=g['v_inv'][:, :, lo:hi],
-                     Pi=g['Pi'][:, lo:hi], mu=g['mu'][lo:hi], t_grid=self._t_grid())
+                     Pi=g['Pi'][:, lo:hi], mu=g['mu'][lo:hi])
+            # the per-pattern model is megabytes: re-upload only when it changed
+            fp = (id(self.gtr), float(np.sum(g['mu'])), float(np.sum(g['eigenvals'])), float(np.sum(g['Pi'][0])), lo, hi,
+                  bool(g['approximate']), self._device_data_id)
+            upload_model = fp != getattr(self, '_device_model_fp', None)
+            self._device_model_fp = fp
+        else:
+            self._device_model_fp = None
         tvec = np.array([self._branch_length_to_gtr(n) for n in topo.nodes], dtype=np.float64)
         lam = np.max(g['eigenvals']) * np.max(g['mu'])
         if lam * tvec[1:].max() > 10:
             raise ValueError('Error in computing exp(Q * t): Q has positive eigenvalues or the branch length t is too large. '
                              'This is most likely caused by incorrect input data.')     # gtr.py:1041-1047
-        eng.set_gtr(g)
+        if upload_model:
+            eng.set_gtr(g)
         eng.set_branch_lengths(tvec)
         self._t_last = tvec
         return eng
-
-    def _t_grid(self):
-        from .gtr import GTRSiteSpecific  # noqa: F401
-        rs = self.gtr.rate_scale
-        return (1.0 / rs) * np.concatenate((np.linspace(0, 0.1, 11)[:-1], np.linspace(0.1, 1, 21)[:-1],
-                                            np.linspace(1, 5, 21)[:-1], np.linspace(5, 10, 11)))
 
     def _gather_patterns(self, x, axis=0):
         return x if self.comm.world_size == 1 else self.comm.allgather(x, axis=axis)

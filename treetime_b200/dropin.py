@@ -112,8 +112,8 @@ class B200MarginalMixin(DeviceMarginalMixin):
     def _device_ok(self):
         from . import _lib
         g = self.gtr
-        if getattr(g, 'is_site_specific', False):
-            return 'site-specific models run in the reference'
+        if getattr(g, 'is_site_specific', False) and int(g.n_states) > 8:
+            return 'site-specific models with more than 8 states run in the reference'
         if self._engine is None and self._engine_factory.__module__ == 'treetime_b200.device_mixin':
             if not _lib.load().ttb_supports_n_states(int(g.n_states)):
                 return 'no kernels for %d states' % g.n_states

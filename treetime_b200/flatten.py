@@ -116,6 +116,13 @@ def encode_tips(topo, compressed_alignment, profile_map, n_states, Lp):
     return codes, table, chars
 
 
+def expqt_t_grid(rate_scale):
+    """The 61-point grid on which the reference interpolates site-specific exp(Qt)
+    (gtr_site_specific.py:336-344)."""
+    return (1.0 / rate_scale) * np.concatenate((np.linspace(0, 0.1, 11)[:-1], np.linspace(0.1, 1, 21)[:-1],
+                                                np.linspace(1, 5, 21)[:-1], np.linspace(5, 10, 11)))
+
+
 def gtr_arrays(gtr):
     """GTR object (reference's or ours) -> dict of arrays for the engine/oracle."""
     Pi = np.ascontiguousarray(gtr.Pi, dtype=np.float64)
@@ -128,6 +135,7 @@ def gtr_arrays(gtr):
         d['mu'] = np.ascontiguousarray(gtr.mu, dtype=np.float64)
         d['rate_scale'] = float(gtr.rate_scale)
         d['approximate'] = bool(getattr(gtr, 'approximate', True))
+        d['t_grid'] = expqt_t_grid(d['rate_scale'])
     else:
         d['site_specific'] = False
         d['mu'] = float(gtr.mu)
