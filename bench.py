@@ -34,6 +34,8 @@ WORKLOADS = {
     'cfg2': (2000, 10000, 'nuc', 5e-4, '2k tips x 10 kb nucleotide (BASELINE.json configs[1])'),
     'cfg1': (200, 1400, 'nuc', 2e-3, '200-tip x 1.4 kb nucleotide (BASELINE.json configs[0])'),
     'cfg4': (5000, 1000, 'aa_nogap', 1e-2, '5k tips x 1,000-site amino-acid alignment, 20-state model (BASELINE.json configs[3])'),
+    'cfg5': (100000, 3750, 'nuc_site_specific', 3.3e-5, '100k tips x 30 kb nucleotide with site-specific GTR, one of 8 pattern shards '
+                                                       '(3,750 uncompressed sites per GPU) (BASELINE.json configs[4])'),
     'tiny': (64, 500, 'nuc', 1e-2, 'smoke-sized'),
 }
 SURVEY_BYTES_PER_UPDATE = {5: 165.5, 4: 133.5, 20: 645.5, 22: 709.5}    # 4 q s + 0.5 s + 1.5
@@ -43,12 +45,17 @@ def make_workload(name, seed):
     from treetime_b200 import synth
     from treetime_b200.gtr import GTR
     n_tips, L, alphabet, mean_bl, _ = WORKLOADS[name]
+    compress = True
     if alphabet == 'nuc':
         gtr = GTR.custom(pi=np.array([0.3, 0.2, 0.2, 0.29, 0.01]), W=np.ones((5, 5)), alphabet='nuc')
+    elif alphabet == 'nuc_site_specific':
+        from treetime_b200.gtr import GTRSiteSpecific
+        gtr = GTRSiteSpecific.random(L=L, alphabet='nuc', rng=np.random.default_rng(1000 + seed))
+        compress = False          # treeanc.py:186-187: no pattern compression with site-specific models
     else:
         gtr = GTR.random(alphabet=alphabet, rng=np.random.default_rng(1234))
     tree = synth.random_tree(n_tips, seed=1, mean_bl=mean_bl)           # same tree on every rank
-    topo, flat, g = synth.make_flat_problem(tree, gtr, L, seed)         # rank-specific columns
+    topo, flat, g = synth.make_flat_problem(tree, gtr, L, seed, compress=compress)   # rank-specific columns
     return topo, flat, g
 
 
@@ -138,14 +145,16 @@ def cpu_sample(flat, g, n_patterns):
     s = dict(flat)
     s['tip_codes'] = np.ascontiguousarray(flat['tip_codes'][:, :n])
     s['multiplicity'] = flat['multiplicity'][:n].copy()
-    return s, n
+    if g.get('site_specific'):     # the model is per pattern: slice it with the columns
+        g = dict(g, eigenvals=g['eigenvals'][:, :n], v=g['v'][:, :, :n], v_inv=g['v_inv'][:, :, :n], Pi=g['Pi'][:, :n], mu=g['mu'][:n])
+    return s, n, g
 
 
 def run_cpu(flat, g, n_patterns, repeats):
     """Time the oracle port (oracle/flat_numpy.py: the reference's per-node numpy calls)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import flat_numpy as O
-    s, n = cpu_sample(flat, g, n_patterns)
+    s, n, g = cpu_sample(flat, g, n_patterns)
     n_br = flat['parent'].shape[0] - 1
     times = []
     for _ in range(repeats):

@@ -98,6 +98,7 @@ struct ttb_engine {
   std::vector<int> tip_nodes;
   Sched post, pre_int, pre_all;
   int sched_tiles = -1;  // tiles the group pointers were built for
+  bool sched_ss = false;
   bool prepared = false;
   // device tree
   DBuf<int> d_parent, d_child_ptr, d_child_idx, d_tip_row, d_int_slot, d_tip_nodes;
@@ -114,7 +115,8 @@ struct ttb_engine {
   DBuf<double> d_t, d_eig, d_v, d_vinv, d_Pi, d_mu;
   // site-specific model
   bool site_specific = false;
-  DBuf<double> d_ss_eig, d_ss_mu, d_ss_V, d_ss_Vinv, d_ss_Pi, d_ss_tlo, d_ss_thi, d_ss_w, d_ss_grid;
+  DBuf<double> d_ss_eig, d_ss_mu, d_ss_V, d_ss_Vinv, d_ss_Pi, d_ss_w, d_ss_grid, d_ss_E;
+  DBuf<int> d_ss_lo;
   std::vector<double> ss_grid, h_t;
   double ss_tmax = 0.0;
   bool ss_interp_dirty = true;
@@ -166,7 +168,7 @@ struct ttb_engine {
     d.mu = d_mu.p;
     d.site_specific = site_specific ? 1 : 0;
     d.ss_eig = d_ss_eig.p; d.ss_mu = d_ss_mu.p; d.ss_V = d_ss_V.p; d.ss_Vinv = d_ss_Vinv.p; d.ss_Pi = d_ss_Pi.p;
-    d.ss_tlo = d_ss_tlo.p; d.ss_thi = d_ss_thi.p; d.ss_w = d_ss_w.p; d.ss_grid = d_ss_grid.p;
+    d.ss_lo = d_ss_lo.p; d.ss_w = d_ss_w.p; d.ss_grid = d_ss_grid.p; d.ss_E = d_ss_E.p;
     d.ss_ngrid = (int)ss_grid.size();
     d.ss_tmax = ss_tmax;
     d.pq = (q * q + 1) / 2 * 2;
@@ -250,15 +252,17 @@ void build_sched(ttb_handle h, const std::vector<int>& key, const std::vector<ch
 
 // Split every level into groups of consecutive nodes so that a launch has enough blocks to
 // fill the GPU but every block still pipelines over several chunks.
-void build_groups(Sched& sc, int tiles) {
+void build_groups(Sched& sc, int tiles, bool site_specific) {
   sc.group_ptr.clear();
   sc.launches.clear();
-  const long long target_blocks = 148LL * 32;
+  // site-specific kernels stage a 50 KB model tile per block: longer runs amortise it
+  const long long target_blocks = site_specific ? 148LL * 8 : 148LL * 32;
+  const long long max_group = site_specific ? 128 : 32;
   for (size_t l = 0; l + 1 < sc.level_node_begin.size(); ++l) {
     const int nb = sc.level_node_begin[l], ne = sc.level_node_begin[l + 1];
     const int n = ne - nb;
     long long G = ((long long)n * tiles + target_blocks - 1) / target_blocks;
-    G = std::max(1LL, std::min(32LL, G));
+    G = std::max(1LL, std::min(max_group, G));
     TtbLevelLaunch L;
     L.group_off = (int)sc.group_ptr.size();
     L.n_groups = 0;
@@ -302,13 +306,14 @@ int ensure_state(ttb_handle h, bool tips) {
   const size_t pq = (q * q + 1) / 2 * 2, tus = ((size_t)h->n_codes * q + 1) / 2 * 2;
   if ((rc = h->d_P.alloc((size_t)h->n_nodes * pq))) return rc;
   if ((rc = h->d_TU.alloc((size_t)h->n_tips * tus))) return rc;
-  if (h->sched_tiles != h->tiles()) {
+  if (h->sched_tiles != h->tiles() || h->sched_ss != h->site_specific) {
     for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all}) {
-      build_groups(*sc, h->tiles());
+      build_groups(*sc, h->tiles(), h->site_specific);
       if ((rc = upload(sc->d_group_ptr, sc->group_ptr.data(), sc->group_ptr.size(), h->stream))) return rc;
     }
     CK(cudaStreamSynchronize(h->stream));
     h->sched_tiles = h->tiles();
+    h->sched_ss = h->site_specific;
     h->drop_graphs();
   }
   if (!h->prepared) {
@@ -390,11 +395,12 @@ int ttb_destroy(ttb_handle h) {
                      &h->d_enodes, &h->d_ekinds, &h->post.d_group_ptr, &h->pre_int.d_group_ptr, &h->pre_all.d_group_ptr, &h->post.d_node_chunk};
   for (auto* b : ib) b->release();
   DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_ss_eig, &h->d_ss_mu, &h->d_ss_V, &h->d_ss_Vinv, &h->d_ss_Pi,
-                        &h->d_ss_tlo, &h->d_ss_thi, &h->d_ss_w, &h->d_ss_grid, &h->d_TU, &h->d_P, &h->d_S,
+                        &h->d_ss_w, &h->d_ss_grid, &h->d_ss_E, &h->d_TU, &h->d_P, &h->d_S,
                         &h->d_F, &h->d_M, &h->d_Mtip, &h->d_LH, &h->d_lh_partial, &h->d_results, &h->d_stage,
                         &h->d_partial, &h->d_ets, &h->d_eout};
   for (auto* b : db) b->release();
   h->d_codes.release();
+  h->d_ss_lo.release();
   h->post.d_chunks.release(); h->pre_int.d_chunks.release(); h->pre_all.d_chunks.release();
   h->d_idx.release();
   h->d_idxtip.release();
@@ -578,8 +584,17 @@ int ttb_set_gtr_site_specific(ttb_handle h, const double* eigvals, const double*
   if ((rc = upload_planes(h, h->d_ss_Vinv, Vi.data(), q * q))) return rc;
   if ((rc = upload_planes(h, h->d_ss_Pi, Pi, q))) return rc;
   if ((rc = upload(h->d_ss_grid, t_grid, (size_t)n_grid, h->stream))) return rc;
-  CK(cudaStreamSynchronize(h->stream));   // V / Vi are locals
   h->ss_grid.assign(t_grid, t_grid + n_grid);
+  if ((rc = h->d_ss_E.alloc((size_t)n_grid * q * (size_t)h->ld))) return rc;
+  {
+    const bool was = h->site_specific;
+    h->site_specific = true;
+    ss_grid_table_kernel<<<148 * 8, 256, 0, h->stream>>>(h->dev(), h->d_ss_E.p);
+    h->site_specific = was;
+    h->launches += 1;
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(h->stream));   // V / Vi are locals
   h->ss_tmax = approximate ? 10.0 / rate_scale : 0.0;
   h->ss_interp_dirty = true;
   h->gap_index = gap_index;
@@ -594,21 +609,20 @@ int ttb_set_gtr_site_specific(ttb_handle h, const double* eigvals, const double*
 static int update_ss_interp(ttb_handle h) {
   if (!h->site_specific || !h->ss_interp_dirty) return 0;
   const int n = h->n_nodes, ng = (int)h->ss_grid.size();
-  std::vector<double> tlo(n, 0.0), thi(n, 0.0), w(n, -1.0);
+  std::vector<double> w(n, -1.0);
+  std::vector<int> glo(n, 0);
   for (int i = 1; i < n; ++i) {
     const double t = h->h_t[i];
     if (h->ss_tmax > 0.0 && t < h->ss_tmax) {
       int lo = (int)(std::lower_bound(h->ss_grid.begin(), h->ss_grid.end(), t) - h->ss_grid.begin());
       lo = std::max(1, std::min(ng - 1, lo));
-      tlo[i] = h->ss_grid[lo - 1];
-      thi[i] = h->ss_grid[lo];
-      w[i] = (t - tlo[i]) / (thi[i] - tlo[i]);
+      glo[i] = lo - 1;
+      w[i] = (t - h->ss_grid[lo - 1]) / (h->ss_grid[lo] - h->ss_grid[lo - 1]);
     }
   }
   const bool realloc = !h->d_ss_w.p;
   int rc;
-  if ((rc = upload(h->d_ss_tlo, tlo.data(), (size_t)n, h->stream))) return rc;
-  if ((rc = upload(h->d_ss_thi, thi.data(), (size_t)n, h->stream))) return rc;
+  if ((rc = upload(h->d_ss_lo, glo.data(), (size_t)n, h->stream))) return rc;
   if ((rc = upload(h->d_ss_w, w.data(), (size_t)n, h->stream))) return rc;
   CK(cudaStreamSynchronize(h->stream));
   if (realloc) h->drop_graphs();

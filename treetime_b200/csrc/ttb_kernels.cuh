@@ -70,9 +70,9 @@ struct TtbDev {
   const double* ss_V;     // [q*q][ld]    V_a[i][k]    at (i*q+k)*ld + a
   const double* ss_Vinv;  // [q*q][ld]    Vinv_a[k][j] at (k*q+j)*ld + a
   const double* ss_Pi;    // [q][ld]
-  const double* ss_tlo;   // [n_nodes] interpolation bracket of every branch length on the 61-point grid
-  const double* ss_thi;   // [n_nodes]
+  const int* ss_lo;       // [n_nodes] lower grid index of the interpolation bracket of every branch length
   const double* ss_w;     // [n_nodes] (t - t_lo)/(t_hi - t_lo), or < 0: evaluate exp(Qt) exactly
+  const double* ss_E;     // [ss_ngrid][q][ld] exp(t_g mu_a lambda_k(a)) on the grid: no exp in the level kernels
   const double* ss_grid;  // [ss_ngrid] the grid itself (branch objective at trial lengths)
   int ss_ngrid;
   double ss_tmax;         // interpolate while t < ss_tmax (= 10 / rate_scale), 0 = never
@@ -209,27 +209,35 @@ __global__ void tip_table_kernel(TtbDev p, const int* __restrict__ tip_nodes) {
 // ---------------------------------------------------------------------------------------
 template <int Q>
 struct SiteModel {
-  const double* V;
-  const double* Vi;
+  const double* V;    // V_a[i][k] at V[(i*Q+k)*vs]
+  const double* Vi;   // Vinv_a[k][j] at Vi[(k*Q+j)*vs]
+  long long vs;       // plane stride of V / Vi: ld in global memory, TTB_TILE for a staged tile
   const double* lam;
   double mu;
   long long ld;
-  __device__ SiteModel(const TtbDev& p, long long a) : V(p.ss_V + a), Vi(p.ss_Vinv + a), lam(p.ss_eig + a), mu(p.ss_mu[a]), ld(p.ld) {}
-  __device__ __forceinline__ void efac_at(double t, double tlo, double thi, double w, double (&e)[Q]) const {
+  // model planes read from global memory (fetch / branch kernels)
+  __device__ SiteModel(const TtbDev& p, long long a)
+      : V(p.ss_V + a), Vi(p.ss_Vinv + a), vs(p.ld), lam(p.ss_eig + a), mu(p.ss_mu[a]), ld(p.ld), E(p.ss_E + a) {}
+  // V / Vinv of this block's pattern tile staged in shared memory (level kernels)
+  __device__ SiteModel(const TtbDev& p, long long a, const double* smem_model, int tid)
+      : V(smem_model + tid), Vi(smem_model + Q * Q * TTB_TILE + tid), vs(TTB_TILE), lam(p.ss_eig + a), mu(p.ss_mu[a]), ld(p.ld),
+        E(p.ss_E + a) {}
+  const double* E;   // this pattern's column of the grid table
+  __device__ __forceinline__ void efac_at(double t, int lo, double w, double (&e)[Q]) const {
     if (w < 0.0) {
 #pragma unroll
       for (int k = 0; k < Q; ++k) e[k] = exp(t * mu * __ldg(lam + (size_t)k * ld));
     } else {
+      const double* Elo = E + (size_t)lo * Q * ld;
 #pragma unroll
       for (int k = 0; k < Q; ++k) {
-        const double l = mu * __ldg(lam + (size_t)k * ld);
-        const double elo = exp(tlo * l), ehi = exp(thi * l);
+        const double elo = __ldg(Elo + (size_t)k * ld), ehi = __ldg(Elo + (size_t)(Q + k) * ld);
         e[k] = elo + (ehi - elo) * w;
       }
     }
   }
   __device__ __forceinline__ void efac(const TtbDev& p, int node, double (&e)[Q]) const {
-    efac_at(p.t[node], p.ss_tlo[node], p.ss_thi[node], p.ss_w[node], e);
+    efac_at(p.t[node], p.ss_lo[node], p.ss_w[node], e);
   }
   // child -> parent: U[j] = max(1e-12, sum_i S[i] P[i][j])
   __device__ __forceinline__ void up(const double (&S)[Q], const double (&e)[Q], double (&U)[Q], bool clamp = true) const {
@@ -238,14 +246,14 @@ struct SiteModel {
     for (int k = 0; k < Q; ++k) {
       double acc = 0.0;
 #pragma unroll
-      for (int i = 0; i < Q; ++i) acc = fma(S[i], __ldg(V + (size_t)(i * Q + k) * ld), acc);
+      for (int i = 0; i < Q; ++i) acc = fma(S[i], V[(size_t)(i * Q + k) * vs], acc);
       wk[k] = acc * e[k];
     }
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
       double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < Q; ++k) acc = fma(wk[k], __ldg(Vi + (size_t)(k * Q + j) * ld), acc);
+      for (int k = 0; k < Q; ++k) acc = fma(wk[k], Vi[(size_t)(k * Q + j) * vs], acc);
       U[j] = clamp ? fmax(TTB_TINY, acc) : acc;
     }
   }
@@ -256,18 +264,29 @@ struct SiteModel {
     for (int k = 0; k < Q; ++k) {
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < Q; ++j) acc = fma(__ldg(Vi + (size_t)(k * Q + j) * ld), O[j], acc);
+      for (int j = 0; j < Q; ++j) acc = fma(Vi[(size_t)(k * Q + j) * vs], O[j], acc);
       wk[k] = acc * e[k];
     }
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
       double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < Q; ++k) acc = fma(__ldg(V + (size_t)(i * Q + k) * ld), wk[k], acc);
+      for (int k = 0; k < Q; ++k) acc = fma(V[(size_t)(i * Q + k) * vs], wk[k], acc);
       msg[i] = acc;
     }
   }
 };
+
+// E[g][k][a] = exp(t_g * mu_a * lambda_k(a)): the eigen-factor of gtr_site_specific._expQt (:363) on the
+// interpolation grid (:336-344).  One thread per (g, k, a).
+static __global__ void ss_grid_table_kernel(TtbDev p, double* __restrict__ E) {
+  const long long n = (long long)p.ss_ngrid * p.q * p.ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long a = i % p.ld;
+    const int k = (int)((i / p.ld) % p.q), g = (int)(i / (p.ld * p.q));
+    E[i] = (a < p.Lp) ? exp(p.ss_grid[g] * p.ss_mu[a] * p.ss_eig[(size_t)k * p.ld + a]) : 1.0;
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // Shared-memory ring of the level kernels.
@@ -281,15 +300,18 @@ struct Pipe {
   unsigned char* base;
   uint64_t* full;   // [STAGES] producer -> consumers (transaction barrier)
   uint64_t* empty;  // [STAGES] consumers -> producer (one arrival per warp)
+  uint64_t* mbar;   // site-specific models: "model tile loaded" barrier
+  double* model;    // site-specific models: V and Vinv planes of this block's pattern tile [2*Q*Q][TILE]
   __host__ __device__ static int stage_size(int rows, int pq, int tu_stride) {
     return rows * TTB_TILE * 8 + CB * pq * 8 + CB * tu_stride * 8 + 2 * CB * TTB_TILE + 32;
   }
-  __host__ static size_t smem_bytes(int rows, int pq, int tu_stride) {
-    return 128 + (size_t)STAGES * stage_size(rows, pq, tu_stride);
+  __host__ static size_t smem_bytes(int rows, int pq, int tu_stride, bool site_specific = false) {
+    return 128 + (size_t)STAGES * stage_size(rows, pq, tu_stride) + (site_specific ? (size_t)2 * Q * Q * TTB_TILE * 8 : 0);
   }
   __device__ Pipe(unsigned char* smem, int rows, int pq, int tu_stride) {
     full = reinterpret_cast<uint64_t*>(smem);
     empty = full + STAGES;
+    mbar = empty + STAGES;
     base = smem + 128;
     off_P = rows * TTB_TILE * 8;
     off_TU = off_P + CB * pq * 8;
@@ -297,12 +319,24 @@ struct Pipe {
     off_oidx = off_codes + CB * TTB_TILE;
     off_desc = off_oidx + CB * TTB_TILE;
     stage_bytes = off_desc + 32;
+    model = reinterpret_cast<double*>(base + (size_t)STAGES * stage_bytes);
   }
+  // Stage the per-pattern eigen-systems of this tile once per block (warp 0), wait with wait_model().
+  __device__ void load_model(const TtbDev& p, long long a0, int cols, int lane) const {
+    if (lane == 0) mbar_arrive_expect_tx(mbar, (uint32_t)(2 * Q * Q * cols * 8));
+    __syncwarp();
+    for (int r = lane; r < 2 * Q * Q; r += 32) {
+      const double* src = (r < Q * Q ? p.ss_V + (size_t)r * p.ld : p.ss_Vinv + (size_t)(r - Q * Q) * p.ld) + a0;
+      tma_load_1d(model + (size_t)r * TTB_TILE, src, cols * 8, mbar);
+    }
+  }
+  __device__ void wait_model() const { mbar_wait(mbar, 0); }
   __device__ void init() const {  // one thread
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, TTB_BLOCK / 32);
     }
+    mbar_init(mbar, 1);
     mbar_fence_init();
   }
   __device__ double* rows(int s) const { return reinterpret_cast<double*>(base + (size_t)s * stage_bytes); }
@@ -405,8 +439,10 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
     }
   };
 
+  if (SS && warp == 0) pipe.load_model(p, a0, cols, lane);
   if (warp == 0)
     for (int u = 0; u < min(n_chunks, Pipe<Q>::STAGES - 1); ++u) issue(u);
+  if (SS) pipe.wait_model();
 
   double X[Q];
   double F = 0.0;
@@ -428,7 +464,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
       for (int b = 0; b < nch; ++b) {
         double U[Q];
         if constexpr (SS) {
-          const SiteModel<Q> sm(p, a);
+          const SiteModel<Q> sm(p, a, pipe.model, tid);
           double sc[Q], e[Q];
           if (c.src(b) < 0) {
             const int code = pipe.codes(s)[b * TTB_TILE + tid];
@@ -715,8 +751,10 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
     }
   };
 
+  if (SS && warp == 0) pipe.load_model(p, a0, cols, lane);
   if (warp == 0)
     for (int u = 0; u < min(n_chunks, Pipe<Q>::STAGES - 1); ++u) issue(u);
+  if (SS) pipe.wait_model();
 
   double Mp[Q];
   unsigned int ndiff = 0;
@@ -748,7 +786,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
         int best = 0;
         if constexpr (SS) {
           // site-specific model: per-pattern eigen-system instead of a staged exp(Qt)
-          const SiteModel<Q> sm(p, a);
+          const SiteModel<Q> sm(p, a, pipe.model, tid);
           double U[Q], Sc[Q], O[Q], e[Q], msg[Q];
           if (TIPS && src < 0) {
             const int code = pipe.codes(s)[b * TTB_TILE + tid];
@@ -982,10 +1020,11 @@ __global__ void __launch_bounds__(TTB_BLOCK) branch_eval_kernel(TtbDev p, const 
   const int e = blockIdx.x;
   const int node = nodes[e];
   const int kind = kinds ? kinds[e] : 0;
-  __shared__ double s_interp[3];   // site-specific: {t_lo, t_hi, w} of the trial length
+  __shared__ double s_interp[2];   // site-specific: {lower grid index, w} of the trial length
   if (SS && mode == 0 && threadIdx.x == 0) {
     const double t = ts[e];
-    double tlo = 0.0, thi = 0.0, w = -1.0;
+    double w = -1.0;
+    int glo = 0;
     if (p.ss_tmax > 0.0 && t < p.ss_tmax) {   // expQt_interpolator(t), gtr_site_specific.py:367-371
       int lo = 0, hi = p.ss_ngrid;              // searchsorted(grid, t, 'left') clipped to [1, n-1]
       while (lo < hi) {
@@ -993,11 +1032,10 @@ __global__ void __launch_bounds__(TTB_BLOCK) branch_eval_kernel(TtbDev p, const 
         if (p.ss_grid[mid] < t) lo = mid + 1; else hi = mid;
       }
       lo = max(1, min(p.ss_ngrid - 1, lo));
-      tlo = p.ss_grid[lo - 1];
-      thi = p.ss_grid[lo];
-      w = (t - tlo) / (thi - tlo);
+      glo = lo - 1;
+      w = (t - p.ss_grid[glo]) / (p.ss_grid[lo] - p.ss_grid[glo]);
     }
-    s_interp[0] = tlo; s_interp[1] = thi; s_interp[2] = w;
+    s_interp[0] = (double)glo; s_interp[1] = w;
   }
   if (!SS && mode == 0) {
     const double mt = p.mu[0] * ts[e];
@@ -1019,7 +1057,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) branch_eval_kernel(TtbDev p, const 
         // einsum('ai,ija,aj->a', pc, expQt(t), pp), gtr.py:951-952, with the per-pattern matrix
         const SiteModel<Q> sm(p, a);
         double ek[Q], w[Q];
-        sm.efac_at(ts[e], s_interp[0], s_interp[1], s_interp[2], ek);
+        sm.efac_at(ts[e], (int)s_interp[0], s_interp[1], ek);
         sm.down(pp, ek, w);
 #pragma unroll
         for (int i = 0; i < Q; ++i) g = fma(pc[i], w[i], g);

@@ -9,17 +9,17 @@
 namespace {
 constexpr int Q = TTB_Q;
 
-size_t post_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(Pipe<Q>::CB * (Q + 1), d.pq, d.tu_stride); }
-size_t pre_smem(const TtbDev& d) { return Pipe<Q>::smem_bytes(Q + Pipe<Q>::CB * Q, d.pq, d.tu_stride); }
+size_t post_smem(const TtbDev& d, bool ss = false) { return Pipe<Q>::smem_bytes(Pipe<Q>::CB * (Q + 1), d.pq, d.tu_stride, ss); }
+size_t pre_smem(const TtbDev& d, bool ss = false) { return Pipe<Q>::smem_bytes(Q + Pipe<Q>::CB * Q, d.pq, d.tu_stride, ss); }
 
 constexpr bool HAS_SS = (Q <= 8);   // site-specific models: nucleotide-sized alphabets only
 
 template <bool SS>
 int prepare_t(const TtbDev& d) {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(post_level_kernel<Q, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d))) != cudaSuccess) return (int)e;
-  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d))) != cudaSuccess) return (int)e;
-  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(post_level_kernel<Q, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, SS))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
   return 0;
 }
 
@@ -45,7 +45,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
     nk += 2;
   }
   if (ev) { cudaEventRecord(ev[1], s); pk[0] = nk; }
-  const size_t psm = post_smem(d);
+  const size_t psm = post_smem(d, SS);
   int l0 = 0;
   if (!SS) {
     // level 1 (all children are tips) is a pure write stream: dedicated kernel, no pipeline
@@ -69,7 +69,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   }
   if (ev) { cudaEventRecord(ev[3], s); pk[2] = nk - pk[0] - pk[1]; }
   if (!pl.lh_only) {
-    const size_t rsm = pre_smem(d);
+    const size_t rsm = pre_smem(d, SS);
     for (int l = 0; l < pl.n_pre_levels; ++l) {
       const TtbLevelLaunch& L = pl.pre_levels[l];
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
