@@ -128,14 +128,17 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def ncu_traffic(workload):
-    """dram bytes per pass of the dominant kernel from the committed ncu capture, if any."""
+def ncu_traffic(workload, kernel_prefix):
+    """DRAM bytes per pass (read + write, summed over the level launches) of the dominant kernel from
+    the committed ncu capture (profiles/traffic.json, made by tools/ncu_traffic.py), or None."""
     p = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get(workload)
-        except Exception:
-            return None
+    try:
+        ks = json.load(open(p))[workload]['kernels']
+        for name, a in ks.items():
+            if name.startswith(kernel_prefix):
+                return a['dram_bytes']
+    except Exception:
+        pass
     return None
 
 
@@ -164,7 +167,21 @@ def run_cpu(flat, g, n_patterns, repeats):
     return n_br * n, times, res.total_LH
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there)
+    must not pollute it: point fd 1 at stderr for the whole run and keep the real stdout aside."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_stdout_fd, obj):
+    os.write(real_stdout_fd, (json.dumps(obj) + '\n').encode())
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -198,7 +215,7 @@ def main():
         val = updates / (ms / 1e3)
         sample = 'first %d of %d compressed patterns of the same tree/alignment per step (cost is linear in patterns)' % (
             min(n_pat, flat['multiplicity'].shape[0]), flat['multiplicity'].shape[0])
-        print(json.dumps({
+        _emit(real_stdout, {
             'impl': 'reference', 'metric': 'marginal ancestral reconstruction branch x pattern updates/s', 'value': val,
             'unit': 'updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -207,7 +224,7 @@ def main():
             'e2e': {'value': val, 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'note': 'oracle/flat_numpy.py: flat-array port of the reference numpy path (bit-identical to the '
                     'reference on the build container); single-threaded like the reference',
-        }))
+        })
         return 0
 
     # ------------------------------------------------------------------ GPU arm
@@ -385,7 +402,7 @@ def main():
                 'bound': 'hbm', 'kernel': '%s_level_kernel<%d> (%d level launches per pass)' % ('pre' if dom == 'preorder' else 'post', q, dom_launches),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
                 'algorithmic_bytes_per_pass': int(dom_bytes), 'kernel_ms_per_pass': dom_ms,
-                'traffic': ncu_traffic(args.workload),
+                'traffic': ncu_traffic(args.workload, 'pre_level_kernel' if dom == 'preorder' else 'post_level_kernel'),
                 'phases_ms': {k: v[0] for k, v in phases.items()}, 'phase_launches': {k: v[1] for k, v in phases.items()},
                 'whole_pass': {'algorithmic_bytes': int(post_b + pre_b), 'bytes_per_update': (post_b + pre_b) / float(updates_local),
                                'achieved_gbs': (post_b + pre_b) / (pass_ms / 1e3) / 1e9,
@@ -410,7 +427,7 @@ def main():
                                    'sample': 'one pass over the first %d of %d patterns (same tree, same model); '
                                              'host has %d cores, the reference path is single-threaded numpy'
                                              % (min(n_pat, Lp), Lp, os.cpu_count() or 0)}
-        print(json.dumps(out))
+        _emit(real_stdout, out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
