@@ -169,3 +169,51 @@ def test_dropin_treetime_run_marginal():
         assert np.isclose(a.numdate, b.numdate, rtol=0, atol=1e-6)
         assert np.isclose(a.branch_length, b.branch_length, rtol=1e-7, atol=1e-12)
     assert np.isclose(ref.tree.sequence_marginal_LH, ours.tree.sequence_marginal_LH, rtol=1e-10)
+
+
+def test_dropin_batched_branch_grids_match_reference_interpolators():
+    """N1: BranchLenInterpolator tables built from device-evaluated grids equal the reference's."""
+    refenv.activate()
+    import oracle_engine
+    from io import StringIO
+    from Bio import Phylo
+    from Bio.Align import MultipleSeqAlignment
+    from Bio.SeqRecord import SeqRecord
+    from Bio.Seq import Seq
+    from treetime import GTR as RG, ClockTree
+    from treetime.branch_len_interpolator import BranchLenInterpolator
+    from treetime_b200 import synth
+    from treetime_b200.dropin import accelerate, branch_length_grid, B200ClockMixin
+    from treetime_b200.gtr import GTR
+    pi = np.array([.3, .2, .2, .29, .01])
+    T = synth.random_tree(20, seed=51, mean_bl=0.004, zero_frac=0.2)
+    g = GTR.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc')
+    aln = {k: g.alphabet[v] for k, v in synth.evolve_alignment(T, 400, g.Pi, g.W, seed=51).items()}
+    dates = {k: 2000.0 + i * 0.1 for i, k in enumerate(sorted(aln))}
+    mk = lambda: RG.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc')  # noqa: E731
+    mkaln = lambda: MultipleSeqAlignment([SeqRecord(Seq(''.join(aln[k])), id=k, name=k, description='') for k in aln])  # noqa: E731
+    mktree = lambda: Phylo.read(StringIO(T.to_newick()), 'newick')  # noqa: E731
+    kw = dict(dates=dates, verbose=0, rng_seed=1, branch_length_mode='marginal')
+    ref = ClockTree(tree=mktree(), aln=mkaln(), gtr=mk(), **kw)
+    ours = accelerate(ClockTree)(tree=mktree(), aln=mkaln(), gtr=mk(), engine_factory=oracle_engine.factory, **kw)
+    assert isinstance(ours, B200ClockMixin)
+    ref.init_date_constraints()
+    ours.init_date_constraints()
+    assert ours._b200_live and 'prob_t_profiles' not in ours.gtr.__dict__
+    n_checked = 0
+    for a, b in zip(ref.tree.find_clades(), ours.tree.find_clades()):
+        if a.up is None:
+            continue
+        ia, ib = a.branch_length_interpolator, b.branch_length_interpolator
+        # same grid (our restated grid construction) and same tabulated values
+        assert np.array_equal(ia.x, ib.x)
+        assert np.allclose(ia.y, ib.y, rtol=1e-9, atol=1e-8), np.abs(ia.y - ib.y).max()
+        assert np.isclose(ia.peak_pos, ib.peak_pos)
+        gexp = branch_length_grid(a.mutation_length, ref.one_mutation, ref.branch_grid_points)
+        assert set(np.unique(gexp)) >= set(ia.x) or len(ia.x) <= len(gexp)
+        n_checked += 1
+    assert n_checked == 38
+    # the proxy still behaves like the (pp, pc) tuple when somebody indexes it
+    n = list(ours.tree.find_clades())[3]
+    m = list(ref.tree.find_clades())[3]
+    assert np.array_equal(n.profile_pair[0], m.profile_pair[0]) and np.array_equal(n.profile_pair[1], m.profile_pair[1])

@@ -46,10 +46,25 @@ class DeviceMarginalMixin(object):
 
     # -- device synchronisation -------------------------------------------------------------
     def _flat(self):
+        """The flattening the DEVICE currently knows (node._fid = device node id).  It is rebuilt only
+        at the start of a pass (_refresh_topology): between passes the per-node results on the device
+        stay addressable even if the host tree was edited, exactly like the reference's stale per-node
+        attributes after prune_short_branches / polytomy resolution."""
         if self._topo is None:
+            self._refresh_topology()
+        return self._topo
+
+    def _topology_changed(self):
+        return self._topo is None or getattr(self, '_topo_dirty', False)
+
+    def _refresh_topology(self):
+        if self._topology_changed():
             self._topo = FlatTopology(self.tree.root)
             for i, n in enumerate(self._topo.nodes):
                 n._fid = i
+            self._topo_dirty = False
+            self._cache = {}
+            self._seq_cache = {}
         return self._topo
 
     def _shard(self):
@@ -82,7 +97,7 @@ class DeviceMarginalMixin(object):
 
     def _sync_device(self):
         """Bring the engine up to date with tree topology, patterns, model and branch lengths."""
-        topo = self._flat()
+        topo = self._refresh_topology()
         if self._engine is None:
             self._engine = self._engine_factory(self.gtr.n_states, self.device)
         eng = self._engine
@@ -162,7 +177,7 @@ class DeviceMarginalMixin(object):
                 self._unsupported("sampling every node from its profile is not provided; sample_from_profile='root' is")
         else:
             raise ValueError("sample_from_profile must be a bool or 'root'")
-        if any(getattr(n, 'mask', None) is not None for n in self._flat().nodes):
+        if any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
             self._unsupported('per-branch masks (ARG mode) are not supported on the device path')
         eng = self._sync_device()
         topo = self._flat()

@@ -74,30 +74,27 @@ class B200MarginalMixin(DeviceMarginalMixin):
         self._b200_live = False
         super(B200MarginalMixin, self).__init__(*args, **kwargs)
 
-    # -- topology changes invalidate the flattening (prepare_tree / reroot / resolve_polytomies) --
-    def _prepare_nodes(self):
-        super(B200MarginalMixin, self)._prepare_nodes()
-        self._drop_node_caches()
-        self._topo = None
-
-    def _flat(self):
-        """The reference edits `clades` lists in place (prune_short_branches, polytomy resolution)
-        without notifying anybody: re-validate the cached flattening against the live tree."""
+    # -- the reference edits `clades` lists in place (prune_short_branches, polytomy resolution, reroot)
+    #    without telling anybody: compare the cached flattening with the live tree at the start of
+    #    every pass.  Between passes node._fid keeps addressing the device's (older) numbering, which
+    #    mirrors the reference's stale per-node attributes.
+    def _topology_changed(self):
         topo = self._topo
-        if topo is not None:
-            ok = topo.nodes[0] is self.tree.root
-            if ok:
-                cp, ci, nodes = topo.child_ptr, topo.child_idx, topo.nodes
-                for i, n in enumerate(nodes):
-                    kids = n.clades
-                    b = cp[i]
-                    if len(kids) != cp[i + 1] - b or any(nodes[ci[b + k]] is not c for k, c in enumerate(kids)):
-                        ok = False
-                        break
-            if not ok:
-                self._drop_node_caches()
-                self._topo = None
-        return DeviceMarginalMixin._flat(self)
+        if topo is None or topo.nodes[0] is not self.tree.root:
+            return True
+        cp, ci, nodes = topo.child_ptr, topo.child_idx, topo.nodes
+        for i, n in enumerate(nodes):
+            kids = n.clades
+            b = cp[i]
+            if len(kids) != cp[i + 1] - b or any(nodes[ci[b + k]] is not c for k, c in enumerate(kids)):
+                return True
+        return False
+
+    def _refresh_topology(self):
+        if self._topology_changed() and self._topo is not None:
+            for n in self._topo.nodes:
+                n.__dict__.pop('_fid', None)
+        return DeviceMarginalMixin._refresh_topology(self)
 
     def _drop_node_caches(self):
         self._b200_live = False
@@ -135,10 +132,17 @@ class B200MarginalMixin(DeviceMarginalMixin):
                 prev_live = self._b200_live and self.sequence_reconstruction == 'marginal'
                 old = None
                 if self.sequence_reconstruction and not prev_live:
-                    old = {id(n): np.array(n.cseq) for n in self.tree.find_clades()
-                           if n.up is not None and n.cseq is not None and (reconstruct_tip_states or not n.is_terminal())}
+                    old = {}
+                    for n in self.tree.find_clades():
+                        if n.up is not None and (reconstruct_tip_states or not n.is_terminal()):
+                            try:
+                                c = n.cseq
+                            except ValueError:      # node created after the last reconstruction
+                                c = None
+                            if c is not None:
+                                old[id(n)] = np.array(c)
                 self._drop_node_caches()
-                topo = self._flat()
+                topo = self._refresh_topology()
                 _install_hook(type(self.tree.root))
                 # the reference keeps stale per-node arrays from an earlier (reference) pass: drop them
                 for n in topo.nodes:
@@ -215,6 +219,122 @@ class B200MarginalMixin(DeviceMarginalMixin):
         return super(DeviceMarginalMixin, self).optimize_gtr_rate()
 
 
+def branch_length_grid(mutation_length, one_mutation, n_grid_points, max_branch_length=4.0):
+    """The t-grid on which BranchLenInterpolator tabulates a branch (restated from
+    branch_len_interpolator.py:36-62 so that all branches can be tabulated in one device call)."""
+    if mutation_length < np.min((1e-5, 0.1 * one_mutation)):  # zero-length branch
+        short_range = 10 * one_mutation
+        return np.concatenate([
+            short_range * (np.linspace(0, 1.0, n_grid_points // 2)[:-1]),
+            (short_range + (max_branch_length - short_range) * (np.linspace(0, 1.0, n_grid_points // 2 + 1) ** 2)),
+        ])
+    sigma = mutation_length
+    grid_left = mutation_length * (1 - np.linspace(1, 0.0, n_grid_points // 3) ** 2.0)
+    grid_zero = grid_left[1] * np.logspace(-20, 0, 6)[:5]
+    grid_zero2 = grid_left[1] * np.linspace(0, 1, 10)[1:-1]
+    grid_right = mutation_length + (3 * sigma * (np.linspace(0, 1, n_grid_points // 3) ** 2))
+    far_grid = grid_right.max() + max_branch_length * np.linspace(0, 1, n_grid_points // 3) ** 2
+    grid = np.concatenate((grid_zero, grid_zero2, grid_left, grid_right[1:], far_grid[1:]))
+    grid.sort()
+    return grid
+
+
+class _PairProxy(object):
+    """Stands in for `node.profile_pair = (pp, pc)` while ClockTree builds its branch-length
+    interpolators: the tabulated log-likelihoods were computed on the device for all branches at
+    once, so the two (L', q) arrays are only materialised if somebody really indexes the pair."""
+
+    def __init__(self, tt, node, grid, values):
+        self.tt, self.node, self.grid, self.values = tt, node, grid, values
+        self._pair = None
+
+    def materialize(self):
+        if self._pair is None:
+            self._pair = (self.node.marginal_outgroup_LH, self.node.marginal_subtree_LH)
+        return self._pair
+
+    def lookup(self, t):
+        i = int(np.searchsorted(self.grid, t))
+        for k in (i, i - 1, i + 1):
+            if 0 <= k < self.grid.shape[0] and self.grid[k] == t:
+                return self.values[k]
+        return None
+
+    def __getitem__(self, i):
+        return self.materialize()[i]
+
+    def __iter__(self):
+        return iter(self.materialize())
+
+    def __len__(self):
+        return 2
+
+
+class B200ClockMixin(object):
+    """N1: batched branch-likelihood grids for BranchLenInterpolator in marginal mode
+    (branch_len_interpolator.py:103-110, caller clock_tree.py:344-370).  All (branch x grid point)
+    values of GTR.prob_t_profiles are evaluated in a few device calls from the resident messages;
+    the reference's interpolator construction then runs unchanged on the tabulated numbers."""
+
+    GRID_EVAL_CHUNK = 1 << 18
+
+    def _tabulate_branch_grids(self):
+        # every node of the live tree the device knows (nodes created since the last pass carry explicit arrays)
+        nodes = [n for n in self.tree.find_clades() if n.up is not None and '_fid' in n.__dict__ and n._fid > 0]
+        grids = [branch_length_grid(n.mutation_length, self.one_mutation, self.branch_grid_points) for n in nodes]
+        fids = np.concatenate([np.full(g.shape[0], n._fid, dtype=np.int32) for n, g in zip(nodes, grids)])
+        ts = np.concatenate(grids)
+        vals = np.empty(ts.shape[0])
+        for lo in range(0, ts.shape[0], self.GRID_EVAL_CHUNK):
+            hi = min(ts.shape[0], lo + self.GRID_EVAL_CHUNK)
+            f = self._engine.branch_objective(fids[lo:hi], ts[lo:hi])
+            if self.comm.world_size > 1:
+                f = self.comm.allreduce_sum(f)
+            vals[lo:hi] = f
+        out, k = {}, 0
+        for n, g in zip(nodes, grids):
+            out[id(n)] = _PairProxy(self, n, g, vals[k:k + g.shape[0]])
+            k += g.shape[0]
+        return out
+
+    def marginal_branch_profile(self, node):
+        tab = getattr(self, '_b200_grid_tab', None)
+        if tab is not None and id(node) in tab:
+            return tab[id(node)]
+        return super(B200ClockMixin, self).marginal_branch_profile(node)
+
+    def init_date_constraints(self, *args, **kwargs):
+        use = (getattr(self, 'branch_length_mode', None) == 'marginal' and self._device_ok() is None and self.aln
+               and not any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()))
+        if not use:
+            return super(B200ClockMixin, self).init_date_constraints(*args, **kwargs)
+        if not self.sequence_reconstruction:     # clock_tree.py:335-338
+            self.infer_ancestral_sequences('probabilistic', marginal=True, sample_from_profile='root')
+        if not self._b200_live:
+            return super(B200ClockMixin, self).init_date_constraints(*args, **kwargs)
+        self._b200_grid_tab = self._tabulate_branch_grids()
+        gtr = self.gtr
+        original = gtr.prob_t_profiles
+
+        def prob_t_profiles(profile_pair, multiplicity, t, return_log=False, ignore_gaps=True):
+            if isinstance(profile_pair, _PairProxy):
+                v = profile_pair.lookup(t) if (return_log and ignore_gaps) else None
+                if v is not None:
+                    return v
+                profile_pair = profile_pair.materialize()
+            return original(profile_pair, multiplicity, t, return_log=return_log, ignore_gaps=ignore_gaps)
+
+        gtr.prob_t_profiles = prob_t_profiles
+        try:
+            return super(B200ClockMixin, self).init_date_constraints(*args, **kwargs)
+        finally:
+            del gtr.prob_t_profiles
+            self._b200_grid_tab = None
+
+
 def accelerate(base):
     """Return `class B200<base>(B200MarginalMixin, base)`."""
-    return type('B200' + base.__name__, (B200MarginalMixin, base), {'__doc__': B200MarginalMixin.__doc__})
+    bases = (B200MarginalMixin, base)
+    if hasattr(base, 'init_date_constraints'):        # ClockTree / TreeTime: also batch the branch grids
+        bases = (B200ClockMixin, B200MarginalMixin, base)
+    return type('B200' + base.__name__, bases, {'__doc__': B200MarginalMixin.__doc__})

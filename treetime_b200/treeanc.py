@@ -231,9 +231,7 @@ class TreeAnc(DeviceMarginalMixin):
         for clade in self.tree.get_nonterminals(order='preorder'):
             for c in clade.clades:
                 c.dist2root = clade.dist2root + (c.mutation_length if hasattr(c, 'mutation_length') else c.branch_length)
-        self._topo = None          # re-flatten lazily
-        self._cache = {}
-        self._seq_cache = {}
+        self._topo_dirty = True    # re-flatten at the next pass
 
     @property
     def leaves_lookup(self):
@@ -332,7 +330,7 @@ class TreeAnc(DeviceMarginalMixin):
                         clade.up = node.up
                     pruned = True
         if pruned:
-            self._topo = None
+            self._topo_dirty = True
 
     # -- sequences out -------------------------------------------------------------------------
     def sequence(self, node, reconstructed=False, as_string=True, compressed=False):
