@@ -61,8 +61,8 @@ def make_workload(name, seed):
 
 def algorithmic_bytes(flat, q):
     """Bytes the level kernels must move per pass under THIS design:
-    postorder: read (S,F) of internal children + 1-byte codes of tip children, write (S,F) per
-    internal node; preorder: read parent profile once per parent with an internal child, per
+    postorder: read S of internal children + 1-byte codes of tip children, write S per internal
+    node (the log-prefactors are summed per block run, not stored per node); preorder: read parent profile once per parent with an internal child, per
     internal child read S, write profile, read+write the 1-byte state."""
     Lp = flat['multiplicity'].shape[0]
     n_nodes = flat['parent'].shape[0]
@@ -71,7 +71,7 @@ def algorithmic_bytes(flat, q):
     n_int = n_nodes - n_tips
     has_int_child = np.zeros(n_nodes, dtype=bool)
     has_int_child[flat['parent'][1:][~tip[1:]]] = True
-    post = Lp * (n_int * (q + 1) * 8 + (n_int - 1) * (q + 1) * 8 + n_tips * 1)
+    post = Lp * (n_int * q * 8 + (n_int - 1) * q * 8 + n_tips * 1)
     pre = Lp * (int(has_int_child.sum()) * q * 8 + (n_int - 1) * (2 * q * 8 + 2))
     return post, pre
 

@@ -98,6 +98,7 @@ struct ttb_engine {
   std::vector<int> tip_nodes;
   Sched post, pre_int, pre_all;
   int sched_tiles = -1;  // tiles the group pointers were built for
+  int n_fgroups = 0;     // postorder block runs (rows of Fpart)
   bool sched_ss = false;
   bool prepared = false;
   // device tree
@@ -121,7 +122,7 @@ struct ttb_engine {
   double ss_tmax = 0.0;
   bool ss_interp_dirty = true;
   // state
-  DBuf<double> d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
+  DBuf<double> d_Fred, d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
   DBuf<uint8_t> d_idx, d_idxtip, d_bstage;   // d_bstage: packed byte staging for contiguous H2D / D2H
   DBuf<unsigned long long> d_nd;
   DBuf<int> d_enodes, d_ekinds;
@@ -176,7 +177,9 @@ struct ttb_engine {
     d.TU = d_TU.p;
     d.P = d_P.p;
     d.S = d_S.p;
-    d.F = d_F.p;
+    d.Fpart = d_F.p;
+    d.Fred = d_Fred.p;
+    d.n_fgroups = n_fgroups;
     d.M = d_M.p;
     d.Mtip = d_Mtip.p;
     d.idx = d_idx.p;
@@ -312,17 +315,20 @@ int ensure_state(ttb_handle h, bool tips) {
       if ((rc = upload(sc->d_group_ptr, sc->group_ptr.data(), sc->group_ptr.size(), h->stream))) return rc;
     }
     CK(cudaStreamSynchronize(h->stream));
+    h->n_fgroups = 0;
+    for (const TtbLevelLaunch& L : h->post.launches) h->n_fgroups += L.n_groups;
     h->sched_tiles = h->tiles();
     h->sched_ss = h->site_specific;
     h->drop_graphs();
   }
+  if ((rc = h->d_F.alloc((size_t)h->n_fgroups * ld))) return rc;
+  if ((rc = h->d_Fred.alloc((size_t)TTB_FLANES * ld))) return rc;
   if (!h->prepared) {
     const int e = ttb_qops(h->q)->prepare(h->dev());
     if (e) return fail(TTB_ECUDA, std::string("cudaFuncSetAttribute(shared memory) failed: ") + cudaGetErrorString((cudaError_t)e));
     h->prepared = true;
   }
   if ((rc = h->d_S.alloc((size_t)h->n_int * q * ld))) return rc;
-  if ((rc = h->d_F.alloc((size_t)h->n_int * ld))) return rc;
   if ((rc = h->d_LH.alloc(ld))) return rc;
   if ((rc = h->d_lh_partial.alloc(h->tiles()))) return rc;
   if ((rc = h->d_nd.alloc(1024))) return rc;
@@ -396,7 +402,7 @@ int ttb_destroy(ttb_handle h) {
   for (auto* b : ib) b->release();
   DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_ss_eig, &h->d_ss_mu, &h->d_ss_V, &h->d_ss_Vinv, &h->d_ss_Pi,
                         &h->d_ss_w, &h->d_ss_grid, &h->d_ss_E, &h->d_TU, &h->d_P, &h->d_S,
-                        &h->d_F, &h->d_M, &h->d_Mtip, &h->d_LH, &h->d_lh_partial, &h->d_results, &h->d_stage,
+                        &h->d_F, &h->d_Fred, &h->d_M, &h->d_Mtip, &h->d_LH, &h->d_lh_partial, &h->d_results, &h->d_stage,
                         &h->d_partial, &h->d_ets, &h->d_eout};
   for (auto* b : db) b->release();
   h->d_codes.release();

@@ -27,6 +27,7 @@
 #define TTB_BLOCK 128
 #define TTB_TILE 128          // patterns per tile = threads per block: one 1 KB row per state
 #define TTB_CB 2              // children per pipeline chunk (binary nodes = one chunk)
+#define TTB_FLANES 16         // lanes of the two-stage reduction of the per-run log-prefactor sums
 
 // One pipeline chunk of a level kernel: up to TTB_CB children of one node (32 bytes).
 //   postorder: out = slot of the node being computed; src[b] = slot of internal child b or
@@ -82,7 +83,9 @@ struct TtbDev {
   double* TU;    // [n_tips][tu_stride]  tip message table: TU[code*q+j] = sum_i prof[code][i] P[i][j]
   double* P;     // [n_nodes][pq]  exp(Q t_c), P[i*q+j] = Prob(child=i | parent=j)
   double* S;     // [n_int][q][ld]  marginal_subtree_LH
-  double* F;     // [n_int][ld]     marginal_subtree_LH_prefactor
+  double* Fpart; // [n_fgroups][ld] per-pattern sums of log-normalisers over the nodes of one postorder block run
+  int n_fgroups; //                 (sum over all runs = marginal_subtree_LH_prefactor of the root)
+  double* Fred;  // [TTB_FLANES][ld] first reduction stage of Fpart
   double* M;     // [n_int][q][ld]  marginal_profile
   double* Mtip;  // [n_tips][q][ld] marginal_profile of tips (reconstruct_tip_states) or null
   uint8_t* idx;     // [n_int][ld]  argmax state
@@ -388,9 +391,9 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // ---------------------------------------------------------------------------------------
 template <int Q, bool SS>
 __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
-                                                              const int* __restrict__ group_ptr, int tiles) {
+                                                              const int* __restrict__ group_ptr, int tiles, int fbase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int RPC = Q + 1;  // rows per child
+  constexpr int RPC = Q;  // rows per child (the log-prefactors never travel: see Fpart)
   Pipe<Q> pipe(smem_raw, Pipe<Q>::CB * RPC, p.pq, p.tu_stride);
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
@@ -427,9 +430,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
       if (src >= 0) {
         if (r < Q)
           tma_load_1d(pipe.rows(s) + (b * RPC + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, bar);
-        else if (r == Q)
-          tma_load_1d(pipe.rows(s) + (b * RPC + Q) * TTB_TILE, p.F + (size_t)src * p.ld + a0, cols * 8, bar);
-        else if (!SS)
+        else if (r == Q && !SS)
           tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
       } else {
         const int row = -1 - src;
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
   if (SS) pipe.wait_model();
 
   double X[Q];
-  double F = 0.0;
+  double Facc = 0.0;   // sum of log-normalisers of this block's nodes (for this thread's pattern)
   int scale = 0, seen = 0;
   for (int u = 0; u < n_chunks; ++u) {
     if (warp == 0 && u + Pipe<Q>::STAGES - 1 < n_chunks) issue(u + Pipe<Q>::STAGES - 1);
@@ -457,7 +458,6 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
     if (c.flags & 1) {
 #pragma unroll
       for (int j = 0; j < Q; ++j) X[j] = 1.0;
-      F = 0.0;
       scale = 0;
       seen = 0;
     }
@@ -476,8 +476,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
             const double* rows = pipe.rows(s) + (b * RPC) * TTB_TILE + tid;
 #pragma unroll
             for (int i = 0; i < Q; ++i) sc[i] = rows[i * TTB_TILE];
-            F += rows[Q * TTB_TILE];
-          }
+            }
           sm.efac(p, c.cnode(b), e);
           sm.up(sc, e, U);
         } else if (c.src(b) < 0) {
@@ -491,7 +490,6 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
           double sc[Q];
 #pragma unroll
           for (int i = 0; i < Q; ++i) sc[i] = rows[i * TTB_TILE];
-          F += rows[Q * TTB_TILE];
 #pragma unroll
           for (int j = 0; j < Q; ++j) U[j] = sc[0] * Pc[j];
 #pragma unroll
@@ -522,28 +520,33 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
       double* __restrict__ so = p.S + (size_t)c.out * Q * p.ld + a;
 #pragma unroll
       for (int j = 0; j < Q; ++j) so[(size_t)j * p.ld] = X[j] * inv;
-      p.F[(size_t)c.out * p.ld + a] = F + (log(Z) - scale * (256.0 * 0.693147180559945309417232121458));
+      Facc += log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
     }
   }
+  if (act) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc;
 }
 
 // Postorder level 1: every child is a tip, so there is nothing to stream in but one code byte
-// per (tip, pattern); the kernel is a pure write stream of (q+1) doubles per (node, pattern).
-// One thread per (node, pattern), tip tables read through L1.
+// per (tip, pattern); the kernel is a pure write stream of q doubles per (node, pattern).
+// Block = (run of nodes, tile); one thread per pattern, tip tables read through L1.
 template <int Q>
 __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
-                                                                   const int* __restrict__ node_chunk, int tiles) {
-  const int node = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+                                                                   const int* __restrict__ group_ptr, int tiles, int fbase) {
+  const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const long long a = (long long)tile * TTB_TILE + threadIdx.x;
   if (a >= p.Lp) return;
-  const int k0 = node_chunk[node], k1 = node_chunk[node + 1];
+  const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
   double X[Q];
-#pragma unroll
-  for (int j = 0; j < Q; ++j) X[j] = 1.0;
-  int scale = 0, seen = 0, out = 0;
+  double Facc = 0.0;
+  int scale = 0, seen = 0;
   for (int k = k0; k < k1; ++k) {
     const Chunk c = load_chunk_global(chunks + k);
-    out = c.out;
+    if (c.flags & 1) {
+#pragma unroll
+      for (int j = 0; j < Q; ++j) X[j] = 1.0;
+      scale = 0;
+      seen = 0;
+    }
     const int nch = c.nch();
     for (int b = 0; b < nch; ++b) {
       const int row = -1 - c.src(b);
@@ -562,15 +565,29 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
         }
       }
     }
+    if (c.flags & 2) {
+      double Z = X[0];
+#pragma unroll
+      for (int j = 1; j < Q; ++j) Z += X[j];
+      const double inv = 1.0 / Z;
+      double* __restrict__ so = p.S + (size_t)c.out * Q * p.ld + a;
+#pragma unroll
+      for (int j = 0; j < Q; ++j) so[(size_t)j * p.ld] = X[j] * inv;
+      Facc += log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
+    }
   }
-  double Z = X[0];
-#pragma unroll
-  for (int j = 1; j < Q; ++j) Z += X[j];
-  const double inv = 1.0 / Z;
-  double* __restrict__ so = p.S + (size_t)out * Q * p.ld + a;
-#pragma unroll
-  for (int j = 0; j < Q; ++j) so[(size_t)j * p.ld] = X[j] * inv;
-  p.F[(size_t)out * p.ld + a] = log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
+  p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc;
+}
+
+// First stage of the log-prefactor reduction: Fred[c][a] = sum of Fpart[g][a] over g = c mod TTB_FLANES
+// (grid = (tiles, TTB_FLANES); fixed order => deterministic).
+static __global__ void __launch_bounds__(TTB_BLOCK) fsum_kernel(TtbDev p) {
+  const long long a = (long long)blockIdx.x * TTB_BLOCK + threadIdx.x;
+  if (a >= p.Lp) return;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int g = blockIdx.y; g < p.n_fgroups; g += TTB_FLANES) acc += p.Fpart[(size_t)g * p.ld + a];
+  p.Fred[(size_t)blockIdx.y * p.ld + a] = acc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -592,7 +609,10 @@ __global__ void __launch_bounds__(TTB_BLOCK) root_kernel(TtbDev p, int lh_only) 
       R[j] = (SS ? p.ss_Pi[(size_t)j * p.ld + a] : p.Pi[j]) * s[(size_t)j * p.ld];   // Pi.T at the root, treeanc.py:817-820
       Z += R[j];
     }
-    const double lh = p.F[(size_t)slot * p.ld + a] + log(Z);
+    double F = 0.0;   // fixed summation order (fsum_kernel lanes, then here): deterministic
+#pragma unroll
+    for (int c = 0; c < TTB_FLANES; ++c) F += p.Fred[(size_t)c * p.ld + a];
+    const double lh = F + log(Z);
     p.LH[a] = lh;
     contrib = lh * p.mult[a];
     if (!lh_only) {

@@ -9,7 +9,7 @@
 namespace {
 constexpr int Q = TTB_Q;
 
-size_t post_smem(const TtbDev& d, bool ss = false) { return Pipe<Q>::smem_bytes(Pipe<Q>::CB * (Q + 1), d.pq, d.tu_stride, ss); }
+size_t post_smem(const TtbDev& d, bool ss = false) { return Pipe<Q>::smem_bytes(Pipe<Q>::CB * Q, d.pq, d.tu_stride, ss); }
 size_t pre_smem(const TtbDev& d, bool ss = false) { return Pipe<Q>::smem_bytes(Q + Pipe<Q>::CB * Q, d.pq, d.tu_stride, ss); }
 
 constexpr bool HAS_SS = (Q <= 8);   // site-specific models: nucleotide-sized alphabets only
@@ -49,20 +49,24 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   int l0 = 0;
   if (!SS) {
     // level 1 (all children are tips) is a pure write stream: dedicated kernel, no pipeline
-    post_leaf_level_kernel<Q><<<(unsigned)((long long)pl.n_post_leaf_nodes * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_post_chunks,
-                                                                                                    pl.d_post_node_chunk, tiles);
+    const TtbLevelLaunch& L = pl.post_levels[0];
+    post_leaf_level_kernel<Q><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_post_chunks,
+                                                                                          pl.d_post_group_ptr + L.group_off, tiles, 0);
     ++nk;
     l0 = 1;
   }
+  int fbase = l0 ? pl.post_levels[0].n_groups : 0;
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
     post_level_kernel<Q, SS><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, psm, s>>>(d, pl.d_post_chunks,
-                                                                                             pl.d_post_group_ptr + L.group_off, tiles);
+                                                                                             pl.d_post_group_ptr + L.group_off, tiles, fbase);
+    fbase += L.n_groups;
     ++nk;
   }
   if (ev) { cudaEventRecord(ev[2], s); pk[1] = nk - pk[0]; }
+  fsum_kernel<<<dim3(tiles, TTB_FLANES), TTB_BLOCK, 0, s>>>(d);
   root_kernel<Q, SS><<<tiles, TTB_BLOCK, 0, s>>>(d, pl.lh_only ? 1 : 0);
-  ++nk;
+  nk += 2;
   if (!pl.lh_only) {
     zero_slots_kernel<<<4, 256, 0, s>>>(d);
     ++nk;
