@@ -320,7 +320,7 @@ def main():
 
         def e2e_step():
             for e, cp, sp, lp, m, *_ in shards:
-                e.set_patterns(cp, flat['code_profiles'], m)
+                e.set_patterns(cp, flat['code_profiles'], m, validate=False)
                 e.set_gtr(g)
                 e.set_branch_lengths(flat['t'])
                 e.marginal()
@@ -358,23 +358,67 @@ def main():
         pe0.record(); db.copy_(pb, non_blocking=True); pe1.record(); pb.copy_(db, non_blocking=True); pe2.record()
         torch.cuda.synchronize()
         pcie = (0.268435456 / (pe0.elapsed_time(pe1) / 1e3), 0.268435456 / (pe1.elapsed_time(pe2) / 1e3))
-        e2e = (e2e_s, h2d, d2h, nblk, lh_check, pcie)
         for sh in shards:
             sh[0].close()
         del shards
+        torch.cuda.empty_cache()
+        # ---- sparse host interface: the alignment goes in as (reference row + differences), the
+        # sequences come back as (root row + states that differ from the parent).  Same information,
+        # ~100x fewer PCIe bytes; one handle, no blocking needed.
+        from treetime_b200.sparse import sparse_from_dense
+        ref_c, e_row, e_pos, e_code = sparse_from_dense(flat['tip_codes'])
+        pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()  # noqa: E731
+        ref_c, e_row, e_pos, e_code = pin(ref_c), pin(e_row), pin(e_pos), pin(e_code)
+        max_mut = max(1 << 16, 8 * n_nodes)
+        m_node = torch.empty(max_mut, dtype=torch.int32, pin_memory=True).numpy()
+        m_pos = torch.empty(max_mut, dtype=torch.int32, pin_memory=True).numpy()
+        m_state = torch.empty(max_mut, dtype=torch.uint8, pin_memory=True).numpy()
+        m_root = torch.empty(Lp, dtype=torch.uint8, pin_memory=True).numpy()
+        lh_pin = torch.empty(Lp, dtype=torch.float64, pin_memory=True).numpy()
+        import ctypes
+        from treetime_b200 import _lib as L_
+        from treetime_b200.engine import _ip, _up
+
+        def sparse_step():
+            eng.set_patterns_sparse(ref_c, e_row, e_pos, e_code, flat['code_profiles'], flat['multiplicity'])
+            eng.set_gtr(g)
+            eng.set_branch_lengths(flat['t'])
+            eng.marginal()
+            if world > 1:
+                dist.all_reduce(res_t)
+            eng.enqueue_site_lh(lh_pin)
+            n_ = ctypes.c_int64()
+            L_.check(eng.lib.ttb_fetch_mutations(eng.h, _up(m_root), max_mut, _ip(m_node), _ip(m_pos), _up(m_state), ctypes.byref(n_)))
+            tot_, _ = eng.results()
+            return tot_, int(n_.value)
+
+        sparse_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            tot_sp, n_mut = sparse_step()
+        barrier()
+        sp_s = (time.perf_counter() - t0) / k_e2e
+        sp_h2d = int(ref_c.nbytes + e_row.nbytes + e_pos.nbytes + e_code.nbytes + flat['code_profiles'].nbytes + flat['multiplicity'].nbytes
+                     + flat['t'].nbytes + 8 * (2 * q * q + 2 * q + 1))
+        sp_d2h = int(Lp + n_mut * 9 + 8 * Lp + 24)
+        sp_check = abs(tot_sp - (total_lh_local if world == 1 else float(res_t[0].item()))) / abs(tot_sp)
+        e2e = (e2e_s, h2d, d2h, nblk, lh_check, pcie, sp_s, sp_h2d, sp_d2h, sp_check, n_mut, int(e_row.shape[0]))
 
     # ---- reduce over ranks: max time, summed work
     ms_step = ms_total / args.steps
     if world > 1:
-        tmax = torch.tensor([ms_step, e2e[0] if e2e else 0.0], device='cuda', dtype=torch.float64)
+        tmax = torch.tensor([ms_step, e2e[0] if e2e else 0.0, e2e[6] if e2e else 0.0], device='cuda', dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = torch.tensor([float(updates_local)], device='cuda', dtype=torch.float64)
         dist.all_reduce(tsum)
         ms_step = float(tmax[0].item())
         e2e_time = float(tmax[1].item())
+        sp_time = float(tmax[2].item())
         updates_total = float(tsum[0].item())
     else:
         e2e_time = e2e[0] if e2e else 0.0
+        sp_time = e2e[6] if e2e else 0.0
         updates_total = float(updates_local)
 
     if rank == 0:
@@ -413,6 +457,12 @@ def main():
             },
         }
         if e2e:
+            out['e2e_sparse_io'] = {
+                'value': updates_total / sp_time, 'unit': 'updates/s', 'ms_per_step': 1e3 * sp_time,
+                'h2d_bytes_per_step': e2e[7], 'd2h_bytes_per_step': e2e[8], 'rel_lh_diff_vs_resident_pass': e2e[9],
+                'alignment_differences': e2e[11], 'mutations_returned': e2e[10],
+                'what': 'same pass through ttb_set_patterns_sparse (reference row + differences, like TreeTime\'s VCF '
+                        'alignments) and ttb_fetch_mutations (root row + states differing from the parent) + per-pattern LH'}
             out['e2e'] = {'value': updates_total / e2e_time, 'unit': 'updates/s', 'ms_per_step': 1e3 * e2e_time,
                           'h2d_bytes_per_step': e2e[1], 'd2h_bytes_per_step': e2e[2],
                           'pattern_blocks': e2e[3], 'rel_lh_diff_vs_resident_pass': e2e[4],

@@ -82,6 +82,13 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
 int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes, int32_t n_codes,
                      const double* code_profiles, const double* multiplicity);
 
+/* Sparse variant of ttb_set_patterns (the analogue of TreeTime's dict-of-differences / VCF alignments,
+ * sequence_data.py:363-383): every tip row equals ref_codes[n_patterns] except at the n_entries listed
+ * (tip_row, pattern, code) positions.  The dense code matrix is built on the device. */
+int ttb_set_patterns_sparse(ttb_handle h, int64_t n_patterns, const uint8_t* ref_codes, int64_t n_entries,
+                            const int32_t* entry_row, const int32_t* entry_pos, const uint8_t* entry_code,
+                            int32_t n_codes, const double* code_profiles, const double* multiplicity);
+
 /* Single-site GTR eigen-system (gtr.py:612-629): eigvals[q], v[q][q], v_inv[q][q], Pi[q], mu.
  * gap_index = gtr.gap_index or -1 (used by the branch objective, gtr.py:954-959). */
 int ttb_set_gtr(ttb_handle h, const double* eigvals, const double* v, const double* v_inv,
@@ -120,6 +127,13 @@ int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* ou
 
 /* All internal nodes at once: out[n_internal][n_patterns], rows in node (preorder) order. */
 int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out);
+
+/* Sparse form of the reconstructed sequences: root_idx[n_patterns] plus every (node, pattern, state) where
+ * an internal node's state differs from its parent's (what `node.mutations` lists, treeanc.py:27-42, on
+ * compressed patterns).  Up to max_n entries are written (unordered); *n receives the total count, so a
+ * caller that passed too small a buffer can retry.  Synchronous. */
+int ttb_fetch_mutations(ttb_handle h, uint8_t* root_idx, int32_t max_n, int32_t* node, int32_t* pos, uint8_t* state,
+                        int64_t* n);
 
 /* Stream-ordered variants without a host sync: the data is valid after ttb_sync / ttb_results.
  * `out` should be page-locked memory (otherwise the driver stages and the call blocks).  With

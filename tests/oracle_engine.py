@@ -28,7 +28,7 @@ class OracleEngine(object):
         self.res = None
         self.prev_idx = None
 
-    def set_patterns(self, tip_codes, code_profiles, multiplicity):
+    def set_patterns(self, tip_codes, code_profiles, multiplicity, validate=True):
         self.flat.update(tip_codes=np.array(tip_codes), code_profiles=np.array(code_profiles, dtype=float),
                          multiplicity=np.array(multiplicity, dtype=float))
         self.n_patterns = tip_codes.shape[1]

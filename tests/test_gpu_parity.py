@@ -179,6 +179,39 @@ def test_branch_objective_hamming_counts():
     assert np.allclose(T_i, rT.sum(axis=-1), rtol=1e-10, atol=1e-12)
 
 
+def test_sparse_input_and_sparse_result():
+    """ttb_set_patterns_sparse (reference row + differences) and ttb_fetch_mutations (root row +
+    states that differ from the parent) carry the same information as the dense calls."""
+    from treetime_b200.sparse import sparse_from_dense, expand_mutations
+    from treetime_b200.engine import Engine
+    tree = synth.random_tree(120, seed=21, mean_bl=0.004)
+    topo, flat, g = util.make_flat(tree, util.nuc_gtr(), 900, 21, amb_frac=0.01)
+    dense = util.engine_for(flat, g)
+    dense.marginal()
+    tot, nd = dense.results()
+    ref, row, pos, code = sparse_from_dense(flat['tip_codes'])
+    assert row.shape[0] < 0.2 * flat['tip_codes'].size
+    sp = Engine(5)
+    sp.set_tree(flat['parent'], flat['child_ptr'], flat['child_idx'], flat['tip_row'])
+    sp.set_patterns_sparse(ref, row, pos, code, flat['code_profiles'], flat['multiplicity'])
+    sp.set_gtr(g)
+    sp.set_branch_lengths(flat['t'])
+    sp.marginal()
+    tot2, nd2 = sp.results()
+    assert tot2 == tot and nd2 == nd
+    assert np.array_equal(sp.site_lh(), dense.site_lh())
+    full = dense.all_seq_idx()
+    root_idx, mn, mp, ms = sp.mutations()
+    assert np.array_equal(expand_mutations(flat['parent'], flat['tip_row'], root_idx, mn, mp, ms), full)
+    # a too small buffer is reported and retried
+    r2, mn2, mp2, ms2 = sp.mutations(max_n=3)
+    assert np.array_equal(mn2, mn) and np.array_equal(ms2, ms)
+    from treetime_b200._lib import TTBError
+    with pytest.raises(TTBError):
+        sp.set_patterns_sparse(ref, np.array([10 ** 6], dtype=np.int32), np.array([0], dtype=np.int32), np.array([0], dtype=np.uint8),
+                               flat['code_profiles'], flat['multiplicity'])
+
+
 def test_api_errors():
     from treetime_b200.engine import Engine
     from treetime_b200._lib import TTBError

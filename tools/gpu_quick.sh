@@ -9,7 +9,7 @@ python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_cfg3_$TAG.json'))
 r=d['roofline']
-print('cfg3: %.3e upd/s  %.2f ms/step  phases %s  dom %s %.0f GB/s frac %.3f  whole %.3f  e2e %.2f ms' % (d['value'], d['ms_per_step'], {k:round(v,2) for k,v in r['phases_ms'].items()}, r['kernel'][:12], r['achieved'], r['frac'], r['whole_pass']['frac'], d.get('e2e',{}).get('ms_per_step',0)))
+print('cfg3: %.3e upd/s  %.2f ms/step  phases %s  dom %s %.0f GB/s frac %.3f  whole %.3f  e2e %.2f ms' % (d['value'], d['ms_per_step'], {k:round(v,2) for k,v in r['phases_ms'].items()}, r['kernel'][:12], r['achieved'], r['frac'], r['whole_pass']['frac'], d.get('e2e',{}).get('ms_per_step',0)), 'sparse-io e2e %.2f ms' % d.get('e2e_sparse_io',{}).get('ms_per_step',0))
 PY
 tail -3 gpurun_out/bench_cfg3_$TAG.err
 python bench.py --workload cfg2 --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_cfg2_$TAG.json 2> gpurun_out/bench_cfg2_$TAG.err

@@ -83,6 +83,8 @@ SIGNATURES = {
     'ttb_set_stream': ([_H, ctypes.c_void_p], ctypes.c_int),
     'ttb_set_tree': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_int_p, _c_int_p], ctypes.c_int),
     'ttb_set_patterns': ([_H, ctypes.c_int64, _c_u8_p, ctypes.c_int32, _c_dbl_p, _c_dbl_p], ctypes.c_int),
+    'ttb_set_patterns_sparse': ([_H, ctypes.c_int64, _c_u8_p, ctypes.c_int64, _c_int_p, _c_int_p, _c_u8_p, ctypes.c_int32,
+                                 _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_set_gtr': ([_H, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, ctypes.c_double, ctypes.c_int32], ctypes.c_int),
     'ttb_set_gtr_site_specific': ([_H, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, ctypes.c_int32,
                                    ctypes.c_double, ctypes.c_int32, ctypes.c_int32], ctypes.c_int),
@@ -95,6 +97,7 @@ SIGNATURES = {
     'ttb_fetch_node': ([_H, ctypes.c_int32, ctypes.c_int32, _c_dbl_p], ctypes.c_int),
     'ttb_fetch_seq_idx': ([_H, ctypes.c_int32, _c_int_p, _c_u8_p], ctypes.c_int),
     'ttb_fetch_all_seq_idx': ([_H, _c_u8_p], ctypes.c_int),
+    'ttb_fetch_mutations': ([_H, _c_u8_p, ctypes.c_int32, _c_int_p, _c_int_p, _c_u8_p, ctypes.POINTER(ctypes.c_int64)], ctypes.c_int),
     'ttb_enqueue_fetch_site_lh': ([_H, _c_dbl_p], ctypes.c_int),
     'ttb_enqueue_fetch_all_seq_idx': ([_H, _c_u8_p], ctypes.c_int),
     'ttb_profile_marginal': ([_H, ctypes.c_int32, _c_dbl_p, _c_int_p], ctypes.c_int),

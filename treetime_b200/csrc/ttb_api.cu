@@ -123,11 +123,18 @@ struct ttb_engine {
   bool ss_interp_dirty = true;
   // state
   DBuf<double> d_Fred, d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
-  DBuf<uint8_t> d_idx, d_idxtip, d_bstage;   // d_bstage: packed byte staging for contiguous H2D / D2H
+  DBuf<uint8_t> d_idx, d_idxtip, d_bstage, d_mut_state;
+  DBuf<int> d_mut_node, d_mut_pos, d_ent_row, d_ent_pos;
+  DBuf<unsigned long long> d_mut_count;   // d_bstage: packed byte staging for contiguous H2D / D2H
   DBuf<unsigned long long> d_nd;
   DBuf<int> d_enodes, d_ekinds;
   DBuf<double> d_ets, d_eout;
   double* h_results = nullptr;  // pinned {total, ndiff}
+  // page-locked scratch through which small pageable inputs (branch lengths, model, multiplicities)
+  // are staged, so that those uploads never block the host behind queued GPU work
+  unsigned char* h_scratch = nullptr;
+  size_t scratch_cap = 0, scratch_used = 0;
+  cudaEvent_t scratch_ev = nullptr;
   bool have_pass = false;       // a full (non LH-only) pass has completed
   bool have_tip_pass = false;
   bool first_full = true;       // no previous state indices to diff against
@@ -205,6 +212,28 @@ int upload(DBuf<T>& b, const T* src, size_t n, cudaStream_t s) {
   int rc = b.alloc(n);
   if (rc) return rc;
   if (n) CK(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+// Asynchronous H2D of a small pageable host array: copy it into the handle's page-locked scratch
+// first.  The scratch is a bump allocator guarded by an event (recycled only after the copies that
+// read it have executed).
+int upload_small(ttb_handle h, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return 0;
+  const size_t need = (bytes + 255) / 256 * 256;
+  if (need > h->scratch_cap / 2) {   // too big for the scratch: plain (possibly blocking) copy
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+  }
+  if (h->scratch_used + need > h->scratch_cap) {
+    CK(cudaEventSynchronize(h->scratch_ev));
+    h->scratch_used = 0;
+  }
+  unsigned char* p = h->h_scratch + h->scratch_used;
+  memcpy(p, src, bytes);
+  h->scratch_used += need;
+  CK(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->scratch_ev, h->stream));
   return 0;
 }
 
@@ -388,6 +417,9 @@ int ttb_create(ttb_handle* out, int device, int n_states) {
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   CK(cudaMallocHost(&h->h_results, 2 * sizeof(double)));
+  h->scratch_cap = 16u << 20;
+  CK(cudaMallocHost(&h->h_scratch, h->scratch_cap));
+  CK(cudaEventCreateWithFlags(&h->scratch_ev, cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -411,8 +443,12 @@ int ttb_destroy(ttb_handle h) {
   h->d_idx.release();
   h->d_idxtip.release();
   h->d_bstage.release();
+  h->d_mut_state.release(); h->d_mut_node.release(); h->d_mut_pos.release(); h->d_ent_row.release(); h->d_ent_pos.release();
+  h->d_mut_count.release();
   h->d_nd.release();
   if (h->h_results) cudaFreeHost(h->h_results);
+  if (h->h_scratch) cudaFreeHost(h->h_scratch);
+  if (h->scratch_ev) cudaEventDestroy(h->scratch_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return 0;
@@ -494,11 +530,16 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   return 0;
 }
 
-int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes, int32_t n_codes,
-                     const double* code_profiles, const double* multiplicity) {
+}  // extern "C" (templates need C++ linkage)
+
+// Shared by the dense and the sparse setter: sizes, tables, multiplicities, invalidation.
+// `fill` uploads the tip codes into h->d_codes (already allocated for the new size).
+template <typename Fill>
+static int set_patterns_common(ttb_handle h, int64_t n_patterns, int32_t n_codes, const double* code_profiles,
+                               const double* multiplicity, Fill fill) {
   if (int rc = use_device(h)) return rc;
   if (!h->n_nodes) return fail(TTB_EINVAL, "ttb_set_patterns: call ttb_set_tree first");
-  if (n_patterns <= 0 || !tip_codes || n_codes <= 0 || n_codes > 255 || !code_profiles || !multiplicity)
+  if (n_patterns <= 0 || n_codes <= 0 || n_codes > 255 || !code_profiles || !multiplicity)
     return fail(TTB_EINVAL, "ttb_set_patterns: bad arguments");
   if ((size_t)n_codes * h->q * 8 > 16 * 1024) return fail(TTB_EUNSUPPORTED, "ttb_set_patterns: too many distinct characters for the tip tables");
   const long long Lp = n_patterns, ld = (Lp + 31) / 32 * 32;
@@ -507,16 +548,12 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
   cudaStream_t s = h->stream;
   int rc;
   if ((rc = h->d_codes.alloc((size_t)h->n_tips * ld))) return rc;
-  // one contiguous H2D copy into a packed staging buffer, re-pitched to the padded layout on the device
-  if ((rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)Lp))) return rc;
-  CK(cudaMemcpyAsync(h->d_bstage.p, tip_codes, (size_t)h->n_tips * Lp, cudaMemcpyHostToDevice, s));
-  pitch_bytes_kernel<<<148 * 8, 256, 0, s>>>(h->d_bstage.p, Lp, h->d_codes.p, ld, Lp, h->n_tips, 0);
-  h->launches += 1;
-  CK(cudaGetLastError());
-  if ((rc = upload(h->d_code_prof, code_profiles, (size_t)n_codes * h->q, s))) return rc;
+  if ((rc = fill(Lp, ld, s))) return rc;
+  if ((rc = h->d_code_prof.alloc((size_t)n_codes * h->q))) return rc;
+  if ((rc = upload_small(h, h->d_code_prof.p, code_profiles, (size_t)n_codes * h->q * sizeof(double)))) return rc;
   if ((rc = h->d_mult.alloc(ld))) return rc;
   CK(cudaMemsetAsync(h->d_mult.p, 0, h->d_mult.bytes(), s));
-  CK(cudaMemcpyAsync(h->d_mult.p, multiplicity, Lp * sizeof(double), cudaMemcpyHostToDevice, s));
+  if ((rc = upload_small(h, h->d_mult.p, multiplicity, Lp * sizeof(double)))) return rc;
   h->h_mult.assign(multiplicity, multiplicity + Lp);
   if (ld != h->ld || Lp != h->Lp) {
     if (h->site_specific) { h->site_specific = false; h->have_gtr = false; }   // per-pattern model no longer matches
@@ -537,6 +574,52 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
   return 0;
 }
 
+extern "C" {
+
+int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes, int32_t n_codes,
+                     const double* code_profiles, const double* multiplicity) {
+  if (!h) return fail(TTB_EINVAL, "null handle");
+  if (!tip_codes) return fail(TTB_EINVAL, "ttb_set_patterns: bad arguments");
+  return set_patterns_common(h, n_patterns, n_codes, code_profiles, multiplicity, [&](long long Lp, long long ld, cudaStream_t s) -> int {
+    // one contiguous H2D copy into a packed staging buffer, re-pitched to the padded layout on the device
+    if (int rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)Lp)) return rc;
+    CK(cudaMemcpyAsync(h->d_bstage.p, tip_codes, (size_t)h->n_tips * Lp, cudaMemcpyHostToDevice, s));
+    pitch_bytes_kernel<<<148 * 8, 256, 0, s>>>(h->d_bstage.p, Lp, h->d_codes.p, ld, Lp, h->n_tips, 0);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int ttb_set_patterns_sparse(ttb_handle h, int64_t n_patterns, const uint8_t* ref_codes, int64_t n_entries,
+                            const int32_t* entry_row, const int32_t* entry_pos, const uint8_t* entry_code,
+                            int32_t n_codes, const double* code_profiles, const double* multiplicity) {
+  if (!h) return fail(TTB_EINVAL, "null handle");
+  if (!ref_codes || n_entries < 0 || (n_entries && (!entry_row || !entry_pos || !entry_code)))
+    return fail(TTB_EINVAL, "ttb_set_patterns_sparse: bad arguments");
+  for (int64_t i = 0; i < n_entries; ++i)
+    if (entry_row[i] < 0 || entry_row[i] >= h->n_tips || entry_pos[i] < 0 || entry_pos[i] >= n_patterns || entry_code[i] >= n_codes)
+      return fail(TTB_EINVAL, "ttb_set_patterns_sparse: entry out of range");
+  return set_patterns_common(h, n_patterns, n_codes, code_profiles, multiplicity, [&](long long Lp, long long ld, cudaStream_t s) -> int {
+    int rc;
+    if ((rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)Lp))) return rc;
+    CK(cudaMemcpyAsync(h->d_bstage.p, ref_codes, (size_t)Lp, cudaMemcpyHostToDevice, s));
+    fill_ref_codes_kernel<<<148 * 8, 256, 0, s>>>(h->d_bstage.p, h->d_codes.p, ld, Lp, h->n_tips);
+    h->launches += 1;
+    if (n_entries) {
+      if ((rc = upload(h->d_ent_row, entry_row, (size_t)n_entries, s))) return rc;
+      if ((rc = upload(h->d_ent_pos, entry_pos, (size_t)n_entries, s))) return rc;
+      if ((rc = h->d_mut_state.alloc(std::max(h->d_mut_state.n, (size_t)n_entries)))) return rc;
+      CK(cudaMemcpyAsync(h->d_mut_state.p, entry_code, (size_t)n_entries, cudaMemcpyHostToDevice, s));
+      scatter_codes_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, s>>>(h->d_ent_row.p, h->d_ent_pos.p, h->d_mut_state.p,
+                                                                               n_entries, h->d_codes.p, ld);
+      h->launches += 1;
+    }
+    CK(cudaGetLastError());
+    return 0;
+  });
+}
+
 int ttb_set_gtr(ttb_handle h, const double* eigvals, const double* v, const double* v_inv, const double* Pi,
                 double mu, int32_t gap_index) {
   if (int rc = use_device(h)) return rc;
@@ -545,11 +628,15 @@ int ttb_set_gtr(ttb_handle h, const double* eigvals, const double* v, const doub
   cudaStream_t s = h->stream;
   int rc;
   const bool realloc = !h->d_eig.p;
-  if ((rc = upload(h->d_eig, eigvals, q, s))) return rc;
-  if ((rc = upload(h->d_v, v, q * q, s))) return rc;
-  if ((rc = upload(h->d_vinv, v_inv, q * q, s))) return rc;
-  if ((rc = upload(h->d_Pi, Pi, q, s))) return rc;
-  if ((rc = upload(h->d_mu, &mu, 1, s))) return rc;   // pageable sources are staged before the call returns
+  (void)s;
+  if ((rc = h->d_eig.alloc(q)) || (rc = h->d_v.alloc(q * q)) || (rc = h->d_vinv.alloc(q * q)) || (rc = h->d_Pi.alloc(q)) ||
+      (rc = h->d_mu.alloc(1)))
+    return rc;
+  if ((rc = upload_small(h, h->d_eig.p, eigvals, q * sizeof(double)))) return rc;
+  if ((rc = upload_small(h, h->d_v.p, v, q * q * sizeof(double)))) return rc;
+  if ((rc = upload_small(h, h->d_vinv.p, v_inv, q * q * sizeof(double)))) return rc;
+  if ((rc = upload_small(h, h->d_Pi.p, Pi, q * sizeof(double)))) return rc;
+  if ((rc = upload_small(h, h->d_mu.p, &mu, sizeof(double)))) return rc;
   if (realloc || h->site_specific) h->drop_graphs();
   h->site_specific = false;
   h->mu = mu;
@@ -642,7 +729,7 @@ int ttb_set_branch_lengths(ttb_handle h, const double* t) {
   const bool realloc = !h->d_t.p;
   if (int rc = h->d_t.alloc(h->n_nodes)) return rc;
   // pageable source: the copy is staged before the call returns, so the caller may reuse `t`
-  CK(cudaMemcpyAsync(h->d_t.p, t, h->n_nodes * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (int rc = upload_small(h, h->d_t.p, t, h->n_nodes * sizeof(double))) return rc;
   h->h_t.assign(t, t + h->n_nodes);
   h->ss_interp_dirty = true;
   if (realloc) h->drop_graphs();
@@ -758,6 +845,38 @@ int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* ou
     CK(cudaMemcpyAsync(out + (size_t)k * h->Lp, src, h->Lp, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ttb_fetch_mutations(ttb_handle h, uint8_t* root_idx, int32_t max_n, int32_t* node, int32_t* pos, uint8_t* state,
+                        int64_t* n) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, true)) return rc;
+  if (!root_idx || !n || max_n < 0 || (max_n && (!node || !pos || !state))) return fail(TTB_EINVAL, "ttb_fetch_mutations: bad arguments");
+  int rc;
+  if ((rc = h->d_mut_node.alloc(std::max(h->d_mut_node.n, (size_t)std::max(max_n, 1))))) return rc;
+  if ((rc = h->d_mut_pos.alloc(std::max(h->d_mut_pos.n, (size_t)std::max(max_n, 1))))) return rc;
+  if ((rc = h->d_mut_state.alloc(std::max(h->d_mut_state.n, (size_t)std::max(max_n, 1))))) return rc;
+  if ((rc = h->d_mut_count.alloc(1))) return rc;
+  cudaStream_t s = h->stream;
+  CK(cudaMemsetAsync(h->d_mut_count.p, 0, sizeof(unsigned long long), s));
+  const int chunks = std::max(1, std::min(h->n_nodes - 1, (148 * 16 + h->tiles() - 1) / h->tiles()));
+  mutations_kernel<<<dim3(h->tiles(), chunks), TTB_BLOCK, 0, s>>>(h->dev(), max_n, h->d_mut_node.p, h->d_mut_pos.p, h->d_mut_state.p,
+                                                                  h->d_mut_count.p);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  unsigned long long cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, h->d_mut_count.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(root_idx, h->d_idx.p + (size_t)h->int_slot[0] * h->ld, (size_t)h->Lp, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const size_t m = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)max_n);
+  if (m) {
+    CK(cudaMemcpyAsync(node, h->d_mut_node.p, m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(pos, h->d_mut_pos.p, m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(state, h->d_mut_state.p, m, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  *n = (int64_t)cnt;
   return 0;
 }
 

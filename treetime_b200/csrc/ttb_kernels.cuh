@@ -665,6 +665,45 @@ static __global__ void pitch_bytes_kernel(const uint8_t* __restrict__ src, long 
   }
 }
 
+// Sparse alignment input (the analogue of TreeTime's VCF / dict-of-differences alignments,
+// sequence_data.py:363-383): every tip row starts as the reference row, then the listed
+// (tip row, pattern, code) differences are scattered in.
+static __global__ void fill_ref_codes_kernel(const uint8_t* __restrict__ ref, uint8_t* __restrict__ codes, long long ld,
+                                             long long Lp, long long rows) {
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    uint8_t* __restrict__ d = codes + r * ld;
+    for (long long c = threadIdx.x; c < ld; c += blockDim.x) d[c] = (c < Lp) ? ref[c] : 0;
+  }
+}
+static __global__ void scatter_codes_kernel(const int* __restrict__ row, const int* __restrict__ pos, const uint8_t* __restrict__ code,
+                                            long long n, uint8_t* __restrict__ codes, long long ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) codes[(long long)row[i] * ld + pos[i]] = code[i];
+}
+
+// Sparse result: the reconstructed sequences as (node, pattern, state) wherever an internal node's
+// state differs from its parent's (the content of `node.mutations`, treeanc.py:27-42, on compressed
+// patterns) -- together with the root row this determines every sequence.  grid = (tiles, node chunks).
+static __global__ void mutations_kernel(TtbDev p, int max_n, int* __restrict__ out_node, int* __restrict__ out_pos,
+                                        uint8_t* __restrict__ out_state, unsigned long long* __restrict__ counter) {
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.Lp) return;
+  for (int n = 1 + blockIdx.y; n < p.n_nodes; n += gridDim.y) {
+    const int slot = p.int_slot[n];
+    if (slot < 0) continue;
+    const uint8_t s = p.idx[(size_t)slot * p.ld + a];
+    const uint8_t ps = p.idx[(size_t)p.int_slot[p.parent[n]] * p.ld + a];
+    if (s != ps) {
+      const unsigned long long k = atomicAdd(counter, 1ull);
+      if (k < (unsigned long long)max_n) {
+        out_node[k] = n;
+        out_pos[k] = (int)a;
+        out_state[k] = s;
+      }
+    }
+  }
+}
+
 static __global__ void zero_slots_kernel(TtbDev p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 1024) p.nd_slots[i] = 0ull;

@@ -113,7 +113,7 @@ class DeviceMarginalMixin(object):
             self._device_data_id = data_id
             codes, table = self._tip_codes()
             lo, hi = self._shard()
-            eng.set_patterns(codes, table, self.data.multiplicity()[lo:hi])
+            eng.set_patterns(codes, table, self.data.multiplicity()[lo:hi], validate=False)   # codes built by _tip_codes
             self._device_patterns = True
         g = gtr_arrays(self.gtr)
         upload_model = True

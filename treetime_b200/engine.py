@@ -63,7 +63,8 @@ class Engine(object):
         self.n_nodes = int(parent.shape[0])
         self.tip_row = tip_row
 
-    def set_patterns(self, tip_codes, code_profiles, multiplicity):
+    def set_patterns(self, tip_codes, code_profiles, multiplicity, validate=True):
+        """validate=False skips the host-side range scan of the code matrix (it costs a pass over it)."""
         tip_codes = np.ascontiguousarray(tip_codes, dtype=np.uint8)
         code_profiles = _f64(code_profiles)
         multiplicity = _f64(multiplicity)
@@ -71,11 +72,24 @@ class Engine(object):
             raise ValueError('code_profiles must have n_states columns')
         if tip_codes.shape[1] != multiplicity.shape[0]:
             raise ValueError('tip_codes and multiplicity disagree on the number of patterns')
-        if tip_codes.size and int(tip_codes.max()) >= code_profiles.shape[0]:
+        if validate and tip_codes.size and int(tip_codes.max()) >= code_profiles.shape[0]:
             raise ValueError('tip code out of range of code_profiles')
         _lib.check(self.lib.ttb_set_patterns(self.h, tip_codes.shape[1], _up(tip_codes), code_profiles.shape[0],
                                              _dp(code_profiles), _dp(multiplicity)))
         self.n_patterns = int(tip_codes.shape[1])
+
+    def set_patterns_sparse(self, ref_codes, entry_row, entry_pos, entry_code, code_profiles, multiplicity):
+        """Every tip row = ref_codes except at the listed (tip row, pattern, code) entries."""
+        ref_codes = np.ascontiguousarray(ref_codes, dtype=np.uint8)
+        entry_row, entry_pos = _i32(entry_row), _i32(entry_pos)
+        entry_code = np.ascontiguousarray(entry_code, dtype=np.uint8)
+        code_profiles, multiplicity = _f64(code_profiles), _f64(multiplicity)
+        if code_profiles.shape[1] != self.n_states or ref_codes.shape[0] != multiplicity.shape[0]:
+            raise ValueError('inconsistent sparse pattern arguments')
+        _lib.check(self.lib.ttb_set_patterns_sparse(self.h, ref_codes.shape[0], _up(ref_codes), entry_row.shape[0],
+                                                    _ip(entry_row), _ip(entry_pos), _up(entry_code), code_profiles.shape[0],
+                                                    _dp(code_profiles), _dp(multiplicity)))
+        self.n_patterns = int(ref_codes.shape[0])
 
     def set_gtr(self, g):
         """g: dict from flatten.gtr_arrays()."""
@@ -141,6 +155,23 @@ class Engine(object):
             out = np.empty((n_int, self.n_patterns), dtype=np.uint8)
         _lib.check(self.lib.ttb_fetch_all_seq_idx(self.h, _up(out)))
         return out
+
+    def mutations(self, max_n=None):
+        """Sparse form of all reconstructed sequences: (root_idx[L'], node[], pos[], state[]) with one entry per
+        (internal node, pattern) whose state differs from the parent's, sorted by (node, pos)."""
+        if max_n is None:
+            max_n = max(1 << 16, 8 * self.n_nodes)
+        root = np.empty(self.n_patterns, dtype=np.uint8)
+        while True:
+            node = np.empty(max_n, dtype=np.int32); pos = np.empty(max_n, dtype=np.int32); st = np.empty(max_n, dtype=np.uint8)
+            n = ctypes.c_int64()
+            _lib.check(self.lib.ttb_fetch_mutations(self.h, _up(root), max_n, _ip(node), _ip(pos), _up(st), ctypes.byref(n)))
+            if n.value <= max_n:
+                break
+            max_n = int(n.value)
+        m = int(n.value)
+        order = np.lexsort((pos[:m], node[:m]))
+        return root, node[:m][order], pos[:m][order], st[:m][order]
 
     def enqueue_site_lh(self, out):
         """Stream-ordered D2H of tree.sequence_LH into `out` (pinned); valid after sync()."""
