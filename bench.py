@@ -191,7 +191,7 @@ def main():
     ap.add_argument('--cpu-patterns', type=int, default=0, help='patterns in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--e2e-blocks', type=int, default=4, help='pattern blocks (engine handles / streams) of the e2e leg')
+    ap.add_argument('--e2e-blocks', type=int, default=6, help='pattern blocks (engine handles / streams) of the e2e leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 0)
 
@@ -311,19 +311,33 @@ def main():
         for i in range(nblk):
             lo, hi = bounds[i], bounds[i + 1]
             e = Engine(q, device=local_rank)
+            st_i = torch.cuda.Stream()
+            e.set_stream(st_i.cuda_stream)
             e.set_tree(flat['parent'], flat['child_ptr'], flat['child_idx'], flat['tip_row'])
             cp = torch.empty((flat['tip_codes'].shape[0], hi - lo), dtype=torch.uint8, pin_memory=True)
             cp.numpy()[...] = flat['tip_codes'][:, lo:hi]
             sp = torch.empty((n_int, hi - lo), dtype=torch.uint8, pin_memory=True)
             lp = torch.empty(hi - lo, dtype=torch.float64, pin_memory=True)
-            shards.append((e, cp.numpy(), sp.numpy(), lp.numpy(), np.ascontiguousarray(flat['multiplicity'][lo:hi]), cp, sp, lp))
+            shards.append((e, cp.numpy(), sp.numpy(), lp.numpy(), np.ascontiguousarray(flat['multiplicity'][lo:hi]), st_i, cp, sp, lp))
 
         def e2e_step():
-            for e, cp, sp, lp, m, *_ in shards:
+            # software pipeline over the blocks: uploads are chained (block k+1's copy starts when block k's
+            # has landed) and so are the passes; otherwise the DMA engine and the SMs time-slice all
+            # blocks and nothing overlaps
+            up_done = pass_done = None
+            for e, cp, sp, lp, m, st_i, *_ in shards:
+                if up_done is not None:
+                    st_i.wait_event(up_done)
                 e.set_patterns(cp, flat['code_profiles'], m, validate=False)
                 e.set_gtr(g)
                 e.set_branch_lengths(flat['t'])
+                up_done = torch.cuda.Event()
+                up_done.record(st_i)
+                if pass_done is not None:
+                    st_i.wait_event(pass_done)
                 e.marginal()
+                pass_done = torch.cuda.Event()
+                pass_done.record(st_i)
                 e.enqueue_site_lh(lp)
                 e.enqueue_all_seq_idx(sp)
             tot = 0.0
