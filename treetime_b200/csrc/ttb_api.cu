@@ -155,6 +155,7 @@ struct ttb_engine {
     d.q = q;
     d.Lp = Lp;
     d.ld = ld;
+    d.tiles = tiles();
     d.n_nodes = n_nodes;
     d.n_int = n_int;
     d.n_tips = n_tips;
@@ -357,7 +358,8 @@ int ensure_state(ttb_handle h, bool tips) {
     if (e) return fail(TTB_ECUDA, std::string("cudaFuncSetAttribute(shared memory) failed: ") + cudaGetErrorString((cudaError_t)e));
     h->prepared = true;
   }
-  if ((rc = h->d_S.alloc((size_t)h->n_int * q * ld))) return rc;
+  const size_t msg = (size_t)h->tiles() * q * TTB_TILE;   // one node's tile-blocked message: [tiles][q][128]
+  if ((rc = h->d_S.alloc((size_t)h->n_int * msg))) return rc;
   if ((rc = h->d_LH.alloc(ld))) return rc;
   if ((rc = h->d_lh_partial.alloc(h->tiles()))) return rc;
   if ((rc = h->d_nd.alloc(1024))) return rc;
@@ -369,13 +371,13 @@ int ensure_preorder_state(ttb_handle h, bool tips) {
   const size_t q = h->q, ld = h->ld;
   int rc;
   if (!h->d_M.p) {
-    if ((rc = h->d_M.alloc((size_t)h->n_int * q * ld))) return rc;
+    if ((rc = h->d_M.alloc((size_t)h->n_int * h->tiles() * q * TTB_TILE))) return rc;
     if ((rc = h->d_idx.alloc((size_t)h->n_int * ld))) return rc;
     CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), h->stream));
     h->drop_graphs();
   }
   if (tips && !h->d_Mtip.p) {
-    if ((rc = h->d_Mtip.alloc((size_t)h->n_tips * q * ld))) return rc;
+    if ((rc = h->d_Mtip.alloc((size_t)h->n_tips * h->tiles() * q * TTB_TILE))) return rc;
     if ((rc = h->d_idxtip.alloc((size_t)h->n_tips * ld))) return rc;
     CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), h->stream));
     h->drop_graphs();

@@ -44,7 +44,8 @@ struct TtbChunk {
 struct TtbDev {
   int q;
   long long Lp;       // patterns in this shard
-  long long ld;       // padded pattern stride (multiple of 32)
+  long long ld;       // padded pattern stride of the byte / scalar rows (multiple of 32)
+  int tiles;          // number of 128-pattern tiles = ceil(Lp / 128)
   int n_nodes, n_int, n_tips, n_codes;
   int gap_index;
   // tree
@@ -82,12 +83,15 @@ struct TtbDev {
   int tu_stride; // stride of one tip table in doubles (n_codes*q rounded up to even)
   double* TU;    // [n_tips][tu_stride]  tip message table: TU[code*q+j] = sum_i prof[code][i] P[i][j]
   double* P;     // [n_nodes][pq]  exp(Q t_c), P[i*q+j] = Prob(child=i | parent=j)
-  double* S;     // [n_int][q][ld]  marginal_subtree_LH
+  // message arrays are TILE-BLOCKED state-planar: [slot][tile][state][128]: the q rows of one
+  // (node, tile) are one contiguous q KB block = one TMA copy, and 128 consecutive patterns of a
+  // state are one coalesced 1 KB row
+  double* S;     // [n_int][tiles][q][128]  marginal_subtree_LH
   double* Fpart; // [n_fgroups][ld] per-pattern sums of log-normalisers over the nodes of one postorder block run
   int n_fgroups; //                 (sum over all runs = marginal_subtree_LH_prefactor of the root)
   double* Fred;  // [TTB_FLANES][ld] first reduction stage of Fpart
-  double* M;     // [n_int][q][ld]  marginal_profile
-  double* Mtip;  // [n_tips][q][ld] marginal_profile of tips (reconstruct_tip_states) or null
+  double* M;     // [n_int][tiles][q][128]  marginal_profile
+  double* Mtip;  // [n_tips][tiles][q][128] marginal_profile of tips (reconstruct_tip_states) or null
   uint8_t* idx;     // [n_int][ld]  argmax state
   uint8_t* idxtip;  // [n_tips][ld] or null
   double* LH;       // [ld] tree.sequence_LH
@@ -133,6 +137,13 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// Element (slot, state 0, pattern a) of a tile-blocked message array; consecutive states are
+// TTB_TILE doubles apart.
+template <int Q>
+__device__ __forceinline__ size_t msg_off(const TtbDev& p, int slot, long long a) {
+  return ((size_t)slot * p.tiles + (size_t)(a / TTB_TILE)) * (size_t)(Q * TTB_TILE) + (size_t)(a % TTB_TILE);
 }
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -415,22 +426,22 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
     uint32_t bytes = 32;
     for (int b = 0; b < nch; ++b) {
       if (SS)  // site-specific: the transition matrices are per pattern, nothing per branch to stage
-        bytes += (c.src(b) >= 0) ? (uint32_t)(RPC * cols * 8) : (uint32_t)cols;
+        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8) : (uint32_t)cols;
       else
-        bytes += (c.src(b) >= 0) ? (uint32_t)(RPC * cols * 8 + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
+        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8 + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
     }
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, bytes);
       tma_load_1d((void*)pipe.desc(s), chunks + k0 + u, 32, bar);
     }
     __syncwarp();
-    for (int job = lane; job < nch * (RPC + 1); job += 32) {
-      const int b = job / (RPC + 1), r = job % (RPC + 1);
+    for (int job = lane; job < nch * 2; job += 32) {
+      const int b = job >> 1, r = job & 1;
       const int src = c.src(b);
       if (src >= 0) {
-        if (r < Q)
-          tma_load_1d(pipe.rows(s) + (b * RPC + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, bar);
-        else if (r == Q && !SS)
+        if (r == 0)   // the child's q rows of this tile are one contiguous block
+          tma_load_1d(pipe.rows(s) + (b * RPC) * TTB_TILE, p.S + msg_off<Q>(p, src, a0), Q * TTB_TILE * 8, bar);
+        else if (r == 1 && !SS)
           tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
       } else {
         const int row = -1 - src;
@@ -517,9 +528,9 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
 #pragma unroll
       for (int j = 1; j < Q; ++j) Z += X[j];
       const double inv = 1.0 / Z;
-      double* __restrict__ so = p.S + (size_t)c.out * Q * p.ld + a;
+      double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
 #pragma unroll
-      for (int j = 0; j < Q; ++j) so[(size_t)j * p.ld] = X[j] * inv;
+      for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j] * inv;
       Facc += log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
     }
   }
@@ -570,9 +581,9 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
 #pragma unroll
       for (int j = 1; j < Q; ++j) Z += X[j];
       const double inv = 1.0 / Z;
-      double* __restrict__ so = p.S + (size_t)c.out * Q * p.ld + a;
+      double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
 #pragma unroll
-      for (int j = 0; j < Q; ++j) so[(size_t)j * p.ld] = X[j] * inv;
+      for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j] * inv;
       Facc += log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
     }
   }
@@ -601,12 +612,12 @@ __global__ void __launch_bounds__(TTB_BLOCK) root_kernel(TtbDev p, int lh_only) 
   double contrib = 0.0;
   if (a < p.Lp) {
     const int slot = p.int_slot[0];
-    const double* __restrict__ s = p.S + (size_t)slot * Q * p.ld + a;
+    const double* __restrict__ s = p.S + msg_off<Q>(p, slot, a);
     double R[Q];
     double Z = 0.0;
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-      R[j] = (SS ? p.ss_Pi[(size_t)j * p.ld + a] : p.Pi[j]) * s[(size_t)j * p.ld];   // Pi.T at the root, treeanc.py:817-820
+      R[j] = (SS ? p.ss_Pi[(size_t)j * p.ld + a] : p.Pi[j]) * s[j * TTB_TILE];   // Pi.T at the root, treeanc.py:817-820
       Z += R[j];
     }
     double F = 0.0;   // fixed summation order (fsum_kernel lanes, then here): deterministic
@@ -617,11 +628,11 @@ __global__ void __launch_bounds__(TTB_BLOCK) root_kernel(TtbDev p, int lh_only) 
     contrib = lh * p.mult[a];
     if (!lh_only) {
       const double inv = 1.0 / Z;
-      double* __restrict__ m = p.M + (size_t)slot * Q * p.ld + a;
+      double* __restrict__ m = p.M + msg_off<Q>(p, slot, a);
 #pragma unroll
       for (int j = 0; j < Q; ++j) {
         R[j] *= inv;
-        m[(size_t)j * p.ld] = R[j];
+        m[j * TTB_TILE] = R[j];
       }
       int best = 0;
       double bv = R[0];
@@ -775,30 +786,30 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
     uint64_t* bar = pipe.full + s;
     const int nch = c.nch();
     const bool first = c.flags & 1;
-    uint32_t bytes = 32 + (first ? (uint32_t)(Q * cols * 8) : 0u);
+    uint32_t bytes = 32 + (first ? (uint32_t)(Q * TTB_TILE * 8) : 0u);
     for (int b = 0; b < nch; ++b) {
       if (SS)
-        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * cols * 8 + cols) : (uint32_t)(2 * cols);
+        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8 + cols) : (uint32_t)(2 * cols);
       else
-        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * cols * 8 + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
+        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8 + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
     }
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, bytes);
       tma_load_1d((void*)pipe.desc(s), chunks + k0 + u, 32, bar);
     }
     __syncwarp();
-    if (first)
-      for (int r = lane; r < Q; r += 32)
-        tma_load_1d(pipe.rows(s) + r * TTB_TILE, p.M + ((size_t)c.out * Q + r) * p.ld + a0, cols * 8, bar);
-    for (int job = lane; job < nch * (Q + 2); job += 32) {
-      const int b = job / (Q + 2), r = job % (Q + 2);
+    if (first && lane == 31)   // the parent's profile tile: one contiguous q KB block
+      tma_load_1d(pipe.rows(s), p.M + msg_off<Q>(p, c.out, a0), Q * TTB_TILE * 8, bar);
+    // jobs of child b: 0 profile block / codes | 1 old states / tip table | 2 tip old states | 3 exp(Qt)
+    for (int job = lane; job < nch * 4; job += 32) {
+      const int b = job >> 2, r = job & 3;
       const int src = c.src(b);
-      if (r == Q + 1) {
+      if (r == 3) {
         if (!SS) tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
       } else if (src >= 0) {
-        if (r < Q)
-          tma_load_1d(pipe.rows(s) + (Q + b * Q + r) * TTB_TILE, p.S + ((size_t)src * Q + r) * p.ld + a0, cols * 8, bar);
-        else
+        if (r == 0)
+          tma_load_1d(pipe.rows(s) + (Q + b * Q) * TTB_TILE, p.S + msg_off<Q>(p, src, a0), Q * TTB_TILE * 8, bar);
+        else if (r == 1)
           tma_load_1d(pipe.oidx(s) + b * TTB_TILE, p.idx + (size_t)src * p.ld + a0, cols, bar);
       } else if (TIPS) {
         const int row = -1 - src;
@@ -838,10 +849,10 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
         uint8_t* ip;
         if (TIPS && src < 0) {
           const int row = -1 - src;
-          out = p.Mtip + (size_t)row * Q * p.ld + a;
+          out = p.Mtip + msg_off<Q>(p, row, a);
           ip = p.idxtip + (size_t)row * p.ld + a;
         } else {
-          out = p.M + (size_t)src * Q * p.ld + a;
+          out = p.M + msg_off<Q>(p, src, a);
           ip = p.idx + (size_t)src * p.ld + a;
         }
         int best = 0;
@@ -873,7 +884,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
 #pragma unroll
           for (int i = 0; i < Q; ++i) {
             const double x = msg[i] * inv;
-            out[(size_t)i * p.ld] = x;
+            out[i * TTB_TILE] = x;
             if (x > bv) { bv = x; best = i; }
           }
         } else if constexpr (Q <= 8) {
@@ -914,7 +925,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
 #pragma unroll
           for (int i = 0; i < Q; ++i) {
             const double x = prof[i] * inv;
-            out[(size_t)i * p.ld] = x;
+            out[i * TTB_TILE] = x;
             if (x > bv) { bv = x; best = i; }
           }
         } else {
@@ -962,7 +973,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
           double bv = -1.0;
           for (int i = 0; i < Q; ++i) {
             const double x = col[i * TTB_TILE] * inv;
-            out[(size_t)i * p.ld] = x;
+            out[i * TTB_TILE] = x;
             if (x > bv) { bv = x; best = i; }
           }
         }
@@ -990,9 +1001,9 @@ __device__ __forceinline__ void node_subtree(const TtbDev& p, int n, long long a
 #pragma unroll
     for (int i = 0; i < Q; ++i) Sc[i] = p.code_prof[code * Q + i];
   } else {
-    const double* s = p.S + (size_t)p.int_slot[n] * Q * p.ld + a;
+    const double* s = p.S + msg_off<Q>(p, p.int_slot[n], a);
 #pragma unroll
-    for (int i = 0; i < Q; ++i) Sc[i] = s[(size_t)i * p.ld];
+    for (int i = 0; i < Q; ++i) Sc[i] = s[i * TTB_TILE];
   }
 }
 
@@ -1021,9 +1032,9 @@ __device__ __forceinline__ void branch_profiles(const TtbDev& p, int n, int kind
   }
   const int up = p.parent[n];
   double Mp[Q], U[Q];
-  const double* m = p.M + (size_t)p.int_slot[up] * Q * p.ld + a;
+  const double* m = p.M + msg_off<Q>(p, p.int_slot[up], a);
 #pragma unroll
-  for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, m[(size_t)j * p.ld]);
+  for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, m[j * TTB_TILE]);
   if constexpr (SS) {
     const SiteModel<Q> sm(p, a);
     double e[Q];
@@ -1058,9 +1069,9 @@ __global__ void __launch_bounds__(TTB_BLOCK) fetch_node_kernel(TtbDev p, int nod
     }
   } else {
     const int row = p.tip_row[node];
-    const double* m = (row >= 0) ? p.Mtip + (size_t)row * Q * p.ld + a : p.M + (size_t)p.int_slot[node] * Q * p.ld + a;
+    const double* m = (row >= 0) ? p.Mtip + msg_off<Q>(p, row, a) : p.M + msg_off<Q>(p, p.int_slot[node], a);
 #pragma unroll
-    for (int j = 0; j < Q; ++j) x[j] = m[(size_t)j * p.ld];
+    for (int j = 0; j < Q; ++j) x[j] = m[j * TTB_TILE];
   }
 #pragma unroll
   for (int j = 0; j < Q; ++j) out[(size_t)a * Q + j] = x[j];
