@@ -89,6 +89,21 @@ int ttb_set_patterns_sparse(ttb_handle h, int64_t n_patterns, const uint8_t* ref
                             const int32_t* entry_row, const int32_t* entry_pos, const uint8_t* entry_code,
                             int32_t n_codes, const double* code_profiles, const double* multiplicity);
 
+/* N3 -- pattern compression on the device (SequenceData.make_compressed_alignment, sequence_data.py:325-464).
+ * Step 1: upload the raw alignment aln[n_seq][L] (ASCII, already upper-cased), optionally turn leading /
+ * trailing `gap` characters into `fill` (seq2array fill_overhangs, seq_utils.py:196-202; fill_overhangs = 0
+ * skips it) and return per column the extrema over the characters != `ambiguous` plus an all-ambiguous flag:
+ * a column is constant iff lo == hi (or all ambiguous).  The alignment stays resident on the device. */
+int ttb_alignment_stats(ttb_handle h, int64_t n_seq, int64_t L, const uint8_t* aln, int32_t fill_overhangs,
+                        int32_t gap, int32_t fill, int32_t ambiguous, uint8_t* lo, uint8_t* hi, uint8_t* all_amb);
+/* Step 2 (after the host numbered the patterns): pattern p is the column first_pos[p] of the resident
+ * alignment, or -- if const_letter[p] != 0 -- a constant column of that letter; tip t reads alignment row
+ * tip_seq_row[t] (-1 = no sequence = missing_code); lut[256] maps characters to codes (255 = unknown
+ * character -> TTB_EINVAL).  Equivalent to ttb_set_patterns with the gathered code matrix. */
+int ttb_set_patterns_from_alignment(ttb_handle h, int64_t n_patterns, const int64_t* first_pos, const uint8_t* const_letter,
+                                    const int32_t* tip_seq_row, const uint8_t* lut, int32_t missing_code, int32_t n_codes,
+                                    const double* code_profiles, const double* multiplicity);
+
 /* Single-site GTR eigen-system (gtr.py:612-629): eigvals[q], v[q][q], v_inv[q][q], Pi[q], mu.
  * gap_index = gtr.gap_index or -1 (used by the branch objective, gtr.py:954-959). */
 int ttb_set_gtr(ttb_handle h, const double* eigvals, const double* v, const double* v_inv,

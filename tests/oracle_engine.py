@@ -35,6 +35,28 @@ class OracleEngine(object):
         self.res = None
         self.prev_idx = None
 
+    def alignment_stats(self, aln, fill_overhangs=False, gap='-', fill='N', ambiguous='N'):
+        A = np.array(aln, dtype=np.uint8)
+        if fill_overhangs:
+            ng = A != ord(gap); anyng = ng.any(axis=1)
+            first = np.where(anyng, ng.argmax(axis=1), A.shape[1]); last = np.where(anyng, A.shape[1] - 1 - ng[:, ::-1].argmax(axis=1), -1)
+            pos = np.arange(A.shape[1])[None, :]
+            A[(pos < first[:, None]) | (pos > last[:, None])] = ord(fill)
+        self._aln = A
+        a = ord(ambiguous) if ambiguous is not None else 256
+        isa = A == a
+        return np.where(isa, 255, A).min(axis=0).astype(np.uint8), np.where(isa, 0, A).max(axis=0).astype(np.uint8), isa.all(axis=0)
+
+    def set_patterns_from_alignment(self, first_pos, const_letter, tip_seq_row, lut, missing_code, code_profiles, multiplicity):
+        C = self._aln[:, first_pos].copy()
+        cc = const_letter != 0
+        C[:, cc] = const_letter[cc][None, :]
+        codes = np.full((len(tip_seq_row), len(first_pos)), missing_code, dtype=np.uint8)
+        have = np.asarray(tip_seq_row) >= 0
+        codes[have] = lut[C[np.asarray(tip_seq_row)[have]]]
+        assert (codes != 255).all()
+        self.set_patterns(codes, code_profiles, multiplicity)
+
     def set_gtr(self, g):
         self.g = dict(g)
 

@@ -159,3 +159,28 @@ def test_gpu_one_vs_two_engine_shards_agree():
     whole = full.node_array(n, 1)
     halves = np.vstack([p[0].node_array(n, 1) for p in parts])
     assert np.array_equal(whole, halves)
+
+
+def test_gpu_device_pattern_compression():
+    """N3: column statistics + pattern gather on the device == host SequenceData compression."""
+    from treetime_b200.sequence_data import SequenceData
+    z = G.load('nuc40')
+    a = gpu_from_golden(z)
+    b = gpu_from_golden(z, device_compress=True)
+    assert b.data.device_resident
+    assert np.array_equal(a.data.multiplicity(), b.data.multiplicity())
+    assert np.array_equal(a.data.full_to_compressed_sequence_map, b.data.full_to_compressed_sequence_map)
+    assert np.array_equal(a.data.compressed_matrix, b.data.compressed_matrix)
+    check(b, z)
+    assert a.infer_ancestral_sequences(marginal=True) == int(z['N_diff_first'])
+    assert a.sequence_LH() == b.sequence_LH()
+    # larger, regenerated input incl. overhang gaps and an unknown character
+    tree, aln, g, sha = G.regenerate_big('cfg1')
+    names = sorted(aln)
+    aln[names[0]][:9] = '-'; aln[names[1]][-5:] = '-'; aln[names[2]][100:130] = 'N'
+    h = TreeAnc(tree=tree.to_newick(), aln=aln, gtr=g)
+    d = TreeAnc(tree=tree.to_newick(), aln=aln, gtr=g, device_compress=True)
+    assert np.array_equal(h.data.multiplicity(), d.data.multiplicity())
+    assert h.infer_ancestral_sequences(marginal=True) == d.infer_ancestral_sequences(marginal=True)
+    assert h.sequence_LH() == d.sequence_LH()
+    assert np.array_equal(h._engine.all_seq_idx(), d._engine.all_seq_idx())

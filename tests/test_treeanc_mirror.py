@@ -124,3 +124,17 @@ def test_reconstructed_alignment_and_mutations():
         if n.up is not None and not n.is_terminal():
             for a, pos, d in n.mutations:
                 assert aln[n.up.name][pos] == a and aln[n.name][pos] == d and a != d
+
+
+def test_device_compress_path_equals_host_compress():
+    """N3 host logic: patterns numbered from device-style column statistics give the same TreeAnc results."""
+    z = G.load('nuc40')
+    a = mirror_from_golden(z)
+    b = mirror_from_golden(z, device_compress=True)
+    assert b.data.device_resident and not a.data.device_resident
+    assert a.infer_ancestral_sequences(marginal=True) == b.infer_ancestral_sequences(marginal=True) == int(z['N_diff_first'])
+    assert a.sequence_LH() == b.sequence_LH() == float(z['total_LH'])
+    assert np.array_equal(a.tree.sequence_LH, b.tree.sequence_LH)
+    for x, y in zip(a.tree.find_clades(), b.tree.find_clades()):
+        if not x.is_terminal():
+            assert (x.cseq == y.cseq).all() and x.mutations == y.mutations

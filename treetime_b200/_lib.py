@@ -85,6 +85,10 @@ SIGNATURES = {
     'ttb_set_patterns': ([_H, ctypes.c_int64, _c_u8_p, ctypes.c_int32, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_set_patterns_sparse': ([_H, ctypes.c_int64, _c_u8_p, ctypes.c_int64, _c_int_p, _c_int_p, _c_u8_p, ctypes.c_int32,
                                  _c_dbl_p, _c_dbl_p], ctypes.c_int),
+    'ttb_alignment_stats': ([_H, ctypes.c_int64, ctypes.c_int64, _c_u8_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                             ctypes.c_int32, _c_u8_p, _c_u8_p, _c_u8_p], ctypes.c_int),
+    'ttb_set_patterns_from_alignment': ([_H, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), _c_u8_p, _c_int_p, _c_u8_p,
+                                         ctypes.c_int32, ctypes.c_int32, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_set_gtr': ([_H, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, ctypes.c_double, ctypes.c_int32], ctypes.c_int),
     'ttb_set_gtr_site_specific': ([_H, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, ctypes.c_int32,
                                    ctypes.c_double, ctypes.c_int32, ctypes.c_int32], ctypes.c_int),

@@ -123,7 +123,10 @@ struct ttb_engine {
   bool ss_interp_dirty = true;
   // state
   DBuf<double> d_Fred, d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
-  DBuf<uint8_t> d_idx, d_idxtip, d_bstage, d_mut_state;
+  DBuf<uint8_t> d_idx, d_idxtip, d_bstage, d_mut_state, d_aln, d_colstat, d_lut, d_constl;
+  DBuf<long long> d_firstpos;
+  DBuf<int> d_seqrow, d_flag;
+  long long aln_rows = 0, aln_L = 0;
   DBuf<int> d_mut_node, d_mut_pos, d_ent_row, d_ent_pos;
   DBuf<unsigned long long> d_mut_count;   // d_bstage: packed byte staging for contiguous H2D / D2H
   DBuf<unsigned long long> d_nd;
@@ -447,6 +450,8 @@ int ttb_destroy(ttb_handle h) {
   h->d_bstage.release();
   h->d_mut_state.release(); h->d_mut_node.release(); h->d_mut_pos.release(); h->d_ent_row.release(); h->d_ent_pos.release();
   h->d_mut_count.release();
+  h->d_aln.release(); h->d_colstat.release(); h->d_lut.release(); h->d_constl.release(); h->d_firstpos.release();
+  h->d_seqrow.release(); h->d_flag.release();
   h->d_nd.release();
   if (h->h_results) cudaFreeHost(h->h_results);
   if (h->h_scratch) cudaFreeHost(h->h_scratch);
@@ -591,6 +596,70 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
     CK(cudaGetLastError());
     return 0;
   });
+}
+
+int ttb_alignment_stats(ttb_handle h, int64_t n_seq, int64_t L, const uint8_t* aln, int32_t fill_overhangs, int32_t gap,
+                        int32_t fill, int32_t ambiguous, uint8_t* lo, uint8_t* hi, uint8_t* all_amb) {
+  if (int rc = use_device(h)) return rc;
+  if (n_seq <= 0 || L <= 0 || !aln || !lo || !hi || !all_amb) return fail(TTB_EINVAL, "ttb_alignment_stats: bad arguments");
+  cudaStream_t s = h->stream;
+  int rc;
+  if ((rc = h->d_aln.alloc((size_t)n_seq * L))) return rc;
+  if ((rc = h->d_colstat.alloc((size_t)3 * L))) return rc;
+  CK(cudaMemcpyAsync(h->d_aln.p, aln, (size_t)n_seq * L, cudaMemcpyHostToDevice, s));
+  if (fill_overhangs) {
+    fill_overhangs_kernel<<<(unsigned)((n_seq + 3) / 4), 128, 0, s>>>(h->d_aln.p, L, n_seq, (uint8_t)gap, (uint8_t)fill);
+    h->launches += 1;
+  }
+  column_stats_kernel<<<(unsigned)((L + 127) / 128), 128, 0, s>>>(h->d_aln.p, L, n_seq, ambiguous, h->d_colstat.p, h->d_colstat.p + L,
+                                                                h->d_colstat.p + 2 * L);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(lo, h->d_colstat.p, (size_t)L, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hi, h->d_colstat.p + L, (size_t)L, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(all_amb, h->d_colstat.p + 2 * L, (size_t)L, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  h->aln_rows = n_seq;
+  h->aln_L = L;
+  return 0;
+}
+
+int ttb_set_patterns_from_alignment(ttb_handle h, int64_t n_patterns, const int64_t* first_pos, const uint8_t* const_letter,
+                                    const int32_t* tip_seq_row, const uint8_t* lut, int32_t missing_code, int32_t n_codes,
+                                    const double* code_profiles, const double* multiplicity) {
+  if (!h) return fail(TTB_EINVAL, "null handle");
+  if (!h->d_aln.p) return fail(TTB_EINVAL, "ttb_set_patterns_from_alignment: call ttb_alignment_stats first");
+  if (!first_pos || !const_letter || !tip_seq_row || !lut || missing_code < 0 || missing_code >= n_codes)
+    return fail(TTB_EINVAL, "ttb_set_patterns_from_alignment: bad arguments");
+  for (int64_t i = 0; i < n_patterns; ++i)
+    if (!const_letter[i] && (first_pos[i] < 0 || first_pos[i] >= h->aln_L)) return fail(TTB_EINVAL, "ttb_set_patterns_from_alignment: column out of range");
+  for (int t = 0; t < h->n_tips; ++t)
+    if (tip_seq_row[t] >= h->aln_rows) return fail(TTB_EINVAL, "ttb_set_patterns_from_alignment: alignment row out of range");
+  int bad = 0;
+  int rc0 = set_patterns_common(h, n_patterns, n_codes, code_profiles, multiplicity, [&](long long Lp, long long ld, cudaStream_t s) -> int {
+    int rc;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    if ((rc = upload(h->d_firstpos, reinterpret_cast<const long long*>(first_pos), (size_t)Lp, s))) return rc;
+    if ((rc = upload(h->d_constl, const_letter, (size_t)Lp, s))) return rc;
+    if ((rc = upload(h->d_seqrow, tip_seq_row, (size_t)h->n_tips, s))) return rc;
+    if ((rc = upload(h->d_lut, lut, (size_t)256, s))) return rc;
+    if ((rc = h->d_flag.alloc(1))) return rc;
+    CK(cudaMemsetAsync(h->d_flag.p, 0, sizeof(int), s));
+    gather_patterns_kernel<<<148 * 8, 256, 0, s>>>(h->d_aln.p, h->aln_L, h->d_firstpos.p, h->d_constl.p, h->d_seqrow.p, h->d_lut.p,
+                                                    missing_code, Lp, ld, h->n_tips, h->d_codes.p, h->d_flag.p);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&bad, h->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+  });
+  if (rc0) return rc0;
+  if (bad) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "ttb_set_patterns_from_alignment: character '%c' (%d) is not in the profile map", (char)(bad - 1), bad - 1);
+    return fail(TTB_EINVAL, buf);
+  }
+  return 0;
 }
 
 int ttb_set_patterns_sparse(ttb_handle h, int64_t n_patterns, const uint8_t* ref_codes, int64_t n_entries,

@@ -676,6 +676,72 @@ static __global__ void pitch_bytes_kernel(const uint8_t* __restrict__ src, long 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// N3: pattern compression on the device.  Reference: SequenceData.make_compressed_alignment
+// (sequence_data.py:325-464) + seq2array's overhang filling (seq_utils.py:196-202).
+// The raw ASCII alignment [n_seq][L] stays resident; per column the extrema over the
+// non-ambiguous characters decide whether the column is constant (possibly after replacing the
+// ambiguous character by the single other letter, :386-392); the host numbers the patterns
+// (a 30k-element job) and the device gathers the first-occurrence columns into the padded
+// code matrix through the character -> code table.
+// ---------------------------------------------------------------------------------------
+// one warp per sequence: leading / trailing gaps become `fill`
+static __global__ void fill_overhangs_kernel(uint8_t* __restrict__ aln, long long L, long long n_seq, uint8_t gap, uint8_t fill) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_seq) return;
+  const int lane = threadIdx.x & 31;
+  uint8_t* r = aln + row * L;
+  long long first = L, last = -1;
+  for (long long c = lane; c < L; c += 32)
+    if (r[c] != gap) { first = min(first, c); last = max(last, c); }
+  for (int o = 16; o > 0; o >>= 1) {
+    first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  }
+  for (long long c = lane; c < L; c += 32)
+    if (c < first || c > last) r[c] = fill;
+}
+
+// one thread per column, rows streamed (coalesced across columns)
+static __global__ void column_stats_kernel(const uint8_t* __restrict__ aln, long long L, long long n_seq, int amb,
+                                           uint8_t* __restrict__ lo, uint8_t* __restrict__ hi, uint8_t* __restrict__ all_amb) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= L) return;
+  int mn = 255, mx = 0, any = 0;
+  for (long long r = 0; r < n_seq; ++r) {
+    const int v = aln[r * L + c];
+    if (v != amb) { mn = min(mn, v); mx = max(mx, v); any = 1; }
+  }
+  lo[c] = (uint8_t)mn;
+  hi[c] = (uint8_t)mx;
+  all_amb[c] = any ? 0 : 1;
+}
+
+// codes[tip][p] = lut[const_letter[p] ? const_letter[p] : aln[seq_row[tip]][first_pos[p]]]; missing tips = missing_code
+static __global__ void gather_patterns_kernel(const uint8_t* __restrict__ aln, long long L, const long long* __restrict__ first_pos,
+                                              const uint8_t* __restrict__ const_letter, const int* __restrict__ seq_row,
+                                              const uint8_t* __restrict__ lut, int missing_code, long long Lp, long long ld,
+                                              long long n_tips, uint8_t* __restrict__ codes, int* __restrict__ bad) {
+  for (long long t = blockIdx.x; t < n_tips; t += gridDim.x) {
+    const int sr = seq_row[t];
+    const uint8_t* r = aln + (long long)sr * L;
+    uint8_t* d = codes + t * ld;
+    for (long long pidx = threadIdx.x; pidx < ld; pidx += blockDim.x) {
+      uint8_t code = 0;
+      if (pidx < Lp) {
+        if (sr < 0) {
+          code = (uint8_t)missing_code;
+        } else {
+          const uint8_t ch = const_letter[pidx] ? const_letter[pidx] : r[first_pos[pidx]];
+          code = lut[ch];
+          if (code == 255) { atomicExch(bad, (int)ch + 1); code = (uint8_t)missing_code; }
+        }
+      }
+      d[pidx] = code;
+    }
+  }
+}
+
 // Sparse alignment input (the analogue of TreeTime's VCF / dict-of-differences alignments,
 // sequence_data.py:363-383): every tip row starts as the reference row, then the listed
 // (tip row, pattern, code) differences are scattered in.

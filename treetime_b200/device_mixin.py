@@ -111,9 +111,19 @@ class DeviceMarginalMixin(object):
             self._device_patterns = False
         if not self._device_patterns:
             self._device_data_id = data_id
-            codes, table = self._tip_codes()
             lo, hi = self._shard()
-            eng.set_patterns(codes, table, self.data.multiplicity()[lo:hi], validate=False)   # codes built by _tip_codes
+            if getattr(self.data, 'device_resident', False):
+                # the raw alignment already lives on the device (N3): gather the code matrix there
+                chars, lut, table = code_table(self.gtr.profile_map, self.gtr.n_states)
+                lut8 = np.full(256, 255, dtype=np.uint8)
+                for c, i in lut.items():
+                    lut8[ord(c)] = i
+                rows = np.array([self.data._row.get(topo.nodes[n].name, -1) for n in topo.tip_nodes], dtype=np.int32)
+                eng.set_patterns_from_alignment(self.data.pattern_first_position[lo:hi], self.data.pattern_const_letter[lo:hi],
+                                                rows, lut8, len(chars), table, self.data.multiplicity()[lo:hi])
+            else:
+                codes, table = self._tip_codes()
+                eng.set_patterns(codes, table, self.data.multiplicity()[lo:hi], validate=False)   # codes built by _tip_codes
             self._device_patterns = True
         g = gtr_arrays(self.gtr)
         upload_model = True

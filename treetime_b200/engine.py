@@ -78,6 +78,29 @@ class Engine(object):
                                              _dp(code_profiles), _dp(multiplicity)))
         self.n_patterns = int(tip_codes.shape[1])
 
+    def alignment_stats(self, aln, fill_overhangs=False, gap='-', fill='N', ambiguous='N'):
+        """Upload the raw ASCII alignment [n_seq, L] (kept resident) and return per column
+        (lo, hi, all_ambiguous): extrema over the non-ambiguous characters."""
+        aln = np.ascontiguousarray(aln, dtype=np.uint8)
+        L = aln.shape[1]
+        lo = np.empty(L, dtype=np.uint8); hi = np.empty(L, dtype=np.uint8); aa = np.empty(L, dtype=np.uint8)
+        amb = ord(ambiguous) if ambiguous is not None else 256
+        _lib.check(self.lib.ttb_alignment_stats(self.h, aln.shape[0], L, _up(aln), 1 if fill_overhangs else 0, ord(gap),
+                                                ord(fill), amb, _up(lo), _up(hi), _up(aa)))
+        return lo, hi, aa.astype(bool)
+
+    def set_patterns_from_alignment(self, first_pos, const_letter, tip_seq_row, lut, missing_code, code_profiles, multiplicity):
+        """Gather the compressed code matrix on the device from the resident alignment."""
+        first_pos = np.ascontiguousarray(first_pos, dtype=np.int64)
+        const_letter = np.ascontiguousarray(const_letter, dtype=np.uint8)
+        tip_seq_row = _i32(tip_seq_row)
+        lut = np.ascontiguousarray(lut, dtype=np.uint8)
+        code_profiles, multiplicity = _f64(code_profiles), _f64(multiplicity)
+        _lib.check(self.lib.ttb_set_patterns_from_alignment(
+            self.h, first_pos.shape[0], first_pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _up(const_letter), _ip(tip_seq_row),
+            _up(lut), int(missing_code), code_profiles.shape[0], _dp(code_profiles), _dp(multiplicity)))
+        self.n_patterns = int(first_pos.shape[0])
+
     def set_patterns_sparse(self, ref_codes, entry_row, entry_pos, entry_code, code_profiles, multiplicity):
         """Every tip row = ref_codes except at the listed (tip row, pattern, code) entries."""
         ref_codes = np.ascontiguousarray(ref_codes, dtype=np.uint8)

@@ -62,7 +62,10 @@ class SequenceData(object):
     """
 
     def __init__(self, aln, compress=True, convert_upper=True, fill_overhangs=True, ambiguous='N',
-                 sequence_length=None, logger=None):
+                 sequence_length=None, logger=None, device_stats=None):
+        """device_stats: optional callable (matrix, fill_overhangs, gap, fill, ambiguous) -> (lo, hi, all_amb)
+        that computes the per-column statistics on the GPU (Engine.alignment_stats) and
+        keeps the alignment resident there; the host then only numbers the patterns."""
         self.logger = logger or (lambda *a, **k: None)
         self.compress = compress
         self.ambiguous = ambiguous
@@ -82,14 +85,20 @@ class SequenceData(object):
         L = rows[0].shape[0]
         if any(r.shape[0] != L for r in rows):
             raise ValueError('SequenceData: sequences differ in length')
-        self.matrix = np.vstack(rows) if len(rows) > 1 else rows[0][None, :].copy()
-        if fill_overhangs:
-            # with no ambiguous character the reference assigns None into a 'U1' array, which
-            # numpy stores as 'N' (seq_utils.py:196-202): reproduce that
-            self._fill_overhangs(ord(ambiguous) if ambiguous is not None else ord('N'))
+        self._matrix = np.vstack(rows) if len(rows) > 1 else rows[0][None, :].copy()
+        # with no ambiguous character the reference assigns None into a 'U1' array, which numpy stores
+        # as 'N' (seq_utils.py:196-202): reproduce that
+        self._fill_char = (ord(ambiguous) if ambiguous is not None else ord('N')) if fill_overhangs else None
+        self._filled = self._fill_char is None
+        self._col_stats = None
+        self.device_resident = False
         if self.ambiguous is None:                      # sequence_data.py:322-323
-            nuc = np.isin(self.matrix, np.frombuffer(b'acgtACGT-N', dtype=np.uint8)).sum()
-            self.ambiguous = 'N' if nuc > 0.9 * self.matrix.size else 'X'
+            nuc = np.isin(self._matrix, np.frombuffer(b'acgtACGT-N', dtype=np.uint8)).sum()
+            self.ambiguous = 'N' if nuc > 0.9 * self._matrix.size else 'X'
+        if device_stats is not None and compress and not (sequence_length and int(sequence_length) > L):
+            self._col_stats = device_stats(self._matrix, self._fill_char is not None, '-',
+                                           chr(self._fill_char) if self._fill_char is not None else 'N', self.ambiguous)
+            self.device_resident = True
         self.full_length = int(sequence_length) if sequence_length else L
         if self.full_length < L:
             raise AttributeError('SequenceData: specified sequence length is smaller than alignment length!')
@@ -97,9 +106,17 @@ class SequenceData(object):
         self._row = {k: i for i, k in enumerate(self.sequence_names)}
         self.make_compressed_alignment()
 
+    @property
+    def matrix(self):
+        """Host copy of the alignment with overhangs filled (lazily when the device did the statistics)."""
+        if not self._filled:
+            self._fill_overhangs(self._fill_char)
+            self._filled = True
+        return self._matrix
+
     def _fill_overhangs(self, amb):
         """Leading/trailing gaps -> ambiguous (seq2array fill_overhangs, seq_utils.py:196-202)."""
-        A = self.matrix
+        A = self._matrix
         nongap = A != ord('-')
         any_ng = nongap.any(axis=1)
         first = np.where(any_ng, nongap.argmax(axis=1), A.shape[1])
@@ -119,8 +136,11 @@ class SequenceData(object):
         return self._multiplicity if mask is None else self._multiplicity * mask
 
     def make_compressed_alignment(self):
+        n_seq, L = self._matrix.shape
+        if self._col_stats is not None:
+            self._compress_from_stats(*self._col_stats)
+            return
         A = self.matrix
-        n_seq, L = A.shape
         if not self.compress:
             self._multiplicity = np.ones(self.full_length, dtype=float)
             self.full_to_compressed_sequence_map = np.arange(self.full_length)
@@ -185,6 +205,42 @@ class SequenceData(object):
         self.compressed_matrix = np.ascontiguousarray(C)
         self.pattern_first_position = first_pos
         self._finish()
+
+    def _compress_from_stats(self, lo, hi, all_amb):
+        """Number the patterns from per-column statistics computed on the device (same rules as the
+        host path below; sequence_data.py:386-402)."""
+        L = lo.shape[0]
+        amb = ord(self.ambiguous) if self.ambiguous is not None else 256
+        const = (lo == hi) | all_amb
+        letter = np.where(all_amb, amb, lo).astype(np.uint8)
+        key = np.where(const, letter.astype(np.int64), -1 - np.arange(L))
+        uniq, first_idx, inverse = np.unique(key, return_index=True, return_inverse=True)
+        rank = np.argsort(np.argsort(first_idx))
+        pid = rank[inverse]
+        n_pat = uniq.shape[0]
+        first_pos = np.empty(n_pat, dtype=np.int64)
+        first_pos[rank] = first_idx
+        self._multiplicity = np.bincount(pid, minlength=n_pat).astype(float)
+        self.full_to_compressed_sequence_map = pid
+        self._compressed_length = int(n_pat)
+        self.pattern_first_position = first_pos
+        self.pattern_const_letter = np.where(const[first_pos], letter[first_pos], 0).astype(np.uint8)
+        self._compressed_matrix = None                 # gathered lazily on the host if anybody asks
+        self._finish()
+
+    @property
+    def compressed_matrix(self):
+        if self._compressed_matrix is None:
+            C = self.matrix[:, self.pattern_first_position].copy()
+            cc = self.pattern_const_letter != 0
+            if cc.any():
+                C[:, cc] = self.pattern_const_letter[cc][None, :]
+            self._compressed_matrix = np.ascontiguousarray(C)
+        return self._compressed_matrix
+
+    @compressed_matrix.setter
+    def compressed_matrix(self, value):
+        self._compressed_matrix = value
 
     def _finish(self):
         self.compressed_alignment = _CompressedView(self)

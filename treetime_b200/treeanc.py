@@ -92,7 +92,7 @@ class TreeAnc(DeviceMarginalMixin):
     def __init__(self, tree=None, aln=None, gtr=None, fill_overhangs=True, ref=None, verbose=0, ignore_gaps=True,
                  convert_upper=True, seq_multiplicity=None, log=None, compress=True, seq_len=None,
                  ignore_missing_alns=False, keep_node_order=False, rng_seed=None,
-                 device=0, comm=None, engine_factory=None, **kwargs):
+                 device=0, comm=None, engine_factory=None, device_compress=False, **kwargs):
         if tree is None:
             raise TypeError('TreeAnc requires a tree!')
         self.verbose = verbose
@@ -113,8 +113,15 @@ class TreeAnc(DeviceMarginalMixin):
         self.set_gtr(gtr or 'JC69', **kwargs)
         if ref is not None:
             raise NotImplementedError('sparse (VCF) alignments are read by the reference; pass a dense alignment')
+        device_stats = None
+        if device_compress and compress:
+            # N3: pattern compression on the device -- the engine is created now, the raw alignment is
+            # uploaded once and stays resident; the host only numbers the patterns
+            self._engine = self._engine_factory(self.gtr.n_states, self.device)
+            device_stats = self._engine.alignment_stats
         self.data = SequenceData(aln, compress=compress, convert_upper=convert_upper, fill_overhangs=fill_overhangs,
-                                 ambiguous=self.gtr.ambiguous, sequence_length=seq_len, logger=self.logger)
+                                 ambiguous=self.gtr.ambiguous, sequence_length=seq_len, logger=self.logger,
+                                 device_stats=device_stats)
         if self.gtr.is_site_specific and self.data.compress:
             raise TypeError('TreeAnc: sequence compression and site specific gtr models are incompatible!')
         self._check_alignment_tree_gtr_consistency()
@@ -250,7 +257,7 @@ class TreeAnc(DeviceMarginalMixin):
                     raise MissingDataError('TreeAnc._check_alignment_tree_gtr_consistency: At least 30\\% terminal nodes '
                                            'cannot be assigned a sequence!\nAre you sure the alignment belongs to the tree?')
         # extend_profile (seq_utils.py:126-136): unknown characters are missing data
-        present = np.unique(self.data.matrix)
+        present = np.flatnonzero(np.bincount(self.data._matrix.ravel(), minlength=256))     # characters in the alignment
         for b in present:
             c = chr(int(b))
             if c not in self.gtr.profile_map:
