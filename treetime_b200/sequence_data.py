@@ -81,11 +81,20 @@ class SequenceData(object):
         if not items:
             raise ValueError('SequenceData: empty alignment')
         self.sequence_names = [k for k, _ in items]
-        rows = [_to_bytes(s, convert_upper) for _, s in items]
+        if all(isinstance(s, np.ndarray) and s.dtype == np.uint8 for _, s in items):
+            rows = [s for _, s in items]              # already ASCII bytes: upper-case once, vectorised, below
+            bulk_upper = convert_upper
+        else:
+            rows = [_to_bytes(s, convert_upper) for _, s in items]
+            bulk_upper = False
         L = rows[0].shape[0]
         if any(r.shape[0] != L for r in rows):
             raise ValueError('SequenceData: sequences differ in length')
         self._matrix = np.vstack(rows) if len(rows) > 1 else rows[0][None, :].copy()
+        if bulk_upper:
+            lower = (self._matrix >= 97) & (self._matrix <= 122)
+            if lower.any():
+                self._matrix[lower] -= 32
         # with no ambiguous character the reference assigns None into a 'U1' array, which numpy stores
         # as 'N' (seq_utils.py:196-202): reproduce that
         self._fill_char = (ord(ambiguous) if ambiguous is not None else ord('N')) if fill_overhangs else None
