@@ -42,7 +42,8 @@ enum {
 enum {
   TTB_SUBTREE = 0,  /* node.marginal_subtree_LH   (treeanc.py:877)  */
   TTB_OUTGROUP = 1, /* node.marginal_outgroup_LH  (treeanc.py:895-899) */
-  TTB_PROFILE = 2   /* node.marginal_profile      (treeanc.py:822-824,910-912) */
+  TTB_PROFILE = 2,  /* node.marginal_profile      (treeanc.py:822-824,910-912) */
+  TTB_JOINT_ROOT_LX = 3 /* root.joint_Lx after ttb_joint (treeanc.py:1003-1004); node must be 0 */
 };
 
 /* flags of ttb_marginal */
@@ -124,6 +125,13 @@ int ttb_set_branch_lengths(ttb_handle h, const double* t);
 /* Enqueue one marginal reconstruction: batched expQt, level-ordered postorder, root,
  * level-ordered preorder (treeanc.py:762-812), one CUDA graph launch.  Asynchronous. */
 int ttb_marginal(ttb_handle h, int32_t flags);
+/* N2 -- joint (max-product) ML reconstruction, TreeAnc._ml_anc_joint (treeanc.py:934-1080): log-space
+ * postorder with back-pointers, root state, back-trace; flags: TTB_RECONSTRUCT_TIPS.  Results through
+ * ttb_results (total = tree.sequence_joint_LH, n_diff), ttb_fetch_site_lh (tree.sequence_LH of the joint
+ * path, :1021) and the ttb_fetch_*seq_idx / ttb_fetch_mutations calls.  It overwrites the marginal
+ * messages: marginal accessors need a new ttb_marginal afterwards.  Not available for site-specific models. */
+int ttb_joint(ttb_handle h, int32_t flags);
+
 /* Wait for the last ttb_marginal and return this shard's partial results:
  * total_lh = sum_a LH_a * multiplicity_a (treeanc.py:828), n_diff = number of (node, pattern)
  * state indices that changed w.r.t. the previous reconstruction (treeanc.py:925-926). */

@@ -429,3 +429,65 @@ def mutation_counts(flat, gtr, res):
             T_ia += 0.5 * flat['t'][c] * mut_stack.sum(axis=1) * m
             n_ija += mut_stack * m
     return n_ija, T_ia
+
+
+# ----------------------------------------------------------------------------
+# N2: joint (max-product) ML reconstruction
+# ----------------------------------------------------------------------------
+class JointResult(object):
+    def __init__(self, n_nodes):
+        self.joint_Lx = [None] * n_nodes
+        self.joint_Cx = [None] * n_nodes
+        self.seq_idx = [None] * n_nodes
+        self.sequence_LH = None
+        self.total_LH = None      # tree.sequence_joint_LH
+        self.N_diff = None
+
+
+def joint(flat, gtr, reconstruct_tip_states=False, prev_seq_idx=None):
+    """treeanc.py:934-1080 (_ml_anc_joint), argmax root (no sampling), no masks."""
+    gtr = make_gtr(gtr)
+    parent, cptr, cidx = flat['parent'], flat['child_ptr'], flat['child_idx']
+    n_nodes = parent.shape[0]
+    L = flat['multiplicity'].shape[0]
+    q = gtr.n_states
+    t = flat['t']
+    res = JointResult(n_nodes)
+    # postorder: children before parents = descending preorder ids (:957-1000)
+    for n in range(n_nodes - 1, 0, -1):
+        log_transitions = np.log(np.maximum(TINY_NUMBER, gtr.expQt(t[n])))
+        if flat['tip_row'][n] >= 0:
+            tmp_prof = flat['code_profiles'][flat['tip_codes'][flat['tip_row'][n]]]
+            msg_from_children = np.log(np.maximum(tmp_prof, TINY_NUMBER))
+            msg_from_children[np.isnan(msg_from_children) | np.isinf(msg_from_children)] = -BIG_NUMBER
+        else:
+            msg_from_children = np.sum(np.stack([res.joint_Lx[c] for c in cidx[cptr[n]:cptr[n + 1]]], axis=0), axis=0)
+        Lx = np.zeros((L, q))
+        Cx = np.zeros((L, q), dtype=np.uint16)
+        for char_i in range(q):
+            msg_to_parent = log_transitions[:, char_i].T + msg_from_children
+            Cx[:, char_i] = msg_to_parent.argmax(axis=1)
+            Lx[:, char_i] = msg_to_parent.max(axis=1)
+        res.joint_Lx[n], res.joint_Cx[n] = Lx, Cx
+    # root (:1003-1023)
+    msg_from_children = np.sum(np.stack([res.joint_Lx[c] for c in cidx[cptr[0]:cptr[1]]], axis=0), axis=0)
+    res.joint_Lx[0] = msg_from_children + np.log(gtr.Pi).T
+    normalized_profile = (res.joint_Lx[0].T - res.joint_Lx[0].max(axis=1)).T
+    prof, _ = normalize_profile(np.exp(normalized_profile), return_offset=False)     # prof2seq(normalize=True)
+    idxs = prof.argmax(axis=1)
+    res.sequence_LH = np.choose(idxs, res.joint_Lx[0].T)
+    res.total_LH = (res.sequence_LH * flat['multiplicity']).sum()
+    res.seq_idx[0] = idxs
+    # preorder back-trace (:1029-1048): internal nodes in preorder, then the tips
+    order = [n for n in range(1, n_nodes) if flat['tip_row'][n] < 0]
+    if reconstruct_tip_states:
+        order += [n for n in range(1, n_nodes) if flat['tip_row'][n] >= 0]
+    N_diff = 0
+    for n in order:
+        res.seq_idx[n] = np.choose(res.seq_idx[parent[n]], res.joint_Cx[n].T)
+        if prev_seq_idx is not None and prev_seq_idx[n] is not None:
+            N_diff += int((res.seq_idx[n] != prev_seq_idx[n]).sum())
+        else:
+            N_diff += L
+    res.N_diff = N_diff
+    return res

@@ -212,6 +212,50 @@ def test_sparse_input_and_sparse_result():
                                flat['code_profiles'], flat['multiplicity'])
 
 
+@pytest.mark.parametrize('kind', ['nuc', 'poly', 'aa'])
+def test_joint_reconstruction(kind):
+    """N2: joint (max-product) reconstruction, TreeAnc._ml_anc_joint (treeanc.py:934-1080)."""
+    if kind == 'nuc':
+        tree = synth.random_tree(150, seed=41, mean_bl=0.01); gtr = util.nuc_gtr(); L = 800; amb = 0.02
+    elif kind == 'poly':
+        tree = synth.random_tree(200, seed=42, mean_bl=0.005, polytomy_frac=0.5, zero_frac=0.3); gtr = util.nuc_gtr(); L = 500; amb = 0.0
+    else:
+        tree = synth.random_tree(50, seed=43, mean_bl=0.05); gtr = util.random_gtr('aa_nogap', 5); L = 200; amb = 0.0
+    topo, flat, g = util.make_flat(tree, gtr, L, 41, amb_frac=amb)
+    eng = util.engine_for(flat, g)
+    for tips in (False, True):
+        eng.joint(reconstruct_tips=tips)
+        tot, nd = eng.results()
+        res = O.joint(flat, g, reconstruct_tip_states=tips)
+        assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+        assert np.allclose(eng.site_lh(), res.sequence_LH, rtol=1e-11, atol=1e-9)
+        n_nodes = flat['parent'].shape[0]
+        internal = [n for n in range(n_nodes) if flat['tip_row'][n] < 0]
+        dev = eng.all_seq_idx()
+        ref = np.array([res.seq_idx[n] for n in internal])
+        mism = (dev != ref).mean()
+        assert mism < 2e-3, mism                              # only rounding-level ties may differ ...
+        if mism:                                              # ... and then the assignment is an equally good optimum
+            seqs = [None] * n_nodes
+            for k, n in enumerate(internal):
+                seqs[n] = dev[k].astype(int)
+            assert np.allclose(util.joint_assignment_lh(flat, g, seqs), res.sequence_LH, rtol=1e-10, atol=1e-8)
+        if tips:
+            tipn = [n for n in range(n_nodes) if flat['tip_row'][n] >= 0][:20]
+            dt = eng.seq_idx(tipn)
+            assert np.mean(dt != np.array([res.seq_idx[n] for n in tipn])) < 5e-3
+    # second pass: nothing changes; marginal accessors are blocked until a marginal pass is run again
+    eng.joint(reconstruct_tips=True)
+    assert eng.results()[1] == 0
+    from treetime_b200._lib import TTBError
+    with pytest.raises(TTBError):
+        eng.node_array(3, 2)
+    lx = eng.node_array(0, 3)
+    assert np.allclose(lx, res.joint_Lx[0], rtol=1e-11, atol=1e-9)
+    eng.marginal()
+    assert abs(eng.results()[0] - O.marginal(flat, g).total_LH) <= LH_RTOL * abs(O.marginal(flat, g).total_LH)
+
+
 def test_api_errors():
     from treetime_b200.engine import Engine
     from treetime_b200._lib import TTBError

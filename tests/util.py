@@ -40,3 +40,25 @@ def tie_mask(profile, rel=1e-12):
     """True where the top-2 entries of a profile row are closer than `rel` (argmax ties)."""
     s = np.sort(profile, axis=1)
     return (s[:, -1] - s[:, -2]) <= rel * s[:, -1]
+
+
+def joint_assignment_lh(flat, g, seq_idx):
+    """Per-pattern log-likelihood of a full assignment of internal states under the joint model
+    (tips contribute their best compatible state): an assignment is a joint-ML optimum iff this
+    equals tree.sequence_LH of the joint pass.  seq_idx[n] for internal nodes, None for tips."""
+    import flat_numpy as O
+    G = O.make_gtr(g)
+    parent = flat['parent']
+    L = flat['multiplicity'].shape[0]
+    lh = np.log(G.Pi)[seq_idx[0]].astype(float)
+    ar = np.arange(L)
+    for n in range(1, parent.shape[0]):
+        logP = np.log(np.maximum(O.TINY_NUMBER, G.expQt(flat['t'][n])))
+        sp = seq_idx[parent[n]]
+        if flat['tip_row'][n] >= 0:
+            prof = flat['code_profiles'][flat['tip_codes'][flat['tip_row'][n]]]
+            msg = np.log(np.maximum(prof, O.TINY_NUMBER))                 # (L, q) over child states i
+            lh += (logP[:, sp].T + msg).max(axis=1)
+        else:
+            lh += logP[seq_idx[n], sp]
+    return lh

@@ -94,6 +94,7 @@ SIGNATURES = {
                                    ctypes.c_double, ctypes.c_int32, ctypes.c_int32], ctypes.c_int),
     'ttb_set_branch_lengths': ([_H, _c_dbl_p], ctypes.c_int),
     'ttb_marginal': ([_H, ctypes.c_int32], ctypes.c_int),
+    'ttb_joint': ([_H, ctypes.c_int32], ctypes.c_int),
     'ttb_results': ([_H, _c_dbl_p, ctypes.POINTER(ctypes.c_int64)], ctypes.c_int),
     'ttb_results_device_ptr': ([_H, ctypes.POINTER(ctypes.c_void_p)], ctypes.c_int),
     'ttb_sync': ([_H], ctypes.c_int),

@@ -96,6 +96,11 @@ struct ttb_engine {
   int n_nodes = 0, n_int = 0, n_tips = 0;
   std::vector<int> parent, child_ptr, child_idx, tip_row, int_slot;
   std::vector<int> tip_nodes;
+  // joint back-trace: non-root nodes by depth, internal only / all
+  std::vector<int> jpre_int_nodes, jpre_all_nodes;
+  std::vector<TtbLevelLaunch> jpre_int_levels, jpre_all_levels;
+  DBuf<int> d_jpre_int, d_jpre_all;
+  bool have_joint = false, have_joint_tips = false;
   Sched post, pre_int, pre_all;
   int sched_tiles = -1;  // tiles the group pointers were built for
   int n_fgroups = 0;     // postorder block runs (rows of Fpart)
@@ -122,8 +127,8 @@ struct ttb_engine {
   double ss_tmax = 0.0;
   bool ss_interp_dirty = true;
   // state
-  DBuf<double> d_Fred, d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
-  DBuf<uint8_t> d_idx, d_idxtip, d_bstage, d_mut_state, d_aln, d_colstat, d_lut, d_constl;
+  DBuf<double> d_LP, d_TL, d_Fred, d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
+  DBuf<uint8_t> d_TC, d_Cx, d_idx, d_idxtip, d_bstage, d_mut_state, d_aln, d_colstat, d_lut, d_constl;
   DBuf<long long> d_firstpos;
   DBuf<int> d_seqrow, d_flag;
   long long aln_rows = 0, aln_L = 0;
@@ -195,6 +200,7 @@ struct ttb_engine {
     d.Mtip = d_Mtip.p;
     d.idx = d_idx.p;
     d.idxtip = d_idxtip.p;
+    d.LP = d_LP.p; d.TL = d_TL.p; d.TC = d_TC.p; d.Cx = d_Cx.p;
     d.LH = d_LH.p;
     d.lh_partial = d_lh_partial.p;
     d.nd_slots = d_nd.p;
@@ -336,6 +342,25 @@ int enqueue_pass(ttb_handle h, int flags, int count_diff, cudaStream_t s, int* n
   return 0;
 }
 
+void fill_plan(ttb_handle h, TtbPassPlan& pl, bool tips, int count_diff) {
+  pl.d = h->dev();
+  pl.tiles = h->tiles();
+  pl.lh_only = false;
+  pl.tips = tips;
+  pl.count_diff = count_diff;
+  pl.d_tip_nodes = h->d_tip_nodes.p;
+  pl.d_post_chunks = h->post.d_chunks.p;
+  pl.d_post_group_ptr = h->post.d_group_ptr.p;
+  pl.d_post_node_chunk = h->post.d_node_chunk.p;
+  pl.n_post_leaf_nodes = h->post.level_node_begin.size() > 1 ? h->post.level_node_begin[1] : 0;
+  pl.post_levels = h->post.launches.data();
+  pl.n_post_levels = (int)h->post.launches.size();
+  pl.d_pre_chunks = nullptr; pl.d_pre_group_ptr = nullptr; pl.pre_levels = nullptr; pl.n_pre_levels = 0;
+  pl.d_jpre_nodes = tips ? h->d_jpre_all.p : h->d_jpre_int.p;
+  pl.jpre_levels = tips ? h->jpre_all_levels.data() : h->jpre_int_levels.data();
+  pl.n_jpre_levels = (int)(tips ? h->jpre_all_levels.size() : h->jpre_int_levels.size());
+}
+
 int ensure_state(ttb_handle h, bool tips) {
   const size_t q = h->q, ld = h->ld;
   int rc;
@@ -388,6 +413,12 @@ int ensure_preorder_state(ttb_handle h, bool tips) {
   return 0;
 }
 
+// reconstructed states exist after a marginal OR a joint pass
+int check_states(ttb_handle h) {
+  if (!h->have_pass && !h->have_joint) return fail(TTB_EINVAL, "no reconstruction has been run yet (call ttb_marginal or ttb_joint first)");
+  return 0;
+}
+
 int check_ready(ttb_handle h, bool need_pass) {
   if (!h->n_nodes) return fail(TTB_EINVAL, "ttb_set_tree has not been called");
   if (!h->Lp) return fail(TTB_EINVAL, "ttb_set_patterns has not been called");
@@ -437,7 +468,7 @@ int ttb_destroy(ttb_handle h) {
   DBuf<int>* ib[] = {&h->d_parent, &h->d_child_ptr, &h->d_child_idx, &h->d_tip_row, &h->d_int_slot, &h->d_tip_nodes,
                      &h->d_enodes, &h->d_ekinds, &h->post.d_group_ptr, &h->pre_int.d_group_ptr, &h->pre_all.d_group_ptr, &h->post.d_node_chunk};
   for (auto* b : ib) b->release();
-  DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_ss_eig, &h->d_ss_mu, &h->d_ss_V, &h->d_ss_Vinv, &h->d_ss_Pi,
+  DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_LP, &h->d_TL, &h->d_ss_eig, &h->d_ss_mu, &h->d_ss_V, &h->d_ss_Vinv, &h->d_ss_Pi,
                         &h->d_ss_w, &h->d_ss_grid, &h->d_ss_E, &h->d_TU, &h->d_P, &h->d_S,
                         &h->d_F, &h->d_Fred, &h->d_M, &h->d_Mtip, &h->d_LH, &h->d_lh_partial, &h->d_results, &h->d_stage,
                         &h->d_partial, &h->d_ets, &h->d_eout};
@@ -448,6 +479,7 @@ int ttb_destroy(ttb_handle h) {
   h->d_idx.release();
   h->d_idxtip.release();
   h->d_bstage.release();
+  h->d_TC.release(); h->d_Cx.release(); h->d_jpre_int.release(); h->d_jpre_all.release();
   h->d_mut_state.release(); h->d_mut_node.release(); h->d_mut_pos.release(); h->d_ent_row.release(); h->d_ent_pos.release();
   h->d_mut_count.release();
   h->d_aln.release(); h->d_colstat.release(); h->d_lut.release(); h->d_constl.release(); h->d_firstpos.release();
@@ -510,6 +542,24 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   h->tip_nodes.assign(n_tips, 0);
   for (int n = 0; n < n_nodes; ++n)
     if (tip_row[n] >= 0) h->tip_nodes[tip_row[n]] = n;
+  {  // joint back-trace lists: non-root nodes grouped by depth
+    int maxd = 0;
+    for (int n = 1; n < n_nodes; ++n) maxd = std::max(maxd, depth[n]);
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<int>& nodes = pass ? h->jpre_all_nodes : h->jpre_int_nodes;
+      std::vector<TtbLevelLaunch>& levels = pass ? h->jpre_all_levels : h->jpre_int_levels;
+      nodes.clear();
+      levels.clear();
+      std::vector<std::vector<int>> by(maxd + 1);
+      for (int n = 1; n < n_nodes; ++n)
+        if (pass || slot[n] >= 0) by[depth[n]].push_back(n);
+      for (int dd = 1; dd <= maxd; ++dd)
+        if (!by[dd].empty()) {
+          levels.push_back({(int)nodes.size(), (int)by[dd].size()});
+          nodes.insert(nodes.end(), by[dd].begin(), by[dd].end());
+        }
+    }
+  }
   build_sched(h, height, is_int, true, [](int) { return true; }, h->post);
   build_sched(h, depth, has_int_child, false, [&](int c) { return slot[c] >= 0; }, h->pre_int);
   build_sched(h, depth, is_int, false, [](int) { return true; }, h->pre_all);
@@ -522,6 +572,8 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   if ((rc = upload(h->d_tip_row, h->tip_row.data(), h->tip_row.size(), s))) return rc;
   if ((rc = upload(h->d_int_slot, h->int_slot.data(), h->int_slot.size(), s))) return rc;
   if ((rc = upload(h->d_tip_nodes, h->tip_nodes.data(), h->tip_nodes.size(), s))) return rc;
+  if ((rc = upload(h->d_jpre_int, h->jpre_int_nodes.data(), h->jpre_int_nodes.size(), s))) return rc;
+  if ((rc = upload(h->d_jpre_all, h->jpre_all_nodes.data(), h->jpre_all_nodes.size(), s))) return rc;
   for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all})
     if ((rc = upload(sc->d_chunks, sc->chunks.data(), sc->chunks.size(), s))) return rc;
   if ((rc = upload(h->post.d_node_chunk, h->post.node_chunk.data(), h->post.node_chunk.size(), s))) return rc;
@@ -532,6 +584,8 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   h->d_t.release();
   h->have_t = false;
   h->have_pass = h->have_tip_pass = false;
+  h->have_joint = h->have_joint_tips = false;
+  h->d_LP.release(); h->d_TL.release(); h->d_TC.release(); h->d_Cx.release();
   h->first_full = true;
   h->drop_graphs();
   return 0;
@@ -846,6 +900,59 @@ int ttb_marginal(ttb_handle h, int32_t flags) {
     h->have_pass = true;
     h->have_tip_pass = tips;
   }
+  h->have_joint = h->have_joint_tips = false;
+  return 0;
+}
+
+int ttb_joint(ttb_handle h, int32_t flags) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, false)) return rc;
+  if (h->site_specific) return fail(TTB_EUNSUPPORTED, "ttb_joint: joint reconstruction is not implemented for site-specific models");
+  const bool tips = flags & TTB_RECONSTRUCT_TIPS;
+  const bool had_P = h->d_P.p != nullptr;
+  if (int rc = ensure_state(h, tips)) return rc;
+  if (!had_P) h->drop_graphs();
+  const size_t q = h->q;
+  const size_t pq = (q * q + 1) / 2 * 2, tus = ((size_t)h->n_codes * q + 1) / 2 * 2;
+  int rc;
+  const bool fresh = !h->d_Cx.p || !h->d_idx.p || (tips && !h->d_idxtip.p);
+  if ((rc = h->d_LP.alloc((size_t)h->n_nodes * pq))) return rc;
+  if ((rc = h->d_TL.alloc((size_t)h->n_tips * tus))) return rc;
+  if ((rc = h->d_TC.alloc((size_t)h->n_tips * tus))) return rc;
+  if ((rc = h->d_Cx.alloc((size_t)h->n_int * h->tiles() * q * TTB_TILE))) return rc;
+  if (!h->d_idx.p) {
+    if ((rc = h->d_idx.alloc((size_t)h->n_int * h->ld))) return rc;
+    CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), h->stream));
+  }
+  if (tips && !h->d_idxtip.p) {
+    if ((rc = h->d_idxtip.alloc((size_t)h->n_tips * h->ld))) return rc;
+    CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), h->stream));
+  }
+  if (fresh) h->drop_graphs();
+  const int key = 8 | (tips ? TTB_RECONSTRUCT_TIPS : 0);
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    TtbPassPlan pl;
+    fill_plan(h, pl, tips, 1);
+    cudaGraph_t graph;
+    CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+    const int nk = ttb_qops(h->q)->enqueue_joint(pl, h->own_stream);
+    cudaError_t ce = cudaStreamEndCapture(h->own_stream, &graph);
+    if (ce != cudaSuccess) return fail(TTB_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    if (nk <= 0) return fail(TTB_EUNSUPPORTED, "ttb_joint: not available for this model");
+    cudaGraphExec_t exec;
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    h->graphs[key] = exec;
+    h->graph_kernels[key] = nk;
+    it = h->graphs.find(key);
+  }
+  CK(cudaGraphLaunch(it->second, h->stream));
+  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  h->launches += h->graph_kernels[key];
+  h->have_pass = h->have_tip_pass = false;   // the marginal messages were overwritten
+  h->have_joint = true;
+  h->have_joint_tips = tips;
   return 0;
 }
 
@@ -881,9 +988,13 @@ int ttb_fetch_site_lh(ttb_handle h, double* out) {
 
 int ttb_fetch_node(ttb_handle h, int32_t node, int32_t which, double* out) {
   if (int rc = use_device(h)) return rc;
-  if (node < 0 || node >= h->n_nodes || !out || which < 0 || which > 2) return fail(TTB_EINVAL, "ttb_fetch_node: bad arguments");
+  if (node < 0 || node >= h->n_nodes || !out || which < 0 || which > 3) return fail(TTB_EINVAL, "ttb_fetch_node: bad arguments");
   const bool tip = h->tip_row[node] >= 0;
-  if (which == TTB_SUBTREE) {
+  if (which == TTB_JOINT_ROOT_LX) {
+    if (node != 0 || !h->have_joint) return fail(TTB_EINVAL, "ttb_fetch_node: TTB_JOINT_ROOT_LX needs node 0 after ttb_joint");
+  } else if (h->have_joint && !h->have_pass) {
+    return fail(TTB_EINVAL, "ttb_fetch_node: the marginal messages were overwritten by ttb_joint; run ttb_marginal again");
+  } else if (which == TTB_SUBTREE) {
     if (!tip && !h->d_S.p) return fail(TTB_EINVAL, "ttb_fetch_node: run ttb_marginal first");
   } else {
     if (int rc = check_ready(h, true)) return rc;
@@ -901,14 +1012,14 @@ int ttb_fetch_node(ttb_handle h, int32_t node, int32_t which, double* out) {
 
 int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* out) {
   if (int rc = use_device(h)) return rc;
-  if (int rc = check_ready(h, true)) return rc;
+  if (int rc = check_states(h)) return rc;
   if (n < 0 || (n && (!nodes || !out))) return fail(TTB_EINVAL, "ttb_fetch_seq_idx: bad arguments");
   for (int k = 0; k < n; ++k) {
     const int node = nodes[k];
     if (node < 0 || node >= h->n_nodes) return fail(TTB_EINVAL, "ttb_fetch_seq_idx: bad node id");
     const uint8_t* src;
     if (h->tip_row[node] >= 0) {
-      if (!h->have_tip_pass) return fail(TTB_EINVAL, "ttb_fetch_seq_idx: tip states exist only after TTB_RECONSTRUCT_TIPS");
+      if (!h->have_tip_pass && !h->have_joint_tips) return fail(TTB_EINVAL, "ttb_fetch_seq_idx: tip states exist only after TTB_RECONSTRUCT_TIPS");
       src = h->d_idxtip.p + (size_t)h->tip_row[node] * h->ld;
     } else {
       src = h->d_idx.p + (size_t)h->int_slot[node] * h->ld;
@@ -922,7 +1033,7 @@ int ttb_fetch_seq_idx(ttb_handle h, int32_t n, const int32_t* nodes, uint8_t* ou
 int ttb_fetch_mutations(ttb_handle h, uint8_t* root_idx, int32_t max_n, int32_t* node, int32_t* pos, uint8_t* state,
                         int64_t* n) {
   if (int rc = use_device(h)) return rc;
-  if (int rc = check_ready(h, true)) return rc;
+  if (int rc = check_states(h)) return rc;
   if (!root_idx || !n || max_n < 0 || (max_n && (!node || !pos || !state))) return fail(TTB_EINVAL, "ttb_fetch_mutations: bad arguments");
   int rc;
   if ((rc = h->d_mut_node.alloc(std::max(h->d_mut_node.n, (size_t)std::max(max_n, 1))))) return rc;
@@ -960,7 +1071,7 @@ int ttb_enqueue_fetch_site_lh(ttb_handle h, double* out) {
 
 int ttb_enqueue_fetch_all_seq_idx(ttb_handle h, uint8_t* out) {
   if (int rc = use_device(h)) return rc;
-  if (int rc = check_ready(h, true)) return rc;
+  if (int rc = check_states(h)) return rc;
   if (!out) return fail(TTB_EINVAL, "ttb_enqueue_fetch_all_seq_idx: null output");
   if (int rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)h->Lp)) return rc;
   pitch_bytes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_idx.p, h->ld, h->d_bstage.p, h->Lp, h->Lp, h->n_int, 0);
@@ -972,7 +1083,7 @@ int ttb_enqueue_fetch_all_seq_idx(ttb_handle h, uint8_t* out) {
 
 int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out) {
   if (int rc = use_device(h)) return rc;
-  if (int rc = check_ready(h, true)) return rc;
+  if (int rc = check_states(h)) return rc;
   if (!out) return fail(TTB_EINVAL, "ttb_fetch_all_seq_idx: null output");
   if (int rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)h->Lp)) return rc;
   pitch_bytes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_idx.p, h->ld, h->d_bstage.p, h->Lp, h->Lp, h->n_int, 0);

@@ -94,6 +94,13 @@ struct TtbDev {
   double* Mtip;  // [n_tips][tiles][q][128] marginal_profile of tips (reconstruct_tip_states) or null
   uint8_t* idx;     // [n_int][ld]  argmax state
   uint8_t* idxtip;  // [n_tips][ld] or null
+  // joint (max-product) reconstruction, treeanc.py:934-1080 (N2): reuses S for the summed child
+  // messages; LP = log(max(1e-12, exp(Qt))), TL / TC = per tip-branch tables of the leaf message and
+  // its argmax, Cx = best child state for every parent state (the back-pointers)
+  double* LP;       // [n_nodes][pq]
+  double* TL;       // [n_tips][tu_stride]
+  uint8_t* TC;      // [n_tips][tu_stride]
+  uint8_t* Cx;      // [n_int][tiles][q][128]
   double* LH;       // [ld] tree.sequence_LH
   double* lh_partial;             // [tiles]
   unsigned long long* nd_slots;   // [1024]
@@ -291,6 +298,101 @@ struct SiteModel {
   }
 };
 
+// ---------------------------------------------------------------------------------------
+// N2: joint ML reconstruction.  Reference: TreeAnc._ml_anc_joint, treeanc.py:934-1080.
+//   log_transitions = log(max(1e-12, expQt(t)))                         (:967)
+//   leaf message    = log(max(profile, 1e-12))                          (:968-976)
+//   Lx_c[j] = max_i (log_transitions_c[i][j] + msg_c[i]),  Cx_c[j] = argmax_i   (:986-1000)
+//   msg_n[i] = sum_c Lx_c[i]                                            (:978)
+// ---------------------------------------------------------------------------------------
+template <int Q>
+__global__ void joint_tables_kernel(TtbDev p, const int* __restrict__ tip_nodes) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nlp = (long long)p.n_nodes * Q * Q;
+  if (gid < nlp) {
+    const int n = (int)(gid / (Q * Q)), k = (int)(gid % (Q * Q));
+    p.LP[(size_t)n * p.pq + k] = log(fmax(TTB_TINY, p.P[(size_t)n * p.pq + k]));
+  }
+  const int per = p.n_codes * Q;
+  if (gid < (long long)p.n_tips * per) {
+    const int row = (int)(gid / per), r = (int)(gid % per);
+    const int code = r / Q, j = r % Q;
+    const double* P = p.P + (size_t)tip_nodes[row] * p.pq;
+    double best = -1e300;
+    int arg = 0;
+    for (int i = 0; i < Q; ++i) {
+      const double v = log(fmax(TTB_TINY, P[i * Q + j])) + log(fmax(p.code_prof[code * Q + i], TTB_TINY));
+      if (v > best) { best = v; arg = i; }
+    }
+    p.TL[(size_t)row * p.tu_stride + r] = best;
+    p.TC[(size_t)row * p.tu_stride + r] = (uint8_t)arg;
+  }
+}
+
+// Root of the joint pass (treeanc.py:1003-1023): Lx_r = msg_r + log Pi; state = first argmax of
+// exp(Lx_r - max) (what prof2seq sees); sequence_LH = Lx_r[state].
+template <int Q>
+__global__ void __launch_bounds__(TTB_BLOCK) joint_root_kernel(TtbDev p) {
+  __shared__ double sred[TTB_BLOCK / 32];
+  const long long a = (long long)blockIdx.x * TTB_BLOCK + threadIdx.x;
+  double contrib = 0.0;
+  if (a < p.Lp) {
+    const int slot = p.int_slot[0];
+    double* __restrict__ s = p.S + msg_off<Q>(p, slot, a);
+    double R[Q];
+    double mx = -1e300;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      R[i] = s[i * TTB_TILE] + log(p.Pi[i]);
+      mx = fmax(mx, R[i]);
+    }
+    int best = 0;
+    double bv = -1.0;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      s[i * TTB_TILE] = R[i];   // root.joint_Lx (fetchable for root sampling on the host)
+      const double e = exp(R[i] - mx);
+      if (e > bv) { bv = e; best = i; }
+    }
+    p.idx[(size_t)slot * p.ld + a] = (uint8_t)best;
+    const double lh = R[best];
+    p.LH[a] = lh;
+    contrib = lh * p.mult[a];
+  }
+  const double bs = block_sum<TTB_BLOCK>(contrib, sred);
+  if (threadIdx.x == 0) p.lh_partial[blockIdx.x] = bs;
+}
+
+// Backtrace of one depth level (treeanc.py:1034-1048): state_c = Cx_c[state_parent]; tips read the
+// per-branch table instead.  One thread per (node, pattern).
+template <int Q>
+__global__ void __launch_bounds__(TTB_BLOCK) joint_pre_level_kernel(TtbDev p, const int* __restrict__ nodes, int tiles, int count_diff) {
+  const int n = nodes[blockIdx.x / tiles];
+  const long long a = (long long)(blockIdx.x % tiles) * TTB_TILE + threadIdx.x;
+  unsigned int nd = 0;
+  if (a < p.Lp) {
+    const int ps = p.idx[(size_t)p.int_slot[p.parent[n]] * p.ld + a];
+    const int row = p.tip_row[n];
+    int st;
+    uint8_t* ip;
+    if (row >= 0) {
+      const int code = p.codes[(size_t)row * p.ld + a];
+      st = p.TC[(size_t)row * p.tu_stride + code * Q + ps];
+      ip = p.idxtip + (size_t)row * p.ld + a;
+    } else {
+      const int slot = p.int_slot[n];
+      st = p.Cx[((size_t)slot * p.tiles + (size_t)(a / TTB_TILE)) * (size_t)(Q * TTB_TILE) + (size_t)ps * TTB_TILE + (size_t)(a % TTB_TILE)];
+      ip = p.idx + (size_t)slot * p.ld + a;
+    }
+    if (count_diff) nd = (*ip != (uint8_t)st);
+    *ip = (uint8_t)st;
+  }
+  if (count_diff) {
+    nd = __reduce_add_sync(0xffffffffu, nd);
+    if ((threadIdx.x & 31) == 0 && nd) atomicAdd(p.nd_slots + (blockIdx.x & 1023), (unsigned long long)nd);
+  }
+}
+
 // E[g][k][a] = exp(t_g * mu_a * lambda_k(a)): the eigen-factor of gtr_site_specific._expQt (:363) on the
 // interpolation grid (:336-344).  One thread per (g, k, a).
 static __global__ void ss_grid_table_kernel(TtbDev p, double* __restrict__ E) {
@@ -400,7 +502,7 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // Block = (run of nodes of the level given by group_ptr, one 128-pattern tile).
 // Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool SS>
+template <int Q, bool SS, bool JOINT = false>
 __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles, int fbase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -442,13 +544,13 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
         if (r == 0)   // the child's q rows of this tile are one contiguous block
           tma_load_1d(pipe.rows(s) + (b * RPC) * TTB_TILE, p.S + msg_off<Q>(p, src, a0), Q * TTB_TILE * 8, bar);
         else if (r == 1 && !SS)
-          tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
+          tma_load_1d(pipe.P(s) + b * p.pq, (JOINT ? p.LP : p.P) + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
       } else {
         const int row = -1 - src;
         if (r == 0)
           tma_load_1d(pipe.codes(s) + b * TTB_TILE, p.codes + (size_t)row * p.ld + a0, cols, bar);
         else if (r == 1 && !SS)
-          tma_load_1d(pipe.TU(s) + b * p.tu_stride, p.TU + (size_t)row * p.tu_stride, p.tu_stride * 8, bar);
+          tma_load_1d(pipe.TU(s) + b * p.tu_stride, (JOINT ? p.TL : p.TU) + (size_t)row * p.tu_stride, p.tu_stride * 8, bar);
       }
     }
   };
@@ -468,7 +570,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
     const Chunk c = load_chunk_smem(pipe.desc(s));
     if (c.flags & 1) {
 #pragma unroll
-      for (int j = 0; j < Q; ++j) X[j] = 1.0;
+      for (int j = 0; j < Q; ++j) X[j] = JOINT ? 0.0 : 1.0;
       scale = 0;
       seen = 0;
     }
@@ -501,12 +603,34 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
           double sc[Q];
 #pragma unroll
           for (int i = 0; i < Q; ++i) sc[i] = rows[i * TTB_TILE];
+          if constexpr (JOINT) {
+            // max-plus "matvec" with back-pointers: Lx_c[j] = max_i (logP[i][j] + msg_c[i]), first maximum
+            uint8_t* cx = p.Cx + ((size_t)c.src(b) * p.tiles + (size_t)tile) * (size_t)(Q * TTB_TILE) + tid;
 #pragma unroll
-          for (int j = 0; j < Q; ++j) U[j] = sc[0] * Pc[j];
+            for (int j = 0; j < Q; ++j) {
+              double best = Pc[j] + sc[0];
+              int arg = 0;
 #pragma unroll
-          for (int i = 1; i < Q; ++i)
+              for (int i = 1; i < Q; ++i) {
+                const double v = Pc[i * Q + j] + sc[i];
+                if (v > best) { best = v; arg = i; }
+              }
+              U[j] = best;
+              cx[j * TTB_TILE] = (uint8_t)arg;
+            }
+          } else {
 #pragma unroll
-            for (int j = 0; j < Q; ++j) U[j] = fma(sc[i], Pc[i * Q + j], U[j]);
+            for (int j = 0; j < Q; ++j) U[j] = sc[0] * Pc[j];
+#pragma unroll
+            for (int i = 1; i < Q; ++i)
+#pragma unroll
+              for (int j = 0; j < Q; ++j) U[j] = fma(sc[i], Pc[i * Q + j], U[j]);
+          }
+        }
+        if constexpr (JOINT) {
+#pragma unroll
+          for (int j = 0; j < Q; ++j) X[j] += U[j];
+          continue;
         }
 #pragma unroll
         for (int j = 0; j < Q; ++j) X[j] *= U[j];
@@ -523,7 +647,13 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
       }
     }
     pipe.consumer_release(u, lane);  // all smem reads of this stage are done
-    if (act && (c.flags & 2)) {
+    if (JOINT) {
+      if (act && (c.flags & 2)) {
+        double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
+#pragma unroll
+        for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j];
+      }
+    } else if (act && (c.flags & 2)) {
       double Z = X[0];
 #pragma unroll
       for (int j = 1; j < Q; ++j) Z += X[j];
@@ -534,13 +664,13 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
       Facc += log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
     }
   }
-  if (act) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc;
+  if (!JOINT && act) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc;
 }
 
 // Postorder level 1: every child is a tip, so there is nothing to stream in but one code byte
 // per (tip, pattern); the kernel is a pure write stream of q doubles per (node, pattern).
 // Block = (run of nodes, tile); one thread per pattern, tip tables read through L1.
-template <int Q>
+template <int Q, bool JOINT = false>
 __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                                    const int* __restrict__ group_ptr, int tiles, int fbase) {
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
@@ -554,7 +684,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
     const Chunk c = load_chunk_global(chunks + k);
     if (c.flags & 1) {
 #pragma unroll
-      for (int j = 0; j < Q; ++j) X[j] = 1.0;
+      for (int j = 0; j < Q; ++j) X[j] = JOINT ? 0.0 : 1.0;
       scale = 0;
       seen = 0;
     }
@@ -562,7 +692,12 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
     for (int b = 0; b < nch; ++b) {
       const int row = -1 - c.src(b);
       const int code = __ldg(p.codes + (size_t)row * p.ld + a);
-      const double* tu = p.TU + (size_t)row * p.tu_stride + code * Q;
+      const double* tu = (JOINT ? p.TL : p.TU) + (size_t)row * p.tu_stride + code * Q;
+      if constexpr (JOINT) {
+#pragma unroll
+        for (int j = 0; j < Q; ++j) X[j] += __ldg(tu + j);
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < Q; ++j) X[j] *= __ldg(tu + j);
       if (++seen > 2) {
@@ -576,7 +711,13 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
         }
       }
     }
-    if (c.flags & 2) {
+    if (JOINT) {
+      if (c.flags & 2) {
+        double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
+#pragma unroll
+        for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j];
+      }
+    } else if (c.flags & 2) {
       double Z = X[0];
 #pragma unroll
       for (int j = 1; j < Q; ++j) Z += X[j];
@@ -587,7 +728,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
       Facc += log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
     }
   }
-  p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc;
+  if (!JOINT) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc;
 }
 
 // First stage of the log-prefactor reduction: Fred[c][a] = sum of Fpart[g][a] over g = c mod TTB_FLANES
@@ -1124,7 +1265,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) fetch_node_kernel(TtbDev p, int nod
   const long long a = (long long)blockIdx.x * TTB_BLOCK + threadIdx.x;
   if (a >= p.Lp) return;
   double x[Q], y[Q];
-  if (which == 0) {
+  if (which == 0 || which == 3) {   // 3 = joint_Lx of the root (the joint pass keeps it in S)
     node_subtree<Q>(p, node, a, x);
   } else if (which == 1) {
     if (node == 0) {

@@ -1,6 +1,7 @@
 // ttb_q.cu -- instantiates the kernels for ONE alphabet size (-DTTB_Q=<q>) and exports
 // their launchers as a TtbQOps table.
 #include "ttb_qops.h"
+#include <algorithm>
 
 #ifndef TTB_Q
 #error "compile with -DTTB_Q=<n_states>"
@@ -18,6 +19,7 @@ template <bool SS>
 int prepare_t(const TtbDev& d) {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(post_level_kernel<Q, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, SS))) != cudaSuccess) return (int)e;
+  if (!SS && (e = cudaFuncSetAttribute(post_level_kernel<Q, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, false))) != cudaSuccess) return (int)e;
   if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
   if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
   return 0;
@@ -98,6 +100,44 @@ int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   return enqueue_pass_t<false>(pl, s, ev, pk);
 }
 
+int enqueue_joint_q(const TtbPassPlan& pl, cudaStream_t s) {
+  const TtbDev& d = pl.d;
+  if (d.site_specific) return 0;
+  const int tiles = pl.tiles;
+  int nk = 0;
+  const int nthr = d.n_nodes * Q;
+  expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
+  const long long nt = std::max((long long)d.n_nodes * Q * Q, (long long)d.n_tips * d.n_codes * Q);
+  joint_tables_kernel<Q><<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(d, pl.d_tip_nodes);
+  nk += 2;
+  const size_t psm = post_smem(d, false);
+  int l0 = 0;
+  if (pl.n_post_leaf_nodes) {
+    const TtbLevelLaunch& L = pl.post_levels[0];
+    post_leaf_level_kernel<Q, true><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_post_chunks,
+                                                                                                pl.d_post_group_ptr + L.group_off, tiles, 0);
+    ++nk;
+    l0 = 1;
+  }
+  for (int l = l0; l < pl.n_post_levels; ++l) {
+    const TtbLevelLaunch& L = pl.post_levels[l];
+    post_level_kernel<Q, false, true><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, psm, s>>>(d, pl.d_post_chunks,
+                                                                                                      pl.d_post_group_ptr + L.group_off, tiles, 0);
+    ++nk;
+  }
+  joint_root_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d);
+  zero_slots_kernel<<<4, 256, 0, s>>>(d);
+  nk += 2;
+  for (int l = 0; l < pl.n_jpre_levels; ++l) {
+    const TtbLevelLaunch& L = pl.jpre_levels[l];
+    joint_pre_level_kernel<Q><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_jpre_nodes + L.group_off, tiles,
+                                                                                            pl.count_diff);
+    ++nk;
+  }
+  finish_kernel<<<1, 256, 0, s>>>(d, tiles);
+  return nk + 1;
+}
+
 void fetch_node_q(const TtbDev& d, int tiles, int node, int which, double* out, cudaStream_t s) {
   if constexpr (HAS_SS) {
     if (d.site_specific) {
@@ -130,4 +170,4 @@ void counts_q(const TtbDev& d, int tiles, int chunks, int chunk, double* partial
 
 #define TTB_CAT2(a, b) a##b
 #define TTB_CAT(a, b) TTB_CAT2(a, b)
-extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {prepare_q, enqueue_pass_q, fetch_node_q, branch_eval_q, counts_q};
+extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {prepare_q, enqueue_pass_q, enqueue_joint_q, fetch_node_q, branch_eval_q, counts_q};

@@ -27,6 +27,10 @@ struct TtbPassPlan {
   int n_pre_levels;
   bool lh_only, tips;
   int count_diff;
+  // joint reconstruction: nodes to back-trace, grouped by depth (matching `tips`)
+  const int* d_jpre_nodes;
+  const TtbLevelLaunch* jpre_levels;   // group_off = first node, n_groups = node count
+  int n_jpre_levels;
 };
 
 struct TtbQOps {
@@ -34,6 +38,8 @@ struct TtbQOps {
   int (*prepare)(const TtbDev& d);
   // enqueue every kernel of one pass; optional events ev[6] bracket the phases; returns #kernels
   int (*enqueue_pass)(const TtbPassPlan& plan, cudaStream_t s, cudaEvent_t* ev, int* phase_kernels);
+  // joint (max-product) reconstruction, same schedule; returns #kernels, 0 if unsupported for this model
+  int (*enqueue_joint)(const TtbPassPlan& plan, cudaStream_t s);
   void (*fetch_node)(const TtbDev& d, int tiles, int node, int which, double* out, cudaStream_t s);
   void (*branch_eval)(const TtbDev& d, int n_eval, int nb, const int* nodes, const int* kinds, const double* ts,
                       int mode, double* partial, double* out, cudaStream_t s);

@@ -3,7 +3,7 @@ import ctypes
 import numpy as np
 from . import _lib
 
-SUBTREE, OUTGROUP, PROFILE = 0, 1, 2
+SUBTREE, OUTGROUP, PROFILE, JOINT_ROOT_LX = 0, 1, 2, 3
 RECONSTRUCT_TIPS, LH_ONLY = 1, 2
 BRANCH, BRANCH_ROOT = 0, 1
 
@@ -139,6 +139,10 @@ class Engine(object):
     def marginal(self, reconstruct_tips=False, lh_only=False):
         flags = (RECONSTRUCT_TIPS if reconstruct_tips else 0) | (LH_ONLY if lh_only else 0)
         _lib.check(self.lib.ttb_marginal(self.h, flags))
+
+    def joint(self, reconstruct_tips=False):
+        """Joint (max-product) reconstruction; results() returns (sequence_joint_LH, N_diff)."""
+        _lib.check(self.lib.ttb_joint(self.h, RECONSTRUCT_TIPS if reconstruct_tips else 0))
 
     def results(self):
         tot = ctypes.c_double()
