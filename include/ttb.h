@@ -49,7 +49,8 @@ enum {
 /* flags of ttb_marginal */
 enum {
   TTB_RECONSTRUCT_TIPS = 1, /* reconstruct_tip_states=True (treeanc.py:900-903) */
-  TTB_LH_ONLY = 2           /* postorder + root only: the cost function of optimize_gtr_rate (treeanc.py:1685-1689) */
+  TTB_LH_ONLY = 2,          /* postorder + root only: the cost function of optimize_gtr_rate (treeanc.py:1685-1689) */
+  TTB_JOINT_NO_TRACE = 4    /* ttb_joint: stop after the root (the caller samples the root, then ttb_joint_retrace) */
 };
 
 /* kinds of branch evaluated by ttb_branch_objective / ttb_branch_hamming */
@@ -131,11 +132,16 @@ int ttb_marginal(ttb_handle h, int32_t flags);
  * path, :1021) and the ttb_fetch_*seq_idx / ttb_fetch_mutations calls.  It overwrites the marginal
  * messages: marginal accessors need a new ttb_marginal afterwards.  Not available for site-specific models. */
 int ttb_joint(ttb_handle h, int32_t flags);
+/* Back-trace from caller-chosen root states root_idx[n_patterns] (sample_from_profile='root',
+ * treeanc.py:1008-1023); needs a preceding ttb_joint (usually with TTB_JOINT_NO_TRACE). */
+int ttb_joint_retrace(ttb_handle h, const uint8_t* root_idx, int32_t flags);
 
 /* Wait for the last ttb_marginal and return this shard's partial results:
  * total_lh = sum_a LH_a * multiplicity_a (treeanc.py:828), n_diff = number of (node, pattern)
  * state indices that changed w.r.t. the previous reconstruction (treeanc.py:925-926). */
 int ttb_results(ttb_handle h, double* total_lh, int64_t* n_diff);
+/* The part of n_diff that belongs to terminal nodes (TTB_RECONSTRUCT_TIPS passes). */
+int ttb_results_tips(ttb_handle h, int64_t* n_diff_tips);
 /* Device address of the double[2] {total_lh, n_diff} written by the last pass (for NCCL allreduce). */
 int ttb_results_device_ptr(ttb_handle h, void** dptr);
 int ttb_sync(ttb_handle h);

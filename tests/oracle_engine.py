@@ -15,6 +15,7 @@ class OracleEngine(object):
         self.g = None
         self.res = None
         self.prev_idx = None
+        self._prev_before = None
         self.launches = 0
 
     def set_stream(self, s):
@@ -72,12 +73,57 @@ class OracleEngine(object):
             return
         self.t_pass = self.flat['t'].copy()
         self.g_pass = dict(self.g)
+        self._prev_before = list(self.prev_idx) if self.prev_idx is not None else None
         r = O.marginal(self.flat, self.g, reconstruct_tip_states=reconstruct_tips, prev_seq_idx=self.prev_idx)
         if self.prev_idx is None:
             pass
         self.res = r
         self.prev_idx = list(r.seq_idx)
         self._tot, self._nd, self._site = r.total_LH, r.N_diff, r.sequence_LH
+
+    def joint(self, reconstruct_tips=False, trace=True):
+        self.launches += 1
+        self._prev_before = list(self.prev_idx) if self.prev_idx is not None else None
+        r = O.joint(self.flat, self.g, reconstruct_tip_states=reconstruct_tips, prev_seq_idx=self.prev_idx)
+        self.jres = r
+        self.res = None
+        self._tot, self._site = r.total_LH, r.sequence_LH
+        if trace:
+            self._nd = r.N_diff
+            self.prev_idx = list(r.seq_idx)
+            self.seqs = r.seq_idx
+
+    def joint_retrace(self, root_idx, reconstruct_tips=False):
+        r = self.jres
+        n_nodes = self.n_nodes
+        seq = [None] * n_nodes
+        seq[0] = np.asarray(root_idx).astype(int)
+        order = [n for n in range(1, n_nodes) if self.tip_row[n] < 0]
+        if reconstruct_tips:
+            order += [n for n in range(1, n_nodes) if self.tip_row[n] >= 0]
+        nd = 0
+        L = self.n_patterns
+        for n in order:
+            seq[n] = np.choose(seq[self.flat['parent'][n]], r.joint_Cx[n].T)
+            if self.prev_idx is not None and self.prev_idx[n] is not None:
+                nd += int((seq[n] != self.prev_idx[n]).sum())
+            else:
+                nd += L
+        self._site = np.choose(seq[0], r.joint_Lx[0].T)
+        self._tot = (self._site * self.flat['multiplicity']).sum()
+        self._nd = nd
+        self.prev_idx = list(seq)
+        self.seqs = seq
+
+    def results_tips(self):
+        # share of the last N_diff that came from tips (recomputed: the oracle returns only the total)
+        src = self.res.seq_idx if self.res is not None else self.seqs
+        nd = 0
+        for n in range(self.n_nodes):
+            if self.tip_row[n] >= 0 and src[n] is not None:
+                prev = self._prev_before[n] if self._prev_before is not None else None
+                nd += int((src[n] != prev).sum()) if prev is not None else self.n_patterns
+        return nd
 
     def results(self):
         return self._tot, self._nd
@@ -89,14 +135,18 @@ class OracleEngine(object):
         return self._site.copy()
 
     def node_array(self, node, which):
+        if which == 3:
+            return np.array(self.jres.joint_Lx[0])
         r = self.res
         return np.array((r.subtree_LH, r.outgroup_LH, r.profile)[which][node])
 
     def seq_idx(self, nodes):
-        return np.array([self.res.seq_idx[int(n)] for n in np.atleast_1d(nodes)], dtype=np.uint8)
+        src = self.res.seq_idx if self.res is not None else self.seqs
+        return np.array([src[int(n)] for n in np.atleast_1d(nodes)], dtype=np.uint8)
 
     def all_seq_idx(self, out=None):
-        rows = [self.res.seq_idx[n] for n in range(self.n_nodes) if self.tip_row[n] < 0]
+        src = self.res.seq_idx if self.res is not None else self.seqs
+        rows = [src[n] for n in range(self.n_nodes) if self.tip_row[n] < 0]
         return np.array(rows, dtype=np.uint8)
 
     def _pair(self, n, kind):

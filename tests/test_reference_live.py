@@ -217,3 +217,30 @@ def test_dropin_batched_branch_grids_match_reference_interpolators():
     n = list(ours.tree.find_clades())[3]
     m = list(ref.tree.find_clades())[3]
     assert np.array_equal(n.profile_pair[0], m.profile_pair[0]) and np.array_equal(n.profile_pair[1], m.profile_pair[1])
+
+
+def test_dropin_joint_reconstruction_and_treetime_run_joint():
+    """N2: joint ML reconstruction through the drop-in equals the reference (incl. root sampling with the
+    shared RNG and a full TreeTime.run in joint mode)."""
+    rt, dt = _pair(seed=36)
+    assert rt.infer_ancestral_sequences(marginal=False) == dt.infer_ancestral_sequences(marginal=False)
+    assert dt._b200_live and dt._engine.launch_count() > 0
+    assert rt.tree.sequence_joint_LH == dt.tree.sequence_joint_LH and np.array_equal(rt.tree.sequence_LH, dt.tree.sequence_LH)
+    for a, b in zip(rt.tree.find_clades(), dt.tree.find_clades()):
+        if not a.is_terminal():
+            assert (a.cseq == b.cseq).all() and a.mutations == b.mutations
+    assert rt.infer_ancestral_sequences(marginal=False) == dt.infer_ancestral_sequences(marginal=False) == 0
+    # root sampling consumes the RNG identically
+    n1 = rt.infer_ancestral_sequences(marginal=False, sample_from_profile='root', reconstruct_tip_states=True)
+    n2 = dt.infer_ancestral_sequences(marginal=False, sample_from_profile='root', reconstruct_tip_states=True)
+    assert n1 == n2
+    for a, b in zip(rt.tree.find_clades(), dt.tree.find_clades()):
+        assert (a.cseq == b.cseq).all()
+    # joint after marginal and back
+    assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
+    assert rt.infer_ancestral_sequences(marginal=False) == dt.infer_ancestral_sequences(marginal=False)
+    # joint branch-length optimisation runs the reference's code on top of the lazily fetched sequences
+    rt.optimize_tree(branch_length_mode='joint', max_iter=2, prune_short=False)
+    dt.optimize_tree(branch_length_mode='joint', max_iter=2, prune_short=False)
+    a = np.array([c.branch_length for c in rt.tree.find_clades()]); b = np.array([c.branch_length for c in dt.tree.find_clades()])
+    assert np.allclose(a[1:], b[1:], rtol=1e-9, atol=1e-14)

@@ -138,3 +138,16 @@ def test_device_compress_path_equals_host_compress():
     for x, y in zip(a.tree.find_clades(), b.tree.find_clades()):
         if not x.is_terminal():
             assert (x.cseq == y.cseq).all() and x.mutations == y.mutations
+
+
+def test_mirror_joint_reconstruction():
+    """N2 through the mirror API: infer_ancestral_sequences(marginal=False)."""
+    z = G.load('nuc40')
+    tt = mirror_from_golden(z)
+    n1 = tt.infer_ancestral_sequences(marginal=False)
+    assert n1 == (len(z['node_names']) - 40 - 1) * tt.data.compressed_length
+    assert tt.sequence_reconstruction == 'joint' and np.isfinite(tt.tree.sequence_joint_LH)
+    assert tt.infer_ancestral_sequences(marginal=False) == 0
+    with pytest.raises(AttributeError):
+        tt.tree.root.marginal_profile          # marginal state does not exist after a joint pass
+    assert tt.infer_ancestral_sequences(marginal=True) >= 0 and tt.tree.root.marginal_profile.shape[1] == 5

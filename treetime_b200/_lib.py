@@ -95,7 +95,9 @@ SIGNATURES = {
     'ttb_set_branch_lengths': ([_H, _c_dbl_p], ctypes.c_int),
     'ttb_marginal': ([_H, ctypes.c_int32], ctypes.c_int),
     'ttb_joint': ([_H, ctypes.c_int32], ctypes.c_int),
+    'ttb_joint_retrace': ([_H, _c_u8_p, ctypes.c_int32], ctypes.c_int),
     'ttb_results': ([_H, _c_dbl_p, ctypes.POINTER(ctypes.c_int64)], ctypes.c_int),
+    'ttb_results_tips': ([_H, ctypes.POINTER(ctypes.c_int64)], ctypes.c_int),
     'ttb_results_device_ptr': ([_H, ctypes.POINTER(ctypes.c_void_p)], ctypes.c_int),
     'ttb_sync': ([_H], ctypes.c_int),
     'ttb_fetch_site_lh': ([_H, _c_dbl_p], ctypes.c_int),

@@ -391,7 +391,7 @@ int ensure_state(ttb_handle h, bool tips) {
   if ((rc = h->d_LH.alloc(ld))) return rc;
   if ((rc = h->d_lh_partial.alloc(h->tiles()))) return rc;
   if ((rc = h->d_nd.alloc(1024))) return rc;
-  if ((rc = h->d_results.alloc(2))) return rc;
+  if ((rc = h->d_results.alloc(4))) return rc;
   return 0;
 }
 
@@ -452,7 +452,7 @@ int ttb_create(ttb_handle* out, int device, int n_states) {
   h->q = n_states;
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
-  CK(cudaMallocHost(&h->h_results, 2 * sizeof(double)));
+  CK(cudaMallocHost(&h->h_results, 4 * sizeof(double)));
   h->scratch_cap = 16u << 20;
   CK(cudaMallocHost(&h->h_scratch, h->scratch_cap));
   CK(cudaEventCreateWithFlags(&h->scratch_ev, cudaEventDisableTiming));
@@ -894,7 +894,7 @@ int ttb_marginal(ttb_handle h, int32_t flags) {
     it = h->graphs.find(key);
   }
   CK(cudaGraphLaunch(it->second, h->stream));
-  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   h->launches += h->graph_kernels[key];
   if (!lh_only) {
     h->have_pass = true;
@@ -909,6 +909,7 @@ int ttb_joint(ttb_handle h, int32_t flags) {
   if (int rc = check_ready(h, false)) return rc;
   if (h->site_specific) return fail(TTB_EUNSUPPORTED, "ttb_joint: joint reconstruction is not implemented for site-specific models");
   const bool tips = flags & TTB_RECONSTRUCT_TIPS;
+  const bool trace = !(flags & TTB_JOINT_NO_TRACE);
   const bool had_P = h->d_P.p != nullptr;
   if (int rc = ensure_state(h, tips)) return rc;
   if (!had_P) h->drop_graphs();
@@ -929,14 +930,14 @@ int ttb_joint(ttb_handle h, int32_t flags) {
     CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), h->stream));
   }
   if (fresh) h->drop_graphs();
-  const int key = 8 | (tips ? TTB_RECONSTRUCT_TIPS : 0);
+  const int key = 8 | (tips ? TTB_RECONSTRUCT_TIPS : 0) | (trace ? 0 : 16);
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
     TtbPassPlan pl;
     fill_plan(h, pl, tips, 1);
     cudaGraph_t graph;
     CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
-    const int nk = ttb_qops(h->q)->enqueue_joint(pl, h->own_stream);
+    const int nk = ttb_qops(h->q)->enqueue_joint(pl, h->own_stream, trace ? 1 : 0);
     cudaError_t ce = cudaStreamEndCapture(h->own_stream, &graph);
     if (ce != cudaSuccess) return fail(TTB_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
     if (nk <= 0) return fail(TTB_EUNSUPPORTED, "ttb_joint: not available for this model");
@@ -948,10 +949,31 @@ int ttb_joint(ttb_handle h, int32_t flags) {
     it = h->graphs.find(key);
   }
   CK(cudaGraphLaunch(it->second, h->stream));
-  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   h->launches += h->graph_kernels[key];
   h->have_pass = h->have_tip_pass = false;   // the marginal messages were overwritten
   h->have_joint = true;
+  h->have_joint_tips = tips && trace;
+  return 0;
+}
+
+int ttb_joint_retrace(ttb_handle h, const uint8_t* root_idx, int32_t flags) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->have_joint) return fail(TTB_EINVAL, "ttb_joint_retrace: call ttb_joint first");
+  if (!root_idx) return fail(TTB_EINVAL, "ttb_joint_retrace: null root_idx");
+  const bool tips = flags & TTB_RECONSTRUCT_TIPS;
+  if (tips && !h->d_idxtip.p) return fail(TTB_EINVAL, "ttb_joint_retrace: ttb_joint was run without TTB_RECONSTRUCT_TIPS");
+  for (long long a = 0; a < h->Lp; ++a)
+    if (root_idx[a] >= h->q) return fail(TTB_EINVAL, "ttb_joint_retrace: root state out of range");
+  int rc;
+  if ((rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)h->Lp))) return rc;
+  CK(cudaMemcpyAsync(h->d_bstage.p, root_idx, (size_t)h->Lp, cudaMemcpyHostToDevice, h->stream));
+  TtbPassPlan pl;
+  fill_plan(h, pl, tips, 1);
+  const int nk = ttb_qops(h->q)->enqueue_joint_retrace(pl, h->d_bstage.p, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  h->launches += nk;
   h->have_joint_tips = tips;
   return 0;
 }
@@ -964,10 +986,18 @@ int ttb_results(ttb_handle h, double* total_lh, int64_t* n_diff) {
   return 0;
 }
 
+int ttb_results_tips(ttb_handle h, int64_t* n_diff_tips) {
+  if (int rc = use_device(h)) return rc;
+  if (!n_diff_tips) return fail(TTB_EINVAL, "null argument");
+  CK(cudaStreamSynchronize(h->stream));
+  *n_diff_tips = (int64_t)h->h_results[2];
+  return 0;
+}
+
 int ttb_results_device_ptr(ttb_handle h, void** dptr) {
   if (int rc = use_device(h)) return rc;
   if (!dptr) return fail(TTB_EINVAL, "dptr is null");
-  if (int rc = h->d_results.alloc(2)) return rc;
+  if (int rc = h->d_results.alloc(4)) return rc;
   *dptr = h->d_results.p;
   return 0;
 }
@@ -1113,7 +1143,7 @@ int ttb_profile_marginal(ttb_handle h, int32_t flags, double* ms, int32_t* launc
   int rc = enqueue_pass(h, flags, lh_only ? 0 : 1, h->stream, &nk, ev, pk);
   if (rc) return rc;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   float f;
   CK(cudaEventElapsedTime(&f, ev[0], ev[1])); ms[0] = f;

@@ -104,7 +104,7 @@ struct TtbDev {
   double* LH;       // [ld] tree.sequence_LH
   double* lh_partial;             // [tiles]
   unsigned long long* nd_slots;   // [1024]
-  double* results;                // {total_lh, n_diff}
+  double* results;                // {total_lh, n_diff, n_diff of tips}
 };
 
 // ---------------------------------------------------------------------------------------
@@ -363,6 +363,25 @@ __global__ void __launch_bounds__(TTB_BLOCK) joint_root_kernel(TtbDev p) {
   if (threadIdx.x == 0) p.lh_partial[blockIdx.x] = bs;
 }
 
+// Root of the joint pass with a caller-chosen root state (sample_from_profile='root',
+// treeanc.py:1008-1023: the root is sampled on the host from exp(joint_Lx - max)).
+template <int Q>
+__global__ void __launch_bounds__(TTB_BLOCK) joint_root_override_kernel(TtbDev p, const uint8_t* __restrict__ root_idx) {
+  __shared__ double sred[TTB_BLOCK / 32];
+  const long long a = (long long)blockIdx.x * TTB_BLOCK + threadIdx.x;
+  double contrib = 0.0;
+  if (a < p.Lp) {
+    const int slot = p.int_slot[0];
+    const int st = root_idx[a];
+    const double lh = p.S[msg_off<Q>(p, slot, a) + (size_t)st * TTB_TILE];   // joint_Lx of the root
+    p.idx[(size_t)slot * p.ld + a] = (uint8_t)st;
+    p.LH[a] = lh;
+    contrib = lh * p.mult[a];
+  }
+  const double bs = block_sum<TTB_BLOCK>(contrib, sred);
+  if (threadIdx.x == 0) p.lh_partial[blockIdx.x] = bs;
+}
+
 // Backtrace of one depth level (treeanc.py:1034-1048): state_c = Cx_c[state_parent]; tips read the
 // per-branch table instead.  One thread per (node, pattern).
 template <int Q>
@@ -388,8 +407,9 @@ __global__ void __launch_bounds__(TTB_BLOCK) joint_pre_level_kernel(TtbDev p, co
     *ip = (uint8_t)st;
   }
   if (count_diff) {
-    nd = __reduce_add_sync(0xffffffffu, nd);
-    if ((threadIdx.x & 31) == 0 && nd) atomicAdd(p.nd_slots + (blockIdx.x & 1023), (unsigned long long)nd);
+    nd = __reduce_add_sync(0xffffffffu, nd);   // a block handles one node: all tips or all internal
+    if ((threadIdx.x & 31) == 0 && nd)
+      atomicAdd(p.nd_slots + (p.tip_row[n] >= 0 ? 512 : 0) + (blockIdx.x & 511), (unsigned long long)nd);
   }
 }
 
@@ -793,16 +813,18 @@ static __global__ void __launch_bounds__(256) finish_kernel(TtbDev p, int tiles)
   double x = 0.0;
   for (int i = threadIdx.x; i < tiles; i += 256) x += p.lh_partial[i];
   const double tot = block_sum<256>(x, sred);
-  __shared__ unsigned long long snd[256];
-  unsigned long long nd = 0;
-  for (int i = threadIdx.x; i < 1024; i += 256) nd += p.nd_slots[i];
+  __shared__ unsigned long long snd[256], snt[256];
+  unsigned long long nd = 0, nt = 0;
+  for (int i = threadIdx.x; i < 512; i += 256) { nd += p.nd_slots[i]; nt += p.nd_slots[512 + i]; }
   snd[threadIdx.x] = nd;
+  snt[threadIdx.x] = nt;
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned long long s = 0;
-    for (int i = 0; i < 256; ++i) s += snd[i];
+    unsigned long long s = 0, st = 0;
+    for (int i = 0; i < 256; ++i) { s += snd[i]; st += snt[i]; }
     p.results[0] = tot;
-    p.results[1] = (double)s;
+    p.results[1] = (double)(s + st);   // N_diff
+    p.results[2] = (double)st;         // ... of which tips
   }
 }
 
@@ -1036,7 +1058,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
   if (SS) pipe.wait_model();
 
   double Mp[Q];
-  unsigned int ndiff = 0;
+  unsigned int ndiff = 0, ndiff_tip = 0;   // changed states of internal nodes / of tips
   for (int u = 0; u < n_chunks; ++u) {
     if (warp == 0 && u + Pipe<Q>::STAGES - 1 < n_chunks) issue(u + Pipe<Q>::STAGES - 1);
     const int s = u % Pipe<Q>::STAGES;
@@ -1184,7 +1206,10 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
             if (x > bv) { bv = x; best = i; }
           }
         }
-        if (count_diff) ndiff += (pipe.oidx(s)[b * TTB_TILE + tid] != (uint8_t)best);
+        if (count_diff) {
+          const unsigned int ch = (pipe.oidx(s)[b * TTB_TILE + tid] != (uint8_t)best);
+          if (TIPS && src < 0) ndiff_tip += ch; else ndiff += ch;
+        }
         *ip = (uint8_t)best;
       }
     }
@@ -1193,7 +1218,11 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
   }
   if (count_diff) {
     ndiff = __reduce_add_sync(0xffffffffu, ndiff);
-    if (lane == 0 && ndiff) atomicAdd(p.nd_slots + (blockIdx.x & 1023), (unsigned long long)ndiff);
+    if (lane == 0 && ndiff) atomicAdd(p.nd_slots + (blockIdx.x & 511), (unsigned long long)ndiff);
+    if (TIPS) {
+      ndiff_tip = __reduce_add_sync(0xffffffffu, ndiff_tip);
+      if (lane == 0 && ndiff_tip) atomicAdd(p.nd_slots + 512 + (blockIdx.x & 511), (unsigned long long)ndiff_tip);
+    }
   }
 }
 

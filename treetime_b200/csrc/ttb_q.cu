@@ -100,7 +100,7 @@ int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   return enqueue_pass_t<false>(pl, s, ev, pk);
 }
 
-int enqueue_joint_q(const TtbPassPlan& pl, cudaStream_t s) {
+int enqueue_joint_q(const TtbPassPlan& pl, cudaStream_t s, int trace) {
   const TtbDev& d = pl.d;
   if (d.site_specific) return 0;
   const int tiles = pl.tiles;
@@ -128,6 +128,22 @@ int enqueue_joint_q(const TtbPassPlan& pl, cudaStream_t s) {
   joint_root_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d);
   zero_slots_kernel<<<4, 256, 0, s>>>(d);
   nk += 2;
+  for (int l = 0; trace && l < pl.n_jpre_levels; ++l) {
+    const TtbLevelLaunch& L = pl.jpre_levels[l];
+    joint_pre_level_kernel<Q><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_jpre_nodes + L.group_off, tiles,
+                                                                                            pl.count_diff);
+    ++nk;
+  }
+  finish_kernel<<<1, 256, 0, s>>>(d, tiles);
+  return nk + 1;
+}
+
+int enqueue_joint_retrace_q(const TtbPassPlan& pl, const uint8_t* d_root_idx, cudaStream_t s) {
+  const TtbDev& d = pl.d;
+  const int tiles = pl.tiles;
+  joint_root_override_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d, d_root_idx);
+  zero_slots_kernel<<<4, 256, 0, s>>>(d);
+  int nk = 2;
   for (int l = 0; l < pl.n_jpre_levels; ++l) {
     const TtbLevelLaunch& L = pl.jpre_levels[l];
     joint_pre_level_kernel<Q><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_jpre_nodes + L.group_off, tiles,
@@ -170,4 +186,4 @@ void counts_q(const TtbDev& d, int tiles, int chunks, int chunk, double* partial
 
 #define TTB_CAT2(a, b) a##b
 #define TTB_CAT(a, b) TTB_CAT2(a, b)
-extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {prepare_q, enqueue_pass_q, enqueue_joint_q, fetch_node_q, branch_eval_q, counts_q};
+extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {prepare_q, enqueue_pass_q, enqueue_joint_q, enqueue_joint_retrace_q, fetch_node_q, branch_eval_q, counts_q};

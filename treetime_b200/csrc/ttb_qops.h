@@ -39,7 +39,9 @@ struct TtbQOps {
   // enqueue every kernel of one pass; optional events ev[6] bracket the phases; returns #kernels
   int (*enqueue_pass)(const TtbPassPlan& plan, cudaStream_t s, cudaEvent_t* ev, int* phase_kernels);
   // joint (max-product) reconstruction, same schedule; returns #kernels, 0 if unsupported for this model
-  int (*enqueue_joint)(const TtbPassPlan& plan, cudaStream_t s);
+  int (*enqueue_joint)(const TtbPassPlan& plan, cudaStream_t s, int trace);
+  // root states chosen by the caller (root sampling) + back-trace
+  int (*enqueue_joint_retrace)(const TtbPassPlan& plan, const uint8_t* d_root_idx, cudaStream_t s);
   void (*fetch_node)(const TtbDev& d, int tiles, int node, int which, double* out, cudaStream_t s);
   void (*branch_eval)(const TtbDev& d, int n_eval, int nb, const int* nodes, const int* kinds, const double* ts,
                       int mode, double* partial, double* out, cudaStream_t s);

@@ -155,7 +155,8 @@ class DeviceMarginalMixin(object):
     def _node_array(self, node, which):
         key = (node._fid, which)
         if key not in self._cache:
-            if not self.sequence_reconstruction and not (which == SUBTREE and self._engine is not None):
+            if self.sequence_reconstruction != 'marginal' and not (which == SUBTREE and self._engine is not None
+                                                                   and not self.sequence_reconstruction):
                 raise AttributeError('marginal ancestral inference needs to be performed first!')
             if which == PROFILE and node.is_terminal() and not self.reconstructed_tip_sequences:
                 raise AttributeError('tip profiles exist only after reconstruct_tip_states=True')
@@ -200,11 +201,7 @@ class DeviceMarginalMixin(object):
         self.tree.sequence_LH = self._gather_patterns(eng.site_lh())
         self.tree.total_sequence_LH = float(tot)
         self.tree.sequence_marginal_LH = self.tree.total_sequence_LH
-        n_rec = (topo.n_nodes - 1) if reconstruct_tip_states else (topo.n_nodes - topo.n_tips - 1)
-        if self.sequence_reconstruction:
-            N_diff = int(round(nd))
-        else:
-            N_diff = n_rec * self.data.compressed_length               # treeanc.py:927-928
+        N_diff = self._n_diff(eng, topo, nd, reconstruct_tip_states, self.reconstructed_tip_sequences)
         root = self.tree.root
         root._cseq_override = None
         self.reconstructed_tip_sequences = reconstruct_tip_states
@@ -213,6 +210,76 @@ class DeviceMarginalMixin(object):
             seq, _, _ = prof2seq(self._node_array(root, PROFILE), self.gtr, sample_from_prof=True, normalize=False, rng=self.rng)
             root._cseq_override = seq
         self.logger('TreeAnc._ml_anc_marginal: ...done', 3)
+        return N_diff
+
+    def _n_diff(self, eng, topo, nd, reconstruct_tip_states, prev_tips):
+        """N_diff of a pass (treeanc.py:925-928 / 1042-1045).  The device counts changed states against
+        the previous device states; two host-side corrections reproduce the reference:
+          * no previous reconstruction -> every reconstructed position counts;
+          * tips reconstructed now but not before -> the reference compares them with the alignment's own
+            (possibly ambiguous) characters, the device compared them with stale / unset states."""
+        L = self.data.compressed_length
+        if not self.sequence_reconstruction:
+            n_rec = (topo.n_nodes - 1) if reconstruct_tip_states else (topo.n_nodes - topo.n_tips - 1)
+            return n_rec * L
+        nd = int(round(nd))
+        if reconstruct_tip_states and not prev_tips:
+            nd_tips = eng.results_tips()
+            if self.comm.world_size > 1:
+                nd_tips = int(round(self.comm.allreduce_sum(np.array([float(nd_tips)]))[0]))
+            fresh = 0
+            ca = self.data.compressed_alignment
+            tips = list(topo.tip_nodes)
+            for b in range(0, len(tips), 256):                        # batched D2H, one transition per run
+                blk = tips[b:b + 256]
+                idx = self._gather_patterns(eng.seq_idx(blk), axis=1)
+                for k, n in enumerate(blk):
+                    name = topo.nodes[n].name
+                    if name in ca:
+                        fresh += int((self.gtr.alphabet[idx[k]] != np.asarray(ca[name])).sum())
+                    else:
+                        fresh += L      # a tip without sequence has no cseq: the reference's comparison is all-True
+            nd = nd - nd_tips + fresh
+        return nd
+
+    def _ml_anc_joint(self, sample_from_profile=False, reconstruct_tip_states=False, debug=False, **kwargs):
+        """treeanc.py:934-1080 (N2): joint ML reconstruction -- log-space postorder with back-pointers,
+        root state (argmax, or sampled on the host with the caller's RNG), back-trace."""
+        self.logger('TreeAnc._ml_anc_joint: type of reconstruction: Joint', 2)
+        if sample_from_profile == 'root':
+            root_sample = True
+        elif isinstance(sample_from_profile, bool):
+            root_sample = sample_from_profile           # treeanc.py:1008-1011: a bool only affects the root
+        else:
+            raise ValueError("sample_from_profile must be a bool or 'root'")
+        if any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
+            self._unsupported('per-branch masks (ARG mode) are not supported on the device path')
+        if getattr(self.gtr, 'is_site_specific', False):
+            self._unsupported('joint reconstruction with site-specific models runs in the reference')
+        eng = self._sync_device()
+        topo = self._flat()
+        if root_sample:
+            eng.joint(reconstruct_tips=reconstruct_tip_states, trace=False)
+            eng.results()
+            lx = self._gather_patterns(eng.node_array(0, 3), axis=0)              # root.joint_Lx
+            normalized = (lx.T - lx.max(axis=1)).T
+            seq, _, idxs = prof2seq(np.exp(normalized), self.gtr, sample_from_prof=True, rng=self.rng)
+            lo, hi = self._shard()
+            eng.joint_retrace(idxs[lo:hi].astype(np.uint8), reconstruct_tips=reconstruct_tip_states)
+        else:
+            eng.joint(reconstruct_tips=reconstruct_tip_states)
+        tot, nd = eng.results()
+        if self.comm.world_size > 1:
+            tot, nd = self.comm.allreduce_sum(np.array([tot, float(nd)]))
+        self._cache = {}
+        self._seq_cache = {}
+        self.tree.sequence_LH = self._gather_patterns(eng.site_lh())
+        self.tree.sequence_joint_LH = float(tot)
+        N_diff = self._n_diff(eng, topo, nd, reconstruct_tip_states, self.reconstructed_tip_sequences)
+        self.tree.root._cseq_override = None
+        self.reconstructed_tip_sequences = reconstruct_tip_states
+        self.sequence_reconstruction = 'joint'
+        self.logger('TreeAnc._ml_anc_joint: ...done', 3)
         return N_diff
 
     def sequence_LH(self, pos=None, full_sequence=False):

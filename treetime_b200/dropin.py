@@ -175,6 +175,55 @@ class B200MarginalMixin(DeviceMarginalMixin):
                                                                reconstruct_tip_states=reconstruct_tip_states,
                                                                debug=debug, **kwargs)
 
+    def _ml_anc_joint(self, sample_from_profile=False, reconstruct_tip_states=False, debug=False, **kwargs):
+        """Joint ML reconstruction (treeanc.py:934-1080) on the device, with the same fallbacks."""
+        why = self._device_ok()
+        if why is None and getattr(self.gtr, 'is_site_specific', False):
+            why = 'site-specific model'
+        if why is None and any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
+            why = 'per-branch masks (ARG mode)'
+        if why is None:
+            try:
+                prev_live = self._b200_live and self.sequence_reconstruction in ('joint', 'marginal')
+                old = None
+                if self.sequence_reconstruction and not prev_live:
+                    old = {}
+                    for n in self.tree.find_clades():
+                        if n.up is not None and (reconstruct_tip_states or not n.is_terminal()):
+                            try:
+                                c = n.cseq
+                            except ValueError:
+                                c = None
+                            if c is not None:
+                                old[id(n)] = np.array(c)
+                self._drop_node_caches()
+                topo = self._refresh_topology()
+                _install_hook(type(self.tree.root))
+                for n in topo.nodes:
+                    d = n.__dict__
+                    for k in ('marginal_subtree_LH', 'marginal_outgroup_LH', 'marginal_profile', '_cseq', 'joint_Lx', 'joint_Cx',
+                              'seq_idx', 'branch_state'):
+                        d.pop(k, None)
+                N_diff = DeviceMarginalMixin._ml_anc_joint(self, sample_from_profile=sample_from_profile,
+                                                           reconstruct_tip_states=reconstruct_tip_states, debug=debug)
+                self._b200_live = True
+                if old is not None:
+                    N_diff = 0
+                    for n in topo.nodes[1:]:
+                        if reconstruct_tip_states or not n.is_terminal():
+                            N_diff += int((n.cseq != old[id(n)]).sum()) if id(n) in old else self.data.compressed_length
+                return N_diff
+            except Unsupported as e:
+                why = str(e)
+        self.logger('B200: falling back to the reference implementation (%s)' % why, 2)
+        if self._b200_live and self._topo is not None:
+            for n in self._topo.nodes:
+                if '_cseq' not in n.__dict__ and (self.reconstructed_tip_sequences or not n.is_terminal()):
+                    n.__dict__['_cseq'] = self._node_cseq(n)
+        self._drop_node_caches()
+        return super(DeviceMarginalMixin, self)._ml_anc_joint(sample_from_profile=sample_from_profile,
+                                                            reconstruct_tip_states=reconstruct_tip_states, debug=debug, **kwargs)
+
     # accessors: the reference's own versions work through the lazy node attributes
     def sequence_LH(self, *args, **kwargs):
         return super(DeviceMarginalMixin, self).sequence_LH(*args, **kwargs)

@@ -140,15 +140,28 @@ class Engine(object):
         flags = (RECONSTRUCT_TIPS if reconstruct_tips else 0) | (LH_ONLY if lh_only else 0)
         _lib.check(self.lib.ttb_marginal(self.h, flags))
 
-    def joint(self, reconstruct_tips=False):
-        """Joint (max-product) reconstruction; results() returns (sequence_joint_LH, N_diff)."""
-        _lib.check(self.lib.ttb_joint(self.h, RECONSTRUCT_TIPS if reconstruct_tips else 0))
+    def joint(self, reconstruct_tips=False, trace=True):
+        """Joint (max-product) reconstruction; results() returns (sequence_joint_LH, N_diff).
+        trace=False stops after the root so that the caller can sample the root (joint_retrace)."""
+        _lib.check(self.lib.ttb_joint(self.h, (RECONSTRUCT_TIPS if reconstruct_tips else 0) | (0 if trace else 4)))
+
+    def joint_retrace(self, root_idx, reconstruct_tips=False):
+        root_idx = np.ascontiguousarray(root_idx, dtype=np.uint8)
+        if root_idx.shape[0] != self.n_patterns:
+            raise ValueError('root_idx must have one state per pattern')
+        _lib.check(self.lib.ttb_joint_retrace(self.h, _up(root_idx), RECONSTRUCT_TIPS if reconstruct_tips else 0))
 
     def results(self):
         tot = ctypes.c_double()
         nd = ctypes.c_int64()
         _lib.check(self.lib.ttb_results(self.h, ctypes.byref(tot), ctypes.byref(nd)))
         return tot.value, nd.value
+
+    def results_tips(self):
+        """The share of N_diff that comes from terminal nodes."""
+        nd = ctypes.c_int64()
+        _lib.check(self.lib.ttb_results_tips(self.h, ctypes.byref(nd)))
+        return nd.value
 
     def results_device_ptr(self):
         p = ctypes.c_void_p()

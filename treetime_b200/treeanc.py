@@ -16,7 +16,7 @@ With a communicator of world_size > 1 (treetime_b200.dist) every rank holds the
 same tree/model and one contiguous block of the compressed patterns; scalars are
 all-reduced, per-node arrays are all-gathered on access.
 
-Not provided here (outside SURVEY.md §8): joint/Fitch reconstruction, masks
+Not provided here (outside SURVEY.md §8): Fitch reconstruction, joint-mode branch-length optimisation, masks
 (ARG mode), sampling of non-root nodes from their profiles.  They raise
 NotImplementedError; the drop-in mixin for the real TreeTime
 (treetime_b200.dropin) falls back to the reference's own code for them.
@@ -276,9 +276,7 @@ class TreeAnc(DeviceMarginalMixin):
             raise MissingDataError('TreeAnc.infer_ancestral_sequences: ERROR, sequences or tree are missing')
         self.logger('TreeAnc.infer_ancestral_sequences with method: %s, %s' % (method, 'marginal' if marginal else 'joint'), 1)
         if method.lower() in ['ml', 'probabilistic']:
-            if not marginal:
-                raise NotImplementedError('joint ML reconstruction is outside the B200 hot path (SURVEY.md §8f N2); '
-                                          'use marginal=True or the reference implementation')
+            _ml_anc = self._ml_anc_marginal if marginal else self._ml_anc_joint
         elif method.lower() in ['fitch', 'parsimony']:
             raise NotImplementedError('Fitch reconstruction is outside the B200 hot path; use the reference implementation')
         else:
@@ -286,7 +284,7 @@ class TreeAnc(DeviceMarginalMixin):
                                      "got '{}'".format(method))
         if infer_gtr:
             self.infer_gtr(marginal=marginal, **kwargs)
-        return self._ml_anc_marginal(reconstruct_tip_states=reconstruct_tip_states, **kwargs)
+        return _ml_anc(reconstruct_tip_states=reconstruct_tip_states, **kwargs)
 
     def _branch_length_to_gtr(self, node):
         """treeanc.py:752-760."""
