@@ -24,6 +24,7 @@ from treetime_b200 import synth  # noqa: E402
 from treetime_b200.flatten import flatten_treeanc  # noqa: E402
 
 OUT = os.path.join(refenv.REPO, 'tests', 'golden')
+ONLY = set(a[7:] for a in sys.argv if a.startswith('--only='))     # e.g. --only=poly70: regenerate one fixture
 
 
 def sha(a):
@@ -45,6 +46,8 @@ def gtr_params(gtr):
 
 def run_case(name, newick, aln, gtr, store_every=1, reconstruct_tips=False, optimize=False, infer_gtr=False,
              n_bl=6, compress=True, store_inputs=True, extra=None, cseq_as_idx=False):
+    if ONLY and name not in ONLY:
+        return
     t0 = time.time()
     pre = gtr_params(gtr)       # profile map / ambiguous as the user built the model (before extend_profile)
     tt = refenv.reference_treeanc(newick, aln, gtr, rng_seed=1, compress=compress)
@@ -127,6 +130,43 @@ def run_case(name, newick, aln, gtr, store_every=1, reconstruct_tips=False, opti
                                                                  time.time() - t0, os.path.getsize(path) // 1024))
 
 
+def run_joint_case(src, gtr, reconstruct_tips=False):
+    """N2 fixtures: joint reconstruction (treeanc.py:934-1080) on the inputs of an existing fixture."""
+    z = np.load(os.path.join(OUT, src + '.npz'))
+    newick = str(z['newick'])
+    aln = {str(k): np.array(list(str(v))) for k, v in zip(z['aln_names'], z['aln_seqs'])}
+    tt = refenv.reference_treeanc(newick, aln, gtr, rng_seed=1)
+    topo, flat, g = flatten_treeanc(tt)
+    N1 = tt.infer_ancestral_sequences(marginal=False, reconstruct_tip_states=reconstruct_tips, debug=True)   # keep Lx / Cx
+    out = dict(source=np.array(src), reconstruct_tips=np.array(reconstruct_tips), N_diff_first=np.array(N1),
+               sequence_joint_LH=np.array(tt.tree.sequence_joint_LH), sequence_LH=np.array(tt.tree.sequence_LH),
+               cseq=np.array([''.join(n.cseq) if n.cseq is not None else '' for n in topo.nodes]),
+               root_joint_Lx=np.array(tt.tree.root.joint_Lx))
+    stored = list(range(1, topo.n_nodes, max(1, topo.n_nodes // 8)))
+    out['stored_nodes'] = np.array(stored)
+    for i in stored:
+        n = topo.nodes[i]
+        if hasattr(n, 'joint_Lx') and getattr(n, 'joint_Cx', None) is not None:
+            out['Lx_%d' % i] = np.array(n.joint_Lx)
+            out['Cx_%d' % i] = np.array(n.joint_Cx)
+    out['N_diff_second'] = np.array(tt.infer_ancestral_sequences(marginal=False, reconstruct_tip_states=reconstruct_tips))
+    out['N_diff_marginal_after'] = np.array(tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=reconstruct_tips))
+    name = 'joint_' + src + ('_tips' if reconstruct_tips else '')
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **out)
+    print('%-22s joint_LH=%.6f N_diff=%d/%d/%d %d KB' % (name, out['sequence_joint_LH'], N1, out['N_diff_second'],
+                                                       out['N_diff_marginal_after'], os.path.getsize(path) // 1024))
+
+
+def joint_cases():
+    from treetime import GTR
+    nuc = lambda: GTR.custom(pi=np.array([.3, .2, .2, .29, .01]), W=np.ones((5, 5)), alphabet='nuc')  # noqa: E731
+    run_joint_case('nuc40', nuc())
+    run_joint_case('nuc40', nuc(), reconstruct_tips=True)
+    run_joint_case('poly70', nuc())
+    run_joint_case('aa16_jtt92', GTR.standard('JTT92'), reconstruct_tips=True)
+
+
 def chars(idx, gtr):
     return {k: gtr.alphabet[v] for k, v in idx.items()}
 
@@ -190,4 +230,8 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if '--only-joint' in sys.argv:      # adds the joint_*.npz fixtures next to the existing ones
+        joint_cases()
+    else:
+        main()
+        joint_cases()

@@ -6,6 +6,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 SMALL = ['kat3', 'nuc40', 'nuc40_tips', 'poly70', 'aa16_jtt92', 'aa16_q22']
 SITE_SPECIFIC = ['sitespec20']
 BIG = ['cfg1_200x1400', 'cfg2_2000x10000']
+JOINT = ['joint_nuc40', 'joint_nuc40_tips', 'joint_poly70', 'joint_aa16_jtt92_tips']      # N2; inputs live in z['source']
 
 
 def load(name):

@@ -254,6 +254,13 @@ def test_joint_reconstruction(kind):
     assert np.allclose(lx, res.joint_Lx[0], rtol=1e-11, atol=1e-9)
     eng.marginal()
     assert abs(eng.results()[0] - O.marginal(flat, g).total_LH) <= LH_RTOL * abs(O.marginal(flat, g).total_LH)
+    # a fresh engine: joint first, then marginal -- the joint states are the marginal pass's "previous" states
+    e2 = util.engine_for(flat, g)
+    e2.joint()
+    rj = O.joint(flat, g)
+    e2.marginal()
+    nd_ref = O.marginal(flat, g, prev_seq_idx=rj.seq_idx).N_diff
+    assert abs(e2.results()[1] - nd_ref) <= 2e-3 * nd_ref + 4
 
 
 def test_api_errors():

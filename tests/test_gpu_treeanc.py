@@ -57,6 +57,36 @@ def test_gpu_reconstruction_matches_reference_golden(name):
     print('%s: rel dLH=%.1e  max|dprofile|=%.1e' % (name, abs(tt.sequence_LH() - float(z['total_LH'])) / abs(float(z['total_LH'])), worst))
 
 
+@pytest.mark.parametrize('name', G.JOINT)
+def test_gpu_joint_reconstruction_matches_reference_golden(name):
+    """N2: infer_ancestral_sequences(marginal=False) on the device vs the reference's _ml_anc_joint."""
+    import util
+    zj = G.load(name)
+    z = G.load(str(zj['source']))
+    tips = bool(zj['reconstruct_tips'])
+    tt = gpu_from_golden(z)
+    assert tt.infer_ancestral_sequences(marginal=False, reconstruct_tip_states=tips, debug=True) == int(zj['N_diff_first'])
+    tot = float(zj['sequence_joint_LH'])
+    assert abs(tt.tree.sequence_joint_LH - tot) <= LH_RTOL * abs(tot)
+    assert np.allclose(tt.tree.sequence_LH, zj['sequence_LH'], rtol=1e-11, atol=1e-9)
+    assert np.allclose(tt.tree.root.joint_Lx, zj['root_joint_Lx'], rtol=1e-11, atol=1e-9)
+    nodes = list(tt.tree.find_clades())
+    flat, g = G.flat_and_gtr(z)
+    seqs, n_bad = [None] * len(nodes), 0
+    lut = {c: i for i, c in enumerate(tt.gtr.alphabet)}
+    for i, (n, s) in enumerate(zip(nodes, zj['cseq'])):
+        if n.is_terminal() and not tips:
+            continue
+        c = n.cseq
+        n_bad += int((np.array(list(str(s))) != c).sum())
+        seqs[i] = np.array([lut[x] for x in c])
+    if n_bad:        # states may differ only where two assignments are equally likely to rounding
+        assert n_bad < 2e-3 * len(nodes) * tt.data.compressed_length
+        assert np.allclose(util.joint_assignment_lh(flat, g, seqs), zj['sequence_LH'], rtol=1e-10, atol=1e-8)
+    assert tt.infer_ancestral_sequences(marginal=False, reconstruct_tip_states=tips) == int(zj['N_diff_second'])
+    assert tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips) == int(zj['N_diff_marginal_after']) or n_bad
+
+
 def test_gpu_site_specific_golden():
     """Site-specific model (reference default: interpolated expQt) against the reference's output."""
     from treetime_b200.gtr import GTRSiteSpecific

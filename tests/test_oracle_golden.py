@@ -44,6 +44,28 @@ def test_oracle_matches_reference_golden(name):
         assert np.array_equal(n_ija.sum(axis=-1), z['n_ij']) and np.array_equal(T_ia.sum(axis=-1), z['T_i'])
 
 
+@pytest.mark.parametrize('name', G.JOINT)
+def test_oracle_joint_matches_reference_golden(name):
+    """N2: the joint oracle is bit-identical to TreeAnc._ml_anc_joint (treeanc.py:934-1080)."""
+    zj = G.load(name)
+    z = G.load(str(zj['source']))
+    flat, g = G.flat_and_gtr(z)
+    tips = bool(zj['reconstruct_tips'])
+    res = O.joint(flat, g, reconstruct_tip_states=tips)
+    assert res.N_diff == int(zj['N_diff_first'])
+    assert res.total_LH == float(zj['sequence_joint_LH'])
+    assert np.array_equal(res.sequence_LH, zj['sequence_LH'])
+    assert np.array_equal(res.joint_Lx[0], zj['root_joint_Lx'])
+    ab = np.array([str(c) for c in z['gtr_alphabet']])
+    for i, s in enumerate(zj['cseq']):
+        if res.seq_idx[i] is not None and (tips or flat['tip_row'][i] < 0):
+            assert ''.join(ab[res.seq_idx[i]]) == str(s)
+    for i in zj['stored_nodes']:
+        if 'Lx_%d' % i in zj.files:
+            assert np.array_equal(res.joint_Lx[i], zj['Lx_%d' % i]) and np.array_equal(res.joint_Cx[i], zj['Cx_%d' % i])
+    assert O.joint(flat, g, reconstruct_tip_states=tips, prev_seq_idx=res.seq_idx).N_diff == int(zj['N_diff_second']) == 0
+
+
 def test_reference_known_answer_lh_normalisation():
     """test/test_treetime.py:137-155: over all 4^3 column patterns of a 3-tip tree sum exp(LH) = 1;
     plus the values captured from the reference."""

@@ -140,6 +140,23 @@ def test_device_compress_path_equals_host_compress():
             assert (x.cseq == y.cseq).all() and x.mutations == y.mutations
 
 
+@pytest.mark.parametrize('name', G.JOINT)
+def test_mirror_joint_matches_reference_golden(name):
+    """N2 host logic (N_diff bookkeeping incl. tips, attributes) against the reference's golden output."""
+    zj = G.load(name)
+    z = G.load(str(zj['source']))
+    tips = bool(zj['reconstruct_tips'])
+    tt = mirror_from_golden(z)
+    assert tt.infer_ancestral_sequences(marginal=False, reconstruct_tip_states=tips, debug=True) == int(zj['N_diff_first'])
+    assert tt.tree.sequence_joint_LH == float(zj['sequence_joint_LH']) and np.array_equal(tt.tree.root.joint_Lx, zj['root_joint_Lx'])
+    assert np.array_equal(tt.tree.sequence_LH, zj['sequence_LH'])
+    for n, s in zip(tt.tree.find_clades(), zj['cseq']):
+        if tips or not n.is_terminal():
+            assert ''.join(n.cseq) == str(s)
+    assert tt.infer_ancestral_sequences(marginal=False, reconstruct_tip_states=tips) == int(zj['N_diff_second'])
+    assert tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips) == int(zj['N_diff_marginal_after'])
+
+
 def test_mirror_joint_reconstruction():
     """N2 through the mirror API: infer_ancestral_sequences(marginal=False)."""
     z = G.load('nuc40')

@@ -400,14 +400,18 @@ int ensure_preorder_state(ttb_handle h, bool tips) {
   int rc;
   if (!h->d_M.p) {
     if ((rc = h->d_M.alloc((size_t)h->n_int * h->tiles() * q * TTB_TILE))) return rc;
-    if ((rc = h->d_idx.alloc((size_t)h->n_int * ld))) return rc;
-    CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), h->stream));
+    if (!h->d_idx.p) {      // a joint pass may already have left states here: they are the "previous" ones
+      if ((rc = h->d_idx.alloc((size_t)h->n_int * ld))) return rc;
+      CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), h->stream));
+    }
     h->drop_graphs();
   }
   if (tips && !h->d_Mtip.p) {
     if ((rc = h->d_Mtip.alloc((size_t)h->n_tips * h->tiles() * q * TTB_TILE))) return rc;
-    if ((rc = h->d_idxtip.alloc((size_t)h->n_tips * ld))) return rc;
-    CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), h->stream));
+    if (!h->d_idxtip.p) {
+      if ((rc = h->d_idxtip.alloc((size_t)h->n_tips * ld))) return rc;
+      CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), h->stream));
+    }
     h->drop_graphs();
   }
   return 0;

@@ -279,6 +279,10 @@ class DeviceMarginalMixin(object):
         self.tree.root._cseq_override = None
         self.reconstructed_tip_sequences = reconstruct_tip_states
         self.sequence_reconstruction = 'joint'
+        if debug:       # the reference keeps joint_Lx / joint_Cx of every node in debug mode; here only the root's is resident
+            self.tree.root.joint_Lx = self._gather_patterns(eng.node_array(0, 3), axis=0)
+        elif 'joint_Lx' in self.tree.root.__dict__:
+            del self.tree.root.joint_Lx
         self.logger('TreeAnc._ml_anc_joint: ...done', 3)
         return N_diff
 

@@ -36,23 +36,20 @@ def random_tree(n_tips, seed=1, mean_bl=1e-3, polytomy_frac=0.0, zero_frac=0.0):
     root = lineages[0]
     root.branch_length = None
     if polytomy_frac > 0:
-        # collapse internal, non-root branches top-down
+        # collapse internal, non-root branches top-down; every internal node is drawn exactly once
         stack = [root]
         while stack:
             n = stack.pop()
-            changed = True
-            while changed:
-                changed = False
-                new = []
-                for c in n.clades:
-                    if c.clades and rng.random() < polytomy_frac:
-                        for g in c.clades:
-                            g.branch_length = (g.branch_length or 0.0) + (c.branch_length or 0.0)
-                        new.extend(c.clades)
-                        changed = True
-                    else:
-                        new.append(c)
-                n.clades = new
+            queue, new = list(n.clades), []
+            while queue:
+                c = queue.pop(0)
+                if c.clades and rng.random() < polytomy_frac:
+                    for g in c.clades:
+                        g.branch_length = (g.branch_length or 0.0) + (c.branch_length or 0.0)
+                    queue.extend(c.clades)
+                else:
+                    new.append(c)
+            n.clades = new
             stack.extend(c for c in n.clades if c.clades)
     return Tree(root=root)
 
