@@ -123,6 +123,7 @@ struct ttb_engine {
   bool site_specific = false;
   DBuf<double> d_ss_eig, d_ss_mu, d_ss_V, d_ss_Vinv, d_ss_Pi, d_ss_w, d_ss_grid, d_ss_E;
   DBuf<int> d_ss_lo;
+  DBuf<double2> d_ss_rec;
   std::vector<double> ss_grid, h_t;
   double ss_tmax = 0.0;
   bool ss_interp_dirty = true;
@@ -185,6 +186,7 @@ struct ttb_engine {
     d.mu = d_mu.p;
     d.site_specific = site_specific ? 1 : 0;
     d.ss_eig = d_ss_eig.p; d.ss_mu = d_ss_mu.p; d.ss_V = d_ss_V.p; d.ss_Vinv = d_ss_Vinv.p; d.ss_Pi = d_ss_Pi.p;
+    d.ss_rec = d_ss_rec.p;
     d.ss_lo = d_ss_lo.p; d.ss_w = d_ss_w.p; d.ss_grid = d_ss_grid.p; d.ss_E = d_ss_E.p;
     d.ss_ngrid = (int)ss_grid.size();
     d.ss_tmax = ss_tmax;
@@ -479,6 +481,7 @@ int ttb_destroy(ttb_handle h) {
   for (auto* b : db) b->release();
   h->d_codes.release();
   h->d_ss_lo.release();
+  h->d_ss_rec.release();
   h->post.d_chunks.release(); h->pre_int.d_chunks.release(); h->pre_all.d_chunks.release();
   h->d_idx.release();
   h->d_idxtip.release();
@@ -807,7 +810,7 @@ int ttb_set_gtr_site_specific(ttb_handle h, const double* eigvals, const double*
   if ((rc = upload_planes(h, h->d_ss_Pi, Pi, q))) return rc;
   if ((rc = upload(h->d_ss_grid, t_grid, (size_t)n_grid, h->stream))) return rc;
   h->ss_grid.assign(t_grid, t_grid + n_grid);
-  if ((rc = h->d_ss_E.alloc((size_t)n_grid * q * (size_t)h->ld))) return rc;
+  if ((rc = h->d_ss_E.alloc((size_t)h->tiles() * n_grid * q * TTB_TILE))) return rc;   // tile-blocked, see TtbDev::ss_E
   {
     const bool was = h->site_specific;
     h->site_specific = true;
@@ -842,10 +845,22 @@ static int update_ss_interp(ttb_handle h) {
       w[i] = (t - h->ss_grid[lo - 1]) / (h->ss_grid[lo] - h->ss_grid[lo - 1]);
     }
   }
+  std::vector<double2> rec(n);
+  for (int i = 0; i < n; ++i) rec[i] = make_double2(w[i], i ? h->h_t[i] : 0.0);
   const bool realloc = !h->d_ss_w.p;
   int rc;
   if ((rc = upload(h->d_ss_lo, glo.data(), (size_t)n, h->stream))) return rc;
   if ((rc = upload(h->d_ss_w, w.data(), (size_t)n, h->stream))) return rc;
+  if ((rc = upload(h->d_ss_rec, rec.data(), (size_t)n, h->stream))) return rc;
+  // the producer warps read each child's bracket from its chunk descriptor
+  for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all}) {
+    const int nc = (int)sc->chunks.size();
+    if (nc && sc->d_chunks.p) {
+      ss_patch_chunks_kernel<<<(nc + 255) / 256, 256, 0, h->stream>>>(sc->d_chunks.p, nc, h->d_ss_lo.p);
+      h->launches += 1;
+    }
+  }
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   if (realloc) h->drop_graphs();
   h->ss_interp_dirty = false;

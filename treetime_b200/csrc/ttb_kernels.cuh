@@ -25,6 +25,8 @@
 #define TTB_TINY 1e-12        // ttconf.TINY_NUMBER  (treetime/config.py:4)
 #define TTB_SUPERTINY 1e-24   // ttconf.SUPERTINY_NUMBER (treetime/config.py:5)
 #define TTB_BLOCK 128
+// the streaming level kernels add one producer warp (bulk-copy issue only) to the TTB_BLOCK pattern threads
+#define TTB_LEVEL_THREADS (TTB_BLOCK + 32)
 #define TTB_TILE 128          // patterns per tile = threads per block: one 1 KB row per state
 #define TTB_CB 2              // children per pipeline chunk (binary nodes = one chunk)
 #define TTB_FLANES 16         // lanes of the two-stage reduction of the per-run log-prefactor sums
@@ -38,7 +40,7 @@ struct TtbChunk {
   int flags;  // bit0 first chunk of the node, bit1 last chunk, bits 8.. number of children
   int src[TTB_CB];
   int cnode[TTB_CB];
-  int pad[2];
+  int lo[TTB_CB];  // site-specific models: interpolation bracket of child b's branch (patched by ss_patch_chunks_kernel)
 };
 
 struct TtbDev {
@@ -74,7 +76,9 @@ struct TtbDev {
   const double* ss_Pi;    // [q][ld]
   const int* ss_lo;       // [n_nodes] lower grid index of the interpolation bracket of every branch length
   const double* ss_w;     // [n_nodes] (t - t_lo)/(t_hi - t_lo), or < 0: evaluate exp(Qt) exactly
-  const double* ss_E;     // [ss_ngrid][q][ld] exp(t_g mu_a lambda_k(a)) on the grid: no exp in the level kernels
+  const double2* ss_rec;  // [n_nodes] {ss_w, t}: 16-byte records the level kernels stage with one bulk copy per child
+  const double* ss_E;     // [tiles][ss_ngrid][q][128] exp(t_g mu_a lambda_k(a)) on the grid, tile-blocked like the messages:
+                          // the two grid rows of a branch are one contiguous 2q KB block per tile (no exp in the level kernels)
   const double* ss_grid;  // [ss_ngrid] the grid itself (branch objective at trial lengths)
   int ss_ngrid;
   double ss_tmax;         // interpolate while t < ss_tmax (= 10 / rate_scale), 0 = never
@@ -228,7 +232,7 @@ __global__ void tip_table_kernel(TtbDev p, const int* __restrict__ tip_nodes) {
 // The up-message is clamped at 1e-12 (:406), the matrix itself is not clamped.
 // Per-thread view: this thread's pattern column of the pattern-contiguous model planes.
 // ---------------------------------------------------------------------------------------
-template <int Q>
+template <int Q, bool REG = false>
 struct SiteModel {
   const double* V;    // V_a[i][k] at V[(i*Q+k)*vs]
   const double* Vi;   // Vinv_a[k][j] at Vi[(k*Q+j)*vs]
@@ -236,23 +240,62 @@ struct SiteModel {
   const double* lam;
   double mu;
   long long ld;
+  const double* E;    // this pattern's column of the grid table
+  // REG: this pattern's eigen-system held in registers for the whole block (2*Q*Q doubles; Q <= 5).
+  // The level kernels handle one pattern per thread for a whole run of nodes, so the 2*Q*Q shared-memory
+  // loads per matvec pair of the staged variant (the measured limiter at q = 5) disappear.
+  double Vr[REG ? Q * Q : 1], Vir[REG ? Q * Q : 1];
+  __device__ SiteModel() {}
   // model planes read from global memory (fetch / branch kernels)
   __device__ SiteModel(const TtbDev& p, long long a)
-      : V(p.ss_V + a), Vi(p.ss_Vinv + a), vs(p.ld), lam(p.ss_eig + a), mu(p.ss_mu[a]), ld(p.ld), E(p.ss_E + a) {}
-  // V / Vinv of this block's pattern tile staged in shared memory (level kernels)
+      : V(p.ss_V + a), Vi(p.ss_Vinv + a), vs(p.ld), lam(p.ss_eig + a), mu(p.ss_mu[a]), ld(p.ld), E(e_column(p, a)) {}
+  // V / Vinv of this block's pattern tile staged in shared memory (level kernels, Q > 5)
   __device__ SiteModel(const TtbDev& p, long long a, const double* smem_model, int tid)
       : V(smem_model + tid), Vi(smem_model + Q * Q * TTB_TILE + tid), vs(TTB_TILE), lam(p.ss_eig + a), mu(p.ss_mu[a]), ld(p.ld),
-        E(p.ss_E + a) {}
-  const double* E;   // this pattern's column of the grid table
+        E(e_column(p, a)) {}
+  // this pattern's column of the tile-blocked grid table: row (g, k) at E[(g*Q + k) * TTB_TILE]
+  __device__ static __forceinline__ const double* e_column(const TtbDev& p, long long a) {
+    return p.ss_E + (size_t)(a / TTB_TILE) * ((size_t)p.ss_ngrid * Q * TTB_TILE) + (size_t)(a % TTB_TILE);
+  }
+  // level kernels: registers (REG) or the staged tile
+  __device__ __forceinline__ void init_level(const TtbDev& p, long long a, bool act, const double* smem_model, int tid) {
+    lam = p.ss_eig + a; ld = p.ld; E = e_column(p, a);
+    mu = act ? p.ss_mu[a] : 0.0;
+    if constexpr (REG) {
+      V = Vi = nullptr; vs = 0;
+#pragma unroll
+      for (int r = 0; r < Q * Q; ++r) {
+        Vr[r] = act ? __ldg(p.ss_V + (size_t)r * p.ld + a) : 0.0;
+        Vir[r] = act ? __ldg(p.ss_Vinv + (size_t)r * p.ld + a) : 0.0;
+      }
+    } else {
+      V = smem_model + tid; Vi = smem_model + Q * Q * TTB_TILE + tid; vs = TTB_TILE;
+    }
+  }
+  __device__ __forceinline__ double v(int r) const { if constexpr (REG) return Vr[r]; else return V[(size_t)r * vs]; }
+  __device__ __forceinline__ double vi(int r) const { if constexpr (REG) return Vir[r]; else return Vi[(size_t)r * vs]; }
   __device__ __forceinline__ void efac_at(double t, int lo, double w, double (&e)[Q]) const {
     if (w < 0.0) {
 #pragma unroll
       for (int k = 0; k < Q; ++k) e[k] = exp(t * mu * __ldg(lam + (size_t)k * ld));
     } else {
-      const double* Elo = E + (size_t)lo * Q * ld;
+      const double* Elo = E + (size_t)lo * Q * TTB_TILE;
 #pragma unroll
       for (int k = 0; k < Q; ++k) {
-        const double elo = __ldg(Elo + (size_t)k * ld), ehi = __ldg(Elo + (size_t)(Q + k) * ld);
+        const double elo = __ldg(Elo + k * TTB_TILE), ehi = __ldg(Elo + (Q + k) * TTB_TILE);
+        e[k] = elo + (ehi - elo) * w;
+      }
+    }
+  }
+  // the same from the two grid rows staged in shared memory (rows = this thread's column of [2][Q][128])
+  __device__ __forceinline__ void efac_staged(double t, double w, const double* rows, double (&e)[Q]) const {
+    if (w < 0.0) {
+#pragma unroll
+      for (int k = 0; k < Q; ++k) e[k] = exp(t * mu * __ldg(lam + (size_t)k * ld));
+    } else {
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        const double elo = rows[k * TTB_TILE], ehi = rows[(Q + k) * TTB_TILE];
         e[k] = elo + (ehi - elo) * w;
       }
     }
@@ -267,14 +310,14 @@ struct SiteModel {
     for (int k = 0; k < Q; ++k) {
       double acc = 0.0;
 #pragma unroll
-      for (int i = 0; i < Q; ++i) acc = fma(S[i], V[(size_t)(i * Q + k) * vs], acc);
+      for (int i = 0; i < Q; ++i) acc = fma(S[i], v(i * Q + k), acc);
       wk[k] = acc * e[k];
     }
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
       double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < Q; ++k) acc = fma(wk[k], Vi[(size_t)(k * Q + j) * vs], acc);
+      for (int k = 0; k < Q; ++k) acc = fma(wk[k], vi(k * Q + j), acc);
       U[j] = clamp ? fmax(TTB_TINY, acc) : acc;
     }
   }
@@ -285,18 +328,28 @@ struct SiteModel {
     for (int k = 0; k < Q; ++k) {
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < Q; ++j) acc = fma(Vi[(size_t)(k * Q + j) * vs], O[j], acc);
+      for (int j = 0; j < Q; ++j) acc = fma(vi(k * Q + j), O[j], acc);
       wk[k] = acc * e[k];
     }
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
       double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < Q; ++k) acc = fma(V[(size_t)(i * Q + k) * vs], wk[k], acc);
+      for (int k = 0; k < Q; ++k) acc = fma(v(i * Q + k), wk[k], acc);
       msg[i] = acc;
     }
   }
 };
+// site-specific level kernels keep the eigen-system in registers up to this alphabet size
+#define TTB_SS_REG_MAXQ 5
+// ... and then the level kernels also stage, per child, the two grid rows of its branch (2q KB per tile, in the
+// stage's P area) and its {w, t} record (16 bytes, in the TU area): no global load is left on the consumers' path.
+template <int Q, bool SS>
+__host__ __device__ constexpr bool ss_staged() { return SS && Q <= TTB_SS_REG_MAXQ; }
+template <int Q, bool SS>
+__host__ __device__ inline int stage_pq(int pq) { return ss_staged<Q, SS>() ? 2 * Q * TTB_TILE : pq; }
+template <int Q, bool SS>
+__host__ __device__ inline int stage_tu(int tu_stride) { return ss_staged<Q, SS>() ? 2 : tu_stride; }
 
 // ---------------------------------------------------------------------------------------
 // N2: joint ML reconstruction.  Reference: TreeAnc._ml_anc_joint, treeanc.py:934-1080.
@@ -416,12 +469,22 @@ __global__ void __launch_bounds__(TTB_BLOCK) joint_pre_level_kernel(TtbDev p, co
 // E[g][k][a] = exp(t_g * mu_a * lambda_k(a)): the eigen-factor of gtr_site_specific._expQt (:363) on the
 // interpolation grid (:336-344).  One thread per (g, k, a).
 static __global__ void ss_grid_table_kernel(TtbDev p, double* __restrict__ E) {
-  const long long n = (long long)p.ss_ngrid * p.q * p.ld;
+  const long long n = (long long)p.tiles * p.ss_ngrid * p.q * TTB_TILE;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long a = i % p.ld;
-    const int k = (int)((i / p.ld) % p.q), g = (int)(i / (p.ld * p.q));
+    const int lane = (int)(i % TTB_TILE);
+    const int k = (int)((i / TTB_TILE) % p.q), g = (int)((i / ((long long)TTB_TILE * p.q)) % p.ss_ngrid);
+    const long long a = (i / ((long long)TTB_TILE * p.q * p.ss_ngrid)) * TTB_TILE + lane;
     E[i] = (a < p.Lp) ? exp(p.ss_grid[g] * p.ss_mu[a] * p.ss_eig[(size_t)k * p.ld + a]) : 1.0;
   }
+}
+
+// Site-specific models: write every child's interpolation bracket into its chunk descriptor, so the producer
+// warp knows which grid rows to stage without a dependent global load (run when branch lengths change).
+static __global__ void ss_patch_chunks_kernel(TtbChunk* __restrict__ chunks, int n_chunks, const int* __restrict__ ss_lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_chunks) return;
+  const int nch = chunks[i].flags >> 8;
+  for (int b = 0; b < TTB_CB; ++b) chunks[i].lo[b] = b < nch ? ss_lo[chunks[i].cnode[b]] : 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -442,7 +505,7 @@ struct Pipe {
     return rows * TTB_TILE * 8 + CB * pq * 8 + CB * tu_stride * 8 + 2 * CB * TTB_TILE + 32;
   }
   __host__ static size_t smem_bytes(int rows, int pq, int tu_stride, bool site_specific = false) {
-    return 128 + (size_t)STAGES * stage_size(rows, pq, tu_stride) + (site_specific ? (size_t)2 * Q * Q * TTB_TILE * 8 : 0);
+    return 128 + (size_t)STAGES * stage_size(rows, pq, tu_stride) + ((site_specific && Q > TTB_SS_REG_MAXQ) ? (size_t)2 * Q * Q * TTB_TILE * 8 : 0);
   }
   __device__ Pipe(unsigned char* smem, int rows, int pq, int tu_stride) {
     full = reinterpret_cast<uint64_t*>(smem);
@@ -497,14 +560,17 @@ struct Pipe {
 
 // Chunk descriptor held in registers as scalars (no local-memory arrays).
 struct Chunk {
-  int out, flags, src0, src1, cnode0, cnode1;
+  int out, flags, src0, src1, cnode0, cnode1, lo0, lo1;
   __device__ __forceinline__ int nch() const { return flags >> 8; }
+  __device__ __forceinline__ int lo(int b) const { return b ? lo1 : lo0; }
+  // staged grid rows of child b: children of one chunk with the same bracket share one copy
+  __device__ __forceinline__ int erow(int b) const { return (b && lo1 != lo0) ? 1 : 0; }
   __device__ __forceinline__ int src(int b) const { return b ? src1 : src0; }
   __device__ __forceinline__ int cnode(int b) const { return b ? cnode1 : cnode0; }
 };
 __device__ __forceinline__ Chunk chunk_from(const int4 a, const int4 b) {
   Chunk c;
-  c.out = a.x; c.flags = a.y; c.src0 = a.z; c.src1 = a.w; c.cnode0 = b.x; c.cnode1 = b.y;
+  c.out = a.x; c.flags = a.y; c.src0 = a.z; c.src1 = a.w; c.cnode0 = b.x; c.cnode1 = b.y; c.lo0 = b.z; c.lo1 = b.w;
   return c;
 }
 __device__ __forceinline__ Chunk load_chunk_global(const TtbChunk* __restrict__ c) {
@@ -523,11 +589,13 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
 template <int Q, bool SS, bool JOINT = false>
-__global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+__global__ void __launch_bounds__(TTB_LEVEL_THREADS, (SS && Q <= 5) ? 2 : 1) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles, int fbase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int RPC = Q;  // rows per child (the log-prefactors never travel: see Fpart)
-  Pipe<Q> pipe(smem_raw, Pipe<Q>::CB * RPC, p.pq, p.tu_stride);
+  constexpr bool EST = ss_staged<Q, SS>();   // site-specific, grid rows + branch record staged per child
+  constexpr int EROWS = 2 * Q * TTB_TILE;
+  Pipe<Q> pipe(smem_raw, Pipe<Q>::CB * RPC, stage_pq<Q, SS>(p.pq), stage_tu<Q, SS>(p.tu_stride));
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
   const int n_chunks = k1 - k0;
@@ -539,17 +607,17 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
   if (tid == 0) pipe.init();
   __syncthreads();
 
-  auto issue = [&](int u) {  // executed by warp 0: fill the stage of chunk number u
+  auto issue = [&](int u, const Chunk& c) {  // executed by the producer warp: fill the stage of chunk number u
     const int s = u % Pipe<Q>::STAGES;
-    const Chunk c = load_chunk_global(chunks + k0 + u);
     pipe.producer_acquire(u);
     uint64_t* bar = pipe.full + s;
     const int nch = c.nch();
     uint32_t bytes = 32;
     for (int b = 0; b < nch; ++b) {
-      if (SS)  // site-specific: the transition matrices are per pattern, nothing per branch to stage
+      if (SS) {  // site-specific: the transition matrices are per pattern; per branch only the grid rows + record
         bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8) : (uint32_t)cols;
-      else
+        if (EST) bytes += 16u + ((b == 0 || c.lo1 != c.lo0) ? (uint32_t)(EROWS * 8) : 0u);
+      } else
         bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8 + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
     }
     if (lane == 0) {
@@ -557,10 +625,16 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
       tma_load_1d((void*)pipe.desc(s), chunks + k0 + u, 32, bar);
     }
     __syncwarp();
-    for (int job = lane; job < nch * 2; job += 32) {
-      const int b = job >> 1, r = job & 1;
+    for (int job = lane; job < nch * 3; job += 32) {
+      const int b = job / 3, r = job % 3;
       const int src = c.src(b);
-      if (src >= 0) {
+      if (r == 2) {
+        if (EST) {
+          tma_load_1d(pipe.TU(s) + b * 2, p.ss_rec + c.cnode(b), 16, bar);
+          if (b == 0 || c.lo1 != c.lo0)
+            tma_load_1d(pipe.P(s) + c.erow(b) * EROWS, p.ss_E + ((size_t)tile * p.ss_ngrid + c.lo(b)) * (Q * TTB_TILE), EROWS * 8, bar);
+        }
+      } else if (src >= 0) {
         if (r == 0)   // the child's q rows of this tile are one contiguous block
           tma_load_1d(pipe.rows(s) + (b * RPC) * TTB_TILE, p.S + msg_off<Q>(p, src, a0), Q * TTB_TILE * 8, bar);
         else if (r == 1 && !SS)
@@ -575,16 +649,28 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
     }
   };
 
-  if (SS && warp == 0) pipe.load_model(p, a0, cols, lane);
-  if (warp == 0)
-    for (int u = 0; u < min(n_chunks, Pipe<Q>::STAGES - 1); ++u) issue(u);
-  if (SS) pipe.wait_model();
+  constexpr bool MREG = Q <= TTB_SS_REG_MAXQ;
+  if (SS && !MREG && warp == 0) pipe.load_model(p, a0, cols, lane);
+  if (warp == TTB_BLOCK / 32) {
+    // Producer warp: runs ahead of the pattern threads by up to STAGES chunks (bounded by the empty
+    // barriers); the descriptor of the next chunk is fetched while the current one is issued, so no
+    // global-memory latency sits on the consumers' path.
+    Chunk c = load_chunk_global(chunks + k0);
+    for (int u = 0; u < n_chunks; ++u) {
+      const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
+      issue(u, c);
+      c = cn;
+    }
+    return;
+  }
+  if (SS && !MREG) pipe.wait_model();
+  SiteModel<Q, MREG> sm;
+  if constexpr (SS) sm.init_level(p, a, act, pipe.model, tid);
 
   double X[Q];
   double Facc = 0.0;   // sum of log-normalisers of this block's nodes (for this thread's pattern)
   int scale = 0, seen = 0;
   for (int u = 0; u < n_chunks; ++u) {
-    if (warp == 0 && u + Pipe<Q>::STAGES - 1 < n_chunks) issue(u + Pipe<Q>::STAGES - 1);
     const int s = u % Pipe<Q>::STAGES;
     pipe.consumer_wait(u);
     const Chunk c = load_chunk_smem(pipe.desc(s));
@@ -599,7 +685,6 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
       for (int b = 0; b < nch; ++b) {
         double U[Q];
         if constexpr (SS) {
-          const SiteModel<Q> sm(p, a, pipe.model, tid);
           double sc[Q], e[Q];
           if (c.src(b) < 0) {
             const int code = pipe.codes(s)[b * TTB_TILE + tid];
@@ -610,7 +695,11 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_level_kernel(TtbDev p, const T
 #pragma unroll
             for (int i = 0; i < Q; ++i) sc[i] = rows[i * TTB_TILE];
             }
-          sm.efac(p, c.cnode(b), e);
+          if constexpr (EST) {
+            const double2 rec = reinterpret_cast<const double2*>(pipe.TU(s))[b];
+            sm.efac_staged(rec.y, rec.x, pipe.P(s) + c.erow(b) * EROWS + tid, e);
+          } else
+            sm.efac(p, c.cnode(b), e);
           sm.up(sc, e, U);
         } else if (c.src(b) < 0) {
           const int code = pipe.codes(s)[b * TTB_TILE + tid];
@@ -993,10 +1082,12 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // Stage rows: [0, Q) parent profile, child b -> rows [Q + b*Q, Q + (b+1)*Q) = S_c.
 // ---------------------------------------------------------------------------------------
 template <int Q, bool TIPS, bool SS>
-__global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+__global__ void __launch_bounds__(TTB_LEVEL_THREADS, (SS && Q <= 5) ? 2 : 1) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Pipe<Q> pipe(smem_raw, Q + Pipe<Q>::CB * Q, p.pq, p.tu_stride);
+  constexpr bool EST = ss_staged<Q, SS>();
+  constexpr int EROWS = 2 * Q * TTB_TILE;
+  Pipe<Q> pipe(smem_raw, Q + Pipe<Q>::CB * Q, stage_pq<Q, SS>(p.pq), stage_tu<Q, SS>(p.tu_stride));
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
   const int n_chunks = k1 - k0;
@@ -1008,18 +1099,18 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
   if (tid == 0) pipe.init();
   __syncthreads();
 
-  auto issue = [&](int u) {  // executed by warp 0
+  auto issue = [&](int u, const Chunk& c) {  // executed by the producer warp
     const int s = u % Pipe<Q>::STAGES;
-    const Chunk c = load_chunk_global(chunks + k0 + u);
     pipe.producer_acquire(u);
     uint64_t* bar = pipe.full + s;
     const int nch = c.nch();
     const bool first = c.flags & 1;
     uint32_t bytes = 32 + (first ? (uint32_t)(Q * TTB_TILE * 8) : 0u);
     for (int b = 0; b < nch; ++b) {
-      if (SS)
+      if (SS) {
         bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8 + cols) : (uint32_t)(2 * cols);
-      else
+        if (EST) bytes += 16u + ((b == 0 || c.lo1 != c.lo0) ? (uint32_t)(EROWS * 8) : 0u);
+      } else
         bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8 + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
     }
     if (lane == 0) {
@@ -1034,7 +1125,13 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
       const int b = job >> 2, r = job & 3;
       const int src = c.src(b);
       if (r == 3) {
-        if (!SS) tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
+        if (!SS)
+          tma_load_1d(pipe.P(s) + b * p.pq, p.P + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
+        else if (EST) {
+          tma_load_1d(pipe.TU(s) + b * 2, p.ss_rec + c.cnode(b), 16, bar);
+          if (b == 0 || c.lo1 != c.lo0)
+            tma_load_1d(pipe.P(s) + c.erow(b) * EROWS, p.ss_E + ((size_t)tile * p.ss_ngrid + c.lo(b)) * (Q * TTB_TILE), EROWS * 8, bar);
+        }
       } else if (src >= 0) {
         if (r == 0)
           tma_load_1d(pipe.rows(s) + (Q + b * Q) * TTB_TILE, p.S + msg_off<Q>(p, src, a0), Q * TTB_TILE * 8, bar);
@@ -1052,15 +1149,27 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
     }
   };
 
-  if (SS && warp == 0) pipe.load_model(p, a0, cols, lane);
-  if (warp == 0)
-    for (int u = 0; u < min(n_chunks, Pipe<Q>::STAGES - 1); ++u) issue(u);
-  if (SS) pipe.wait_model();
+  constexpr bool MREG = Q <= TTB_SS_REG_MAXQ;
+  if (SS && !MREG && warp == 0) pipe.load_model(p, a0, cols, lane);
+  if (warp == TTB_BLOCK / 32) {
+    // Producer warp: runs ahead of the pattern threads by up to STAGES chunks (bounded by the empty
+    // barriers); the descriptor of the next chunk is fetched while the current one is issued, so no
+    // global-memory latency sits on the consumers' path.
+    Chunk c = load_chunk_global(chunks + k0);
+    for (int u = 0; u < n_chunks; ++u) {
+      const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
+      issue(u, c);
+      c = cn;
+    }
+    return;
+  }
+  if (SS && !MREG) pipe.wait_model();
+  SiteModel<Q, MREG> sm;
+  if constexpr (SS) sm.init_level(p, a, act, pipe.model, tid);
 
   double Mp[Q];
   unsigned int ndiff = 0, ndiff_tip = 0;   // changed states of internal nodes / of tips
   for (int u = 0; u < n_chunks; ++u) {
-    if (warp == 0 && u + Pipe<Q>::STAGES - 1 < n_chunks) issue(u + Pipe<Q>::STAGES - 1);
     const int s = u % Pipe<Q>::STAGES;
     pipe.consumer_wait(u);
     const Chunk c = load_chunk_smem(pipe.desc(s));
@@ -1087,7 +1196,6 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
         int best = 0;
         if constexpr (SS) {
           // site-specific model: per-pattern eigen-system instead of a staged exp(Qt)
-          const SiteModel<Q> sm(p, a, pipe.model, tid);
           double U[Q], Sc[Q], O[Q], e[Q], msg[Q];
           if (TIPS && src < 0) {
             const int code = pipe.codes(s)[b * TTB_TILE + tid];
@@ -1098,7 +1206,11 @@ __global__ void __launch_bounds__(TTB_BLOCK) pre_level_kernel(TtbDev p, const Tt
 #pragma unroll
             for (int i = 0; i < Q; ++i) Sc[i] = rows[i * TTB_TILE];
           }
-          sm.efac(p, c.cnode(b), e);
+          if constexpr (EST) {
+            const double2 rec = reinterpret_cast<const double2*>(pipe.TU(s))[b];
+            sm.efac_staged(rec.y, rec.x, pipe.P(s) + c.erow(b) * EROWS + tid, e);
+          } else
+            sm.efac(p, c.cnode(b), e);
           sm.up(Sc, e, U);
           outgroup_message<Q>(Mp, U, O);
           sm.down(O, e, msg);

@@ -10,8 +10,12 @@
 namespace {
 constexpr int Q = TTB_Q;
 
-size_t post_smem(const TtbDev& d, bool ss = false) { return Pipe<Q>::smem_bytes(Pipe<Q>::CB * Q, d.pq, d.tu_stride, ss); }
-size_t pre_smem(const TtbDev& d, bool ss = false) { return Pipe<Q>::smem_bytes(Q + Pipe<Q>::CB * Q, d.pq, d.tu_stride, ss); }
+size_t level_smem(int rows, const TtbDev& d, bool ss) {
+  return ss ? Pipe<Q>::smem_bytes(rows, stage_pq<Q, true>(d.pq), stage_tu<Q, true>(d.tu_stride), true)
+            : Pipe<Q>::smem_bytes(rows, d.pq, d.tu_stride, false);
+}
+size_t post_smem(const TtbDev& d, bool ss = false) { return level_smem(Pipe<Q>::CB * Q, d, ss); }
+size_t pre_smem(const TtbDev& d, bool ss = false) { return level_smem(Q + Pipe<Q>::CB * Q, d, ss); }
 
 constexpr bool HAS_SS = (Q <= 8);   // site-specific models: nucleotide-sized alphabets only
 
@@ -60,7 +64,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   int fbase = l0 ? pl.post_levels[0].n_groups : 0;
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
-    post_level_kernel<Q, SS><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, psm, s>>>(d, pl.d_post_chunks,
+    post_level_kernel<Q, SS><<<(unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s>>>(d, pl.d_post_chunks,
                                                                                              pl.d_post_group_ptr + L.group_off, tiles, fbase);
     fbase += L.n_groups;
     ++nk;
@@ -80,9 +84,9 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
       const TtbLevelLaunch& L = pl.pre_levels[l];
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
       if (pl.tips)
-        pre_level_kernel<Q, true, SS><<<grid, TTB_BLOCK, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
+        pre_level_kernel<Q, true, SS><<<grid, TTB_LEVEL_THREADS, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
       else
-        pre_level_kernel<Q, false, SS><<<grid, TTB_BLOCK, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
+        pre_level_kernel<Q, false, SS><<<grid, TTB_LEVEL_THREADS, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
       ++nk;
     }
   }
@@ -121,7 +125,7 @@ int enqueue_joint_q(const TtbPassPlan& pl, cudaStream_t s, int trace) {
   }
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
-    post_level_kernel<Q, false, true><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, psm, s>>>(d, pl.d_post_chunks,
+    post_level_kernel<Q, false, true><<<(unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s>>>(d, pl.d_post_chunks,
                                                                                                       pl.d_post_group_ptr + L.group_off, tiles, 0);
     ++nk;
   }
