@@ -232,6 +232,9 @@ __global__ void tip_table_kernel(TtbDev p, const int* __restrict__ tip_nodes) {
 // The up-message is clamped at 1e-12 (:406), the matrix itself is not clamped.
 // Per-thread view: this thread's pattern column of the pattern-contiguous model planes.
 // ---------------------------------------------------------------------------------------
+// max(lo, x) as one compare + select (fmax's NaN handling costs ~8 instructions per call in fp64)
+__device__ __forceinline__ double at_least(double x, double lo) { return x > lo ? x : lo; }
+
 template <int Q, bool REG = false>
 struct SiteModel {
   const double* V;    // V_a[i][k] at V[(i*Q+k)*vs]
@@ -274,10 +277,14 @@ struct SiteModel {
   }
   __device__ __forceinline__ double v(int r) const { if constexpr (REG) return Vr[r]; else return V[(size_t)r * vs]; }
   __device__ __forceinline__ double vi(int r) const { if constexpr (REG) return Vir[r]; else return Vi[(size_t)r * vs]; }
+  // exact eigen-factors (t * rate_scale >= 10 or approximate=False): rare, kept out of line so the
+  // inlined exp() bodies do not inflate the level kernels' register pressure
+  __device__ __noinline__ static void efac_exact(double tmu, const double* lam, long long ld, double* e) {
+    for (int k = 0; k < Q; ++k) e[k] = exp(tmu * __ldg(lam + (size_t)k * ld));
+  }
   __device__ __forceinline__ void efac_at(double t, int lo, double w, double (&e)[Q]) const {
     if (w < 0.0) {
-#pragma unroll
-      for (int k = 0; k < Q; ++k) e[k] = exp(t * mu * __ldg(lam + (size_t)k * ld));
+      efac_exact(t * mu, lam, ld, e);
     } else {
       const double* Elo = E + (size_t)lo * Q * TTB_TILE;
 #pragma unroll
@@ -290,8 +297,7 @@ struct SiteModel {
   // the same from the two grid rows staged in shared memory (rows = this thread's column of [2][Q][128])
   __device__ __forceinline__ void efac_staged(double t, double w, const double* rows, double (&e)[Q]) const {
     if (w < 0.0) {
-#pragma unroll
-      for (int k = 0; k < Q; ++k) e[k] = exp(t * mu * __ldg(lam + (size_t)k * ld));
+      efac_exact(t * mu, lam, ld, e);
     } else {
 #pragma unroll
       for (int k = 0; k < Q; ++k) {
@@ -318,7 +324,7 @@ struct SiteModel {
       double acc = 0.0;
 #pragma unroll
       for (int k = 0; k < Q; ++k) acc = fma(wk[k], vi(k * Q + j), acc);
-      U[j] = clamp ? fmax(TTB_TINY, acc) : acc;
+      U[j] = clamp ? at_least(acc, TTB_TINY) : acc;
     }
   }
   // parent -> child: msg[i] = sum_j P[i][j] O[j]
@@ -589,7 +595,7 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
 template <int Q, bool SS, bool JOINT = false>
-__global__ void __launch_bounds__(TTB_LEVEL_THREADS, (SS && Q <= 5) ? 2 : 1) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? 168 : 255) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles, int fbase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int RPC = Q;  // rows per child (the log-prefactors never travel: see Fpart)
@@ -668,7 +674,9 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS, (SS && Q <= 5) ? 2 : 1) pos
   if constexpr (SS) sm.init_level(p, a, act, pipe.model, tid);
 
   double X[Q];
-  double Facc = 0.0;   // sum of log-normalisers of this block's nodes (for this thread's pattern)
+  // sum of log-normalisers of this block's nodes (for this thread's pattern), kept as Facc + log(Zprod):
+  // the normalisers are multiplied up and one log is taken whenever the product leaves [1e-150, 1e150]
+  double Facc = 0.0, Zprod = 1.0;
   int scale = 0, seen = 0;
   for (int u = 0; u < n_chunks; ++u) {
     const int s = u % Pipe<Q>::STAGES;
@@ -770,10 +778,19 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS, (SS && Q <= 5) ? 2 : 1) pos
       double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
 #pragma unroll
       for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j] * inv;
-      Facc += log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
+      if (scale) Facc -= scale * (256.0 * 0.693147180559945309417232121458);
+      if (Z < 1e-150 || Z > 1e150) {
+        Facc += log(Z);
+      } else {
+        Zprod *= Z;
+        if (Zprod < 1e-150 || Zprod > 1e150) {
+          Facc += log(Zprod);
+          Zprod = 1.0;
+        }
+      }
     }
   }
-  if (!JOINT && act) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc;
+  if (!JOINT && act) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc + log(Zprod);
 }
 
 // Postorder level 1: every child is a tip, so there is nothing to stream in but one code byte
@@ -1082,7 +1099,7 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // Stage rows: [0, Q) parent profile, child b -> rows [Q + b*Q, Q + (b+1)*Q) = S_c.
 // ---------------------------------------------------------------------------------------
 template <int Q, bool TIPS, bool SS>
-__global__ void __launch_bounds__(TTB_LEVEL_THREADS, (SS && Q <= 5) ? 2 : 1) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? 168 : 255) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool EST = ss_staged<Q, SS>();
@@ -1178,7 +1195,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS, (SS && Q <= 5) ? 2 : 1) pre
       if (c.flags & 1) {
         const double* m = pipe.rows(s) + tid;
 #pragma unroll
-        for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, m[j * TTB_TILE]);
+        for (int j = 0; j < Q; ++j) Mp[j] = at_least(m[j * TTB_TILE], TTB_TINY);
       }
       for (int b = 0; b < nch; ++b) {
         const int src = c.src(b);
