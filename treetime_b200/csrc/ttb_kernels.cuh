@@ -552,15 +552,21 @@ struct Pipe {
   __device__ const int4* desc(int s) const { return reinterpret_cast<const int4*>(base + (size_t)s * stage_bytes + off_desc); }
   // Producer side: the stage used by chunk number u (0-based within the block) is free once all
   // consumer warps released its previous use.
-  __device__ void producer_acquire(int u) const {
-    if (u >= STAGES) mbar_wait(empty + u % STAGES, ((u / STAGES) - 1) & 1);
+  // Ring cursor: stage s of round r (phase = r & 1); advance() walks it without a modulo per chunk.
+  struct Cursor {
+    int s = 0, phase = 0;
+    __device__ __forceinline__ void advance() {
+      if (++s == STAGES) { s = 0; phase ^= 1; }
+    }
+  };
+  __device__ void producer_acquire(const Cursor& c, int u) const {
+    if (u >= STAGES) mbar_wait(empty + c.s, c.phase ^ 1);
   }
-  __device__ void consumer_wait(int u) const { mbar_wait(full + u % STAGES, (u / STAGES) & 1); }
-  __device__ void consumer_release(int u, int lane) const {
+  __device__ void consumer_wait(const Cursor& c) const { mbar_wait(full + c.s, c.phase); }
+  __device__ void consumer_release(const Cursor& c) const {
     // every thread releases for itself: same speed as a warp-elected arrive (measured) and
     // compute-sanitizer racecheck can follow it
-    (void)lane;
-    mbar_arrive(empty + u % STAGES);
+    mbar_arrive(empty + c.s);
   }
 };
 
@@ -613,9 +619,10 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   if (tid == 0) pipe.init();
   __syncthreads();
 
+  typename Pipe<Q>::Cursor cur;
   auto issue = [&](int u, const Chunk& c) {  // executed by the producer warp: fill the stage of chunk number u
-    const int s = u % Pipe<Q>::STAGES;
-    pipe.producer_acquire(u);
+    const int s = cur.s;
+    pipe.producer_acquire(cur, u);
     uint64_t* bar = pipe.full + s;
     const int nch = c.nch();
     uint32_t bytes = 32;
@@ -665,6 +672,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     for (int u = 0; u < n_chunks; ++u) {
       const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
       issue(u, c);
+      cur.advance();
       c = cn;
     }
     return;
@@ -679,8 +687,8 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   double Facc = 0.0, Zprod = 1.0;
   int scale = 0, seen = 0;
   for (int u = 0; u < n_chunks; ++u) {
-    const int s = u % Pipe<Q>::STAGES;
-    pipe.consumer_wait(u);
+    const int s = cur.s;
+    pipe.consumer_wait(cur);
     const Chunk c = load_chunk_smem(pipe.desc(s));
     if (c.flags & 1) {
 #pragma unroll
@@ -690,7 +698,9 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     }
     const int nch = c.nch();
     if (act) {
-      for (int b = 0; b < nch; ++b) {
+#pragma unroll
+      for (int b = 0; b < Pipe<Q>::CB; ++b) {
+        if (b >= nch) break;
         double U[Q];
         if constexpr (SS) {
           double sc[Q], e[Q];
@@ -763,7 +773,8 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
         }
       }
     }
-    pipe.consumer_release(u, lane);  // all smem reads of this stage are done
+    pipe.consumer_release(cur);  // all smem reads of this stage are done
+    cur.advance();
     if (JOINT) {
       if (act && (c.flags & 2)) {
         double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
@@ -1059,7 +1070,9 @@ static __global__ void zero_slots_kernel(TtbDev p) {
 // up-message U:  O ~ max(1e-12, profile_p) / U_c, normalised.  Reference:
 // treeanc.py:895-899 (log(max(TINY, up.marginal_profile)) - marginal_log_Lx, normalize(log=True)).
 // For small alphabets the quotient is formed division-free as Mp[j] * prod_{k != j} U[k].
-template <int Q>
+// NORM = false leaves the message unnormalised (its consumer normalises the product anyway; only used where
+// nothing is clamped in between).
+template <int Q, bool NORM = true>
 __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const double (&U)[Q], double (&O)[Q]) {
   double z = 0.0;
   if (Q <= 8) {
@@ -1082,6 +1095,7 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
       z += O[j];
     }
   }
+  if (!NORM) return;
   const double inv = 1.0 / z;
 #pragma unroll
   for (int j = 0; j < Q; ++j) O[j] *= inv;
@@ -1116,9 +1130,10 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   if (tid == 0) pipe.init();
   __syncthreads();
 
+  typename Pipe<Q>::Cursor cur;
   auto issue = [&](int u, const Chunk& c) {  // executed by the producer warp
-    const int s = u % Pipe<Q>::STAGES;
-    pipe.producer_acquire(u);
+    const int s = cur.s;
+    pipe.producer_acquire(cur, u);
     uint64_t* bar = pipe.full + s;
     const int nch = c.nch();
     const bool first = c.flags & 1;
@@ -1176,6 +1191,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     for (int u = 0; u < n_chunks; ++u) {
       const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
       issue(u, c);
+      cur.advance();
       c = cn;
     }
     return;
@@ -1187,8 +1203,8 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   double Mp[Q];
   unsigned int ndiff = 0, ndiff_tip = 0;   // changed states of internal nodes / of tips
   for (int u = 0; u < n_chunks; ++u) {
-    const int s = u % Pipe<Q>::STAGES;
-    pipe.consumer_wait(u);
+    const int s = cur.s;
+    pipe.consumer_wait(cur);
     const Chunk c = load_chunk_smem(pipe.desc(s));
     const int nch = c.nch();
     if (act) {
@@ -1197,7 +1213,9 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 #pragma unroll
         for (int j = 0; j < Q; ++j) Mp[j] = at_least(m[j * TTB_TILE], TTB_TINY);
       }
-      for (int b = 0; b < nch; ++b) {
+#pragma unroll
+      for (int b = 0; b < Pipe<Q>::CB; ++b) {
+        if (b >= nch) break;
         const int src = c.src(b);
         const double* Pc = pipe.P(s) + b * p.pq;
         double* __restrict__ out;
@@ -1229,7 +1247,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
           } else
             sm.efac(p, c.cnode(b), e);
           sm.up(Sc, e, U);
-          outgroup_message<Q>(Mp, U, O);
+          outgroup_message<Q, (Q > 8)>(Mp, U, O);
           sm.down(O, e, msg);
           double z = 0.0;
 #pragma unroll
@@ -1343,7 +1361,8 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
       }
     }
     if constexpr (Q > 8) fence_proxy_async_smem();  // the stage was written through the generic proxy
-    pipe.consumer_release(u, lane);
+    pipe.consumer_release(cur);
+    cur.advance();
   }
   if (count_diff) {
     ndiff = __reduce_add_sync(0xffffffffu, ndiff);
