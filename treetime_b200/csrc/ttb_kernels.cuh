@@ -284,7 +284,10 @@ struct SiteModel {
   }
   __device__ __forceinline__ void efac_at(double t, int lo, double w, double (&e)[Q]) const {
     if (w < 0.0) {
-      efac_exact(t * mu, lam, ld, e);
+      double ex[Q];   // only this array lives in local memory; e[] stays in registers on the hot path
+      efac_exact(t * mu, lam, ld, ex);
+#pragma unroll
+      for (int k = 0; k < Q; ++k) e[k] = ex[k];
     } else {
       const double* Elo = E + (size_t)lo * Q * TTB_TILE;
 #pragma unroll
@@ -297,7 +300,10 @@ struct SiteModel {
   // the same from the two grid rows staged in shared memory (rows = this thread's column of [2][Q][128])
   __device__ __forceinline__ void efac_staged(double t, double w, const double* rows, double (&e)[Q]) const {
     if (w < 0.0) {
-      efac_exact(t * mu, lam, ld, e);
+      double ex[Q];   // only this array lives in local memory; e[] stays in registers on the hot path
+      efac_exact(t * mu, lam, ld, ex);
+#pragma unroll
+      for (int k = 0; k < Q; ++k) e[k] = ex[k];
     } else {
 #pragma unroll
       for (int k = 0; k < Q; ++k) {
