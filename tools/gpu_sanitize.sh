@@ -7,8 +7,8 @@ import sys; sys.path[:0]=['.','oracle','tests']
 import numpy as np, util, flat_numpy as O
 from treetime_b200 import synth
 from treetime_b200.gtr import GTRSiteSpecific
-def run(gtr, n, L, seed, **kw):
-    tree = synth.random_tree(n, seed=seed, mean_bl=0.01, polytomy_frac=0.3)
+def run(gtr, n, L, seed, mean_bl=0.01, **kw):
+    tree = synth.random_tree(n, seed=seed, mean_bl=mean_bl, polytomy_frac=0.3)
     topo, flat, g = util.make_flat(tree, gtr, L, seed, amb_frac=0.02, amb_chars=('X' if gtr.n_states > 8 else 'N-RY'), **kw)
     eng = util.engine_for(flat, g)
     eng.marginal(); tot,_ = eng.results()
@@ -17,13 +17,17 @@ def run(gtr, n, L, seed, **kw):
     nodes=np.arange(1,flat['parent'].shape[0],dtype=np.int32)
     eng.branch_objective(nodes, np.full(nodes.shape[0],0.01)); eng.branch_hamming(nodes)
     eng.node_array(3,1); eng.all_seq_idx()
-    if not g['site_specific']: eng.mutation_counts()
+    if not g['site_specific']:
+        eng.mutation_counts()
+        eng.joint(); eng.results(); eng.joint(reconstruct_tips=True); eng.results(); eng.all_seq_idx()
+        eng.marginal(); eng.results()
     res = O.marginal(flat, g)
     assert abs(tot-res.total_LH) < 1e-9*abs(res.total_LH)
     print('ok', g['Pi'].shape, tot)
 run(util.nuc_gtr(), 40, 300, 1)
 run(util.random_gtr('aa_nogap', 3), 20, 150, 2)
 run(GTRSiteSpecific.random(L=200, alphabet='nuc', rng=np.random.default_rng(5)), 30, 200, 3, compress=False)
+run(GTRSiteSpecific.random(L=130, alphabet='nuc', rng=np.random.default_rng(6)), 24, 130, 4, mean_bl=3.0, compress=False)   # long branches: exact exp path
 PY
 for tool in memcheck racecheck synccheck; do
   echo "== $tool"
