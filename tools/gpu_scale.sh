@@ -20,3 +20,15 @@ except Exception as e:
     print('N=$N failed', e); print(open('gpurun_out/scale_${TAG}_n$N.err').read()[-1500:])
 PY
 done
+# BASELINE.json configs[4] in full: 8 shards of 3,750 sites of the 100k-tip site-specific workload
+if [ $NMAX -ge 8 ]; then
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29529 bench.py --workload cfg5 --gpus 8 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/scale_${TAG}_cfg5_n8.json 2> gpurun_out/scale_${TAG}_cfg5_n8.err
+  python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/scale_${TAG}_cfg5_n8.json'))
+    print('cfg5 N=8 value=%.4e ms/step=%.2f whole-pass frac %.3f' % (d['value'], d['ms_per_step'], d['roofline']['whole_pass']['frac']))
+except Exception as e:
+    print('cfg5 N=8 failed', e); print(open('gpurun_out/scale_${TAG}_cfg5_n8.err').read()[-1500:])
+PY
+fi
