@@ -164,6 +164,17 @@ int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out);
 int ttb_fetch_mutations(ttb_handle h, uint8_t* root_idx, int32_t max_n, int32_t* node, int32_t* pos, uint8_t* state,
                         int64_t* n);
 
+/* N2: sufficient statistics of the joint branch-length optimisation (TreeAnc.add_branch_state,
+ * treeanc.py:1148-1163; GTR.state_pair, gtr.py:631-705) for n branches given by their child nodes:
+ * counts[b][i][c] = sum of multiplicities of this shard's patterns where the parent's reconstructed state is i
+ * and the child shows c; c is the child's reconstructed state index for internal nodes (and for tips when
+ * tip_states != 0, which needs a TTB_RECONSTRUCT_TIPS pass), otherwise the tip's alignment code, so that the
+ * caller can treat ambiguous characters as the reference does.  first[b][i][c] = first pattern with that pair
+ * (0x7fffffff if none): the reference lists pairs of large alphabets in order of first occurrence.
+ * Rows are `width` wide, width >= max(n_states, n_codes) (n_states with tip_states).  Synchronous. */
+int ttb_branch_state_pairs(ttb_handle h, int32_t n, const int32_t* nodes, int32_t tip_states, int32_t width, double* counts,
+                           int32_t* first);
+
 /* Stream-ordered variants without a host sync: the data is valid after ttb_sync / ttb_results.
  * `out` should be page-locked memory (otherwise the driver stages and the call blocks).  With
  * page-locked INPUT buffers ttb_set_patterns is asynchronous too (when sizes are unchanged): the

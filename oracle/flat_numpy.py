@@ -491,3 +491,90 @@ def joint(flat, gtr, reconstruct_tip_states=False, prev_seq_idx=None):
             N_diff += L
     res.N_diff = N_diff
     return res
+
+
+# ---------------------------------------------------------------------------------------
+# N2: sufficient statistics of the joint branch-length optimisation.
+# Reference: TreeAnc.add_branch_state (treeanc.py:1148-1163) -> GTR.state_pair (gtr.py:631-705):
+# per branch, the multiplicity-weighted number of patterns for every (parent character, child
+# character) pair.  Restated on indices: parent = reconstructed state index, child = reconstructed
+# state index (internal nodes, and tips with tip_states) or the tip's alignment code.
+# ---------------------------------------------------------------------------------------
+PAIR_NONE = 0x7fffffff
+
+
+def branch_pair_tables(flat, seq_idx, tip_states=False):
+    """C[n_nodes-1, q, W] multiplicity sums and F[...] index of the first pattern showing each pair
+    (PAIR_NONE if none), W = q with tip_states else max(q, n_codes); row k belongs to node k+1."""
+    parent, tip_row = flat['parent'], flat['tip_row']
+    mult = np.asarray(flat['multiplicity'], dtype=float)
+    q = flat['code_profiles'].shape[1]
+    W = q if tip_states else max(q, flat['code_profiles'].shape[0])
+    n_nodes = parent.shape[0]
+    L = mult.shape[0]
+    C = np.zeros((n_nodes - 1, q, W))
+    F = np.full((n_nodes - 1, q, W), PAIR_NONE, dtype=np.int32)
+    pos = np.arange(L)
+    for n in range(1, n_nodes):
+        p = np.asarray(seq_idx[parent[n]]).astype(int)
+        if tip_row[n] >= 0 and not tip_states:
+            c = flat['tip_codes'][tip_row[n]].astype(int)
+        else:
+            c = np.asarray(seq_idx[n]).astype(int)
+        np.add.at(C[n - 1], (p, c), mult)
+        np.minimum.at(F[n - 1], (p, c), pos)
+    return C, F
+
+
+def state_pair(alphabet, gap_index, seq_p, seq_ch, pattern_multiplicity, ignore_gaps=False):
+    """GTR.state_pair (gtr.py:631-705) on character arrays -- the quirks included: alphabets of < 10
+    letters count only positions where both characters are letters of the alphabet and list the pairs
+    in alphabet order; larger alphabets map every other character to index 1 and list the pairs in
+    order of first occurrence."""
+    alphabet = [str(a) for a in alphabet]
+    out = []
+    if len(alphabet) < 10:
+        bp = [seq_p == a for a in alphabet]
+        bc = [seq_ch == a for a in alphabet]
+        for n1 in range(len(alphabet)):
+            if gap_index is None or not ignore_gaps or n1 != gap_index:
+                for n2 in range(len(alphabet)):
+                    if gap_index is None or not ignore_gaps or n2 != gap_index:
+                        count = ((bp[n1] & bc[n2]) * pattern_multiplicity).sum()
+                        if count:
+                            out.append(((n1, n2), count))
+    else:
+        num = []
+        for seq in (seq_p, seq_ch):
+            tmp = np.ones(seq.shape[0], dtype=int)
+            for ni, a in enumerate(alphabet):
+                tmp[seq == a] = ni
+            num.append(tmp)
+        acc = {}
+        for i in range(seq_p.shape[0]):
+            if (not ignore_gaps) or (gap_index != num[0][i] and gap_index != num[1][i]):
+                key = (num[0][i], num[1][i])
+                acc[key] = acc.get(key, 0) + pattern_multiplicity[i]
+        out = list(acc.items())
+    return (np.array([x[0] for x in out], dtype=int).reshape(-1, 2) if out else np.zeros((0, 2), dtype=int),
+            np.array([x[1] for x in out], dtype=int))
+
+
+def prob_t_compressed(gtr, seq_pair, multiplicity, t):
+    """GTR.prob_t_compressed(return_log=True), gtr.py:710-745."""
+    if t < 0:
+        return -BIG_NUMBER
+    logQt = np.log(np.maximum(gtr.expQt(t), SUPERTINY_NUMBER))
+    return np.sum(logQt[seq_pair[:, 1], seq_pair[:, 0]] * multiplicity)
+
+
+def optimal_t_compressed(gtr, seq_pair, multiplicity, tol=1e-10):
+    """GTR.optimal_t_compressed(profiles=False), gtr.py:816-925."""
+    from scipy.optimize import minimize_scalar
+    hamming = np.sum(multiplicity[seq_pair[:, 1] != seq_pair[:, 0]]) / np.sum(multiplicity)
+    opt = minimize_scalar(lambda s: -1.0 * prob_t_compressed(gtr, seq_pair, multiplicity, s ** 2),
+                          bracket=[-np.sqrt(MAX_BRANCH_LENGTH), np.sqrt(hamming), np.sqrt(MAX_BRANCH_LENGTH)], tol=tol, method='brent')
+    new_len = opt['x'] ** 2
+    if 'success' in opt and opt['success'] is not True and opt['success'] != True:      # noqa: E712
+        new_len = hamming
+    return new_len

@@ -151,6 +151,12 @@ def run_joint_case(src, gtr, reconstruct_tips=False):
             out['Cx_%d' % i] = np.array(n.joint_Cx)
     out['N_diff_second'] = np.array(tt.infer_ancestral_sequences(marginal=False, reconstruct_tip_states=reconstruct_tips))
     out['N_diff_marginal_after'] = np.array(tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=reconstruct_tips))
+    if not reconstruct_tips:
+        # joint branch-length optimisation (treeanc.py:1176-1243,1449-1473) from a fresh object
+        t2 = refenv.reference_treeanc(newick, aln, gtr, rng_seed=1)
+        t2.optimize_tree(branch_length_mode='joint', max_iter=2, prune_short=False)
+        out['opt_joint_branch_length'] = np.array([n.branch_length for n in t2.tree.find_clades()])
+        out['opt_joint_sequence_LH'] = np.array(t2.tree.unconstrained_sequence_LH)
     name = 'joint_' + src + ('_tips' if reconstruct_tips else '')
     path = os.path.join(OUT, name + '.npz')
     np.savez_compressed(path, **out)

@@ -115,6 +115,12 @@ class OracleEngine(object):
         self.prev_idx = list(seq)
         self.seqs = seq
 
+    def branch_state_pairs(self, nodes, tip_states=False):
+        src = self.res.seq_idx if self.res is not None else self.seqs
+        C, F = O.branch_pair_tables(self.flat, src, tip_states=tip_states)
+        k = np.atleast_1d(nodes).astype(int) - 1
+        return C[k], F[k]
+
     def results_tips(self):
         # share of the last N_diff that came from tips (recomputed: the oracle returns only the total)
         src = self.res.seq_idx if self.res is not None else self.seqs

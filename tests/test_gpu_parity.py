@@ -263,6 +263,49 @@ def test_joint_reconstruction(kind):
     assert abs(e2.results()[1] - nd_ref) <= 2e-3 * nd_ref + 4
 
 
+@pytest.mark.parametrize('kind', ['nuc', 'aa'])
+def test_branch_state_pairs(kind):
+    """N2: ttb_branch_state_pairs against the oracle's restatement of the GTR.state_pair counting."""
+    if kind == 'nuc':
+        tree = synth.random_tree(120, seed=51, mean_bl=0.02, polytomy_frac=0.2); gtr = util.nuc_gtr(); L = 3000; amb = 0.03
+    else:
+        tree = synth.random_tree(40, seed=52, mean_bl=0.05); gtr = util.random_gtr('aa_nogap', 7); L = 500; amb = 0.0
+    topo, flat, g = util.make_flat(tree, gtr, L, 51, amb_frac=amb)
+    eng = util.engine_for(flat, g)
+    nodes = np.arange(1, flat['parent'].shape[0], dtype=np.int32)
+    for tips in (False, True):
+        eng.joint(reconstruct_tips=tips)
+        eng.results()
+        n_nodes = flat['parent'].shape[0]
+        seqs = [None] * n_nodes
+        internal = [n for n in range(n_nodes) if flat['tip_row'][n] < 0]
+        for k, row in zip(internal, eng.all_seq_idx()):
+            seqs[k] = row
+        if tips:
+            tipn = [n for n in range(n_nodes) if flat['tip_row'][n] >= 0]
+            for k, row in zip(tipn, eng.seq_idx(tipn)):
+                seqs[k] = row
+        C, F = eng.branch_state_pairs(nodes, tip_states=tips)
+        Cr, Fr = O.branch_pair_tables(flat, seqs, tip_states=tips)       # same sequences: bit-exact integer work
+        assert np.array_equal(C, Cr) and np.array_equal(F, Fr)
+        assert np.allclose(C.sum(axis=(1, 2)), flat['multiplicity'].sum())
+    # a subset, after a marginal pass
+    eng.marginal()
+    eng.results()
+    sub = nodes[::7]
+    C2, F2 = eng.branch_state_pairs(sub)
+    seqs = [None] * n_nodes
+    for k, row in zip(internal, eng.all_seq_idx()):
+        seqs[k] = row
+    Cr, Fr = O.branch_pair_tables(flat, seqs)
+    assert np.array_equal(C2, Cr[sub - 1]) and np.array_equal(F2, Fr[sub - 1])
+    from treetime_b200._lib import TTBError
+    with pytest.raises(TTBError):
+        eng.branch_state_pairs(nodes, tip_states=True)      # the marginal pass did not reconstruct tips
+    with pytest.raises(TTBError):
+        eng.branch_state_pairs([0])
+
+
 def test_api_errors():
     from treetime_b200.engine import Engine
     from treetime_b200._lib import TTBError

@@ -87,6 +87,21 @@ def test_gpu_joint_reconstruction_matches_reference_golden(name):
     assert tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips) == int(zj['N_diff_marginal_after']) or n_bad
 
 
+@pytest.mark.parametrize('name', ['joint_nuc40', 'joint_poly70'])
+def test_gpu_joint_branch_length_optimisation_golden(name):
+    """N2: optimize_tree(branch_length_mode='joint') -- device pair counts + lock-step Brent -- vs the reference."""
+    zj = G.load(name)
+    z = G.load(str(zj['source']))
+    tt = gpu_from_golden(z)
+    tt.optimize_tree(branch_length_mode='joint', max_iter=2, prune_short=False)
+    got = np.array([n.branch_length for n in tt.tree.find_clades()])
+    want = zj['opt_joint_branch_length']
+    # minima located from function values agree to ~sqrt(eps); zero-length branches exactly
+    assert np.allclose(got[1:], want[1:], rtol=5e-6, atol=1e-10)
+    tot = float(zj['opt_joint_sequence_LH'])
+    assert abs(tt.tree.unconstrained_sequence_LH - tot) <= 1e-7 * abs(tot)
+
+
 def test_gpu_site_specific_golden():
     """Site-specific model (reference default: interpolated expQt) against the reference's output."""
     from treetime_b200.gtr import GTRSiteSpecific

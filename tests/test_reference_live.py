@@ -238,8 +238,57 @@ def test_dropin_joint_reconstruction_and_treetime_run_joint():
     # joint after marginal and back
     assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
     assert rt.infer_ancestral_sequences(marginal=False) == dt.infer_ancestral_sequences(marginal=False)
-    # joint branch-length optimisation runs the reference's code on top of the lazily fetched sequences
+    # joint branch-length optimisation: the reference's per-branch code on device pair counts (node.branch_state)
+    for a, b in zip(rt.tree.find_clades(), dt.tree.find_clades()):
+        if a.up is not None:
+            rt.add_branch_state(a)
+            assert np.array_equal(a.branch_state['pair'], b.branch_state['pair'])
+            assert np.array_equal(a.branch_state['multiplicity'], b.branch_state['multiplicity'])
+            assert rt.optimal_branch_length(a) == dt.optimal_branch_length(b)
+    launches = dt._engine.launch_count()
     rt.optimize_tree(branch_length_mode='joint', max_iter=2, prune_short=False)
     dt.optimize_tree(branch_length_mode='joint', max_iter=2, prune_short=False)
+    assert dt._engine.launch_count() > launches
     a = np.array([c.branch_length for c in rt.tree.find_clades()]); b = np.array([c.branch_length for c in dt.tree.find_clades()])
-    assert np.allclose(a[1:], b[1:], rtol=1e-9, atol=1e-14)
+    assert np.array_equal(a[1:], b[1:])
+    # ... and with every branch in one lock-step Brent
+    dt.batched_joint_branch_lengths = True
+    rt.optimize_tree(branch_length_mode='joint', max_iter=2, prune_short=True)
+    dt.optimize_tree(branch_length_mode='joint', max_iter=2, prune_short=True)
+    a = np.array([c.branch_length for c in rt.tree.find_clades()]); b = np.array([c.branch_length for c in dt.tree.find_clades()])
+    # a minimum located from function values is only defined to ~sqrt(eps) relative: the batched objective
+    # sums the same terms in a different order
+    assert a.shape == b.shape and np.allclose(a[1:], b[1:], rtol=5e-6, atol=1e-10)
+
+
+def test_state_pair_restatement_matches_reference():
+    """oracle state_pair / fold_state_pairs == GTR.state_pair for the small- and large-alphabet code paths,
+    with and without ignore_gaps, ambiguous characters included."""
+    refenv.activate()
+    import flat_numpy as O
+    from treetime import GTR as RG
+    from treetime_b200.pairs import fold_state_pairs, NONE
+    rng = np.random.default_rng(5)
+    for name in ('nuc', 'aa'):
+        g = RG.standard('JC69', alphabet=name)
+        ab = [str(c) for c in g.alphabet]
+        chars = sorted(g.profile_map.keys())
+        L = 400
+        sp = rng.choice(ab, size=L)
+        sc = np.where(rng.random(L) < 0.2, rng.choice(chars, size=L), sp)
+        mult = rng.integers(1, 5, size=L).astype(float)
+        for ig in (False, True):
+            ref = g.state_pair(sp, sc, pattern_multiplicity=mult, ignore_gaps=ig)
+            mine = O.state_pair(ab, g.gap_index, sp, sc, mult, ignore_gaps=ig)
+            assert np.array_equal(ref[0], mine[0]) and np.array_equal(ref[1], mine[1])
+            # the device table form: parent state x child code
+            q, W = len(ab), len(chars)
+            C = np.zeros((q, W)); F = np.full((q, W), NONE, dtype=np.int32)
+            pi = np.array([ab.index(c) for c in sp]); ci = np.array([chars.index(c) for c in sc])
+            np.add.at(C, (pi, ci), mult); np.minimum.at(F, (pi, ci), np.arange(L))
+            fp, fm = fold_state_pairs(C, F, ab, chars, g.gap_index, ig)
+            assert np.array_equal(ref[0], fp) and np.array_equal(ref[1], fm)
+            if len(ref[1]):
+                t = 0.1
+                assert O.prob_t_compressed(g, mine[0], mine[1], t) == g.prob_t_compressed(ref[0], ref[1], t, return_log=True)
+                assert O.optimal_t_compressed(g, mine[0], mine[1]) == g.optimal_t_compressed(ref[0], ref[1])

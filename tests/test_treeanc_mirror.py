@@ -157,6 +157,61 @@ def test_mirror_joint_matches_reference_golden(name):
     assert tt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips) == int(zj['N_diff_marginal_after'])
 
 
+def test_mirror_joint_branch_lengths():
+    """N2: optimize_tree(branch_length_mode='joint') -- pair counts from the engine, all branches in one
+    lock-step Brent -- against the oracle's per-branch restatement of GTR.optimal_t_compressed."""
+    import flat_numpy as O
+    from treetime_b200.flatten import flatten_treeanc
+    z = G.load('nuc40')
+    tt = mirror_from_golden(z)
+    tt.infer_ancestral_sequences(marginal=False)
+    topo, flat, g = flatten_treeanc(tt)
+    gt = O.make_gtr(g)
+    res = O.joint(flat, g)
+    ab = [str(c) for c in tt.gtr.alphabet]
+    chars = sorted(tt.gtr.profile_map.keys())
+    want = []
+    for n in range(1, flat['parent'].shape[0]):
+        sp = np.array(ab)[res.seq_idx[flat['parent'][n]]]
+        sc = np.array(chars + ['?'])[flat['tip_codes'][flat['tip_row'][n]]] if flat['tip_row'][n] >= 0 else np.array(ab)[res.seq_idx[n]]
+        pairs, mult = O.state_pair(ab, tt.gtr.gap_index, sp, sc, flat['multiplicity'], ignore_gaps=tt.ignore_gaps)
+        bs = tt._branch_state(topo.nodes[n])
+        assert np.array_equal(bs['pair'], pairs) and np.array_equal(bs['multiplicity'], mult)
+        want.append(O.optimal_t_compressed(gt, pairs, mult))
+    one = tt.optimal_branch_length(topo.nodes[5])
+    assert abs(one - want[4]) <= 5e-6 * max(want[4], 1e-6)       # minima from function values: ~sqrt(eps) relative
+    tt.optimize_branch_lengths_joint()
+    got = np.array([n.branch_length for n in topo.nodes[1:]])
+    assert np.allclose(got, np.maximum(0, want), rtol=5e-6, atol=1e-10)
+    # the full loop terminates and leaves a consistent tree
+    tt2 = mirror_from_golden(z)
+    tt2.optimize_tree(branch_length_mode='joint', max_iter=3, prune_short=True)
+    assert np.isfinite(tt2.tree.unconstrained_sequence_LH) and tt2.sequence_reconstruction == 'joint'
+    # tip without sequence: the reference's error
+    z2 = G.load('nuc40')
+    aln = G.alignment(z2)
+    del aln[sorted(aln)[0]]
+    tt3 = TreeAnc(tree=str(z2['newick']), aln=aln, gtr=G.model(z2), engine_factory=oracle_engine.factory)
+    tt3.infer_ancestral_sequences(marginal=False)
+    from treetime_b200.treeanc import MissingDataError
+    with pytest.raises(MissingDataError):
+        tt3.optimize_branch_lengths_joint()
+    tt3.infer_ancestral_sequences(marginal=False, reconstruct_tip_states=True)
+    tt3.optimize_branch_lengths_joint()
+
+
+@pytest.mark.parametrize('name', ['joint_nuc40', 'joint_poly70'])
+def test_mirror_joint_branch_length_optimisation_golden(name):
+    zj = G.load(name)
+    z = G.load(str(zj['source']))
+    tt = mirror_from_golden(z)
+    tt.optimize_tree(branch_length_mode='joint', max_iter=2, prune_short=False)
+    got = np.array([n.branch_length for n in tt.tree.find_clades()])
+    assert np.allclose(got[1:], zj['opt_joint_branch_length'][1:], rtol=5e-6, atol=1e-10)
+    tot = float(zj['opt_joint_sequence_LH'])
+    assert abs(tt.tree.unconstrained_sequence_LH - tot) <= 1e-7 * abs(tot)
+
+
 def test_mirror_joint_reconstruction():
     """N2 through the mirror API: infer_ancestral_sequences(marginal=False)."""
     z = G.load('nuc40')

@@ -136,7 +136,8 @@ struct ttb_engine {
   DBuf<int> d_mut_node, d_mut_pos, d_ent_row, d_ent_pos;
   DBuf<unsigned long long> d_mut_count;   // d_bstage: packed byte staging for contiguous H2D / D2H
   DBuf<unsigned long long> d_nd;
-  DBuf<int> d_enodes, d_ekinds;
+  DBuf<int> d_enodes, d_ekinds, d_pair_first;
+  DBuf<double> d_pair_counts;
   DBuf<double> d_ets, d_eout;
   double* h_results = nullptr;  // pinned {total, ndiff}
   // page-locked scratch through which small pageable inputs (branch lengths, model, multiplicities)
@@ -299,14 +300,28 @@ void build_sched(ttb_handle h, const std::vector<int>& key, const std::vector<ch
 void build_groups(Sched& sc, int tiles, bool site_specific) {
   sc.group_ptr.clear();
   sc.launches.clear();
-  // site-specific kernels stage a 50 KB model tile per block: longer runs amortise it
-  const long long target_blocks = site_specific ? 148LL * 8 : 148LL * 32;
+  // Site-specific kernels load a per-pattern eigen-system per block (longer runs amortise it) and are
+  // issue-bound, so a partly filled last wave costs its full duration: size the grid of a level to fill
+  // whole waves of the 2 blocks/SM these kernels run at.
+  const long long slots = 148LL * 2;
+  const long long target_blocks = site_specific ? slots * 4 : 148LL * 32;
   const long long max_group = site_specific ? 128 : 32;
   for (size_t l = 0; l + 1 < sc.level_node_begin.size(); ++l) {
     const int nb = sc.level_node_begin[l], ne = sc.level_node_begin[l + 1];
     const int n = ne - nb;
-    long long G = ((long long)n * tiles + target_blocks - 1) / target_blocks;
-    G = std::max(1LL, std::min(max_group, G));
+    long long G;
+    if (site_specific) {
+      long long waves = 4;
+      for (;;) {
+        const long long groups = std::max(1LL, std::min((long long)n, waves * slots / tiles));
+        G = (n + groups - 1) / groups;
+        if (G <= max_group) break;
+        ++waves;
+      }
+    } else {
+      G = ((long long)n * tiles + target_blocks - 1) / target_blocks;
+      G = std::max(1LL, std::min(max_group, G));
+    }
     TtbLevelLaunch L;
     L.group_off = (int)sc.group_ptr.size();
     L.n_groups = 0;
@@ -482,6 +497,8 @@ int ttb_destroy(ttb_handle h) {
   h->d_codes.release();
   h->d_ss_lo.release();
   h->d_ss_rec.release();
+  h->d_pair_first.release();
+  h->d_pair_counts.release();
   h->post.d_chunks.release(); h->pre_int.d_chunks.release(); h->pre_all.d_chunks.release();
   h->d_idx.release();
   h->d_idxtip.release();
@@ -1226,6 +1243,38 @@ int ttb_branch_hamming(ttb_handle h, int32_t n_eval, const int32_t* nodes, const
     for (double m : h->h_mult) s += m;
     *den = s;
   }
+  return 0;
+}
+
+int ttb_branch_state_pairs(ttb_handle h, int32_t n, const int32_t* nodes, int32_t tip_states, int32_t width, double* counts,
+                           int32_t* first) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_states(h)) return rc;
+  if (n <= 0 || !nodes || !counts || !first) return fail(TTB_EINVAL, "ttb_branch_state_pairs: bad arguments");
+  const int need = tip_states ? h->q : std::max(h->q, h->n_codes);
+  if (width < need) return fail(TTB_EINVAL, "ttb_branch_state_pairs: width must be >= max(n_states, n_codes)");
+  bool any_tip = false;
+  for (int k = 0; k < n; ++k) {
+    if (nodes[k] <= 0 || nodes[k] >= h->n_nodes) return fail(TTB_EINVAL, "ttb_branch_state_pairs: node index out of range (the root has no branch)");
+    any_tip |= h->tip_row[nodes[k]] >= 0;
+  }
+  if (tip_states && any_tip && !(h->have_tip_pass || h->have_joint_tips))
+    return fail(TTB_EINVAL, "ttb_branch_state_pairs: tip states requested but the last pass did not reconstruct tips");
+  const size_t bins = (size_t)h->q * width;
+  const size_t smem = bins * (sizeof(double) + sizeof(int));
+  if (smem > 200 * 1024) return fail(TTB_EUNSUPPORTED, "ttb_branch_state_pairs: table too large for shared memory");
+  int rc;
+  if ((rc = h->d_enodes.alloc((size_t)n))) return rc;
+  if ((rc = h->d_pair_counts.alloc((size_t)n * bins))) return rc;
+  if ((rc = h->d_pair_first.alloc((size_t)n * bins))) return rc;
+  CK(cudaMemcpyAsync(h->d_enodes.p, nodes, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(pair_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pair_counts_kernel<<<n, 256, smem, h->stream>>>(h->dev(), h->d_enodes.p, tip_states ? 1 : 0, width, h->d_pair_counts.p, h->d_pair_first.p);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(counts, h->d_pair_counts.p, (size_t)n * bins * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(first, h->d_pair_first.p, (size_t)n * bins * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -1067,6 +1067,42 @@ static __global__ void mutations_kernel(TtbDev p, int max_n, int* __restrict__ o
   }
 }
 
+// N2: parent/child state-pair counts of a batch of branches -- the sufficient statistics of the joint
+// branch-length optimisation (TreeAnc.add_branch_state, treeanc.py:1148-1163; GTR.state_pair, gtr.py:631-705).
+// counts[b][i][c] = sum of multiplicities of the patterns where the parent of nodes[b] is in state i and the
+// child shows c (c = reconstructed state index for internal nodes and, with tip_states, for tips; otherwise
+// the tip's alignment code, so the host can treat ambiguous characters the way the reference does);
+// first[b][i][c] = first such pattern (the reference's large-alphabet path lists pairs in order of first
+// occurrence), 0x7fffffff if none.  One block per branch; W = row width of the tables.
+static __global__ void pair_counts_kernel(TtbDev p, const int* __restrict__ nodes, int tip_states, int W,
+                                          double* __restrict__ counts, int* __restrict__ first) {
+  extern __shared__ __align__(16) unsigned char pc_smem[];
+  const int bins = p.q * W;
+  double* sc = reinterpret_cast<double*>(pc_smem);
+  int* sf = reinterpret_cast<int*>(sc + bins);
+  for (int k = threadIdx.x; k < bins; k += blockDim.x) {
+    sc[k] = 0.0;
+    sf[k] = 0x7fffffff;
+  }
+  __syncthreads();
+  const int n = nodes[blockIdx.x];
+  const uint8_t* pr = p.idx + (size_t)p.int_slot[p.parent[n]] * p.ld;
+  const int row = p.tip_row[n];
+  const uint8_t* ch = row < 0 ? p.idx + (size_t)p.int_slot[n] * p.ld
+                              : (tip_states ? p.idxtip : p.codes) + (size_t)row * p.ld;
+  for (long long a = threadIdx.x; a < p.Lp; a += blockDim.x) {
+    const int i = pr[a], c = ch[a];
+    if (i >= p.q || c >= W) continue;   // 0xff: state not set
+    atomicAdd(sc + i * W + c, p.mult[a]);
+    atomicMin(sf + i * W + c, (int)a);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < bins; k += blockDim.x) {
+    counts[(size_t)blockIdx.x * bins + k] = sc[k];
+    first[(size_t)blockIdx.x * bins + k] = sf[k];
+  }
+}
+
 static __global__ void zero_slots_kernel(TtbDev p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 1024) p.nd_slots[i] = 0ull;

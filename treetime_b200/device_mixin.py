@@ -12,6 +12,7 @@ from .brent import brent_lockstep
 from .dist import default_comm, shard_bounds
 from .flatten import FlatTopology, code_table, encode_chars, gtr_arrays
 from .gtr import infer_gtr_from_counts
+from .pairs import NONE as PAIR_NONE, count_matrices, fold_state_pairs, optimal_t_from_counts
 from .seq_utils import prof2seq
 
 SUBTREE, OUTGROUP, PROFILE = 0, 1, 2
@@ -404,6 +405,89 @@ class DeviceMarginalMixin(object):
             if deltaLH < LHtol:
                 self.logger('TreeAnc.optimize_tree_marginal: deltaLH=%f, stopping iteration.' % deltaLH, 1)
                 break
+        return ttconf.SUCCESS
+
+    # -- joint branch lengths (N2) ---------------------------------------------------------------
+    def _pair_tables(self):
+        """Parent/child pair counts of every branch from the device (ttb_branch_state_pairs), cached until
+        the next reconstruction.  Returns (C[n_nodes-1, q, W], F, tip_states, code characters)."""
+        if 'pairs' not in self._cache:
+            if not self.sequence_reconstruction or self._engine is None:
+                raise Exception('ancestral sequences need to be reconstructed first!')
+            eng, topo = self._engine, self._flat()
+            tip_states = bool(self.reconstructed_tip_sequences)
+            C, F = eng.branch_state_pairs(np.arange(1, topo.n_nodes, dtype=np.int32), tip_states=tip_states)
+            if self.comm.world_size > 1:
+                lo, _ = self._shard()
+                F = np.where(F != PAIR_NONE, F + lo, F)              # global pattern index of the first occurrence
+                C = self.comm.allreduce_sum(C)
+                F = self.comm.allgather(F[None], axis=0).min(axis=0)
+            chars, _, _ = code_table(self.gtr.profile_map, self.gtr.n_states)
+            self._cache['pairs'] = (C, F, tip_states, list(chars) + [None])   # last code = tip without sequence
+        return self._cache['pairs']
+
+    def _branch_state(self, node):
+        """The reference's node.branch_state = {'pair', 'multiplicity'} (treeanc.py:1148-1163) from device counts."""
+        C, F, tip_states, code_chars = self._pair_tables()
+        alphabet = [str(c) for c in self.gtr.alphabet]
+        if node.is_terminal() and not tip_states:
+            if node.name not in self.data.compressed_alignment:
+                raise self._missing_data_error(
+                    "TreeAnc.optimal_branch_length: terminal node alignments required; sequence is missing for leaf: '%s'. "
+                    'Missing terminal sequences can be inferred from sister nodes by rerunning with `reconstruct_tip_states=True` '
+                    'or `--reconstruct-tip-states`' % node.name)
+            cols = code_chars
+        else:
+            cols = alphabet
+        pairs, mult = fold_state_pairs(C[node._fid - 1], F[node._fid - 1], alphabet, cols, self.gtr.gap_index, self.ignore_gaps)
+        return {'pair': pairs, 'multiplicity': mult}
+
+    def add_branch_state(self, node):
+        """treeanc.py:1148-1163."""
+        node.branch_state = self._branch_state(node)
+
+    def optimal_branch_length(self, node):
+        """treeanc.py:1245-1270: optimal length of the branch above `node` given the reconstructed sequences."""
+        if node.up is None:
+            return self.one_mutation
+        bs = self._branch_state(node)
+        q = self.gtr.n_states
+        M = np.zeros((1, q, q))
+        M[0, bs['pair'][:, 0], bs['pair'][:, 1]] = bs['multiplicity']
+        return float(optimal_t_from_counts(self.gtr, M)[0][0])
+
+    def optimize_branch_lengths_joint(self, **kwargs):
+        """treeanc.py:1176-1243 with every branch optimised in one lock-step Brent on the device's pair counts."""
+        self.logger('TreeAnc.optimize_branch_length: running branch length optimization using jointML ancestral sequences', 1)
+        if getattr(self.gtr, 'is_site_specific', False):
+            self._unsupported('joint branch-length optimisation with site-specific models runs in the reference')
+        store_old = kwargs.get('store_old', False)
+        topo = self._flat()
+        C, F, tip_states, code_chars = self._pair_tables()
+        alphabet = [str(c) for c in self.gtr.alphabet]
+        is_tip = np.array([n.is_terminal() for n in topo.nodes[1:]])
+        if not tip_states:
+            for n in topo.nodes[1:]:
+                if n.is_terminal() and n.name not in self.data.compressed_alignment:
+                    self._branch_state(n)                                   # raises the reference's MissingDataError
+        M = count_matrices(C[:, :, :len(alphabet)], alphabet, alphabet, self.gtr.gap_index, self.ignore_gaps)
+        if not tip_states and is_tip.any():
+            M[is_tip] = count_matrices(C[is_tip], alphabet, code_chars, self.gtr.gap_index, self.ignore_gaps)
+        new, self._last_brent = optimal_t_from_counts(self.gtr, M)
+        max_bl = 0
+        for n, t in zip(topo.nodes[1:], new):
+            if store_old:
+                n._old_length = n.branch_length
+            t = max(0, float(t))
+            n.branch_length = t
+            n.mutation_length = t
+            max_bl = max(max_bl, t)
+        if max_bl > 0.15:
+            self.logger("TreeAnc.optimize_branch_lengths_joint: THIS TREE HAS LONG BRANCHES. TreeTime's JOINT IS NOT DESIGNED TO "
+                        "OPTIMIZE LONG BRANCHES; use branch_length_mode='input' or 'marginal'", 0, warn=True)
+        self.tree.root.up = None
+        self.tree.root.dist2root = 0.0
+        self._prepare_nodes()
         return ttconf.SUCCESS
 
     # -- model inference -------------------------------------------------------------------------

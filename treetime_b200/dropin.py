@@ -32,11 +32,19 @@ _hooked = set()
 def _lazy_getattr(node, name):
     """Called only when normal attribute lookup fails (so cached values and everything the
     reference sets itself take precedence)."""
-    if name in _LAZY or name == '_cseq':
+    if name in _LAZY or name == '_cseq' or name == 'branch_state':
         tt = node.__dict__.get('tt')
         if tt is not None and getattr(tt, '_b200_live', False) and '_fid' in node.__dict__:
             try:
-                if name == '_cseq':
+                if name == 'branch_state':
+                    # N2: pair counts of the branch from the device instead of GTR.state_pair on host sequences
+                    if node.up is None or getattr(node, 'mask', None) is not None or tt.gtr.is_site_specific:
+                        raise AttributeError(name)
+                    try:
+                        val = tt._branch_state(node)
+                    except tt._missing_data_error:
+                        raise AttributeError(name)      # the reference raises its own error for a leaf without sequence
+                elif name == '_cseq':
                     if node.is_terminal() and not tt.reconstructed_tip_sequences:
                         raise AttributeError(name)
                     val = tt._node_cseq(node)
@@ -101,7 +109,7 @@ class B200MarginalMixin(DeviceMarginalMixin):
         if self._topo is not None:
             for n in self._topo.nodes:
                 d = n.__dict__
-                for k in ('marginal_subtree_LH', 'marginal_outgroup_LH', 'marginal_profile'):
+                for k in ('marginal_subtree_LH', 'marginal_outgroup_LH', 'marginal_profile', 'branch_state'):
                     d.pop(k, None)
         self._cache = {}
         self._seq_cache = {}
@@ -233,6 +241,28 @@ class B200MarginalMixin(DeviceMarginalMixin):
 
     def get_branch_mutation_matrix(self, node, full_sequence=False):
         return super(DeviceMarginalMixin, self).get_branch_mutation_matrix(node, full_sequence=full_sequence)
+
+    # N2 branch lengths: by default the reference's per-branch code runs on the lazily provided
+    # node.branch_state (bit-identical results, no sequences cross PCIe); with
+    # `batched_joint_branch_lengths = True` all branches are optimised in one lock-step Brent.
+    batched_joint_branch_lengths = False
+
+    def add_branch_state(self, node):
+        if self._b200_live and getattr(node, 'mask', None) is None and not self.gtr.is_site_specific:
+            return DeviceMarginalMixin.add_branch_state(self, node)
+        return super(DeviceMarginalMixin, self).add_branch_state(node)
+
+    def optimal_branch_length(self, node):
+        return super(DeviceMarginalMixin, self).optimal_branch_length(node)
+
+    def optimize_branch_lengths_joint(self, **kwargs):
+        if (self.batched_joint_branch_lengths and self._b200_live and not self.gtr.is_site_specific
+                and not any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades())):
+            try:
+                return DeviceMarginalMixin.optimize_branch_lengths_joint(self, **kwargs)
+            except Unsupported:
+                pass
+        return super(DeviceMarginalMixin, self).optimize_branch_lengths_joint(**kwargs)
 
     def optimize_tree_marginal(self, *args, **kwargs):
         if self._device_ok() is None and not any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):

@@ -40,6 +40,7 @@ class Engine(object):
         self.h = h
         self.n_nodes = 0
         self.n_patterns = 0
+        self.n_codes = 0
         self._keep = {}
 
     def close(self):
@@ -77,6 +78,7 @@ class Engine(object):
         _lib.check(self.lib.ttb_set_patterns(self.h, tip_codes.shape[1], _up(tip_codes), code_profiles.shape[0],
                                              _dp(code_profiles), _dp(multiplicity)))
         self.n_patterns = int(tip_codes.shape[1])
+        self.n_codes = int(code_profiles.shape[0])
 
     def alignment_stats(self, aln, fill_overhangs=False, gap='-', fill='N', ambiguous='N'):
         """Upload the raw ASCII alignment [n_seq, L] (kept resident) and return per column
@@ -100,6 +102,7 @@ class Engine(object):
             self.h, first_pos.shape[0], first_pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _up(const_letter), _ip(tip_seq_row),
             _up(lut), int(missing_code), code_profiles.shape[0], _dp(code_profiles), _dp(multiplicity)))
         self.n_patterns = int(first_pos.shape[0])
+        self.n_codes = int(np.asarray(code_profiles).shape[0])
 
     def set_patterns_sparse(self, ref_codes, entry_row, entry_pos, entry_code, code_profiles, multiplicity):
         """Every tip row = ref_codes except at the listed (tip row, pattern, code) entries."""
@@ -113,6 +116,7 @@ class Engine(object):
                                                     _ip(entry_row), _ip(entry_pos), _up(entry_code), code_profiles.shape[0],
                                                     _dp(code_profiles), _dp(multiplicity)))
         self.n_patterns = int(ref_codes.shape[0])
+        self.n_codes = int(np.asarray(code_profiles).shape[0])
 
     def set_gtr(self, g):
         """g: dict from flatten.gtr_arrays()."""
@@ -256,6 +260,17 @@ class Engine(object):
         T_i = np.empty(q, dtype=np.float64)
         _lib.check(self.lib.ttb_mutation_counts(self.h, _dp(n_ij), _dp(T_i)))
         return n_ij, T_i
+
+    def branch_state_pairs(self, nodes, tip_states=False):
+        """(counts[n, q, W], first[n, q, W]) of ttb_branch_state_pairs: parent-state x child-state (or tip code)
+        multiplicity sums and the first pattern showing each pair; W = q with tip_states else max(q, n_codes)."""
+        nodes = _i32(np.atleast_1d(nodes))
+        q = self.n_states
+        W = q if tip_states else max(q, self.n_codes)
+        counts = np.empty((nodes.shape[0], q, W), dtype=np.float64)
+        first = np.empty((nodes.shape[0], q, W), dtype=np.int32)
+        _lib.check(self.lib.ttb_branch_state_pairs(self.h, nodes.shape[0], _ip(nodes), 1 if tip_states else 0, W, _dp(counts), _ip(first)))
+        return counts, first
 
     def device_bytes(self):
         b = ctypes.c_int64()

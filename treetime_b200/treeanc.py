@@ -294,7 +294,7 @@ class TreeAnc(DeviceMarginalMixin):
 
     def optimize_tree(self, prune_short=True, marginal_sequences=False, branch_length_mode='joint', max_iter=5,
                       infer_gtr=False, pc=1.0, method_anc='probabilistic', **kwargs):
-        """treeanc.py:1384-1473; only the marginal and input modes run on the device path."""
+        """treeanc.py:1384-1473."""
         if branch_length_mode == 'marginal':
             self.optimize_tree_marginal(max_iter=max_iter, infer_gtr=infer_gtr, pc=pc, **kwargs)
             if prune_short:
@@ -307,7 +307,24 @@ class TreeAnc(DeviceMarginalMixin):
             return ttconf.SUCCESS
         elif branch_length_mode != 'joint':
             raise UnknownMethodError("TreeAnc.optimize_tree: `branch_length_mode` should be in ['marginal', 'joint', 'input']")
-        raise NotImplementedError("branch_length_mode='joint' is outside the B200 hot path; use the reference implementation")
+        # joint mode (treeanc.py:1449-1473): reconstruct, optimise every branch on the device's pair counts, repeat
+        self.logger('TreeAnc.optimize_tree: sequences...', 1)
+        self.reconstruct_anc(method=method_anc, infer_gtr=infer_gtr, pc=pc, marginal=marginal_sequences, **kwargs)
+        self.optimize_branch_lengths_joint(store_old=False)
+        n = 0
+        while n < max_iter:
+            n += 1
+            if prune_short:
+                self.prune_short_branches()
+            N_diff = self.reconstruct_anc(method=method_anc, infer_gtr=False, marginal=marginal_sequences, **kwargs)
+            self.logger('TreeAnc.optimize_tree: Iteration %d. #Nuc changed since prev reconstructions: %d' % (n, N_diff), 2)
+            if N_diff < 1:
+                break
+            self.optimize_branch_lengths_joint(store_old=False)
+        self.tree.unconstrained_sequence_LH = (self.tree.sequence_LH * self.data.multiplicity()).sum()
+        self._prepare_nodes()
+        self.logger('TreeAnc.optimize_tree: Unconstrained sequence LH:%f' % self.tree.unconstrained_sequence_LH, 2)
+        return ttconf.SUCCESS
 
     def optimize_branch_lengths(self, **kwargs):
         """Branch-length optimisation in marginal mode (north-star surface name)."""
