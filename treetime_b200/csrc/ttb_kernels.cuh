@@ -232,8 +232,14 @@ __global__ void tip_table_kernel(TtbDev p, const int* __restrict__ tip_nodes) {
 // The up-message is clamped at 1e-12 (:406), the matrix itself is not clamped.
 // Per-thread view: this thread's pattern column of the pattern-contiguous model planes.
 // ---------------------------------------------------------------------------------------
-// max(lo, x) as one compare + select (fmax's NaN handling costs ~8 instructions per call in fp64)
-__device__ __forceinline__ double at_least(double x, double lo) { return x > lo ? x : lo; }
+// max(lo, x) for lo >= 0 and non-NaN x through the integer order of the bit patterns: there is no fp64
+// min/max instruction, fmax() (and `x > lo ? x : lo`, which the compiler turns into it) costs ~10
+// instructions for its NaN handling; this is a 64-bit integer compare + select.  Negative x (sign bit set)
+// compares below every non-negative lo.
+__device__ __forceinline__ double at_least(double x, double lo) {
+  const long long xb = __double_as_longlong(x), lb = __double_as_longlong(lo);
+  return __longlong_as_double(xb > lb ? xb : lb);
+}
 
 template <int Q, bool REG = false>
 struct SiteModel {
