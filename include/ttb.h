@@ -175,6 +175,17 @@ int ttb_fetch_mutations(ttb_handle h, uint8_t* root_idx, int32_t max_n, int32_t*
 int ttb_branch_state_pairs(ttb_handle h, int32_t n, const int32_t* nodes, int32_t tip_states, int32_t width, double* counts,
                            int32_t* first);
 
+/* N4: evolve sequences down the tree on the device (SeqGen.evolve, seqgen.py:38-67): root ~ Pi unless
+ * root_idx[n_patterns] is given, every child state drawn from column (parent state) of exp(Q t_child) with
+ * argmax(cumsum(p) > u) (seqgen.py:19-36).  u comes from `uniforms` ([n_nodes][n_patterns], node order of
+ * ttb_set_tree; pass the reference's draws to reproduce its sequences exactly) or, if null, from a
+ * counter-based Philox4x32-10 stream keyed by `seed` (counter = site, node).  Needs tree, patterns (only their
+ * number and the code table matter; multiplicities should be 1), model and branch lengths.  The tips' states
+ * become the engine's alignment (code = state2code[state]); states_out (optional, [n_nodes][n_patterns])
+ * receives every node's state index.  Synchronous. */
+int ttb_seqgen(ttb_handle h, uint64_t seed, const uint8_t* root_idx, const double* uniforms, const uint8_t* state2code,
+               uint8_t* states_out);
+
 /* Stream-ordered variants without a host sync: the data is valid after ttb_sync / ttb_results.
  * `out` should be page-locked memory (otherwise the driver stages and the call blocks).  With
  * page-locked INPUT buffers ttb_set_patterns is asynchronous too (when sizes are unchanged): the

@@ -578,3 +578,29 @@ def optimal_t_compressed(gtr, seq_pair, multiplicity, tol=1e-10):
     if 'success' in opt and opt['success'] is not True and opt['success'] != True:      # noqa: E712
         new_len = hamming
     return new_len
+
+
+# ---------------------------------------------------------------------------------------
+# N4: SeqGen.  Reference: SeqGen.evolve + sample_from_profile (seqgen.py:19-67), GTR.evolve (gtr.py:997-1025).
+# ---------------------------------------------------------------------------------------
+def seqgen(flat, gtr, uniforms, root_idx=None):
+    """State indices [n_nodes, L] evolved down the tree: root = argmax(cumsum(Pi) > u_0) unless given,
+    child = argmax(cumsum(expQt(t_c)[:, parent state]) > u_c) -- exactly the reference's draw when
+    `uniforms[n]` is the rng.random(L) vector it used for node n."""
+    parent, t = flat['parent'], flat['t']
+    n_nodes = parent.shape[0]
+    L = uniforms.shape[1]
+    states = np.zeros((n_nodes, L), dtype=np.uint8)
+    site = np.arange(L)
+    if root_idx is not None:
+        states[0] = root_idx
+    else:
+        Pi = gtr.Pi
+        prof = Pi.T if Pi.ndim == 2 else np.repeat([Pi], L, axis=0)         # seqgen.py:53-58
+        states[0] = np.argmax(prof.cumsum(axis=1).T > uniforms[0], axis=0)
+    for n in range(1, n_nodes):
+        P = gtr.expQt(t[n])                          # (q, q) or (q, q, L): P[i, j(, a)] = Prob(child i | parent j)
+        sp = states[parent[n]].astype(int)
+        prof = P[:, sp, site].T if P.ndim == 3 else P[:, sp].T               # profile.dot(expQt(t).T) for one-hot profiles
+        states[n] = np.argmax(prof.cumsum(axis=1).T > uniforms[n], axis=0)
+    return states

@@ -121,6 +121,17 @@ class OracleEngine(object):
         k = np.atleast_1d(nodes).astype(int) - 1
         return C[k], F[k]
 
+    def seqgen(self, seed, state2code, root_idx=None, uniforms=None, return_states=True):
+        L = self.n_patterns
+        if uniforms is None:        # the device uses Philox; any stream of uniforms has the same distribution
+            uniforms = np.random.default_rng(seed).random((self.n_nodes, L))
+        st = O.seqgen(self.flat, O.make_gtr(self.g), np.asarray(uniforms), root_idx=root_idx)
+        tips = self.tip_row >= 0
+        self.flat['tip_codes'] = np.asarray(state2code, dtype=np.uint8)[st[tips]][np.argsort(self.tip_row[tips])]
+        self.res = None
+        self.prev_idx = None
+        return st if return_states else None
+
     def results_tips(self):
         # share of the last N_diff that came from tips (recomputed: the oracle returns only the total)
         src = self.res.seq_idx if self.res is not None else self.seqs

@@ -306,6 +306,77 @@ def test_branch_state_pairs(kind):
         eng.branch_state_pairs([0])
 
 
+@pytest.mark.parametrize('kind', ['nuc', 'aa', 'ss'])
+def test_seqgen(kind):
+    """N4: ttb_seqgen.  With caller-supplied uniforms the kernel must equal the oracle's restatement of
+    SeqGen.evolve (seqgen.py:38-67) state for state; with the device's Philox stream the transition
+    frequencies must follow exp(Qt) and the run must be reproducible from the seed."""
+    from treetime_b200.flatten import code_table
+    from treetime_b200.gtr import GTRSiteSpecific
+    if kind == 'nuc':
+        tree = synth.random_tree(60, seed=71, mean_bl=0.2, polytomy_frac=0.2); gtr = util.nuc_gtr(); L = 2000
+    elif kind == 'aa':
+        tree = synth.random_tree(20, seed=72, mean_bl=0.3); gtr = util.random_gtr('aa_nogap', 9); L = 700
+    else:
+        L = 900
+        tree = synth.random_tree(30, seed=73, mean_bl=0.2); gtr = GTRSiteSpecific.random(L=L, alphabet='nuc', rng=np.random.default_rng(8))
+    topo, flat, g = util.make_flat(tree, gtr, L, 71, compress=False)
+    assert flat['multiplicity'].shape[0] == L
+    eng = util.engine_for(flat, g)
+    chars, lut, table = code_table(gtr.profile_map, gtr.n_states)
+    s2c = np.array([lut[str(c)] for c in gtr.alphabet], dtype=np.uint8)
+    n_nodes = flat['parent'].shape[0]
+    rng = np.random.default_rng(5)
+    U = rng.random((n_nodes, L))
+    G_ = O.make_gtr(g)
+    got = eng.seqgen(0, s2c, uniforms=U)
+    want = O.seqgen(flat, G_, U)
+    assert (got != want).mean() < 2e-5          # device exp(Qt) differs from numpy's by ulps: a draw on a boundary may flip
+    root = rng.integers(0, gtr.n_states, size=L).astype(np.uint8)
+    got = eng.seqgen(0, s2c, root_idx=root, uniforms=U)
+    assert (got[0] == root).all() and (got != O.seqgen(flat, G_, U, root_idx=root)).mean() < 2e-5
+    # the tips became the alignment: a reconstruction on it equals the oracle's on the same codes
+    tips = flat['tip_row'] >= 0
+    f2 = dict(flat, tip_codes=s2c[got[tips]][np.argsort(flat['tip_row'][tips])])
+    eng.marginal()
+    tot, _ = eng.results()
+    ref = O.marginal(f2, g)
+    assert abs(tot - ref.total_LH) <= LH_RTOL * abs(ref.total_LH)
+    # Philox stream: reproducible, seed-dependent, right distribution
+    a = eng.seqgen(1234, s2c)
+    b = eng.seqgen(1234, s2c)
+    c = eng.seqgen(1235, s2c)
+    assert (a == b).all() and (a != c).mean() > 0.05
+    q = gtr.n_states
+    if kind != 'ss':
+        n = int(np.argmax(flat['t'][1:])) + 1          # longest branch: most transitions
+        P = G_.expQt(flat['t'][n])
+        pa, ch = a[flat['parent'][n]].astype(int), a[n].astype(int)
+        cnt = np.zeros((q, q)); np.add.at(cnt, (ch, pa), 1)
+        exp = P * np.bincount(pa, minlength=q)[None, :]
+        ok = exp > 5
+        chi2 = ((cnt - exp)[ok] ** 2 / exp[ok]).sum()
+        dof = ok.sum() - (ok.any(axis=0)).sum()
+        assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (chi2, dof)
+        piroot = np.bincount(a[0], minlength=q) / L
+        assert np.abs(piroot - g['Pi']).max() < 5 * np.sqrt(0.25 / L)
+    else:
+        # per-site models: compare the mean log-probability of the drawn transitions with its expectation
+        n = int(np.argmax(flat['t'][1:])) + 1
+        P = G_.expQt(flat['t'][n])                    # (q, q, L)
+        pa, ch = a[flat['parent'][n]].astype(int), a[n].astype(int)
+        site = np.arange(L)
+        lp = np.log(np.maximum(P[ch, pa, site], 1e-300))
+        col = np.maximum(P[:, pa, site], 1e-300)
+        mean = (col * np.log(col)).sum(axis=0)
+        var = (col * np.log(col) ** 2).sum(axis=0) - mean ** 2
+        z = (lp.sum() - mean.sum()) / np.sqrt(var.sum())
+        assert abs(z) < 5, z
+    from treetime_b200._lib import TTBError
+    with pytest.raises(TTBError):
+        eng.seqgen(1, np.full(q, 255, dtype=np.uint8))
+
+
 def test_api_errors():
     from treetime_b200.engine import Engine
     from treetime_b200._lib import TTBError

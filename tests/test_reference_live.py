@@ -292,3 +292,38 @@ def test_state_pair_restatement_matches_reference():
                 t = 0.1
                 assert O.prob_t_compressed(g, mine[0], mine[1], t) == g.prob_t_compressed(ref[0], ref[1], t, return_log=True)
                 assert O.optimal_t_compressed(g, mine[0], mine[1]) == g.optimal_t_compressed(ref[0], ref[1])
+
+
+def test_seqgen_reproduces_reference_sequences():
+    """N4: treetime_b200.SeqGen(reference_rng=True) == treetime.seqgen.SeqGen with the same seed -- single-model
+    and site-specific GTR (oracle-backed engine here; the GPU test checks the kernel against the same oracle)."""
+    refenv.activate()
+    import oracle_engine
+    from io import StringIO
+    from Bio import Phylo
+    from treetime import GTR as RG
+    from treetime.gtr_site_specific import GTR_site_specific
+    from treetime.seqgen import SeqGen as RefSeqGen
+    from treetime_b200 import synth
+    from treetime_b200.gtr import GTR, GTRSiteSpecific
+    from treetime_b200.seqgen import SeqGen
+    T = synth.random_tree(25, seed=61, mean_bl=0.15, polytomy_frac=0.2)
+    L = 300
+    pi = np.array([.3, .2, .2, .29, .01])
+    cases = [(RG.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc'), GTR.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc'))]
+    rs = GTR_site_specific.random(L=L, alphabet='nuc', rng=np.random.default_rng(62))
+    ms = GTRSiteSpecific(alphabet='nuc', seq_len=L)
+    ms.assign_rates(mu=np.array(rs.mu), pi=np.array(rs.Pi), W=np.array(rs.W))
+    cases.append((rs, ms))
+    for rg, mg in cases:
+        ref = RefSeqGen(L, tree=Phylo.read(StringIO(T.to_newick()), 'newick'), gtr=rg, rng_seed=7, verbose=0)
+        ref.evolve()
+        mine = SeqGen(L, tree=T.to_newick(), gtr=mg, rng_seed=7, engine_factory=oracle_engine.factory)
+        aln = mine.evolve(reference_rng=True)
+        want = {r.id: np.array(list(str(r.seq))) for r in ref.get_aln(internal=True)}
+        got = mine.get_aln(internal=True)
+        named = [k for k in want if k in got]
+        assert len(named) >= 25
+        for k in named:
+            assert (want[k] == got[k]).all(), k
+        assert set(aln) == set(n.name for n in T.get_terminals())

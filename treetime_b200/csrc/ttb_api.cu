@@ -137,7 +137,8 @@ struct ttb_engine {
   DBuf<unsigned long long> d_mut_count;   // d_bstage: packed byte staging for contiguous H2D / D2H
   DBuf<unsigned long long> d_nd;
   DBuf<int> d_enodes, d_ekinds, d_pair_first;
-  DBuf<double> d_pair_counts;
+  DBuf<double> d_pair_counts, d_sg_uniforms;
+  DBuf<uint8_t> d_sg_states;
   DBuf<double> d_ets, d_eout;
   double* h_results = nullptr;  // pinned {total, ndiff}
   // page-locked scratch through which small pageable inputs (branch lengths, model, multiplicities)
@@ -499,6 +500,8 @@ int ttb_destroy(ttb_handle h) {
   h->d_ss_rec.release();
   h->d_pair_first.release();
   h->d_pair_counts.release();
+  h->d_sg_states.release();
+  h->d_sg_uniforms.release();
   h->post.d_chunks.release(); h->pre_int.d_chunks.release(); h->pre_all.d_chunks.release();
   h->d_idx.release();
   h->d_idxtip.release();
@@ -1275,6 +1278,57 @@ int ttb_branch_state_pairs(ttb_handle h, int32_t n, const int32_t* nodes, int32_
   CK(cudaMemcpyAsync(counts, h->d_pair_counts.p, (size_t)n * bins * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(first, h->d_pair_first.p, (size_t)n * bins * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ttb_seqgen(ttb_handle h, uint64_t seed, const uint8_t* root_idx, const double* uniforms, const uint8_t* state2code,
+               uint8_t* states_out) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, false)) return rc;
+  if (!state2code) return fail(TTB_EINVAL, "ttb_seqgen: state2code is null");
+  for (int i = 0; i < h->q; ++i)
+    if (state2code[i] >= h->n_codes) return fail(TTB_EINVAL, "ttb_seqgen: state2code entry out of range of the code table");
+  if (root_idx)
+    for (long long a = 0; a < h->Lp; ++a)
+      if (root_idx[a] >= h->q) return fail(TTB_EINVAL, "ttb_seqgen: root state out of range");
+  if (int rc = update_ss_interp(h)) return rc;
+  const size_t q = h->q, Lp = (size_t)h->Lp, ld = (size_t)h->ld;
+  int rc;
+  if (!h->site_specific) {
+    const size_t pq = (q * q + 1) / 2 * 2;
+    const bool had_P = h->d_P.p != nullptr;
+    if ((rc = h->d_P.alloc((size_t)h->n_nodes * pq))) return rc;
+    if (!had_P) h->drop_graphs();
+  }
+  if ((rc = h->d_sg_states.alloc((size_t)h->n_nodes * ld))) return rc;
+  if ((rc = h->d_bstage.alloc(std::max(std::max((size_t)h->n_tips, (size_t)h->n_int) * Lp, Lp + 256)))) return rc;
+  cudaStream_t s = h->stream;
+  const uint8_t* d_root = nullptr;
+  CK(cudaMemcpyAsync(h->d_bstage.p, state2code, q, cudaMemcpyHostToDevice, s));
+  if (root_idx) {
+    CK(cudaMemcpyAsync(h->d_bstage.p + 256, root_idx, Lp, cudaMemcpyHostToDevice, s));
+    d_root = h->d_bstage.p + 256;
+  }
+  const double* d_uni = nullptr;
+  if (uniforms) {
+    if ((rc = h->d_sg_uniforms.alloc((size_t)h->n_nodes * Lp))) return rc;
+    CK(cudaMemcpyAsync(h->d_sg_uniforms.p, uniforms, (size_t)h->n_nodes * Lp * sizeof(double), cudaMemcpyHostToDevice, s));
+    d_uni = h->d_sg_uniforms.p;
+  }
+  const int nk = ttb_qops(h->q)->seqgen(h->dev(), h->tiles(), (unsigned long long)seed, d_root, d_uni, h->d_sg_states.p, s);
+  seqgen_tip_codes_kernel<<<dim3(h->tiles(), std::min(h->n_tips, 148 * 4)), TTB_BLOCK, 0, s>>>(h->dev(), h->d_tip_nodes.p, h->d_sg_states.p,
+                                                                                            h->d_bstage.p, h->d_codes.p);
+  h->launches += nk + 1;
+  CK(cudaGetLastError());
+  // the alignment changed: no reconstruction is valid any more, previous states are meaningless
+  if (h->d_idx.p) CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), s));
+  if (h->d_idxtip.p) CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), s));
+  h->have_pass = h->have_tip_pass = false;
+  h->have_joint = h->have_joint_tips = false;
+  if (states_out)
+    CK(cudaMemcpy2DAsync(states_out, Lp, h->d_sg_states.p, ld, Lp, (size_t)h->n_nodes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  h->d_sg_uniforms.release();
   return 0;
 }
 

@@ -1423,6 +1423,85 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 }
 
 // ---------------------------------------------------------------------------------------
+// N4: SeqGen on the device.  Reference: SeqGen.evolve / sample_from_profile (seqgen.py:19-67):
+//   root ~ Pi (or given);  child state = argmax(cumsum(expQt(t_c)[:, parent state]) > u),  u ~ U[0,1)
+// Sites are independent and nodes are numbered in preorder (parent < child), so one thread owns a site and
+// walks the whole tree; states[node][site] is re-read by the same thread for the children.
+// Uniform numbers: either supplied by the caller ([n_nodes][Lp], the reference's own draws -> identical
+// sequences) or Philox4x32-10 keyed by the seed with counter (site, node): reproducible for any launch shape.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double seqgen_uniform(const double* __restrict__ uniforms, unsigned long long seed, int node, long long a,
+                                                 long long Lp) {
+  if (uniforms) return uniforms[(size_t)node * Lp + a];
+  uint32_t r[4];
+  philox4x32_10((uint32_t)a, (uint32_t)((unsigned long long)a >> 32), (uint32_t)node, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  return (double)((((unsigned long long)r[0] << 32) | r[1]) >> 11) * 0x1p-53;   // 53 random bits -> [0, 1)
+}
+template <int Q>
+__device__ __forceinline__ int sample_cdf(const double (&pr)[Q], double u) {
+  // np.argmax(cumsum(p) > u): first state whose cumulative probability exceeds u, 0 if none does
+  double cum = 0.0;
+  int st = 0;
+  bool found = false;
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    cum += pr[i];
+    if (!found && cum > u) { st = i; found = true; }
+  }
+  return st;
+}
+template <int Q, bool SS>
+__global__ void __launch_bounds__(TTB_BLOCK) seqgen_kernel(TtbDev p, unsigned long long seed, const uint8_t* __restrict__ root_idx,
+                                                          const double* __restrict__ uniforms, uint8_t* __restrict__ states) {
+  const long long a = (long long)blockIdx.x * TTB_BLOCK + threadIdx.x;
+  if (a >= p.Lp) return;
+  double pr[Q];
+  if (root_idx) {
+    states[a] = root_idx[a];
+  } else {
+#pragma unroll
+    for (int i = 0; i < Q; ++i) pr[i] = SS ? p.ss_Pi[(size_t)i * p.ld + a] : p.Pi[i];
+    states[a] = (uint8_t)sample_cdf<Q>(pr, seqgen_uniform(uniforms, seed, 0, a, p.Lp));
+  }
+  for (int n = 1; n < p.n_nodes; ++n) {
+    const int sp = states[(size_t)p.parent[n] * p.ld + a];
+    if constexpr (SS) {
+      const SiteModel<Q> sm(p, a);
+      double e[Q], onehot[Q];
+#pragma unroll
+      for (int j = 0; j < Q; ++j) onehot[j] = j == sp ? 1.0 : 0.0;
+      sm.efac(p, n, e);
+      sm.down(onehot, e, pr);            // column sp of this site's exp(Qt)
+    } else {
+      const double* P = p.P + (size_t)n * p.pq;
+#pragma unroll
+      for (int i = 0; i < Q; ++i) pr[i] = P[i * Q + sp];
+    }
+    states[(size_t)n * p.ld + a] = (uint8_t)sample_cdf<Q>(pr, seqgen_uniform(uniforms, seed, n, a, p.Lp));
+  }
+}
+// tip rows of the generated states -> alignment codes of the engine's code table
+static __global__ void seqgen_tip_codes_kernel(TtbDev p, const int* __restrict__ tip_nodes, const uint8_t* __restrict__ states,
+                                               const uint8_t* __restrict__ state2code, uint8_t* __restrict__ codes) {
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.Lp) return;
+  for (int row = blockIdx.y; row < p.n_tips; row += gridDim.y)
+    codes[(size_t)row * p.ld + a] = state2code[states[(size_t)tip_nodes[row] * p.ld + a]];
+}
+
+// ---------------------------------------------------------------------------------------
 // Per-node fetch in the reference's (L', q) row-major layout (TreeAnc node attributes).
 // ---------------------------------------------------------------------------------------
 template <int Q>

@@ -186,8 +186,23 @@ void counts_q(const TtbDev& d, int tiles, int chunks, int chunk, double* partial
   const int width = Q * Q + Q;
   counts_reduce_kernel<<<(width + 127) / 128, 128, 0, s>>>(partial, chunks * tiles, width, out);
 }
+int seqgen_q(const TtbDev& d, int tiles, unsigned long long seed, const uint8_t* root_idx, const double* uniforms, uint8_t* states,
+             cudaStream_t s) {
+  int nk = 0;
+  if constexpr (HAS_SS) {
+    if (d.site_specific) {
+      seqgen_kernel<Q, true><<<tiles, TTB_BLOCK, 0, s>>>(d, seed, root_idx, uniforms, states);
+      return 1;
+    }
+  }
+  const int nthr = d.n_nodes * Q;
+  expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
+  ++nk;
+  seqgen_kernel<Q, false><<<tiles, TTB_BLOCK, 0, s>>>(d, seed, root_idx, uniforms, states);
+  return nk + 1;
+}
 }  // namespace
 
 #define TTB_CAT2(a, b) a##b
 #define TTB_CAT(a, b) TTB_CAT2(a, b)
-extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {prepare_q, enqueue_pass_q, enqueue_joint_q, enqueue_joint_retrace_q, fetch_node_q, branch_eval_q, counts_q};
+extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {prepare_q, enqueue_pass_q, enqueue_joint_q, enqueue_joint_retrace_q, fetch_node_q, branch_eval_q, counts_q, seqgen_q};

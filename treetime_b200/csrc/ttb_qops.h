@@ -46,6 +46,9 @@ struct TtbQOps {
   void (*branch_eval)(const TtbDev& d, int n_eval, int nb, const int* nodes, const int* kinds, const double* ts,
                       int mode, double* partial, double* out, cudaStream_t s);
   void (*counts)(const TtbDev& d, int tiles, int chunks, int chunk, double* partial, double* out, cudaStream_t s);
+  // N4: evolve sequences down the tree; states[n_nodes][ld]; returns #kernels
+  int (*seqgen)(const TtbDev& d, int tiles, unsigned long long seed, const uint8_t* root_idx, const double* uniforms, uint8_t* states,
+                cudaStream_t s);
 };
 
 const TtbQOps* ttb_qops(int q);

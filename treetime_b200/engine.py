@@ -272,6 +272,23 @@ class Engine(object):
         _lib.check(self.lib.ttb_branch_state_pairs(self.h, nodes.shape[0], _ip(nodes), 1 if tip_states else 0, W, _dp(counts), _ip(first)))
         return counts, first
 
+    def seqgen(self, seed, state2code, root_idx=None, uniforms=None, return_states=True):
+        """ttb_seqgen: evolve sequences down the tree; the tips become the engine's alignment.  Returns the
+        state indices of every node [n_nodes, n_patterns] (or None)."""
+        state2code = np.ascontiguousarray(state2code, dtype=np.uint8)
+        if state2code.shape[0] != self.n_states:
+            raise ValueError('state2code needs one entry per state')
+        r = None if root_idx is None else np.ascontiguousarray(root_idx, dtype=np.uint8)
+        u = None if uniforms is None else _f64(uniforms)
+        if u is not None and u.shape != (self.n_nodes, self.n_patterns):
+            raise ValueError('uniforms must be [n_nodes, n_patterns]')
+        if r is not None and r.shape[0] != self.n_patterns:
+            raise ValueError('root_idx must have n_patterns entries')
+        out = np.empty((self.n_nodes, self.n_patterns), dtype=np.uint8) if return_states else None
+        _lib.check(self.lib.ttb_seqgen(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF, _up(r) if r is not None else None,
+                                       _dp(u) if u is not None else None, _up(state2code), _up(out) if out is not None else None))
+        return out
+
     def device_bytes(self):
         b = ctypes.c_int64()
         _lib.check(self.lib.ttb_device_bytes(self.h, ctypes.byref(b)))
