@@ -827,10 +827,25 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
   if (a >= p.Lp) return;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
   double X[Q];
-  double Facc = 0.0;
+  double Facc = 0.0, Zprod = 1.0;   // log-normalisers as Facc + log(Zprod), see post_level_kernel
   int scale = 0, seen = 0;
+  // Software pipeline: the descriptor and the code bytes of the NEXT chunk are requested before the
+  // current one is processed -- the code byte comes from DRAM and everything else depends on it.
+  Chunk c = load_chunk_global(chunks + k0);
+  int code[Pipe<Q>::CB];
+#pragma unroll
+  for (int b = 0; b < Pipe<Q>::CB; ++b) code[b] = b < c.nch() ? __ldg(p.codes + (size_t)(-1 - c.src(b)) * p.ld + a) : 0;
   for (int k = k0; k < k1; ++k) {
-    const Chunk c = load_chunk_global(chunks + k);
+    Chunk cn = c;
+    int ncode[Pipe<Q>::CB];
+#pragma unroll
+    for (int b = 0; b < Pipe<Q>::CB; ++b) ncode[b] = 0;
+    if (k + 1 < k1) {
+      cn = load_chunk_global(chunks + k + 1);
+#pragma unroll
+      for (int b = 0; b < Pipe<Q>::CB; ++b)
+        if (b < cn.nch()) ncode[b] = __ldg(p.codes + (size_t)(-1 - cn.src(b)) * p.ld + a);
+    }
     if (c.flags & 1) {
 #pragma unroll
       for (int j = 0; j < Q; ++j) X[j] = JOINT ? 0.0 : 1.0;
@@ -838,10 +853,11 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
       seen = 0;
     }
     const int nch = c.nch();
-    for (int b = 0; b < nch; ++b) {
+#pragma unroll
+    for (int b = 0; b < Pipe<Q>::CB; ++b) {
+      if (b >= nch) break;
       const int row = -1 - c.src(b);
-      const int code = __ldg(p.codes + (size_t)row * p.ld + a);
-      const double* tu = (JOINT ? p.TL : p.TU) + (size_t)row * p.tu_stride + code * Q;
+      const double* tu = (JOINT ? p.TL : p.TU) + (size_t)row * p.tu_stride + code[b] * Q;
       if constexpr (JOINT) {
 #pragma unroll
         for (int j = 0; j < Q; ++j) X[j] += __ldg(tu + j);
@@ -874,10 +890,22 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
       double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
 #pragma unroll
       for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j] * inv;
-      Facc += log(Z) - scale * (256.0 * 0.693147180559945309417232121458);
+      if (scale) Facc -= scale * (256.0 * 0.693147180559945309417232121458);
+      if (Z < 1e-150 || Z > 1e150) {
+        Facc += log(Z);
+      } else {
+        Zprod *= Z;
+        if (Zprod < 1e-150 || Zprod > 1e150) {
+          Facc += log(Zprod);
+          Zprod = 1.0;
+        }
+      }
     }
+    c = cn;
+#pragma unroll
+    for (int b = 0; b < Pipe<Q>::CB; ++b) code[b] = ncode[b];
   }
-  if (!JOINT) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc;
+  if (!JOINT) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc + log(Zprod);
 }
 
 // First stage of the log-prefactor reduction: Fred[c][a] = sum of Fpart[g][a] over g = c mod TTB_FLANES
