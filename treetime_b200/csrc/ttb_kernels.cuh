@@ -116,6 +116,15 @@ struct TtbDev {
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Programmatic dependent launch (level kernels are launched with the programmatic-stream-serialization
+// attribute): pdl_launch_dependents() lets the next level's blocks become resident as soon as every block of
+// this level has started, so that their prologue (barrier init, per-pattern model into registers, descriptor
+// prefetch) overlaps this level's tail; pdl_wait() blocks until the previous grid has completed and its
+// writes are visible.  Every block that touches node data calls pdl_wait(), hence completion of level l
+// implies completion of all earlier levels.  Both are no-ops for an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -628,6 +637,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long a = a0 + tid;
   const bool act = a < p.Lp;
+  pdl_launch_dependents();
   if (tid == 0) pipe.init();
   __syncthreads();
 
@@ -681,6 +691,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     // barriers); the descriptor of the next chunk is fetched while the current one is issued, so no
     // global-memory latency sits on the consumers' path.
     Chunk c = load_chunk_global(chunks + k0);
+    pdl_wait();   // everything the bulk copies read was written by earlier levels
     for (int u = 0; u < n_chunks; ++u) {
       const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
       issue(u, c);
@@ -692,6 +703,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   if (SS && !MREG) pipe.wait_model();
   SiteModel<Q, MREG> sm;
   if constexpr (SS) sm.init_level(p, a, act, pipe.model, tid);
+  pdl_wait();
 
   double X[Q];
   // sum of log-normalisers of this block's nodes (for this thread's pattern), kept as Facc + log(Zprod):
@@ -824,8 +836,10 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
                                                                    const int* __restrict__ group_ptr, int tiles, int fbase) {
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const long long a = (long long)tile * TTB_TILE + threadIdx.x;
+  pdl_launch_dependents();
   if (a >= p.Lp) return;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
+  pdl_wait();   // the tip tables come from the preceding kernel
   double X[Q];
   double Facc = 0.0, Zprod = 1.0;   // log-normalisers as Facc + log(Zprod), see post_level_kernel
   int scale = 0, seen = 0;
@@ -1203,6 +1217,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long a = a0 + tid;
   const bool act = a < p.Lp;
+  pdl_launch_dependents();
   if (tid == 0) pipe.init();
   __syncthreads();
 
@@ -1264,6 +1279,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     // barriers); the descriptor of the next chunk is fetched while the current one is issued, so no
     // global-memory latency sits on the consumers' path.
     Chunk c = load_chunk_global(chunks + k0);
+    pdl_wait();   // everything the bulk copies read was written by earlier levels
     for (int u = 0; u < n_chunks; ++u) {
       const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
       issue(u, c);
@@ -1275,6 +1291,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   if (SS && !MREG) pipe.wait_model();
   SiteModel<Q, MREG> sm;
   if constexpr (SS) sm.init_level(p, a, act, pipe.model, tid);
+  pdl_wait();
 
   double Mp[Q];
   unsigned int ndiff = 0, ndiff_tip = 0;   // changed states of internal nodes / of tips

@@ -17,6 +17,22 @@ size_t level_smem(int rows, const TtbDev& d, bool ss) {
 size_t post_smem(const TtbDev& d, bool ss = false) { return level_smem(Pipe<Q>::CB * Q, d, ss); }
 size_t pre_smem(const TtbDev& d, bool ss = false) { return level_smem(Q + Pipe<Q>::CB * Q, d, ss); }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait() in ttb_kernels.cuh).
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 constexpr bool HAS_SS = (Q <= 8);   // site-specific models: nucleotide-sized alphabets only
 
 template <bool SS>
@@ -56,16 +72,16 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   if (!SS) {
     // level 1 (all children are tips) is a pure write stream: dedicated kernel, no pipeline
     const TtbLevelLaunch& L = pl.post_levels[0];
-    post_leaf_level_kernel<Q><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_post_chunks,
-                                                                                          pl.d_post_group_ptr + L.group_off, tiles, 0);
+    launch_pdl(post_leaf_level_kernel<Q>, (unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s, d, pl.d_post_chunks,
+               pl.d_post_group_ptr + L.group_off, tiles, 0);
     ++nk;
     l0 = 1;
   }
   int fbase = l0 ? pl.post_levels[0].n_groups : 0;
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
-    post_level_kernel<Q, SS><<<(unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s>>>(d, pl.d_post_chunks,
-                                                                                             pl.d_post_group_ptr + L.group_off, tiles, fbase);
+    launch_pdl(post_level_kernel<Q, SS>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d, pl.d_post_chunks,
+               pl.d_post_group_ptr + L.group_off, tiles, fbase);
     fbase += L.n_groups;
     ++nk;
   }
@@ -84,9 +100,11 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
       const TtbLevelLaunch& L = pl.pre_levels[l];
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
       if (pl.tips)
-        pre_level_kernel<Q, true, SS><<<grid, TTB_LEVEL_THREADS, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
+        launch_pdl(pre_level_kernel<Q, true, SS>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
+                   pl.count_diff);
       else
-        pre_level_kernel<Q, false, SS><<<grid, TTB_LEVEL_THREADS, rsm, s>>>(d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff);
+        launch_pdl(pre_level_kernel<Q, false, SS>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
+                   pl.count_diff);
       ++nk;
     }
   }
