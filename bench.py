@@ -41,6 +41,28 @@ WORKLOADS = {
 SURVEY_BYTES_PER_UPDATE = {5: 165.5, 4: 133.5, 20: 645.5, 22: 709.5}    # 4 q s + 0.5 s + 1.5
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads (and so its first-touch pinned buffers) to the CPUs next to its GPU: with
+    several ranks the end-to-end leg is otherwise limited by cross-socket host traffic, not by PCIe."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), 'pci_domain_id', 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), 'pci_device_id', 0)
+        path = '/sys/bus/pci/devices/%04x:%02x:%02x.0' % (dom, bus, dev)
+        node = int(open(path + '/numa_node').read())
+        cpus = open(path + '/local_cpulist').read().strip()
+        ids = set()
+        for part in cpus.split(','):
+            a, _, b = part.partition('-')
+            ids.update(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids & os.sched_getaffinity(0) or ids)
+        return {'numa_node': node, 'cpus': cpus}
+    except Exception as e:       # best effort: containers may hide sysfs
+        return {'error': str(e)[:80]}
+
+
 def make_workload(name, seed):
     from treetime_b200 import synth
     from treetime_b200.gtr import GTR
@@ -233,6 +255,7 @@ def main():
     from treetime_b200.engine import Engine
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     topo, flat, g = make_workload(args.workload, seed=1 + rank)
@@ -481,7 +504,7 @@ def main():
                         'alignments) and ttb_fetch_mutations (root row + states differing from the parent) + per-pattern LH'}
             out['e2e'] = {'value': updates_total / e2e_time, 'unit': 'updates/s', 'ms_per_step': 1e3 * e2e_time,
                           'h2d_bytes_per_step': e2e[1], 'd2h_bytes_per_step': e2e[2],
-                          'pattern_blocks': e2e[3], 'rel_lh_diff_vs_resident_pass': e2e[4],
+                          'host_binding': numa, 'pattern_blocks': e2e[3], 'rel_lh_diff_vs_resident_pass': e2e[4],
                           'pcie_probe_gbs': {'h2d': e2e[5][0], 'd2h': e2e[5][1]},
                           'what': 'per step and per pattern block: ttb_set_patterns/gtr/branch_lengths from pinned host '
                                   'memory, ttb_marginal, ttb_enqueue_fetch_site_lh + ttb_enqueue_fetch_all_seq_idx into '

@@ -48,6 +48,10 @@ template <typename T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }   // `delete handle` frees every device buffer, listed in ttb_destroy or not
   int alloc(size_t count) {
     if (count == n && p) return 0;
     release();
