@@ -309,8 +309,12 @@ void build_groups(Sched& sc, int tiles, bool site_specific) {
   // issue-bound, so a partly filled last wave costs its full duration: size the grid of a level to fill
   // whole waves of the 2 blocks/SM these kernels run at.
   const long long slots = 148LL * 2;
-  const long long target_blocks = site_specific ? slots * 4 : 148LL * 32;
-  const long long max_group = site_specific ? 128 : 32;
+  // single-model kernels: ~2 waves of 3 blocks/SM per level -- longer runs amortise a block's prologue and first
+  // bulk copy (measured: 888 vs 4736 blocks per level: cfg2 0.95 -> 0.75 ms, cfg3 14.26 -> 14.13 ms, cfg4 2.33 -> 2.20 ms)
+  long long target_blocks = site_specific ? slots * 4 : 148LL * 6;
+  long long max_group = site_specific ? 128 : 32;
+  if (const char* e = getenv("TTB_TARGET_BLOCKS")) target_blocks = std::max(1LL, atoll(e));   // tuning knobs (measurement only)
+  if (const char* e = getenv("TTB_MAX_GROUP")) max_group = std::max(1LL, atoll(e));
   for (size_t l = 0; l + 1 < sc.level_node_begin.size(); ++l) {
     const int nb = sc.level_node_begin[l], ne = sc.level_node_begin[l + 1];
     const int n = ne - nb;
