@@ -315,12 +315,14 @@ void build_groups(Sched& sc, int tiles, bool site_specific) {
   long long max_group = site_specific ? 128 : 32;
   if (const char* e = getenv("TTB_TARGET_BLOCKS")) target_blocks = std::max(1LL, atoll(e));   // tuning knobs (measurement only)
   if (const char* e = getenv("TTB_MAX_GROUP")) max_group = std::max(1LL, atoll(e));
+  long long ss_waves = 4;
+  if (const char* e = getenv("TTB_SS_WAVES")) ss_waves = std::max(1LL, atoll(e));
   for (size_t l = 0; l + 1 < sc.level_node_begin.size(); ++l) {
     const int nb = sc.level_node_begin[l], ne = sc.level_node_begin[l + 1];
     const int n = ne - nb;
     long long G;
     if (site_specific) {
-      long long waves = 4;
+      long long waves = ss_waves;
       for (;;) {
         const long long groups = std::max(1LL, std::min((long long)n, waves * slots / tiles));
         G = (n + groups - 1) / groups;
