@@ -50,7 +50,8 @@ enum {
 enum {
   TTB_RECONSTRUCT_TIPS = 1, /* reconstruct_tip_states=True (treeanc.py:900-903) */
   TTB_LH_ONLY = 2,          /* postorder + root only: the cost function of optimize_gtr_rate (treeanc.py:1685-1689) */
-  TTB_JOINT_NO_TRACE = 4    /* ttb_joint: stop after the root (the caller samples the root, then ttb_joint_retrace) */
+  TTB_JOINT_NO_TRACE = 4,   /* ttb_joint: stop after the root (the caller samples the root, then ttb_joint_retrace) */
+  TTB_KEEP_PREV_STATES = 32 /* ttb_marginal: keep a copy of the states this pass overwrites (needed by ttb_sample_states) */
 };
 
 /* kinds of branch evaluated by ttb_branch_objective / ttb_branch_hamming */
@@ -135,6 +136,17 @@ int ttb_joint(ttb_handle h, int32_t flags);
 /* Back-trace from caller-chosen root states root_idx[n_patterns] (sample_from_profile='root',
  * treeanc.py:1008-1023); needs a preceding ttb_joint (usually with TTB_JOINT_NO_TRACE). */
 int ttb_joint_retrace(ttb_handle h, const uint8_t* root_idx, int32_t flags);
+
+/* sample_from_profile=True (treeanc.py:786-798,919-923): replace the argmax states of the n listed nodes by states
+ * drawn from their marginal profiles exactly like prof2seq (seq_utils.py:266-269): state = first i with
+ * cumsum(profile)[i] >= u, state 0 if there is none.  uniforms[n][n_patterns] holds the caller's draws, row k for
+ * nodes[k] -- for the reference's sequences pass rng.random(L') per reconstructed non-root node in preorder, after
+ * the root's own draw.  The profiles do not depend on drawn states, so this follows a ttb_marginal run with
+ * TTB_KEEP_PREV_STATES; n_diff / n_diff_tips receive the number of (internal / tip node, pattern) states that
+ * differ from the states before that pass (treeanc.py:925-926) and replace the pass's own counts.  Tips need
+ * TTB_RECONSTRUCT_TIPS.  Synchronous. */
+int ttb_sample_states(ttb_handle h, int32_t n, const int32_t* nodes, const double* uniforms, int64_t* n_diff,
+                      int64_t* n_diff_tips);
 
 /* Wait for the last ttb_marginal and return this shard's partial results:
  * total_lh = sum_a LH_a * multiplicity_a (treeanc.py:828), n_diff = number of (node, pattern)

@@ -297,8 +297,15 @@ def total_LH_and_root(flat, gtr, res):
     return res
 
 
-def preorder(flat, gtr, res, reconstruct_tip_states=False, prev_seq_idx=None, masks=None):
-    """treeanc.py:880-932 (preorder_traversal_marginal), argmax assignment."""
+def sample_idx(profile, u):
+    """prof2seq with sample_from_prof=True (seq_utils.py:266-269): first state whose cumulative probability reaches u."""
+    cumdis = profile.cumsum(axis=1).T
+    return np.argmax(cumdis >= u, axis=0)
+
+
+def preorder(flat, gtr, res, reconstruct_tip_states=False, prev_seq_idx=None, masks=None, uniforms=None):
+    """treeanc.py:880-932 (preorder_traversal_marginal); argmax assignment, or -- uniforms = {node: u[L']}, the
+    reference's rng.random(L') draws -- sampled from the profile (sample_from_profile=True)."""
     gtr = make_gtr(gtr)
     parent = flat['parent']
     n_nodes = parent.shape[0]
@@ -317,7 +324,10 @@ def preorder(flat, gtr, res, reconstruct_tip_states=False, prev_seq_idx=None, ma
             res.profile[n], _ = normalize_profile(res.subtree_LH[n] * (m * msg.T + (1.0 - m)).T, return_offset=False)
         else:
             res.profile[n], _ = normalize_profile(res.subtree_LH[n] * msg, return_offset=False)
-        idx = res.profile[n].argmax(axis=1)
+        if uniforms is not None:
+            idx = sample_idx(res.profile[n], uniforms[n])
+        else:
+            idx = res.profile[n].argmax(axis=1)
         if prev_seq_idx is not None and prev_seq_idx[n] is not None:
             N_diff += int((idx != prev_seq_idx[n]).sum())
         else:
@@ -327,11 +337,12 @@ def preorder(flat, gtr, res, reconstruct_tip_states=False, prev_seq_idx=None, ma
     return res
 
 
-def marginal(flat, gtr, reconstruct_tip_states=False, prev_seq_idx=None, masks=None):
-    """treeanc.py:762-812 (_ml_anc_marginal) without sampling."""
+def marginal(flat, gtr, reconstruct_tip_states=False, prev_seq_idx=None, masks=None, uniforms=None):
+    """treeanc.py:762-812 (_ml_anc_marginal); the root is always the argmax here (root sampling stays with the caller)."""
     res = postorder(flat, gtr, masks=masks)
     total_LH_and_root(flat, gtr, res)
-    preorder(flat, gtr, res, reconstruct_tip_states=reconstruct_tip_states, prev_seq_idx=prev_seq_idx, masks=masks)
+    preorder(flat, gtr, res, reconstruct_tip_states=reconstruct_tip_states, prev_seq_idx=prev_seq_idx, masks=masks,
+             uniforms=uniforms)
     return res
 
 

@@ -64,7 +64,23 @@ class OracleEngine(object):
     def set_branch_lengths(self, t):
         self.flat['t'] = np.array(t, dtype=float)
 
-    def marginal(self, reconstruct_tips=False, lh_only=False):
+    def sample_states(self, nodes, uniforms):
+        """Engine.sample_states: redraw the states of `nodes` from their profiles, count changes vs the previous pass."""
+        nd = ndt = 0
+        for k, n in enumerate(np.atleast_1d(nodes)):
+            n = int(n)
+            idx = O.sample_idx(self.res.profile[n], np.asarray(uniforms)[k])
+            prev = self._prev_before[n] if self._prev_before is not None else None
+            d = int((idx != prev).sum()) if prev is not None else self.n_patterns
+            if self.tip_row[n] >= 0:
+                ndt += d
+            else:
+                nd += d
+            self.res.seq_idx[n] = idx
+            self.prev_idx[n] = idx
+        return nd, ndt
+
+    def marginal(self, reconstruct_tips=False, lh_only=False, keep_prev=False):
         self.launches += 1
         if lh_only:
             r = O.sequence_LH_only(self.flat, self.g)

@@ -377,6 +377,58 @@ def test_seqgen(kind):
         eng.seqgen(1, np.full(q, 255, dtype=np.uint8))
 
 
+@pytest.mark.parametrize('kind', ['nuc', 'aa', 'ss'])
+def test_sample_states(kind):
+    """sample_from_profile=True (treeanc.py:919-923, seq_utils.py:266-269): states drawn on the device from the
+    marginal profiles with the caller's uniforms equal the oracle's draws (bit-exact except where a cumulative sum
+    lies within rounding of its uniform), N_diff counts against the previous pass."""
+    rng = np.random.default_rng(101)
+    if kind == 'ss':
+        from treetime_b200.gtr import GTRSiteSpecific
+        gtr = GTRSiteSpecific.random(L=333, alphabet='nuc', rng=np.random.default_rng(5))
+        tree = synth.random_tree(30, seed=9, mean_bl=0.05)
+        topo, flat, g = util.make_flat(tree, gtr, 333, 9, amb_frac=0.02, compress=False)
+    else:
+        gtr = util.nuc_gtr() if kind == 'nuc' else util.random_gtr('aa', 3)
+        tree = synth.random_tree(45, seed=8, mean_bl=0.08)
+        topo, flat, g = util.make_flat(tree, gtr, 500, 8, amb_frac=0.03)
+    n_nodes = flat['parent'].shape[0]
+    L = flat['multiplicity'].shape[0]
+    eng = util.engine_for(flat, g)
+    prev = None
+    for tips in (False, True, True):
+        nodes = [n for n in range(1, n_nodes) if tips or flat['tip_row'][n] < 0]
+        U = rng.random((len(nodes), L))
+        uni = {n: U[k] for k, n in enumerate(nodes)}
+        res = O.marginal(flat, g, reconstruct_tip_states=tips, prev_seq_idx=prev, uniforms=uni)
+        eng.marginal(reconstruct_tips=tips, keep_prev=True)
+        eng.results()
+        nd, nd_tips = eng.sample_states(nodes, U)
+        got = eng.seq_idx(nodes)
+        near = 0
+        for k, n in enumerate(nodes):
+            bad = got[k] != res.seq_idx[n]
+            if bad.any():    # only where a running sum is within rounding of the uniform
+                cum = np.cumsum(res.profile[n], axis=1)
+                assert (np.abs(cum - U[k][:, None]).min(axis=1)[bad] < 1e-12).all(), n
+                near += int(bad.sum())
+        assert near <= 2
+        if prev is not None:
+            exp_int = sum(int((res.seq_idx[n] != prev[n]).sum()) for n in nodes if flat['tip_row'][n] < 0 and prev[n] is not None)
+            exp_tip = sum(int((res.seq_idx[n] != prev[n]).sum()) for n in nodes if flat['tip_row'][n] >= 0 and prev[n] is not None)
+            assert abs(nd - exp_int) <= near
+            if all(prev[n] is not None for n in nodes):
+                assert abs(nd_tips - exp_tip) <= near
+        assert (got != np.array([res.profile[n].argmax(axis=1) for n in nodes])).any()   # really sampled
+        # the root keeps its argmax; the profiles are those of the plain pass
+        assert np.abs(eng.node_array(nodes[0], 2) - res.profile[nodes[0]]).max() < PROF_ATOL
+        prev = list(res.seq_idx)
+    from treetime_b200._lib import TTBError
+    eng.marginal()
+    with pytest.raises(TTBError):
+        eng.sample_states(nodes[:1], U[:1])       # the last pass did not keep the previous states
+
+
 def test_api_errors():
     from treetime_b200.engine import Engine
     from treetime_b200._lib import TTBError

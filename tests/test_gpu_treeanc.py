@@ -229,3 +229,24 @@ def test_gpu_device_pattern_compression():
     assert h.infer_ancestral_sequences(marginal=True) == d.infer_ancestral_sequences(marginal=True)
     assert h.sequence_LH() == d.sequence_LH()
     assert np.array_equal(h._engine.all_seq_idx(), d._engine.all_seq_idx())
+
+
+def test_gpu_sample_from_profile_all_nodes():
+    """infer_ancestral_sequences(marginal=True, sample_from_profile=True) on the device: same sampled sequences and
+    N_diff as the same TreeAnc on the CPU oracle engine (which test_reference_live pins to the reference), the
+    host generator consumed identically."""
+    import oracle_engine
+    z = G.load('nuc40')
+    a = gpu_from_golden(z)
+    b = gpu_from_golden(z, engine_factory=oracle_engine.factory)
+    for kw in (dict(), dict(reconstruct_tip_states=True), dict(reconstruct_tip_states=True), dict()):
+        na = a.infer_ancestral_sequences(marginal=True, sample_from_profile=True, **kw)
+        nb = b.infer_ancestral_sequences(marginal=True, sample_from_profile=True, **kw)
+        diff = 0
+        for x, y in zip(a.tree.find_clades(), b.tree.find_clades()):
+            if kw or not x.is_terminal():
+                diff += int((x.cseq != y.cseq).sum())
+        assert diff <= 1            # a draw within rounding of a cumulative sum may fall either way
+        assert abs(na - nb) <= 2 * diff and na > 0
+    assert a.rng.random() == b.rng.random()
+    assert a._engine.launch_count() > 0

@@ -327,3 +327,44 @@ def test_seqgen_reproduces_reference_sequences():
         for k in named:
             assert (want[k] == got[k]).all(), k
         assert set(aln) == set(n.name for n in T.get_terminals())
+
+
+def test_sample_from_profile_all_nodes_matches_reference():
+    """sample_from_profile=True (treeanc.py:786-798,919-923): every node's sequence is drawn from its marginal
+    profile with the caller's generator; the drop-in and the mirror consume the RNG like the reference, so the
+    sampled sequences, N_diff and the following draws are identical -- also with reconstructed tips and across
+    repeated calls (N_diff against the previous sampled states)."""
+    rt, dt = _pair(seed=41)
+    for kw in (dict(), dict(reconstruct_tip_states=True), dict(), dict(reconstruct_tip_states=True)):
+        n1 = rt.infer_ancestral_sequences(marginal=True, sample_from_profile=True, **kw)
+        n2 = dt.infer_ancestral_sequences(marginal=True, sample_from_profile=True, **kw)
+        assert dt._b200_live
+        assert n1 == n2 and n1 > 0
+        for a, b in zip(rt.tree.find_clades(), dt.tree.find_clades()):
+            if kw or not a.is_terminal():
+                assert (a.cseq == b.cseq).all()
+                assert np.array_equal(a.marginal_profile, b.marginal_profile)
+    assert rt.rng.random() == dt.rng.random()
+    # a sampled pass followed by an argmax pass: N_diff counts against the sampled states
+    assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
+    # the mirror (own containers) does the same
+    refenv.activate()
+    import oracle_engine
+    from treetime import GTR as RG
+    from treetime_b200 import synth
+    from treetime_b200.gtr import GTR
+    from treetime_b200.treeanc import TreeAnc
+    pi = np.array([.3, .2, .2, .29, .01])
+    T = synth.random_tree(25, seed=43, mean_bl=0.02)
+    g = GTR.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc')
+    idx = synth.evolve_alignment(T, 200, g.Pi, g.W, seed=43)
+    aln = {k: g.alphabet[v] for k, v in idx.items()}
+    r2 = refenv.reference_treeanc(T.to_newick(), aln, RG.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc'), rng_seed=7)
+    m2 = TreeAnc(tree=T.to_newick(), aln=aln, gtr=g, rng_seed=7, engine_factory=oracle_engine.factory)
+    for _ in range(2):
+        assert (r2.infer_ancestral_sequences(marginal=True, sample_from_profile=True)
+                == m2.infer_ancestral_sequences(marginal=True, sample_from_profile=True))
+        rn = {n.name: n for n in r2.tree.find_clades()}
+        for n in m2.tree.find_clades():
+            if not n.is_terminal():
+                assert (n.cseq == rn[n.name].cseq).all()

@@ -96,6 +96,8 @@ SIGNATURES = {
     'ttb_marginal': ([_H, ctypes.c_int32], ctypes.c_int),
     'ttb_joint': ([_H, ctypes.c_int32], ctypes.c_int),
     'ttb_joint_retrace': ([_H, _c_u8_p, ctypes.c_int32], ctypes.c_int),
+    'ttb_sample_states': ([_H, ctypes.c_int32, _c_int_p, _c_dbl_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)],
+                          ctypes.c_int),
     'ttb_results': ([_H, _c_dbl_p, ctypes.POINTER(ctypes.c_int64)], ctypes.c_int),
     'ttb_results_tips': ([_H, ctypes.POINTER(ctypes.c_int64)], ctypes.c_int),
     'ttb_results_device_ptr': ([_H, ctypes.POINTER(ctypes.c_void_p)], ctypes.c_int),

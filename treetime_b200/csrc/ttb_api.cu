@@ -143,6 +143,10 @@ struct ttb_engine {
   DBuf<int> d_enodes, d_ekinds, d_pair_first;
   DBuf<double> d_pair_counts, d_sg_uniforms;
   DBuf<uint8_t> d_sg_states;
+  // sample_from_profile=True: states of the previous pass (snapshot taken by TTB_KEEP_PREV_STATES)
+  DBuf<uint8_t> d_idx_prev, d_idxtip_prev;
+  DBuf<unsigned long long> d_scount;
+  bool have_prev = false, have_prev_tips = false;
   DBuf<double> d_ets, d_eout;
   double* h_results = nullptr;  // pinned {total, ndiff}
   // page-locked scratch through which small pageable inputs (branch lengths, model, multiplicities)
@@ -512,6 +516,7 @@ int ttb_destroy(ttb_handle h) {
   h->d_pair_counts.release();
   h->d_sg_states.release();
   h->d_sg_uniforms.release();
+  h->d_idx_prev.release(); h->d_idxtip_prev.release(); h->d_scount.release();
   h->post.d_chunks.release(); h->pre_int.d_chunks.release(); h->pre_all.d_chunks.release();
   h->d_idx.release();
   h->d_idxtip.release();
@@ -916,6 +921,7 @@ int ttb_marginal(ttb_handle h, int32_t flags) {
   if (int rc = check_ready(h, false)) return rc;
   const bool lh_only = flags & TTB_LH_ONLY;
   const bool tips = (flags & TTB_RECONSTRUCT_TIPS) && !lh_only;
+  const bool keep_prev = (flags & TTB_KEEP_PREV_STATES) && !lh_only;
   flags = (lh_only ? TTB_LH_ONLY : 0) | (tips ? TTB_RECONSTRUCT_TIPS : 0);
   const bool had_P = h->d_P.p != nullptr;
   if (int rc = ensure_state(h, tips)) return rc;
@@ -923,6 +929,18 @@ int ttb_marginal(ttb_handle h, int32_t flags) {
   if (!lh_only)
     if (int rc = ensure_preorder_state(h, tips)) return rc;
   if (int rc = update_ss_interp(h)) return rc;
+  if (keep_prev) {   // the states this pass is about to overwrite: what ttb_sample_states counts changes against
+    if (int rc = h->d_idx_prev.alloc(h->d_idx.n)) return rc;
+    CK(cudaMemcpyAsync(h->d_idx_prev.p, h->d_idx.p, h->d_idx.bytes(), cudaMemcpyDeviceToDevice, h->stream));
+    if (tips) {
+      if (int rc = h->d_idxtip_prev.alloc(h->d_idxtip.n)) return rc;
+      CK(cudaMemcpyAsync(h->d_idxtip_prev.p, h->d_idxtip.p, h->d_idxtip.bytes(), cudaMemcpyDeviceToDevice, h->stream));
+    }
+  }
+  if (!lh_only) {
+    h->have_prev = keep_prev;
+    h->have_prev_tips = keep_prev && tips;
+  }
   const int count_diff = lh_only ? 0 : 1;
   const int key = flags;
   auto it = h->graphs.find(key);
@@ -1024,6 +1042,47 @@ int ttb_joint_retrace(ttb_handle h, const uint8_t* root_idx, int32_t flags) {
   CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   h->launches += nk;
   h->have_joint_tips = tips;
+  return 0;
+}
+
+int ttb_sample_states(ttb_handle h, int32_t n, const int32_t* nodes, const double* uniforms, int64_t* n_diff,
+                      int64_t* n_diff_tips) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, true)) return rc;
+  if (n < 0 || (n && (!nodes || !uniforms))) return fail(TTB_EINVAL, "ttb_sample_states: bad arguments");
+  if (!h->have_prev) return fail(TTB_EINVAL, "ttb_sample_states: the last ttb_marginal was not run with TTB_KEEP_PREV_STATES");
+  for (int k = 0; k < n; ++k) {
+    const int node = nodes[k];
+    if (node < 0 || node >= h->n_nodes) return fail(TTB_EINVAL, "ttb_sample_states: bad node id");
+    if (h->tip_row[node] >= 0 && !(h->have_tip_pass && h->have_prev_tips))
+      return fail(TTB_EINVAL, "ttb_sample_states: tip profiles exist only after TTB_RECONSTRUCT_TIPS");
+  }
+  cudaStream_t s = h->stream;
+  int rc;
+  if ((rc = h->d_scount.alloc(2))) return rc;
+  CK(cudaMemsetAsync(h->d_scount.p, 0, 2 * sizeof(unsigned long long), s));
+  const size_t Lp = (size_t)h->Lp;
+  // the uniforms travel in blocks of at most 256 MB
+  const int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n, 1), ((size_t)1 << 25) / Lp));
+  if (n) {
+    if ((rc = h->d_sg_uniforms.alloc((size_t)blk * Lp))) return rc;
+    if ((rc = h->d_enodes.alloc((size_t)n))) return rc;
+    CK(cudaMemcpyAsync(h->d_enodes.p, nodes, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+  }
+  for (int k0 = 0; k0 < n; k0 += blk) {
+    const int m = std::min(blk, n - k0);
+    CK(cudaMemcpyAsync(h->d_sg_uniforms.p, uniforms + (size_t)k0 * Lp, (size_t)m * Lp * sizeof(double), cudaMemcpyHostToDevice, s));
+    ttb_qops(h->q)->sample_states(h->dev(), h->tiles(), m, h->d_enodes.p + k0, h->d_sg_uniforms.p, h->d_idx_prev.p,
+                                  h->d_idxtip_prev.p, h->d_scount.p, s);
+    CK(cudaGetLastError());
+    h->launches += 1;
+  }
+  unsigned long long c[2] = {0, 0};
+  CK(cudaMemcpyAsync(c, h->d_scount.p, sizeof c, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  h->d_sg_uniforms.release();
+  if (n_diff) *n_diff = (int64_t)c[0];
+  if (n_diff_tips) *n_diff_tips = (int64_t)c[1];
   return 0;
 }
 
@@ -1179,6 +1238,7 @@ int ttb_profile_marginal(ttb_handle h, int32_t flags, double* ms, int32_t* launc
   if (!ms || !launches) return fail(TTB_EINVAL, "ttb_profile_marginal: null output");
   const bool lh_only = flags & TTB_LH_ONLY;
   const bool tips = (flags & TTB_RECONSTRUCT_TIPS) && !lh_only;
+  const bool keep_prev = (flags & TTB_KEEP_PREV_STATES) && !lh_only;
   flags = (lh_only ? TTB_LH_ONLY : 0) | (tips ? TTB_RECONSTRUCT_TIPS : 0);
   const bool had_P = h->d_P.p != nullptr;
   if (int rc = ensure_state(h, tips)) return rc;
@@ -1186,6 +1246,18 @@ int ttb_profile_marginal(ttb_handle h, int32_t flags, double* ms, int32_t* launc
   if (!lh_only)
     if (int rc = ensure_preorder_state(h, tips)) return rc;
   if (int rc = update_ss_interp(h)) return rc;
+  if (keep_prev) {   // the states this pass is about to overwrite: what ttb_sample_states counts changes against
+    if (int rc = h->d_idx_prev.alloc(h->d_idx.n)) return rc;
+    CK(cudaMemcpyAsync(h->d_idx_prev.p, h->d_idx.p, h->d_idx.bytes(), cudaMemcpyDeviceToDevice, h->stream));
+    if (tips) {
+      if (int rc = h->d_idxtip_prev.alloc(h->d_idxtip.n)) return rc;
+      CK(cudaMemcpyAsync(h->d_idxtip_prev.p, h->d_idxtip.p, h->d_idxtip.bytes(), cudaMemcpyDeviceToDevice, h->stream));
+    }
+  }
+  if (!lh_only) {
+    h->have_prev = keep_prev;
+    h->have_prev_tips = keep_prev && tips;
+  }
   cudaEvent_t ev[6];
   for (auto& e : ev) CK(cudaEventCreate(&e));
   int nk = 0, pk[4] = {0, 0, 0, 0};
@@ -1206,6 +1278,7 @@ int ttb_profile_marginal(ttb_handle h, int32_t flags, double* ms, int32_t* launc
   if (!lh_only) {
     h->have_pass = true;
     h->have_tip_pass = tips;
+    h->have_prev = h->have_prev_tips = false;
   }
   return 0;
 }

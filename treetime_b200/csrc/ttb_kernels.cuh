@@ -1468,6 +1468,56 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 }
 
 // ---------------------------------------------------------------------------------------
+// A7 with sample_from_profile=True: node._cseq is drawn from marginal_profile instead of being its
+// argmax.  Reference: prof2seq (seq_utils.py:266-269): idx = argmax(cumsum(profile) >= u) -- the first state
+// whose running sum reaches u, state 0 if none does -- with one uniform per (node, pattern) from the
+// caller's generator (u[k][Lp] for the k-th listed node).  The profiles themselves do not depend on the drawn
+// states (children use the parent's profile, treeanc.py:895), so this runs after the pass: it overwrites the
+// argmax states and counts the changes against the states of the previous pass (prev_*: the snapshot taken
+// by TTB_KEEP_PREV_STATES); counts[0] internal nodes, counts[1] tips.  Grid (tiles, nodes).
+// ---------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(TTB_BLOCK) sample_states_kernel(TtbDev p, const int* __restrict__ nodes, const double* __restrict__ u,
+                                                                  const uint8_t* __restrict__ prev_idx,
+                                                                  const uint8_t* __restrict__ prev_idxtip,
+                                                                  unsigned long long* __restrict__ counts) {
+  const int node = nodes[blockIdx.y];
+  const long long a = (long long)blockIdx.x * TTB_TILE + threadIdx.x;
+  const int row = p.tip_row[node];
+  unsigned int changed = 0;
+  if (a < p.Lp) {
+    const double* m;
+    size_t at;
+    if (row >= 0) {
+      m = p.Mtip + msg_off<Q>(p, row, a);
+      at = (size_t)row * p.ld + a;
+    } else {
+      const int slot = p.int_slot[node];
+      m = p.M + msg_off<Q>(p, slot, a);
+      at = (size_t)slot * p.ld + a;
+    }
+    const double x = u[(size_t)blockIdx.y * p.Lp + a];
+    double cum = 0.0;
+    int best = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      cum += m[i * TTB_TILE];          // sequential like numpy's cumsum
+      if (!found && cum >= x) { best = i; found = true; }
+    }
+    if (row >= 0) {
+      changed = prev_idxtip[at] != (uint8_t)best;
+      p.idxtip[at] = (uint8_t)best;
+    } else {
+      changed = prev_idx[at] != (uint8_t)best;
+      p.idx[at] = (uint8_t)best;
+    }
+  }
+  changed = __reduce_add_sync(0xffffffffu, changed);
+  if ((threadIdx.x & 31) == 0 && changed) atomicAdd(counts + (row >= 0 ? 1 : 0), (unsigned long long)changed);
+}
+
+// ---------------------------------------------------------------------------------------
 // N4: SeqGen on the device.  Reference: SeqGen.evolve / sample_from_profile (seqgen.py:19-67):
 //   root ~ Pi (or given);  child state = argmax(cumsum(expQt(t_c)[:, parent state]) > u),  u ~ U[0,1)
 // Sites are independent and nodes are numbered in preorder (parent < child), so one thread owns a site and

@@ -182,18 +182,16 @@ class DeviceMarginalMixin(object):
         """treeanc.py:762-812: postorder, root, preorder -- one graph launch on the device."""
         self.logger('TreeAnc._ml_anc_marginal: type of reconstruction: Marginal', 2)
         if sample_from_profile == 'root':
-            root_sample = True
+            root_sample, other_sample = True, False
         elif isinstance(sample_from_profile, bool):
-            root_sample = sample_from_profile
-            if sample_from_profile:
-                self._unsupported("sampling every node from its profile is not provided; sample_from_profile='root' is")
+            root_sample = other_sample = sample_from_profile
         else:
             raise ValueError("sample_from_profile must be a bool or 'root'")
         if any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
             self._unsupported('per-branch masks (ARG mode) are not supported on the device path')
         eng = self._sync_device()
         topo = self._flat()
-        eng.marginal(reconstruct_tips=reconstruct_tip_states)
+        eng.marginal(reconstruct_tips=reconstruct_tip_states, keep_prev=other_sample)
         tot, nd = eng.results()
         if self.comm.world_size > 1:
             tot, nd = self.comm.allreduce_sum(np.array([tot, float(nd)]))
@@ -202,7 +200,7 @@ class DeviceMarginalMixin(object):
         self.tree.sequence_LH = self._gather_patterns(eng.site_lh())
         self.tree.total_sequence_LH = float(tot)
         self.tree.sequence_marginal_LH = self.tree.total_sequence_LH
-        N_diff = self._n_diff(eng, topo, nd, reconstruct_tip_states, self.reconstructed_tip_sequences)
+        had_reconstruction, prev_tips = self.sequence_reconstruction, self.reconstructed_tip_sequences
         root = self.tree.root
         root._cseq_override = None
         self.reconstructed_tip_sequences = reconstruct_tip_states
@@ -210,24 +208,51 @@ class DeviceMarginalMixin(object):
         if root_sample:                                                 # treeanc.py:831-838, host RNG
             seq, _, _ = prof2seq(self._node_array(root, PROFILE), self.gtr, sample_from_prof=True, normalize=False, rng=self.rng)
             root._cseq_override = seq
+        nd_tips = None
+        if other_sample:
+            nd, nd_tips = self._sample_states(eng, topo, reconstruct_tip_states)
+        N_diff = self._n_diff(eng, topo, nd, reconstruct_tip_states, prev_tips, had_reconstruction, nd_tips)
         self.logger('TreeAnc._ml_anc_marginal: ...done', 3)
         return N_diff
 
-    def _n_diff(self, eng, topo, nd, reconstruct_tip_states, prev_tips):
+    def _sample_states(self, eng, topo, reconstruct_tip_states):
+        """sample_from_profile=True (treeanc.py:919-923): every reconstructed non-root node draws its sequence from
+        its marginal profile.  The uniforms come from the caller's generator in the reference's order -- one
+        rng.random(L') per node in preorder (seq_utils.py:268), after the root's draw -- and go to the device in
+        blocks; a block of k rows of rng.random((k, L')) is the same stream as k successive rng.random(L') calls."""
+        L = self.data.compressed_length
+        lo, hi = self._shard()
+        ids = [n._fid for n in topo.nodes[1:] if reconstruct_tip_states or not n.is_terminal()]
+        blk = max(1, (1 << 24) // max(L, 1))                             # <= 128 MB of uniforms per block
+        nd = nd_tips = 0
+        for b in range(0, len(ids), blk):
+            part = ids[b:b + blk]
+            u = self.rng.random(size=(len(part), L))
+            a, t = eng.sample_states(part, u[:, lo:hi])
+            nd += a
+            nd_tips += t
+        if self.comm.world_size > 1:
+            nd, nd_tips = (int(round(x)) for x in self.comm.allreduce_sum(np.array([float(nd), float(nd_tips)])))
+        return nd + nd_tips, nd_tips
+
+    def _n_diff(self, eng, topo, nd, reconstruct_tip_states, prev_tips, had_reconstruction=Ellipsis, nd_tips=None):
         """N_diff of a pass (treeanc.py:925-928 / 1042-1045).  The device counts changed states against
         the previous device states; two host-side corrections reproduce the reference:
           * no previous reconstruction -> every reconstructed position counts;
           * tips reconstructed now but not before -> the reference compares them with the alignment's own
             (possibly ambiguous) characters, the device compared them with stale / unset states."""
         L = self.data.compressed_length
-        if not self.sequence_reconstruction:
+        if had_reconstruction is Ellipsis:
+            had_reconstruction = self.sequence_reconstruction
+        if not had_reconstruction:
             n_rec = (topo.n_nodes - 1) if reconstruct_tip_states else (topo.n_nodes - topo.n_tips - 1)
             return n_rec * L
         nd = int(round(nd))
         if reconstruct_tip_states and not prev_tips:
-            nd_tips = eng.results_tips()
-            if self.comm.world_size > 1:
-                nd_tips = int(round(self.comm.allreduce_sum(np.array([float(nd_tips)]))[0]))
+            if nd_tips is None:
+                nd_tips = eng.results_tips()
+                if self.comm.world_size > 1:
+                    nd_tips = int(round(self.comm.allreduce_sum(np.array([float(nd_tips)]))[0]))
             fresh = 0
             ca = self.data.compressed_alignment
             tips = list(topo.tip_nodes)

@@ -12,8 +12,8 @@ path in front of `treetime.TreeAnc` in the MRO, so that `ClockTree` / `TreeTime.
 What is overridden (reference lines in treeanc.py): `_ml_anc_marginal` (:762-812),
 `optimize_tree_marginal` (:1297-1360), `optimal_marginal_branch_length` (:1272-1295),
 `infer_gtr` marginal branch (:1500-1632), `optimize_gtr_rate` (:1679-1708).  Everything the
-device path does not cover -- per-branch masks (ARG), sampling all nodes from their profiles,
-site-specific models, alphabets without compiled kernels, joint / Fitch reconstruction --
+device path does not cover -- per-branch masks (ARG),
+site-specific models with more than 8 states, alphabets without compiled kernels, joint / Fitch reconstruction --
 falls through to the reference's own implementation (`super()`).
 
 Per-node results stay on the device.  The reference reads them as plain attributes of the
@@ -129,8 +129,6 @@ class B200MarginalMixin(DeviceMarginalMixin):
     # -- the pass ---------------------------------------------------------------------------
     def _ml_anc_marginal(self, sample_from_profile=False, reconstruct_tip_states=False, debug=False, **kwargs):
         why = self._device_ok()
-        if why is None and sample_from_profile is True:
-            why = 'sampling every node from its profile'
         if why is None and any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
             why = 'per-branch masks (ARG mode)'
         if why is None:

@@ -4,7 +4,7 @@ import numpy as np
 from . import _lib
 
 SUBTREE, OUTGROUP, PROFILE, JOINT_ROOT_LX = 0, 1, 2, 3
-RECONSTRUCT_TIPS, LH_ONLY = 1, 2
+RECONSTRUCT_TIPS, LH_ONLY, KEEP_PREV_STATES = 1, 2, 32
 BRANCH, BRANCH_ROOT = 0, 1
 
 
@@ -140,9 +140,21 @@ class Engine(object):
         _lib.check(self.lib.ttb_set_branch_lengths(self.h, _dp(t)))
 
     # -- the pass -------------------------------------------------------------
-    def marginal(self, reconstruct_tips=False, lh_only=False):
-        flags = (RECONSTRUCT_TIPS if reconstruct_tips else 0) | (LH_ONLY if lh_only else 0)
+    def marginal(self, reconstruct_tips=False, lh_only=False, keep_prev=False):
+        """keep_prev: keep the states this pass overwrites (sample_states counts N_diff against them)."""
+        flags = (RECONSTRUCT_TIPS if reconstruct_tips else 0) | (LH_ONLY if lh_only else 0) | (KEEP_PREV_STATES if keep_prev else 0)
         _lib.check(self.lib.ttb_marginal(self.h, flags))
+
+    def sample_states(self, nodes, uniforms):
+        """ttb_sample_states: draw the states of `nodes` from their marginal profiles with the caller's uniforms
+        [len(nodes), n_patterns]; returns (changed states of internal nodes, of tips) w.r.t. the previous pass."""
+        nodes = _i32(np.atleast_1d(nodes))
+        u = _f64(uniforms)
+        if u.shape != (nodes.shape[0], self.n_patterns):
+            raise ValueError('uniforms must be [len(nodes), n_patterns]')
+        nd, ndt = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.ttb_sample_states(self.h, nodes.shape[0], _ip(nodes), _dp(u), ctypes.byref(nd), ctypes.byref(ndt)))
+        return nd.value, ndt.value
 
     def joint(self, reconstruct_tips=False, trace=True):
         """Joint (max-product) reconstruction; results() returns (sequence_joint_LH, N_diff).

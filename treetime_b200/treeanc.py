@@ -16,8 +16,8 @@ With a communicator of world_size > 1 (treetime_b200.dist) every rank holds the
 same tree/model and one contiguous block of the compressed patterns; scalars are
 all-reduced, per-node arrays are all-gathered on access.
 
-Not provided here (outside SURVEY.md §8): Fitch reconstruction, joint-mode branch-length optimisation, masks
-(ARG mode), sampling of non-root nodes from their profiles.  They raise
+Not provided here (outside SURVEY.md §8): Fitch reconstruction, masks
+(ARG mode).  They raise
 NotImplementedError; the drop-in mixin for the real TreeTime
 (treetime_b200.dropin) falls back to the reference's own code for them.
 """
