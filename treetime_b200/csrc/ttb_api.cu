@@ -4,6 +4,8 @@
 #include "ttb_qops.h"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -108,7 +110,7 @@ struct ttb_engine {
   Sched post, pre_int, pre_all;
   int sched_tiles = -1;  // tiles the group pointers were built for
   int n_fgroups = 0;     // postorder block runs (rows of Fpart)
-  bool sched_ss = false;
+  int sched_ss = 0;      // 0 single model, 1 site-specific, 2 site-specific symmetric (3 blocks/SM)
   bool prepared = false;
   // device tree
   DBuf<int> d_parent, d_child_ptr, d_child_idx, d_tip_row, d_int_slot, d_tip_nodes;
@@ -125,7 +127,8 @@ struct ttb_engine {
   DBuf<double> d_t, d_eig, d_v, d_vinv, d_Pi, d_mu;
   // site-specific model
   bool site_specific = false;
-  DBuf<double> d_ss_eig, d_ss_mu, d_ss_V, d_ss_Vinv, d_ss_Pi, d_ss_w, d_ss_grid, d_ss_E;
+  DBuf<double> d_ss_eig, d_ss_mu, d_ss_V, d_ss_Vinv, d_ss_Pi, d_ss_w, d_ss_grid, d_ss_E, d_ss_c, d_ss_Ec;
+  bool ss_sym = false;
   DBuf<int> d_ss_lo;
   DBuf<double2> d_ss_rec;
   std::vector<double> ss_grid, h_t;
@@ -198,6 +201,7 @@ struct ttb_engine {
     d.ss_eig = d_ss_eig.p; d.ss_mu = d_ss_mu.p; d.ss_V = d_ss_V.p; d.ss_Vinv = d_ss_Vinv.p; d.ss_Pi = d_ss_Pi.p;
     d.ss_rec = d_ss_rec.p;
     d.ss_lo = d_ss_lo.p; d.ss_w = d_ss_w.p; d.ss_grid = d_ss_grid.p; d.ss_E = d_ss_E.p;
+    d.ss_sym = ss_sym ? 1 : 0; d.ss_c = d_ss_c.p; d.ss_Ec = d_ss_Ec.p;
     d.ss_ngrid = (int)ss_grid.size();
     d.ss_tmax = ss_tmax;
     d.pq = (q * q + 1) / 2 * 2;
@@ -306,13 +310,14 @@ void build_sched(ttb_handle h, const std::vector<int>& key, const std::vector<ch
 
 // Split every level into groups of consecutive nodes so that a launch has enough blocks to
 // fill the GPU but every block still pipelines over several chunks.
-void build_groups(Sched& sc, int tiles, bool site_specific) {
+void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm) {
   sc.group_ptr.clear();
   sc.launches.clear();
   // Site-specific kernels load a per-pattern eigen-system per block (longer runs amortise it) and are
   // issue-bound, so a partly filled last wave costs its full duration: size the grid of a level to fill
-  // whole waves of the 2 blocks/SM these kernels run at.
-  const long long slots = 148LL * 2;
+  // whole waves of the 2 blocks/SM these kernels run at (3 for the symmetric variant).
+  long long slots = 148LL * ss_blocks_per_sm;
+  if (const char* e = getenv("TTB_SS_SLOTS")) slots = std::max(1LL, atoll(e));
   // single-model kernels: ~2 waves of 3 blocks/SM per level -- longer runs amortise a block's prologue and first
   // bulk copy (measured: 888 vs 4736 blocks per level: cfg2 0.95 -> 0.75 ms, cfg3 14.26 -> 14.13 ms, cfg4 2.33 -> 2.20 ms)
   long long target_blocks = site_specific ? slots * 4 : 148LL * 6;
@@ -399,16 +404,17 @@ int ensure_state(ttb_handle h, bool tips) {
   const size_t pq = (q * q + 1) / 2 * 2, tus = ((size_t)h->n_codes * q + 1) / 2 * 2;
   if ((rc = h->d_P.alloc((size_t)h->n_nodes * pq))) return rc;
   if ((rc = h->d_TU.alloc((size_t)h->n_tips * tus))) return rc;
-  if (h->sched_tiles != h->tiles() || h->sched_ss != h->site_specific) {
+  const int ss_mode = h->site_specific ? (h->ss_sym ? 2 : 1) : 0;
+  if (h->sched_tiles != h->tiles() || h->sched_ss != ss_mode) {
     for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all}) {
-      build_groups(*sc, h->tiles(), h->site_specific);
+      build_groups(*sc, h->tiles(), h->site_specific, ss_mode == 2 ? 3 : 2);
       if ((rc = upload(sc->d_group_ptr, sc->group_ptr.data(), sc->group_ptr.size(), h->stream))) return rc;
     }
     CK(cudaStreamSynchronize(h->stream));
     h->n_fgroups = 0;
     for (const TtbLevelLaunch& L : h->post.launches) h->n_fgroups += L.n_groups;
     h->sched_tiles = h->tiles();
-    h->sched_ss = h->site_specific;
+    h->sched_ss = ss_mode;
     h->drop_graphs();
   }
   if ((rc = h->d_F.alloc((size_t)h->n_fgroups * ld))) return rc;
@@ -517,6 +523,7 @@ int ttb_destroy(ttb_handle h) {
   h->d_sg_states.release();
   h->d_sg_uniforms.release();
   h->d_idx_prev.release(); h->d_idxtip_prev.release(); h->d_scount.release();
+  h->d_ss_c.release(); h->d_ss_Ec.release();
   h->post.d_chunks.release(); h->pre_int.d_chunks.release(); h->pre_all.d_chunks.release();
   h->d_idx.release();
   h->d_idxtip.release();
@@ -854,7 +861,47 @@ int ttb_set_gtr_site_specific(ttb_handle h, const double* eigvals, const double*
     h->launches += 1;
     CK(cudaGetLastError());
   }
-  CK(cudaStreamSynchronize(h->stream));   // V / Vi are locals
+  // Symmetric structure of a reversible model's eigen-system (GTR._eig_single_site, gtr.py:612-629):
+  // Vinv[k][j] = V[j][k] * c_k / Pi[j].  If every pattern has it (to 1e-9 of the largest entry) the level kernels use
+  // the symmetric form; anything else keeps the general kernels.  TTB_SS_SYM=0 in the environment forces the latter.
+  bool sym = q <= TTB_SS_REG_MAXQ;
+  if (const char* e = getenv("TTB_SS_SYM")) sym = sym && atoi(e) != 0;
+  std::vector<double> C;
+  if (sym) {
+    C.assign(q * L, 0.0);
+    for (size_t a = 0; a < L && sym; ++a) {
+      double vmax = 0.0;
+      for (size_t r = 0; r < q * q; ++r) vmax = std::max(vmax, std::fabs(Vi[r * L + a]));
+      for (size_t k = 0; k < q && sym; ++k) {
+        size_t js = 0;
+        for (size_t j = 1; j < q; ++j)
+          if (std::fabs(V[(j * q + k) * L + a]) > std::fabs(V[(js * q + k) * L + a])) js = j;
+        const double vjk = V[(js * q + k) * L + a];
+        if (vjk == 0.0) { sym = false; break; }
+        const double c = Vi[(k * q + js) * L + a] * Pi[js * L + a] / vjk;
+        C[k * L + a] = c;
+        for (size_t j = 0; j < q; ++j) {
+          const double pj = Pi[j * L + a];
+          if (!(pj > 0.0) || !(std::fabs(Vi[(k * q + j) * L + a] - V[(j * q + k) * L + a] * c / pj) <= 1e-9 * vmax)) { sym = false; break; }
+        }
+      }
+    }
+  }
+  h->ss_sym = sym;
+  if (sym) {
+    if ((rc = upload_planes(h, h->d_ss_c, C.data(), q))) return rc;
+    if ((rc = h->d_ss_Ec.alloc((size_t)h->tiles() * n_grid * q * TTB_TILE))) return rc;
+    const bool was = h->site_specific;
+    h->site_specific = true;
+    ss_grid_table_kernel<<<148 * 8, 256, 0, h->stream>>>(h->dev(), h->d_ss_Ec.p, h->d_ss_c.p);
+    h->site_specific = was;
+    h->launches += 1;
+    CK(cudaGetLastError());
+  } else {
+    h->d_ss_c.release();
+    h->d_ss_Ec.release();
+  }
+  CK(cudaStreamSynchronize(h->stream));   // V / Vi / C are locals
   h->ss_tmax = approximate ? 10.0 / rate_scale : 0.0;
   h->ss_interp_dirty = true;
   h->gap_index = gap_index;

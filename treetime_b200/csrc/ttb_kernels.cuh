@@ -79,6 +79,12 @@ struct TtbDev {
   const double2* ss_rec;  // [n_nodes] {ss_w, t}: 16-byte records the level kernels stage with one bulk copy per child
   const double* ss_E;     // [tiles][ss_ngrid][q][128] exp(t_g mu_a lambda_k(a)) on the grid, tile-blocked like the messages:
                           // the two grid rows of a branch are one contiguous 2q KB block per tile (no exp in the level kernels)
+  // symmetric form (reversible models, gtr.py:612-629): Vinv_a[k][j] = V_a[j][k] * c_k / Pi_a[j] with c_k the squared
+  // 1-norm of eigenvector k.  When the uploaded model has this structure (checked at upload) the level kernels keep only
+  // V_a and 1/Pi_a in registers (q^2 + q instead of 2 q^2 doubles) and read the eigen-factors pre-multiplied by c_k.
+  int ss_sym;
+  const double* ss_c;     // [q][ld]      c_k of pattern a at k*ld + a
+  const double* ss_Ec;    // like ss_E, every entry times c_k(a)
   const double* ss_grid;  // [ss_ngrid] the grid itself (branch objective at trial lengths)
   int ss_ngrid;
   double ss_tmax;         // interpolate while t < ss_tmax (= 10 / rate_scale), 0 = never
@@ -250,7 +256,7 @@ __device__ __forceinline__ double at_least(double x, double lo) {
   return __longlong_as_double(xb > lb ? xb : lb);
 }
 
-template <int Q, bool REG = false>
+template <int Q, bool REG = false, bool SYM = false>
 struct SiteModel {
   const double* V;    // V_a[i][k] at V[(i*Q+k)*vs]
   const double* Vi;   // Vinv_a[k][j] at Vi[(k*Q+j)*vs]
@@ -262,7 +268,10 @@ struct SiteModel {
   // REG: this pattern's eigen-system held in registers for the whole block (2*Q*Q doubles; Q <= 5).
   // The level kernels handle one pattern per thread for a whole run of nodes, so the 2*Q*Q shared-memory
   // loads per matvec pair of the staged variant (the measured limiter at q = 5) disappear.
-  double Vr[REG ? Q * Q : 1], Vir[REG ? Q * Q : 1];
+  // SYM (with REG): only V_a and r_j = 1/Pi_a[j]; Vinv_a[k][j] = V_a[j][k] c_k r_j with c_k folded into the eigen-factors
+  // (grid table ss_Ec; the exact path multiplies by c_k from the planes at cpl).
+  double Vr[REG ? Q * Q : 1], Vir[(REG && !SYM) ? Q * Q : 1], rr[(REG && SYM) ? Q : 1];
+  const double* cpl;
   __device__ SiteModel() {}
   // model planes read from global memory (fetch / branch kernels)
   __device__ SiteModel(const TtbDev& p, long long a)
@@ -273,13 +282,20 @@ struct SiteModel {
         E(e_column(p, a)) {}
   // this pattern's column of the tile-blocked grid table: row (g, k) at E[(g*Q + k) * TTB_TILE]
   __device__ static __forceinline__ const double* e_column(const TtbDev& p, long long a) {
-    return p.ss_E + (size_t)(a / TTB_TILE) * ((size_t)p.ss_ngrid * Q * TTB_TILE) + (size_t)(a % TTB_TILE);
+    return (SYM ? p.ss_Ec : p.ss_E) + (size_t)(a / TTB_TILE) * ((size_t)p.ss_ngrid * Q * TTB_TILE) + (size_t)(a % TTB_TILE);
   }
   // level kernels: registers (REG) or the staged tile
   __device__ __forceinline__ void init_level(const TtbDev& p, long long a, bool act, const double* smem_model, int tid) {
     lam = p.ss_eig + a; ld = p.ld; E = e_column(p, a);
     mu = act ? p.ss_mu[a] : 0.0;
-    if constexpr (REG) {
+    if constexpr (REG && SYM) {
+      V = Vi = nullptr; vs = 0;
+      cpl = p.ss_c + a;
+#pragma unroll
+      for (int r = 0; r < Q * Q; ++r) Vr[r] = act ? __ldg(p.ss_V + (size_t)r * p.ld + a) : 0.0;
+#pragma unroll
+      for (int j = 0; j < Q; ++j) rr[j] = act ? 1.0 / __ldg(p.ss_Pi + (size_t)j * p.ld + a) : 0.0;
+    } else if constexpr (REG) {
       V = Vi = nullptr; vs = 0;
 #pragma unroll
       for (int r = 0; r < Q * Q; ++r) {
@@ -296,6 +312,9 @@ struct SiteModel {
   // inlined exp() bodies do not inflate the level kernels' register pressure
   __device__ __noinline__ static void efac_exact(double tmu, const double* lam, long long ld, double* e) {
     for (int k = 0; k < Q; ++k) e[k] = exp(tmu * __ldg(lam + (size_t)k * ld));
+  }
+  __device__ __noinline__ static void efac_exact_sym(double tmu, const double* lam, const double* c, long long ld, double* e) {
+    for (int k = 0; k < Q; ++k) e[k] = __ldg(c + (size_t)k * ld) * exp(tmu * __ldg(lam + (size_t)k * ld));
   }
   __device__ __forceinline__ void efac_at(double t, int lo, double w, double (&e)[Q]) const {
     if (w < 0.0) {
@@ -316,7 +335,8 @@ struct SiteModel {
   __device__ __forceinline__ void efac_staged(double t, double w, const double* rows, double (&e)[Q]) const {
     if (w < 0.0) {
       double ex[Q];   // only this array lives in local memory; e[] stays in registers on the hot path
-      efac_exact(t * mu, lam, ld, ex);
+      if constexpr (SYM) efac_exact_sym(t * mu, lam, cpl, ld, ex);
+      else efac_exact(t * mu, lam, ld, ex);
 #pragma unroll
       for (int k = 0; k < Q; ++k) e[k] = ex[k];
     } else {
@@ -333,6 +353,24 @@ struct SiteModel {
   // child -> parent: U[j] = max(1e-12, sum_i S[i] P[i][j])
   __device__ __forceinline__ void up(const double (&S)[Q], const double (&e)[Q], double (&U)[Q], bool clamp = true) const {
     double wk[Q];
+    if constexpr (REG && SYM) {   // U[j] = r_j sum_k V[j][k] (c_k e_k) sum_i S[i] V[i][k]
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) acc = fma(S[i], Vr[i * Q + k], acc);
+        wk[k] = acc * e[k];
+      }
+#pragma unroll
+      for (int j = 0; j < Q; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < Q; ++k) acc = fma(wk[k], Vr[j * Q + k], acc);
+        acc *= rr[j];
+        U[j] = clamp ? at_least(acc, TTB_TINY) : acc;
+      }
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
       double acc = 0.0;
@@ -351,6 +389,26 @@ struct SiteModel {
   // parent -> child: msg[i] = sum_j P[i][j] O[j]
   __device__ __forceinline__ void down(const double (&O)[Q], const double (&e)[Q], double (&msg)[Q]) const {
     double wk[Q];
+    if constexpr (REG && SYM) {   // msg[i] = sum_k V[i][k] (c_k e_k) sum_j V[j][k] r_j O[j]
+      double y[Q];
+#pragma unroll
+      for (int j = 0; j < Q; ++j) y[j] = rr[j] * O[j];
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) acc = fma(Vr[j * Q + k], y[j], acc);
+        wk[k] = acc * e[k];
+      }
+#pragma unroll
+      for (int i = 0; i < Q; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < Q; ++k) acc = fma(Vr[i * Q + k], wk[k], acc);
+        msg[i] = acc;
+      }
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
       double acc = 0.0;
@@ -369,6 +427,13 @@ struct SiteModel {
 };
 // site-specific level kernels keep the eigen-system in registers up to this alphabet size
 #define TTB_SS_REG_MAXQ 5
+// symmetric variant: register cap and ring depth chosen so that three blocks (12 pattern warps) fit one SM
+#ifndef TTB_SS_SYM_REGS
+#define TTB_SS_SYM_REGS 128
+#endif
+#ifndef TTB_SS_SYM_STAGES
+#define TTB_SS_SYM_STAGES 2
+#endif
 // ... and then the level kernels also stage, per child, the two grid rows of its branch (2q KB per tile, in the
 // stage's P area) and its {w, t} record (16 bytes, in the TU area): no global load is left on the consumers' path.
 template <int Q, bool SS>
@@ -495,13 +560,13 @@ __global__ void __launch_bounds__(TTB_BLOCK) joint_pre_level_kernel(TtbDev p, co
 
 // E[g][k][a] = exp(t_g * mu_a * lambda_k(a)): the eigen-factor of gtr_site_specific._expQt (:363) on the
 // interpolation grid (:336-344).  One thread per (g, k, a).
-static __global__ void ss_grid_table_kernel(TtbDev p, double* __restrict__ E) {
+static __global__ void ss_grid_table_kernel(TtbDev p, double* __restrict__ E, const double* __restrict__ c = nullptr) {
   const long long n = (long long)p.tiles * p.ss_ngrid * p.q * TTB_TILE;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int lane = (int)(i % TTB_TILE);
     const int k = (int)((i / TTB_TILE) % p.q), g = (int)((i / ((long long)TTB_TILE * p.q)) % p.ss_ngrid);
     const long long a = (i / ((long long)TTB_TILE * p.q * p.ss_ngrid)) * TTB_TILE + lane;
-    E[i] = (a < p.Lp) ? exp(p.ss_grid[g] * p.ss_mu[a] * p.ss_eig[(size_t)k * p.ld + a]) : 1.0;
+    E[i] = (a < p.Lp) ? (c ? c[(size_t)k * p.ld + a] : 1.0) * exp(p.ss_grid[g] * p.ss_mu[a] * p.ss_eig[(size_t)k * p.ld + a]) : 1.0;
   }
 }
 
@@ -517,9 +582,9 @@ static __global__ void ss_patch_chunks_kernel(TtbChunk* __restrict__ chunks, int
 // ---------------------------------------------------------------------------------------
 // Shared-memory ring of the level kernels.
 // ---------------------------------------------------------------------------------------
-template <int Q>
+template <int Q, int NST = ((Q <= 8) ? 3 : 2)>
 struct Pipe {
-  static constexpr int STAGES = (Q <= 8) ? 3 : 2;
+  static constexpr int STAGES = NST;
   static constexpr int CB = (Q <= 8) ? TTB_CB : 1;   // children per chunk (the host schedule uses the same rule)
   // per-stage byte offsets (all multiples of 16)
   int off_P, off_TU, off_codes, off_oidx, off_desc, stage_bytes;
@@ -621,14 +686,16 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // Block = (run of nodes of the level given by group_ptr, one 128-pattern tile).
 // Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool SS, bool JOINT = false>
-__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? 168 : 255) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+template <int Q, bool SS, bool JOINT = false, bool SYM = false>
+__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : 255) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles, int fbase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int RPC = Q;  // rows per child (the log-prefactors never travel: see Fpart)
   constexpr bool EST = ss_staged<Q, SS>();   // site-specific, grid rows + branch record staged per child
   constexpr int EROWS = 2 * Q * TTB_TILE;
-  Pipe<Q> pipe(smem_raw, Pipe<Q>::CB * RPC, stage_pq<Q, SS>(p.pq), stage_tu<Q, SS>(p.tu_stride));
+  static_assert(!SYM || (SS && Q <= TTB_SS_REG_MAXQ && !JOINT), "SYM is a variant of the register-resident site-specific kernels");
+  using PipeT = Pipe<Q, SYM ? TTB_SS_SYM_STAGES : Pipe<Q>::STAGES>;
+  PipeT pipe(smem_raw, PipeT::CB * RPC, stage_pq<Q, SS>(p.pq), stage_tu<Q, SS>(p.tu_stride));
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
   const int n_chunks = k1 - k0;
@@ -641,7 +708,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   if (tid == 0) pipe.init();
   __syncthreads();
 
-  typename Pipe<Q>::Cursor cur;
+  typename PipeT::Cursor cur;
   auto issue = [&](int u, const Chunk& c) {  // executed by the producer warp: fill the stage of chunk number u
     const int s = cur.s;
     pipe.producer_acquire(cur, u);
@@ -667,7 +734,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
         if (EST) {
           tma_load_1d(pipe.TU(s) + b * 2, p.ss_rec + c.cnode(b), 16, bar);
           if (b == 0 || c.lo1 != c.lo0)
-            tma_load_1d(pipe.P(s) + c.erow(b) * EROWS, p.ss_E + ((size_t)tile * p.ss_ngrid + c.lo(b)) * (Q * TTB_TILE), EROWS * 8, bar);
+            tma_load_1d(pipe.P(s) + c.erow(b) * EROWS, (SYM ? p.ss_Ec : p.ss_E) + ((size_t)tile * p.ss_ngrid + c.lo(b)) * (Q * TTB_TILE), EROWS * 8, bar);
         }
       } else if (src >= 0) {
         if (r == 0)   // the child's q rows of this tile are one contiguous block
@@ -701,7 +768,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     return;
   }
   if (SS && !MREG) pipe.wait_model();
-  SiteModel<Q, MREG> sm;
+  SiteModel<Q, MREG, SYM> sm;
   if constexpr (SS) sm.init_level(p, a, act, pipe.model, tid);
   pdl_wait();
 
@@ -1202,13 +1269,14 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // Tips take part only with TIPS (reconstruct_tip_states).
 // Stage rows: [0, Q) parent profile, child b -> rows [Q + b*Q, Q + (b+1)*Q) = S_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool TIPS, bool SS>
-__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? 168 : 255) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+template <int Q, bool TIPS, bool SS, bool SYM = false>
+__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : 255) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool EST = ss_staged<Q, SS>();
   constexpr int EROWS = 2 * Q * TTB_TILE;
-  Pipe<Q> pipe(smem_raw, Q + Pipe<Q>::CB * Q, stage_pq<Q, SS>(p.pq), stage_tu<Q, SS>(p.tu_stride));
+  using PipeT = Pipe<Q, SYM ? TTB_SS_SYM_STAGES : Pipe<Q>::STAGES>;
+  PipeT pipe(smem_raw, Q + PipeT::CB * Q, stage_pq<Q, SS>(p.pq), stage_tu<Q, SS>(p.tu_stride));
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int k0 = group_ptr[g], k1 = group_ptr[g + 1];
   const int n_chunks = k1 - k0;
@@ -1221,7 +1289,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   if (tid == 0) pipe.init();
   __syncthreads();
 
-  typename Pipe<Q>::Cursor cur;
+  typename PipeT::Cursor cur;
   auto issue = [&](int u, const Chunk& c) {  // executed by the producer warp
     const int s = cur.s;
     pipe.producer_acquire(cur, u);
@@ -1253,7 +1321,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
         else if (EST) {
           tma_load_1d(pipe.TU(s) + b * 2, p.ss_rec + c.cnode(b), 16, bar);
           if (b == 0 || c.lo1 != c.lo0)
-            tma_load_1d(pipe.P(s) + c.erow(b) * EROWS, p.ss_E + ((size_t)tile * p.ss_ngrid + c.lo(b)) * (Q * TTB_TILE), EROWS * 8, bar);
+            tma_load_1d(pipe.P(s) + c.erow(b) * EROWS, (SYM ? p.ss_Ec : p.ss_E) + ((size_t)tile * p.ss_ngrid + c.lo(b)) * (Q * TTB_TILE), EROWS * 8, bar);
         }
       } else if (src >= 0) {
         if (r == 0)
@@ -1289,7 +1357,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     return;
   }
   if (SS && !MREG) pipe.wait_model();
-  SiteModel<Q, MREG> sm;
+  SiteModel<Q, MREG, SYM> sm;
   if constexpr (SS) sm.init_level(p, a, act, pipe.model, tid);
   pdl_wait();
 

@@ -10,12 +10,14 @@
 namespace {
 constexpr int Q = TTB_Q;
 
-size_t level_smem(int rows, const TtbDev& d, bool ss) {
+constexpr bool HAS_SYM = (Q <= TTB_SS_REG_MAXQ);   // symmetric register-resident site-specific kernels
+size_t level_smem(int rows, const TtbDev& d, bool ss, bool sym = false) {
+  if (ss && sym) return Pipe<Q, TTB_SS_SYM_STAGES>::smem_bytes(rows, stage_pq<Q, true>(d.pq), stage_tu<Q, true>(d.tu_stride), true);
   return ss ? Pipe<Q>::smem_bytes(rows, stage_pq<Q, true>(d.pq), stage_tu<Q, true>(d.tu_stride), true)
             : Pipe<Q>::smem_bytes(rows, d.pq, d.tu_stride, false);
 }
-size_t post_smem(const TtbDev& d, bool ss = false) { return level_smem(Pipe<Q>::CB * Q, d, ss); }
-size_t pre_smem(const TtbDev& d, bool ss = false) { return level_smem(Q + Pipe<Q>::CB * Q, d, ss); }
+size_t post_smem(const TtbDev& d, bool ss = false, bool sym = false) { return level_smem(Pipe<Q>::CB * Q, d, ss, sym); }
+size_t pre_smem(const TtbDev& d, bool ss = false, bool sym = false) { return level_smem(Q + Pipe<Q>::CB * Q, d, ss, sym); }
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait() in ttb_kernels.cuh).
 template <typename... KArgs, typename... Args>
@@ -42,6 +44,11 @@ int prepare_t(const TtbDev& d) {
   if (!SS && (e = cudaFuncSetAttribute(post_level_kernel<Q, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, false))) != cudaSuccess) return (int)e;
   if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
   if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
+  if constexpr (SS && HAS_SYM) {
+    if ((e = cudaFuncSetAttribute(post_level_kernel<Q, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, true, true))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, true, true))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, true, true))) != cudaSuccess) return (int)e;
+  }
   return 0;
 }
 
@@ -53,7 +60,7 @@ int prepare_q(const TtbDev& d) {
   return 0;
 }
 
-template <bool SS>
+template <bool SS, bool SYM = false>
 int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
   const TtbDev& d = pl.d;
   const int tiles = pl.tiles;
@@ -67,7 +74,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
     nk += 2;
   }
   if (ev) { cudaEventRecord(ev[1], s); pk[0] = nk; }
-  const size_t psm = post_smem(d, SS);
+  const size_t psm = post_smem(d, SS, SYM);
   int l0 = 0;
   if (!SS) {
     // level 1 (all children are tips) is a pure write stream: dedicated kernel, no pipeline
@@ -80,7 +87,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   int fbase = l0 ? pl.post_levels[0].n_groups : 0;
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
-    launch_pdl(post_level_kernel<Q, SS>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d, pl.d_post_chunks,
+    launch_pdl(post_level_kernel<Q, SS, false, SYM>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d, pl.d_post_chunks,
                pl.d_post_group_ptr + L.group_off, tiles, fbase);
     fbase += L.n_groups;
     ++nk;
@@ -95,15 +102,15 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   }
   if (ev) { cudaEventRecord(ev[3], s); pk[2] = nk - pk[0] - pk[1]; }
   if (!pl.lh_only) {
-    const size_t rsm = pre_smem(d, SS);
+    const size_t rsm = pre_smem(d, SS, SYM);
     for (int l = 0; l < pl.n_pre_levels; ++l) {
       const TtbLevelLaunch& L = pl.pre_levels[l];
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
       if (pl.tips)
-        launch_pdl(pre_level_kernel<Q, true, SS>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
+        launch_pdl(pre_level_kernel<Q, true, SS, SYM>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
                    pl.count_diff);
       else
-        launch_pdl(pre_level_kernel<Q, false, SS>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
+        launch_pdl(pre_level_kernel<Q, false, SS, SYM>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
                    pl.count_diff);
       ++nk;
     }
@@ -116,6 +123,9 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
 }
 
 int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
+  if constexpr (HAS_SYM) {
+    if (pl.d.site_specific && pl.d.ss_sym) return enqueue_pass_t<true, true>(pl, s, ev, pk);
+  }
   if constexpr (HAS_SS) {
     if (pl.d.site_specific) return enqueue_pass_t<true>(pl, s, ev, pk);
   }
