@@ -224,6 +224,12 @@ int ttb_branch_hamming(ttb_handle h, int32_t n_eval, const int32_t* nodes, const
  * n_ij[q][q] and T_i[q] summed over this shard's patterns and all branches. */
 int ttb_mutation_counts(ttb_handle h, double* n_ij, double* T_i);
 
+/* The same statistics per pattern, before the sum over patterns: n_ija[q][q][n_patterns] and T_ia[q][n_patterns]
+ * (treeanc.py:1551-1572) -- the input of GTR_site_specific.infer (gtr_site_specific.py:207-310), i.e. of
+ * infer_gtr(marginal=True, site_specific=True).  Works for single and for site-specific current models (the latter
+ * with the per-pattern transition matrices, treeanc.py:1107-1108). */
+int ttb_mutation_counts_per_site(ttb_handle h, double* n_ija, double* T_ia);
+
 /* Bytes of device memory currently held by the handle. */
 int ttb_device_bytes(ttb_handle h, int64_t* bytes);
 /* Kernel launches issued by the library since creation (bench.py's gpu_launches). */

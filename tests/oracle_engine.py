@@ -211,6 +211,9 @@ class OracleEngine(object):
         n_ija, T_ia = O.mutation_counts(self._pass_flat(), self.g_pass, self.res)
         return n_ija.sum(axis=-1), T_ia.sum(axis=-1)
 
+    def mutation_counts_per_site(self):
+        return O.mutation_counts(self._pass_flat(), self.g_pass, self.res)
+
     def launch_count(self):
         return self.launches
 

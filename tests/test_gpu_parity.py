@@ -429,6 +429,34 @@ def test_sample_states(kind):
         eng.sample_states(nodes[:1], U[:1])       # the last pass did not keep the previous states
 
 
+@pytest.mark.parametrize('kind', ['nuc', 'aa', 'ss', 'ss_exact'])
+def test_mutation_counts_per_site(kind):
+    """A10 per pattern: n_ija (q,q,L') and T_ia (q,L') of infer_gtr (treeanc.py:1551-1572) before the sum over
+    patterns, single and site-specific current models; the totals equal ttb_mutation_counts."""
+    if kind.startswith('ss'):
+        from treetime_b200.gtr import GTRSiteSpecific
+        gtr = GTRSiteSpecific.random(L=260, alphabet='nuc', rng=np.random.default_rng(23))
+        gtr.approximate = kind == 'ss'
+        tree = synth.random_tree(35, seed=14, mean_bl=0.06)
+        topo, flat, g = util.make_flat(tree, gtr, 260, 14, amb_frac=0.02, compress=False)
+    else:
+        gtr = util.nuc_gtr() if kind == 'nuc' else util.random_gtr('aa', 4)
+        tree = synth.random_tree(50, seed=15, mean_bl=0.05)
+        topo, flat, g = util.make_flat(tree, gtr, 400, 15, amb_frac=0.02)
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    eng.results()
+    res = O.marginal(flat, g)
+    n_ija, T_ia = O.mutation_counts(flat, g, res)
+    a, b = eng.mutation_counts_per_site()
+    assert a.shape == n_ija.shape and b.shape == T_ia.shape
+    assert np.allclose(a, n_ija, rtol=1e-9, atol=1e-12), np.abs(a - n_ija).max()
+    assert np.allclose(b, T_ia, rtol=1e-9, atol=1e-14), np.abs(b - T_ia).max()
+    if not kind.startswith('ss'):
+        n_ij, T_i = eng.mutation_counts()
+        assert np.allclose(n_ij, a.sum(axis=-1), rtol=1e-11) and np.allclose(T_i, b.sum(axis=-1), rtol=1e-11)
+
+
 def test_api_errors():
     from treetime_b200.engine import Engine
     from treetime_b200._lib import TTBError

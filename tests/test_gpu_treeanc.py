@@ -250,3 +250,22 @@ def test_gpu_sample_from_profile_all_nodes():
         assert abs(na - nb) <= 2 * diff and na > 0
     assert a.rng.random() == b.rng.random()
     assert a._engine.launch_count() > 0
+
+
+def test_gpu_infer_site_specific_gtr():
+    """infer_gtr(marginal=True, site_specific=True): the device's per-pattern statistics give the same
+    GTRSiteSpecific as the CPU oracle engine (pinned to the reference in test_reference_live), and the following
+    reconstruction under that model agrees."""
+    import oracle_engine
+    z = G.load('nuc40')
+    a = gpu_from_golden(z, compress=False)
+    b = gpu_from_golden(z, compress=False, engine_factory=oracle_engine.factory)
+    for tt in (a, b):
+        tt.infer_ancestral_sequences(marginal=True)
+    for it in range(2):
+        ga = a.infer_gtr(marginal=True, site_specific=True, pc=1.0)
+        gb = b.infer_gtr(marginal=True, site_specific=True, pc=1.0)
+        assert ga.is_site_specific
+        assert np.allclose(ga.Pi, gb.Pi, rtol=1e-8, atol=1e-12) and np.allclose(ga.mu, gb.mu, rtol=1e-8) and np.allclose(ga.W, gb.W, rtol=1e-8)
+        a.infer_ancestral_sequences(marginal=True); b.infer_ancestral_sequences(marginal=True)
+        assert abs(a.sequence_LH() - b.sequence_LH()) <= LH_RTOL * abs(b.sequence_LH())

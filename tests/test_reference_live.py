@@ -368,3 +368,49 @@ def test_sample_from_profile_all_nodes_matches_reference():
         for n in m2.tree.find_clades():
             if not n.is_terminal():
                 assert (n.cseq == rn[n.name].cseq).all()
+
+
+def test_site_specific_gtr_inference_matches_reference():
+    """infer_gtr(marginal=True, site_specific=True) (treeanc.py:1551-1627 + GTR_site_specific.infer): per-pattern
+    statistics from the engine, first under a single model, then under the inferred site-specific model (per-pattern
+    transition matrices), through the drop-in and through the mirror."""
+    rt, dt = _pair(seed=52, n=20, L=120, compress=False)
+    assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
+    for it in range(2):
+        g1 = rt.infer_gtr(marginal=True, site_specific=True, pc=1.0)
+        launches = dt._engine.launch_count()
+        g2 = dt.infer_gtr(marginal=True, site_specific=True, pc=1.0)
+        assert dt._b200_live
+        assert np.allclose(g1.Pi, g2.Pi, rtol=1e-10, atol=1e-14) and np.allclose(g1.mu, g2.mu, rtol=1e-10)
+        assert np.allclose(g1.W, g2.W, rtol=1e-10)
+        assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
+        assert np.isclose(rt.sequence_LH(), dt.sequence_LH(), rtol=1e-11)
+    # a single model inferred from a site-specific one: totals of the per-pattern statistics
+    g1 = rt.infer_gtr(marginal=True, site_specific=False, pc=1.0)
+    g2 = dt.infer_gtr(marginal=True, site_specific=False, pc=1.0)
+    assert np.allclose(g1.Pi, g2.Pi, rtol=1e-10) and np.allclose(g1.W, g2.W, rtol=1e-10)
+    # compressed data + site-specific inference is refused like in the reference
+    rt2, dt2 = _pair(seed=53, n=10, L=60)
+    dt2.infer_ancestral_sequences(marginal=True)
+    with pytest.raises(TypeError):
+        dt2.infer_gtr(marginal=True, site_specific=True)
+    # the mirror: own GTRSiteSpecific from the same statistics
+    refenv.activate()
+    import oracle_engine
+    from treetime import GTR as RG
+    from treetime_b200 import synth
+    from treetime_b200.gtr import GTR
+    from treetime_b200.treeanc import TreeAnc
+    pi = np.array([.3, .2, .2, .29, .01])
+    T = synth.random_tree(15, seed=54, mean_bl=0.03)
+    g = GTR.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc')
+    idx = synth.evolve_alignment(T, 90, g.Pi, g.W, seed=54)
+    aln = {k: g.alphabet[v] for k, v in idx.items()}
+    r3 = refenv.reference_treeanc(T.to_newick(), aln, RG.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc'), rng_seed=7, compress=False)
+    m3 = TreeAnc(tree=T.to_newick(), aln=aln, gtr=g, rng_seed=7, compress=False, engine_factory=oracle_engine.factory)
+    r3.infer_ancestral_sequences(marginal=True); m3.infer_ancestral_sequences(marginal=True)
+    a = r3.infer_gtr(marginal=True, site_specific=True, pc=2.0)
+    b = m3.infer_gtr(marginal=True, site_specific=True, pc=2.0)
+    assert np.allclose(a.Pi, b.Pi, rtol=1e-10, atol=1e-14) and np.allclose(a.mu, b.mu, rtol=1e-10) and np.allclose(a.W, b.W, rtol=1e-10)
+    assert r3.infer_ancestral_sequences(marginal=True) == m3.infer_ancestral_sequences(marginal=True)
+    assert np.isclose(r3.sequence_LH(), m3.sequence_LH(), rtol=1e-11)

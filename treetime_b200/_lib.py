@@ -113,6 +113,7 @@ SIGNATURES = {
     'ttb_branch_objective': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_branch_hamming': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_mutation_counts': ([_H, _c_dbl_p, _c_dbl_p], ctypes.c_int),
+    'ttb_mutation_counts_per_site': ([_H, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_seqgen': ([_H, ctypes.c_uint64, _c_u8_p, _c_dbl_p, _c_u8_p, _c_u8_p], ctypes.c_int),
     'ttb_branch_state_pairs': ([_H, ctypes.c_int32, _c_int_p, ctypes.c_int32, ctypes.c_int32, _c_dbl_p, _c_int_p], ctypes.c_int),
     'ttb_device_bytes': ([_H, ctypes.POINTER(ctypes.c_int64)], ctypes.c_int),

@@ -1486,6 +1486,33 @@ int ttb_mutation_counts(ttb_handle h, double* n_ij, double* T_i) {
   return 0;
 }
 
+int ttb_mutation_counts_per_site(ttb_handle h, double* n_ija, double* T_ia) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, true)) return rc;
+  if (!n_ija || !T_ia) return fail(TTB_EINVAL, "ttb_mutation_counts_per_site: null output");
+  const int q = h->q, width = q * q + q;
+  const int tiles = h->tiles();
+  const size_t ld = (size_t)h->ld, Lp = (size_t)h->Lp;
+  // enough branch chunks to fill the GPU, bounded by 1 GB of partial sums
+  int chunks = std::max(1, std::min(h->n_nodes - 1, (148 * 8 + tiles - 1) / tiles));
+  chunks = (int)std::max<size_t>(1, std::min<size_t>((size_t)chunks, ((size_t)1 << 27) / ((size_t)width * ld)));
+  const int chunk = (h->n_nodes - 1 + chunks - 1) / chunks;
+  chunks = (h->n_nodes - 1 + chunk - 1) / chunk;
+  int rc;
+  if ((rc = h->d_partial.alloc((size_t)chunks * width * ld))) return rc;
+  if ((rc = h->d_stage.alloc((size_t)width * ld))) return rc;
+  ttb_qops(h->q)->site_counts(h->dev(), tiles, chunks, chunk, h->d_partial.p, h->d_stage.p, h->stream);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpy2DAsync(n_ija, Lp * sizeof(double), h->d_stage.p, ld * sizeof(double), Lp * sizeof(double), (size_t)q * q,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpy2DAsync(T_ia, Lp * sizeof(double), h->d_stage.p + (size_t)q * q * ld, ld * sizeof(double), Lp * sizeof(double), (size_t)q,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->d_partial.release();
+  return 0;
+}
+
 int ttb_device_bytes(ttb_handle h, int64_t* bytes) {
   if (!h || !bytes) return fail(TTB_EINVAL, "null argument");
   size_t b = h->d_codes.bytes() + h->d_code_prof.bytes() + h->d_mult.bytes() + h->d_TU.bytes() + h->d_t.bytes() +

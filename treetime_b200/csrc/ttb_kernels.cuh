@@ -1898,6 +1898,87 @@ __global__ void __launch_bounds__(TTB_BLOCK) counts_kernel(TtbDev p, int chunk, 
   }
 }
 
+// A10, per-pattern form: n_ija (q,q,L') and T_ia (q,L') exactly as infer_gtr accumulates them before summing
+// (treeanc.py:1551-1572) -- the input of GTR_site_specific.infer (gtr_site_specific.py:207-310) -- for a single
+// model or, with SS, for per-pattern transition matrices (get_branch_mutation_matrix's 'ija' branch, :1107-1108;
+// exp(Qt) interpolated or exact like everywhere else).  grid = (tiles, branch chunks); every thread owns one
+// pattern and writes its sums to partial[chunk][k][ld]; site_counts_reduce_kernel adds the chunks in fixed order.
+template <int Q, bool SS>
+__global__ void __launch_bounds__(TTB_BLOCK) site_counts_kernel(TtbDev p, int chunk, double* __restrict__ partial) {
+  __shared__ double sPc[Q * Q];
+  const long long a = (long long)blockIdx.x * TTB_BLOCK + threadIdx.x;
+  const bool act = a < p.Lp;
+  double nij[Q * Q], Ti[Q];
+#pragma unroll
+  for (int k = 0; k < Q * Q; ++k) nij[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < Q; ++k) Ti[k] = 0.0;
+  const int n0 = 1 + blockIdx.y * chunk;
+  const int n1 = min(p.n_nodes, n0 + chunk);
+  const double m = act ? p.mult[a] : 0.0;
+  for (int n = n0; n < n1; ++n) {
+    if constexpr (!SS) {
+      __syncthreads();
+      for (int k = threadIdx.x; k < Q * Q; k += TTB_BLOCK) sPc[k] = p.P[(size_t)n * p.pq + k] + TTB_SUPERTINY;
+      __syncthreads();
+    }
+    if (!act) continue;
+    double pp[Q], pc[Q];
+    branch_profiles<Q, SS>(p, n, 0, a, pp, pc);
+    double tot = 0.0;
+    double mm[Q * Q];
+    if constexpr (SS) {
+      const SiteModel<Q> sm(p, a);
+      double e[Q];
+      sm.efac(p, n, e);
+#pragma unroll
+      for (int i = 0; i < Q; ++i)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          double pij = 0.0;
+#pragma unroll
+          for (int k = 0; k < Q; ++k) pij = fma(sm.v(i * Q + k) * e[k], sm.vi(k * Q + j), pij);
+          mm[i * Q + j] = pc[i] * pp[j] * (pij + TTB_SUPERTINY);
+          tot += mm[i * Q + j];
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < Q; ++i)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          mm[i * Q + j] = pc[i] * pp[j] * sPc[i * Q + j];
+          tot += mm[i * Q + j];
+        }
+    }
+    const double w = m / tot;
+    const double ht = 0.5 * p.t[n];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+#pragma unroll
+      for (int j = 0; j < Q; ++j) {
+        const double x = mm[i * Q + j] * w;
+        nij[i * Q + j] += x;
+        Ti[i] += ht * x;
+        Ti[j] += ht * x;
+      }
+  }
+  if (!act) return;
+  double* out = partial + (size_t)blockIdx.y * (Q * Q + Q) * p.ld + a;
+#pragma unroll
+  for (int k = 0; k < Q * Q; ++k) out[(size_t)k * p.ld] = nij[k];
+#pragma unroll
+  for (int k = 0; k < Q; ++k) out[(size_t)(Q * Q + k) * p.ld] = Ti[k];
+}
+
+// out[k][a] = sum over chunks of partial[chunk][k][a]  (rows = width * ld elements per chunk)
+static __global__ void site_counts_reduce_kernel(const double* __restrict__ partial, int n_part, long long rows, double* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < n_part; ++b) s += partial[(size_t)b * rows + i];
+    out[i] = s;
+  }
+}
+
 static __global__ void counts_reduce_kernel(const double* __restrict__ partial, int n_part, int width, double* __restrict__ out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= width) return;

@@ -229,6 +229,17 @@ int seqgen_q(const TtbDev& d, int tiles, unsigned long long seed, const uint8_t*
   seqgen_kernel<Q, false><<<tiles, TTB_BLOCK, 0, s>>>(d, seed, root_idx, uniforms, states);
   return nk + 1;
 }
+void site_counts_q(const TtbDev& d, int tiles, int chunks, int chunk, double* partial, double* out, cudaStream_t s) {
+  bool done = false;
+  if constexpr (HAS_SS) {
+    if (d.site_specific) {
+      site_counts_kernel<Q, true><<<dim3(tiles, chunks), TTB_BLOCK, 0, s>>>(d, chunk, partial);
+      done = true;
+    }
+  }
+  if (!done) site_counts_kernel<Q, false><<<dim3(tiles, chunks), TTB_BLOCK, 0, s>>>(d, chunk, partial);
+  site_counts_reduce_kernel<<<148 * 4, 256, 0, s>>>(partial, chunks, (long long)(Q * Q + Q) * d.ld, out);
+}
 void sample_states_q(const TtbDev& d, int tiles, int n, const int* nodes, const double* uniforms, const uint8_t* prev_idx,
                      const uint8_t* prev_idxtip, unsigned long long* counts, cudaStream_t s) {
   sample_states_kernel<Q><<<dim3(tiles, n), TTB_BLOCK, 0, s>>>(d, nodes, uniforms, prev_idx, prev_idxtip, counts);
@@ -237,4 +248,4 @@ void sample_states_q(const TtbDev& d, int tiles, int n, const int* nodes, const 
 
 #define TTB_CAT2(a, b) a##b
 #define TTB_CAT(a, b) TTB_CAT2(a, b)
-extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {prepare_q, enqueue_pass_q, enqueue_joint_q, enqueue_joint_retrace_q, fetch_node_q, branch_eval_q, counts_q, seqgen_q, sample_states_q};
+extern const TtbQOps TTB_CAT(ttb_qops_, TTB_Q) = {prepare_q, enqueue_pass_q, enqueue_joint_q, enqueue_joint_retrace_q, fetch_node_q, branch_eval_q, counts_q, seqgen_q, site_counts_q, sample_states_q};

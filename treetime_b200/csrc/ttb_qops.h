@@ -49,6 +49,8 @@ struct TtbQOps {
   // N4: evolve sequences down the tree; states[n_nodes][ld]; returns #kernels
   int (*seqgen)(const TtbDev& d, int tiles, unsigned long long seed, const uint8_t* root_idx, const double* uniforms, uint8_t* states,
                 cudaStream_t s);
+  // A10 per pattern: out[q*q+q][ld] (partial: [chunks][q*q+q][ld])
+  void (*site_counts)(const TtbDev& d, int tiles, int chunks, int chunk, double* partial, double* out, cudaStream_t s);
   // sample_from_profile=True: draw the states of n nodes from their profiles (device arrays throughout)
   void (*sample_states)(const TtbDev& d, int tiles, int n, const int* nodes, const double* uniforms, const uint8_t* prev_idx,
                         const uint8_t* prev_idxtip, unsigned long long* counts, cudaStream_t s);

@@ -519,27 +519,47 @@ class DeviceMarginalMixin(object):
     def infer_gtr(self, marginal=False, site_specific=False, normalized_rate=True, fixed_pi=None, pc=5.0, **kwargs):
         """treeanc.py:1500-1632, marginal branch: the n_ij / T_i accumulation over all branches
         (:1556-1572) is one device kernel; GTR.infer (gtr.py:491-599) stays on the host."""
-        if site_specific:
-            self._unsupported('site-specific GTR inference is not provided on the device path')
+        if site_specific and self.data.compress:
+            raise TypeError('TreeAnc.infer_gtr(): sequence compression and site specific GTR models are incompatible!')
         if not marginal:
             self._unsupported('joint-mode GTR inference is outside the B200 hot path')
         if not self.ok:
             raise self._missing_data_error('TreeAnc.infer_gtr: ERROR, sequences or tree are missing')
         if self.sequence_reconstruction != 'marginal':
             self._ml_anc_marginal(**kwargs)
-        n_ij, T_i = self._engine.mutation_counts()
-        if self.comm.world_size > 1:
-            red = self.comm.allreduce_sum(np.concatenate([n_ij.ravel(), T_i]))
-            q = self.gtr.n_states
-            n_ij, T_i = red[:q * q].reshape(q, q), red[q * q:]
-        root_cseq = self.tree.root.cseq
-        m = self.data.multiplicity()
-        root_state = np.array([np.sum((root_cseq == nuc) * m) for nuc in self.gtr.alphabet])
-        self._gtr = self._infer_gtr_from_counts(n_ij, T_i, root_state, fixed_pi, pc)
+        q = self.gtr.n_states
+        if site_specific or getattr(self.gtr, 'is_site_specific', False):
+            # per-pattern statistics (treeanc.py:1551-1572 before the sum over patterns), sharded like the patterns
+            n_ija, T_ia = self._engine.mutation_counts_per_site()
+            if self.comm.world_size > 1:
+                n_ija = self.comm.allgather(n_ija, axis=2)
+                T_ia = self.comm.allgather(T_ia, axis=1)
+            n_ij, T_i = n_ija.sum(axis=-1), T_ia.sum(axis=-1)
+        else:
+            n_ij, T_i = self._engine.mutation_counts()
+            if self.comm.world_size > 1:
+                red = self.comm.allreduce_sum(np.concatenate([n_ij.ravel(), T_i]))
+                n_ij, T_i = red[:q * q].reshape(q, q), red[q * q:]
+        if site_specific:
+            root_state = self.tree.root.marginal_profile.T                      # treeanc.py:1594-1595
+            self._gtr = self._infer_site_specific_gtr_from_counts(n_ija, T_ia, root_state, pc)
+        else:
+            root_cseq = self.tree.root.cseq
+            m = self.data.multiplicity()
+            root_state = np.array([np.sum((root_cseq == nuc) * m) for nuc in self.gtr.alphabet])
+            self._gtr = self._infer_gtr_from_counts(n_ij, T_i, root_state, fixed_pi, pc)
         if normalized_rate:
             self.logger('TreeAnc.infer_gtr: setting overall rate to 1.0...', 2)
-            self._gtr.mu = 1.0
+            if site_specific:
+                self._gtr.mu /= self._gtr.average_rate().mean()                 # treeanc.py:1626-1627
+            else:
+                self._gtr.mu = 1.0
         return self._gtr
+
+    def _infer_site_specific_gtr_from_counts(self, n_ija, T_ia, root_state, pc):
+        from .gtr import infer_site_specific_gtr_from_counts
+        return infer_site_specific_gtr_from_counts(n_ija, T_ia, root_state, pc=pc, alphabet=self.gtr.alphabet,
+                                                   prof_map=self.gtr.profile_map, logger=self.logger)
 
     def _infer_gtr_from_counts(self, n_ij, T_i, root_state, fixed_pi, pc):
         return infer_gtr_from_counts(n_ij, T_i, root_state, fixed_pi=fixed_pi, pc=pc, alphabet=self.gtr.alphabet,

@@ -276,9 +276,9 @@ class B200MarginalMixin(DeviceMarginalMixin):
         return super(DeviceMarginalMixin, self).optimal_marginal_branch_length(node, tol=tol)
 
     def infer_gtr(self, marginal=False, site_specific=False, **kwargs):
-        if marginal and not site_specific and self._device_ok() is None:
+        if marginal and self._device_ok() is None:
             try:
-                gtr = DeviceMarginalMixin.infer_gtr(self, marginal=True, site_specific=False, **kwargs)
+                gtr = DeviceMarginalMixin.infer_gtr(self, marginal=True, site_specific=site_specific, **kwargs)
                 return gtr
             except Unsupported:
                 pass
@@ -289,6 +289,12 @@ class B200MarginalMixin(DeviceMarginalMixin):
         from treetime.gtr import GTR
         return GTR.infer(n_ij, T_i, root_state, fixed_pi=fixed_pi, pc=pc, alphabet=self.gtr.alphabet,
                          logger=self.logger, prof_map=self.gtr.profile_map)
+
+    def _infer_site_specific_gtr_from_counts(self, n_ija, T_ia, root_state, pc):
+        """The reference's own GTR_site_specific.infer on the device's per-pattern statistics."""
+        from treetime.gtr_site_specific import GTR_site_specific
+        return GTR_site_specific.infer(n_ija, T_ia, pc=pc, root_state=root_state, logger=self.logger,
+                                       alphabet=self.gtr.alphabet, prof_map=self.gtr.profile_map)
 
     def optimize_gtr_rate(self):
         if self._device_ok() is None and self._b200_live:

@@ -273,6 +273,14 @@ class Engine(object):
         _lib.check(self.lib.ttb_mutation_counts(self.h, _dp(n_ij), _dp(T_i)))
         return n_ij, T_i
 
+    def mutation_counts_per_site(self):
+        """(n_ija[q, q, L'], T_ia[q, L']): the statistics of mutation_counts() before the sum over patterns."""
+        q = self.n_states
+        n_ija = np.empty((q, q, self.n_patterns), dtype=np.float64)
+        T_ia = np.empty((q, self.n_patterns), dtype=np.float64)
+        _lib.check(self.lib.ttb_mutation_counts_per_site(self.h, _dp(n_ija), _dp(T_ia)))
+        return n_ija, T_ia
+
     def branch_state_pairs(self, nodes, tip_states=False):
         """(counts[n, q, W], first[n, q, W]) of ttb_branch_state_pairs: parent-state x child-state (or tip code)
         multiplicity sums and the first pattern showing each pair; W = q with tip_states else max(q, n_codes)."""

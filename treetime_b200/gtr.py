@@ -276,3 +276,48 @@ def infer_gtr_from_counts(nij, Ti, root_state, fixed_pi=None, pc=1.0, gap_limit=
         pi /= pi.sum()
     gtr.assign_rates(mu=mu, W=W_ij, pi=pi)
     return gtr
+
+
+def infer_site_specific_gtr_from_counts(sub_ija, T_ia, root_state, pc=1.0, gap_limit=0.01, Nit=30, dp=1e-5,
+                                        alphabet='nuc', prof_map=None, logger=None):
+    """Per-site model from per-site statistics: the fixed point of n_ija + pc = pi_ia W_ij mu_a (T_ja + pc + root)
+    that the reference's GTR_site_specific.infer iterates (gtr_site_specific.py:207-310).  sub_ija (q, q, L):
+    expected changes j -> i at site a, T_ia (q, L): time spent in state i, root_state (q, L): root profile.
+    Consumer of the device-side per-pattern counts (ttb_mutation_counts_per_site).  Host-only arithmetic on
+    (q, L) arrays, in the reference's order of operations."""
+    gtr = GTRSiteSpecific(alphabet=alphabet, prof_map=prof_map, logger=logger)
+    q = gtr.n_states
+    L = sub_ija.shape[-1]
+    n_ija = np.array(sub_ija, dtype=float)
+    ar = np.arange(q)
+    n_ija[ar, ar, :] = 0
+    n_ij = n_ija.sum(axis=-1)
+    m_ia = np.sum(n_ija, axis=1) + root_state + pc
+    n_a = n_ija.sum(axis=1).sum(axis=0) + pc
+    Lambda = np.sum(root_state, axis=0) + q * pc
+    p_ia_old = np.zeros((q, L))
+    p_ia = np.ones((q, L)) / q
+    mu_a = np.ones(L)
+    W_ij = np.ones((q, q)) - np.eye(q)
+    n_iter = 0
+    while np.linalg.norm(p_ia_old - p_ia) > dp and n_iter < Nit:
+        n_iter += 1
+        p_ia_old = np.copy(p_ia)
+        S_ij = np.einsum('a,ia,ja', mu_a, p_ia, T_ia)
+        W_ij = (n_ij + n_ij.T + pc) / (S_ij + S_ij.T + pc)
+        avg_pi = p_ia.mean(axis=-1)
+        average_rate = W_ij.dot(avg_pi).dot(avg_pi)
+        W_ij = W_ij / average_rate
+        mu_a *= average_rate
+        p_ia = m_ia / (mu_a * np.dot(W_ij, T_ia) + Lambda)
+        p_ia = p_ia / p_ia.sum(axis=0)
+        mu_a = n_a / (pc + np.einsum('ia,ij,ja->a', p_ia, W_ij, T_ia))
+    if n_iter >= Nit and logger is not None:
+        logger('WARNING: maximum number of iterations has been reached in GTR inference', 3, warn=True)
+    if gtr.gap_index is not None:
+        # like the single-site model, the reference resets the gap frequency of EVERY site (:293-306)
+        for a in range(L):
+            p_ia[gtr.gap_index, a] = gap_limit
+            p_ia[:, a] /= p_ia[:, a].sum()
+    gtr.assign_rates(mu=mu_a, W=W_ij, pi=p_ia)
+    return gtr
