@@ -124,6 +124,14 @@ int ttb_set_gtr_site_specific(ttb_handle h, const double* eigvals, const double*
  * (treeanc.py:752-760).  t[root] is ignored. */
 int ttb_set_branch_lengths(ttb_handle h, const double* t);
 
+/* Per-branch masks of the ARG mode (arg.py:128-133; node.mask, treeanc.py:454,489-490): masks[n_masks][n_patterns]
+ * with entries 0 / 1, node_mask[n_nodes] = row of `masks` used by the branch above that node or -1 (node.mask is None).
+ * A masked (branch, pattern) passes no information: the child's up-message is dropped (treeanc.py:862-872), the
+ * child's profile is its subtree profile (:909-917), and the pattern's multiplicity is zero in that branch's
+ * likelihood and substitution statistics (data.multiplicity(mask=node.mask), :1294,1326-1333,1564-1572).
+ * n_masks = 0 removes all masks.  A new tree or alignment also removes them.  Not available for ttb_joint. */
+int ttb_set_branch_masks(ttb_handle h, int32_t n_masks, const uint8_t* masks, const int32_t* node_mask);
+
 /* Enqueue one marginal reconstruction: batched expQt, level-ordered postorder, root,
  * level-ordered preorder (treeanc.py:762-812), one CUDA graph launch.  Asynchronous. */
 int ttb_marginal(ttb_handle h, int32_t flags);

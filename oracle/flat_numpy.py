@@ -346,9 +346,9 @@ def marginal(flat, gtr, reconstruct_tip_states=False, prev_seq_idx=None, masks=N
     return res
 
 
-def sequence_LH_only(flat, gtr):
+def sequence_LH_only(flat, gtr, masks=None):
     """The LH-only path of optimize_gtr_rate's cost function (treeanc.py:1685-1689)."""
-    res = postorder(flat, gtr)
+    res = postorder(flat, gtr, masks=masks)
     total_LH_and_root(flat, gtr, res)
     return res
 
@@ -424,8 +424,9 @@ def branch_mutation_matrix(flat, gtr, res, n):
     return np.einsum('aij,a->aij', stack, 1.0 / normalizer)
 
 
-def mutation_counts(flat, gtr, res):
-    """treeanc.py:1556-1572: n_ija (q,q,L') and T_ia (q,L') accumulated over branches."""
+def mutation_counts(flat, gtr, res, masks=None):
+    """treeanc.py:1556-1572: n_ija (q,q,L') and T_ia (q,L') accumulated over branches; masks = {node: mask[L']}
+    as in data.multiplicity(mask=c.mask)."""
     gtr = make_gtr(gtr)
     q = gtr.n_states
     L = flat['multiplicity'].shape[0]
@@ -436,9 +437,10 @@ def mutation_counts(flat, gtr, res):
     for node in range(flat['parent'].shape[0]):
         for c in flat['child_idx'][flat['child_ptr'][node]:flat['child_ptr'][node + 1]]:
             mut_stack = np.transpose(branch_mutation_matrix(flat, gtr, res, c), (1, 2, 0))
-            T_ia += 0.5 * flat['t'][c] * mut_stack.sum(axis=0) * m
-            T_ia += 0.5 * flat['t'][c] * mut_stack.sum(axis=1) * m
-            n_ija += mut_stack * m
+            mc = m if masks is None or masks.get(int(c)) is None else m * masks[int(c)]
+            T_ia += 0.5 * flat['t'][c] * mut_stack.sum(axis=0) * mc
+            T_ia += 0.5 * flat['t'][c] * mut_stack.sum(axis=1) * mc
+            n_ija += mut_stack * mc
     return n_ija, T_ia
 
 

@@ -17,6 +17,27 @@ class OracleEngine(object):
         self.prev_idx = None
         self._prev_before = None
         self.launches = 0
+        self.masks = None
+
+    def set_branch_masks(self, masks, node_mask):
+        if masks is None or len(masks) == 0:
+            self.masks = None
+        else:
+            M = np.asarray(masks, dtype=float)
+            self.masks = {n: M[k] for n, k in enumerate(node_mask) if k >= 0}
+
+    def _mult(self, n, kind=0):
+        """data.multiplicity(mask=node.mask); merged root branch: mask(n1) * mask(n2) if both exist (treeanc.py:1326-1333)."""
+        m = self.flat['multiplicity']
+        if self.masks is None:
+            return m
+        if kind == 1:
+            c0 = self.flat['child_ptr'][0]
+            n1, n2 = int(self.flat['child_idx'][c0]), int(self.flat['child_idx'][c0 + 1])
+            if n1 in self.masks and n2 in self.masks:
+                return m * (self.masks[n1] * self.masks[n2])
+            return m
+        return m * self.masks[n] if n in self.masks else m
 
     def set_stream(self, s):
         pass
@@ -28,6 +49,7 @@ class OracleEngine(object):
         self.tip_row = np.array(tip_row)
         self.res = None
         self.prev_idx = None
+        self.masks = None
 
     def set_patterns(self, tip_codes, code_profiles, multiplicity, validate=True):
         self.flat.update(tip_codes=np.array(tip_codes), code_profiles=np.array(code_profiles, dtype=float),
@@ -35,6 +57,7 @@ class OracleEngine(object):
         self.n_patterns = tip_codes.shape[1]
         self.res = None
         self.prev_idx = None
+        self.masks = None
 
     def alignment_stats(self, aln, fill_overhangs=False, gap='-', fill='N', ambiguous='N'):
         A = np.array(aln, dtype=np.uint8)
@@ -83,14 +106,14 @@ class OracleEngine(object):
     def marginal(self, reconstruct_tips=False, lh_only=False, keep_prev=False):
         self.launches += 1
         if lh_only:
-            r = O.sequence_LH_only(self.flat, self.g)
+            r = O.sequence_LH_only(self.flat, self.g, masks=self.masks)
             self._tot, self._nd = r.total_LH, 0
             self._site = r.sequence_LH
             return
         self.t_pass = self.flat['t'].copy()
         self.g_pass = dict(self.g)
         self._prev_before = list(self.prev_idx) if self.prev_idx is not None else None
-        r = O.marginal(self.flat, self.g, reconstruct_tip_states=reconstruct_tips, prev_seq_idx=self.prev_idx)
+        r = O.marginal(self.flat, self.g, reconstruct_tip_states=reconstruct_tips, prev_seq_idx=self.prev_idx, masks=self.masks)
         if self.prev_idx is None:
             pass
         self.res = r
@@ -195,7 +218,7 @@ class OracleEngine(object):
     def branch_objective(self, nodes, t, kinds=None):
         G = O.make_gtr(self.g_pass)
         kinds = np.zeros(len(nodes), dtype=int) if kinds is None else kinds
-        return np.array([G.prob_t_profiles(self._pair(int(n), int(k)), self.flat['multiplicity'], float(tt), return_log=True)
+        return np.array([G.prob_t_profiles(self._pair(int(n), int(k)), self._mult(int(n), int(k)), float(tt), return_log=True)
                          for n, k, tt in zip(nodes, kinds, t)])
 
     def branch_hamming(self, nodes, kinds=None):
@@ -204,15 +227,15 @@ class OracleEngine(object):
         num = []
         for n, k in zip(nodes, kinds):
             pp, pc = self._pair(int(n), int(k))
-            num.append(np.sum(m * np.sum(pp * pc, axis=1)))
+            num.append(np.sum(self._mult(int(n), int(k)) * np.sum(pp * pc, axis=1)))
         return np.array(num), m.sum()
 
     def mutation_counts(self):
-        n_ija, T_ia = O.mutation_counts(self._pass_flat(), self.g_pass, self.res)
+        n_ija, T_ia = O.mutation_counts(self._pass_flat(), self.g_pass, self.res, masks=self.masks)
         return n_ija.sum(axis=-1), T_ia.sum(axis=-1)
 
     def mutation_counts_per_site(self):
-        return O.mutation_counts(self._pass_flat(), self.g_pass, self.res)
+        return O.mutation_counts(self._pass_flat(), self.g_pass, self.res, masks=self.masks)
 
     def launch_count(self):
         return self.launches

@@ -465,3 +465,73 @@ def test_api_errors():
     eng = Engine(5)
     with pytest.raises(TTBError):
         eng.marginal()       # nothing set
+
+
+@pytest.mark.parametrize('kind', ['nuc', 'aa', 'ss'])
+def test_branch_masks(kind):
+    """Per-branch masks (ARG mode, treeanc.py:862-872,909-917,1294,1326-1333,1564-1572): masked up-messages are
+    dropped, masked children keep their subtree profile, masked patterns leave the branch's likelihood and
+    substitution statistics -- against the oracle with the same masks."""
+    if kind == 'ss':
+        from treetime_b200.gtr import GTRSiteSpecific
+        gtr = GTRSiteSpecific.random(L=300, alphabet='nuc', rng=np.random.default_rng(31))
+        tree = synth.random_tree(33, seed=16, mean_bl=0.05)
+        topo, flat, g = util.make_flat(tree, gtr, 300, 16, amb_frac=0.02, compress=False)
+    else:
+        gtr = util.nuc_gtr() if kind == 'nuc' else util.random_gtr('aa_nogap', 6)
+        tree = synth.random_tree(48, seed=17, mean_bl=0.04)
+        topo, flat, g = util.make_flat(tree, gtr, 420, 17, amb_frac=0.02 if kind == 'nuc' else 0.0)
+    n_nodes = flat['parent'].shape[0]
+    L = flat['multiplicity'].shape[0]
+    rng = np.random.default_rng(7)
+    M = np.ones((3, L), dtype=np.uint8)
+    M[0, L // 2:] = 0                       # segment mask
+    M[2] = rng.random(L) < 0.7              # arbitrary 0/1 pattern
+    node_mask = rng.integers(-1, 3, size=n_nodes).astype(np.int32)
+    masks = {n: M[k].astype(float) for n, k in enumerate(node_mask) if k >= 0}
+    eng = util.engine_for(flat, g)
+    eng.set_branch_masks(M, node_mask)
+    for tips in (False, True):
+        eng.marginal(reconstruct_tips=tips)
+        tot, nd = eng.results()
+        res = O.marginal(flat, g, reconstruct_tip_states=tips, masks=masks)
+        assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+        compare_all(flat, g, eng, res, reconstruct_tips=tips)
+    # branch objective / hamming numerators with masked multiplicities, incl. the merged root branch
+    import oracle_engine
+    oe = oracle_engine.OracleEngine(g['Pi'].shape[0])
+    oe.set_tree(flat['parent'], flat['child_ptr'], flat['child_idx'], flat['tip_row'])
+    oe.set_patterns(flat['tip_codes'], flat['code_profiles'], flat['multiplicity'])
+    oe.set_gtr(g); oe.set_branch_lengths(flat['t']); oe.set_branch_masks(M, node_mask)
+    oe.marginal(reconstruct_tips=True)
+    nodes = np.arange(1, n_nodes, 2, dtype=np.int32)
+    kinds = np.zeros(nodes.shape[0], dtype=np.int32)
+    if flat['child_ptr'][1] - flat['child_ptr'][0] == 2 and kind != 'ss':
+        nodes = np.append(nodes, flat['child_idx'][flat['child_ptr'][0]]).astype(np.int32)
+        kinds = np.append(kinds, 1).astype(np.int32)
+    for tval in (1e-3, 0.08):
+        f = eng.branch_objective(nodes, np.full(nodes.shape[0], tval), kinds)
+        ref = oe.branch_objective(nodes, np.full(nodes.shape[0], tval), kinds)
+        assert np.allclose(f, ref, rtol=1e-10, atol=1e-9), np.abs(f - ref).max()
+    num, den = eng.branch_hamming(nodes, kinds)
+    rnum, rden = oe.branch_hamming(nodes, kinds)
+    assert np.allclose(num, rnum, rtol=1e-11) and np.isclose(den, rden)
+    a, b = eng.mutation_counts_per_site()
+    ra, rb = oe.mutation_counts_per_site()
+    assert np.allclose(a, ra, rtol=1e-9, atol=1e-12) and np.allclose(b, rb, rtol=1e-9, atol=1e-14)
+    if kind != 'ss':
+        n_ij, T_i = eng.mutation_counts()
+        assert np.allclose(n_ij, ra.sum(axis=-1), rtol=1e-10) and np.allclose(T_i, rb.sum(axis=-1), rtol=1e-10)
+    # masks off again: back to the plain kernels
+    eng.set_branch_masks(None, None)
+    eng.marginal()
+    tot, _ = eng.results()
+    res = O.marginal(flat, g)
+    assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+    from treetime_b200._lib import TTBError
+    eng.set_branch_masks(M, node_mask)
+    if kind != 'ss':
+        with pytest.raises(TTBError):
+            eng.joint()
+    with pytest.raises(TTBError):
+        eng.set_branch_masks(M * 2, node_mask)

@@ -106,16 +106,52 @@ def test_dropin_mixin_on_real_treeanc():
     assert np.isclose(rt.gtr.mu, dt.gtr.mu, rtol=1e-9)
 
 
-def test_dropin_falls_back_to_reference_for_masks():
+def test_dropin_per_branch_masks_on_the_device_path():
+    """ARG mode (arg.py:128-133): per-branch 0/1 masks are handled by the engine -- masked up-messages dropped
+    (treeanc.py:862-872), masked children keep their subtree profile (:909-917), masked multiplicities in the
+    branch-length objective (:1294,1326-1333) and in the substitution statistics (:1564-1572).  Fractional masks
+    and joint reconstruction with masks fall back to the reference."""
     rt, dt = _pair(seed=34)
     # joint (device path, N2) then marginal: N_diff is counted against the joint sequences
     assert rt.infer_ancestral_sequences(marginal=False) == dt.infer_ancestral_sequences(marginal=False)
     assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
-    # a per-branch mask (ARG mode) => reference implementation, identical numbers
     L = rt.data.compressed_length
-    mask = np.ones(L); mask[::3] = 0
-    list(rt.tree.find_clades())[4].mask = mask
-    list(dt.tree.find_clades())[4].mask = mask
+    seg = np.zeros(L); seg[:L // 2] = 1
+    total = np.ones(L)
+    rn, dn = list(rt.tree.find_clades()), list(dt.tree.find_clades())
+    for k, (a, b) in enumerate(zip(rn, dn)):          # every node carries a mask, like setup_arg leaves them
+        a.mask = b.mask = (seg if k % 3 == 0 else total)
+    for tips in (False, True):
+        assert (rt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips)
+                == dt.infer_ancestral_sequences(marginal=True, reconstruct_tip_states=tips))
+        assert dt._b200_live
+        assert np.isclose(rt.sequence_LH(), dt.sequence_LH(), rtol=1e-13)
+        assert np.allclose(rt.tree.sequence_LH, dt.tree.sequence_LH, rtol=1e-12, atol=1e-12)
+        for a, b in zip(rn, dn):
+            if a.up is not None:
+                assert np.allclose(a.marginal_outgroup_LH, b.marginal_outgroup_LH, rtol=1e-12, atol=1e-15)
+            if tips or not a.is_terminal():
+                assert np.allclose(a.marginal_profile, b.marginal_profile, rtol=1e-12, atol=1e-15)
+                assert (a.cseq == b.cseq).all()
+    for a, b in zip(rn[1:], dn[1:]):
+        x, y = rt.optimal_marginal_branch_length(a), dt.optimal_marginal_branch_length(b)
+        assert np.isclose(x, y, rtol=1e-6, atol=1e-12), (a.name, x, y)
+    g1 = rt.infer_gtr(marginal=True, pc=1.0); g2 = dt.infer_gtr(marginal=True, pc=1.0)
+    assert np.allclose(g1.W, g2.W, rtol=1e-9) and np.allclose(g1.Pi, g2.Pi, rtol=1e-9)
+    rt.optimize_tree(branch_length_mode='marginal', max_iter=2, infer_gtr=False, prune_short=False)
+    dt.optimize_tree(branch_length_mode='marginal', max_iter=2, infer_gtr=False, prune_short=False)
+    assert dt._b200_live
+    a = np.array([c.branch_length for c in rt.tree.find_clades()]); b = np.array([c.branch_length for c in dt.tree.find_clades()])
+    assert np.allclose(a[1:], b[1:], rtol=1e-7, atol=1e-12)
+    assert np.isclose(rt.sequence_LH(), dt.sequence_LH(), rtol=1e-10)
+    # removing the masks again
+    for a, b in zip(rn, dn):
+        a.mask = b.mask = None
+    assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
+    assert dt._b200_live and np.isclose(rt.sequence_LH(), dt.sequence_LH(), rtol=1e-13)
+    # a fractional mask has no device form => reference implementation, identical numbers
+    frac = np.ones(L); frac[::3] = 0.5
+    rn[4].mask = dn[4].mask = frac
     assert rt.infer_ancestral_sequences(marginal=True) == dt.infer_ancestral_sequences(marginal=True)
     assert not dt._b200_live
     assert rt.sequence_LH() == dt.sequence_LH()

@@ -93,6 +93,7 @@ SIGNATURES = {
     'ttb_set_gtr_site_specific': ([_H, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, ctypes.c_int32,
                                    ctypes.c_double, ctypes.c_int32, ctypes.c_int32], ctypes.c_int),
     'ttb_set_branch_lengths': ([_H, _c_dbl_p], ctypes.c_int),
+    'ttb_set_branch_masks': ([_H, ctypes.c_int32, _c_u8_p, _c_int_p], ctypes.c_int),
     'ttb_marginal': ([_H, ctypes.c_int32], ctypes.c_int),
     'ttb_joint': ([_H, ctypes.c_int32], ctypes.c_int),
     'ttb_joint_retrace': ([_H, _c_u8_p, ctypes.c_int32], ctypes.c_int),

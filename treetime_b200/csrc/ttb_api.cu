@@ -149,6 +149,10 @@ struct ttb_engine {
   // sample_from_profile=True: states of the previous pass (snapshot taken by TTB_KEEP_PREV_STATES)
   DBuf<uint8_t> d_idx_prev, d_idxtip_prev;
   DBuf<unsigned long long> d_scount;
+  // per-branch masks (ARG mode)
+  DBuf<int> d_mask_id;
+  DBuf<uint8_t> d_masks;
+  bool have_masks = false;
   bool have_prev = false, have_prev_tips = false;
   DBuf<double> d_ets, d_eout;
   double* h_results = nullptr;  // pinned {total, ndiff}
@@ -202,6 +206,8 @@ struct ttb_engine {
     d.ss_rec = d_ss_rec.p;
     d.ss_lo = d_ss_lo.p; d.ss_w = d_ss_w.p; d.ss_grid = d_ss_grid.p; d.ss_E = d_ss_E.p;
     d.ss_sym = ss_sym ? 1 : 0; d.ss_c = d_ss_c.p; d.ss_Ec = d_ss_Ec.p;
+    d.mask_id = have_masks ? d_mask_id.p : nullptr;
+    d.masks = have_masks ? d_masks.p : nullptr;
     d.ss_ngrid = (int)ss_grid.size();
     d.ss_tmax = ss_tmax;
     d.pq = (q * q + 1) / 2 * 2;
@@ -524,6 +530,7 @@ int ttb_destroy(ttb_handle h) {
   h->d_sg_uniforms.release();
   h->d_idx_prev.release(); h->d_idxtip_prev.release(); h->d_scount.release();
   h->d_ss_c.release(); h->d_ss_Ec.release();
+  h->d_mask_id.release(); h->d_masks.release();
   h->post.d_chunks.release(); h->pre_int.d_chunks.release(); h->pre_all.d_chunks.release();
   h->d_idx.release();
   h->d_idxtip.release();
@@ -635,6 +642,8 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   h->have_pass = h->have_tip_pass = false;
   h->have_joint = h->have_joint_tips = false;
   h->d_LP.release(); h->d_TL.release(); h->d_TC.release(); h->d_Cx.release();
+  h->have_masks = false;      // masks are per node: the caller sends them again for the new tree
+  h->d_mask_id.release(); h->d_masks.release();
   h->first_full = true;
   h->drop_graphs();
   return 0;
@@ -680,6 +689,11 @@ static int set_patterns_common(ttb_handle h, int64_t n_patterns, int32_t n_codes
   h->ld = ld;
   h->n_codes = n_codes;
   h->have_pass = h->have_tip_pass = false;
+  if (h->have_masks) {        // masks are per pattern: the caller sends them again for the new alignment
+    h->have_masks = false;
+    h->d_mask_id.release(); h->d_masks.release();
+    h->drop_graphs();
+  }
   h->first_full = true;
   return 0;
 }
@@ -949,6 +963,33 @@ static int update_ss_interp(ttb_handle h) {
   return 0;
 }
 
+int ttb_set_branch_masks(ttb_handle h, int32_t n_masks, const uint8_t* masks, const int32_t* node_mask) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->n_nodes || !h->Lp) return fail(TTB_EINVAL, "ttb_set_branch_masks: call ttb_set_tree and ttb_set_patterns first");
+  const bool had = h->have_masks;
+  if (n_masks <= 0 || !masks || !node_mask) {
+    h->have_masks = false;
+    h->d_mask_id.release();
+    h->d_masks.release();
+    if (had) h->drop_graphs();
+    return 0;
+  }
+  for (int n = 0; n < h->n_nodes; ++n)
+    if (node_mask[n] < -1 || node_mask[n] >= n_masks) return fail(TTB_EINVAL, "ttb_set_branch_masks: mask index out of range");
+  const size_t Lp = (size_t)h->Lp, ld = (size_t)h->ld;
+  for (size_t i = 0; i < (size_t)n_masks * Lp; ++i)
+    if (masks[i] > 1) return fail(TTB_EINVAL, "ttb_set_branch_masks: masks must be 0 or 1");
+  int rc;
+  if ((rc = h->d_masks.alloc((size_t)n_masks * ld))) return rc;
+  CK(cudaMemsetAsync(h->d_masks.p, 0, h->d_masks.bytes(), h->stream));
+  CK(cudaMemcpy2DAsync(h->d_masks.p, ld, masks, Lp, Lp, (size_t)n_masks, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = upload(h->d_mask_id, node_mask, (size_t)h->n_nodes, h->stream))) return rc;
+  CK(cudaStreamSynchronize(h->stream));   // pageable sources
+  h->have_masks = true;
+  h->drop_graphs();     // other kernels, other arguments
+  return 0;
+}
+
 int ttb_set_branch_lengths(ttb_handle h, const double* t) {
   if (int rc = use_device(h)) return rc;
   if (!h->n_nodes || !t) return fail(TTB_EINVAL, "ttb_set_branch_lengths: call ttb_set_tree first");
@@ -1022,6 +1063,7 @@ int ttb_joint(ttb_handle h, int32_t flags) {
   if (int rc = use_device(h)) return rc;
   if (int rc = check_ready(h, false)) return rc;
   if (h->site_specific) return fail(TTB_EUNSUPPORTED, "ttb_joint: joint reconstruction is not implemented for site-specific models");
+  if (h->have_masks) return fail(TTB_EUNSUPPORTED, "ttb_joint: joint reconstruction is not implemented with per-branch masks");
   const bool tips = flags & TTB_RECONSTRUCT_TIPS;
   const bool trace = !(flags & TTB_JOINT_NO_TRACE);
   const bool had_P = h->d_P.p != nullptr;

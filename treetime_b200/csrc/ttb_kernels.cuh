@@ -88,6 +88,12 @@ struct TtbDev {
   const double* ss_grid;  // [ss_ngrid] the grid itself (branch objective at trial lengths)
   int ss_ngrid;
   double ss_tmax;         // interpolate while t < ss_tmax (= 10 / rate_scale), 0 = never
+  // per-branch masks (ARG mode, arg.py:128-133): mask_id[node] = row of `masks` or -1, masks[n_masks][ld] in {0,1};
+  // both null when no node has a mask.  A masked (branch, pattern) carries no information: its up-message is 1
+  // (treeanc.py:867-872), the child keeps its subtree profile (:914-917) and the pattern drops out of the
+  // branch's multiplicities (:1294,1332,1564-1572).
+  const int* mask_id;
+  const uint8_t* masks;
   // state
   int pq;        // stride of one exp(Qt) matrix in doubles (q*q rounded up to even: 16-byte multiple for TMA)
   int tu_stride; // stride of one tip table in doubles (n_codes*q rounded up to even)
@@ -167,6 +173,26 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 
 // Element (slot, state 0, pattern a) of a tile-blocked message array; consecutive states are
 // TTB_TILE doubles apart.
+// true if pattern a of the branch above `node` is masked out
+__device__ __forceinline__ bool masked_out(const TtbDev& p, int node, long long a) {
+  if (!p.mask_id) return false;
+  const int m = __ldg(p.mask_id + node);
+  return m >= 0 && __ldg(p.masks + (size_t)m * p.ld + a) == 0;
+}
+// multiplicity(mask=node.mask)[a] (sequence_data.py:302-306) for the branch above `node`; kind 1 = merged root branch:
+// mask(n1) * mask(n2) when both children of the root carry one, no mask otherwise (treeanc.py:1326-1333)
+__device__ __forceinline__ double branch_weight(const TtbDev& p, int node, int kind, long long a) {
+  const double m = p.mult[a];
+  if (!p.mask_id) return m;
+  if (kind == 1) {
+    const int c0 = p.child_ptr[0];
+    const int m1 = __ldg(p.mask_id + p.child_idx[c0]), m2 = __ldg(p.mask_id + p.child_idx[c0 + 1]);
+    if (m1 < 0 || m2 < 0) return m;
+    return (__ldg(p.masks + (size_t)m1 * p.ld + a) && __ldg(p.masks + (size_t)m2 * p.ld + a)) ? m : 0.0;
+  }
+  return masked_out(p, node, a) ? 0.0 : m;
+}
+
 template <int Q>
 __device__ __forceinline__ size_t msg_off(const TtbDev& p, int slot, long long a) {
   return ((size_t)slot * p.tiles + (size_t)(a / TTB_TILE)) * (size_t)(Q * TTB_TILE) + (size_t)(a % TTB_TILE);
@@ -686,7 +712,7 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // Block = (run of nodes of the level given by group_ptr, one 128-pattern tile).
 // Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool SS, bool JOINT = false, bool SYM = false>
+template <int Q, bool SS, bool JOINT = false, bool SYM = false, bool MASK = false>
 __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : 255) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles, int fbase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -850,6 +876,9 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
           for (int j = 0; j < Q; ++j) X[j] += U[j];
           continue;
         }
+        if constexpr (MASK) {
+          if (masked_out(p, c.cnode(b), a)) continue;   // log_Lx * 0: the child says nothing about this pattern
+        }
 #pragma unroll
         for (int j = 0; j < Q; ++j) X[j] *= U[j];
         if (++seen > 2) {  // polytomy: keep the running product in range (exact scaling)
@@ -944,6 +973,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
         for (int j = 0; j < Q; ++j) X[j] += __ldg(tu + j);
         continue;
       }
+      if (!JOINT && masked_out(p, c.cnode(b), a)) continue;
 #pragma unroll
       for (int j = 0; j < Q; ++j) X[j] *= __ldg(tu + j);
       if (++seen > 2) {
@@ -1269,7 +1299,7 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // Tips take part only with TIPS (reconstruct_tip_states).
 // Stage rows: [0, Q) parent profile, child b -> rows [Q + b*Q, Q + (b+1)*Q) = S_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool TIPS, bool SS, bool SYM = false>
+template <int Q, bool TIPS, bool SS, bool SYM = false, bool MASK = false>
 __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : 255) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1390,6 +1420,8 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
           ip = p.idx + (size_t)src * p.ld + a;
         }
         int best = 0;
+        bool mo = false;   // this (branch, pattern) is masked out: up-message 1, profile = subtree profile
+        if constexpr (MASK) mo = masked_out(p, c.cnode(b), a);
         if constexpr (SS) {
           // site-specific model: per-pattern eigen-system instead of a staged exp(Qt)
           double U[Q], Sc[Q], O[Q], e[Q], msg[Q];
@@ -1408,12 +1440,16 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
           } else
             sm.efac(p, c.cnode(b), e);
           sm.up(Sc, e, U);
+          if (MASK && mo) {
+#pragma unroll
+            for (int j = 0; j < Q; ++j) U[j] = 1.0;
+          }
           outgroup_message<Q, (Q > 8)>(Mp, U, O);
           sm.down(O, e, msg);
           double z = 0.0;
 #pragma unroll
           for (int i = 0; i < Q; ++i) {
-            msg[i] *= Sc[i];
+            msg[i] = ((MASK && mo) ? 1.0 : msg[i]) * Sc[i];
             z += msg[i];
           }
           const double inv = 1.0 / z;
@@ -1446,6 +1482,10 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 #pragma unroll
               for (int j = 0; j < Q; ++j) U[j] = fma(Sc[i], Pc[i * Q + j], U[j]);
           }
+          if (MASK && mo) {
+#pragma unroll
+            for (int j = 0; j < Q; ++j) U[j] = 1.0;
+          }
           outgroup_message<Q>(Mp, U, O);
           double prof[Q];
           double z = 0.0;
@@ -1454,7 +1494,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
             double msg = O[0] * Pc[i * Q];
 #pragma unroll
             for (int j = 1; j < Q; ++j) msg = fma(O[j], Pc[i * Q + j], msg);
-            prof[i] = Sc[i] * msg;
+            prof[i] = Sc[i] * ((MASK && mo) ? 1.0 : msg);
             z += prof[i];
           }
           const double inv = 1.0 / z;
@@ -1487,6 +1527,10 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
               for (int j = 0; j < Q; ++j) O[j] = fma(si, Pc[i * Q + j], O[j]);
             }
           }
+          if (MASK && mo) {
+#pragma unroll
+            for (int j = 0; j < Q; ++j) O[j] = 1.0;
+          }
           double z = 0.0;
 #pragma unroll
           for (int j = 0; j < Q; ++j) {
@@ -1502,7 +1546,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
             double msg = 0.0;
 #pragma unroll
             for (int j = 0; j < Q; ++j) msg = fma(O[j], Pc[i * Q + j], msg);
-            const double pr = col[i * TTB_TILE] * msg;
+            const double pr = col[i * TTB_TILE] * ((MASK && mo) ? 1.0 : msg);
             col[i * TTB_TILE] = pr;
             z2 += pr;
           }
@@ -1724,6 +1768,10 @@ __device__ __forceinline__ void branch_profiles(const TtbDev& p, int n, int kind
       U[j] = u;
     }
   }
+  if (masked_out(p, n, a)) {
+#pragma unroll
+    for (int j = 0; j < Q; ++j) U[j] = 1.0;
+  }
   outgroup_message<Q>(Mp, U, pp);
 }
 
@@ -1816,14 +1864,14 @@ __global__ void __launch_bounds__(TTB_BLOCK) branch_eval_kernel(TtbDev p, const 
           g = fma(pc[i], w, g);
         }
       }
-      double val = p.mult[a] * log(g + TTB_SUPERTINY);
+      double val = branch_weight(p, node, kind, a) * log(g + TTB_SUPERTINY);
       if (p.gap_index >= 0) val *= (1.0 - pp[p.gap_index]) * (1.0 - pc[p.gap_index]);
       acc += val;
     } else {
       double d = 0.0;
 #pragma unroll
       for (int j = 0; j < Q; ++j) d = fma(pp[j], pc[j], d);
-      acc += p.mult[a] * d;
+      acc += branch_weight(p, node, kind, a) * d;
     }
   }
   const double bs = block_sum<TTB_BLOCK>(acc, sred);
@@ -1875,7 +1923,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) counts_kernel(TtbDev p, int chunk, 
         mm[i * Q + j] = pc[i] * pp[j] * sPc[i * Q + j];
         tot += mm[i * Q + j];
       }
-    const double w = m / tot;
+    const double w = (masked_out(p, n, a) ? 0.0 : m) / tot;
     const double ht = 0.5 * p.t[n];
 #pragma unroll
     for (int i = 0; i < Q; ++i)
@@ -1950,7 +1998,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) site_counts_kernel(TtbDev p, int ch
           tot += mm[i * Q + j];
         }
     }
-    const double w = m / tot;
+    const double w = (masked_out(p, n, a) ? 0.0 : m) / tot;
     const double ht = 0.5 * p.t[n];
 #pragma unroll
     for (int i = 0; i < Q; ++i)

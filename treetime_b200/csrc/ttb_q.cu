@@ -44,6 +44,10 @@ int prepare_t(const TtbDev& d) {
   if (!SS && (e = cudaFuncSetAttribute(post_level_kernel<Q, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, false))) != cudaSuccess) return (int)e;
   if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
   if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
+  // masked (ARG mode) variants
+  if ((e = cudaFuncSetAttribute(post_level_kernel<Q, SS, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, SS))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, SS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, SS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
   if constexpr (SS && HAS_SYM) {
     if ((e = cudaFuncSetAttribute(post_level_kernel<Q, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, true, true))) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, true, true))) != cudaSuccess) return (int)e;
@@ -60,7 +64,7 @@ int prepare_q(const TtbDev& d) {
   return 0;
 }
 
-template <bool SS, bool SYM = false>
+template <bool SS, bool SYM = false, bool MASK = false>
 int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
   const TtbDev& d = pl.d;
   const int tiles = pl.tiles;
@@ -87,7 +91,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   int fbase = l0 ? pl.post_levels[0].n_groups : 0;
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
-    launch_pdl(post_level_kernel<Q, SS, false, SYM>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d, pl.d_post_chunks,
+    launch_pdl(post_level_kernel<Q, SS, false, SYM, MASK>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d, pl.d_post_chunks,
                pl.d_post_group_ptr + L.group_off, tiles, fbase);
     fbase += L.n_groups;
     ++nk;
@@ -107,10 +111,10 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
       const TtbLevelLaunch& L = pl.pre_levels[l];
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
       if (pl.tips)
-        launch_pdl(pre_level_kernel<Q, true, SS, SYM>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
+        launch_pdl(pre_level_kernel<Q, true, SS, SYM, MASK>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
                    pl.count_diff);
       else
-        launch_pdl(pre_level_kernel<Q, false, SS, SYM>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
+        launch_pdl(pre_level_kernel<Q, false, SS, SYM, MASK>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
                    pl.count_diff);
       ++nk;
     }
@@ -123,6 +127,12 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
 }
 
 int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
+  if (pl.d.mask_id) {   // per-branch masks: the general kernels with the mask test compiled in
+    if constexpr (HAS_SS) {
+      if (pl.d.site_specific) return enqueue_pass_t<true, false, true>(pl, s, ev, pk);
+    }
+    return enqueue_pass_t<false, false, true>(pl, s, ev, pk);
+  }
   if constexpr (HAS_SYM) {
     if (pl.d.site_specific && pl.d.ss_sym) return enqueue_pass_t<true, true>(pl, s, ev, pk);
   }

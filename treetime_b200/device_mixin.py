@@ -37,6 +37,7 @@ class DeviceMarginalMixin(object):
         self._device_topology = None
         self._device_patterns = False
         self._device_data_id = None
+        self._device_masks = None
         self._cache = {}
         self._seq_cache = {}
 
@@ -107,6 +108,7 @@ class DeviceMarginalMixin(object):
             eng.set_tree(topo.parent, topo.child_ptr, topo.child_idx, topo.tip_row)
             self._device_topology = sig
             self._device_patterns = False
+            self._device_masks = None
         data_id = (id(self.data), self.data.compressed_length, len(self.gtr.profile_map))
         if data_id != self._device_data_id:
             self._device_patterns = False
@@ -126,6 +128,8 @@ class DeviceMarginalMixin(object):
                 codes, table = self._tip_codes()
                 eng.set_patterns(codes, table, self.data.multiplicity()[lo:hi], validate=False)   # codes built by _tip_codes
             self._device_patterns = True
+            self._device_masks = None
+        self._sync_masks(eng, topo)
         g = gtr_arrays(self.gtr)
         upload_model = True
         if g['site_specific']:
@@ -149,6 +153,64 @@ class DeviceMarginalMixin(object):
         eng.set_branch_lengths(tvec)
         self._t_last = tvec
         return eng
+
+    def _has_masks(self):
+        return any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades())
+
+    def _mask_problem(self):
+        """None if every node.mask has a device form (0/1 over the patterns), else the reason."""
+        L = self.data.compressed_length
+        seen = set()
+        for n in self.tree.find_clades():
+            m = getattr(n, 'mask', None)
+            if m is None or id(m) in seen:
+                continue
+            seen.add(id(m))
+            arr = np.asarray(m, dtype=float)
+            if arr.shape != (L,):
+                return 'a branch mask must have one entry per alignment pattern'
+            if not np.all((arr == 0) | (arr == 1)):
+                return 'fractional branch masks are not supported on the device path'
+        return None
+
+    def _sync_masks(self, eng, topo):
+        """Per-branch masks (node.mask, set by arg.py:128-133): distinct 0/1 vectors over the patterns + one index per
+        node.  Fractional masks have no device form (a masked message is dropped, not scaled)."""
+        node_masks = [getattr(n, 'mask', None) for n in topo.nodes]
+        if all(m is None for m in node_masks):
+            if self._device_masks is not None:
+                eng.set_branch_masks(None, None)
+                self._device_masks = None
+            return
+        L = self.data.compressed_length
+        rows, index, node_mask = [], {}, np.full(topo.n_nodes, -1, dtype=np.int32)
+        for i, m in enumerate(node_masks):
+            if m is None:
+                continue
+            arr = np.asarray(m, dtype=float)
+            if arr.shape != (L,):
+                self._unsupported('a branch mask must have one entry per alignment pattern')
+            if not np.all((arr == 0) | (arr == 1)):
+                self._unsupported('fractional branch masks are not supported on the device path')
+            key = arr.tobytes()
+            if key not in index:
+                index[key] = len(rows)
+                rows.append(arr.astype(np.uint8))
+            node_mask[i] = index[key]
+        sig = (node_mask.tobytes(), tuple(index))
+        if sig != self._device_masks:
+            lo, hi = self._shard()
+            eng.set_branch_masks(np.array(rows)[:, lo:hi], node_mask)
+            self._device_masks = sig
+
+    def _branch_mask(self, node, kind=0):
+        """The mask data.multiplicity() gets for the branch above `node` (treeanc.py:1294) or, kind 1, for the merged
+        branch across a bifurcating root (:1326-1333); None = no mask."""
+        if kind == 1:
+            n1, n2 = self.tree.root.clades
+            m1, m2 = getattr(n1, 'mask', None), getattr(n2, 'mask', None)
+            return None if m1 is None or m2 is None else np.asarray(m1) * np.asarray(m2)
+        return getattr(node, 'mask', None)
 
     def _gather_patterns(self, x, axis=0):
         return x if self.comm.world_size == 1 else self.comm.allgather(x, axis=axis)
@@ -187,8 +249,6 @@ class DeviceMarginalMixin(object):
             root_sample = other_sample = sample_from_profile
         else:
             raise ValueError("sample_from_profile must be a bool or 'root'")
-        if any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
-            self._unsupported('per-branch masks (ARG mode) are not supported on the device path')
         eng = self._sync_device()
         topo = self._flat()
         eng.marginal(reconstruct_tips=reconstruct_tip_states, keep_prev=other_sample)
@@ -279,7 +339,7 @@ class DeviceMarginalMixin(object):
         else:
             raise ValueError("sample_from_profile must be a bool or 'root'")
         if any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
-            self._unsupported('per-branch masks (ARG mode) are not supported on the device path')
+            self._unsupported('joint reconstruction with per-branch masks (ARG mode) runs in the reference')
         if getattr(self.gtr, 'is_site_specific', False):
             self._unsupported('joint reconstruction with site-specific models runs in the reference')
         eng = self._sync_device()
@@ -350,6 +410,9 @@ class DeviceMarginalMixin(object):
         if self.comm.world_size > 1:
             num = self.comm.allreduce_sum(num)
         den = self.data.multiplicity().sum()
+        if self._device_masks is not None:          # data.multiplicity(mask=...) per branch
+            topo = self._flat()
+            den = np.array([self.data.multiplicity(mask=self._branch_mask(topo.nodes[f], k)).sum() for f, k in zip(fids, kinds)])
         hamming = 1 - num / den
 
         def neg_prob(idx, s):
@@ -439,6 +502,8 @@ class DeviceMarginalMixin(object):
         if 'pairs' not in self._cache:
             if not self.sequence_reconstruction or self._engine is None:
                 raise Exception('ancestral sequences need to be reconstructed first!')
+            if self._has_masks():
+                self._unsupported('pair counts under per-branch masks (ARG mode) run in the reference')
             eng, topo = self._engine, self._flat()
             tip_states = bool(self.reconstructed_tip_sequences)
             C, F = eng.branch_state_pairs(np.arange(1, topo.n_nodes, dtype=np.int32), tip_states=tip_states)
@@ -545,7 +610,7 @@ class DeviceMarginalMixin(object):
             self._gtr = self._infer_site_specific_gtr_from_counts(n_ija, T_ia, root_state, pc)
         else:
             root_cseq = self.tree.root.cseq
-            m = self.data.multiplicity()
+            m = self.data.multiplicity(mask=getattr(self.tree.root, 'mask', None))      # treeanc.py:1610
             root_state = np.array([np.sum((root_cseq == nuc) * m) for nuc in self.gtr.alphabet])
             self._gtr = self._infer_gtr_from_counts(n_ij, T_i, root_state, fixed_pi, pc)
         if normalized_rate:

@@ -129,8 +129,8 @@ class B200MarginalMixin(DeviceMarginalMixin):
     # -- the pass ---------------------------------------------------------------------------
     def _ml_anc_marginal(self, sample_from_profile=False, reconstruct_tip_states=False, debug=False, **kwargs):
         why = self._device_ok()
-        if why is None and any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
-            why = 'per-branch masks (ARG mode)'
+        if why is None:
+            why = self._mask_problem()
         if why is None:
             try:
                 # N_diff against a previous reconstruction that did not come from the device (joint /
@@ -263,7 +263,7 @@ class B200MarginalMixin(DeviceMarginalMixin):
         return super(DeviceMarginalMixin, self).optimize_branch_lengths_joint(**kwargs)
 
     def optimize_tree_marginal(self, *args, **kwargs):
-        if self._device_ok() is None and not any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()):
+        if self._device_ok() is None and self._mask_problem() is None:
             try:
                 return DeviceMarginalMixin.optimize_tree_marginal(self, *args, **kwargs)
             except Unsupported:
@@ -271,7 +271,7 @@ class B200MarginalMixin(DeviceMarginalMixin):
         return super(DeviceMarginalMixin, self).optimize_tree_marginal(*args, **kwargs)
 
     def optimal_marginal_branch_length(self, node, tol=1e-10):
-        if self._b200_live and getattr(node, 'mask', None) is None:
+        if self._b200_live:
             return DeviceMarginalMixin.optimal_marginal_branch_length(self, node, tol=tol)
         return super(DeviceMarginalMixin, self).optimal_marginal_branch_length(node, tol=tol)
 

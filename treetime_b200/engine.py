@@ -139,6 +139,17 @@ class Engine(object):
             raise ValueError('t must have one entry per node')
         _lib.check(self.lib.ttb_set_branch_lengths(self.h, _dp(t)))
 
+    def set_branch_masks(self, masks, node_mask):
+        """masks [n_masks, n_patterns] of 0/1 (or None to remove them), node_mask[n_nodes] = mask row or -1."""
+        if masks is None or len(masks) == 0:
+            _lib.check(self.lib.ttb_set_branch_masks(self.h, 0, None, None))
+            return
+        masks = np.ascontiguousarray(masks, dtype=np.uint8)
+        node_mask = _i32(node_mask)
+        if masks.shape[1] != self.n_patterns or node_mask.shape[0] != self.n_nodes:
+            raise ValueError('masks must be [n_masks, n_patterns] and node_mask [n_nodes]')
+        _lib.check(self.lib.ttb_set_branch_masks(self.h, masks.shape[0], _up(masks), _ip(node_mask)))
+
     # -- the pass -------------------------------------------------------------
     def marginal(self, reconstruct_tips=False, lh_only=False, keep_prev=False):
         """keep_prev: keep the states this pass overwrites (sample_states counts N_diff against them)."""
