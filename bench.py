@@ -189,6 +189,50 @@ def run_cpu(flat, g, n_patterns, repeats):
     return n_br * n, times, res.total_LH
 
 
+_POOL_STATE = {}
+
+
+def _cpu_worker_init(flat, g):
+    """Worker of the multi-process CPU arm: one pattern slice per process, numpy pinned to one thread."""
+    try:
+        import threadpoolctl
+        _POOL_STATE['limit'] = threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    _POOL_STATE['flat'], _POOL_STATE['g'] = flat, g
+
+
+def _cpu_worker_run(bounds):
+    import flat_numpy as O
+    lo, hi = bounds
+    flat, g = _POOL_STATE['flat'], _POOL_STATE['g']
+    s = dict(flat)
+    s['tip_codes'] = np.ascontiguousarray(flat['tip_codes'][:, lo:hi])
+    s['multiplicity'] = flat['multiplicity'][lo:hi].copy()
+    if g.get('site_specific'):
+        g = dict(g, eigenvals=g['eigenvals'][:, lo:hi], v=g['v'][:, :, lo:hi], v_inv=g['v_inv'][:, :, lo:hi], Pi=g['Pi'][:, lo:hi],
+                 mu=g['mu'][lo:hi])
+    return float(O.marginal(s, g).total_LH)
+
+
+def run_cpu_parallel(flat, g, per_worker, workers, repeats):
+    """The reference path is single-threaded numpy; patterns are independent, so the strongest CPU arm this host
+    offers is one process per core, each running the oracle port on its own slice of the pattern axis."""
+    import multiprocessing as mp
+    Lp = flat['multiplicity'].shape[0]
+    per_worker = max(1, min(per_worker, Lp // workers))
+    bounds = [(k * per_worker, (k + 1) * per_worker) for k in range(workers)]
+    n_br = flat['parent'].shape[0] - 1
+    times = []
+    with mp.get_context('fork').Pool(workers, initializer=_cpu_worker_init, initargs=(flat, g)) as pool:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker_run, bounds, chunksize=1)
+            times.append(time.perf_counter() - t0)
+    return n_br * per_worker * workers, times, per_worker
+
+
 def _claim_stdout():
     """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there)
     must not pollute it: point fd 1 at stderr for the whole run and keep the real stdout aside."""
@@ -211,6 +255,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-patterns', type=int, default=0, help='patterns in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--cpu-workers', type=int, default=0, help='processes of the CPU (reference) arm (0 = one per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-blocks', type=int, default=6, help='pattern blocks (engine handles / streams) of the e2e leg')
@@ -231,21 +276,38 @@ def main():
         n_br = flat['parent'].shape[0] - 1
         total_steps = args.steps + args.warmup
         n_pat = args.cpu_patterns or int(max(64, min(flat['multiplicity'].shape[0], 120.0 * 2.0e6 / (n_br * max(1, total_steps)))))
-        updates, times, _ = run_cpu(flat, g, n_pat, total_steps)
+        # one process per host core, bounded by memory: the port keeps ~6 (n_nodes, patterns, q) fp64 arrays per slice
+        workers = max(1, min(os.cpu_count() or 1, args.cpu_workers or 64))
+        per_worker = max(64, min(n_pat, flat['multiplicity'].shape[0] // workers))
+        try:
+            import psutil
+            per_pattern = 6.0 * flat['parent'].shape[0] * q * 8          # bytes one pattern costs a worker
+            budget = 0.5 * psutil.virtual_memory().available
+            per_worker = int(min(per_worker, max(64, budget // (workers * per_pattern))))
+            workers = int(max(1, min(workers, budget // (per_worker * per_pattern))))
+        except Exception:
+            pass
+        if workers > 1:
+            updates, times, per_worker = run_cpu_parallel(flat, g, per_worker, workers, total_steps)
+            sample = ('%d processes (one per core), each one pass over its own %d of %d compressed patterns of the same '
+                      'tree/alignment per step (cost is linear in patterns)' % (workers, per_worker, flat['multiplicity'].shape[0]))
+        else:
+            updates, times, _ = run_cpu(flat, g, n_pat, total_steps)
+            sample = 'first %d of %d compressed patterns of the same tree/alignment per step (cost is linear in patterns)' % (
+                min(n_pat, flat['multiplicity'].shape[0]), flat['multiplicity'].shape[0])
         timed = times[args.warmup:]
         ms = 1e3 * float(np.mean(timed))
         val = updates / (ms / 1e3)
-        sample = 'first %d of %d compressed patterns of the same tree/alignment per step (cost is linear in patterns)' % (
-            min(n_pat, flat['multiplicity'].shape[0]), flat['multiplicity'].shape[0])
         _emit(real_stdout, {
             'impl': 'reference', 'metric': 'marginal ancestral reconstruction branch x pattern updates/s', 'value': val,
             'unit': 'updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': '%s: %s' % (args.workload, desc), 'n_tips': n_tips, 'n_sites': L, 'n_states': q},
-            'cpu_baseline': {'value': val, 'unit': 'updates/s', 'cores': 1, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': val, 'unit': 'updates/s', 'cores': workers, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'note': 'oracle/flat_numpy.py: flat-array port of the reference numpy path (bit-identical to the '
-                    'reference on the build container); single-threaded like the reference',
+                    'reference on the build container).  The reference itself is single-threaded; patterns are '
+                    'independent, so this arm runs one process per host core on disjoint pattern slices',
         })
         return 0
 
