@@ -683,6 +683,7 @@ static int set_patterns_common(ttb_handle h, int64_t n_patterns, int32_t n_codes
     h->d_TU.release();
     h->drop_graphs();  // n_codes is a kernel parameter
   }
+  if (n_codes != h->n_codes) h->prepared = false;   // the stages' shared-memory size depends on the code table
   if (h->d_idx.p) CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), s));  // new data: no previous states
   if (h->d_idxtip.p) CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), s));
   h->Lp = Lp;
