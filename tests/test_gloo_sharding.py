@@ -35,9 +35,38 @@ def _worker(rank, world, port, q):
     out['lh2'] = tt.sequence_LH()
     tt.infer_gtr(marginal=True)
     out['W'] = np.array(tt.gtr.W)
+    out.update(_extras(TreeAnc, tree, aln, util, dict(comm=TorchComm(), engine_factory=oracle_engine.factory)))
     q.put(out)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _extras(TreeAnc, tree, aln, util, kw):
+    """The paths with pattern-axis state besides the plain pass: sampled sequences (every rank draws the full
+    uniforms and uses its slice), per-branch masks (sliced with the patterns), per-pattern statistics + site-specific
+    GTR inference (all-gathered)."""
+    out = {}
+    t2 = TreeAnc(tree=tree.to_newick(), aln=aln, gtr=util.nuc_gtr(), rng_seed=11, compress=False, **kw)
+    out['s_n'] = [t2.infer_ancestral_sequences(marginal=True, sample_from_profile=True, reconstruct_tip_states=tips)
+                  for tips in (False, True, True)]
+    out['s_seq'] = [''.join(n.cseq) for n in t2.tree.find_clades()]
+    out['s_rng'] = t2.rng.random()
+    L = t2.data.compressed_length
+    seg = np.zeros(L); seg[: L // 3] = 1
+    for k, n in enumerate(t2.tree.find_clades()):
+        n.mask = seg if k % 2 else np.ones(L)
+    out['m_n'] = t2.infer_ancestral_sequences(marginal=True)
+    out['m_lh'] = t2.sequence_LH()
+    nodes = list(t2.tree.find_clades())
+    out['m_bl'] = np.array([t2.optimal_marginal_branch_length(n) for n in nodes[1:6]])
+    for n in nodes:
+        n.mask = None
+    t2.infer_ancestral_sequences(marginal=True)
+    g = t2.infer_gtr(marginal=True, site_specific=True, pc=1.0)
+    out['ss_pi'] = np.array(g.Pi); out['ss_mu'] = np.array(g.mu)
+    t2.infer_ancestral_sequences(marginal=True)
+    out['ss_lh'] = t2.sequence_LH()
+    return out
 
 
 def test_two_rank_sharding_equals_single_rank():
@@ -81,3 +110,10 @@ def test_two_rank_sharding_equals_single_rank():
         assert np.isclose(o['lh2'], tt.sequence_LH(), rtol=1e-12)
         assert np.allclose(o['W'], tt.gtr.W, rtol=1e-8)
     assert np.array_equal(outs[0]['bl'], outs[1]['bl'])                      # ranks stay in lock-step
+    ref = _extras(TreeAnc, tree, aln, util, dict(engine_factory=oracle_engine.factory))
+    for o in outs:
+        assert o['s_n'] == ref['s_n'] and o['s_seq'] == ref['s_seq'] and o['s_rng'] == ref['s_rng']
+        assert o['m_n'] == ref['m_n'] and np.isclose(o['m_lh'], ref['m_lh'], rtol=1e-12)
+        assert np.allclose(o['m_bl'], ref['m_bl'], rtol=1e-7, atol=1e-12)
+        assert np.allclose(o['ss_pi'], ref['ss_pi'], rtol=1e-9, atol=1e-13) and np.allclose(o['ss_mu'], ref['ss_mu'], rtol=1e-9)
+        assert np.isclose(o['ss_lh'], ref['ss_lh'], rtol=1e-11)
