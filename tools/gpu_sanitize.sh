@@ -21,6 +21,17 @@ def run(gtr, n, L, seed, mean_bl=0.01, **kw):
         eng.mutation_counts()
         eng.joint(); eng.results(); eng.joint(reconstruct_tips=True); eng.results(); eng.all_seq_idx()
         eng.marginal(); eng.results()
+    # sampled sequences, per-pattern statistics, per-branch masks (MASK kernels), back to the plain kernels
+    L_ = flat['multiplicity'].shape[0]; n_nodes = flat['parent'].shape[0]
+    eng.marginal(reconstruct_tips=True, keep_prev=True); eng.results()
+    eng.sample_states(np.arange(1, n_nodes, dtype=np.int32), np.random.default_rng(1).random((n_nodes - 1, L_)))
+    eng.mutation_counts_per_site()
+    M = np.ones((2, L_), dtype=np.uint8); M[0, L_ // 2:] = 0
+    eng.set_branch_masks(M, (np.arange(n_nodes) % 3 - 1).astype(np.int32))
+    eng.marginal(reconstruct_tips=True); eng.results()
+    eng.branch_objective(nodes, np.full(nodes.shape[0],0.01)); eng.mutation_counts_per_site()
+    eng.set_branch_masks(None, None)
+    eng.marginal(); eng.results()
     res = O.marginal(flat, g)
     assert abs(tot-res.total_LH) < 1e-9*abs(res.total_LH)
     print('ok', g['Pi'].shape, tot)
