@@ -27,11 +27,12 @@ def main():
             scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1.0)
             d[r[mi]] = v * scale
     seq = list(launches.values())
-    # one pass = from an expqt launch up to (excluding) the next one
-    starts = [i for i, d in enumerate(seq) if d['name'].startswith('expqt')]
-    if len(starts) < 2:
+    # one pass = the launches after a finish_kernel up to and including the next one (site-specific passes have no
+    # expqt launch to split at)
+    ends = [i for i, d in enumerate(seq) if d['name'].startswith('finish_kernel')]
+    if len(ends) < 2:
         print('no complete pass in the capture'); return
-    one = seq[starts[0]:starts[1]]
+    one = seq[ends[0] + 1:ends[1] + 1]
     agg = OrderedDict()
     for d in one:
         a = agg.setdefault(d['name'], {'launches': 0, 'us': 0.0, 'dram_bytes': 0.0})
