@@ -173,6 +173,62 @@ def joint_cases():
     run_joint_case('aa16_jtt92', GTR.standard('JTT92'), reconstruct_tips=True)
 
 
+def run_extras_case(src, make_gtr):
+    """Fixtures for the paths beyond the plain pass, on the inputs of an existing fixture: sampled sequences
+    (sample_from_profile=True, treeanc.py:786-798,919-923), per-branch masks (ARG mode, :862-872,909-917,1294,1564-1572)
+    and site-specific GTR inference (:1594-1627, gtr_site_specific.py:207-310)."""
+    if ONLY and ('extras_' + src) not in ONLY:
+        return
+    z = np.load(os.path.join(OUT, src + '.npz'))
+    newick = str(z['newick'])
+    aln = {str(k): np.array(list(str(v))) for k, v in zip(z['aln_names'], z['aln_seqs'])}
+    out = dict(source=np.array(src))
+    # 1. sampled sequences, generator seeded with 7
+    tt = refenv.reference_treeanc(newick, aln, make_gtr(), rng_seed=7)
+    nodes = list(tt.tree.find_clades())
+    for k, tips in enumerate((False, True)):
+        out['sample_N_diff_%d' % k] = np.array(tt.infer_ancestral_sequences(marginal=True, sample_from_profile=True, reconstruct_tip_states=tips))
+        out['sample_cseq_%d' % k] = np.array([''.join(n.cseq) if n.cseq is not None else '' for n in nodes])
+    out['sample_next_uniform'] = np.array(tt.rng.random())
+    # 2. per-branch masks: node k carries the segment mask if k % 3 == 0 else the all-ones mask
+    tt = refenv.reference_treeanc(newick, aln, make_gtr(), rng_seed=1)
+    nodes = list(tt.tree.find_clades())
+    L = tt.data.compressed_length
+    seg = np.zeros(L); seg[:L // 2] = 1
+    for k, n in enumerate(nodes):
+        n.mask = seg if k % 3 == 0 else np.ones(L)
+    out['mask_segment'] = seg
+    out['mask_N_diff'] = np.array(tt.infer_ancestral_sequences(marginal=True))
+    out['mask_total_LH'] = np.array(tt.tree.total_sequence_LH)
+    out['mask_sequence_LH'] = np.array(tt.tree.sequence_LH)
+    out['mask_cseq'] = np.array([''.join(n.cseq) if n.cseq is not None else '' for n in nodes])
+    bl_nodes = list(range(1, len(nodes), max(1, len(nodes) // 8)))[:8]
+    out['mask_bl_nodes'] = np.array(bl_nodes)
+    out['mask_bl_opt'] = np.array([tt.optimal_marginal_branch_length(nodes[i]) for i in bl_nodes])
+    out['mask_profile_nodes'] = np.array([i for i in bl_nodes if not nodes[i].is_terminal()])
+    for i in out['mask_profile_nodes']:
+        out['mask_profile_%d' % i] = np.array(nodes[i].marginal_profile)
+        out['mask_outgroup_%d' % i] = np.array(nodes[i].marginal_outgroup_LH)
+    g = tt.infer_gtr(marginal=True, pc=1.0)
+    out['mask_inferred_W'] = np.array(g.W); out['mask_inferred_Pi'] = np.array(g.Pi)
+    # 3. site-specific GTR inference (no pattern compression), then a reconstruction under the inferred model
+    tt = refenv.reference_treeanc(newick, aln, make_gtr(), rng_seed=1, compress=False)
+    tt.infer_ancestral_sequences(marginal=True)
+    g = tt.infer_gtr(marginal=True, site_specific=True, pc=1.0)
+    out['ss_Pi'] = np.array(g.Pi); out['ss_mu'] = np.array(g.mu); out['ss_W'] = np.array(g.W)
+    out['ss_N_diff'] = np.array(tt.infer_ancestral_sequences(marginal=True))
+    out['ss_total_LH'] = np.array(tt.tree.total_sequence_LH)
+    path = os.path.join(OUT, 'extras_' + src + '.npz')
+    np.savez_compressed(path, **out)
+    print('%-22s sampled N_diff=%d/%d  masked LH=%.6f  site-specific LH=%.6f  %d KB' % (
+        'extras_' + src, out['sample_N_diff_0'], out['sample_N_diff_1'], out['mask_total_LH'], out['ss_total_LH'], os.path.getsize(path) // 1024))
+
+
+def extras_cases():
+    from treetime import GTR
+    run_extras_case('nuc40', lambda: GTR.custom(pi=np.array([.3, .2, .2, .29, .01]), W=np.ones((5, 5)), alphabet='nuc'))
+
+
 def chars(idx, gtr):
     return {k: gtr.alphabet[v] for k, v in idx.items()}
 
@@ -238,6 +294,9 @@ def main():
 if __name__ == '__main__':
     if '--only-joint' in sys.argv:      # adds the joint_*.npz fixtures next to the existing ones
         joint_cases()
+    elif '--only-extras' in sys.argv:   # adds the extras_*.npz fixtures (sampling, masks, site-specific inference)
+        extras_cases()
     else:
         main()
         joint_cases()
+        extras_cases()

@@ -60,3 +60,52 @@ def regenerate_big(name):
     sha = hashlib.sha256(np.ascontiguousarray(np.vstack([idx[k] for k in sorted(idx)])).tobytes()).hexdigest()
     aln = {k: g.alphabet[v] for k, v in idx.items()}
     return tree, aln, g, sha
+
+
+EXTRAS = ['extras_nuc40']       # sampling / masks / site-specific inference on the inputs of z['source']
+
+
+def check_extras(make_tt, zx, exact):
+    """The TreeAnc built by make_tt(**kw) against the reference's outputs in an extras_* fixture.
+    exact: bit-level agreement expected (CPU oracle engine) or only to the stated tolerances (CUDA engine)."""
+    rt = 0.0 if exact else 1e-9
+    # 1. sampled sequences: same generator, same draws
+    tt = make_tt(rng_seed=7)
+    nodes = list(tt.tree.find_clades())
+    for k, tips in enumerate((False, True)):
+        nd = tt.infer_ancestral_sequences(marginal=True, sample_from_profile=True, reconstruct_tip_states=tips)
+        got = [''.join(n.cseq) if (tips or not n.is_terminal()) else None for n in nodes]
+        diff = sum(sum(a != b for a, b in zip(g, str(r))) for g, r in zip(got, zx['sample_cseq_%d' % k]) if g is not None)
+        assert diff <= (0 if exact else 1), diff        # a uniform within rounding of a cumulative sum may fall either way
+        assert abs(nd - int(zx['sample_N_diff_%d' % k])) <= 2 * diff
+    assert tt.rng.random() == float(zx['sample_next_uniform'])
+    # 2. per-branch masks
+    tt = make_tt(rng_seed=1)
+    nodes = list(tt.tree.find_clades())
+    seg, L = zx['mask_segment'], tt.data.compressed_length
+    for k, n in enumerate(nodes):
+        n.mask = seg if k % 3 == 0 else np.ones(L)
+    assert tt.infer_ancestral_sequences(marginal=True) == int(zx['mask_N_diff'])
+    tot = float(zx['mask_total_LH'])
+    assert abs(tt.sequence_LH() - tot) <= max(rt, 1e-13) * abs(tot)
+    assert np.allclose(tt.tree.sequence_LH, zx['mask_sequence_LH'], rtol=1e-11, atol=1e-11)
+    for n, s in zip(nodes, zx['mask_cseq']):
+        if not n.is_terminal():
+            assert ''.join(n.cseq) == str(s)
+    for i in zx['mask_profile_nodes']:
+        assert np.allclose(nodes[i].marginal_profile, zx['mask_profile_%d' % i], rtol=0, atol=1e-12)
+        assert np.allclose(nodes[i].marginal_outgroup_LH, zx['mask_outgroup_%d' % i], rtol=0, atol=1e-12)
+    for i, bl in zip(zx['mask_bl_nodes'], zx['mask_bl_opt']):
+        got = tt.optimal_marginal_branch_length(nodes[i])
+        assert abs(got - bl) <= 1e-6 * bl + 1e-12, (i, got, bl)
+    g = tt.infer_gtr(marginal=True, pc=1.0)
+    assert np.allclose(g.W, zx['mask_inferred_W'], rtol=1e-8) and np.allclose(g.Pi, zx['mask_inferred_Pi'], rtol=1e-8)
+    # 3. site-specific GTR inference
+    tt = make_tt(rng_seed=1, compress=False)
+    tt.infer_ancestral_sequences(marginal=True)
+    g = tt.infer_gtr(marginal=True, site_specific=True, pc=1.0)
+    assert np.allclose(g.Pi, zx['ss_Pi'], rtol=1e-8, atol=1e-12) and np.allclose(g.mu, zx['ss_mu'], rtol=1e-8)
+    assert np.allclose(g.W, zx['ss_W'], rtol=1e-8)
+    assert tt.infer_ancestral_sequences(marginal=True) == int(zx['ss_N_diff'])
+    tot = float(zx['ss_total_LH'])
+    assert abs(tt.sequence_LH() - tot) <= 1e-9 * abs(tot)

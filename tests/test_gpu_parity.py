@@ -423,6 +423,20 @@ def test_sample_states(kind):
         # the root keeps its argmax; the profiles are those of the plain pass
         assert np.abs(eng.node_array(nodes[0], 2) - res.profile[nodes[0]]).max() < PROF_ATOL
         prev = list(res.seq_idx)
+    # the uniforms of many nodes travel in several blocks: same states whatever the block size
+    import os
+    eng.marginal(reconstruct_tips=True, keep_prev=True)
+    eng.results()
+    eng.sample_states(nodes, U)
+    whole = eng.seq_idx(nodes)
+    os.environ['TTB_SAMPLE_BLOCK_DOUBLES'] = str(3 * L + 1)          # 3 nodes per block
+    try:
+        eng.marginal(reconstruct_tips=True, keep_prev=True)
+        eng.results()
+        nd2, ndt2 = eng.sample_states(nodes, U)
+    finally:
+        del os.environ['TTB_SAMPLE_BLOCK_DOUBLES']
+    assert np.array_equal(eng.seq_idx(nodes), whole) and nd2 == 0 and ndt2 == 0
     from treetime_b200._lib import TTBError
     eng.marginal()
     with pytest.raises(TTBError):

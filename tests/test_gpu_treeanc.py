@@ -269,3 +269,12 @@ def test_gpu_infer_site_specific_gtr():
         assert np.allclose(ga.Pi, gb.Pi, rtol=1e-8, atol=1e-12) and np.allclose(ga.mu, gb.mu, rtol=1e-8) and np.allclose(ga.W, gb.W, rtol=1e-8)
         a.infer_ancestral_sequences(marginal=True); b.infer_ancestral_sequences(marginal=True)
         assert abs(a.sequence_LH() - b.sequence_LH()) <= LH_RTOL * abs(b.sequence_LH())
+
+
+@pytest.mark.parametrize('name', G.EXTRAS)
+def test_gpu_sampling_masks_site_specific_inference_vs_reference_golden(name):
+    """The same golden vectors of the unmodified reference (sampled sequences, per-branch masks, site-specific GTR
+    inference) against the CUDA engine."""
+    zx = G.load(name)
+    z = G.load(str(zx['source']))
+    G.check_extras(lambda **kw: TreeAnc(tree=str(z['newick']), aln=G.alignment(z), gtr=G.model(z), **kw), zx, exact=False)

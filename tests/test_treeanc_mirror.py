@@ -223,3 +223,14 @@ def test_mirror_joint_reconstruction():
     with pytest.raises(AttributeError):
         tt.tree.root.marginal_profile          # marginal state does not exist after a joint pass
     assert tt.infer_ancestral_sequences(marginal=True) >= 0 and tt.tree.root.marginal_profile.shape[1] == 5
+
+
+@pytest.mark.parametrize('name', G.EXTRAS)
+def test_mirror_sampling_masks_site_specific_inference_vs_reference_golden(name):
+    """Golden vectors of the unmodified reference for sample_from_profile=True, per-branch masks and
+    infer_gtr(site_specific=True) (oracle/make_golden.py --only-extras) through the mirror on the CPU oracle engine."""
+    import oracle_engine
+    zx = G.load(name)
+    z = G.load(str(zx['source']))
+    G.check_extras(lambda **kw: TreeAnc(tree=str(z['newick']), aln=G.alignment(z), gtr=G.model(z),
+                                        engine_factory=oracle_engine.factory, **kw), zx, exact=True)

@@ -1152,8 +1152,10 @@ int ttb_sample_states(ttb_handle h, int32_t n, const int32_t* nodes, const doubl
   if ((rc = h->d_scount.alloc(2))) return rc;
   CK(cudaMemsetAsync(h->d_scount.p, 0, 2 * sizeof(unsigned long long), s));
   const size_t Lp = (size_t)h->Lp;
-  // the uniforms travel in blocks of at most 256 MB
-  const int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n, 1), ((size_t)1 << 25) / Lp));
+  // the uniforms travel in blocks of at most 256 MB (TTB_SAMPLE_BLOCK_DOUBLES overrides the block size: tests)
+  size_t blk_doubles = (size_t)1 << 25;
+  if (const char* e = getenv("TTB_SAMPLE_BLOCK_DOUBLES")) blk_doubles = (size_t)std::max(1LL, atoll(e));
+  const int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n, 1), blk_doubles / Lp));
   if (n) {
     if ((rc = h->d_sg_uniforms.alloc((size_t)blk * Lp))) return rc;
     if ((rc = h->d_enodes.alloc((size_t)n))) return rc;
