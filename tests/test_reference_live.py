@@ -450,3 +450,40 @@ def test_site_specific_gtr_inference_matches_reference():
     assert np.allclose(a.Pi, b.Pi, rtol=1e-10, atol=1e-14) and np.allclose(a.mu, b.mu, rtol=1e-10) and np.allclose(a.W, b.W, rtol=1e-10)
     assert r3.infer_ancestral_sequences(marginal=True) == m3.infer_ancestral_sequences(marginal=True)
     assert np.isclose(r3.sequence_LH(), m3.sequence_LH(), rtol=1e-11)
+
+
+def test_gtr_inference_from_reconstructed_sequences_matches_reference():
+    """infer_gtr(marginal=False) (treeanc.py:1573-1589): the mutation / state-time counts the reference collects from
+    node.mutations and node.cseq come from the device's pair counts -- after a joint and after a marginal
+    reconstruction, with and without reconstructed tips, through the drop-in and the mirror."""
+    for recon in (dict(marginal=False), dict(marginal=True), dict(marginal=False, reconstruct_tip_states=True)):
+        rt, dt = _pair(seed=61)
+        assert rt.infer_ancestral_sequences(**recon) == dt.infer_ancestral_sequences(**recon)
+        calls, orig = [], dt._engine.branch_state_pairs
+        dt._engine.branch_state_pairs = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+        g1 = rt.infer_gtr(marginal=False, pc=2.0)
+        g2 = dt.infer_gtr(marginal=False, pc=2.0)
+        assert calls                                          # counted from the engine's pair tables
+        assert np.allclose(g1.W, g2.W, rtol=1e-12) and np.allclose(g1.Pi, g2.Pi, rtol=1e-12) and np.isclose(g1.mu, g2.mu, rtol=1e-12)
+    # no reconstruction yet: infer_gtr runs the joint reconstruction itself (treeanc.py:1546-1547)
+    rt, dt = _pair(seed=62)
+    g1 = rt.infer_gtr(marginal=False, normalized_rate=False); g2 = dt.infer_gtr(marginal=False, normalized_rate=False)
+    assert np.allclose(g1.W, g2.W, rtol=1e-12) and np.allclose(g1.Pi, g2.Pi, rtol=1e-12) and np.isclose(g1.mu, g2.mu, rtol=1e-12)
+    assert dt.sequence_reconstruction == rt.sequence_reconstruction == 'joint'
+    # the mirror: infer_ancestral_sequences(infer_gtr=True) in joint mode
+    refenv.activate()
+    import oracle_engine
+    from treetime import GTR as RG
+    from treetime_b200 import synth
+    from treetime_b200.gtr import GTR
+    from treetime_b200.treeanc import TreeAnc
+    pi = np.array([.3, .2, .2, .29, .01])
+    T = synth.random_tree(30, seed=63, mean_bl=0.02)
+    g = GTR.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc')
+    idx = synth.evolve_alignment(T, 250, g.Pi, g.W, seed=63)
+    aln = synth.sprinkle_ambiguous({k: g.alphabet[v] for k, v in idx.items()}, 0.03, 'N-RY', seed=5)
+    r = refenv.reference_treeanc(T.to_newick(), aln, RG.custom(pi=pi.copy(), W=np.ones((5, 5)), alphabet='nuc'), rng_seed=1)
+    m = TreeAnc(tree=T.to_newick(), aln=aln, gtr=g, rng_seed=1, engine_factory=oracle_engine.factory)
+    assert r.infer_ancestral_sequences(marginal=False, infer_gtr=True) == m.infer_ancestral_sequences(marginal=False, infer_gtr=True)
+    assert np.allclose(r.gtr.W, m.gtr.W, rtol=1e-10) and np.allclose(r.gtr.Pi, m.gtr.Pi, rtol=1e-10)
+    assert np.isclose(r.tree.sequence_joint_LH, m.tree.sequence_joint_LH, rtol=1e-12)

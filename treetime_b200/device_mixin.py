@@ -586,10 +586,10 @@ class DeviceMarginalMixin(object):
         (:1556-1572) is one device kernel; GTR.infer (gtr.py:491-599) stays on the host."""
         if site_specific and self.data.compress:
             raise TypeError('TreeAnc.infer_gtr(): sequence compression and site specific GTR models are incompatible!')
-        if not marginal:
-            self._unsupported('joint-mode GTR inference is outside the B200 hot path')
         if not self.ok:
             raise self._missing_data_error('TreeAnc.infer_gtr: ERROR, sequences or tree are missing')
+        if not marginal:
+            return self._infer_gtr_from_sequences(site_specific, normalized_rate, fixed_pi, pc, **kwargs)
         if self.sequence_reconstruction != 'marginal':
             self._ml_anc_marginal(**kwargs)
         q = self.gtr.n_states
@@ -619,6 +619,46 @@ class DeviceMarginalMixin(object):
                 self._gtr.mu /= self._gtr.average_rate().mean()                 # treeanc.py:1626-1627
             else:
                 self._gtr.mu = 1.0
+        return self._gtr
+
+    def _infer_gtr_from_sequences(self, site_specific, normalized_rate, fixed_pi, pc, **kwargs):
+        """infer_gtr(marginal=False) (treeanc.py:1573-1589): substitutions counted on the reconstructed sequences.
+        Everything the reference collects from node.mutations and node.cseq is in the per-branch parent/child pair
+        counts the device already provides (ttb_branch_state_pairs, N2): a mutation j -> i adds its multiplicity to
+        n_ij and moves half the branch from T_i to T_j, every position adds the branch length to T_(child state);
+        pairs with an ambiguous character are skipped like the reference's `except: continue` / `cseq == nuc`."""
+        if site_specific:
+            self._unsupported('site-specific GTR inference from reconstructed sequences runs in the reference')
+        if not self.sequence_reconstruction:
+            self._ml_anc_joint(**kwargs)
+        C, F, tip_states, code_chars = self._pair_tables()               # raises Unsupported under masks
+        topo = self._flat()
+        q = self.gtr.n_states
+        alphabet = [str(c) for c in self.gtr.alphabet]
+        t = np.array([self._branch_length_to_gtr(n) for n in topo.nodes[1:]])
+        is_tip = np.array([n.is_terminal() for n in topo.nodes[1:]])
+        M = np.array(C[:, :, :q])                                        # [branch, parent j, child i]
+        if not tip_states and is_tip.any():
+            # tips show their alignment characters: keep the columns that are plain alphabet letters
+            col = {ch: k for k, ch in enumerate(code_chars) if ch is not None and k < C.shape[2]}
+            Mt = np.zeros((int(is_tip.sum()), q, q))
+            for i, ch in enumerate(alphabet):
+                if ch in col:
+                    Mt[:, :, i] = C[is_tip][:, :, col[ch]]
+            M[is_tip] = Mt
+        child = M.sum(axis=1)                                            # positions per child state
+        off = M.copy()
+        ar = np.arange(q)
+        off[:, ar, ar] = 0
+        n_ij = off.sum(axis=0).T                                         # i = derived, j = ancestral state
+        T_i = (t[:, None] * (child + 0.5 * off.sum(axis=2) - 0.5 * off.sum(axis=1))).sum(axis=0)
+        root_cseq = self.tree.root.cseq
+        m = self.data.multiplicity(mask=getattr(self.tree.root, 'mask', None))
+        root_state = np.array([np.sum((root_cseq == nuc) * m) for nuc in self.gtr.alphabet])
+        self._gtr = self._infer_gtr_from_counts(n_ij, T_i, root_state, fixed_pi, pc)
+        if normalized_rate:
+            self.logger('TreeAnc.infer_gtr: setting overall rate to 1.0...', 2)
+            self._gtr.mu = 1.0
         return self._gtr
 
     def _infer_site_specific_gtr_from_counts(self, n_ija, T_ia, root_state, pc):

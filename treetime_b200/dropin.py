@@ -276,9 +276,9 @@ class B200MarginalMixin(DeviceMarginalMixin):
         return super(DeviceMarginalMixin, self).optimal_marginal_branch_length(node, tol=tol)
 
     def infer_gtr(self, marginal=False, site_specific=False, **kwargs):
-        if marginal and self._device_ok() is None:
+        if self._device_ok() is None and (marginal or (not site_specific and (self._b200_live or not self.sequence_reconstruction))):
             try:
-                gtr = DeviceMarginalMixin.infer_gtr(self, marginal=True, site_specific=site_specific, **kwargs)
+                gtr = DeviceMarginalMixin.infer_gtr(self, marginal=marginal, site_specific=site_specific, **kwargs)
                 return gtr
             except Unsupported:
                 pass
