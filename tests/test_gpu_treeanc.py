@@ -278,3 +278,16 @@ def test_gpu_sampling_masks_site_specific_inference_vs_reference_golden(name):
     zx = G.load(name)
     z = G.load(str(zx['source']))
     G.check_extras(lambda **kw: TreeAnc(tree=str(z['newick']), aln=G.alignment(z), gtr=G.model(z), **kw), zx, exact=False)
+
+
+def test_gpu_infer_gtr_from_reconstructed_sequences():
+    """infer_gtr(marginal=False): counts from the device's pair tables equal those of the CPU oracle engine (pinned to
+    the reference in test_reference_live), after joint and marginal reconstructions, with and without tips."""
+    import oracle_engine
+    z = G.load('nuc40')
+    for recon in (dict(marginal=False), dict(marginal=True), dict(marginal=False, reconstruct_tip_states=True)):
+        a = gpu_from_golden(z)
+        b = gpu_from_golden(z, engine_factory=oracle_engine.factory)
+        assert a.infer_ancestral_sequences(**recon) == b.infer_ancestral_sequences(**recon)
+        ga, gb = a.infer_gtr(marginal=False, pc=2.0), b.infer_gtr(marginal=False, pc=2.0)
+        assert np.allclose(ga.W, gb.W, rtol=1e-10) and np.allclose(ga.Pi, gb.Pi, rtol=1e-10)
