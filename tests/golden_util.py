@@ -91,7 +91,10 @@ def check_extras(make_tt, zx, exact):
     assert np.allclose(tt.tree.sequence_LH, zx['mask_sequence_LH'], rtol=1e-11, atol=1e-11)
     for n, s in zip(nodes, zx['mask_cseq']):
         if not n.is_terminal():
-            assert ''.join(n.cseq) == str(s)
+            bad = n.cseq != np.array(list(str(s)))
+            if bad.any():       # identical except at exact ties (e.g. a pattern masked on every branch below a node)
+                import util
+                assert not exact and util.tie_mask(n.marginal_profile)[bad].all(), n.name
     for i in zx['mask_profile_nodes']:
         assert np.allclose(nodes[i].marginal_profile, zx['mask_profile_%d' % i], rtol=0, atol=1e-12)
         assert np.allclose(nodes[i].marginal_outgroup_LH, zx['mask_outgroup_%d' % i], rtol=0, atol=1e-12)
