@@ -451,6 +451,11 @@ struct SiteModel {
     }
   }
 };
+// Large alphabets: ptxas takes 192 registers for the postorder kernel when left alone (one block per SM: ncu shows 5
+// resident warps, issue slots 27 %); it needs only 126 without spilling, which lets three blocks share an SM.
+#ifndef TTB_POST_LARGEQ_REGS
+#define TTB_POST_LARGEQ_REGS 128
+#endif
 // site-specific level kernels keep the eigen-system in registers up to this alphabet size
 #define TTB_SS_REG_MAXQ 5
 // symmetric variant: register cap and ring depth chosen so that three blocks (12 pattern warps) fit one SM
@@ -713,7 +718,7 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
 template <int Q, bool SS, bool JOINT = false, bool SYM = false, bool MASK = false>
-__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : 255) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : (Q > 8 ? (JOINT ? 168 : TTB_POST_LARGEQ_REGS) : 255)) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles, int fbase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int RPC = Q;  // rows per child (the log-prefactors never travel: see Fpart)
@@ -1300,7 +1305,7 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // Stage rows: [0, Q) parent profile, child b -> rows [Q + b*Q, Q + (b+1)*Q) = S_c.
 // ---------------------------------------------------------------------------------------
 template <int Q, bool TIPS, bool SS, bool SYM = false, bool MASK = false>
-__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : 255) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
+__global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : (Q > 8 ? 168 : 255)) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool EST = ss_staged<Q, SS>();
