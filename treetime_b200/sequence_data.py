@@ -35,6 +35,50 @@ def _to_bytes(seq, convert_upper=True):
     return b
 
 
+def _blocks(L, width=2048):
+    return [(a, min(L, a + width)) for a in range(0, L, width)]
+
+
+def _pool_map(fn, jobs):
+    """numpy releases the GIL inside its loops: a few threads over column blocks keep the temporaries cache-sized and use
+    the host's cores (the column scans are the host side of N3)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    n = max(1, min(len(jobs), os.cpu_count() or 1, 16))
+    if n == 1:
+        return [fn(j) for j in jobs]
+    with ThreadPoolExecutor(max_workers=n) as ex:
+        return list(ex.map(fn, jobs))
+
+
+def _column_stats(A, amb):
+    """Per column: min and max over the entries != amb (255 / 0 if there is none) and whether all entries == amb."""
+    L = A.shape[1]
+    lo = np.empty(L, dtype=np.uint8); hi = np.empty(L, dtype=np.uint8); all_amb = np.empty(L, dtype=bool)
+
+    def one(b):
+        a0, a1 = b
+        X = A[:, a0:a1]
+        is_amb = X == amb
+        lo[a0:a1] = np.where(is_amb, 255, X).min(axis=0)
+        hi[a0:a1] = np.where(is_amb, 0, X).max(axis=0)
+        all_amb[a0:a1] = is_amb.all(axis=0)
+    _pool_map(one, _blocks(L))
+    return lo, hi, all_amb
+
+
+def _gather_columns(A, cols):
+    """A[:, cols] as a new C-contiguous matrix, row blocks in parallel."""
+    cols = np.asarray(cols)
+    out = np.empty((A.shape[0], cols.shape[0]), dtype=A.dtype)
+
+    def one(b):
+        r0, r1 = b
+        np.take(A[r0:r1], cols, axis=1, out=out[r0:r1])
+    _pool_map(one, _blocks(A.shape[0], 512))
+    return out
+
+
 def read_fasta(path):
     names, seqs, cur = [], [], []
     with open(path) as fh:
@@ -91,7 +135,7 @@ class SequenceData(object):
         if any(r.shape[0] != L for r in rows):
             raise ValueError('SequenceData: sequences differ in length')
         self._matrix = np.vstack(rows) if len(rows) > 1 else rows[0][None, :].copy()
-        if bulk_upper:
+        if bulk_upper and self._matrix.max() >= 97:        # one pass without temporaries decides whether any letter is lower case
             lower = (self._matrix >= 97) & (self._matrix <= 122)
             if lower.any():
                 self._matrix[lower] -= 32
@@ -126,12 +170,16 @@ class SequenceData(object):
     def _fill_overhangs(self, amb):
         """Leading/trailing gaps -> ambiguous (seq2array fill_overhangs, seq_utils.py:196-202)."""
         A = self._matrix
-        nongap = A != ord('-')
-        any_ng = nongap.any(axis=1)
-        first = np.where(any_ng, nongap.argmax(axis=1), A.shape[1])
-        last = np.where(any_ng, A.shape[1] - 1 - nongap[:, ::-1].argmax(axis=1), -1)
-        pos = np.arange(A.shape[1])[None, :]
-        A[(pos < first[:, None]) | (pos > last[:, None])] = amb
+        gap = ord('-')
+        # only rows that start or end with a gap have overhangs: no full-matrix temporaries for the others
+        for r in np.nonzero((A[:, 0] == gap) | (A[:, -1] == gap))[0]:
+            row = A[r]
+            ng = np.nonzero(row != gap)[0]
+            if ng.size == 0:
+                row[:] = amb
+            else:
+                row[:ng[0]] = amb
+                row[ng[-1] + 1:] = amb
 
     @property
     def aln(self):
@@ -159,10 +207,7 @@ class SequenceData(object):
             self._finish()
             return
         amb = ord(self.ambiguous) if self.ambiguous is not None else 256
-        is_amb = A == amb
-        lo = np.where(is_amb, 255, A).min(axis=0)      # extrema over non-ambiguous entries
-        hi = np.where(is_amb, 0, A).max(axis=0)
-        all_amb = is_amb.all(axis=0)
+        lo, hi, all_amb = _column_stats(A, amb)        # extrema over non-ambiguous entries
         # constant (possibly after replacing the ambiguous character by the single other letter)
         const = (lo == hi) | all_amb
         letter = np.where(all_amb, amb, lo).astype(np.uint8)
@@ -177,7 +222,7 @@ class SequenceData(object):
         n_pat = uniq.shape[0]
         first_pos = np.empty(n_pat, dtype=np.int64)
         first_pos[rank] = first_idx
-        C = A[:, first_pos].copy()
+        C = _gather_columns(A, first_pos)
         cc = const[first_pos]
         if cc.any():                                    # constant patterns: ambiguous replaced (:391)
             C[:, cc] = letter[first_pos][cc][None, :]
@@ -240,7 +285,7 @@ class SequenceData(object):
     @property
     def compressed_matrix(self):
         if self._compressed_matrix is None:
-            C = self.matrix[:, self.pattern_first_position].copy()
+            C = _gather_columns(self.matrix, self.pattern_first_position)
             cc = self.pattern_const_letter != 0
             if cc.any():
                 C[:, cc] = self.pattern_const_letter[cc][None, :]
