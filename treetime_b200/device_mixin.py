@@ -87,8 +87,14 @@ class DeviceMarginalMixin(object):
             for c, i in lut.items():
                 lut8[ord(c)] = i
             rows = np.array([self.data._row.get(topo.nodes[n].name, -1) for n in topo.tip_nodes])
-            have = rows >= 0
-            codes[have] = lut8[self.data.compressed_matrix[rows[have], lo:hi]]
+            have = np.flatnonzero(rows >= 0)
+            cm = self.data.compressed_matrix
+            from .sequence_data import _blocks, _pool_map
+
+            def encode(b):          # row blocks on the host's threads: gather the tips' rows, map characters to codes
+                k = have[b[0]:b[1]]
+                codes[k] = np.take(lut8, cm[rows[k], lo:hi])
+            _pool_map(encode, _blocks(have.shape[0], 256))
         else:
             ca = self.data.compressed_alignment
             for n in topo.tip_nodes:

@@ -257,7 +257,12 @@ class TreeAnc(DeviceMarginalMixin):
                     raise MissingDataError('TreeAnc._check_alignment_tree_gtr_consistency: At least 30\\% terminal nodes '
                                            'cannot be assigned a sequence!\nAre you sure the alignment belongs to the tree?')
         # extend_profile (seq_utils.py:126-136): unknown characters are missing data
-        present = np.flatnonzero(np.bincount(self.data._matrix.ravel(), minlength=256))     # characters in the alignment
+        # characters in the alignment: histogram per block of rows on the host's threads (np.bincount widens its input to
+        # 8-byte integers, so one call over the whole matrix allocates eight times the alignment)
+        from .sequence_data import _blocks, _pool_map
+        M = self.data._matrix
+        hist = _pool_map(lambda b: np.bincount(M[b[0]:b[1]].ravel(), minlength=256), _blocks(M.shape[0], 256))
+        present = np.flatnonzero(np.sum(hist, axis=0))
         for b in present:
             c = chr(int(b))
             if c not in self.gtr.profile_map:
