@@ -81,8 +81,8 @@ class DeviceMarginalMixin(object):
         topo = self._flat()
         chars, lut, table = code_table(self.gtr.profile_map, self.gtr.n_states)
         lo, hi = self._shard()
-        codes = np.full((topo.n_tips, hi - lo), len(chars), dtype=np.uint8)     # default: missing = all ones
         if hasattr(self.data, 'compressed_matrix'):
+            codes = np.empty((topo.n_tips, hi - lo), dtype=np.uint8)
             lut8 = np.full(256, 255, dtype=np.uint8)
             for c, i in lut.items():
                 lut8[ord(c)] = i
@@ -95,13 +95,15 @@ class DeviceMarginalMixin(object):
                 k = have[b[0]:b[1]]
                 codes[k] = np.take(lut8, cm[rows[k], lo:hi])
             _pool_map(encode, _blocks(have.shape[0], 256))
+            codes[rows < 0] = len(chars)                                      # tips without sequence: missing = all ones
         else:
+            codes = np.full((topo.n_tips, hi - lo), len(chars), dtype=np.uint8)
             ca = self.data.compressed_alignment
             for n in topo.tip_nodes:
                 name = topo.nodes[n].name
                 if name in ca:
                     codes[topo.tip_row[n]] = encode_chars(np.asarray(ca[name])[lo:hi], chars)
-        if (codes == 255).any():
+        if codes.size and codes.max() == 255:             # one pass, no temporary
             raise KeyError('alignment contains characters that are not in the profile map')
         return codes, table
 
