@@ -1155,7 +1155,7 @@ int ttb_sample_states(ttb_handle h, int32_t n, const int32_t* nodes, const doubl
   // the uniforms travel in blocks of at most 256 MB (TTB_SAMPLE_BLOCK_DOUBLES overrides the block size: tests)
   size_t blk_doubles = (size_t)1 << 25;
   if (const char* e = getenv("TTB_SAMPLE_BLOCK_DOUBLES")) blk_doubles = (size_t)std::max(1LL, atoll(e));
-  const int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n, 1), blk_doubles / Lp));
+  const int blk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)std::max(n, 1), blk_doubles / Lp, (size_t)65535}));   // grid.y <= 65535
   if (n) {
     if ((rc = h->d_sg_uniforms.alloc((size_t)blk * Lp))) return rc;
     if ((rc = h->d_enodes.alloc((size_t)n))) return rc;
