@@ -123,3 +123,55 @@ def test_product_path_fails_loudly_without_gpu():
     tt = TreeAnc(tree=tree, aln=aln, gtr=g)
     with pytest.raises(_lib.TTBError):
         tt.infer_ancestral_sequences(marginal=True)       # no CPU fallback
+
+
+def test_threaded_column_scans_equal_plain_numpy():
+    """The host side of pattern compression works on column / row blocks on a thread pool: same statistics, same
+    gather, same overhang filling as the one-shot numpy expressions they replaced."""
+    from treetime_b200 import sequence_data as sdm
+    rng = np.random.default_rng(3)
+    A = rng.choice(np.frombuffer(b'ACGT-NRY', dtype=np.uint8), size=(700, 5000), p=[.22, .22, .22, .22, .05, .05, .01, .01])
+    A[:, 10] = ord('N'); A[:, 11] = ord('A'); A[5, 11] = ord('N')        # all-ambiguous and constant-after-replacement columns
+    amb = ord('N')
+    lo, hi, aa = sdm._column_stats(A, amb)
+    is_amb = A == amb
+    assert np.array_equal(lo, np.where(is_amb, 255, A).min(axis=0)) and np.array_equal(hi, np.where(is_amb, 0, A).max(axis=0))
+    assert np.array_equal(aa, is_amb.all(axis=0))
+    cols = rng.permutation(5000)[:1234]
+    G_ = sdm._gather_columns(A, cols)
+    assert G_.flags['C_CONTIGUOUS'] and np.array_equal(G_, A[:, cols])
+    # overhangs: only rows that start / end with a gap are touched; an all-gap row becomes all ambiguous
+    B = A[:40, :200].copy()
+    B[3] = ord('-'); B[5, :20] = ord('-'); B[7, -30:] = ord('-'); B[9, 0] = ord('-'); B[11, 50:60] = ord('-')
+    sd = SequenceData({'s%02d' % i: B[i].copy() for i in range(40)}, ambiguous='N', fill_overhangs=True)
+    nongap = B != ord('-'); any_ng = nongap.any(axis=1)
+    first = np.where(any_ng, nongap.argmax(axis=1), B.shape[1]); last = np.where(any_ng, B.shape[1] - 1 - nongap[:, ::-1].argmax(axis=1), -1)
+    pos = np.arange(B.shape[1])[None, :]
+    ref = B.copy(); ref[(pos < first[:, None]) | (pos > last[:, None])] = ord('N')
+    assert np.array_equal(sd.matrix, ref)
+
+
+def test_vectorised_branch_length_floor_and_override():
+    """_branch_lengths_to_gtr applies treeanc.py:752-760 to all nodes at once and still honours a subclass that
+    overrides the per-node method."""
+    import oracle_engine
+    from treetime_b200.treeanc import TreeAnc
+    tree = synth.random_tree(30, seed=2, mean_bl=1e-4, zero_frac=0.3)
+    g = util.nuc_gtr()
+    aln = {k: g.alphabet[v] for k, v in synth.evolve_alignment(tree, 120, g.Pi, g.W, seed=2).items()}
+    tt = TreeAnc(tree=tree.to_newick(), aln=aln, gtr=g, engine_factory=oracle_engine.factory)
+    nodes = tt._flat().nodes
+    per_node = np.array([tt._branch_length_to_gtr(n) for n in nodes])
+    assert np.array_equal(tt._branch_lengths_to_gtr(nodes), per_node) and (per_node[1:] > 0).all()
+    tt.use_mutation_length = True
+    for n in nodes:
+        n.mutation_length = 2.0 * (n.branch_length or 0.0)
+    assert np.array_equal(tt._branch_lengths_to_gtr(nodes), np.array([tt._branch_length_to_gtr(n) for n in nodes]))
+
+    class Doubling(TreeAnc):
+        def _branch_length_to_gtr(self, node):
+            return 2.0 * TreeAnc._branch_length_to_gtr(self, node)
+    t2 = Doubling(tree=tree.to_newick(), aln=aln, gtr=util.nuc_gtr(), engine_factory=oracle_engine.factory)
+    n2 = t2._flat().nodes
+    assert np.array_equal(t2._branch_lengths_to_gtr(n2), np.array([t2._branch_length_to_gtr(n) for n in n2]))
+    assert np.array_equal(t2._branch_lengths_to_gtr(n2)[1:], 2.0 * per_node[1:])
