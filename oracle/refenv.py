@@ -1,19 +1,34 @@
-"""TEST-ONLY: make the UNMODIFIED reference importable in the build container.
+"""TEST-ONLY: make the UNMODIFIED reference importable.
 
-Puts oracle/bioshim (a stand-in for the missing Biopython) and /root/reference
-first on sys.path.  Used by oracle/make_golden.py and
-oracle/validate_against_reference.py, and by tests that are skipped when
-/root/reference does not exist (i.e. on the GPU box)."""
+Puts oracle/bioshim (a stand-in for the missing Biopython) and the reference first on sys.path.  The
+reference is /root/reference in the build container or -- on the GPU box, where that path does not exist
+-- the pip-installed, git-ignored copy oracle/_ref made by oracle/stage_ref.py.  Used by
+oracle/make_golden.py, oracle/validate_against_reference.py, the live-reference tests (skipped when
+neither exists) and bench.py's `--impl reference` arm."""
 import os
 import sys
 
-REFERENCE = os.environ.get('TREETIME_REFERENCE', '/root/reference')
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
+STAGED = os.path.join(HERE, '_ref')
+
+
+def _find():
+    for p in (os.environ.get('TREETIME_REFERENCE'), '/root/reference', STAGED):
+        if p and os.path.isfile(os.path.join(p, 'treetime', 'treeanc.py')):
+            return p
+    return os.environ.get('TREETIME_REFERENCE', '/root/reference')
+
+
+REFERENCE = _find()
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE, 'treetime'))
+    return os.path.isfile(os.path.join(REFERENCE, 'treetime', 'treeanc.py'))
+
+
+def is_staged_copy():
+    return os.path.abspath(REFERENCE) == os.path.abspath(STAGED)
 
 
 def activate():

@@ -234,3 +234,61 @@ def test_mirror_sampling_masks_site_specific_inference_vs_reference_golden(name)
     z = G.load(str(zx['source']))
     G.check_extras(lambda **kw: TreeAnc(tree=str(z['newick']), aln=G.alignment(z), gtr=G.model(z),
                                         engine_factory=oracle_engine.factory, **kw), zx, exact=True)
+
+
+def _small_problem(newick, L=120, seed=5):
+    from treetime_b200 import synth
+    from treetime_b200.gtr import GTR
+    from treetime_b200.tree import read_newick
+    g = GTR.custom(pi=np.array([.3, .2, .2, .29, .01]), W=np.ones((5, 5)), alphabet='nuc')
+    T = read_newick(newick)
+    idx = synth.evolve_alignment(T, L, g.Pi, g.W, seed=seed, mu=30.0)
+    aln = {k: g.alphabet[v] for k, v in idx.items()}
+    return g, aln
+
+
+def test_same_shape_tip_permutation_reuploads_the_tip_codes():
+    """Advisor finding (round 1): swapping two leaves keeps parent / child_idx identical; the device must still
+    get the new row -> tip assignment instead of returning the LH of the old one."""
+    nwk = '(A:0.02,(B:0.03,(C:0.01,D:0.04):0.02):0.01);'
+    g, aln = _small_problem(nwk)
+    tt = TreeAnc(tree=nwk, aln=aln, gtr=g, rng_seed=1, engine_factory=oracle_engine.factory)
+    tt.infer_ancestral_sequences(marginal=True)
+    lh0 = tt.sequence_LH()
+    tips = {n.name: n for n in tt.tree.get_terminals()}
+    a, d = tips['A'], tips['D']
+    pa, pd = a.up, d.up
+    ia, id_ = pa.clades.index(a), pd.clades.index(d)
+    pa.clades[ia], pd.clades[id_] = d, a
+    a.branch_length, d.branch_length = d.branch_length, a.branch_length
+    a.mutation_length, d.mutation_length = a.branch_length, d.branch_length
+    tt._prepare_nodes()
+    tt.infer_ancestral_sequences(marginal=True)
+    swapped = '(D:0.02,(B:0.03,(C:0.01,A:0.04):0.02):0.01);'
+    fresh = TreeAnc(tree=swapped, aln=aln, gtr=g, rng_seed=1, engine_factory=oracle_engine.factory)
+    fresh.infer_ancestral_sequences(marginal=True)
+    assert abs(lh0 - fresh.sequence_LH()) > 1e-6          # the permutation matters for this alignment
+    assert tt.sequence_LH() == fresh.sequence_LH()
+
+
+def test_n_diff_after_a_topology_change_compares_surviving_nodes():
+    """Advisor finding (round 1): after collapsing an internal node the next pass must compare every surviving node
+    with its own previous sequence (treeanc.py:925-926), not count every position as changed."""
+    nwk = '((A:0.02,B:0.03):0.01,((C:0.01,D:0.04):0.00001,E:0.02):0.02,F:0.03);'
+    g, aln = _small_problem(nwk, L=150, seed=9)
+    tt = TreeAnc(tree=nwk, aln=aln, gtr=g, rng_seed=1, engine_factory=oracle_engine.factory)
+    tt.infer_ancestral_sequences(marginal=True)
+    before = {id(n): n.cseq.copy() for n in tt.tree.get_nonterminals()}
+    cd = [n for n in tt.tree.get_nonterminals() if sorted(c.name or '' for c in n.clades) == ['C', 'D']][0]
+    up = cd.up
+    k = up.clades.index(cd)
+    for c in cd.clades:
+        c.branch_length += cd.branch_length
+        c.mutation_length = c.branch_length
+    up.clades[k:k + 1] = cd.clades
+    tt._prepare_nodes()
+    n_diff = tt.infer_ancestral_sequences(marginal=True)
+    expect = sum(int((n.cseq != before[id(n)]).sum()) for n in tt.tree.get_nonterminals() if n.up is not None)
+    assert n_diff == expect
+    assert n_diff < tt.data.compressed_length            # far from "every position of every node"
+    assert tt.infer_ancestral_sequences(marginal=True) == 0

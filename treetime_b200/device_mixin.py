@@ -42,6 +42,8 @@ class DeviceMarginalMixin(object):
         self._device_masks = None
         self._cache = {}
         self._seq_cache = {}
+        self._stale_states = None
+        self._device_tips = None
 
     def _unsupported(self, why):
         raise Unsupported(why)
@@ -61,8 +63,28 @@ class DeviceMarginalMixin(object):
     def _topology_changed(self):
         return self._topo is None or getattr(self, '_topo_dirty', False)
 
+    def _snapshot_states(self):
+        """State indices of every reconstructed node of the CURRENT device topology, keyed by node object:
+        {id(node): uint8[L' shard]}.  Taken just before the flattening is rebuilt: ttb_set_tree drops the
+        device's previous states, but the reference compares every surviving node with its own old cseq
+        (treeanc.py:925-926) -- so after prune_short_branches / resolve_polytomies / reroot N_diff is counted
+        on the host against this snapshot.  None when there is nothing to compare with."""
+        eng, topo = self._engine, self._topo
+        if eng is None or topo is None or not self.sequence_reconstruction or not getattr(self, '_b200_live', True):
+            return None
+        try:
+            rows = eng.all_seq_idx()
+            old = {id(topo.nodes[n]): rows[k] for k, n in enumerate(topo.internal_nodes)}
+            if self.reconstructed_tip_sequences:
+                tips = eng.seq_idx(topo.tip_nodes)
+                old.update({id(topo.nodes[n]): tips[k] for k, n in enumerate(topo.tip_nodes)})
+        except RuntimeError:            # TTBError: the engine holds no reconstruction
+            return None
+        return old
+
     def _refresh_topology(self):
         if self._topology_changed():
+            self._stale_states = self._snapshot_states()
             self._topo = FlatTopology(self.tree.root)
             for i, n in enumerate(self._topo.nodes):
                 n._fid = i
@@ -122,6 +144,12 @@ class DeviceMarginalMixin(object):
         data_id = (id(self.data), self.data.compressed_length, len(self.gtr.profile_map))
         if data_id != self._device_data_id:
             self._device_patterns = False
+        # the same shape with the tips in other positions (swapped leaves, reroot + ladderize of a symmetric tree,
+        # `tt.tree = other`) leaves parent / child_idx unchanged: the row -> tip assignment is part of the identity
+        tips = hash(tuple(topo.nodes[n].name for n in topo.tip_nodes))
+        if tips != self._device_tips:
+            self._device_patterns = False
+            self._device_tips = tips
         if not self._device_patterns:
             self._device_data_id = data_id
             lo, hi = self._shard()
@@ -275,6 +303,7 @@ class DeviceMarginalMixin(object):
             raise ValueError("sample_from_profile must be a bool or 'root'")
         eng = self._sync_device()
         topo = self._flat()
+        stale, self._stale_states = self._stale_states, None
         eng.marginal(reconstruct_tips=reconstruct_tip_states, keep_prev=other_sample)
         tot, nd = eng.results()
         if self.comm.world_size > 1:
@@ -295,7 +324,7 @@ class DeviceMarginalMixin(object):
         nd_tips = None
         if other_sample:
             nd, nd_tips = self._sample_states(eng, topo, reconstruct_tip_states)
-        N_diff = self._n_diff(eng, topo, nd, reconstruct_tip_states, prev_tips, had_reconstruction, nd_tips)
+        N_diff = self._n_diff(eng, topo, nd, reconstruct_tip_states, prev_tips, had_reconstruction, nd_tips, stale=stale)
         self.logger('TreeAnc._ml_anc_marginal: ...done', 3)
         return N_diff
 
@@ -319,10 +348,12 @@ class DeviceMarginalMixin(object):
             nd, nd_tips = (int(round(x)) for x in self.comm.allreduce_sum(np.array([float(nd), float(nd_tips)])))
         return nd + nd_tips, nd_tips
 
-    def _n_diff(self, eng, topo, nd, reconstruct_tip_states, prev_tips, had_reconstruction=Ellipsis, nd_tips=None):
+    def _n_diff(self, eng, topo, nd, reconstruct_tip_states, prev_tips, had_reconstruction=Ellipsis, nd_tips=None, stale=None):
         """N_diff of a pass (treeanc.py:925-928 / 1042-1045).  The device counts changed states against
-        the previous device states; two host-side corrections reproduce the reference:
+        the previous device states; host-side corrections reproduce the reference:
           * no previous reconstruction -> every reconstructed position counts;
+          * the topology was rebuilt since the previous pass (`stale` = _snapshot_states() of the old numbering)
+            -> every surviving node is compared with its own old states, new nodes count fully;
           * tips reconstructed now but not before -> the reference compares them with the alignment's own
             (possibly ambiguous) characters, the device compared them with stale / unset states."""
         L = self.data.compressed_length
@@ -331,6 +362,25 @@ class DeviceMarginalMixin(object):
         if not had_reconstruction:
             n_rec = (topo.n_nodes - 1) if reconstruct_tip_states else (topo.n_nodes - topo.n_tips - 1)
             return n_rec * L
+        if stale is not None:
+            lo, hi = self._shard()
+            rows = eng.all_seq_idx()
+            nd = 0
+            for k, n in enumerate(topo.internal_nodes):
+                if n:                                                # the root's sequence is not compared
+                    old = stale.get(id(topo.nodes[n]))
+                    nd += (hi - lo) if old is None else int((rows[k] != old).sum())
+            nd_tips = 0
+            if reconstruct_tip_states:
+                for b in range(0, topo.n_tips, 256):
+                    blk = topo.tip_nodes[b:b + 256]
+                    idx = eng.seq_idx(blk)
+                    for k, n in enumerate(blk):
+                        old = stale.get(id(topo.nodes[n]))
+                        nd_tips += (hi - lo) if old is None else int((idx[k] != old).sum())
+            if self.comm.world_size > 1:
+                nd, nd_tips = (int(round(x)) for x in self.comm.allreduce_sum(np.array([float(nd), float(nd_tips)])))
+            nd += nd_tips
         nd = int(round(nd))
         if reconstruct_tip_states and not prev_tips:
             if nd_tips is None:
@@ -368,6 +418,7 @@ class DeviceMarginalMixin(object):
             self._unsupported('joint reconstruction with site-specific models runs in the reference')
         eng = self._sync_device()
         topo = self._flat()
+        stale, self._stale_states = self._stale_states, None
         if root_sample:
             eng.joint(reconstruct_tips=reconstruct_tip_states, trace=False)
             eng.results()
@@ -385,7 +436,7 @@ class DeviceMarginalMixin(object):
         self._seq_cache = {}
         self.tree.sequence_LH = self._gather_patterns(eng.site_lh())
         self.tree.sequence_joint_LH = float(tot)
-        N_diff = self._n_diff(eng, topo, nd, reconstruct_tip_states, self.reconstructed_tip_sequences)
+        N_diff = self._n_diff(eng, topo, nd, reconstruct_tip_states, self.reconstructed_tip_sequences, stale=stale)
         self.tree.root._cseq_override = None
         self.reconstructed_tip_sequences = reconstruct_tip_states
         self.sequence_reconstruction = 'joint'
@@ -420,7 +471,10 @@ class DeviceMarginalMixin(object):
         used by infer_gtr are accumulated on the device instead)."""
         pp, pc = self.marginal_branch_profile(node)
         expQt = self.gtr.expQt(self._t_last[node._fid]) + ttconf.SUPERTINY_NUMBER
-        stack = np.einsum('ai,aj,ij->aij', pc, pp, expQt)
+        if np.ndim(expQt) == 3:                                                  # site-specific: treeanc.py:1107-1108
+            stack = np.einsum('ai,aj,ija->aij', pc, pp, expQt)
+        else:
+            stack = np.einsum('ai,aj,ij->aij', pc, pp, expQt)
         stack = stack / stack.sum(axis=2).sum(axis=1)[:, None, None]
         return stack[self.data.full_to_compressed_sequence_map] if full_sequence else stack
 
@@ -722,4 +776,26 @@ class DeviceMarginalMixin(object):
         else:
             self.gtr.mu = old_mu
             self.logger('treeanc:optimize_gtr_rate: optimization failed, continuing with previous mu', 1, warn=True)
+        self._invalidate_after_lh_only()
+
+    def _invalidate_after_lh_only(self):
+        """The LH-only trial passes overwrote S and P on the device but not M: outgroup messages, branch objectives and
+        substitution counts recomputed from M_old / (S_new P_new) would mix two passes, and arrays cached on the host come
+        from yet another state.  The reference's stored arrays stay self-consistent (they belong to the last trial rate);
+        here one full pass at the final rate makes everything consistent again (same options as the last reconstruction)."""
+        if self.sequence_reconstruction == 'marginal' and self._engine is not None:
+            eng = self._sync_device()
+            eng.marginal(reconstruct_tips=bool(self.reconstructed_tip_sequences))
+            tot, _ = eng.results()
+            if self.comm.world_size > 1:
+                tot = self.comm.allreduce_sum(np.array([tot]))[0]
+            self.tree.sequence_LH = self._gather_patterns(eng.site_lh())
+            self.tree.total_sequence_LH = float(tot)
+            self.tree.sequence_marginal_LH = self.tree.total_sequence_LH
+        self._cache = {}
+        self._seq_cache = {}
+        drop = getattr(self, '_drop_node_caches', None)
+        if drop is not None and getattr(self, '_b200_live', False):
+            drop()
+            self._b200_live = True
 

@@ -147,8 +147,8 @@ class B200MarginalMixin(DeviceMarginalMixin):
                                 c = None
                             if c is not None:
                                 old[id(n)] = np.array(c)
+                topo = self._refresh_topology()      # (snapshots the device's states if the tree was edited: N_diff)
                 self._drop_node_caches()
-                topo = self._refresh_topology()
                 _install_hook(type(self.tree.root))
                 # the reference keeps stale per-node arrays from an earlier (reference) pass: drop them
                 for n in topo.nodes:
@@ -202,8 +202,8 @@ class B200MarginalMixin(DeviceMarginalMixin):
                                 c = None
                             if c is not None:
                                 old[id(n)] = np.array(c)
-                self._drop_node_caches()
                 topo = self._refresh_topology()
+                self._drop_node_caches()
                 _install_hook(type(self.tree.root))
                 for n in topo.nodes:
                     d = n.__dict__
@@ -391,8 +391,9 @@ class B200ClockMixin(object):
                and not any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades()))
         if not use:
             return super(B200ClockMixin, self).init_date_constraints(*args, **kwargs)
-        if not self.sequence_reconstruction:     # clock_tree.py:335-338
-            self.infer_ancestral_sequences('probabilistic', marginal=True, sample_from_profile='root')
+        if not self.sequence_reconstruction:     # clock_tree.py:335-338: everything but clock_rate is forwarded
+            fwd = {k: v for k, v in kwargs.items() if k != 'clock_rate'}
+            self.infer_ancestral_sequences('probabilistic', marginal=True, sample_from_profile='root', **fwd)
         if not self._b200_live:
             return super(B200ClockMixin, self).init_date_constraints(*args, **kwargs)
         self._b200_grid_tab = self._tabulate_branch_grids()

@@ -234,7 +234,22 @@ class GTRSiteSpecific(GTR):
         return gtr
 
     def expQt(self, t):
-        raise NotImplementedError('site-specific exp(Qt) is evaluated on the device')
+        """Per-site transition matrices stacked as (q, q, L): [i, j, a] = Prob(i <- j | site a, t)
+        (gtr_site_specific.py:350-371).  Host-side accessor for single branches (get_branch_mutation_matrix); the
+        passes evaluate it on the device.  With `approximate` and t * rate_scale < 10 the reference interpolates the
+        matrices linearly on its 61-point grid; the matrices are linear in the eigen-factors exp(lambda mu t), so
+        interpolating those gives the same result."""
+        from .flatten import expqt_t_grid
+        lam = self.eigenvals * self.mu
+        if getattr(self, 'approximate', True) and t * self.rate_scale < 10:
+            grid = expqt_t_grid(self.rate_scale)
+            hi = int(np.clip(np.searchsorted(grid, t), 1, grid.shape[0] - 1))
+            lo = hi - 1
+            e = np.exp(lam * grid[lo])
+            e = e + (np.exp(lam * grid[hi]) - e) * ((t - grid[lo]) / (grid[hi] - grid[lo]))
+        else:
+            e = np.exp(lam * t)
+        return np.einsum('jia,ja,kja->ika', self.v, e, self.v_inv)
 
 
 def infer_gtr_from_counts(nij, Ti, root_state, fixed_pi=None, pc=1.0, gap_limit=0.01, alphabet='nuc',
