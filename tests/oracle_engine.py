@@ -59,6 +59,25 @@ class OracleEngine(object):
         self.prev_idx = None
         self.masks = None
 
+    def set_patterns_sparse(self, ref_codes, entry_row, entry_pos, entry_code, code_profiles, multiplicity):
+        n_tips = int((self.tip_row >= 0).sum())
+        codes = np.repeat(np.asarray(ref_codes, dtype=np.uint8)[None, :], n_tips, axis=0)
+        codes[np.asarray(entry_row), np.asarray(entry_pos)] = entry_code
+        self.set_patterns(codes, code_profiles, multiplicity)
+
+    def mutations(self, max_n=None):
+        idx = self.all_seq_idx()
+        internal = np.nonzero(self.tip_row < 0)[0]
+        slot = {int(n): k for k, n in enumerate(internal)}
+        node, pos, st = [], [], []
+        for k, n in enumerate(internal):
+            if n == 0:
+                continue
+            d = np.nonzero(idx[k] != idx[slot[int(self.flat['parent'][n])]])[0]
+            node.append(np.full(d.shape[0], n, dtype=np.int32)); pos.append(d.astype(np.int32)); st.append(idx[k][d])
+        cat = lambda x, dt: np.concatenate(x).astype(dt) if x else np.zeros(0, dtype=dt)  # noqa: E731
+        return idx[0].copy(), cat(node, np.int32), cat(pos, np.int32), cat(st, np.uint8)
+
     def alignment_stats(self, aln, fill_overhangs=False, gap='-', fill='N', ambiguous='N'):
         A = np.array(aln, dtype=np.uint8)
         if fill_overhangs:

@@ -292,3 +292,20 @@ def test_n_diff_after_a_topology_change_compares_surviving_nodes():
     assert n_diff == expect
     assert n_diff < tt.data.compressed_length            # far from "every position of every node"
     assert tt.infer_ancestral_sequences(marginal=True) == 0
+
+
+def test_sparse_host_interface_gives_the_same_reconstruction():
+    """TreeAnc(sparse_io=True): tip codes uploaded as reference row + differences, sequences read back as root row +
+    differences from the parent (sequence_differences); same numbers as the dense interface."""
+    from treetime_b200.sparse import expand_mutations
+    z = G.load('nuc40')
+    dense = mirror_from_golden(z)
+    sparse = mirror_from_golden(z, sparse_io=True)
+    assert dense.infer_ancestral_sequences(marginal=True) == sparse.infer_ancestral_sequences(marginal=True)
+    assert dense.sequence_LH() == sparse.sequence_LH()
+    root, node, pos, state = sparse.sequence_differences()
+    topo = sparse._flat()
+    idx = expand_mutations(topo.parent, topo.tip_row, root, node, pos, state)
+    for k, n in enumerate(topo.internal_nodes):
+        assert (sparse.gtr.alphabet[idx[k]] == topo.nodes[n].cseq).all()
+        assert (dense._flat().nodes[n].cseq == topo.nodes[n].cseq).all()

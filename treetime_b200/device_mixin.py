@@ -44,6 +44,12 @@ class DeviceMarginalMixin(object):
         self._seq_cache = {}
         self._stale_states = None
         self._device_tips = None
+        self._tips_of_topo = (None, None)
+        # sparse host interface: the tip codes cross PCIe as (reference row + differences) -- the analogue of the
+        # reference's dict-of-differences alignments (sequence_data.py:363-383) -- and sequence_differences() returns
+        # the reconstruction as (root row + states differing from the parent), the content of node.mutations
+        self.sparse_io = False
+        self._sparse_codes = None
 
     def _unsupported(self, why):
         raise Unsupported(why)
@@ -146,7 +152,9 @@ class DeviceMarginalMixin(object):
             self._device_patterns = False
         # the same shape with the tips in other positions (swapped leaves, reroot + ladderize of a symmetric tree,
         # `tt.tree = other`) leaves parent / child_idx unchanged: the row -> tip assignment is part of the identity
-        tips = hash(tuple(topo.nodes[n].name for n in topo.tip_nodes))
+        if self._tips_of_topo[0] is not topo:                  # once per flattening, not per pass
+            self._tips_of_topo = (topo, hash(tuple(topo.nodes[n].name for n in topo.tip_nodes)))
+        tips = self._tips_of_topo[1]
         if tips != self._device_tips:
             self._device_patterns = False
             self._device_tips = tips
@@ -162,6 +170,14 @@ class DeviceMarginalMixin(object):
                 rows = np.array([self.data._row.get(topo.nodes[n].name, -1) for n in topo.tip_nodes], dtype=np.int32)
                 eng.set_patterns_from_alignment(self.data.pattern_first_position[lo:hi], self.data.pattern_const_letter[lo:hi],
                                                 rows, lut8, len(chars), table, self.data.multiplicity()[lo:hi])
+            elif self.sparse_io:
+                key = (self._device_data_id, self._device_tips, lo, hi)
+                if self._sparse_codes is None or self._sparse_codes[0] != key:
+                    from .sparse import sparse_from_dense
+                    codes, table = self._tip_codes()
+                    self._sparse_codes = (key, sparse_from_dense(codes), table, np.ascontiguousarray(self.data.multiplicity()[lo:hi]))
+                _, (ref, e_row, e_pos, e_code), table, mult = self._sparse_codes
+                eng.set_patterns_sparse(ref, e_row, e_pos, e_code, table, mult)
             else:
                 codes, table = self._tip_codes()
                 eng.set_patterns(codes, table, self.data.multiplicity()[lo:hi], validate=False)   # codes built by _tip_codes
@@ -202,9 +218,23 @@ class DeviceMarginalMixin(object):
             return np.array([self._branch_length_to_gtr(n) for n in nodes], dtype=np.float64)
         attr = 'mutation_length' if self.use_mutation_length else 'branch_length'
         floor = ttconf.MIN_BRANCH_LENGTH * self.one_mutation
-        vals = np.array(list(map(operator.attrgetter(attr), nodes)), dtype=np.float64)      # None (an unset root) -> nan
-        vals[0] = floor if not np.isfinite(vals[0]) else vals[0]
+        n = len(nodes)
+        vals = np.empty(n, dtype=np.float64)
+        try:        # instance attributes straight from the nodes' dicts, no list of boxed floats in between
+            vals[1:] = np.fromiter(map(operator.itemgetter(attr), self._node_dicts(nodes)[1:]), dtype=np.float64, count=n - 1)
+            root_val = nodes[0].__dict__.get(attr)
+        except (KeyError, TypeError, ValueError):           # properties, slots, None on a non-root node
+            vals = np.array(list(map(operator.attrgetter(attr), nodes)), dtype=np.float64)      # None -> nan
+            root_val = vals[0]
+        vals[0] = floor if (root_val is None or not np.isfinite(root_val)) else root_val
         return np.maximum(floor, vals)
+
+    def _node_dicts(self, nodes):
+        """The nodes' instance dicts, cached per flattening (the per-pass scans read attributes from them at C speed)."""
+        cached = getattr(self, '_dicts_of', None)
+        if cached is None or cached[0] is not nodes:
+            cached = self._dicts_of = (nodes, [n.__dict__ for n in nodes])
+        return cached[1]
 
     def _has_masks(self):
         return any(getattr(n, 'mask', None) is not None for n in self.tree.find_clades())
@@ -228,8 +258,9 @@ class DeviceMarginalMixin(object):
     def _sync_masks(self, eng, topo):
         """Per-branch masks (node.mask, set by arg.py:128-133): distinct 0/1 vectors over the patterns + one index per
         node.  Fractional masks have no device form (a masked message is dropped, not scaled)."""
-        node_masks = [n.__dict__.get('mask') for n in topo.nodes]      # instance attribute on both clade classes
-        if set(map(id, node_masks)) == {id(None)}:
+        from itertools import repeat
+        node_masks = list(map(dict.get, self._node_dicts(topo.nodes), repeat('mask')))   # instance attribute on both clade classes
+        if not any(map(operator.is_not, node_masks, repeat(None))):      # identity, not ==: masks are arrays
             if self._device_masks is not None:
                 eng.set_branch_masks(None, None)
                 self._device_masks = None
@@ -290,6 +321,22 @@ class DeviceMarginalMixin(object):
                 idx = self._gather_patterns(self._engine.seq_idx([k])[0], axis=0)
                 self._seq_cache[k] = self.gtr.alphabet[idx]
         return self._seq_cache[k]
+
+    def sequence_differences(self):
+        """Every reconstructed internal sequence in sparse form: (root state indices [L'], node, pos, state) with one
+        entry per (internal node, compressed position) whose state differs from the parent's, sorted by (node, pos);
+        `node` indexes tree.find_clades() order.  This is what `node.mutations` enumerates (treeanc.py:27-42), for the
+        whole tree in one device call instead of one dense sequence per node."""
+        if not self.sequence_reconstruction:
+            raise ValueError('Ancestral sequences are not yet inferred')
+        root, node, pos, state = self._engine.mutations()
+        if self.comm.world_size > 1:
+            lo, _ = self._shard()
+            root = self.comm.allgather(root, axis=0)
+            node, pos, state = (self.comm.allgather(x, axis=0) for x in (node, pos + lo, state))
+            order = np.lexsort((pos, node))
+            node, pos, state = node[order], pos[order], state[order]
+        return root, node, pos, state
 
     # -- ancestral reconstruction ---------------------------------------------------------
     def _ml_anc_marginal(self, sample_from_profile=False, reconstruct_tip_states=False, debug=False, **kwargs):

@@ -55,11 +55,23 @@ class TorchComm(object):
         return t.cpu().numpy()
 
     def allgather(self, x, axis=0):
-        """Concatenate per-rank arrays (possibly of different length along `axis`)."""
-        x = np.ascontiguousarray(x)
-        parts = [None] * self.world_size
-        self.dist.all_gather_object(parts, x, group=self.group)
-        return np.concatenate(parts, axis=axis)
+        """Concatenate per-rank arrays (possibly of different length along `axis`): two tensor collectives -- the
+        per-rank lengths, then the data padded to the longest shard -- no pickling (the per-pattern likelihoods are
+        gathered every pass, the q^2 L' site statistics per GTR inference)."""
+        torch = self.torch
+        x = np.ascontiguousarray(np.moveaxis(np.asarray(x), axis, 0))
+        n = torch.tensor([x.shape[0]], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world_size)]
+        self.dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(s.item()) for s in sizes]
+        width = max(sizes)
+        t = torch.zeros((width,) + x.shape[1:], dtype=torch.from_numpy(x[:0]).dtype, device=self.device)
+        if x.shape[0]:
+            t[:x.shape[0]] = torch.from_numpy(x).to(self.device)
+        parts = [torch.empty_like(t) for _ in range(self.world_size)]
+        self.dist.all_gather(parts, t, group=self.group)
+        out = np.concatenate([p[:k].cpu().numpy() for p, k in zip(parts, sizes)], axis=0)
+        return np.moveaxis(out, 0, axis)
 
     def barrier(self):
         self.dist.barrier(group=self.group)

@@ -92,7 +92,7 @@ class TreeAnc(DeviceMarginalMixin):
     def __init__(self, tree=None, aln=None, gtr=None, fill_overhangs=True, ref=None, verbose=0, ignore_gaps=True,
                  convert_upper=True, seq_multiplicity=None, log=None, compress=True, seq_len=None,
                  ignore_missing_alns=False, keep_node_order=False, rng_seed=None,
-                 device=0, comm=None, engine_factory=None, device_compress=False, **kwargs):
+                 device=0, comm=None, engine_factory=None, device_compress=False, sparse_io=False, **kwargs):
         if tree is None:
             raise TypeError('TreeAnc requires a tree!')
         self.verbose = verbose
@@ -107,6 +107,7 @@ class TreeAnc(DeviceMarginalMixin):
         self.keep_node_order = keep_node_order
         self.rng = np.random.default_rng(seed=rng_seed)
         self._init_device(device=device, comm=comm, engine_factory=engine_factory)
+        self.sparse_io = bool(sparse_io)
         self._tree = None
         self.tree = tree
         self._gtr = None
