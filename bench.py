@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- marginal ancestral reconstruction throughput (branch x pattern updates/s).
+"""bench.py -- marginal ancestral reconstruction throughput (branch x pattern updates/s; log-LH rel err).
 
-    python bench.py [--gpus N --steps K --warmup W] [--workload cfg3|cfg2|cfg1|cfg4|tiny]
+    python bench.py [--gpus N --steps K --warmup W] [--workload cfg3|cfg2|cfg1|cfg4|cfg5|tiny] [--scaling auto|strong|weak]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...        # CPU arm: the oracle port of the reference's numpy path
+    python bench.py --impl reference ...   # CPU arm: the UNMODIFIED reference (oracle/_ref) on the host cores
 
-One step = one full `infer_ancestral_sequences(marginal=True)` pass (batched expQt, level-ordered
-postorder, root, level-ordered preorder, reductions) over one synthetic alignment shard.
-N > 1: one process per GPU, the tree/model replicated, every rank owns its own block of
-alignment columns (weak scaling: the per-GPU shard is fixed), the only collective is the
-all-reduce of {total log-LH, N_diff}.
+One step = one full `infer_ancestral_sequences(marginal=True)` pass (batched expQt, level-ordered postorder,
+root, level-ordered preorder, reductions) over one synthetic alignment.
 
-Prints ONE JSON line (rank 0).  `value` = updates/s with inputs resident in HBM, timed with CUDA
-events around the K steps (max over ranks); `e2e` = the same metric through the C-ABI with HOST
-buffers: per step the tip codes / branch lengths / model are copied host->device from pinned
-memory and the per-pattern LH, the totals and every reconstructed sequence are copied back.
+N = 1: BASELINE.json configs[2] (20k tips x 29,903 sites) on one GPU.
+N > 1: one process per GPU, tree/model replicated.  Default `--scaling strong`: ONE configs[2] alignment, the
+compressed patterns sharded over the ranks (dist.shard_bounds), the only collective is the all-reduce of
+{total log-LH, N_diff}; `updates_per_step` is constant in N.  The same run also measures the weak form (every rank
+a full-size alignment) as `weak_scaling`, and at N = 8 BASELINE.json configs[4] in full (100k tips x 30 kb,
+site-specific GTR, 8 shards of 3,750 sites) as `north_star_config`.
+
+Prints ONE JSON line (rank 0).  `value` = updates/s with inputs resident in HBM, CUDA events around the K steps, max
+over ranks.  `e2e` = the same metric through the product API (treetime_b200.TreeAnc, the mirror of treetime.TreeAnc):
+per step the alignment shard (sparse host form), model and branch lengths go host->device, the pass runs, and the
+per-pattern LH, the totals and every reconstructed sequence (sparse form) come back device->host.
+`parity` = the CPU oracle port (bit-identical to the reference on the build container) on a pattern slice of the same
+tree against the device's resident pass: log-LH relative error, max profile error, argmax mismatches off exact ties.
 """
 import argparse
 import json
@@ -33,23 +39,22 @@ WORKLOADS = {
     'cfg3': (20000, 29903, 'nuc', 1.0 / 29903, '20k tips x 29,903-site SARS-CoV-2-shaped nucleotide alignment (BASELINE.json configs[2])'),
     'cfg2': (2000, 10000, 'nuc', 5e-4, '2k tips x 10 kb nucleotide (BASELINE.json configs[1])'),
     'cfg1': (200, 1400, 'nuc', 2e-3, '200-tip x 1.4 kb nucleotide (BASELINE.json configs[0])'),
-    'cfg4': (5000, 1000, 'aa_nogap', 1e-2, '5k tips x 1,000-site amino-acid alignment, 20-state model (BASELINE.json configs[3])'),
+    'cfg4': (5000, 1000, 'aa_nogap', 1e-2, '5k tips x 1,000-site amino-acid alignment, JTT92 (20 states) (BASELINE.json configs[3])'),
     'cfg5': (100000, 3750, 'nuc_site_specific', 3.3e-5, '100k tips x 30 kb nucleotide with site-specific GTR, one of 8 pattern shards '
                                                        '(3,750 uncompressed sites per GPU) (BASELINE.json configs[4])'),
     'tiny': (64, 500, 'nuc', 1e-2, 'smoke-sized'),
 }
 SURVEY_BYTES_PER_UPDATE = {5: 165.5, 4: 133.5, 20: 645.5, 22: 709.5}    # 4 q s + 0.5 s + 1.5
+NUC_PI = np.array([0.3, 0.2, 0.2, 0.29, 0.01])
+METRIC = 'marginal ancestral reconstruction branch x pattern updates/s'
 
 
 def bind_to_gpu_numa_node(local_rank):
-    """Pin this rank's host threads (and so its first-touch pinned buffers) to the CPUs next to its GPU: with
-    several ranks the end-to-end leg is otherwise limited by cross-socket host traffic, not by PCIe."""
+    """Pin this rank's host threads (and so its first-touch pinned buffers) to the CPUs next to its GPU."""
     try:
         import torch
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
-        dom = getattr(torch.cuda.get_device_properties(local_rank), 'pci_domain_id', 0)
-        dev = getattr(torch.cuda.get_device_properties(local_rank), 'pci_device_id', 0)
-        path = '/sys/bus/pci/devices/%04x:%02x:%02x.0' % (dom, bus, dev)
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = '/sys/bus/pci/devices/%04x:%02x:%02x.0' % (getattr(pr, 'pci_domain_id', 0), pr.pci_bus_id, getattr(pr, 'pci_device_id', 0))
         node = int(open(path + '/numa_node').read())
         cpus = open(path + '/local_cpulist').read().strip()
         ids = set()
@@ -63,29 +68,66 @@ def bind_to_gpu_numa_node(local_rank):
         return {'error': str(e)[:80]}
 
 
-def make_workload(name, seed):
-    from treetime_b200 import synth
+def jtt92():
+    """(W, pi) of JTT92 as the unmodified reference builds it (aa_models.py), carried by the committed golden fixture."""
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'aa16_jtt92.npz'), allow_pickle=False)
+    return z['gtr_W'].copy(), z['gtr_Pi'].copy()
+
+
+def make_model(name, seed):
     from treetime_b200.gtr import GTR
     n_tips, L, alphabet, mean_bl, _ = WORKLOADS[name]
-    compress = True
     if alphabet == 'nuc':
-        gtr = GTR.custom(pi=np.array([0.3, 0.2, 0.2, 0.29, 0.01]), W=np.ones((5, 5)), alphabet='nuc')
-    elif alphabet == 'nuc_site_specific':
+        return GTR.custom(pi=NUC_PI.copy(), W=np.ones((5, 5)), alphabet='nuc'), True
+    if alphabet == 'nuc_site_specific':
         from treetime_b200.gtr import GTRSiteSpecific
-        gtr = GTRSiteSpecific.random(L=L, alphabet='nuc', rng=np.random.default_rng(1000 + seed))
-        compress = False          # treeanc.py:186-187: no pattern compression with site-specific models
-    else:
-        gtr = GTR.random(alphabet=alphabet, rng=np.random.default_rng(1234))
-    tree = synth.random_tree(n_tips, seed=1, mean_bl=mean_bl)           # same tree on every rank
-    topo, flat, g = synth.make_flat_problem(tree, gtr, L, seed, compress=compress)   # rank-specific columns
-    return topo, flat, g
+        # treeanc.py:186-187: no pattern compression with site-specific models
+        return GTRSiteSpecific.random(L=L, alphabet='nuc', rng=np.random.default_rng(1000 + seed)), False
+    W, pi = jtt92()
+    return GTR.custom(pi=pi, W=W, alphabet='aa_nogap'), True
+
+
+def make_inputs(name, seed):
+    """(tree, alignment as ASCII byte rows, model, compress): the same tree on every rank (seed 1), columns from `seed`."""
+    from treetime_b200 import synth
+    n_tips, L, alphabet, mean_bl, _ = WORKLOADS[name]
+    gtr, compress = make_model(name, seed)
+    tree = synth.random_tree(n_tips, seed=1, mean_bl=mean_bl)
+    Pi = gtr.Pi if np.ndim(gtr.Pi) == 1 else gtr.Pi.mean(axis=1)
+    idx = synth.evolve_alignment(tree, L, Pi, gtr.W, mu=1.0, seed=seed)
+    ab = np.asarray(gtr.alphabet).astype('S1').view(np.uint8)
+    return tree, {k: ab[v] for k, v in idx.items()}, gtr, compress
+
+
+def make_workload(name, seed):
+    """Flat arrays of the whole problem (what crosses the C-ABI and what the CPU oracle consumes)."""
+    from treetime_b200 import synth
+    from treetime_b200.sequence_data import SequenceData
+    tree, aln, gtr, compress = make_inputs(name, seed)
+    sd = SequenceData(aln, compress=compress, ambiguous=gtr.ambiguous)
+    return synth.flat_problem(tree, sd, gtr)
+
+
+def shard_problem(tt):
+    """Flat arrays of exactly what this rank's engine holds (its pattern shard), taken from the TreeAnc itself."""
+    from treetime_b200.flatten import gtr_arrays
+    topo = tt._flat()
+    lo, hi = tt._shard()
+    codes, table = tt._tip_codes()
+    flat = topo.as_dict()
+    flat.update(tip_codes=codes, code_profiles=table, multiplicity=np.ascontiguousarray(tt.data.multiplicity()[lo:hi], dtype=np.float64),
+                t=np.array(tt._t_last))
+    g = gtr_arrays(tt.gtr)
+    if g['site_specific']:
+        g = dict(g, eigenvals=g['eigenvals'][:, lo:hi], v=g['v'][:, :, lo:hi], v_inv=g['v_inv'][:, :, lo:hi], Pi=g['Pi'][:, lo:hi], mu=g['mu'][lo:hi])
+    return flat, g
 
 
 def algorithmic_bytes(flat, q):
-    """Bytes the level kernels must move per pass under THIS design (DESIGN.md §Kernels):
-    postorder: read S of internal children + 1-byte codes of tip children, write S per internal
-    node (the log-prefactors are summed per block run, not stored per node); preorder: read parent profile once per parent with an internal child, per
-    internal child read S, write profile, read+write the 1-byte state."""
+    """Bytes the level kernels must move per pass under THIS design (DESIGN.md §4):
+    postorder: read S of internal children + 1-byte codes of tip children, write S per internal node (the log-prefactors
+    are summed per block run, not stored per node); preorder: read the parent profile once per parent with an internal
+    child, per internal child read S, write the profile, read + write the 1-byte state."""
     Lp = flat['multiplicity'].shape[0]
     n_nodes = flat['parent'].shape[0]
     tip = flat['tip_row'] >= 0
@@ -175,25 +217,197 @@ def cpu_sample(flat, g, n_patterns):
     return s, n, g
 
 
-def run_cpu(flat, g, n_patterns, repeats):
-    """Time the oracle port (oracle/flat_numpy.py: the reference's per-node numpy calls)."""
+def tie_mask(profile, rel=1e-12):
+    """True where the two largest entries of a profile row are closer than `rel`: the argmax is an exact tie."""
+    s = np.sort(profile, axis=1)
+    return (s[:, -1] - s[:, -2]) <= rel * s[:, -1]
+
+
+def parity_against_port(eng, flat, g, n_patterns, max_profile_nodes=4000):
+    """The CPU oracle port (oracle/flat_numpy.py: the reference's per-node numpy calls, checker only) on the first
+    n_patterns patterns of this shard against the device's resident pass: BASELINE.md §3 / the metric's second half.
+    Returns (parity dict, cpu seconds, updates of the sample)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import flat_numpy as O
-    s, n, g = cpu_sample(flat, g, n_patterns)
+    s, n, gs = cpu_sample(flat, g, n_patterns)
+    t0 = time.perf_counter()
+    res = O.marginal(s, gs)
+    cpu_s = time.perf_counter() - t0
+    m = s['multiplicity']
+    lh = eng.site_lh()[:n]
+    tot_gpu = float((lh * m).sum())
+    internal = np.nonzero(flat['tip_row'] < 0)[0]
+    idx = eng.all_seq_idx()[:, :n]
+    mism = mism_off_ties = 0
+    for k, node in enumerate(internal):
+        bad = idx[k] != res.seq_idx[node]
+        if bad.any():
+            mism += int(bad.sum())
+            mism_off_ties += int((bad & ~tie_mask(res.profile[node])).sum())
+    sel = internal if internal.shape[0] <= max_profile_nodes else internal[np.linspace(0, internal.shape[0] - 1, max_profile_nodes).astype(int)]
+    perr = 0.0
+    for node in sel:
+        perr = max(perr, float(np.abs(eng.node_array(int(node), 2)[:n] - res.profile[node]).max()))
+    par = {'log_lh_rel_err': abs(tot_gpu - float(res.total_LH)) / abs(float(res.total_LH)),
+           'max_site_log_lh_rel_err': float(np.max(np.abs(lh - res.sequence_LH) / np.abs(res.sequence_LH))),
+           'max_profile_abs_err': perr, 'argmax_mismatch': mism, 'argmax_mismatch_off_ties': mism_off_ties,
+           'patterns_compared': int(n), 'internal_nodes_compared_sequences': int(internal.shape[0]),
+           'internal_nodes_compared_profiles': int(len(sel)),
+           'against': 'oracle/flat_numpy.py (CPU restatement of treeanc.py:762-932, bit-identical to the unmodified reference on the '
+                      'build container) on the first patterns of rank 0\'s shard, same tree / model / branch lengths',
+           'tolerances': {'log_lh_rel_err': 1e-9, 'max_profile_abs_err': 1e-6, 'argmax_mismatch_off_ties': 0}}
     n_br = flat['parent'].shape[0] - 1
-    times = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        res = O.marginal(s, g)
-        times.append(time.perf_counter() - t0)
-    return n_br * n, times, res.total_LH
+    return par, cpu_s, n_br * n
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _reference_worker(k, spec, bar, n_steps, out_q):
+    """One host core: the UNMODIFIED reference's TreeAnc on its own slice of the alignment columns."""
+    try:
+        import threadpoolctl
+        _lim = threadpoolctl.threadpool_limits(1)      # noqa: F841
+    except Exception:
+        pass
+    try:
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import refenv
+        refenv.activate()
+        from io import StringIO
+        from Bio import Phylo
+        from Bio.Align import MultipleSeqAlignment
+        from Bio.SeqRecord import SeqRecord
+        from Bio.Seq import Seq
+        from treetime import TreeAnc, GTR as RG
+        lo, hi = spec['bounds'][k]
+        names, chars = spec['names'], spec['chars']
+        aln = MultipleSeqAlignment([SeqRecord(Seq(chars[i, lo:hi].tobytes().decode('ascii')), id=nm, name=nm, description='')
+                                    for i, nm in enumerate(names)])
+        kind = spec['model']['kind']
+        if kind == 'single':
+            gtr = RG.custom(pi=spec['model']['pi'].copy(), W=spec['model']['W'].copy(), alphabet=spec['model']['alphabet'])
+        else:
+            from treetime.gtr_site_specific import GTR_site_specific
+            gtr = GTR_site_specific.custom(mu=spec['model']['mu'][lo:hi].copy(), pi=spec['model']['pi'][:, lo:hi].copy(),
+                                           W=spec['model']['W'].copy(), alphabet=spec['model']['alphabet'])
+        tt = TreeAnc(tree=Phylo.read(StringIO(spec['newick']), 'newick'), aln=aln, gtr=gtr, compress=False, verbose=0)
+        lh = None
+        bar.wait()                                    # set-up done everywhere
+        for _ in range(n_steps):
+            bar.wait()
+            tt.infer_ancestral_sequences(marginal=True)      # the reference's own public call, stock code path
+            lh = float(tt.sequence_LH())
+            bar.wait()
+        out_q.put((k, lh, None))
+    except Exception as e:       # never leave the others waiting on the barrier
+        try:
+            bar.abort()
+        except Exception:
+            pass
+        out_q.put((k, None, repr(e)))
+
+
+def run_reference_arm(args, real_stdout):
+    """`--impl reference`: the unmodified reference (oracle/_ref; /root/reference in the build container) through its
+    own TreeAnc.infer_ancestral_sequences(marginal=True), one process per host core on disjoint column slices of the
+    same workload (the reference is single-threaded numpy; patterns are independent), each step a bounded sample."""
+    import multiprocessing as mp
+    n_tips, L, alphabet, mean_bl, desc = WORKLOADS[args.workload]
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import refenv
+    total_steps = args.steps + args.warmup
+    workers = max(1, min(os.cpu_count() or 1, args.cpu_workers or 64))
+    have_ref = refenv.available()
+    from treetime_b200 import synth
+    from treetime_b200.sequence_data import SequenceData
+    tree, aln, gtr, compress = make_inputs(args.workload, 1)
+    topo, flat, g = synth.flat_problem(tree, SequenceData(aln, compress=compress, ambiguous=gtr.ambiguous), gtr)   # ladderizes `tree`
+    q = g['Pi'].shape[0]
+    n_br = flat['parent'].shape[0] - 1
+    Lp = flat['multiplicity'].shape[0]
+    # ~2.4e6 updates/s per core for the reference, ~4.4e6 for the port: aim at ~120 s for the whole run
+    rate = 2.0e6 if have_ref else 4.0e6
+    per_worker = args.cpu_patterns or int(max(32, min(Lp // workers, 120.0 * rate / (n_br * max(1, total_steps)))))
+    try:
+        import psutil
+        per_pattern = 8.0 * flat['parent'].shape[0] * q * 8          # bytes one pattern costs a worker (per-node arrays)
+        budget = 0.5 * psutil.virtual_memory().available
+        per_worker = int(min(per_worker, max(32, budget // (workers * per_pattern))))
+    except Exception:
+        pass
+    per_worker = max(1, min(per_worker, Lp // workers))
+    bounds = [(k * per_worker, (k + 1) * per_worker) for k in range(workers)]
+    updates = n_br * per_worker * workers
+    if have_ref:
+        from treetime_b200.flatten import code_table
+        chars, _, _ = code_table(gtr.profile_map, gtr.n_states)
+        code2char = np.frombuffer((''.join(chars) + (gtr.ambiguous or 'N')).encode('ascii'), dtype=np.uint8)
+        names = [topo.nodes[n].name for n in topo.tip_nodes]
+        model = ({'kind': 'single', 'pi': np.array(gtr.Pi), 'W': np.array(gtr.W), 'alphabet': 'nuc' if alphabet == 'nuc' else 'aa_nogap'}
+                 if np.ndim(gtr.Pi) == 1 else
+                 {'kind': 'site_specific', 'pi': np.array(gtr.Pi), 'W': np.array(gtr.W), 'mu': np.array(gtr.mu), 'alphabet': 'nuc'})
+        spec = {'bounds': bounds, 'names': names, 'chars': code2char[flat['tip_codes'][:, :per_worker * workers]],
+                'newick': tree.to_newick(), 'model': model}
+        ctx = mp.get_context('fork')
+        bar = ctx.Barrier(workers + 1)
+        out_q = ctx.Queue()
+        procs = [ctx.Process(target=_reference_worker, args=(k, spec, bar, total_steps, out_q)) for k in range(workers)]
+        for p in procs:
+            p.start()
+        times, err = [], None
+        try:
+            bar.wait(timeout=900)
+            for _ in range(total_steps):
+                bar.wait(timeout=900)
+                t0 = time.perf_counter()
+                bar.wait(timeout=1800)
+                times.append(time.perf_counter() - t0)
+        except Exception as e:
+            err = repr(e)
+        res = []
+        for _ in procs:
+            try:
+                res.append(out_q.get(timeout=60 if err is None else 5))
+            except Exception:
+                break
+        for p in procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.terminate()
+        bad = [r for r in res if r[2]]
+        if err or bad or len(times) < total_steps:
+            have_ref = False
+            sys.stderr.write('reference arm fell back to the port: %s %s\n' % (err, bad[:1]))
+        else:
+            kind = 'reference'
+            sample = ('%d processes (one per host core), each the unmodified treetime.TreeAnc(compress=False).infer_ancestral_sequences('
+                      'marginal=True) over its own %d of the %d compressed patterns of the same tree/alignment per step (cost is linear in '
+                      'patterns)' % (workers, per_worker, Lp))
+            note = ('treetime 0.12.1 from %s, Biopython replaced by oracle/bioshim (container stubs, no numerics)'
+                    % ('oracle/_ref (pip-installed copy)' if refenv.is_staged_copy() else refenv.REFERENCE))
+    if not have_ref:
+        updates, times, per_worker = run_port_parallel(flat, g, per_worker, workers, total_steps)
+        kind = 'port'
+        sample = ('%d processes (one per core), each one pass of the oracle port over its own %d of %d compressed patterns of the same '
+                  'tree/alignment per step' % (workers, per_worker, Lp))
+        note = 'oracle/flat_numpy.py: flat-array port of the reference numpy path (the reference itself is not staged: python oracle/stage_ref.py)'
+    timed = times[args.warmup:]
+    ms = 1e3 * float(np.mean(timed))
+    val = updates / (ms / 1e3)
+    _emit(real_stdout, {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'updates/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak' if args.gpus == 1 else args.scaling_resolved,
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': '%s: %s' % (args.workload, desc), 'n_tips': n_tips, 'n_sites': L, 'n_states': q},
+        'cpu_baseline': {'value': val, 'unit': 'updates/s', 'cores': workers, 'kind': kind, 'sample': sample},
+        'e2e': {'value': val, 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': note})
+    return 0
 
 
 _POOL_STATE = {}
 
 
-def _cpu_worker_init(flat, g):
-    """Worker of the multi-process CPU arm: one pattern slice per process, numpy pinned to one thread."""
+def _port_worker_init(flat, g):
     try:
         import threadpoolctl
         _POOL_STATE['limit'] = threadpoolctl.threadpool_limits(1)
@@ -203,7 +417,7 @@ def _cpu_worker_init(flat, g):
     _POOL_STATE['flat'], _POOL_STATE['g'] = flat, g
 
 
-def _cpu_worker_run(bounds):
+def _port_worker_run(bounds):
     import flat_numpy as O
     lo, hi = bounds
     flat, g = _POOL_STATE['flat'], _POOL_STATE['g']
@@ -216,19 +430,18 @@ def _cpu_worker_run(bounds):
     return float(O.marginal(s, g).total_LH)
 
 
-def run_cpu_parallel(flat, g, per_worker, workers, repeats):
-    """The reference path is single-threaded numpy; patterns are independent, so the strongest CPU arm this host
-    offers is one process per core, each running the oracle port on its own slice of the pattern axis."""
+def run_port_parallel(flat, g, per_worker, workers, repeats):
+    """Fallback of the reference arm when the reference is not staged: the oracle port, one process per core."""
     import multiprocessing as mp
     Lp = flat['multiplicity'].shape[0]
     per_worker = max(1, min(per_worker, Lp // workers))
     bounds = [(k * per_worker, (k + 1) * per_worker) for k in range(workers)]
     n_br = flat['parent'].shape[0] - 1
     times = []
-    with mp.get_context('fork').Pool(workers, initializer=_cpu_worker_init, initargs=(flat, g)) as pool:
+    with mp.get_context('fork').Pool(workers, initializer=_port_worker_init, initargs=(flat, g)) as pool:
         for _ in range(repeats):
             t0 = time.perf_counter()
-            pool.map(_cpu_worker_run, bounds, chunksize=1)
+            pool.map(_port_worker_run, bounds, chunksize=1)
             times.append(time.perf_counter() - t0)
     return n_br * per_worker * workers, times, per_worker
 
@@ -246,6 +459,220 @@ def _emit(real_stdout_fd, obj):
     os.write(real_stdout_fd, (json.dumps(obj) + '\n').encode())
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm
+class _Dev(object):
+    def __init__(self, ptr):
+        self.__cuda_array_interface__ = {'shape': (2,), 'typestr': '<f8', 'data': (ptr, False), 'version': 2}
+
+
+class Leg(object):
+    """One measured configuration: a TreeAnc (product API) whose engine also runs the resident timing."""
+
+    def __init__(self, name, seed, comm, local_rank, stream):
+        from treetime_b200.treeanc import TreeAnc
+        self.name = name
+        tree, aln, gtr, compress = make_inputs(name, seed)
+        self.tt = TreeAnc(tree=tree, aln=aln, gtr=gtr, compress=compress, device=local_rank, comm=comm, sparse_io=True, rng_seed=1)
+        self.stream = stream
+        self.q = int(gtr.n_states)
+
+    def prepare(self, comm):
+        """(Re-)shard for `comm` and run the first pass (uploads, allocations, graph capture)."""
+        tt = self.tt
+        tt.comm = comm
+        tt.reload_alignment()
+        tt.infer_ancestral_sequences(marginal=True)
+        self.eng = tt._engine
+        self.eng.set_stream(self.stream.cuda_stream)
+        self.eng.marginal()
+        self.eng.sync()
+        self.flat, self.g = shard_problem(tt)
+        self.n_br = self.flat['parent'].shape[0] - 1
+        self.Lp = self.flat['multiplicity'].shape[0]
+        self.updates_local = self.n_br * self.Lp
+
+
+def timed_resident(leg, steps, warmup, world, local_rank, sample_clocks=True):
+    """K graph replays (+ the all-reduce of {LH, N_diff} when world > 1) between CUDA events on the engine's stream."""
+    import torch
+    import torch.distributed as dist
+    eng, stream = leg.eng, leg.stream
+    res_t = torch.as_tensor(_Dev(eng.results_device_ptr()), device='cuda') if world > 1 else None
+
+    def step():
+        eng.marginal()
+        if world > 1:
+            dist.all_reduce(res_t)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    if sample_clocks:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sample_clocks else None
+    launches = eng.launch_count() - launches0
+    lh_local = eng.results()[0]           # copied to the host before the all-reduce touched the device buffer
+    lh_global = float(res_t[0].item()) if world > 1 else lh_local
+    return ms_total / steps, launches, clocks, lh_global, lh_local, barrier
+
+
+def timed_api_e2e(leg, k, barrier):
+    """The product API with host buffers, per step: alignment shard (sparse host form) + model + branch lengths H2D,
+    infer_ancestral_sequences(marginal=True), per-pattern LH + totals + every reconstructed sequence (sparse) D2H."""
+    tt = leg.tt
+
+    def step():
+        tt.reload_alignment()                                   # this step's input comes from the host again
+        tt.infer_ancestral_sequences(marginal=True)             # ... LH per pattern and totals land on the host
+        return tt.sequence_differences(gather=False)            # ... and so does every internal sequence (sparse form)
+
+    step()
+    step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        root, node, pos, state = step()
+    barrier()
+    sec = (time.perf_counter() - t0) / k
+    _, (ref, e_row, e_pos, e_code), table, mult = tt._sparse_codes
+    q = leg.q
+    model_bytes = sum(np.asarray(v).nbytes for v in (leg.g['eigenvals'], leg.g['v'], leg.g['v_inv'], leg.g['Pi'])) + 8 * np.size(leg.g['mu'])
+    if leg.g.get('site_specific'):
+        model_bytes = 0          # the per-pattern model is re-uploaded only when it changed (fingerprint), like the reference keeps its gtr
+    h2d = int(ref.nbytes + e_row.nbytes + e_pos.nbytes + e_code.nbytes + table.nbytes + mult.nbytes + leg.flat['t'].nbytes + model_bytes)
+    d2h = int(8 * leg.Lp + 32 + root.nbytes + node.nbytes + pos.nbytes + state.nbytes)
+    return sec, h2d, d2h, float(tt.tree.total_sequence_LH), int(node.shape[0]), int(e_row.shape[0])
+
+
+def dense_cabi_e2e(leg, k, nblk_max, local_rank, barrier):
+    """C-ABI with DENSE host buffers (N = 1 only): per step the full tip-code matrix goes host->device from pinned memory
+    and every reconstructed sequence comes back dense; the pattern axis is cut into column blocks with their own
+    handles / streams so that the copies of one block overlap the pass of another."""
+    import torch
+    from treetime_b200.engine import Engine
+    flat, g, q, Lp = leg.flat, leg.g, leg.q, leg.Lp
+    n_int = int((flat['tip_row'] < 0).sum())
+    nblk = max(1, min(nblk_max, Lp // 1024))
+    bounds = [(Lp * i) // nblk for i in range(nblk + 1)]
+    shards = []
+    for i in range(nblk):
+        lo, hi = bounds[i], bounds[i + 1]
+        e = Engine(q, device=local_rank)
+        st_i = torch.cuda.Stream()
+        e.set_stream(st_i.cuda_stream)
+        e.set_tree(flat['parent'], flat['child_ptr'], flat['child_idx'], flat['tip_row'])
+        cp = torch.empty((flat['tip_codes'].shape[0], hi - lo), dtype=torch.uint8, pin_memory=True)
+        cp.numpy()[...] = flat['tip_codes'][:, lo:hi]
+        sp = torch.empty((n_int, hi - lo), dtype=torch.uint8, pin_memory=True)
+        lp = torch.empty(hi - lo, dtype=torch.float64, pin_memory=True)
+        shards.append((e, cp.numpy(), sp.numpy(), lp.numpy(), np.ascontiguousarray(flat['multiplicity'][lo:hi]), st_i, cp, sp, lp))
+
+    def step():
+        up_done = pass_done = None
+        for e, cp, sp, lp, m, st_i, *_ in shards:
+            if up_done is not None:
+                st_i.wait_event(up_done)
+            e.set_patterns(cp, flat['code_profiles'], m, validate=False)
+            e.set_gtr(g)
+            e.set_branch_lengths(flat['t'])
+            up_done = torch.cuda.Event()
+            up_done.record(st_i)
+            if pass_done is not None:
+                st_i.wait_event(pass_done)
+            e.marginal()
+            pass_done = torch.cuda.Event()
+            pass_done.record(st_i)
+            e.enqueue_site_lh(lp)
+            e.enqueue_all_seq_idx(sp)
+        return sum(e.results()[0] for e, *_ in shards)
+
+    step()
+    step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        tot = step()
+    barrier()
+    sec = (time.perf_counter() - t0) / k
+    h2d = int(flat['tip_codes'].nbytes + nblk * (flat['code_profiles'].nbytes + flat['t'].nbytes + 8 * (2 * q * q + 2 * q + 1)) + flat['multiplicity'].nbytes)
+    d2h = int(n_int * Lp + 8 * Lp + 16 * nblk)
+    for sh in shards:
+        sh[0].close()
+    del shards
+    torch.cuda.empty_cache()
+    return sec, h2d, d2h, nblk, tot
+
+
+def pcie_probe():
+    import torch
+    pb = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    db = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    pe0, pe1, pe2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    db.copy_(pb, non_blocking=True); torch.cuda.synchronize()
+    pe0.record(); db.copy_(pb, non_blocking=True); pe1.record(); pb.copy_(db, non_blocking=True); pe2.record()
+    torch.cuda.synchronize()
+    return {'h2d': 0.268435456 / (pe0.elapsed_time(pe1) / 1e3), 'd2h': 0.268435456 / (pe1.elapsed_time(pe2) / 1e3)}
+
+
+def reduce_max_sum(world, maxes, sums):
+    if world == 1:
+        return [float(x) for x in maxes], [float(x) for x in sums]
+    import torch
+    import torch.distributed as dist
+    a = torch.tensor(maxes, device='cuda', dtype=torch.float64)
+    b = torch.tensor(sums, device='cuda', dtype=torch.float64)
+    dist.all_reduce(a, op=dist.ReduceOp.MAX)
+    dist.all_reduce(b)
+    return a.tolist(), b.tolist()
+
+
+def phase_profile(eng):
+    phases = eng.profile_marginal()
+    for _ in range(2):
+        ph = eng.profile_marginal()
+        phases = {k: (min(phases[k][0], ph[k][0]), ph[k][1]) for k in ph}
+    return phases
+
+
+def roofline_block(leg, phases, pass_ms, workload):
+    peak, peak_src = measured_peak()
+    q = leg.q
+    post_b, pre_b = algorithmic_bytes(leg.flat, q)
+    dom = 'preorder' if phases['preorder'][0] >= phases['postorder'][0] else 'postorder'
+    dom_bytes = pre_b if dom == 'preorder' else post_b
+    dom_ms, dom_launches = phases[dom]
+    achieved = dom_bytes / (dom_ms / 1e3) / 1e9
+    return {
+        'bound': 'hbm', 'kernel': '%s_level_kernel<%d> (%d level launches per pass)' % ('pre' if dom == 'preorder' else 'post', q, dom_launches),
+        'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
+        'peak_note': 'peak is a measured COPY bandwidth (1:1 read:write); the preorder kernel streams 2:1 read:write and can sit at or slightly above it',
+        'algorithmic_bytes_per_pass': int(dom_bytes), 'kernel_ms_per_pass': dom_ms,
+        'traffic': ncu_traffic(workload, 'pre_level_kernel' if dom == 'preorder' else 'post_level_kernel'),
+        'phases_ms': {k: v[0] for k, v in phases.items()}, 'phase_launches': {k: v[1] for k, v in phases.items()},
+        'whole_pass': {'algorithmic_bytes': int(post_b + pre_b), 'bytes_per_update': (post_b + pre_b) / float(leg.updates_local),
+                       'achieved_gbs': (post_b + pre_b) / (pass_ms / 1e3) / 1e9, 'frac': (post_b + pre_b) / (pass_ms / 1e3) / 1e9 / peak,
+                       'survey_bytes_per_update': SURVEY_BYTES_PER_UPDATE.get(q),
+                       'survey_frac': (SURVEY_BYTES_PER_UPDATE.get(q, 0) * leg.updates_local / (pass_ms / 1e3) / 1e9 / peak)
+                       if q in SURVEY_BYTES_PER_UPDATE else None}}
+
+
 def main():
     real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -254,11 +681,16 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
-    ap.add_argument('--cpu-patterns', type=int, default=0, help='patterns in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--scaling', default='auto', choices=['auto', 'strong', 'weak'],
+                    help='N > 1: strong = one alignment, patterns sharded over the ranks (default); weak = one full-size alignment per rank')
+    ap.add_argument('--cpu-patterns', type=int, default=0, help='patterns in the CPU sample (0 = auto)')
     ap.add_argument('--cpu-workers', type=int, default=0, help='processes of the CPU (reference) arm (0 = one per core)')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU port (drops `parity` and `cpu_baseline`)')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--e2e-blocks', type=int, default=6, help='pattern blocks (engine handles / streams) of the e2e leg')
+    ap.add_argument('--no-dense-e2e', action='store_true', help='skip the dense C-ABI e2e leg (N = 1)')
+    ap.add_argument('--no-secondary', action='store_true', help='N > 1: skip the weak-scaling and north-star legs')
+    ap.add_argument('--north-star', action='store_true', help='run the configs[4] leg at any N (default: only at N = 8)')
+    ap.add_argument('--e2e-blocks', type=int, default=6, help='pattern blocks (engine handles / streams) of the dense C-ABI e2e leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 0)
 
@@ -266,318 +698,130 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     n_tips, L, alphabet, mean_bl, desc = WORKLOADS[args.workload]
+    site_specific = alphabet == 'nuc_site_specific'
+    mode = args.scaling
+    if mode == 'auto':
+        mode = 'strong' if (max(world, args.gpus) > 1 and not site_specific) else 'weak'
+    if site_specific and mode == 'strong':
+        mode = 'weak'        # the workload already IS one pattern shard per GPU of the 8-shard alignment
+    args.scaling_resolved = mode
 
-    # ------------------------------------------------------------------ CPU (reference) arm
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        topo, flat, g = make_workload(args.workload, seed=1)
-        q = g['Pi'].shape[0]
-        n_br = flat['parent'].shape[0] - 1
-        total_steps = args.steps + args.warmup
-        n_pat = args.cpu_patterns or int(max(64, min(flat['multiplicity'].shape[0], 120.0 * 2.0e6 / (n_br * max(1, total_steps)))))
-        # one process per host core, bounded by memory: the port keeps ~6 (n_nodes, patterns, q) fp64 arrays per slice
-        workers = max(1, min(os.cpu_count() or 1, args.cpu_workers or 64))
-        per_worker = max(64, min(n_pat, flat['multiplicity'].shape[0] // workers))
-        try:
-            import psutil
-            per_pattern = 6.0 * flat['parent'].shape[0] * q * 8          # bytes one pattern costs a worker
-            budget = 0.5 * psutil.virtual_memory().available
-            per_worker = int(min(per_worker, max(64, budget // (workers * per_pattern))))
-            workers = int(max(1, min(workers, budget // (per_worker * per_pattern))))
-        except Exception:
-            pass
-        if workers > 1:
-            updates, times, per_worker = run_cpu_parallel(flat, g, per_worker, workers, total_steps)
-            sample = ('%d processes (one per core), each one pass over its own %d of %d compressed patterns of the same '
-                      'tree/alignment per step (cost is linear in patterns)' % (workers, per_worker, flat['multiplicity'].shape[0]))
-        else:
-            updates, times, _ = run_cpu(flat, g, n_pat, total_steps)
-            sample = 'first %d of %d compressed patterns of the same tree/alignment per step (cost is linear in patterns)' % (
-                min(n_pat, flat['multiplicity'].shape[0]), flat['multiplicity'].shape[0])
-        timed = times[args.warmup:]
-        ms = 1e3 * float(np.mean(timed))
-        val = updates / (ms / 1e3)
-        _emit(real_stdout, {
-            'impl': 'reference', 'metric': 'marginal ancestral reconstruction branch x pattern updates/s', 'value': val,
-            'unit': 'updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '%s: %s' % (args.workload, desc), 'n_tips': n_tips, 'n_sites': L, 'n_states': q},
-            'cpu_baseline': {'value': val, 'unit': 'updates/s', 'cores': workers, 'kind': 'port', 'sample': sample},
-            'e2e': {'value': val, 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'note': 'oracle/flat_numpy.py: flat-array port of the reference numpy path (bit-identical to the '
-                    'reference on the build container).  The reference itself is single-threaded; patterns are '
-                    'independent, so this arm runs one process per host core on disjoint pattern slices',
-        })
-        return 0
+        return run_reference_arm(args, real_stdout)
 
-    # ------------------------------------------------------------------ GPU arm
     import torch
     import torch.distributed as dist
-    from treetime_b200.engine import Engine
+    from treetime_b200.dist import SingleComm, TorchComm
 
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    topo, flat, g = make_workload(args.workload, seed=1 + rank)
-    q = g['Pi'].shape[0]
-    n_nodes = flat['parent'].shape[0]
-    n_br = n_nodes - 1
-    Lp = flat['multiplicity'].shape[0]
-    updates_local = n_br * Lp
-
     stream = torch.cuda.Stream()          # a real (non-default) stream: events on it bracket the engine's work
     torch.cuda.set_stream(stream)
-    eng = Engine(q, device=local_rank)
-    eng.set_stream(stream.cuda_stream)
-    eng.set_tree(flat['parent'], flat['child_ptr'], flat['child_idx'], flat['tip_row'])
-    # pinned host staging for the e2e leg
-    codes_pin = torch.empty(flat['tip_codes'].shape, dtype=torch.uint8, pin_memory=True)
-    codes_pin.numpy()[...] = flat['tip_codes']
-    eng.set_patterns(codes_pin.numpy(), flat['code_profiles'], flat['multiplicity'])
-    eng.set_gtr(g)
-    eng.set_branch_lengths(flat['t'])
+    k_e2e = max(3, min(args.steps, 10))
 
-    class _Dev(object):
-        def __init__(self, ptr):
-            self.__cuda_array_interface__ = {'shape': (2,), 'typestr': '<f8', 'data': (ptr, False), 'version': 2}
+    def measure(leg, comm, sharded, with_parity, with_dense, workload_name):
+        """All numbers of one leg; reductions over ranks inside.  Returns a dict (complete on rank 0)."""
+        leg.prepare(comm)
+        ms_local, launches, clocks, lh_global, lh_local, barrier = timed_resident(leg, args.steps, args.warmup, world, local_rank)
+        phases = phase_profile(leg.eng)
+        api = None
+        if not args.no_e2e:
+            api = timed_api_e2e(leg, k_e2e, barrier)
+        dense = None
+        if with_dense and not args.no_e2e and not args.no_dense_e2e:
+            dense = dense_cabi_e2e(leg, k_e2e, args.e2e_blocks, local_rank, barrier)
+        (ms_step, e2e_s, dense_s), (updates_total, h2d_tot, d2h_tot) = reduce_max_sum(
+            world, [ms_local, api[0] if api else 0.0, dense[0] if dense else 0.0],
+            [float(leg.updates_local), float(api[1]) if api else 0.0, float(api[2]) if api else 0.0])
+        out = {'ms_per_step': ms_step, 'value': updates_total / (ms_step / 1e3), 'updates_per_step': updates_total,
+               'patterns_rank0': int(leg.Lp), 'branches': int(leg.n_br), 'gpu_launches': int(launches), 'clocks': clocks,
+               'log_lh': lh_global, 'device_bytes_rank0': leg.eng.device_bytes()}
+        if rank == 0:
+            out['roofline'] = roofline_block(leg, phases, ms_step, workload_name)
+        if api:
+            # the API's total is all-reduced by the TreeAnc's communicator when the patterns are sharded; the resident total
+            # was all-reduced by the bench: global vs global (sharded) or local vs local (independent alignments)
+            lh_api = api[3]
+            lh_ref = lh_global if sharded else lh_local
+            out['e2e'] = {'value': updates_total / e2e_s, 'unit': 'updates/s', 'ms_per_step': 1e3 * e2e_s,
+                          'h2d_bytes_per_step': int(h2d_tot), 'd2h_bytes_per_step': int(d2h_tot), 'api': 'TreeAnc',
+                          'rel_lh_diff_vs_resident_pass': abs(lh_api - lh_ref) / abs(lh_ref),
+                          'alignment_differences_rank0': api[5], 'mutations_returned_rank0': api[4], 'host_binding': numa,
+                          'what': 'per step through treetime_b200.TreeAnc (mirror of treetime.TreeAnc) with sparse_io: reload_alignment() '
+                                  '[tip codes as reference row + differences, host -> device], infer_ancestral_sequences(marginal=True) '
+                                  '[branch lengths + model up; tree.sequence_LH, total LH, N_diff down], sequence_differences() [every '
+                                  'reconstructed sequence as root row + states differing from the parent, device -> host]; host wall clock, '
+                                  'barrier + synchronize on both sides, max over ranks'}
+        if dense:
+            out['e2e_cabi_dense'] = {'value': updates_total / dense_s, 'unit': 'updates/s', 'ms_per_step': 1e3 * dense_s,
+                                     'h2d_bytes_per_step': dense[1], 'd2h_bytes_per_step': dense[2], 'pattern_blocks': dense[3],
+                                     'rel_lh_diff_vs_resident_pass': abs(dense[4] - lh_global) / abs(lh_global), 'pcie_probe_gbs': pcie_probe(),
+                                     'what': 'C-ABI with dense host buffers: ttb_set_patterns (full tip-code matrix from pinned memory) / gtr / '
+                                             'branch lengths, ttb_marginal, ttb_enqueue_fetch_site_lh + ttb_enqueue_fetch_all_seq_idx (every '
+                                             'sequence dense) per pattern block on its own stream'}
+        if with_parity and rank == 0 and not args.no_cpu_baseline:
+            n_pat = args.cpu_patterns or int(max(48, min(leg.Lp, 20.0 * 2.0e6 / leg.n_br)))
+            par, cpu_s, upd = parity_against_port(leg.eng, leg.flat, leg.g, n_pat)
+            out['parity'] = par
+            out['cpu_baseline'] = {'value': upd / cpu_s, 'unit': 'updates/s', 'cores': 1, 'kind': 'port',
+                                   'sample': 'one pass of oracle/flat_numpy.py over the first %d of %d patterns (same tree, same model); host has %d '
+                                             'cores, the reference path is single-threaded numpy; `--impl reference` times the unmodified reference on '
+                                             'all cores' % (par['patterns_compared'], leg.Lp, os.cpu_count() or 0)}
+        return out
 
-    def step():
-        eng.marginal()
-        if world > 1:
-            dist.all_reduce(res_t)
+    sharded = world > 1 and mode == 'strong'
+    primary_comm = TorchComm() if sharded else SingleComm()
+    leg = Leg(args.workload, 1 if (sharded or world == 1) else 1 + rank, primary_comm, local_rank, stream)
+    res = measure(leg, primary_comm, sharded, True, world == 1, args.workload)
 
-    eng.marginal()
-    eng.sync()
-    res_t = torch.as_tensor(_Dev(eng.results_device_ptr()), device='cuda') if world > 1 else None
+    weak = None
+    if world > 1 and mode == 'strong' and not args.no_secondary:
+        # the weak form on the same engines: every rank the full alignment (the same columns everywhere -- per-GPU work is what counts)
+        weak = measure(leg, SingleComm(), False, False, False, args.workload)
+    del leg
+    torch.cuda.empty_cache()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    launches0 = eng.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    launches = eng.launch_count() - launches0
-    total_lh_local, _ = eng.results() if world == 1 else (float(res_t[0].item()), 0)
-
-    # per-phase device times (un-graphed pass, CUDA events between phases)
-    phases = eng.profile_marginal()
-    for _ in range(2):
-        ph = eng.profile_marginal()
-        phases = {k: (min(phases[k][0], ph[k][0]), ph[k][1]) for k in ph}
-
-    # ---- e2e: host buffers in, host results out, every step.
-    # The pattern axis is cut into E2E_BLOCKS column blocks, each with its own engine handle and
-    # stream (one handle = one pattern shard is the C-ABI's unit anyway), so the H2D copy of block
-    # k+1, the pass over block k and the D2H copy of block k-1 overlap on the two copy engines.
-    e2e = None
-    if not args.no_e2e:
-        n_int = int((flat['tip_row'] < 0).sum())
-        nblk = max(1, min(args.e2e_blocks, Lp // 1024))
-        bounds = [(Lp * i) // nblk for i in range(nblk + 1)]
-        shards = []
-        for i in range(nblk):
-            lo, hi = bounds[i], bounds[i + 1]
-            e = Engine(q, device=local_rank)
-            st_i = torch.cuda.Stream()
-            e.set_stream(st_i.cuda_stream)
-            e.set_tree(flat['parent'], flat['child_ptr'], flat['child_idx'], flat['tip_row'])
-            cp = torch.empty((flat['tip_codes'].shape[0], hi - lo), dtype=torch.uint8, pin_memory=True)
-            cp.numpy()[...] = flat['tip_codes'][:, lo:hi]
-            sp = torch.empty((n_int, hi - lo), dtype=torch.uint8, pin_memory=True)
-            lp = torch.empty(hi - lo, dtype=torch.float64, pin_memory=True)
-            shards.append((e, cp.numpy(), sp.numpy(), lp.numpy(), np.ascontiguousarray(flat['multiplicity'][lo:hi]), st_i, cp, sp, lp))
-
-        def e2e_step():
-            # software pipeline over the blocks: uploads are chained (block k+1's copy starts when block k's
-            # has landed) and so are the passes; otherwise the DMA engine and the SMs time-slice all
-            # blocks and nothing overlaps
-            up_done = pass_done = None
-            for e, cp, sp, lp, m, st_i, *_ in shards:
-                if up_done is not None:
-                    st_i.wait_event(up_done)
-                e.set_patterns(cp, flat['code_profiles'], m, validate=False)
-                e.set_gtr(g)
-                e.set_branch_lengths(flat['t'])
-                up_done = torch.cuda.Event()
-                up_done.record(st_i)
-                if pass_done is not None:
-                    st_i.wait_event(pass_done)
-                e.marginal()
-                pass_done = torch.cuda.Event()
-                pass_done.record(st_i)
-                e.enqueue_site_lh(lp)
-                e.enqueue_all_seq_idx(sp)
-            tot = 0.0
-            for e, *_ in shards:
-                t_, _ = e.results()          # waits for that block's stream (incl. its D2H copies)
-                tot += t_
-            if world > 1:
-                tt_ = torch.tensor([tot], device='cuda', dtype=torch.float64)
-                dist.all_reduce(tt_)
-                tot = float(tt_.item())
-            return tot
-
-        tot_e2e = e2e_step()
-        e2e_step()
-        barrier()
-        k_e2e = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            tot_e2e = e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / k_e2e
-        h2d = int(flat['tip_codes'].nbytes + nblk * (flat['code_profiles'].nbytes + flat['t'].nbytes + 8 * (2 * q * q + 2 * q + 1))
-                  + flat['multiplicity'].nbytes)
-        d2h = int(n_int * Lp + 8 * Lp + 16 * nblk)
-        # sanity: the blocked e2e result equals the resident pass
-        lh_check = abs(tot_e2e - (total_lh_local if world == 1 else float(res_t[0].item()))) / abs(tot_e2e)
-        # PCIe probe for context (pinned 256 MB each way)
-        pb = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
-        db = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-        pe0, pe1, pe2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        db.copy_(pb, non_blocking=True); torch.cuda.synchronize()
-        pe0.record(); db.copy_(pb, non_blocking=True); pe1.record(); pb.copy_(db, non_blocking=True); pe2.record()
-        torch.cuda.synchronize()
-        pcie = (0.268435456 / (pe0.elapsed_time(pe1) / 1e3), 0.268435456 / (pe1.elapsed_time(pe2) / 1e3))
-        for sh in shards:
-            sh[0].close()
-        del shards
+    ns = None
+    if not site_specific and not args.no_secondary and (world == 8 or args.north_star):
+        # BASELINE.json configs[4]: rank r holds shard r (3,750 uncompressed sites, its own per-site models) of the 30 kb alignment
+        leg5 = Leg('cfg5', 1 + rank, SingleComm(), local_rank, stream)
+        ns = measure(leg5, SingleComm(), False, True, False, 'cfg5')
+        del leg5
         torch.cuda.empty_cache()
-        # ---- sparse host interface: the alignment goes in as (reference row + differences), the
-        # sequences come back as (root row + states that differ from the parent).  Same information,
-        # ~100x fewer PCIe bytes; one handle, no blocking needed.
-        from treetime_b200.sparse import sparse_from_dense
-        ref_c, e_row, e_pos, e_code = sparse_from_dense(flat['tip_codes'])
-        pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()  # noqa: E731
-        ref_c, e_row, e_pos, e_code = pin(ref_c), pin(e_row), pin(e_pos), pin(e_code)
-        max_mut = max(1 << 16, 8 * n_nodes)
-        m_node = torch.empty(max_mut, dtype=torch.int32, pin_memory=True).numpy()
-        m_pos = torch.empty(max_mut, dtype=torch.int32, pin_memory=True).numpy()
-        m_state = torch.empty(max_mut, dtype=torch.uint8, pin_memory=True).numpy()
-        m_root = torch.empty(Lp, dtype=torch.uint8, pin_memory=True).numpy()
-        lh_pin = torch.empty(Lp, dtype=torch.float64, pin_memory=True).numpy()
-        import ctypes
-        from treetime_b200 import _lib as L_
-        from treetime_b200.engine import _ip, _up
-
-        def sparse_step():
-            eng.set_patterns_sparse(ref_c, e_row, e_pos, e_code, flat['code_profiles'], flat['multiplicity'])
-            eng.set_gtr(g)
-            eng.set_branch_lengths(flat['t'])
-            eng.marginal()
-            if world > 1:
-                dist.all_reduce(res_t)
-            eng.enqueue_site_lh(lh_pin)
-            n_ = ctypes.c_int64()
-            L_.check(eng.lib.ttb_fetch_mutations(eng.h, _up(m_root), max_mut, _ip(m_node), _ip(m_pos), _up(m_state), ctypes.byref(n_)))
-            tot_, _ = eng.results()
-            return tot_, int(n_.value)
-
-        sparse_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            tot_sp, n_mut = sparse_step()
-        barrier()
-        sp_s = (time.perf_counter() - t0) / k_e2e
-        sp_h2d = int(ref_c.nbytes + e_row.nbytes + e_pos.nbytes + e_code.nbytes + flat['code_profiles'].nbytes + flat['multiplicity'].nbytes
-                     + flat['t'].nbytes + 8 * (2 * q * q + 2 * q + 1))
-        sp_d2h = int(Lp + n_mut * 9 + 8 * Lp + 24)
-        sp_check = abs(tot_sp - (total_lh_local if world == 1 else float(res_t[0].item()))) / abs(tot_sp)
-        e2e = (e2e_s, h2d, d2h, nblk, lh_check, pcie, sp_s, sp_h2d, sp_d2h, sp_check, n_mut, int(e_row.shape[0]))
-
-    # ---- reduce over ranks: max time, summed work
-    ms_step = ms_total / args.steps
-    if world > 1:
-        tmax = torch.tensor([ms_step, e2e[0] if e2e else 0.0, e2e[6] if e2e else 0.0], device='cuda', dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = torch.tensor([float(updates_local)], device='cuda', dtype=torch.float64)
-        dist.all_reduce(tsum)
-        ms_step = float(tmax[0].item())
-        e2e_time = float(tmax[1].item())
-        sp_time = float(tmax[2].item())
-        updates_total = float(tsum[0].item())
-    else:
-        e2e_time = e2e[0] if e2e else 0.0
-        sp_time = e2e[6] if e2e else 0.0
-        updates_total = float(updates_local)
 
     if rank == 0:
-        value = updates_total / (ms_step / 1e3)
-        peak, peak_src = measured_peak()
-        post_b, pre_b = algorithmic_bytes(flat, q)
-        dom = 'preorder' if phases['preorder'][0] >= phases['postorder'][0] else 'postorder'
-        dom_bytes = pre_b if dom == 'preorder' else post_b
-        dom_ms, dom_launches = phases[dom]
-        achieved = dom_bytes / (dom_ms / 1e3) / 1e9
-        # whole-pass figure: the timed graph replays (ms_step), not the sum of the separately timed phases
-        pass_ms = ms_step
+        q = 5 if alphabet.startswith('nuc') else 20
         out = {
-            'metric': 'marginal ancestral reconstruction branch x pattern updates/s', 'value': value, 'unit': 'updates/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '%s: %s' % (args.workload, desc), 'n_tips': n_tips, 'n_sites_per_gpu': L, 'n_states': q,
-                       'patterns_per_gpu': int(Lp), 'branches': int(n_br), 'updates_per_step': updates_total,
-                       'sharding': 'pattern blocks, tree replicated (%d rank%s)' % (world, 's' if world > 1 else ''),
-                       'l2': 'working set (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed' % (eng.device_bytes() / 1e9),
-                       'device_bytes_per_gpu': eng.device_bytes()},
-            'clocks': clocks,
-            'gpu_launches': int(launches),
-            'log_lh_rank0': total_lh_local,
-            'roofline': {
-                'bound': 'hbm', 'kernel': '%s_level_kernel<%d> (%d level launches per pass)' % ('pre' if dom == 'preorder' else 'post', q, dom_launches),
-                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
-                'peak_note': 'peak is a measured COPY bandwidth (1:1 read:write); the preorder kernel streams 2:1 read:write and can sit at or slightly above it',
-                'algorithmic_bytes_per_pass': int(dom_bytes), 'kernel_ms_per_pass': dom_ms,
-                'traffic': ncu_traffic(args.workload, 'pre_level_kernel' if dom == 'preorder' else 'post_level_kernel'),
-                'phases_ms': {k: v[0] for k, v in phases.items()}, 'phase_launches': {k: v[1] for k, v in phases.items()},
-                'whole_pass': {'algorithmic_bytes': int(post_b + pre_b), 'bytes_per_update': (post_b + pre_b) / float(updates_local),
-                               'achieved_gbs': (post_b + pre_b) / (pass_ms / 1e3) / 1e9,
-                               'frac': (post_b + pre_b) / (pass_ms / 1e3) / 1e9 / peak,
-                               'survey_bytes_per_update': SURVEY_BYTES_PER_UPDATE.get(q),
-                               'survey_frac': (SURVEY_BYTES_PER_UPDATE.get(q, 0) * updates_local / (pass_ms / 1e3) / 1e9 / peak)
-                               if q in SURVEY_BYTES_PER_UPDATE else None},
-            },
-        }
-        if e2e:
-            out['e2e_sparse_io'] = {
-                'value': updates_total / sp_time, 'unit': 'updates/s', 'ms_per_step': 1e3 * sp_time,
-                'h2d_bytes_per_step': e2e[7], 'd2h_bytes_per_step': e2e[8], 'rel_lh_diff_vs_resident_pass': e2e[9],
-                'alignment_differences': e2e[11], 'mutations_returned': e2e[10],
-                'what': 'same pass through ttb_set_patterns_sparse (reference row + differences, like TreeTime\'s VCF '
-                        'alignments) and ttb_fetch_mutations (root row + states differing from the parent) + per-pattern LH'}
-            out['e2e'] = {'value': updates_total / e2e_time, 'unit': 'updates/s', 'ms_per_step': 1e3 * e2e_time,
-                          'h2d_bytes_per_step': e2e[1], 'd2h_bytes_per_step': e2e[2],
-                          'host_binding': numa, 'pattern_blocks': e2e[3], 'rel_lh_diff_vs_resident_pass': e2e[4],
-                          'pcie_probe_gbs': {'h2d': e2e[5][0], 'd2h': e2e[5][1]},
-                          'what': 'per step and per pattern block: ttb_set_patterns/gtr/branch_lengths from pinned host '
-                                  'memory, ttb_marginal, ttb_enqueue_fetch_site_lh + ttb_enqueue_fetch_all_seq_idx into '
-                                  'pinned host memory, ttb_results; blocks run on their own streams so copies overlap compute'}
-        if not args.no_cpu_baseline and world >= 1:
-            n_pat = args.cpu_patterns or int(max(64, min(Lp, 20.0 * 2.0e6 / n_br)))
-            upd, times, cpu_lh = run_cpu(flat, g, n_pat, 1)
-            out['cpu_baseline'] = {'value': upd / times[0], 'unit': 'updates/s', 'cores': 1, 'kind': 'port',
-                                   'sample': 'one pass over the first %d of %d patterns (same tree, same model); '
-                                             'host has %d cores, the reference path is single-threaded numpy'
-                                             % (min(n_pat, Lp), Lp, os.cpu_count() or 0)}
+            'metric': METRIC, 'value': res['value'], 'unit': 'updates/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': res['ms_per_step'], 'higher_is_better': True, 'scaling': mode, 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': '%s: %s' % (args.workload, desc), 'n_tips': n_tips, 'n_sites': L, 'n_states': q,
+                       'patterns_rank0': res['patterns_rank0'], 'branches': res['branches'], 'updates_per_step': res['updates_per_step'],
+                       'sharding': ('ONE alignment, compressed patterns sharded over %d ranks (dist.shard_bounds), tree replicated' % world) if sharded
+                       else ('tree replicated, one full-size alignment per rank (%d rank%s)' % (world, 's' if world > 1 else '')),
+                       'l2': 'working set (%.1f GB on rank 0) vs 126 MB L2: no flush needed' % (res['device_bytes_rank0'] / 1e9),
+                       'device_bytes_rank0': res['device_bytes_rank0']},
+            'clocks': res['clocks'], 'gpu_launches': res['gpu_launches'], 'log_lh': res['log_lh'], 'roofline': res['roofline']}
+        for k in ('parity', 'cpu_baseline', 'e2e', 'e2e_cabi_dense'):
+            if k in res:
+                out[k] = res[k]
+        if 'parity' in res:
+            out['log_lh_rel_err'] = res['parity']['log_lh_rel_err']
+            out['max_profile_abs_err'] = res['parity']['max_profile_abs_err']
+            out['argmax_mismatch_off_ties'] = res['parity']['argmax_mismatch_off_ties']
+        if weak is not None:
+            out['weak_scaling'] = {k: weak[k] for k in ('value', 'ms_per_step', 'updates_per_step', 'patterns_rank0', 'clocks', 'e2e') if k in weak}
+            out['weak_scaling']['what'] = 'same run, every rank a full-size configs[2] alignment (per-GPU work fixed)'
+        if ns is not None:
+            blk = {'workload': 'cfg5: ' + WORKLOADS['cfg5'][4], 'n_gpus': world, 'shards_run': world, 'shards_total': 8}
+            blk.update({k: ns[k] for k in ('value', 'ms_per_step', 'updates_per_step', 'patterns_rank0', 'branches', 'clocks', 'gpu_launches',
+                                           'roofline', 'parity', 'e2e', 'log_lh') if k in ns})
+            blk['whole_pass_frac_of_hbm_roofline'] = ns['roofline']['whole_pass']['frac']
+            out['north_star_config'] = blk
         _emit(real_stdout, out)
     if world > 1:
         dist.barrier()

@@ -322,7 +322,13 @@ class DeviceMarginalMixin(object):
                 self._seq_cache[k] = self.gtr.alphabet[idx]
         return self._seq_cache[k]
 
-    def sequence_differences(self):
+    def reload_alignment(self):
+        """Mark the device copy of the alignment stale: the next pass uploads the tip codes again (dense, or as
+        reference row + differences with sparse_io).  The reference has no such call -- its alignment lives in host
+        memory -- this is the host->device half of a pass for callers that stream alignments through one object."""
+        self._device_patterns = False
+
+    def sequence_differences(self, gather=True):
         """Every reconstructed internal sequence in sparse form: (root state indices [L'], node, pos, state) with one
         entry per (internal node, compressed position) whose state differs from the parent's, sorted by (node, pos);
         `node` indexes tree.find_clades() order.  This is what `node.mutations` enumerates (treeanc.py:27-42), for the
@@ -330,7 +336,7 @@ class DeviceMarginalMixin(object):
         if not self.sequence_reconstruction:
             raise ValueError('Ancestral sequences are not yet inferred')
         root, node, pos, state = self._engine.mutations()
-        if self.comm.world_size > 1:
+        if gather and self.comm.world_size > 1:       # gather=False: this rank's pattern shard only, shard-local positions
             lo, _ = self._shard()
             root = self.comm.allgather(root, axis=0)
             node, pos, state = (self.comm.allgather(x, axis=0) for x in (node, pos + lo, state))
