@@ -549,3 +549,58 @@ def test_branch_masks(kind):
             eng.joint()
     with pytest.raises(TTBError):
         eng.set_branch_masks(M * 2, node_mask)
+
+
+@pytest.mark.parametrize('kind', ['nuc', 'aa', 'site_specific', 'tips', 'joint'])
+def test_merged_level_launches(kind, monkeypatch):
+    """Runs of small levels are ONE launch whose blocks walk several levels (build_groups / Pipe::wait_done): every
+    merge threshold -- none, a few levels, the whole tree above the leaf level -- gives the same messages bit for bit
+    (the per-node arithmetic does not change; only the grouping of the log-prefactor sums does)."""
+    rt = False
+    if kind == 'aa':
+        gtr, L, compress = util.random_gtr('aa_nogap', 5), 300, True
+    elif kind == 'site_specific':
+        from treetime_b200.gtr import GTRSiteSpecific
+        L, compress = 700, False
+        gtr = GTRSiteSpecific.random(L=L, alphabet='nuc', rng=np.random.default_rng(3))
+    else:
+        gtr, L, compress = util.nuc_gtr(), 1500, True
+        rt = kind == 'tips'
+    tree = synth.random_tree(400, seed=8, mean_bl=0.01, polytomy_frac=0.3)
+    topo, flat, g = util.make_flat(tree, gtr, L, 8, amb_frac=0.01, amb_chars='N' if kind == 'aa' else 'N-RY', compress=compress)
+    n_nodes = flat['parent'].shape[0]
+    base = None
+    for merge in ('0', '3', '24', '100000'):
+        monkeypatch.setenv('TTB_MERGE_NODES', merge)
+        eng = util.engine_for(flat, g)
+        if kind == 'joint':
+            eng.joint()
+            tot, nd = eng.results()
+            cur = (tot, eng.all_seq_idx(), eng.site_lh())
+            if base is None:
+                base = cur
+                jres = O.joint(flat, g)
+                assert abs(tot - jres.total_LH) <= LH_RTOL * abs(jres.total_LH)
+            else:
+                assert abs(cur[0] - base[0]) <= 1e-12 * abs(base[0]) and np.array_equal(cur[1], base[1]) and np.array_equal(cur[2], base[2])
+            continue
+        launches0 = eng.launch_count()
+        eng.marginal(reconstruct_tips=rt)
+        tot, nd = eng.results()
+        n_launch = eng.launch_count() - launches0
+        prof = [eng.node_array(n, 2) for n in range(0, n_nodes, 9) if flat['tip_row'][n] < 0 or rt]
+        sub = [eng.node_array(n, 0) for n in range(0, n_nodes, 9)]
+        cur = (tot, eng.all_seq_idx(), prof, sub, n_launch)
+        if base is None:
+            base = cur
+            res = O.marginal(flat, g, reconstruct_tip_states=rt)
+            assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH) and nd == res.N_diff
+            compare_all(flat, g, eng, res, reconstruct_tips=rt, every=11)
+        else:
+            assert abs(cur[0] - base[0]) <= 1e-12 * abs(base[0])
+            assert np.array_equal(cur[1], base[1])
+            assert all(np.array_equal(x, y) for x, y in zip(cur[2], base[2]))
+            assert all(np.array_equal(x, y) for x, y in zip(cur[3], base[3]))
+            assert cur[4] < base[4]                      # fewer launches than one per level
+        eng.marginal(reconstruct_tips=rt)
+        assert eng.results()[1] == 0

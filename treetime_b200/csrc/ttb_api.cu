@@ -84,10 +84,11 @@ struct Sched {
   std::vector<int> level_node_begin;  // offsets into node_chunk per level (+ sentinel)
   std::vector<int> group_ptr;         // built once the number of tiles is known
   std::vector<TtbLevelLaunch> launches;
+  std::vector<int> dep;               // per chunk: the chunk whose output it reads (latest one), -1 = tips / the root only
   DBuf<TtbChunk> d_chunks;
-  DBuf<int> d_group_ptr, d_node_chunk;
+  DBuf<int> d_group_ptr, d_node_chunk, d_dep;
   void clear() {
-    chunks.clear(); node_chunk.clear(); level_node_begin.clear(); group_ptr.clear(); launches.clear();
+    chunks.clear(); node_chunk.clear(); level_node_begin.clear(); group_ptr.clear(); launches.clear(); dep.clear();
   }
 };
 
@@ -95,6 +96,7 @@ struct Sched {
 
 struct ttb_engine {
   int device = 0;
+  int n_sm = 148;   // multiprocessors of this device (grid sizing)
   int q = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
@@ -311,29 +313,76 @@ void build_sched(ttb_handle h, const std::vector<int>& key, const std::vector<ch
     sc.level_node_begin.push_back((int)sc.node_chunk.size());
   }
   sc.node_chunk.push_back((int)sc.chunks.size());
-  (void)out_is_node_slot;
+  // Producer -> consumer links between chunks (used by launches that merge several levels, see build_groups):
+  // postorder (out_is_node_slot): a chunk reads the subtree profiles its internal children got in their LAST chunk;
+  // preorder: a parent's first chunk reads the profile the parent received as a child of an earlier chunk.
+  sc.dep.assign(sc.chunks.size(), -1);
+  std::vector<int> wrote(n_nodes, -1);   // node -> chunk that wrote its message in this schedule
+  if (out_is_node_slot) {
+    for (size_t i = 0; i < sc.chunks.size(); ++i) {
+      const TtbChunk& ch = sc.chunks[i];
+      for (int b = 0; b < (ch.flags >> 8); ++b)
+        if (ch.src[b] >= 0) sc.dep[i] = std::max(sc.dep[i], wrote[ch.cnode[b]]);
+      if (ch.flags & 2) wrote[h->parent[ch.cnode[0]]] = (int)i;
+    }
+  } else {
+    for (size_t i = 0; i < sc.chunks.size(); ++i) {
+      const TtbChunk& ch = sc.chunks[i];
+      sc.dep[i] = wrote[h->parent[ch.cnode[0]]];
+      for (int b = 0; b < (ch.flags >> 8); ++b) wrote[ch.cnode[b]] = (int)i;
+    }
+  }
 }
 
 // Split every level into groups of consecutive nodes so that a launch has enough blocks to
 // fill the GPU but every block still pipelines over several chunks.
-void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm) {
+void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm, bool post_order, int n_sm) {
   sc.group_ptr.clear();
   sc.launches.clear();
   // Site-specific kernels load a per-pattern eigen-system per block (longer runs amortise it) and are
   // issue-bound, so a partly filled last wave costs its full duration: size the grid of a level to fill
   // whole waves of the 2 blocks/SM these kernels run at (3 for the symmetric variant).
-  long long slots = 148LL * ss_blocks_per_sm;
+  long long slots = (long long)n_sm * ss_blocks_per_sm;
   if (const char* e = getenv("TTB_SS_SLOTS")) slots = std::max(1LL, atoll(e));
   // single-model kernels: ~2 waves of 3 blocks/SM per level -- longer runs amortise a block's prologue and first
   // bulk copy (measured: 888 vs 4736 blocks per level: cfg2 0.95 -> 0.75 ms, cfg3 14.26 -> 14.13 ms, cfg4 2.33 -> 2.20 ms)
-  long long target_blocks = site_specific ? slots * 4 : 148LL * 6;
+  long long target_blocks = site_specific ? slots * 4 : (long long)n_sm * 6;
   long long max_group = site_specific ? 128 : 32;
   if (const char* e = getenv("TTB_TARGET_BLOCKS")) target_blocks = std::max(1LL, atoll(e));   // tuning knobs (measurement only)
   if (const char* e = getenv("TTB_MAX_GROUP")) max_group = std::max(1LL, atoll(e));
   long long ss_waves = 4;
   if (const char* e = getenv("TTB_SS_WAVES")) ss_waves = std::max(1LL, atoll(e));
-  for (size_t l = 0; l + 1 < sc.level_node_begin.size(); ++l) {
-    const int nb = sc.level_node_begin[l], ne = sc.level_node_begin[l + 1];
+  // Merged-level launches (opt-in, TTB_MERGE_NODES=k): a run of consecutive levels with at most k nodes each becomes ONE
+  // launch with one group per pattern tile -- the block walks all those levels, its producer warp honouring the chunks'
+  // dependencies (Pipe::wait_done).  Parity-tested (tests/test_gpu_parity.py::test_merged_level_launches) and measured
+  // (profiles/R2b_merge_threshold.json): it is SLOWER at every threshold and configuration (cfg2 0.763 -> 0.824 ms at
+  // k = 24, cfg4 2.01 -> 2.61 ms, cfg3 / cfg5 unchanged): with programmatic dependent launches inside the CUDA graph a
+  // small level costs ~2.2 us, while one block walking the nodes of a level one after the other needs ~0.66 us per node
+  // (write -> proxy fence -> bulk read of the same tile is a latency chain).  So the default stays one launch per level.
+  // Postorder level 0 (all children are tips) has its own kernel and is never merged.
+  long long merge_nodes = 0;
+  if (const char* e = getenv("TTB_MERGE_NODES")) merge_nodes = std::max(0LL, atoll(e));
+  const size_t n_levels = sc.level_node_begin.size() - 1;
+  for (size_t l = 0; l < n_levels; ++l) {
+    const int nb = sc.level_node_begin[l];
+    size_t l1 = l + 1;
+    if (merge_nodes > 0 && (l > 0 || !post_order)) {
+      size_t m = l;
+      while (m < n_levels && sc.level_node_begin[m + 1] - sc.level_node_begin[m] <= merge_nodes) ++m;
+      if (m - l >= 2) l1 = m;
+    }
+    if (l1 > l + 1) {
+      TtbLevelLaunch L;
+      L.group_off = (int)sc.group_ptr.size();
+      L.n_groups = 1;
+      L.dep = 1;
+      sc.group_ptr.push_back(sc.node_chunk[nb]);
+      sc.group_ptr.push_back(sc.node_chunk[sc.level_node_begin[l1]]);
+      sc.launches.push_back(L);
+      l = l1 - 1;
+      continue;
+    }
+    const int ne = sc.level_node_begin[l + 1];
     const int n = ne - nb;
     long long G;
     if (site_specific) {
@@ -351,6 +400,7 @@ void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm
     TtbLevelLaunch L;
     L.group_off = (int)sc.group_ptr.size();
     L.n_groups = 0;
+    L.dep = 0;
     for (int i = nb; i < ne; i += (int)G) {
       sc.group_ptr.push_back(sc.node_chunk[i]);
       ++L.n_groups;
@@ -372,12 +422,14 @@ int enqueue_pass(ttb_handle h, int flags, int count_diff, cudaStream_t s, int* n
   pl.d_tip_nodes = h->d_tip_nodes.p;
   pl.d_post_chunks = h->post.d_chunks.p;
   pl.d_post_group_ptr = h->post.d_group_ptr.p;
+  pl.d_post_dep = h->post.d_dep.p;
   pl.d_post_node_chunk = h->post.d_node_chunk.p;
   pl.n_post_leaf_nodes = h->post.level_node_begin.size() > 1 ? h->post.level_node_begin[1] : 0;
   pl.post_levels = h->post.launches.data();
   pl.n_post_levels = (int)h->post.launches.size();
   const Sched& pre = pl.tips ? h->pre_all : h->pre_int;
   pl.d_pre_chunks = pre.d_chunks.p;
+  pl.d_pre_dep = pre.d_dep.p;
   pl.d_pre_group_ptr = pre.d_group_ptr.p;
   pl.pre_levels = pre.launches.data();
   pl.n_pre_levels = (int)pre.launches.size();
@@ -394,11 +446,12 @@ void fill_plan(ttb_handle h, TtbPassPlan& pl, bool tips, int count_diff) {
   pl.d_tip_nodes = h->d_tip_nodes.p;
   pl.d_post_chunks = h->post.d_chunks.p;
   pl.d_post_group_ptr = h->post.d_group_ptr.p;
+  pl.d_post_dep = h->post.d_dep.p;
   pl.d_post_node_chunk = h->post.d_node_chunk.p;
   pl.n_post_leaf_nodes = h->post.level_node_begin.size() > 1 ? h->post.level_node_begin[1] : 0;
   pl.post_levels = h->post.launches.data();
   pl.n_post_levels = (int)h->post.launches.size();
-  pl.d_pre_chunks = nullptr; pl.d_pre_group_ptr = nullptr; pl.pre_levels = nullptr; pl.n_pre_levels = 0;
+  pl.d_pre_chunks = nullptr; pl.d_pre_group_ptr = nullptr; pl.d_pre_dep = nullptr; pl.pre_levels = nullptr; pl.n_pre_levels = 0;
   pl.d_jpre_nodes = tips ? h->d_jpre_all.p : h->d_jpre_int.p;
   pl.jpre_levels = tips ? h->jpre_all_levels.data() : h->jpre_int_levels.data();
   pl.n_jpre_levels = (int)(tips ? h->jpre_all_levels.size() : h->jpre_int_levels.size());
@@ -413,7 +466,7 @@ int ensure_state(ttb_handle h, bool tips) {
   const int ss_mode = h->site_specific ? (h->ss_sym ? 2 : 1) : 0;
   if (h->sched_tiles != h->tiles() || h->sched_ss != ss_mode) {
     for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all}) {
-      build_groups(*sc, h->tiles(), h->site_specific, ss_mode == 2 ? 3 : 2);
+      build_groups(*sc, h->tiles(), h->site_specific, ss_mode == 2 ? 3 : 2, sc == &h->post, h->n_sm);
       if ((rc = upload(sc->d_group_ptr, sc->group_ptr.data(), sc->group_ptr.size(), h->stream))) return rc;
     }
     CK(cudaStreamSynchronize(h->stream));
@@ -498,6 +551,7 @@ int ttb_create(ttb_handle* out, int device, int n_states) {
   ttb_engine* h = new ttb_engine();
   h->device = device;
   h->q = n_states;
+  CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   CK(cudaMallocHost(&h->h_results, 4 * sizeof(double)));
@@ -514,7 +568,8 @@ int ttb_destroy(ttb_handle h) {
   cudaStreamSynchronize(h->stream);
   h->drop_graphs();
   DBuf<int>* ib[] = {&h->d_parent, &h->d_child_ptr, &h->d_child_idx, &h->d_tip_row, &h->d_int_slot, &h->d_tip_nodes,
-                     &h->d_enodes, &h->d_ekinds, &h->post.d_group_ptr, &h->pre_int.d_group_ptr, &h->pre_all.d_group_ptr, &h->post.d_node_chunk};
+                     &h->d_enodes, &h->d_ekinds, &h->post.d_group_ptr, &h->pre_int.d_group_ptr, &h->pre_all.d_group_ptr, &h->post.d_node_chunk,
+                     &h->post.d_dep, &h->pre_int.d_dep, &h->pre_all.d_dep};
   for (auto* b : ib) b->release();
   DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_LP, &h->d_TL, &h->d_ss_eig, &h->d_ss_mu, &h->d_ss_V, &h->d_ss_Vinv, &h->d_ss_Pi,
                         &h->d_ss_w, &h->d_ss_grid, &h->d_ss_E, &h->d_TU, &h->d_P, &h->d_S,
@@ -630,8 +685,10 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   if ((rc = upload(h->d_tip_nodes, h->tip_nodes.data(), h->tip_nodes.size(), s))) return rc;
   if ((rc = upload(h->d_jpre_int, h->jpre_int_nodes.data(), h->jpre_int_nodes.size(), s))) return rc;
   if ((rc = upload(h->d_jpre_all, h->jpre_all_nodes.data(), h->jpre_all_nodes.size(), s))) return rc;
-  for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all})
+  for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all}) {
     if ((rc = upload(sc->d_chunks, sc->chunks.data(), sc->chunks.size(), s))) return rc;
+    if ((rc = upload(sc->d_dep, sc->dep.data(), sc->dep.size(), s))) return rc;
+  }
   if ((rc = upload(h->post.d_node_chunk, h->post.node_chunk.data(), h->post.node_chunk.size(), s))) return rc;
   CK(cudaStreamSynchronize(s));
   // every per-node array is invalid now
@@ -709,7 +766,7 @@ int ttb_set_patterns(ttb_handle h, int64_t n_patterns, const uint8_t* tip_codes,
     // one contiguous H2D copy into a packed staging buffer, re-pitched to the padded layout on the device
     if (int rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)Lp)) return rc;
     CK(cudaMemcpyAsync(h->d_bstage.p, tip_codes, (size_t)h->n_tips * Lp, cudaMemcpyHostToDevice, s));
-    pitch_bytes_kernel<<<148 * 8, 256, 0, s>>>(h->d_bstage.p, Lp, h->d_codes.p, ld, Lp, h->n_tips, 0);
+    pitch_bytes_kernel<<<h->n_sm * 8, 256, 0, s>>>(h->d_bstage.p, Lp, h->d_codes.p, ld, Lp, h->n_tips, 0);
     h->launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -763,7 +820,7 @@ int ttb_set_patterns_from_alignment(ttb_handle h, int64_t n_patterns, const int6
     if ((rc = upload(h->d_lut, lut, (size_t)256, s))) return rc;
     if ((rc = h->d_flag.alloc(1))) return rc;
     CK(cudaMemsetAsync(h->d_flag.p, 0, sizeof(int), s));
-    gather_patterns_kernel<<<148 * 8, 256, 0, s>>>(h->d_aln.p, h->aln_L, h->d_firstpos.p, h->d_constl.p, h->d_seqrow.p, h->d_lut.p,
+    gather_patterns_kernel<<<h->n_sm * 8, 256, 0, s>>>(h->d_aln.p, h->aln_L, h->d_firstpos.p, h->d_constl.p, h->d_seqrow.p, h->d_lut.p,
                                                     missing_code, Lp, ld, h->n_tips, h->d_codes.p, h->d_flag.p);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -793,7 +850,7 @@ int ttb_set_patterns_sparse(ttb_handle h, int64_t n_patterns, const uint8_t* ref
     int rc;
     if ((rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)Lp))) return rc;
     CK(cudaMemcpyAsync(h->d_bstage.p, ref_codes, (size_t)Lp, cudaMemcpyHostToDevice, s));
-    fill_ref_codes_kernel<<<148 * 8, 256, 0, s>>>(h->d_bstage.p, h->d_codes.p, ld, Lp, h->n_tips);
+    fill_ref_codes_kernel<<<h->n_sm * 8, 256, 0, s>>>(h->d_bstage.p, h->d_codes.p, ld, Lp, h->n_tips);
     h->launches += 1;
     if (n_entries) {
       if ((rc = upload(h->d_ent_row, entry_row, (size_t)n_entries, s))) return rc;
@@ -871,7 +928,7 @@ int ttb_set_gtr_site_specific(ttb_handle h, const double* eigvals, const double*
   {
     const bool was = h->site_specific;
     h->site_specific = true;
-    ss_grid_table_kernel<<<148 * 8, 256, 0, h->stream>>>(h->dev(), h->d_ss_E.p);
+    ss_grid_table_kernel<<<h->n_sm * 8, 256, 0, h->stream>>>(h->dev(), h->d_ss_E.p);
     h->site_specific = was;
     h->launches += 1;
     CK(cudaGetLastError());
@@ -908,7 +965,7 @@ int ttb_set_gtr_site_specific(ttb_handle h, const double* eigvals, const double*
     if ((rc = h->d_ss_Ec.alloc((size_t)h->tiles() * n_grid * q * TTB_TILE))) return rc;
     const bool was = h->site_specific;
     h->site_specific = true;
-    ss_grid_table_kernel<<<148 * 8, 256, 0, h->stream>>>(h->dev(), h->d_ss_Ec.p, h->d_ss_c.p);
+    ss_grid_table_kernel<<<h->n_sm * 8, 256, 0, h->stream>>>(h->dev(), h->d_ss_Ec.p, h->d_ss_c.p);
     h->site_specific = was;
     h->launches += 1;
     CK(cudaGetLastError());
@@ -1272,7 +1329,7 @@ int ttb_fetch_mutations(ttb_handle h, uint8_t* root_idx, int32_t max_n, int32_t*
   if ((rc = h->d_mut_count.alloc(1))) return rc;
   cudaStream_t s = h->stream;
   CK(cudaMemsetAsync(h->d_mut_count.p, 0, sizeof(unsigned long long), s));
-  const int chunks = std::max(1, std::min(h->n_nodes - 1, (148 * 16 + h->tiles() - 1) / h->tiles()));
+  const int chunks = std::max(1, std::min(h->n_nodes - 1, (h->n_sm * 16 + h->tiles() - 1) / h->tiles()));
   mutations_kernel<<<dim3(h->tiles(), chunks), TTB_BLOCK, 0, s>>>(h->dev(), max_n, h->d_mut_node.p, h->d_mut_pos.p, h->d_mut_state.p,
                                                                   h->d_mut_count.p);
   h->launches += 1;
@@ -1304,7 +1361,7 @@ int ttb_enqueue_fetch_all_seq_idx(ttb_handle h, uint8_t* out) {
   if (int rc = check_states(h)) return rc;
   if (!out) return fail(TTB_EINVAL, "ttb_enqueue_fetch_all_seq_idx: null output");
   if (int rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)h->Lp)) return rc;
-  pitch_bytes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_idx.p, h->ld, h->d_bstage.p, h->Lp, h->Lp, h->n_int, 0);
+  pitch_bytes_kernel<<<h->n_sm * 8, 256, 0, h->stream>>>(h->d_idx.p, h->ld, h->d_bstage.p, h->Lp, h->Lp, h->n_int, 0);
   h->launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, h->d_bstage.p, (size_t)h->n_int * h->Lp, cudaMemcpyDeviceToHost, h->stream));
@@ -1316,7 +1373,7 @@ int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out) {
   if (int rc = check_states(h)) return rc;
   if (!out) return fail(TTB_EINVAL, "ttb_fetch_all_seq_idx: null output");
   if (int rc = h->d_bstage.alloc(std::max((size_t)h->n_tips, (size_t)h->n_int) * (size_t)h->Lp)) return rc;
-  pitch_bytes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_idx.p, h->ld, h->d_bstage.p, h->Lp, h->Lp, h->n_int, 0);
+  pitch_bytes_kernel<<<h->n_sm * 8, 256, 0, h->stream>>>(h->d_idx.p, h->ld, h->d_bstage.p, h->Lp, h->Lp, h->n_int, 0);
   h->launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, h->d_bstage.p, (size_t)h->n_int * h->Lp, cudaMemcpyDeviceToHost, h->stream));
@@ -1397,7 +1454,7 @@ static int branch_eval(ttb_handle h, int32_t n_eval, const int32_t* nodes, const
     if ((rc = upload(h->d_ets, t, (size_t)n_eval, s))) return rc;
   }
   // enough blocks per branch to fill the GPU without starving long alignments
-  int nb = (int)std::min<long long>(h->tiles(), std::max<long long>(1, (148LL * 16 + n_eval - 1) / n_eval));
+  int nb = (int)std::min<long long>(h->tiles(), std::max<long long>(1, ((long long)h->n_sm * 16 + n_eval - 1) / n_eval));
   nb = std::min(nb, 64);
   if ((rc = h->d_partial.alloc((size_t)n_eval * nb))) return rc;
   if ((rc = h->d_eout.alloc((size_t)n_eval))) return rc;
@@ -1491,7 +1548,7 @@ int ttb_seqgen(ttb_handle h, uint64_t seed, const uint8_t* root_idx, const doubl
     d_uni = h->d_sg_uniforms.p;
   }
   const int nk = ttb_qops(h->q)->seqgen(h->dev(), h->tiles(), (unsigned long long)seed, d_root, d_uni, h->d_sg_states.p, s);
-  seqgen_tip_codes_kernel<<<dim3(h->tiles(), std::min(h->n_tips, 148 * 4)), TTB_BLOCK, 0, s>>>(h->dev(), h->d_tip_nodes.p, h->d_sg_states.p,
+  seqgen_tip_codes_kernel<<<dim3(h->tiles(), std::min(h->n_tips, h->n_sm * 4)), TTB_BLOCK, 0, s>>>(h->dev(), h->d_tip_nodes.p, h->d_sg_states.p,
                                                                                             h->d_bstage.p, h->d_codes.p);
   h->launches += nk + 1;
   CK(cudaGetLastError());
@@ -1514,7 +1571,7 @@ int ttb_mutation_counts(ttb_handle h, double* n_ij, double* T_i) {
   if (h->site_specific) return fail(TTB_EUNSUPPORTED, "ttb_mutation_counts: per-site statistics of site-specific models are not implemented");
   const int q = h->q, width = q * q + q;
   const int tiles = h->tiles();
-  int chunks = std::max(1, std::min(h->n_nodes - 1, (148 * 8 + tiles - 1) / tiles));
+  int chunks = std::max(1, std::min(h->n_nodes - 1, (h->n_sm * 8 + tiles - 1) / tiles));
   const int chunk = (h->n_nodes - 1 + chunks - 1) / chunks;
   chunks = (h->n_nodes - 1 + chunk - 1) / chunk;
   int rc;
@@ -1539,7 +1596,7 @@ int ttb_mutation_counts_per_site(ttb_handle h, double* n_ija, double* T_ia) {
   const int tiles = h->tiles();
   const size_t ld = (size_t)h->ld, Lp = (size_t)h->Lp;
   // enough branch chunks to fill the GPU, bounded by 1 GB of partial sums
-  int chunks = std::max(1, std::min(h->n_nodes - 1, (148 * 8 + tiles - 1) / tiles));
+  int chunks = std::max(1, std::min(h->n_nodes - 1, (h->n_sm * 8 + tiles - 1) / tiles));
   chunks = (int)std::max<size_t>(1, std::min<size_t>((size_t)chunks, ((size_t)1 << 27) / ((size_t)width * ld)));
   const int chunk = (h->n_nodes - 1 + chunks - 1) / chunks;
   chunks = (h->n_nodes - 1 + chunk - 1) / chunk;

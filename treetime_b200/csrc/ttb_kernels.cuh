@@ -149,6 +149,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // Orders this thread's generic-proxy shared-memory writes before later async-proxy (TMA) writes.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Orders this thread's generic-proxy global-memory writes before later async-proxy (TMA) reads of them (merged-level
+// launches: a block's bulk copies re-read message tiles its own pattern threads wrote a few chunks earlier).
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void st_release_cta_shared(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -623,6 +634,7 @@ struct Pipe {
   uint64_t* full;   // [STAGES] producer -> consumers (transaction barrier)
   uint64_t* empty;  // [STAGES] consumers -> producer (one arrival per thread)
   uint64_t* mbar;   // site-specific models: "model tile loaded" barrier
+  uint32_t* done;   // [TTB_BLOCK / 32] merged-level launches: chunks completed by every pattern warp (see wait_done)
   double* model;    // site-specific models: V and Vinv planes of this block's pattern tile [2*Q*Q][TILE]
   __host__ __device__ static int stage_size(int rows, int pq, int tu_stride) {
     return rows * TTB_TILE * 8 + CB * pq * 8 + CB * tu_stride * 8 + 2 * CB * TTB_TILE + 32;
@@ -634,6 +646,7 @@ struct Pipe {
     full = reinterpret_cast<uint64_t*>(smem);
     empty = full + STAGES;
     mbar = empty + STAGES;
+    done = reinterpret_cast<uint32_t*>(smem + 96);
     base = smem + 128;
     off_P = rows * TTB_TILE * 8;
     off_TU = off_P + CB * pq * 8;
@@ -659,7 +672,26 @@ struct Pipe {
       mbar_init(empty + s, TTB_BLOCK);
     }
     mbar_init(mbar, 1);
+    for (int w = 0; w < TTB_BLOCK / 32; ++w) done[w] = 0u;
     mbar_fence_init();
+  }
+  // Merged-level launches (several consecutive small levels in ONE launch, a block walks them all for its pattern tile):
+  // a chunk may read message tiles that this block's own pattern threads wrote a few chunks earlier.  Patterns are
+  // independent, so the dependency never leaves the block: every pattern warp publishes the number of chunks it has
+  // completed (its global writes ordered before by fence.proxy.async + release), and the producer warp waits until all
+  // warps have passed the chunk that wrote the tile before it issues the bulk copy that reads it.
+  __device__ __forceinline__ void publish_done(int warp, int lane, uint32_t n_completed) const {
+    fence_proxy_async_global();
+    __syncwarp();
+    if (lane == 0) st_release_cta_shared(done + warp, n_completed);
+  }
+  __device__ __forceinline__ void wait_done(int lane, uint32_t need) const {
+    if (lane < TTB_BLOCK / 32) {
+      while (ld_acquire_cta_shared(done + lane) < need) {
+      }
+    }
+    __syncwarp();
+    fence_proxy_async_global();
   }
   __device__ double* rows(int s) const { return reinterpret_cast<double*>(base + (size_t)s * stage_bytes); }
   __device__ double* P(int s) const { return reinterpret_cast<double*>(base + (size_t)s * stage_bytes + off_P); }
@@ -719,7 +751,8 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // ---------------------------------------------------------------------------------------
 template <int Q, bool SS, bool JOINT = false, bool SYM = false, bool MASK = false>
 __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : (Q > 8 ? (JOINT ? 168 : TTB_POST_LARGEQ_REGS) : 255)) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
-                                                              const int* __restrict__ group_ptr, int tiles, int fbase) {
+                                                              const int* __restrict__ group_ptr, int tiles, int fbase,
+                                                              const int* __restrict__ dep) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int RPC = Q;  // rows per child (the log-prefactors never travel: see Fpart)
   constexpr bool EST = ss_staged<Q, SS>();   // site-specific, grid rows + branch record staged per child
@@ -789,12 +822,16 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     // barriers); the descriptor of the next chunk is fetched while the current one is issued, so no
     // global-memory latency sits on the consumers' path.
     Chunk c = load_chunk_global(chunks + k0);
+    int d = dep ? __ldg(dep + k0) : -1;   // merged-level launch: the chunk (global index) that wrote what this one reads
     pdl_wait();   // everything the bulk copies read was written by earlier levels
     for (int u = 0; u < n_chunks; ++u) {
       const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
+      const int dn = dep ? __ldg(dep + k0 + min(u + 1, n_chunks - 1)) : -1;
+      if (d >= k0) pipe.wait_done(lane, (uint32_t)(d - k0 + 1));
       issue(u, c);
       cur.advance();
       c = cn;
+      d = dn;
     }
     return;
   }
@@ -925,6 +962,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
         }
       }
     }
+    if (dep) pipe.publish_done(warp, lane, (uint32_t)(u + 1));
   }
   if (!JOINT && act) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc + log(Zprod);
 }
@@ -1306,7 +1344,8 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // ---------------------------------------------------------------------------------------
 template <int Q, bool TIPS, bool SS, bool SYM = false, bool MASK = false>
 __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : (Q > 8 ? 168 : 255)) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
-                                                             const int* __restrict__ group_ptr, int tiles, int count_diff) {
+                                                             const int* __restrict__ group_ptr, int tiles, int count_diff,
+                                                             const int* __restrict__ dep) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool EST = ss_staged<Q, SS>();
   constexpr int EROWS = 2 * Q * TTB_TILE;
@@ -1382,12 +1421,16 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     // barriers); the descriptor of the next chunk is fetched while the current one is issued, so no
     // global-memory latency sits on the consumers' path.
     Chunk c = load_chunk_global(chunks + k0);
+    int d = dep ? __ldg(dep + k0) : -1;   // merged-level launch: the chunk (global index) that wrote what this one reads
     pdl_wait();   // everything the bulk copies read was written by earlier levels
     for (int u = 0; u < n_chunks; ++u) {
       const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
+      const int dn = dep ? __ldg(dep + k0 + min(u + 1, n_chunks - 1)) : -1;
+      if (d >= k0) pipe.wait_done(lane, (uint32_t)(d - k0 + 1));
       issue(u, c);
       cur.advance();
       c = cn;
+      d = dn;
     }
     return;
   }
@@ -1573,6 +1616,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     if constexpr (Q > 8) fence_proxy_async_smem();  // the stage was written through the generic proxy
     pipe.consumer_release(cur);
     cur.advance();
+    if (dep) pipe.publish_done(warp, lane, (uint32_t)(u + 1));
   }
   if (count_diff) {
     ndiff = __reduce_add_sync(0xffffffffu, ndiff);

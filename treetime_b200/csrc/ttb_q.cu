@@ -92,7 +92,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
     launch_pdl(post_level_kernel<Q, SS, false, SYM, MASK>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d, pl.d_post_chunks,
-               pl.d_post_group_ptr + L.group_off, tiles, fbase);
+               pl.d_post_group_ptr + L.group_off, tiles, fbase, L.dep ? pl.d_post_dep : nullptr);
     fbase += L.n_groups;
     ++nk;
   }
@@ -112,10 +112,10 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
       if (pl.tips)
         launch_pdl(pre_level_kernel<Q, true, SS, SYM, MASK>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
-                   pl.count_diff);
+                   pl.count_diff, L.dep ? pl.d_pre_dep : nullptr);
       else
         launch_pdl(pre_level_kernel<Q, false, SS, SYM, MASK>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
-                   pl.count_diff);
+                   pl.count_diff, L.dep ? pl.d_pre_dep : nullptr);
       ++nk;
     }
   }
@@ -164,7 +164,8 @@ int enqueue_joint_q(const TtbPassPlan& pl, cudaStream_t s, int trace) {
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
     post_level_kernel<Q, false, true><<<(unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s>>>(d, pl.d_post_chunks,
-                                                                                                      pl.d_post_group_ptr + L.group_off, tiles, 0);
+                                                                                                      pl.d_post_group_ptr + L.group_off, tiles, 0,
+                                                                                                      L.dep ? pl.d_post_dep : nullptr);
     ++nk;
   }
   joint_root_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d);

@@ -9,6 +9,7 @@
 // [group_ptr[group_off + g], group_ptr[group_off + g + 1]).
 struct TtbLevelLaunch {
   int group_off, n_groups;
+  int dep;   // 1: the launch merges several consecutive small levels (one group per tile; the kernel honours the chunks' `dep`)
 };
 
 struct TtbPassPlan {
@@ -19,10 +20,12 @@ struct TtbPassPlan {
   const int* d_post_node_chunk;    // first chunk of every scheduled postorder node (+ sentinel)
   int n_post_leaf_nodes;           // nodes of postorder level 1 (all children are tips)
   const int* d_post_group_ptr;
+  const int* d_post_dep;           // per chunk: global index of the chunk that wrote what it reads (merged-level launches), -1 = none
   const TtbLevelLaunch* post_levels;
   int n_post_levels;
   const TtbChunk* d_pre_chunks;    // schedule matching `tips`
   const int* d_pre_group_ptr;
+  const int* d_pre_dep;
   const TtbLevelLaunch* pre_levels;
   int n_pre_levels;
   bool lh_only, tips;
