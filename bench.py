@@ -223,16 +223,19 @@ def tie_mask(profile, rel=1e-12):
     return (s[:, -1] - s[:, -2]) <= rel * s[:, -1]
 
 
-def parity_against_port(eng, flat, g, n_patterns, max_profile_nodes=4000):
+def parity_against_port(eng, flat, g, n_patterns, max_profile_nodes=4000, cached=None, near_tie=1e-12):
     """The CPU oracle port (oracle/flat_numpy.py: the reference's per-node numpy calls, checker only) on the first
     n_patterns patterns of this shard against the device's resident pass: BASELINE.md §3 / the metric's second half.
     Returns (parity dict, cpu seconds, updates of the sample)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import flat_numpy as O
-    s, n, gs = cpu_sample(flat, g, n_patterns)
-    t0 = time.perf_counter()
-    res = O.marginal(s, gs)
-    cpu_s = time.perf_counter() - t0
+    if cached is None:
+        s, n, gs = cpu_sample(flat, g, n_patterns)
+        t0 = time.perf_counter()
+        res = O.marginal(s, gs)
+        cpu_s = time.perf_counter() - t0
+        cached = (s, n, gs, res, cpu_s)
+    s, n, gs, res, cpu_s = cached
     m = s['multiplicity']
     lh = eng.site_lh()[:n]
     tot_gpu = float((lh * m).sum())
@@ -243,7 +246,7 @@ def parity_against_port(eng, flat, g, n_patterns, max_profile_nodes=4000):
         bad = idx[k] != res.seq_idx[node]
         if bad.any():
             mism += int(bad.sum())
-            mism_off_ties += int((bad & ~tie_mask(res.profile[node])).sum())
+            mism_off_ties += int((bad & ~tie_mask(res.profile[node], near_tie)).sum())
     sel = internal if internal.shape[0] <= max_profile_nodes else internal[np.linspace(0, internal.shape[0] - 1, max_profile_nodes).astype(int)]
     perr = 0.0
     for node in sel:
@@ -257,6 +260,7 @@ def parity_against_port(eng, flat, g, n_patterns, max_profile_nodes=4000):
                       'build container) on the first patterns of rank 0\'s shard, same tree / model / branch lengths',
            'tolerances': {'log_lh_rel_err': 1e-9, 'max_profile_abs_err': 1e-6, 'argmax_mismatch_off_ties': 0}}
     n_br = flat['parent'].shape[0] - 1
+    par['_cached'] = cached
     return par, cpu_s, n_br * n
 
 
@@ -631,6 +635,44 @@ def pcie_probe():
     return {'h2d': 0.268435456 / (pe0.elapsed_time(pe1) / 1e3), 'd2h': 0.268435456 / (pe1.elapsed_time(pe2) / 1e3)}
 
 
+def precision_study(leg, par64, cached, steps, warmup, local_rank):
+    """north_star: "fp64 versus fp32 ... is decided from measured error".  The same pass with S / M STORED as float
+    (ttb_set_message_storage, arithmetic stays fp64): time and error against the same CPU port slice, next to the fp64
+    numbers of this run.  The engine is switched back to double afterwards."""
+    eng = leg.eng
+    eng.set_message_storage('f32')
+    try:
+        eng.marginal()
+        eng.sync()
+        ms32, _, _, lh32, _, _ = timed_resident(leg, steps, warmup, 1, local_rank, sample_clocks=False)
+        par32, _, _ = parity_against_port(eng, leg.flat, leg.g, 0, cached=cached)
+        par32.pop('_cached')
+        loose, _, _ = parity_against_port(eng, leg.flat, leg.g, 0, cached=cached, near_tie=1e-6)
+        post_b, pre_b = algorithmic_bytes(leg.flat, leg.q)
+        peak, _ = measured_peak()
+        n_int = int((leg.flat['tip_row'] < 0).sum()); n_tips = leg.flat['parent'].shape[0] - n_int
+        # float storage halves every message byte; the 1-byte codes / states stay
+        msg_bytes = (post_b + pre_b) - leg.Lp * (n_tips + 2 * (n_int - 1))
+        bytes32 = msg_bytes / 2 + leg.Lp * (n_tips + 2 * (n_int - 1))
+        keys = ('log_lh_rel_err', 'max_site_log_lh_rel_err', 'max_profile_abs_err', 'argmax_mismatch', 'argmax_mismatch_off_ties')
+        return {'f64_storage': dict({k: par64[k] for k in keys}),
+                'f32_storage': dict({k: par32[k] for k in keys}, ms_per_step=ms32, value=leg.updates_local / (ms32 / 1e3),
+                                    argmax_mismatch_where_top2_gap_exceeds_1e6=loose['argmax_mismatch_off_ties'],
+                                    whole_pass_frac_of_hbm_roofline=bytes32 / (ms32 / 1e3) / 1e9 / peak,
+                                    rel_lh_diff_total_vs_f64=abs(lh32 - leg_lh64(leg)) / abs(lh32)),
+                'patterns_compared': par64['patterns_compared'],
+                'what': 'S / M / Mtip stored as float32, every arithmetic operation in float64 (ttb_set_message_storage(TTB_STORAGE_F32)); '
+                        'errors against the CPU port on the same pattern slice; opt-in, the default and every headline number is float64 storage'}
+    finally:
+        eng.set_message_storage('f64')
+        eng.marginal()
+        eng.sync()
+
+
+def leg_lh64(leg):
+    return leg.lh64
+
+
 def reduce_max_sum(world, maxes, sums):
     if world == 1:
         return [float(x) for x in maxes], [float(x) for x in sums]
@@ -688,6 +730,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU port (drops `parity` and `cpu_baseline`)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-dense-e2e', action='store_true', help='skip the dense C-ABI e2e leg (N = 1)')
+    ap.add_argument('--no-precision-study', action='store_true', help='skip the float-message-storage leg (N = 1)')
     ap.add_argument('--no-secondary', action='store_true', help='N > 1: skip the weak-scaling and north-star legs')
     ap.add_argument('--north-star', action='store_true', help='run the configs[4] leg at any N (default: only at N = 8)')
     ap.add_argument('--e2e-blocks', type=int, default=6, help='pattern blocks (engine handles / streams) of the dense C-ABI e2e leg')
@@ -727,6 +770,7 @@ def main():
         """All numbers of one leg; reductions over ranks inside.  Returns a dict (complete on rank 0)."""
         leg.prepare(comm)
         ms_local, launches, clocks, lh_global, lh_local, barrier = timed_resident(leg, args.steps, args.warmup, world, local_rank)
+        leg.lh64 = lh_local
         phases = phase_profile(leg.eng)
         api = None
         if not args.no_e2e:
@@ -766,7 +810,10 @@ def main():
         if with_parity and rank == 0 and not args.no_cpu_baseline:
             n_pat = args.cpu_patterns or int(max(48, min(leg.Lp, 20.0 * 2.0e6 / leg.n_br)))
             par, cpu_s, upd = parity_against_port(leg.eng, leg.flat, leg.g, n_pat)
+            cached = par.pop('_cached')
             out['parity'] = par
+            if world == 1 and leg.q <= 8 and not args.no_precision_study:
+                out['precision_study'] = precision_study(leg, par, cached, args.steps, args.warmup, local_rank)
             out['cpu_baseline'] = {'value': upd / cpu_s, 'unit': 'updates/s', 'cores': 1, 'kind': 'port',
                                    'sample': 'one pass of oracle/flat_numpy.py over the first %d of %d patterns (same tree, same model); host has %d '
                                              'cores, the reference path is single-threaded numpy; `--impl reference` times the unmodified reference on '
@@ -806,7 +853,7 @@ def main():
                        'l2': 'working set (%.1f GB on rank 0) vs 126 MB L2: no flush needed' % (res['device_bytes_rank0'] / 1e9),
                        'device_bytes_rank0': res['device_bytes_rank0']},
             'clocks': res['clocks'], 'gpu_launches': res['gpu_launches'], 'log_lh': res['log_lh'], 'roofline': res['roofline']}
-        for k in ('parity', 'cpu_baseline', 'e2e', 'e2e_cabi_dense'):
+        for k in ('parity', 'cpu_baseline', 'e2e', 'e2e_cabi_dense', 'precision_study'):
             if k in res:
                 out[k] = res[k]
         if 'parity' in res:

@@ -72,6 +72,15 @@ int ttb_destroy(ttb_handle h);
 /* Run on an externally owned stream (e.g. torch's current stream); NULL = engine's own stream. */
 int ttb_set_stream(ttb_handle h, void* cuda_stream);
 
+/* Storage type of the per-node message arrays (marginal_subtree_LH, marginal_profile) in device memory.  The reference
+ * keeps them as float64 numpy arrays (treeanc.py:877,910-912) and that is the default.  TTB_STORAGE_F32 stores them as
+ * float while every arithmetic operation stays in double: the level kernels move half the bytes.  Opt-in, with a
+ * measured tolerance (total log-LH ~1e-8 relative instead of 1e-16, profiles ~1e-7; sequences can
+ * differ where the two largest profile entries are closer than ~1e-7).  Alphabets of up to 8 states; not with
+ * per-branch masks or ttb_joint.  Changing the type invalidates the current reconstruction. */
+enum { TTB_STORAGE_F64 = 0, TTB_STORAGE_F32 = 1 };
+int ttb_set_message_storage(ttb_handle h, int32_t storage);
+
 /* Tree topology (replaces the Bio.Phylo walk of treeanc.py:857,887).  parent[root] = -1.
  * tip_row[n] = row of the tip-code matrix for terminal nodes, -1 for internal nodes.
  * The level schedules (by height for the postorder, by depth for the preorder) are

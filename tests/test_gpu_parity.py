@@ -604,3 +604,61 @@ def test_merged_level_launches(kind, monkeypatch):
             assert cur[4] < base[4]                      # fewer launches than one per level
         eng.marginal(reconstruct_tips=rt)
         assert eng.results()[1] == 0
+
+
+@pytest.mark.parametrize('kind', ['nuc', 'site_specific', 'tips'])
+def test_float_message_storage(kind):
+    """ttb_set_message_storage(TTB_STORAGE_F32): S / M stored as float, arithmetic in double -- an opt-in whose error is
+    MEASURED here and pinned (north_star: fp64 vs fp32 is decided from measured error): total log-LH 1e-7 relative
+    (fp64 storage: 1e-9 bar, ~1e-16 measured), profiles 1e-6, sequences identical wherever the two largest profile
+    entries are more than 1e-6 apart.  Switching back to double reproduces the fp64 result bit for bit."""
+    rt = kind == 'tips'
+    if kind == 'site_specific':
+        from treetime_b200.gtr import GTRSiteSpecific
+        L, compress = 900, False
+        gtr = GTRSiteSpecific.random(L=L, alphabet='nuc', rng=np.random.default_rng(4))
+    else:
+        gtr, L, compress = util.nuc_gtr(), 3000, True
+    tree = synth.random_tree(600, seed=9, mean_bl=0.004, polytomy_frac=0.1)
+    topo, flat, g = util.make_flat(tree, gtr, L, 9, amb_frac=0.01, compress=compress)
+    res = O.marginal(flat, g, reconstruct_tip_states=rt)
+    eng = util.engine_for(flat, g)
+    eng.marginal(reconstruct_tips=rt)
+    tot64, _ = eng.results()
+    idx64 = eng.all_seq_idx()
+    prof64 = eng.node_array(3, 2) if flat['tip_row'][3] < 0 or rt else eng.node_array(0, 2)
+    bytes64 = eng.device_bytes()
+    eng.set_message_storage('f32')
+    with pytest.raises(Exception):
+        eng.node_array(0, 2)                        # the reconstruction was invalidated
+    eng.marginal(reconstruct_tips=rt)
+    tot32, nd = eng.results()
+    assert eng.device_bytes() < 0.62 * bytes64
+    rel = abs(tot32 - res.total_LH) / abs(res.total_LH)
+    assert rel <= 1e-7, rel
+    assert np.allclose(eng.site_lh(), res.sequence_LH, rtol=1e-5, atol=1e-5)     # per pattern; the total averages the rounding out
+    worst = 0.0
+    internal = np.nonzero(flat['tip_row'] < 0)[0]
+    idx32 = eng.all_seq_idx()
+    flips = 0
+    for k, n in enumerate(internal):
+        if k % 5 == 0:
+            worst = max(worst, np.abs(eng.node_array(int(n), 2) - res.profile[n]).max(), np.abs(eng.node_array(int(n), 0) - res.subtree_LH[n]).max())
+            if n:
+                worst = max(worst, np.abs(eng.node_array(int(n), 1) - res.outgroup_LH[n]).max())
+        bad = idx32[k] != res.seq_idx[n]
+        if bad.any():
+            flips += int(bad.sum())
+            assert util.tie_mask(res.profile[n], rel=1e-6)[bad].all(), 'sequence differs where the top-2 gap exceeds 1e-6 (node %d)' % n
+    assert worst < PROF_ATOL, worst
+    f = eng.branch_objective(np.arange(1, 40, dtype=np.int32), np.full(39, 0.01))          # run-time typed readers
+    ref = np.array([O.branch_objective(flat, g, res, n, 0.01) for n in range(1, 40)])
+    assert np.allclose(f, ref, rtol=1e-5, atol=1e-5)
+    with pytest.raises(Exception):
+        eng.joint()
+    eng.set_message_storage('f64')
+    eng.marginal(reconstruct_tips=rt)
+    assert eng.results()[0] == tot64 and np.array_equal(eng.all_seq_idx(), idx64)
+    assert np.array_equal(prof64, eng.node_array(3, 2) if flat['tip_row'][3] < 0 or rt else eng.node_array(0, 2))
+    print('float storage (%s): rel dLH %.1e, max|dprofile| %.1e, %d of %d states differ (all within 1e-6 of a tie)'
+          % (kind, rel, worst, flips, idx32.size))

@@ -81,6 +81,7 @@ SIGNATURES = {
     'ttb_create': ([ctypes.POINTER(_H), ctypes.c_int, ctypes.c_int], ctypes.c_int),
     'ttb_destroy': ([_H], ctypes.c_int),
     'ttb_set_stream': ([_H, ctypes.c_void_p], ctypes.c_int),
+    'ttb_set_message_storage': ([_H, ctypes.c_int32], ctypes.c_int),
     'ttb_set_tree': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_int_p, _c_int_p], ctypes.c_int),
     'ttb_set_patterns': ([_H, ctypes.c_int64, _c_u8_p, ctypes.c_int32, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_set_patterns_sparse': ([_H, ctypes.c_int64, _c_u8_p, ctypes.c_int64, _c_int_p, _c_int_p, _c_u8_p, ctypes.c_int32,

@@ -124,6 +124,7 @@ struct ttb_engine {
   std::vector<double> h_mult;
   // model
   bool have_gtr = false, have_t = false;
+  bool f32 = false;   // S / M / Mtip stored as float (ttb_set_message_storage)
   double mu = 1.0;
   int gap_index = -1;
   DBuf<double> d_t, d_eig, d_v, d_vinv, d_Pi, d_mu;
@@ -171,6 +172,8 @@ struct ttb_engine {
   long long launches = 0;
 
   int tiles() const { return (int)((Lp + TTB_BLOCK - 1) / TTB_BLOCK); }
+  // doubles to allocate for a message array of n elements in the current storage type
+  size_t msg_doubles(size_t n) const { return f32 ? (n + 1) / 2 : n; }
 
   void drop_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
@@ -216,6 +219,7 @@ struct ttb_engine {
     d.tu_stride = (n_codes * q + 1) / 2 * 2;
     d.TU = d_TU.p;
     d.P = d_P.p;
+    d.f32 = f32 ? 1 : 0;
     d.S = d_S.p;
     d.Fpart = d_F.p;
     d.Fred = d_Fred.p;
@@ -484,7 +488,7 @@ int ensure_state(ttb_handle h, bool tips) {
     h->prepared = true;
   }
   const size_t msg = (size_t)h->tiles() * q * TTB_TILE;   // one node's tile-blocked message: [tiles][q][128]
-  if ((rc = h->d_S.alloc((size_t)h->n_int * msg))) return rc;
+  if ((rc = h->d_S.alloc(h->msg_doubles((size_t)h->n_int * msg)))) return rc;
   if ((rc = h->d_LH.alloc(ld))) return rc;
   if ((rc = h->d_lh_partial.alloc(h->tiles()))) return rc;
   if ((rc = h->d_nd.alloc(1024))) return rc;
@@ -496,7 +500,7 @@ int ensure_preorder_state(ttb_handle h, bool tips) {
   const size_t q = h->q, ld = h->ld;
   int rc;
   if (!h->d_M.p) {
-    if ((rc = h->d_M.alloc((size_t)h->n_int * h->tiles() * q * TTB_TILE))) return rc;
+    if ((rc = h->d_M.alloc(h->msg_doubles((size_t)h->n_int * h->tiles() * q * TTB_TILE)))) return rc;
     if (!h->d_idx.p) {      // a joint pass may already have left states here: they are the "previous" ones
       if ((rc = h->d_idx.alloc((size_t)h->n_int * ld))) return rc;
       CK(cudaMemsetAsync(h->d_idx.p, 0xff, h->d_idx.bytes(), h->stream));
@@ -504,7 +508,7 @@ int ensure_preorder_state(ttb_handle h, bool tips) {
     h->drop_graphs();
   }
   if (tips && !h->d_Mtip.p) {
-    if ((rc = h->d_Mtip.alloc((size_t)h->n_tips * h->tiles() * q * TTB_TILE))) return rc;
+    if ((rc = h->d_Mtip.alloc(h->msg_doubles((size_t)h->n_tips * h->tiles() * q * TTB_TILE)))) return rc;
     if (!h->d_idxtip.p) {
       if ((rc = h->d_idxtip.alloc((size_t)h->n_tips * ld))) return rc;
       CK(cudaMemsetAsync(h->d_idxtip.p, 0xff, h->d_idxtip.bytes(), h->stream));
@@ -608,6 +612,21 @@ int ttb_set_stream(ttb_handle h, void* cuda_stream) {
   if (int rc = use_device(h)) return rc;
   CK(cudaStreamSynchronize(h->stream));
   h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
+
+int ttb_set_message_storage(ttb_handle h, int32_t storage) {
+  if (int rc = use_device(h)) return rc;
+  if (storage != TTB_STORAGE_F64 && storage != TTB_STORAGE_F32) return fail(TTB_EINVAL, "ttb_set_message_storage: unknown storage type");
+  const bool f32 = storage == TTB_STORAGE_F32;
+  if (f32 && h->q > 8) return fail(TTB_EUNSUPPORTED, "float message storage is compiled for alphabets of up to 8 states");
+  if (f32 == h->f32) return 0;
+  CK(cudaStreamSynchronize(h->stream));
+  h->f32 = f32;
+  h->d_S.release(); h->d_M.release(); h->d_Mtip.release();   // reallocated in the new type by the next pass
+  h->have_pass = h->have_tip_pass = false;
+  h->have_joint = h->have_joint_tips = false;
+  h->drop_graphs();
   return 0;
 }
 
@@ -1065,6 +1084,7 @@ int ttb_set_branch_lengths(ttb_handle h, const double* t) {
 int ttb_marginal(ttb_handle h, int32_t flags) {
   if (int rc = use_device(h)) return rc;
   if (int rc = check_ready(h, false)) return rc;
+  if (h->f32 && h->have_masks) return fail(TTB_EUNSUPPORTED, "float message storage is not available together with per-branch masks");
   const bool lh_only = flags & TTB_LH_ONLY;
   const bool tips = (flags & TTB_RECONSTRUCT_TIPS) && !lh_only;
   const bool keep_prev = (flags & TTB_KEEP_PREV_STATES) && !lh_only;
@@ -1121,6 +1141,7 @@ int ttb_joint(ttb_handle h, int32_t flags) {
   if (int rc = use_device(h)) return rc;
   if (int rc = check_ready(h, false)) return rc;
   if (h->site_specific) return fail(TTB_EUNSUPPORTED, "ttb_joint: joint reconstruction is not implemented for site-specific models");
+  if (h->f32) return fail(TTB_EUNSUPPORTED, "ttb_joint: the joint pass keeps log-space sums in double; call ttb_set_message_storage(TTB_STORAGE_F64) first");
   if (h->have_masks) return fail(TTB_EUNSUPPORTED, "ttb_joint: joint reconstruction is not implemented with per-branch masks");
   const bool tips = flags & TTB_RECONSTRUCT_TIPS;
   const bool trace = !(flags & TTB_JOINT_NO_TRACE);
@@ -1384,6 +1405,7 @@ int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out) {
 int ttb_profile_marginal(ttb_handle h, int32_t flags, double* ms, int32_t* launches) {
   if (int rc = use_device(h)) return rc;
   if (int rc = check_ready(h, false)) return rc;
+  if (h->f32 && h->have_masks) return fail(TTB_EUNSUPPORTED, "float message storage is not available together with per-branch masks");
   if (!ms || !launches) return fail(TTB_EINVAL, "ttb_profile_marginal: null output");
   const bool lh_only = flags & TTB_LH_ONLY;
   const bool tips = (flags & TTB_RECONSTRUCT_TIPS) && !lh_only;

@@ -102,6 +102,9 @@ struct TtbDev {
   // message arrays are TILE-BLOCKED state-planar: [slot][tile][state][128]: the q rows of one
   // (node, tile) are one contiguous q KB block = one TMA copy, and 128 consecutive patterns of a
   // state are one coalesced 1 KB row
+  // storage type of S / M / Mtip: 0 = double, 1 = float (ttb_set_message_storage: the level kernels move half the bytes,
+  // all arithmetic stays fp64; the pointers below then address float arrays of the same shape)
+  int f32;
   double* S;     // [n_int][tiles][q][128]  marginal_subtree_LH
   double* Fpart; // [n_fgroups][ld] per-pattern sums of log-normalisers over the nodes of one postorder block run
   int n_fgroups; //                 (sum over all runs = marginal_subtree_LH_prefactor of the root)
@@ -207,6 +210,16 @@ __device__ __forceinline__ double branch_weight(const TtbDev& p, int node, int k
 template <int Q>
 __device__ __forceinline__ size_t msg_off(const TtbDev& p, int slot, long long a) {
   return ((size_t)slot * p.tiles + (size_t)(a / TTB_TILE)) * (size_t)(Q * TTB_TILE) + (size_t)(a % TTB_TILE);
+}
+
+// S / M / Mtip as arrays of their storage type ST (double, or float with ttb_set_message_storage)
+template <typename ST>
+__device__ __forceinline__ ST* msg_base(double* p) { return reinterpret_cast<ST*>(p); }
+template <typename ST>
+__device__ __forceinline__ const ST* msg_base(const double* p) { return reinterpret_cast<const ST*>(p); }
+// run-time typed read (kernels outside the pass: fetch, branch objective, counts, sampling)
+__device__ __forceinline__ double msg_ld(const double* base, size_t off, int f32) {
+  return f32 ? (double)reinterpret_cast<const float*>(base)[off] : base[off];
 }
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -749,7 +762,7 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // Block = (run of nodes of the level given by group_ptr, one 128-pattern tile).
 // Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool SS, bool JOINT = false, bool SYM = false, bool MASK = false>
+template <int Q, bool SS, bool JOINT = false, bool SYM = false, bool MASK = false, typename ST = double>
 __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : (Q > 8 ? (JOINT ? 168 : TTB_POST_LARGEQ_REGS) : 255)) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles, int fbase,
                                                               const int* __restrict__ dep) {
@@ -758,6 +771,8 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   constexpr bool EST = ss_staged<Q, SS>();   // site-specific, grid rows + branch record staged per child
   constexpr int EROWS = 2 * Q * TTB_TILE;
   static_assert(!SYM || (SS && Q <= TTB_SS_REG_MAXQ && !JOINT), "SYM is a variant of the register-resident site-specific kernels");
+  static_assert(sizeof(ST) == 8 || !JOINT, "the joint pass keeps its log-space sums in double");
+  constexpr uint32_t MSG_BYTES = Q * TTB_TILE * sizeof(ST);   // one (node, tile) message block
   using PipeT = Pipe<Q, SYM ? TTB_SS_SYM_STAGES : Pipe<Q>::STAGES>;
   PipeT pipe(smem_raw, PipeT::CB * RPC, stage_pq<Q, SS>(p.pq), stage_tu<Q, SS>(p.tu_stride));
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
@@ -781,10 +796,10 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     uint32_t bytes = 32;
     for (int b = 0; b < nch; ++b) {
       if (SS) {  // site-specific: the transition matrices are per pattern; per branch only the grid rows + record
-        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8) : (uint32_t)cols;
+        bytes += (c.src(b) >= 0) ? MSG_BYTES : (uint32_t)cols;
         if (EST) bytes += 16u + ((b == 0 || c.lo1 != c.lo0) ? (uint32_t)(EROWS * 8) : 0u);
       } else
-        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8 + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
+        bytes += (c.src(b) >= 0) ? (uint32_t)(MSG_BYTES + p.pq * 8) : (uint32_t)(cols + p.tu_stride * 8);
     }
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, bytes);
@@ -802,7 +817,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
         }
       } else if (src >= 0) {
         if (r == 0)   // the child's q rows of this tile are one contiguous block
-          tma_load_1d(pipe.rows(s) + (b * RPC) * TTB_TILE, p.S + msg_off<Q>(p, src, a0), Q * TTB_TILE * 8, bar);
+          tma_load_1d(reinterpret_cast<ST*>(pipe.rows(s)) + (b * RPC) * TTB_TILE, msg_base<ST>(p.S) + msg_off<Q>(p, src, a0), MSG_BYTES, bar);
         else if (r == 1 && !SS)
           tma_load_1d(pipe.P(s) + b * p.pq, (JOINT ? p.LP : p.P) + (size_t)c.cnode(b) * p.pq, p.pq * 8, bar);
       } else {
@@ -868,9 +883,9 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 #pragma unroll
             for (int i = 0; i < Q; ++i) sc[i] = __ldg(p.code_prof + code * Q + i);
           } else {
-            const double* rows = pipe.rows(s) + (b * RPC) * TTB_TILE + tid;
+            const ST* rows = reinterpret_cast<const ST*>(pipe.rows(s)) + (b * RPC) * TTB_TILE + tid;
 #pragma unroll
-            for (int i = 0; i < Q; ++i) sc[i] = rows[i * TTB_TILE];
+            for (int i = 0; i < Q; ++i) sc[i] = (double)rows[i * TTB_TILE];
             }
           if constexpr (EST) {
             const double2 rec = reinterpret_cast<const double2*>(pipe.TU(s))[b];
@@ -884,11 +899,11 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 #pragma unroll
           for (int j = 0; j < Q; ++j) U[j] = tu[j];
         } else {
-          const double* rows = pipe.rows(s) + (b * RPC) * TTB_TILE + tid;
+          const ST* rows = reinterpret_cast<const ST*>(pipe.rows(s)) + (b * RPC) * TTB_TILE + tid;
           const double* Pc = pipe.P(s) + b * p.pq;
           double sc[Q];
 #pragma unroll
-          for (int i = 0; i < Q; ++i) sc[i] = rows[i * TTB_TILE];
+          for (int i = 0; i < Q; ++i) sc[i] = (double)rows[i * TTB_TILE];
           if constexpr (JOINT) {
             // max-plus "matvec" with back-pointers: Lx_c[j] = max_i (logP[i][j] + msg_c[i]), first maximum
             uint8_t* cx = p.Cx + ((size_t)c.src(b) * p.tiles + (size_t)tile) * (size_t)(Q * TTB_TILE) + tid;
@@ -939,18 +954,18 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     cur.advance();
     if (JOINT) {
       if (act && (c.flags & 2)) {
-        double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
+        ST* __restrict__ so = msg_base<ST>(p.S) + msg_off<Q>(p, c.out, a);
 #pragma unroll
-        for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j];
+        for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = (ST)X[j];
       }
     } else if (act && (c.flags & 2)) {
       double Z = X[0];
 #pragma unroll
       for (int j = 1; j < Q; ++j) Z += X[j];
       const double inv = 1.0 / Z;
-      double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
+      ST* __restrict__ so = msg_base<ST>(p.S) + msg_off<Q>(p, c.out, a);
 #pragma unroll
-      for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j] * inv;
+      for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = (ST)(X[j] * inv);
       if (scale) Facc -= scale * (256.0 * 0.693147180559945309417232121458);
       if (Z < 1e-150 || Z > 1e150) {
         Facc += log(Z);
@@ -970,7 +985,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 // Postorder level 1: every child is a tip, so there is nothing to stream in but one code byte
 // per (tip, pattern); the kernel is a pure write stream of q doubles per (node, pattern).
 // Block = (run of nodes, tile); one thread per pattern, tip tables read through L1.
-template <int Q, bool JOINT = false>
+template <int Q, bool JOINT = false, typename ST = double>
 __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                                    const int* __restrict__ group_ptr, int tiles, int fbase) {
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
@@ -1032,18 +1047,18 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
     }
     if (JOINT) {
       if (c.flags & 2) {
-        double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
+        ST* __restrict__ so = msg_base<ST>(p.S) + msg_off<Q>(p, c.out, a);
 #pragma unroll
-        for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j];
+        for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = (ST)X[j];
       }
     } else if (c.flags & 2) {
       double Z = X[0];
 #pragma unroll
       for (int j = 1; j < Q; ++j) Z += X[j];
       const double inv = 1.0 / Z;
-      double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
+      ST* __restrict__ so = msg_base<ST>(p.S) + msg_off<Q>(p, c.out, a);
 #pragma unroll
-      for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = X[j] * inv;
+      for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = (ST)(X[j] * inv);
       if (scale) Facc -= scale * (256.0 * 0.693147180559945309417232121458);
       if (Z < 1e-150 || Z > 1e150) {
         Facc += log(Z);
@@ -1077,19 +1092,19 @@ static __global__ void __launch_bounds__(TTB_BLOCK) fsum_kernel(TtbDev p) {
 // A5': root.  Reference: total_LH_and_root_sequence, treeanc.py:814-838.
 //   profile_r = normalize(Pi * S_r);  LH_a = F_r + log Z_r;  partial sums of LH_a * m_a.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool SS>
+template <int Q, bool SS, typename ST = double>
 __global__ void __launch_bounds__(TTB_BLOCK) root_kernel(TtbDev p, int lh_only) {
   __shared__ double sred[TTB_BLOCK / 32];
   const long long a = (long long)blockIdx.x * TTB_BLOCK + threadIdx.x;
   double contrib = 0.0;
   if (a < p.Lp) {
     const int slot = p.int_slot[0];
-    const double* __restrict__ s = p.S + msg_off<Q>(p, slot, a);
+    const ST* __restrict__ s = msg_base<ST>(p.S) + msg_off<Q>(p, slot, a);
     double R[Q];
     double Z = 0.0;
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-      R[j] = (SS ? p.ss_Pi[(size_t)j * p.ld + a] : p.Pi[j]) * s[j * TTB_TILE];   // Pi.T at the root, treeanc.py:817-820
+      R[j] = (SS ? p.ss_Pi[(size_t)j * p.ld + a] : p.Pi[j]) * (double)s[j * TTB_TILE];   // Pi.T at the root, treeanc.py:817-820
       Z += R[j];
     }
     double F = 0.0;   // fixed summation order (fsum_kernel lanes, then here): deterministic
@@ -1100,11 +1115,11 @@ __global__ void __launch_bounds__(TTB_BLOCK) root_kernel(TtbDev p, int lh_only) 
     contrib = lh * p.mult[a];
     if (!lh_only) {
       const double inv = 1.0 / Z;
-      double* __restrict__ m = p.M + msg_off<Q>(p, slot, a);
+      ST* __restrict__ m = msg_base<ST>(p.M) + msg_off<Q>(p, slot, a);
 #pragma unroll
       for (int j = 0; j < Q; ++j) {
         R[j] *= inv;
-        m[j * TTB_TILE] = R[j];
+        m[j * TTB_TILE] = (ST)R[j];
       }
       int best = 0;
       double bv = R[0];
@@ -1342,13 +1357,15 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // Tips take part only with TIPS (reconstruct_tip_states).
 // Stage rows: [0, Q) parent profile, child b -> rows [Q + b*Q, Q + (b+1)*Q) = S_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool TIPS, bool SS, bool SYM = false, bool MASK = false>
+template <int Q, bool TIPS, bool SS, bool SYM = false, bool MASK = false, typename ST = double>
 __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : (Q > 8 ? 168 : 255)) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff,
                                                              const int* __restrict__ dep) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool EST = ss_staged<Q, SS>();
   constexpr int EROWS = 2 * Q * TTB_TILE;
+  static_assert(sizeof(ST) == 8 || Q <= 8, "float message storage: small alphabets only (the q >= 20 kernel parks doubles in its stage)");
+  constexpr uint32_t MSG_BYTES = Q * TTB_TILE * sizeof(ST);   // one (node, tile) message block
   using PipeT = Pipe<Q, SYM ? TTB_SS_SYM_STAGES : Pipe<Q>::STAGES>;
   PipeT pipe(smem_raw, Q + PipeT::CB * Q, stage_pq<Q, SS>(p.pq), stage_tu<Q, SS>(p.tu_stride));
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
@@ -1370,13 +1387,13 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     uint64_t* bar = pipe.full + s;
     const int nch = c.nch();
     const bool first = c.flags & 1;
-    uint32_t bytes = 32 + (first ? (uint32_t)(Q * TTB_TILE * 8) : 0u);
+    uint32_t bytes = 32 + (first ? MSG_BYTES : 0u);
     for (int b = 0; b < nch; ++b) {
       if (SS) {
-        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8 + cols) : (uint32_t)(2 * cols);
+        bytes += (c.src(b) >= 0) ? (uint32_t)(MSG_BYTES + cols) : (uint32_t)(2 * cols);
         if (EST) bytes += 16u + ((b == 0 || c.lo1 != c.lo0) ? (uint32_t)(EROWS * 8) : 0u);
       } else
-        bytes += (c.src(b) >= 0) ? (uint32_t)(Q * TTB_TILE * 8 + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
+        bytes += (c.src(b) >= 0) ? (uint32_t)(MSG_BYTES + cols + p.pq * 8) : (uint32_t)(2 * cols + p.pq * 8 + p.tu_stride * 8);
     }
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, bytes);
@@ -1384,7 +1401,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     }
     __syncwarp();
     if (first && lane == 31)   // the parent's profile tile: one contiguous q KB block
-      tma_load_1d(pipe.rows(s), p.M + msg_off<Q>(p, c.out, a0), Q * TTB_TILE * 8, bar);
+      tma_load_1d(pipe.rows(s), msg_base<ST>(p.M) + msg_off<Q>(p, c.out, a0), MSG_BYTES, bar);
     // jobs of child b: 0 profile block / codes | 1 old states / tip table | 2 tip old states | 3 exp(Qt)
     for (int job = lane; job < nch * 4; job += 32) {
       const int b = job >> 2, r = job & 3;
@@ -1399,7 +1416,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
         }
       } else if (src >= 0) {
         if (r == 0)
-          tma_load_1d(pipe.rows(s) + (Q + b * Q) * TTB_TILE, p.S + msg_off<Q>(p, src, a0), Q * TTB_TILE * 8, bar);
+          tma_load_1d(reinterpret_cast<ST*>(pipe.rows(s)) + (Q + b * Q) * TTB_TILE, msg_base<ST>(p.S) + msg_off<Q>(p, src, a0), MSG_BYTES, bar);
         else if (r == 1)
           tma_load_1d(pipe.oidx(s) + b * TTB_TILE, p.idx + (size_t)src * p.ld + a0, cols, bar);
       } else if (TIPS) {
@@ -1448,23 +1465,23 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     const int nch = c.nch();
     if (act) {
       if (c.flags & 1) {
-        const double* m = pipe.rows(s) + tid;
+        const ST* m = reinterpret_cast<const ST*>(pipe.rows(s)) + tid;
 #pragma unroll
-        for (int j = 0; j < Q; ++j) Mp[j] = at_least(m[j * TTB_TILE], TTB_TINY);
+        for (int j = 0; j < Q; ++j) Mp[j] = at_least((double)m[j * TTB_TILE], TTB_TINY);
       }
 #pragma unroll
       for (int b = 0; b < Pipe<Q>::CB; ++b) {
         if (b >= nch) break;
         const int src = c.src(b);
         const double* Pc = pipe.P(s) + b * p.pq;
-        double* __restrict__ out;
+        ST* __restrict__ out;
         uint8_t* ip;
         if (TIPS && src < 0) {
           const int row = -1 - src;
-          out = p.Mtip + msg_off<Q>(p, row, a);
+          out = msg_base<ST>(p.Mtip) + msg_off<Q>(p, row, a);
           ip = p.idxtip + (size_t)row * p.ld + a;
         } else {
-          out = p.M + msg_off<Q>(p, src, a);
+          out = msg_base<ST>(p.M) + msg_off<Q>(p, src, a);
           ip = p.idx + (size_t)src * p.ld + a;
         }
         int best = 0;
@@ -1478,9 +1495,9 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 #pragma unroll
             for (int j = 0; j < Q; ++j) Sc[j] = __ldg(p.code_prof + code * Q + j);
           } else {
-            const double* rows = pipe.rows(s) + (Q + b * Q) * TTB_TILE + tid;
+            const ST* rows = reinterpret_cast<const ST*>(pipe.rows(s)) + (Q + b * Q) * TTB_TILE + tid;
 #pragma unroll
-            for (int i = 0; i < Q; ++i) Sc[i] = rows[i * TTB_TILE];
+            for (int i = 0; i < Q; ++i) Sc[i] = (double)rows[i * TTB_TILE];
           }
           if constexpr (EST) {
             const double2 rec = reinterpret_cast<const double2*>(pipe.TU(s))[b];
@@ -1505,7 +1522,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 #pragma unroll
           for (int i = 0; i < Q; ++i) {
             const double x = msg[i] * inv;
-            out[i * TTB_TILE] = x;
+            out[i * TTB_TILE] = (ST)x;
             if (x > bv) { bv = x; best = i; }
           }
         } else if constexpr (Q <= 8) {
@@ -1520,9 +1537,9 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
               Sc[j] = __ldg(p.code_prof + code * Q + j);
             }
           } else {
-            const double* rows = pipe.rows(s) + (Q + b * Q) * TTB_TILE + tid;
+            const ST* rows = reinterpret_cast<const ST*>(pipe.rows(s)) + (Q + b * Q) * TTB_TILE + tid;
 #pragma unroll
-            for (int i = 0; i < Q; ++i) Sc[i] = rows[i * TTB_TILE];
+            for (int i = 0; i < Q; ++i) Sc[i] = (double)rows[i * TTB_TILE];
 #pragma unroll
             for (int j = 0; j < Q; ++j) U[j] = Sc[0] * Pc[j];
 #pragma unroll
@@ -1550,7 +1567,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
 #pragma unroll
           for (int i = 0; i < Q; ++i) {
             const double x = prof[i] * inv;
-            out[i * TTB_TILE] = x;
+            out[i * TTB_TILE] = (ST)x;
             if (x > bv) { bv = x; best = i; }
           }
         } else {
@@ -1602,7 +1619,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
           double bv = -1.0;
           for (int i = 0; i < Q; ++i) {
             const double x = col[i * TTB_TILE] * inv;
-            out[i * TTB_TILE] = x;
+            out[i * TTB_TILE] = (ST)x;
             if (x > bv) { bv = x; best = i; }
           }
         }
@@ -1648,13 +1665,13 @@ __global__ void __launch_bounds__(TTB_BLOCK) sample_states_kernel(TtbDev p, cons
   unsigned int changed = 0;
   if (a < p.Lp) {
     const double* m;
-    size_t at;
+    size_t at, mo;
     if (row >= 0) {
-      m = p.Mtip + msg_off<Q>(p, row, a);
+      m = p.Mtip; mo = msg_off<Q>(p, row, a);
       at = (size_t)row * p.ld + a;
     } else {
       const int slot = p.int_slot[node];
-      m = p.M + msg_off<Q>(p, slot, a);
+      m = p.M; mo = msg_off<Q>(p, slot, a);
       at = (size_t)slot * p.ld + a;
     }
     const double x = u[(size_t)blockIdx.y * p.Lp + a];
@@ -1663,7 +1680,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) sample_states_kernel(TtbDev p, cons
     bool found = false;
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
-      cum += m[i * TTB_TILE];          // sequential like numpy's cumsum
+      cum += msg_ld(m, mo + (size_t)i * TTB_TILE, p.f32);          // sequential like numpy's cumsum
       if (!found && cum >= x) { best = i; found = true; }
     }
     if (row >= 0) {
@@ -1768,9 +1785,9 @@ __device__ __forceinline__ void node_subtree(const TtbDev& p, int n, long long a
 #pragma unroll
     for (int i = 0; i < Q; ++i) Sc[i] = p.code_prof[code * Q + i];
   } else {
-    const double* s = p.S + msg_off<Q>(p, p.int_slot[n], a);
+    const size_t so = msg_off<Q>(p, p.int_slot[n], a);
 #pragma unroll
-    for (int i = 0; i < Q; ++i) Sc[i] = s[i * TTB_TILE];
+    for (int i = 0; i < Q; ++i) Sc[i] = msg_ld(p.S, so + (size_t)i * TTB_TILE, p.f32);
   }
 }
 
@@ -1799,9 +1816,9 @@ __device__ __forceinline__ void branch_profiles(const TtbDev& p, int n, int kind
   }
   const int up = p.parent[n];
   double Mp[Q], U[Q];
-  const double* m = p.M + msg_off<Q>(p, p.int_slot[up], a);
+  const size_t mo = msg_off<Q>(p, p.int_slot[up], a);
 #pragma unroll
-  for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, m[j * TTB_TILE]);
+  for (int j = 0; j < Q; ++j) Mp[j] = fmax(TTB_TINY, msg_ld(p.M, mo + (size_t)j * TTB_TILE, p.f32));
   if constexpr (SS) {
     const SiteModel<Q> sm(p, a);
     double e[Q];
@@ -1840,9 +1857,10 @@ __global__ void __launch_bounds__(TTB_BLOCK) fetch_node_kernel(TtbDev p, int nod
     }
   } else {
     const int row = p.tip_row[node];
-    const double* m = (row >= 0) ? p.Mtip + msg_off<Q>(p, row, a) : p.M + msg_off<Q>(p, p.int_slot[node], a);
+    const double* m = (row >= 0) ? p.Mtip : p.M;
+    const size_t mo = (row >= 0) ? msg_off<Q>(p, row, a) : msg_off<Q>(p, p.int_slot[node], a);
 #pragma unroll
-    for (int j = 0; j < Q; ++j) x[j] = m[j * TTB_TILE];
+    for (int j = 0; j < Q; ++j) x[j] = msg_ld(m, mo + (size_t)j * TTB_TILE, p.f32);
   }
 #pragma unroll
   for (int j = 0; j < Q; ++j) out[(size_t)a * Q + j] = x[j];

@@ -36,6 +36,7 @@ void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t 
 }
 
 constexpr bool HAS_SS = (Q <= 8);   // site-specific models: nucleotide-sized alphabets only
+constexpr bool HAS_F32 = (Q <= 8);  // float message storage (ttb_set_message_storage): the HBM-bound alphabet sizes
 
 template <bool SS>
 int prepare_t(const TtbDev& d) {
@@ -53,6 +54,16 @@ int prepare_t(const TtbDev& d) {
     if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, true, true))) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, true, true))) != cudaSuccess) return (int)e;
   }
+  if constexpr (HAS_F32) {   // float message storage: same stages (the rows just hold floats)
+    if ((e = cudaFuncSetAttribute(post_level_kernel<Q, SS, false, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, SS))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, SS, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, SS, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
+    if constexpr (SS && HAS_SYM) {
+      if ((e = cudaFuncSetAttribute(post_level_kernel<Q, true, false, true, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, true, true))) != cudaSuccess) return (int)e;
+      if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, true, true, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, true, true))) != cudaSuccess) return (int)e;
+      if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, true, true, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, true, true))) != cudaSuccess) return (int)e;
+    }
+  }
   return 0;
 }
 
@@ -64,7 +75,7 @@ int prepare_q(const TtbDev& d) {
   return 0;
 }
 
-template <bool SS, bool SYM = false, bool MASK = false>
+template <bool SS, bool SYM = false, bool MASK = false, typename ST = double>
 int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* pk) {
   const TtbDev& d = pl.d;
   const int tiles = pl.tiles;
@@ -83,7 +94,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   if (!SS) {
     // level 1 (all children are tips) is a pure write stream: dedicated kernel, no pipeline
     const TtbLevelLaunch& L = pl.post_levels[0];
-    launch_pdl(post_leaf_level_kernel<Q>, (unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s, d, pl.d_post_chunks,
+    launch_pdl(post_leaf_level_kernel<Q, false, ST>, (unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s, d, pl.d_post_chunks,
                pl.d_post_group_ptr + L.group_off, tiles, 0);
     ++nk;
     l0 = 1;
@@ -91,14 +102,14 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   int fbase = l0 ? pl.post_levels[0].n_groups : 0;
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
-    launch_pdl(post_level_kernel<Q, SS, false, SYM, MASK>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d, pl.d_post_chunks,
+    launch_pdl(post_level_kernel<Q, SS, false, SYM, MASK, ST>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d, pl.d_post_chunks,
                pl.d_post_group_ptr + L.group_off, tiles, fbase, L.dep ? pl.d_post_dep : nullptr);
     fbase += L.n_groups;
     ++nk;
   }
   if (ev) { cudaEventRecord(ev[2], s); pk[1] = nk - pk[0]; }
   fsum_kernel<<<dim3(tiles, TTB_FLANES), TTB_BLOCK, 0, s>>>(d);
-  root_kernel<Q, SS><<<tiles, TTB_BLOCK, 0, s>>>(d, pl.lh_only ? 1 : 0);
+  root_kernel<Q, SS, ST><<<tiles, TTB_BLOCK, 0, s>>>(d, pl.lh_only ? 1 : 0);
   nk += 2;
   if (!pl.lh_only) {
     zero_slots_kernel<<<4, 256, 0, s>>>(d);
@@ -111,10 +122,10 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
       const TtbLevelLaunch& L = pl.pre_levels[l];
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
       if (pl.tips)
-        launch_pdl(pre_level_kernel<Q, true, SS, SYM, MASK>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
+        launch_pdl(pre_level_kernel<Q, true, SS, SYM, MASK, ST>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
                    pl.count_diff, L.dep ? pl.d_pre_dep : nullptr);
       else
-        launch_pdl(pre_level_kernel<Q, false, SS, SYM, MASK>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
+        launch_pdl(pre_level_kernel<Q, false, SS, SYM, MASK, ST>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
                    pl.count_diff, L.dep ? pl.d_pre_dep : nullptr);
       ++nk;
     }
@@ -132,6 +143,15 @@ int enqueue_pass_q(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
       if (pl.d.site_specific) return enqueue_pass_t<true, false, true>(pl, s, ev, pk);
     }
     return enqueue_pass_t<false, false, true>(pl, s, ev, pk);
+  }
+  if constexpr (HAS_F32) {
+    if (pl.d.f32) {      // float message storage (not combined with masks: ttb_marginal refuses that)
+      if constexpr (HAS_SYM) {
+        if (pl.d.site_specific && pl.d.ss_sym) return enqueue_pass_t<true, true, false, float>(pl, s, ev, pk);
+      }
+      if (pl.d.site_specific) return enqueue_pass_t<true, false, false, float>(pl, s, ev, pk);
+      return enqueue_pass_t<false, false, false, float>(pl, s, ev, pk);
+    }
   }
   if constexpr (HAS_SYM) {
     if (pl.d.site_specific && pl.d.ss_sym) return enqueue_pass_t<true, true>(pl, s, ev, pk);

@@ -58,6 +58,13 @@ class Engine(object):
     def set_stream(self, cuda_stream):
         _lib.check(self.lib.ttb_set_stream(self.h, ctypes.c_void_p(int(cuda_stream) if cuda_stream else None)))
 
+    def set_message_storage(self, dtype):
+        """'f64' (default, the reference's precision) or 'f32': S / M stored as float, arithmetic in double."""
+        code = {'f64': 0, 'float64': 0, 'f32': 1, 'float32': 1}.get(str(dtype))
+        if code is None:
+            raise ValueError("message storage must be 'f64' or 'f32'")
+        _lib.check(self.lib.ttb_set_message_storage(self.h, code))
+
     def set_tree(self, parent, child_ptr, child_idx, tip_row):
         parent, child_ptr, child_idx, tip_row = _i32(parent), _i32(child_ptr), _i32(child_idx), _i32(tip_row)
         _lib.check(self.lib.ttb_set_tree(self.h, parent.shape[0], _ip(parent), _ip(child_ptr), _ip(child_idx), _ip(tip_row)))
