@@ -138,6 +138,7 @@ struct ttb_engine {
   double ss_tmax = 0.0;
   bool ss_interp_dirty = true;
   // state
+  DBuf<double> d_leaf_pairs;   // cherry tables of postorder level 1 (leaf_pair_table_kernel)
   DBuf<double> d_LP, d_TL, d_Fred, d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
   DBuf<uint8_t> d_TC, d_Cx, d_idx, d_idxtip, d_bstage, d_mut_state, d_aln, d_colstat, d_lut, d_constl;
   DBuf<long long> d_firstpos;
@@ -172,6 +173,10 @@ struct ttb_engine {
   long long launches = 0;
 
   int tiles() const { return (int)((Lp + TTB_BLOCK - 1) / TTB_BLOCK); }
+  // chunks of postorder level 1 (they come first in the schedule)
+  int n_leaf_chunks() const {
+    return post.level_node_begin.size() > 1 ? post.node_chunk[post.level_node_begin[1]] : 0;
+  }
   // doubles to allocate for a message array of n elements in the current storage type
   size_t msg_doubles(size_t n) const { return f32 ? (n + 1) / 2 : n; }
 
@@ -427,6 +432,8 @@ int enqueue_pass(ttb_handle h, int flags, int count_diff, cudaStream_t s, int* n
   pl.d_post_chunks = h->post.d_chunks.p;
   pl.d_post_group_ptr = h->post.d_group_ptr.p;
   pl.d_post_dep = h->post.d_dep.p;
+  pl.d_leaf_pairs = h->d_leaf_pairs.p;
+  pl.n_leaf_chunks = h->n_leaf_chunks();
   pl.d_post_node_chunk = h->post.d_node_chunk.p;
   pl.n_post_leaf_nodes = h->post.level_node_begin.size() > 1 ? h->post.level_node_begin[1] : 0;
   pl.post_levels = h->post.launches.data();
@@ -451,6 +458,8 @@ void fill_plan(ttb_handle h, TtbPassPlan& pl, bool tips, int count_diff) {
   pl.d_post_chunks = h->post.d_chunks.p;
   pl.d_post_group_ptr = h->post.d_group_ptr.p;
   pl.d_post_dep = h->post.d_dep.p;
+  pl.d_leaf_pairs = h->d_leaf_pairs.p;
+  pl.n_leaf_chunks = h->n_leaf_chunks();
   pl.d_post_node_chunk = h->post.d_node_chunk.p;
   pl.n_post_leaf_nodes = h->post.level_node_begin.size() > 1 ? h->post.level_node_begin[1] : 0;
   pl.post_levels = h->post.launches.data();
@@ -479,6 +488,15 @@ int ensure_state(ttb_handle h, bool tips) {
     h->sched_tiles = h->tiles();
     h->sched_ss = ss_mode;
     h->drop_graphs();
+  }
+  // cherry tables (nucleotide-sized alphabets, single model): n_codes^2 entries per level-1 chunk, at most 2 GB
+  {
+    const size_t per = (size_t)h->n_codes * h->n_codes * TTB_PAIR_STRIDE(q);
+    const size_t want = (q <= 8 && !h->site_specific && per * 8 <= 32 * 1024) ? (size_t)h->n_leaf_chunks() * per : 0;
+    const bool on = want && want * 8 <= ((size_t)2 << 30) && !getenv("TTB_NO_PAIR_TABLES");
+    const double* before = h->d_leaf_pairs.p;
+    if ((rc = h->d_leaf_pairs.alloc(on ? want : 0))) return rc;
+    if (before != h->d_leaf_pairs.p) h->drop_graphs();
   }
   if ((rc = h->d_F.alloc((size_t)h->n_fgroups * ld))) return rc;
   if ((rc = h->d_Fred.alloc((size_t)TTB_FLANES * ld))) return rc;

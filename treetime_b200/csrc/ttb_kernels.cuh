@@ -982,12 +982,49 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   if (!JOINT && act) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc + log(Zprod);
 }
 
+// Cherry tables for postorder level 1.  The subtree profile of a node whose two children are tips depends on the
+// pattern only through the pair of tip characters (c0, c1):
+//   S[c0][c1][j] = TU_0[c0][j] TU_1[c1][j] / Z,   Z = sum_j TU_0[c0][j] TU_1[c1][j]
+// -- n_codes^2 entries per node (324 for nucleotides) against tens of thousands of patterns.  One block per level-1
+// chunk forms the table once per pass (same operations as the per-pattern path, so S is bit-identical; log Z is taken
+// per entry); the level kernel then only looks entries up.  Entry = TTB_PAIR_STRIDE(Q) doubles: S[0..Q), log Z.
+// Chunks that are not a complete two-tip node (polytomies of tips) keep the per-pattern path.
+#define TTB_PAIR_STRIDE(Q) (((Q) + 2) / 2 * 2)
+template <int Q>
+__global__ void leaf_pair_table_kernel(TtbDev p, const TtbChunk* __restrict__ chunks, double* __restrict__ table) {
+  const Chunk c = load_chunk_global(chunks + blockIdx.x);
+  if ((c.flags & 3) != 3 || c.nch() != 2) return;
+  const int nc = p.n_codes;
+  const double* t0 = p.TU + (size_t)(-1 - c.src0) * p.tu_stride;
+  const double* t1 = p.TU + (size_t)(-1 - c.src1) * p.tu_stride;
+  double* out = table + (size_t)blockIdx.x * nc * nc * TTB_PAIR_STRIDE(Q);
+  for (int e = threadIdx.x; e < nc * nc; e += blockDim.x) {
+    const int c0 = e / nc, c1 = e % nc;
+    double X[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) X[j] = 1.0;
+#pragma unroll
+    for (int j = 0; j < Q; ++j) X[j] *= __ldg(t0 + c0 * Q + j);
+#pragma unroll
+    for (int j = 0; j < Q; ++j) X[j] *= __ldg(t1 + c1 * Q + j);
+    double Z = X[0];
+#pragma unroll
+    for (int j = 1; j < Q; ++j) Z += X[j];
+    const double inv = 1.0 / Z;
+#pragma unroll
+    for (int j = 0; j < Q; ++j) out[(size_t)e * TTB_PAIR_STRIDE(Q) + j] = X[j] * inv;
+    out[(size_t)e * TTB_PAIR_STRIDE(Q) + Q] = log(Z);
+  }
+}
+
 // Postorder level 1: every child is a tip, so there is nothing to stream in but one code byte
 // per (tip, pattern); the kernel is a pure write stream of q doubles per (node, pattern).
-// Block = (run of nodes, tile); one thread per pattern, tip tables read through L1.
+// Block = (run of nodes, tile); one thread per pattern; two-tip nodes through the cherry tables above
+// (pair_table != null), everything else from the tip tables through L1.
 template <int Q, bool JOINT = false, typename ST = double>
 __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
-                                                                   const int* __restrict__ group_ptr, int tiles, int fbase) {
+                                                                   const int* __restrict__ group_ptr, int tiles, int fbase,
+                                                                   const double* __restrict__ pair_table) {
   const int g = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const long long a = (long long)tile * TTB_TILE + threadIdx.x;
   pdl_launch_dependents();
@@ -1014,13 +1051,32 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
       for (int b = 0; b < Pipe<Q>::CB; ++b)
         if (b < cn.nch()) ncode[b] = __ldg(p.codes + (size_t)(-1 - cn.src(b)) * p.ld + a);
     }
+    const int nch = c.nch();
+    if constexpr (!JOINT && Q <= 8) {
+      if (pair_table && (c.flags & 3) == 3 && nch == 2) {     // a complete two-tip node: look the result up
+        const double* e = pair_table + ((size_t)k * p.n_codes * p.n_codes + (size_t)code[0] * p.n_codes + code[1]) * TTB_PAIR_STRIDE(Q);
+        ST* __restrict__ so = msg_base<ST>(p.S) + msg_off<Q>(p, c.out, a);
+        double v[TTB_PAIR_STRIDE(Q)];
+#pragma unroll
+        for (int j = 0; j < TTB_PAIR_STRIDE(Q); j += 2) {       // 16-byte loads: entries are 16-byte aligned
+          const double2 t = __ldg(reinterpret_cast<const double2*>(e + j));
+          v[j] = t.x; v[j + 1] = t.y;
+        }
+#pragma unroll
+        for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = (ST)v[j];
+        Facc += v[Q];
+        c = cn;
+#pragma unroll
+        for (int b = 0; b < Pipe<Q>::CB; ++b) code[b] = ncode[b];
+        continue;
+      }
+    }
     if (c.flags & 1) {
 #pragma unroll
       for (int j = 0; j < Q; ++j) X[j] = JOINT ? 0.0 : 1.0;
       scale = 0;
       seen = 0;
     }
-    const int nch = c.nch();
 #pragma unroll
     for (int b = 0; b < Pipe<Q>::CB; ++b) {
       if (b >= nch) break;

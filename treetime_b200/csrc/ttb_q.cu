@@ -94,8 +94,16 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   if (!SS) {
     // level 1 (all children are tips) is a pure write stream: dedicated kernel, no pipeline
     const TtbLevelLaunch& L = pl.post_levels[0];
+    const double* pairs = nullptr;
+    if constexpr (Q <= 8 && !MASK) {
+      if (pl.d_leaf_pairs && pl.n_leaf_chunks > 0) {      // cherry tables: one block per level-1 chunk
+        leaf_pair_table_kernel<Q><<<pl.n_leaf_chunks, 128, 0, s>>>(d, pl.d_post_chunks, pl.d_leaf_pairs);
+        pairs = pl.d_leaf_pairs;
+        ++nk;
+      }
+    }
     launch_pdl(post_leaf_level_kernel<Q, false, ST>, (unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s, d, pl.d_post_chunks,
-               pl.d_post_group_ptr + L.group_off, tiles, 0);
+               pl.d_post_group_ptr + L.group_off, tiles, 0, pairs);
     ++nk;
     l0 = 1;
   }
@@ -177,7 +185,7 @@ int enqueue_joint_q(const TtbPassPlan& pl, cudaStream_t s, int trace) {
   if (pl.n_post_leaf_nodes) {
     const TtbLevelLaunch& L = pl.post_levels[0];
     post_leaf_level_kernel<Q, true><<<(unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s>>>(d, pl.d_post_chunks,
-                                                                                                pl.d_post_group_ptr + L.group_off, tiles, 0);
+                                                                                                pl.d_post_group_ptr + L.group_off, tiles, 0, nullptr);
     ++nk;
     l0 = 1;
   }

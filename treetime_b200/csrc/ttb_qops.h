@@ -19,6 +19,8 @@ struct TtbPassPlan {
   const TtbChunk* d_post_chunks;
   const int* d_post_node_chunk;    // first chunk of every scheduled postorder node (+ sentinel)
   int n_post_leaf_nodes;           // nodes of postorder level 1 (all children are tips)
+  double* d_leaf_pairs;            // cherry tables of postorder level 1 ([n_leaf_chunks][n_codes^2][stride]) or null
+  int n_leaf_chunks;               // chunks of postorder level 1
   const int* d_post_group_ptr;
   const int* d_post_dep;           // per chunk: global index of the chunk that wrote what it reads (merged-level launches), -1 = none
   const TtbLevelLaunch* post_levels;
