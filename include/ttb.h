@@ -237,6 +237,26 @@ int ttb_branch_objective(ttb_handle h, int32_t n_eval, const int32_t* nodes, con
 int ttb_branch_hamming(ttb_handle h, int32_t n_eval, const int32_t* nodes, const int32_t* kind,
                        double* num, double* den);
 
+/* A8 on the device: GTR.optimal_t_compressed(profiles=True) (gtr.py:816-920) for n branches at once -- scipy's
+ * minimize_scalar(method='brent', bracket=(xa, xb, xc), tol) on cost(s) = -prob_t_profiles(.., s^2, return_log=True)
+ * + exp(s^4 / 10000) (gtr.py:876-891) -- as a lock-step state machine whose state stays on the device:
+ *   ttb_brent_begin   bracket in s = sqrt(t) per branch (the reference: xa = -sqrt(MAX_BRANCH_LENGTH), xb = sqrt(hamming
+ *                     distance), xc = +sqrt(MAX_BRANCH_LENGTH)), tolerance, iteration cap (scipy: 500);
+ *   ttb_brent_eval    enqueue the objective of every unfinished branch at its current trial length (one launch over this
+ *                     shard's patterns; partial sums when the patterns are sharded);
+ *   ttb_brent_f_device_ptr   the n objective values on the device, for an all-reduce between eval and update;
+ *   ttb_brent_update  enqueue the state update + next proposal; with sync != 0 it waits and returns the number of branches
+ *                     still active (the first three updates consume the bracket points; an invalid bracket fails with
+ *                     scipy's message);
+ *   ttb_brent_result  optimum s (t = s^2), cost there, iterations and function evaluations per branch.
+ * Uses the messages of the last ttb_marginal.  All calls but update(sync) / result are asynchronous. */
+int ttb_brent_begin(ttb_handle h, int32_t n, const int32_t* nodes, const int32_t* kind, const double* xa, const double* xb,
+                    const double* xc, double tol, int32_t maxiter);
+int ttb_brent_eval(ttb_handle h);
+int ttb_brent_f_device_ptr(ttb_handle h, void** dptr, int32_t* n);
+int ttb_brent_update(ttb_handle h, int32_t sync, int32_t* n_active);
+int ttb_brent_result(ttb_handle h, double* x, double* fun, int32_t* nit, int32_t* nfev);
+
 /* Expected substitution statistics of infer_gtr(marginal=True) (treeanc.py:1556-1572):
  * n_ij[q][q] and T_i[q] summed over this shard's patterns and all branches. */
 int ttb_mutation_counts(ttb_handle h, double* n_ij, double* T_i);

@@ -662,3 +662,52 @@ def test_float_message_storage(kind):
     assert np.array_equal(prof64, eng.node_array(3, 2) if flat['tip_row'][3] < 0 or rt else eng.node_array(0, 2))
     print('float storage (%s): rel dLH %.1e, max|dprofile| %.1e, %d of %d states differ (all within 1e-6 of a tie)'
           % (kind, rel, worst, flips, idx32.size))
+
+
+@pytest.mark.parametrize('kind', ['nuc', 'site_specific'])
+def test_device_brent_matches_host_lockstep(kind):
+    """ttb_brent_* (A8 on the device): the Brent state machine of scipy / treetime_b200.brent with its state on the
+    device takes the same iterates as the host lock-step version driven by ttb_branch_objective -- all branches of the
+    tree incl. the merged branch across a bifurcating root, tight and loose tolerances."""
+    from treetime_b200.brent import brent_lockstep, BracketError
+    from treetime_b200 import config as ttconf
+    if kind == 'site_specific':
+        from treetime_b200.gtr import GTRSiteSpecific
+        L, compress = 400, False
+        gtr = GTRSiteSpecific.random(L=L, alphabet='nuc', rng=np.random.default_rng(6))
+    else:
+        gtr, L, compress = util.nuc_gtr(), 1200, True
+    tree = synth.random_tree(150, seed=14, mean_bl=0.01)
+    topo, flat, g = util.make_flat(tree, gtr, L, 14, amb_frac=0.01, compress=compress)
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    n_nodes = flat['parent'].shape[0]
+    root_kids = flat['child_idx'][flat['child_ptr'][0]:flat['child_ptr'][1]]
+    fids = np.array([n for n in range(1, n_nodes) if n not in root_kids] + [int(root_kids[0])], dtype=np.int32)
+    kinds = np.zeros(fids.shape[0], dtype=np.int32); kinds[-1] = 1
+    num, den = eng.branch_hamming(fids, kinds)
+    xb = np.sqrt(1 - num / den)
+    smax = np.sqrt(ttconf.MAX_BRANCH_LENGTH)
+    n = fids.shape[0]
+    for tol in (1e-10, 1e-2):
+        calls = [0]
+
+        def neg_prob(idx, s):
+            calls[0] += 1
+            return -1.0 * eng.branch_objective(fids[idx], s ** 2, kinds[idx]) + np.exp(s ** 4 / 10000)
+        host = brent_lockstep(neg_prob, np.full(n, -smax), xb, np.full(n, smax), tol=tol)
+        launches0 = eng.launch_count()
+        dev = eng.brent_minimize(fids, kinds, np.full(n, -smax), xb, np.full(n, smax), tol)
+        assert eng.launch_count() - launches0 <= 3 * (calls[0] + 8)
+        assert dev['success'].all() and host['success'].all()
+        # the objective values differ in the last bits (other block partition of the pattern sum): same minimum to
+        # Brent's own resolution, same iteration counts almost everywhere
+        # (a minimum located from function values is only defined to ~sqrt(eps) relative)
+        assert np.allclose(dev['x'] ** 2, host['x'] ** 2, rtol=max(10 * tol, 5e-6), atol=1e-10)
+        assert np.allclose(dev['fun'], host['fun'], rtol=1e-12)
+        if tol >= 1e-6:          # below sqrt(eps) the last iterations are driven by the rounding of the function values
+            assert np.mean(dev['nit'] == host['nit']) > 0.95 and np.mean(dev['nfev'] == host['nfev']) > 0.95
+        else:
+            assert abs(np.median(dev['nit'] - host['nit'])) <= 2
+    with pytest.raises(BracketError):
+        eng.brent_minimize(fids, kinds, np.full(n, -smax), np.full(n, 2 * smax), np.full(n, smax), 1e-8)

@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(HERE, 'libttb.so')
 CSRC = os.path.join(HERE, 'csrc')
 BUILD_DIR = os.path.join(HERE, 'build')
 Q_VALUES = (2, 3, 4, 5, 6, 7, 8, 20, 21, 22)      # alphabet sizes with compiled kernels
-SOURCES = [os.path.join(CSRC, 'ttb_api.cu'), os.path.join(CSRC, 'ttb_q.cu')]
-HEADERS = [os.path.join(CSRC, 'ttb_kernels.cuh'), os.path.join(CSRC, 'ttb_qops.h'),
+SOURCES = [os.path.join(CSRC, 'ttb_api.cu'), os.path.join(CSRC, 'ttb_q.cu'), os.path.join(CSRC, 'ttb_brent.cu')]
+HEADERS = [os.path.join(CSRC, 'ttb_kernels.cuh'), os.path.join(CSRC, 'ttb_qops.h'), os.path.join(CSRC, 'ttb_brent.h'),
            os.path.join(os.path.dirname(HERE), 'include', 'ttb.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -47,6 +47,9 @@ def build(force=False, verbose=False, extra_flags=()):
     os.makedirs(BUILD_DIR, exist_ok=True)
     jobs = [([nvcc] + NVCC_FLAGS + list(extra_flags) + ['-c', os.path.join(CSRC, 'ttb_api.cu'), '-o',
                                                         os.path.join(BUILD_DIR, 'ttb_api.o')])]
+    # the Brent state machine mirrors scipy's scalar arithmetic: no fused multiply-adds
+    jobs.append([nvcc] + NVCC_FLAGS + list(extra_flags) + ['-fmad=false', '-c', os.path.join(CSRC, 'ttb_brent.cu'), '-o',
+                                                           os.path.join(BUILD_DIR, 'ttb_brent.o')])
     for q in Q_VALUES:
         jobs.append([nvcc] + NVCC_FLAGS + list(extra_flags) + ['-DTTB_Q=%d' % q, '-c', os.path.join(CSRC, 'ttb_q.cu'),
                                                                '-o', os.path.join(BUILD_DIR, 'ttb_q%d.o' % q)])
@@ -113,6 +116,11 @@ SIGNATURES = {
     'ttb_enqueue_fetch_all_seq_idx': ([_H, _c_u8_p], ctypes.c_int),
     'ttb_profile_marginal': ([_H, ctypes.c_int32, _c_dbl_p, _c_int_p], ctypes.c_int),
     'ttb_branch_objective': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p], ctypes.c_int),
+    'ttb_brent_begin': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, ctypes.c_double, ctypes.c_int32], ctypes.c_int),
+    'ttb_brent_eval': ([_H], ctypes.c_int),
+    'ttb_brent_f_device_ptr': ([_H, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32)], ctypes.c_int),
+    'ttb_brent_update': ([_H, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)], ctypes.c_int),
+    'ttb_brent_result': ([_H, _c_dbl_p, _c_dbl_p, _c_int_p, _c_int_p], ctypes.c_int),
     'ttb_branch_hamming': ([_H, ctypes.c_int32, _c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_mutation_counts': ([_H, _c_dbl_p, _c_dbl_p], ctypes.c_int),
     'ttb_mutation_counts_per_site': ([_H, _c_dbl_p, _c_dbl_p], ctypes.c_int),

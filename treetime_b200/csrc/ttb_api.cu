@@ -2,6 +2,7 @@
 // level schedules and the CUDA-graph that covers one marginal reconstruction.
 #include "../../include/ttb.h"
 #include "ttb_qops.h"
+#include "ttb_brent.h"
 
 #include <algorithm>
 #include <cmath>
@@ -138,6 +139,13 @@ struct ttb_engine {
   double ss_tmax = 0.0;
   bool ss_interp_dirty = true;
   // state
+  // device-side lock-step Brent (ttb_brent_*)
+  DBuf<double> d_brent;        // 18 state vectors + trial lengths + objective values, n_brent entries each
+  DBuf<int> d_brent_i;         // nit, nfev, flags
+  DBuf<uint8_t> d_brent_active;
+  int n_brent = 0, brent_stage = 0, brent_maxiter = 500, brent_nb = 1;
+  double brent_tol = 0.0;
+  int* h_brent_flags = nullptr;   // pinned {n_active, bracket error}
   DBuf<double> d_leaf_pairs;   // cherry tables of postorder level 1 (leaf_pair_table_kernel)
   DBuf<double> d_LP, d_TL, d_Fred, d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
   DBuf<uint8_t> d_TC, d_Cx, d_idx, d_idxtip, d_bstage, d_mut_state, d_aln, d_colstat, d_lut, d_constl;
@@ -618,6 +626,7 @@ int ttb_destroy(ttb_handle h) {
   h->d_aln.release(); h->d_colstat.release(); h->d_lut.release(); h->d_constl.release(); h->d_firstpos.release();
   h->d_seqrow.release(); h->d_flag.release();
   h->d_nd.release();
+  if (h->h_brent_flags) cudaFreeHost(h->h_brent_flags);
   if (h->h_results) cudaFreeHost(h->h_results);
   if (h->h_scratch) cudaFreeHost(h->h_scratch);
   if (h->scratch_ev) cudaEventDestroy(h->scratch_ev);
@@ -1518,6 +1527,122 @@ int ttb_branch_hamming(ttb_handle h, int32_t n_eval, const int32_t* nodes, const
     for (double m : h->h_mult) s += m;
     *den = s;
   }
+  return 0;
+}
+
+static TtbBrent brent_view(ttb_handle h) {
+  TtbBrent B;
+  double* d = h->d_brent.p;
+  const size_t n = (size_t)h->n_brent;
+  double** slots[] = {&B.xa, &B.xb, &B.xc, &B.fa, &B.fb, &B.fc, &B.x, &B.w, &B.v, &B.fx, &B.fw, &B.fv, &B.a, &B.b, &B.deltax, &B.rat, &B.u, &B.ts};
+  for (size_t k = 0; k < sizeof(slots) / sizeof(slots[0]); ++k) *slots[k] = d + k * n;
+  B.f = d + 18 * n;
+  B.nit = h->d_brent_i.p;
+  B.nfev = h->d_brent_i.p + n;
+  B.flags = h->d_brent_i.p + 2 * n;
+  B.active = h->d_brent_active.p;
+  return B;
+}
+
+int ttb_brent_begin(ttb_handle h, int32_t n, const int32_t* nodes, const int32_t* kind, const double* xa, const double* xb,
+                    const double* xc, double tol, int32_t maxiter) {
+  if (int rc = use_device(h)) return rc;
+  if (int rc = check_ready(h, true)) return rc;
+  if (n <= 0 || !nodes || !xa || !xb || !xc || !(tol > 0.0) || maxiter <= 0) return fail(TTB_EINVAL, "ttb_brent_begin: bad arguments");
+  const bool root_bif = (h->child_ptr[1] - h->child_ptr[0]) == 2;
+  for (int e = 0; e < n; ++e) {
+    if (nodes[e] <= 0 || nodes[e] >= h->n_nodes) return fail(TTB_EINVAL, "ttb_brent_begin: node id out of range (the root has no branch)");
+    if (kind && kind[e] == TTB_BRANCH_ROOT && (!root_bif || h->parent[nodes[e]] != 0))
+      return fail(TTB_EINVAL, "ttb_brent_begin: TTB_BRANCH_ROOT needs a child of a bifurcating root");
+  }
+  cudaStream_t s = h->stream;
+  int rc;
+  h->n_brent = n;
+  if ((rc = h->d_brent.alloc((size_t)19 * n))) return rc;
+  if ((rc = h->d_brent_i.alloc((size_t)2 * n + 2))) return rc;
+  if ((rc = h->d_brent_active.alloc((size_t)n))) return rc;
+  if (!h->h_brent_flags) CK(cudaMallocHost(&h->h_brent_flags, 2 * sizeof(int)));
+  if ((rc = upload(h->d_enodes, nodes, (size_t)n, s))) return rc;
+  if (kind) {
+    if ((rc = upload(h->d_ekinds, kind, (size_t)n, s))) return rc;
+  } else {
+    h->d_ekinds.release();
+  }
+  TtbBrent B = brent_view(h);
+  CK(cudaMemcpyAsync(B.xa, xa, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(B.xb, xb, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(B.xc, xc, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(h->d_brent_i.p, 0, h->d_brent_i.bytes(), s));
+  CK(cudaMemsetAsync(h->d_brent_active.p, 1, (size_t)n, s));
+  CK(cudaStreamSynchronize(s));      // pageable sources
+  h->brent_tol = tol;
+  h->brent_maxiter = maxiter;
+  h->brent_stage = 0;
+  int nb = (int)std::min<long long>(h->tiles(), std::max<long long>(1, ((long long)h->n_sm * 16 + n - 1) / n));
+  h->brent_nb = std::min(nb, 64);
+  if ((rc = h->d_partial.alloc((size_t)n * h->brent_nb))) return rc;
+  ttb_brent_step(B, n, -1, tol, maxiter, s);      // trial points = the first bracket point
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int ttb_brent_eval(ttb_handle h) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->n_brent || !h->d_brent.p) return fail(TTB_EINVAL, "ttb_brent_eval: call ttb_brent_begin first");
+  if (int rc = check_ready(h, true)) return rc;
+  TtbBrent B = brent_view(h);
+  ttb_qops(h->q)->branch_eval(h->dev(), h->n_brent, h->brent_nb, h->d_enodes.p, h->d_ekinds.p, B.ts, 0, h->d_partial.p,
+                              const_cast<double*>(B.f), h->stream);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int ttb_brent_f_device_ptr(ttb_handle h, void** dptr, int32_t* n) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->n_brent || !h->d_brent.p || !dptr) return fail(TTB_EINVAL, "ttb_brent_f_device_ptr: call ttb_brent_begin first");
+  *dptr = const_cast<double*>(brent_view(h).f);
+  if (n) *n = h->n_brent;
+  return 0;
+}
+
+int ttb_brent_update(ttb_handle h, int32_t sync, int32_t* n_active) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->n_brent || !h->d_brent.p) return fail(TTB_EINVAL, "ttb_brent_update: call ttb_brent_begin first");
+  TtbBrent B = brent_view(h);
+  cudaStream_t s = h->stream;
+  if (h->brent_stage >= 2) CK(cudaMemsetAsync(B.flags, 0, sizeof(int), s));    // the active count of this step (the error flag stays)
+  ttb_brent_step(B, h->n_brent, h->brent_stage, h->brent_tol, h->brent_maxiter, s);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  h->brent_stage += 1;
+  if (sync) {
+    CK(cudaMemcpyAsync(h->h_brent_flags, B.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h->brent_stage >= 3 && h->h_brent_flags[1]) {
+      return fail(TTB_EINVAL, (h->h_brent_flags[1] & 1)
+                                  ? "Bracketing values (xa, xb, xc) do not fulfill this requirement: (xa < xb) and (xb < xc)"
+                                  : "Bracketing values (xa, xb, xc) do not fulfill this requirement: (f(xb) < f(xa)) and (f(xb) < f(xc))");
+    }
+    if (n_active) *n_active = h->brent_stage >= 3 ? h->h_brent_flags[0] : h->n_brent;
+  } else if (n_active) {
+    *n_active = -1;
+  }
+  return 0;
+}
+
+int ttb_brent_result(ttb_handle h, double* x, double* fun, int32_t* nit, int32_t* nfev) {
+  if (int rc = use_device(h)) return rc;
+  if (!h->n_brent || !h->d_brent.p || h->brent_stage < 3) return fail(TTB_EINVAL, "ttb_brent_result: no finished minimisation");
+  TtbBrent B = brent_view(h);
+  const size_t n = (size_t)h->n_brent;
+  cudaStream_t s = h->stream;
+  if (x) CK(cudaMemcpyAsync(x, B.x, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (fun) CK(cudaMemcpyAsync(fun, B.fx, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (nit) CK(cudaMemcpyAsync(nit, B.nit, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (nfev) CK(cudaMemcpyAsync(nfev, B.nfev, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return 0;
 }
 

@@ -1935,6 +1935,10 @@ __global__ void __launch_bounds__(TTB_BLOCK) branch_eval_kernel(TtbDev p, const 
   __shared__ double sPt[Q * Q];
   __shared__ double sred[TTB_BLOCK / 32];
   const int e = blockIdx.x;
+  if (mode == 0 && ts[e] < 0.0) {   // device-side Brent (ttb_brent_*): this branch has converged, nothing to evaluate
+    if (threadIdx.x == 0) partial[(size_t)e * gridDim.y + blockIdx.y] = 0.0;
+    return;
+  }
   const int node = nodes[e];
   const int kind = kinds ? kinds[e] : 0;
   __shared__ double s_interp[2];   // site-specific: {lower grid index, w} of the trial length

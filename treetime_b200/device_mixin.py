@@ -546,17 +546,26 @@ class DeviceMarginalMixin(object):
             den = np.array([self.data.multiplicity(mask=self._branch_mask(topo.nodes[f], k)).sum() for f, k in zip(fids, kinds)])
         hamming = 1 - num / den
 
-        def neg_prob(idx, s):
-            f = eng.branch_objective(fids[idx], s ** 2, kinds[idx])
-            if self.comm.world_size > 1:
-                f = self.comm.allreduce_sum(f)
-            return -1.0 * f + np.exp(s ** 4 / 10000)
-
         n = fids.shape[0]
         smax = np.sqrt(ttconf.MAX_BRANCH_LENGTH)
         with np.errstate(invalid='ignore'):
             xb = np.sqrt(hamming)
-        opt = brent_lockstep(neg_prob, np.full(n, -smax), xb, np.full(n, smax), tol=tol)
+        reduce_dev = None
+        on_device = hasattr(eng, 'brent_minimize')
+        if on_device and self.comm.world_size > 1:
+            reduce_dev = getattr(self.comm, 'allreduce_sum_device', lambda e: None)(eng)
+            on_device = reduce_dev is not None
+        if on_device:
+            # the whole state machine on the device: no per-iteration host round trip (ttb_brent_*)
+            opt = eng.brent_minimize(fids, kinds, np.full(n, -smax), xb, np.full(n, smax), tol, allreduce=reduce_dev)
+        else:
+            def neg_prob(idx, s):
+                f = eng.branch_objective(fids[idx], s ** 2, kinds[idx])
+                if self.comm.world_size > 1:
+                    f = self.comm.allreduce_sum(f)
+                return -1.0 * f + np.exp(s ** 4 / 10000)
+
+            opt = brent_lockstep(neg_prob, np.full(n, -smax), xb, np.full(n, smax), tol=tol)
         new_len = opt['x'] ** 2
         if (new_len > 0.9 * ttconf.MAX_BRANCH_LENGTH).any():
             self.logger('WARNING: GTR.optimal_t_compressed -- The branch length seems to be very long!', 4, warn=True)
@@ -577,32 +586,44 @@ class DeviceMarginalMixin(object):
         """treeanc.py:1297-1360 with all branches of one sweep optimised in one batched Brent."""
         self.infer_ancestral_sequences(marginal=True, **kwargs)
         oldLH = self.sequence_LH()
-        self.logger('TreeAnc.optimize_tree_marginal: initial, LH=%1.2f, total branch_length %1.4f'
-                    % (oldLH, self.tree.total_branch_length()), 2)
+        last_tbl = 0.0
+        if self.verbose > 2:
+            last_tbl = self.tree.total_branch_length()
+            self.logger('TreeAnc.optimize_tree_marginal: initial, LH=%1.2f, total branch_length %1.4f' % (oldLH, last_tbl), 2)
         for i in range(max_iter):
             if infer_gtr:
                 self.infer_gtr(site_specific=site_specific_gtr, marginal=True, normalized_rate=True, pc=pc)
                 self.infer_ancestral_sequences(marginal=True, **kwargs)
-            old_bl = self.tree.total_branch_length()
             tol = 1e-8 + 0.01 ** (i + 1)
             topo = self._flat()
             root = self.tree.root
             root_bif = len(root.clades) == 2
-            fids, kinds = [], []
-            for n in topo.nodes[1:]:
-                if n.up is root and root_bif:
-                    continue
-                fids.append(n._fid)
-                kinds.append(0)
+            # every branch but the two below a bifurcating root, which are optimised as one merged branch (kind 1)
+            ids = np.arange(1, topo.n_nodes, dtype=np.int32)
             if root_bif:
-                fids.append(root.clades[0]._fid)
-                kinds.append(1)
+                ids = ids[topo.parent[1:] != 0]
+                fids = np.concatenate([ids, np.array([root.clades[0]._fid], dtype=np.int32)])
+                kinds = np.zeros(fids.shape[0], dtype=np.int32)
+                kinds[-1] = 1
+            else:
+                fids, kinds = ids, np.zeros(ids.shape[0], dtype=np.int32)
             new = self._optimal_branch_lengths(fids, kinds, tol)
             d = damping ** (i + 1)
-            for k, fid in enumerate(fids[:len(fids) - (1 if root_bif else 0)]):
-                n = topo.nodes[fid]
-                n.branch_length = new[k] * (1 - d) + n.branch_length * d
-                n.mutation_length = n.branch_length
+            # damped update (treeanc.py:1340-1343) for all branches at once; the lengths are read and written through the
+            # nodes' instance dicts (one C-level pass each) instead of three attribute operations per node in Python
+            dicts = self._node_dicts(topo.nodes)
+            try:
+                cur = np.fromiter(map(operator.itemgetter('branch_length'), map(dicts.__getitem__, ids)), dtype=np.float64, count=ids.shape[0])
+                upd = (new[:ids.shape[0]] * (1 - d) + cur * d).tolist()
+                for k, v in zip(ids.tolist(), upd):
+                    dk = dicts[k]
+                    dk['branch_length'] = v
+                    dk['mutation_length'] = v
+            except (KeyError, TypeError, ValueError):        # branch_length is not a plain instance attribute
+                for k, fid in enumerate(ids.tolist()):
+                    n = topo.nodes[fid]
+                    n.branch_length = new[k] * (1 - d) + n.branch_length * d
+                    n.mutation_length = n.branch_length
             if root_bif:
                 # the reference runs this block once per root child (treeanc.py:1317-1339)
                 n1, n2 = root.clades
@@ -618,9 +639,11 @@ class DeviceMarginalMixin(object):
             LH = self.sequence_LH()
             deltaLH = LH - oldLH
             oldLH = LH
-            dbl = self.tree.total_branch_length() - old_bl
-            self.logger('TreeAnc.optimize_tree_marginal: iteration %d, LH=%1.2f (%1.2f), delta branch_length=%1.4f, '
-                        'total branch_length %1.4f' % (i, LH, deltaLH, dbl, self.tree.total_branch_length()), 2)
+            if self.verbose > 2:            # two tree walks per iteration only when somebody reads the message
+                tbl = self.tree.total_branch_length()
+                self.logger('TreeAnc.optimize_tree_marginal: iteration %d, LH=%1.2f (%1.2f), delta branch_length=%1.4f, '
+                            'total branch_length %1.4f' % (i, LH, deltaLH, tbl - last_tbl, tbl), 2)
+                last_tbl = tbl
             if deltaLH < LHtol:
                 self.logger('TreeAnc.optimize_tree_marginal: deltaLH=%f, stopping iteration.' % deltaLH, 1)
                 break

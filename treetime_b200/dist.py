@@ -73,6 +73,25 @@ class TorchComm(object):
         out = np.concatenate([p[:k].cpu().numpy() for p, k in zip(parts, sizes)], axis=0)
         return np.moveaxis(out, 0, axis)
 
+    def allreduce_sum_device(self, engine):
+        """In-place sum over the ranks of n doubles at a device address (NCCL only): a callable (ptr, n) for
+        Engine.brent_minimize, or None when the group cannot reduce device memory (gloo).  The engine runs on its own
+        stream: it is drained before the collective, and the collective before the engine continues."""
+        if self.dist.get_backend(self.group) != 'nccl':
+            return None
+        torch = self.torch
+
+        class _View(object):
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<f8', 'data': (ptr, False), 'version': 2}
+
+        def reduce(ptr, n):
+            engine.sync()
+            t = torch.as_tensor(_View(ptr, n), device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            torch.cuda.current_stream(self.device).synchronize()
+        return reduce
+
     def barrier(self):
         self.dist.barrier(group=self.group)
 

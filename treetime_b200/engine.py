@@ -273,6 +273,48 @@ class Engine(object):
         _lib.check(self.lib.ttb_branch_objective(self.h, nodes.shape[0], _ip(nodes), kp, _dp(t), _dp(out)))
         return out
 
+    def brent_minimize(self, nodes, kinds, xa, xb, xc, tol, maxiter=500, allreduce=None, check_every=4):
+        """Lock-step Brent over s = sqrt(t) for all listed branches with the state machine on the device
+        (ttb_brent_*): per iteration one objective launch + one state-update launch, no host round trip; the host only
+        reads the number of unfinished branches every `check_every` iterations.  allreduce(dev_ptr, n): sums the n
+        objective values in place over the pattern shards (NCCL), or None.  Returns the dict of brent_lockstep."""
+        from .brent import BracketError
+        nodes = _i32(nodes)
+        n = nodes.shape[0]
+        kp = None
+        if kinds is not None:
+            kinds = _i32(kinds)
+            kp = _ip(kinds)
+        xa, xb, xc = _f64(xa), _f64(xb), _f64(xc)
+        swap = xa > xc
+        if swap.any():
+            xa, xc = np.where(swap, xc, xa), np.where(swap, xa, xc)
+        try:
+            _lib.check(self.lib.ttb_brent_begin(self.h, n, _ip(nodes), kp, _dp(xa), _dp(xb), _dp(xc), float(tol), int(maxiter)))
+            ptr, cnt = ctypes.c_void_p(), ctypes.c_int32()
+            if allreduce is not None:
+                _lib.check(self.lib.ttb_brent_f_device_ptr(self.h, ctypes.byref(ptr), ctypes.byref(cnt)))
+            it = 0
+            while True:
+                _lib.check(self.lib.ttb_brent_eval(self.h))
+                if allreduce is not None:
+                    allreduce(ptr.value, n)
+                it += 1
+                sync = it >= 3 and (it - 3) % check_every == 0
+                na = ctypes.c_int32(-1)
+                _lib.check(self.lib.ttb_brent_update(self.h, 1 if sync else 0, ctypes.byref(na)))
+                if (sync and na.value == 0) or it > maxiter + check_every + 3:
+                    break
+        except _lib.TTBError as e:
+            if 'Bracketing values' in str(e):
+                raise BracketError(str(e).split(': ', 1)[-1])
+            raise
+        x = np.empty(n); fun = np.empty(n)
+        nit = np.empty(n, dtype=np.int32); nfev = np.empty(n, dtype=np.int32)
+        _lib.check(self.lib.ttb_brent_result(self.h, _dp(x), _dp(fun), _ip(nit), _ip(nfev)))
+        success = (nit < maxiter) & ~(np.isnan(x) | np.isnan(fun))
+        return dict(x=x, fun=fun, nit=nit.astype(np.int64), nfev=nfev.astype(np.int64), success=success)
+
     def branch_hamming(self, nodes, kinds=None):
         nodes = _i32(nodes)
         num = np.empty(nodes.shape[0], dtype=np.float64)
