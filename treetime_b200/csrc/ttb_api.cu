@@ -353,7 +353,7 @@ void build_sched(ttb_handle h, const std::vector<int>& key, const std::vector<ch
 
 // Split every level into groups of consecutive nodes so that a launch has enough blocks to
 // fill the GPU but every block still pipelines over several chunks.
-void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm, bool post_order, int n_sm) {
+void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm, bool post_order, int n_sm, bool allow_merge) {
   sc.group_ptr.clear();
   sc.launches.clear();
   // Site-specific kernels load a per-pattern eigen-system per block (longer runs amortise it) and are
@@ -379,6 +379,7 @@ void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm
   // Postorder level 0 (all children are tips) has its own kernel and is never merged.
   long long merge_nodes = 0;
   if (const char* e = getenv("TTB_MERGE_NODES")) merge_nodes = std::max(0LL, atoll(e));
+  if (!allow_merge) merge_nodes = 0;     // the DEP kernels exist for single models, double storage, no masks
   const size_t n_levels = sc.level_node_begin.size() - 1;
   for (size_t l = 0; l < n_levels; ++l) {
     const int nb = sc.level_node_begin[l];
@@ -484,10 +485,11 @@ int ensure_state(ttb_handle h, bool tips) {
   const size_t pq = (q * q + 1) / 2 * 2, tus = ((size_t)h->n_codes * q + 1) / 2 * 2;
   if ((rc = h->d_P.alloc((size_t)h->n_nodes * pq))) return rc;
   if ((rc = h->d_TU.alloc((size_t)h->n_tips * tus))) return rc;
-  const int ss_mode = h->site_specific ? (h->ss_sym ? 2 : 1) : 0;
+  // grouping mode: 0 single model, 1 site-specific, 2 site-specific symmetric; +4: no merged-level launches (masks / float storage)
+  const int ss_mode = (h->site_specific ? (h->ss_sym ? 2 : 1) : 0) | ((h->have_masks || h->f32) ? 4 : 0);
   if (h->sched_tiles != h->tiles() || h->sched_ss != ss_mode) {
     for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all}) {
-      build_groups(*sc, h->tiles(), h->site_specific, ss_mode == 2 ? 3 : 2, sc == &h->post, h->n_sm);
+      build_groups(*sc, h->tiles(), h->site_specific, (ss_mode & 3) == 2 ? 3 : 2, sc == &h->post, h->n_sm, ss_mode == 0);
       if ((rc = upload(sc->d_group_ptr, sc->group_ptr.data(), sc->group_ptr.size(), h->stream))) return rc;
     }
     CK(cudaStreamSynchronize(h->stream));

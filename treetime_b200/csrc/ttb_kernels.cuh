@@ -762,7 +762,7 @@ __device__ __forceinline__ Chunk load_chunk_smem(const int4* q) { return chunk_f
 // Block = (run of nodes of the level given by group_ptr, one 128-pattern tile).
 // Stage rows: child b -> rows [b*(Q+1), b*(Q+1)+Q) = S_c, row b*(Q+1)+Q = F_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool SS, bool JOINT = false, bool SYM = false, bool MASK = false, typename ST = double>
+template <int Q, bool SS, bool JOINT = false, bool SYM = false, bool MASK = false, typename ST = double, bool DEP = false>
 __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : (Q > 8 ? (JOINT ? 168 : TTB_POST_LARGEQ_REGS) : 255)) post_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                               const int* __restrict__ group_ptr, int tiles, int fbase,
                                                               const int* __restrict__ dep) {
@@ -837,12 +837,12 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     // barriers); the descriptor of the next chunk is fetched while the current one is issued, so no
     // global-memory latency sits on the consumers' path.
     Chunk c = load_chunk_global(chunks + k0);
-    int d = dep ? __ldg(dep + k0) : -1;   // merged-level launch: the chunk (global index) that wrote what this one reads
+    int d = DEP ? __ldg(dep + k0) : -1;   // merged-level launch (DEP): the chunk (global index) that wrote what this one reads
     pdl_wait();   // everything the bulk copies read was written by earlier levels
     for (int u = 0; u < n_chunks; ++u) {
       const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
-      const int dn = dep ? __ldg(dep + k0 + min(u + 1, n_chunks - 1)) : -1;
-      if (d >= k0) pipe.wait_done(lane, (uint32_t)(d - k0 + 1));
+      const int dn = DEP ? __ldg(dep + k0 + min(u + 1, n_chunks - 1)) : -1;
+      if (DEP && d >= k0) pipe.wait_done(lane, (uint32_t)(d - k0 + 1));
       issue(u, c);
       cur.advance();
       c = cn;
@@ -977,7 +977,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
         }
       }
     }
-    if (dep) pipe.publish_done(warp, lane, (uint32_t)(u + 1));
+    if constexpr (DEP) pipe.publish_done(warp, lane, (uint32_t)(u + 1));
   }
   if (!JOINT && act) p.Fpart[(size_t)(fbase + g) * p.ld + a] = Facc + log(Zprod);
 }
@@ -1413,7 +1413,7 @@ __device__ __forceinline__ void outgroup_message(const double (&Mp)[Q], const do
 // Tips take part only with TIPS (reconstruct_tip_states).
 // Stage rows: [0, Q) parent profile, child b -> rows [Q + b*Q, Q + (b+1)*Q) = S_c.
 // ---------------------------------------------------------------------------------------
-template <int Q, bool TIPS, bool SS, bool SYM = false, bool MASK = false, typename ST = double>
+template <int Q, bool TIPS, bool SS, bool SYM = false, bool MASK = false, typename ST = double, bool DEP = false>
 __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB_SS_REG_MAXQ) ? (SYM ? TTB_SS_SYM_REGS : 168) : (Q > 8 ? 168 : 255)) pre_level_kernel(TtbDev p, const TtbChunk* __restrict__ chunks,
                                                              const int* __restrict__ group_ptr, int tiles, int count_diff,
                                                              const int* __restrict__ dep) {
@@ -1494,12 +1494,12 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     // barriers); the descriptor of the next chunk is fetched while the current one is issued, so no
     // global-memory latency sits on the consumers' path.
     Chunk c = load_chunk_global(chunks + k0);
-    int d = dep ? __ldg(dep + k0) : -1;   // merged-level launch: the chunk (global index) that wrote what this one reads
+    int d = DEP ? __ldg(dep + k0) : -1;   // merged-level launch (DEP): the chunk (global index) that wrote what this one reads
     pdl_wait();   // everything the bulk copies read was written by earlier levels
     for (int u = 0; u < n_chunks; ++u) {
       const Chunk cn = load_chunk_global(chunks + k0 + min(u + 1, n_chunks - 1));
-      const int dn = dep ? __ldg(dep + k0 + min(u + 1, n_chunks - 1)) : -1;
-      if (d >= k0) pipe.wait_done(lane, (uint32_t)(d - k0 + 1));
+      const int dn = DEP ? __ldg(dep + k0 + min(u + 1, n_chunks - 1)) : -1;
+      if (DEP && d >= k0) pipe.wait_done(lane, (uint32_t)(d - k0 + 1));
       issue(u, c);
       cur.advance();
       c = cn;
@@ -1689,7 +1689,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
     if constexpr (Q > 8) fence_proxy_async_smem();  // the stage was written through the generic proxy
     pipe.consumer_release(cur);
     cur.advance();
-    if (dep) pipe.publish_done(warp, lane, (uint32_t)(u + 1));
+    if constexpr (DEP) pipe.publish_done(warp, lane, (uint32_t)(u + 1));
   }
   if (count_diff) {
     ndiff = __reduce_add_sync(0xffffffffu, ndiff);

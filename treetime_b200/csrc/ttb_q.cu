@@ -54,6 +54,12 @@ int prepare_t(const TtbDev& d) {
     if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, true, true))) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, true, true))) != cudaSuccess) return (int)e;
   }
+  if constexpr (!SS) {       // merged-level launches (opt-in): single model, double storage, no masks
+    if ((e = cudaFuncSetAttribute(post_level_kernel<Q, false, false, false, false, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, false))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(post_level_kernel<Q, false, true, false, false, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, false))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, false, false, false, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, false))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, true, false, false, false, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, false))) != cudaSuccess) return (int)e;
+  }
   if constexpr (HAS_F32) {   // float message storage: same stages (the rows just hold floats)
     if ((e = cudaFuncSetAttribute(post_level_kernel<Q, SS, false, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(d, SS))) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(pre_level_kernel<Q, false, SS, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem(d, SS))) != cudaSuccess) return (int)e;
@@ -110,8 +116,18 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   int fbase = l0 ? pl.post_levels[0].n_groups : 0;
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
+    constexpr bool CAN_DEP = !SS && !MASK && sizeof(ST) == 8;     // build_groups merges levels only for these
+    if constexpr (CAN_DEP) {
+      if (L.dep) {
+        launch_pdl(post_level_kernel<Q, false, false, false, false, double, true>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d,
+                   pl.d_post_chunks, pl.d_post_group_ptr + L.group_off, tiles, fbase, pl.d_post_dep);
+        fbase += L.n_groups;
+        ++nk;
+        continue;
+      }
+    }
     launch_pdl(post_level_kernel<Q, SS, false, SYM, MASK, ST>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d, pl.d_post_chunks,
-               pl.d_post_group_ptr + L.group_off, tiles, fbase, L.dep ? pl.d_post_dep : nullptr);
+               pl.d_post_group_ptr + L.group_off, tiles, fbase, nullptr);
     fbase += L.n_groups;
     ++nk;
   }
@@ -129,12 +145,25 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
     for (int l = 0; l < pl.n_pre_levels; ++l) {
       const TtbLevelLaunch& L = pl.pre_levels[l];
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
+      constexpr bool CAN_DEP = !SS && !MASK && sizeof(ST) == 8;
+      if constexpr (CAN_DEP) {
+        if (L.dep) {
+          if (pl.tips)
+            launch_pdl(pre_level_kernel<Q, true, false, false, false, double, true>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks,
+                       pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff, pl.d_pre_dep);
+          else
+            launch_pdl(pre_level_kernel<Q, false, false, false, false, double, true>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks,
+                       pl.d_pre_group_ptr + L.group_off, tiles, pl.count_diff, pl.d_pre_dep);
+          ++nk;
+          continue;
+        }
+      }
       if (pl.tips)
         launch_pdl(pre_level_kernel<Q, true, SS, SYM, MASK, ST>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
-                   pl.count_diff, L.dep ? pl.d_pre_dep : nullptr);
+                   pl.count_diff, nullptr);
       else
         launch_pdl(pre_level_kernel<Q, false, SS, SYM, MASK, ST>, grid, TTB_LEVEL_THREADS, rsm, s, d, pl.d_pre_chunks, pl.d_pre_group_ptr + L.group_off, tiles,
-                   pl.count_diff, L.dep ? pl.d_pre_dep : nullptr);
+                   pl.count_diff, nullptr);
       ++nk;
     }
   }
@@ -191,9 +220,12 @@ int enqueue_joint_q(const TtbPassPlan& pl, cudaStream_t s, int trace) {
   }
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
-    post_level_kernel<Q, false, true><<<(unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s>>>(d, pl.d_post_chunks,
-                                                                                                      pl.d_post_group_ptr + L.group_off, tiles, 0,
-                                                                                                      L.dep ? pl.d_post_dep : nullptr);
+    if (L.dep)
+      post_level_kernel<Q, false, true, false, false, double, true><<<(unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s>>>(
+          d, pl.d_post_chunks, pl.d_post_group_ptr + L.group_off, tiles, 0, pl.d_post_dep);
+    else
+      post_level_kernel<Q, false, true><<<(unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s>>>(d, pl.d_post_chunks,
+                                                                                                        pl.d_post_group_ptr + L.group_off, tiles, 0, nullptr);
     ++nk;
   }
   joint_root_kernel<Q><<<tiles, TTB_BLOCK, 0, s>>>(d);
