@@ -141,45 +141,65 @@ def algorithmic_bytes(flat, q):
 
 
 class ClockSampler(object):
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line).  A reader thread time-stamps every
+    sample; the timed region of a sharded run can be shorter than nvidia-smi's period, so the caller keeps the same step
+    running a little longer (untimed) until a few samples under load exist -- both counts are reported."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
+        self.rows = []          # (time, fields)
 
-    def start(self):
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(',')]))
+
+    def start(self, wait_first=3.0):
+        import threading
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '25'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < wait_first:     # nvidia-smi needs a moment to come up
+            time.sleep(0.01)
 
-    def stop(self):
+    def count_since(self, t):
+        return sum(1 for ts, _ in self.rows if ts >= t)
+
+    def stop(self, t_begin=None, t_end=None, t_load_end=None):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(',')]
-            if len(f) < 9:
+        self.thread.join(timeout=2)
+        sm, mx, reasons, timed = [], [], set(), 0
+        for ts, f in self.rows:
+            if len(f) < 9 or (t_begin is not None and ts < t_begin) or (t_load_end is not None and ts > t_load_end):
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            if t_end is not None and ts <= t_end:
+                timed += 1
             for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
                 if val.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'samples_in_timed_region': timed,
+                'note': 'samples beyond the timed region were taken while the same step kept running (untimed) so that short timed regions still '
+                        'get clocks under load'}
 
 
 def measured_peak():
@@ -521,17 +541,32 @@ def timed_resident(leg, steps, warmup, world, local_rank, sample_clocks=True):
     sampler = ClockSampler(local_rank)
     if sample_clocks:
         sampler.start()
-        time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.perf_counter()
     e0.record(stream)
     for _ in range(steps):
         step()
     e1.record(stream)
     barrier()
+    t_end = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sample_clocks else None
-    launches = eng.launch_count() - launches0
+    launches_timed = eng.launch_count() - launches0
+    clocks = None
+    if sample_clocks:
+        # short timed regions (a sharded pass is ~2 ms): keep the same step running, untimed, until nvidia-smi has seen the load
+        # (a fixed number of extra steps everywhere: the ranks must issue the same collectives)
+        ms_agreed = ms_total
+        if world > 1:
+            tmax = torch.tensor([ms_total], device='cuda', dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms_agreed = float(tmax.item())
+        extra = int(min(400, max(0, 0.35 / max(1e-4, ms_agreed / steps / 1e3) - steps)))
+        for _ in range(extra):
+            step()
+        barrier()
+        clocks = sampler.stop(t_begin, t_end, time.perf_counter())
+    launches = launches_timed
     lh_local = eng.results()[0]           # copied to the host before the all-reduce touched the device buffer
     lh_global = float(res_t[0].item()) if world > 1 else lh_local
     return ms_total / steps, launches, clocks, lh_global, lh_local, barrier
