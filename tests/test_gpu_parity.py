@@ -559,6 +559,7 @@ def test_merged_level_launches(kind, monkeypatch):
     rt = False
     if kind == 'aa':
         gtr, L, compress = util.random_gtr('aa_nogap', 5), 300, True
+        monkeypatch.setenv('TTB_NO_MMA', '1')   # merged launches are a variant of the one-thread-per-pattern kernels
     elif kind == 'site_specific':
         from treetime_b200.gtr import GTRSiteSpecific
         L, compress = 700, False

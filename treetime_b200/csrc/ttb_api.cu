@@ -147,7 +147,7 @@ struct ttb_engine {
   double brent_tol = 0.0;
   int* h_brent_flags = nullptr;   // pinned {n_active, bracket error}
   DBuf<double> d_leaf_pairs;   // cherry tables of postorder level 1 (leaf_pair_table_kernel)
-  DBuf<double> d_LP, d_TL, d_Fred, d_TU, d_P, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
+  DBuf<double> d_LP, d_TL, d_Fred, d_TU, d_P, d_Pf, d_S, d_F, d_M, d_Mtip, d_LH, d_lh_partial, d_results, d_stage, d_partial;
   DBuf<uint8_t> d_TC, d_Cx, d_idx, d_idxtip, d_bstage, d_mut_state, d_aln, d_colstat, d_lut, d_constl;
   DBuf<long long> d_firstpos;
   DBuf<int> d_seqrow, d_flag;
@@ -232,6 +232,7 @@ struct ttb_engine {
     d.tu_stride = (n_codes * q + 1) / 2 * 2;
     d.TU = d_TU.p;
     d.P = d_P.p;
+    d.Pf = d_Pf.p;
     d.f32 = f32 ? 1 : 0;
     d.S = d_S.p;
     d.Fpart = d_F.p;
@@ -246,6 +247,7 @@ struct ttb_engine {
     d.lh_partial = d_lh_partial.p;
     d.nd_slots = d_nd.p;
     d.results = d_results.p;
+    { static const int dbg = getenv("TTB_DBG") ? atoi(getenv("TTB_DBG")) : 0; d.dbg = dbg; }
     return d;
   }
 };
@@ -484,6 +486,15 @@ int ensure_state(ttb_handle h, bool tips) {
   int rc;
   const size_t pq = (q * q + 1) / 2 * 2, tus = ((size_t)h->n_codes * q + 1) / 2 * 2;
   if ((rc = h->d_P.alloc((size_t)h->n_nodes * pq))) return rc;
+  {
+    // large alphabets: exp(Qt) also in mma-fragment order for the tensor-pipe level kernels (ttb_mma.cuh); TTB_NO_MMA=1
+    // keeps the one-thread-per-pattern kernels (A/B measurements)
+    const char* mg = getenv("TTB_MERGE_NODES");   // merged-level launches exist for the one-thread-per-pattern kernels only
+    const bool mma = q > 8 && !h->site_specific && !getenv("TTB_NO_MMA") && !(mg && atoll(mg) > 0);
+    const double* before = h->d_Pf.p;
+    if ((rc = h->d_Pf.alloc(mma ? (size_t)h->n_nodes * TTB_PF_STRIDE : 0))) return rc;
+    if (before != h->d_Pf.p) h->drop_graphs();
+  }
   if ((rc = h->d_TU.alloc((size_t)h->n_tips * tus))) return rc;
   // grouping mode: 0 single model, 1 site-specific, 2 site-specific symmetric; +4: no merged-level launches (masks / float storage)
   const int ss_mode = (h->site_specific ? (h->ss_sym ? 2 : 1) : 0) | ((h->have_masks || h->f32) ? 4 : 0);
@@ -604,7 +615,7 @@ int ttb_destroy(ttb_handle h) {
                      &h->post.d_dep, &h->pre_int.d_dep, &h->pre_all.d_dep};
   for (auto* b : ib) b->release();
   DBuf<double>* db[] = {&h->d_code_prof, &h->d_mult, &h->d_t, &h->d_eig, &h->d_v, &h->d_vinv, &h->d_Pi, &h->d_mu, &h->d_LP, &h->d_TL, &h->d_ss_eig, &h->d_ss_mu, &h->d_ss_V, &h->d_ss_Vinv, &h->d_ss_Pi,
-                        &h->d_ss_w, &h->d_ss_grid, &h->d_ss_E, &h->d_TU, &h->d_P, &h->d_S,
+                        &h->d_ss_w, &h->d_ss_grid, &h->d_ss_E, &h->d_TU, &h->d_P, &h->d_Pf, &h->d_S,
                         &h->d_F, &h->d_Fred, &h->d_M, &h->d_Mtip, &h->d_LH, &h->d_lh_partial, &h->d_results, &h->d_stage,
                         &h->d_partial, &h->d_ets, &h->d_eout};
   for (auto* b : db) b->release();
@@ -740,7 +751,7 @@ int ttb_set_tree(ttb_handle h, int32_t n_nodes, const int32_t* parent, const int
   if ((rc = upload(h->post.d_node_chunk, h->post.node_chunk.data(), h->post.node_chunk.size(), s))) return rc;
   CK(cudaStreamSynchronize(s));
   // every per-node array is invalid now
-  h->d_P.release(); h->d_TU.release(); h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();
+  h->d_P.release(); h->d_Pf.release(); h->d_TU.release(); h->d_S.release(); h->d_F.release(); h->d_M.release(); h->d_Mtip.release();
   h->d_idx.release(); h->d_idxtip.release();
   h->d_t.release();
   h->have_t = false;
@@ -1785,7 +1796,7 @@ int ttb_mutation_counts_per_site(ttb_handle h, double* n_ija, double* T_ia) {
 int ttb_device_bytes(ttb_handle h, int64_t* bytes) {
   if (!h || !bytes) return fail(TTB_EINVAL, "null argument");
   size_t b = h->d_codes.bytes() + h->d_code_prof.bytes() + h->d_mult.bytes() + h->d_TU.bytes() + h->d_t.bytes() +
-             h->d_P.bytes() + h->d_S.bytes() + h->d_F.bytes() + h->d_M.bytes() + h->d_Mtip.bytes() + h->d_LH.bytes() +
+             h->d_P.bytes() + h->d_Pf.bytes() + h->d_S.bytes() + h->d_F.bytes() + h->d_M.bytes() + h->d_Mtip.bytes() + h->d_LH.bytes() +
              h->d_idx.bytes() + h->d_idxtip.bytes() + h->d_stage.bytes() + h->d_partial.bytes() + h->d_parent.bytes() * 5;
   *bytes = (int64_t)b;
   return 0;

@@ -30,6 +30,7 @@
 #define TTB_TILE 128          // patterns per tile = threads per block: one 1 KB row per state
 #define TTB_CB 2              // children per pipeline chunk (binary nodes = one chunk)
 #define TTB_FLANES 16         // lanes of the two-stage reduction of the per-run log-prefactor sums
+#define TTB_PF_STRIDE (2 * 18 * 32)   // doubles per branch of the fragment-ordered exp(Qt) (ttb_mma.cuh: 2 products x 18 fragments x 32 lanes)
 
 // One pipeline chunk of a level kernel: up to TTB_CB children of one node (32 bytes).
 //   postorder: out = slot of the node being computed; src[b] = slot of internal child b or
@@ -99,6 +100,7 @@ struct TtbDev {
   int tu_stride; // stride of one tip table in doubles (n_codes*q rounded up to even)
   double* TU;    // [n_tips][tu_stride]  tip message table: TU[code*q+j] = sum_i prof[code][i] P[i][j]
   double* P;     // [n_nodes][pq]  exp(Q t_c), P[i*q+j] = Prob(child=i | parent=j)
+  double* Pf;    // [n_nodes][TTB_PF_STRIDE] the same matrices in mma-fragment order (q > 8, ttb_mma.cuh) or null
   // message arrays are TILE-BLOCKED state-planar: [slot][tile][state][128]: the q rows of one
   // (node, tile) are one contiguous q KB block = one TMA copy, and 128 consecutive patterns of a
   // state are one coalesced 1 KB row
@@ -124,6 +126,7 @@ struct TtbDev {
   double* lh_partial;             // [tiles]
   unsigned long long* nd_slots;   // [1024]
   double* results;                // {total_lh, n_diff, n_diff of tips}
+  int dbg;   // measurement only (TTB_DBG): bit0 level kernels skip the arithmetic, bit1 skip the message copies (ttb_mma.cuh)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -637,7 +640,7 @@ static __global__ void ss_patch_chunks_kernel(TtbChunk* __restrict__ chunks, int
 // ---------------------------------------------------------------------------------------
 // Shared-memory ring of the level kernels.
 // ---------------------------------------------------------------------------------------
-template <int Q, int NST = ((Q <= 8) ? 3 : 2)>
+template <int Q, int NST = ((Q <= 8) ? 3 : 2), int NCONS = TTB_BLOCK>
 struct Pipe {
   static constexpr int STAGES = NST;
   static constexpr int CB = (Q <= 8) ? TTB_CB : 1;   // children per chunk (the host schedule uses the same rule)
@@ -682,7 +685,7 @@ struct Pipe {
   __device__ void init() const {  // one thread
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, TTB_BLOCK);
+      mbar_init(empty + s, NCONS);   // one arrival per consumer thread
     }
     mbar_init(mbar, 1);
     for (int w = 0; w < TTB_BLOCK / 32; ++w) done[w] = 0u;

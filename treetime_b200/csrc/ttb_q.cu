@@ -1,7 +1,11 @@
 // ttb_q.cu -- instantiates the kernels for ONE alphabet size (-DTTB_Q=<q>) and exports
 // their launchers as a TtbQOps table.
 #include "ttb_qops.h"
+#if TTB_Q > 8
+#include "ttb_mma.cuh"
+#endif
 #include <algorithm>
+#include <cstdlib>
 
 #ifndef TTB_Q
 #error "compile with -DTTB_Q=<n_states>"
@@ -73,8 +77,59 @@ int prepare_t(const TtbDev& d) {
   return 0;
 }
 
+#if TTB_Q > 8
+// Tensor-pipe level kernels (ttb_mma.cuh): NW pattern warps per block, chosen at run time (TTB_MMA_NW, measurement knob).
+constexpr bool HAS_MMA = true;
+int mma_nw() {
+  static const int nw = [] {
+    const char* e = getenv("TTB_MMA_NW");
+    const int v = e ? atoi(e) : 8;
+    return (v == 4 || v == 8 || v == 16) ? v : 8;
+  }();
+  return nw;
+}
+template <int NW>
+size_t mma_post_smem(const TtbDev& d) { return MmaCfg<Q, NW>::PipeT::smem_bytes(Q, TTB_MMA_NF * 32, d.tu_stride); }
+template <int NW>
+size_t mma_pre_smem(const TtbDev& d, bool tips) { return MmaCfg<Q, NW>::PipeT::smem_bytes(2 * Q, TTB_PF_STRIDE, tips ? d.tu_stride : 0); }
+template <int NW>
+int prepare_mma(const TtbDev& d) {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(post_level_mma_kernel<Q, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_post_smem<NW>(d))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_mma_kernel<Q, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_pre_smem<NW>(d, false))) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(pre_level_mma_kernel<Q, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_pre_smem<NW>(d, true))) != cudaSuccess) return (int)e;
+  // two resident blocks per SM need the full shared-memory carve-out
+  cudaFuncSetAttribute(post_level_mma_kernel<Q, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(pre_level_mma_kernel<Q, NW, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(pre_level_mma_kernel<Q, NW, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return 0;
+}
+template <int NW>
+void launch_post_mma(const TtbPassPlan& pl, const TtbLevelLaunch& L, int fbase, cudaStream_t s) {
+  launch_pdl(post_level_mma_kernel<Q, NW>, (unsigned)((long long)L.n_groups * pl.tiles), MmaCfg<Q, NW>::THREADS, mma_post_smem<NW>(pl.d), s, pl.d,
+             pl.d_post_chunks, pl.d_post_group_ptr + L.group_off, pl.tiles, fbase);
+}
+template <int NW>
+void launch_pre_mma(const TtbPassPlan& pl, const TtbLevelLaunch& L, cudaStream_t s) {
+  const unsigned grid = (unsigned)((long long)L.n_groups * pl.tiles);
+  if (pl.tips)
+    launch_pdl(pre_level_mma_kernel<Q, NW, true>, grid, MmaCfg<Q, NW>::THREADS, mma_pre_smem<NW>(pl.d, true), s, pl.d, pl.d_pre_chunks,
+               pl.d_pre_group_ptr + L.group_off, pl.tiles, pl.count_diff);
+  else
+    launch_pdl(pre_level_mma_kernel<Q, NW, false>, grid, MmaCfg<Q, NW>::THREADS, mma_pre_smem<NW>(pl.d, false), s, pl.d, pl.d_pre_chunks,
+               pl.d_pre_group_ptr + L.group_off, pl.tiles, pl.count_diff);
+}
+#else
+constexpr bool HAS_MMA = false;
+#endif
+
 int prepare_q(const TtbDev& d) {
   if (int e = prepare_t<false>(d)) return e;
+#if TTB_Q > 8
+  if (int e = prepare_mma<4>(d)) return e;
+  if (int e = prepare_mma<8>(d)) return e;
+  if (int e = prepare_mma<16>(d)) return e;
+#endif
   if constexpr (HAS_SS) {
     if (int e = prepare_t<true>(d)) return e;
   }
@@ -94,6 +149,17 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
     tip_table_kernel<Q><<<(unsigned)((ntab + 255) / 256), 256, 0, s>>>(d, pl.d_tip_nodes);
     nk += 2;
   }
+  bool use_mma = false;   // large alphabets, single model, no masks: level kernels on the fp64 tensor pipe
+#if TTB_Q > 8
+  if constexpr (!SS && !MASK && sizeof(ST) == 8) {
+    if (d.Pf) {
+      const long long nf = (long long)d.n_nodes * TTB_PF_STRIDE;
+      pfrag_kernel<Q><<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(d, d.Pf);
+      ++nk;
+      use_mma = true;
+    }
+  }
+#endif
   if (ev) { cudaEventRecord(ev[1], s); pk[0] = nk; }
   const size_t psm = post_smem(d, SS, SYM);
   int l0 = 0;
@@ -117,6 +183,18 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   for (int l = l0; l < pl.n_post_levels; ++l) {
     const TtbLevelLaunch& L = pl.post_levels[l];
     constexpr bool CAN_DEP = !SS && !MASK && sizeof(ST) == 8;     // build_groups merges levels only for these
+#if TTB_Q > 8
+    if (use_mma && !L.dep) {
+      switch (mma_nw()) {
+        case 4: launch_post_mma<4>(pl, L, fbase, s); break;
+        case 16: launch_post_mma<16>(pl, L, fbase, s); break;
+        default: launch_post_mma<8>(pl, L, fbase, s); break;
+      }
+      fbase += L.n_groups;
+      ++nk;
+      continue;
+    }
+#endif
     if constexpr (CAN_DEP) {
       if (L.dep) {
         launch_pdl(post_level_kernel<Q, false, false, false, false, double, true>, (unsigned)((long long)L.n_groups * tiles), TTB_LEVEL_THREADS, psm, s, d,
@@ -146,6 +224,17 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
       const TtbLevelLaunch& L = pl.pre_levels[l];
       const unsigned grid = (unsigned)((long long)L.n_groups * tiles);
       constexpr bool CAN_DEP = !SS && !MASK && sizeof(ST) == 8;
+#if TTB_Q > 8
+      if (use_mma && !L.dep) {
+        switch (mma_nw()) {
+          case 4: launch_pre_mma<4>(pl, L, s); break;
+          case 16: launch_pre_mma<16>(pl, L, s); break;
+          default: launch_pre_mma<8>(pl, L, s); break;
+        }
+        ++nk;
+        continue;
+      }
+#endif
       if constexpr (CAN_DEP) {
         if (L.dep) {
           if (pl.tips)
