@@ -15,8 +15,8 @@ CSRC = os.path.join(HERE, 'csrc')
 BUILD_DIR = os.path.join(HERE, 'build')
 Q_VALUES = (2, 3, 4, 5, 6, 7, 8, 20, 21, 22)      # alphabet sizes with compiled kernels
 SOURCES = [os.path.join(CSRC, 'ttb_api.cu'), os.path.join(CSRC, 'ttb_q.cu'), os.path.join(CSRC, 'ttb_brent.cu')]
-HEADERS = [os.path.join(CSRC, 'ttb_kernels.cuh'), os.path.join(CSRC, 'ttb_qops.h'), os.path.join(CSRC, 'ttb_brent.h'),
-           os.path.join(os.path.dirname(HERE), 'include', 'ttb.h')]
+HEADERS = [os.path.join(CSRC, f) for f in ('ttb_kernels.cuh', 'ttb_mma.cuh', 'ttb_qops.h', 'ttb_brent.h')] + \
+          [os.path.join(os.path.dirname(HERE), 'include', 'ttb.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']

@@ -2,6 +2,7 @@
 // level schedules and the CUDA-graph that covers one marginal reconstruction.
 #include "../../include/ttb.h"
 #include "ttb_qops.h"
+#include "ttb_mma.cuh"   // TTB_PF_STRIDE, trace layout
 #include "ttb_brent.h"
 
 #include <algorithm>
@@ -143,6 +144,7 @@ struct ttb_engine {
   DBuf<double> d_brent;        // 18 state vectors + trial lengths + objective values, n_brent entries each
   DBuf<int> d_brent_i;         // nit, nfev, flags
   DBuf<uint8_t> d_brent_active;
+  DBuf<unsigned long long> d_trace;   // measurement only (TTB_TRACE)
   int n_brent = 0, brent_stage = 0, brent_maxiter = 500, brent_nb = 1;
   double brent_tol = 0.0;
   int* h_brent_flags = nullptr;   // pinned {n_active, bracket error}
@@ -247,6 +249,7 @@ struct ttb_engine {
     d.lh_partial = d_lh_partial.p;
     d.nd_slots = d_nd.p;
     d.results = d_results.p;
+    d.trace = d_trace.p;
     { static const int dbg = getenv("TTB_DBG") ? atoi(getenv("TTB_DBG")) : 0; d.dbg = dbg; }
     return d;
   }
@@ -355,7 +358,7 @@ void build_sched(ttb_handle h, const std::vector<int>& key, const std::vector<ch
 
 // Split every level into groups of consecutive nodes so that a launch has enough blocks to
 // fill the GPU but every block still pipelines over several chunks.
-void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm, bool post_order, int n_sm, bool allow_merge) {
+void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm, bool post_order, int n_sm, bool allow_merge, bool mma) {
   sc.group_ptr.clear();
   sc.launches.clear();
   // Site-specific kernels load a per-pattern eigen-system per block (longer runs amortise it) and are
@@ -367,6 +370,10 @@ void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm
   // bulk copy (measured: 888 vs 4736 blocks per level: cfg2 0.95 -> 0.75 ms, cfg3 14.26 -> 14.13 ms, cfg4 2.33 -> 2.20 ms)
   long long target_blocks = site_specific ? slots * 4 : (long long)n_sm * 6;
   long long max_group = site_specific ? 128 : 32;
+  // tensor-pipe kernels of the large alphabets (ttb_mma.cuh): ONE wave of resident blocks per level -- two blocks per SM in
+  // the postorder, one in the preorder -- so that a block's start-up (~2-4 us: barriers, descriptors, first bulk copy) is
+  // paid once per level (cfg4 sweep, profiles/R2p_mma_sweep.txt: 888 -> 296 / 148 blocks: 1.76 -> 1.63 ms per pass)
+  if (mma) target_blocks = post_order ? (long long)n_sm * 2 : (long long)n_sm;
   if (const char* e = getenv("TTB_TARGET_BLOCKS")) target_blocks = std::max(1LL, atoll(e));   // tuning knobs (measurement only)
   if (const char* e = getenv("TTB_MAX_GROUP")) max_group = std::max(1LL, atoll(e));
   long long ss_waves = 4;
@@ -415,6 +422,10 @@ void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm
       }
     } else {
       G = ((long long)n * tiles + target_blocks - 1) / target_blocks;
+      if (mma) {   // never more blocks than one wave holds: a few blocks beyond it would double the level's duration
+        const long long groups_max = std::max(1LL, target_blocks / tiles);
+        G = (n + groups_max - 1) / groups_max;
+      }
       G = std::max(1LL, std::min(max_group, G));
     }
     TtbLevelLaunch L;
@@ -496,11 +507,12 @@ int ensure_state(ttb_handle h, bool tips) {
     if (before != h->d_Pf.p) h->drop_graphs();
   }
   if ((rc = h->d_TU.alloc((size_t)h->n_tips * tus))) return rc;
-  // grouping mode: 0 single model, 1 site-specific, 2 site-specific symmetric; +4: no merged-level launches (masks / float storage)
-  const int ss_mode = (h->site_specific ? (h->ss_sym ? 2 : 1) : 0) | ((h->have_masks || h->f32) ? 4 : 0);
+  // grouping mode: 0 single model, 1 site-specific, 2 site-specific symmetric; +4: no merged-level launches (masks / float storage);
+  // +8: tensor-pipe level kernels (large alphabets)
+  const int ss_mode = (h->site_specific ? (h->ss_sym ? 2 : 1) : 0) | ((h->have_masks || h->f32) ? 4 : 0) | ((h->d_Pf.p && !h->have_masks) ? 8 : 0);
   if (h->sched_tiles != h->tiles() || h->sched_ss != ss_mode) {
     for (Sched* sc : {&h->post, &h->pre_int, &h->pre_all}) {
-      build_groups(*sc, h->tiles(), h->site_specific, (ss_mode & 3) == 2 ? 3 : 2, sc == &h->post, h->n_sm, ss_mode == 0);
+      build_groups(*sc, h->tiles(), h->site_specific, (ss_mode & 3) == 2 ? 3 : 2, sc == &h->post, h->n_sm, ss_mode == 0, (ss_mode & 8) != 0);
       if ((rc = upload(sc->d_group_ptr, sc->group_ptr.data(), sc->group_ptr.size(), h->stream))) return rc;
     }
     CK(cudaStreamSynchronize(h->stream));
@@ -1469,12 +1481,28 @@ int ttb_profile_marginal(ttb_handle h, int32_t flags, double* ms, int32_t* launc
     h->have_prev = keep_prev;
     h->have_prev_tips = keep_prev && tips;
   }
+  const char* trace_path = getenv("TTB_TRACE");   // measurement only: block timelines of the traced level kernels -> raw file
+  const size_t trace_words = 16 + (size_t)TTB_TRACE_SLOTS * TTB_TRACE_SLOT_WORDS;
+  if (trace_path) {
+    if (int rc = h->d_trace.alloc(trace_words)) return rc;
+    CK(cudaMemsetAsync(h->d_trace.p, 0, trace_words * 8, h->stream));
+    const unsigned long long filt = getenv("TTB_TRACE_GRID") ? strtoull(getenv("TTB_TRACE_GRID"), nullptr, 10) : 0ull;   // only launches of this grid size
+    CK(cudaMemcpyAsync(h->d_trace.p + 1, &filt, 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   cudaEvent_t ev[6];
   for (auto& e : ev) CK(cudaEventCreate(&e));
   int nk = 0, pk[4] = {0, 0, 0, 0};
   int rc = enqueue_pass(h, flags, lh_only ? 0 : 1, h->stream, &nk, ev, pk);
   if (rc) return rc;
   CK(cudaGetLastError());
+  if (trace_path) {
+    std::vector<unsigned long long> tr(trace_words);
+    CK(cudaMemcpyAsync(tr.data(), h->d_trace.p, trace_words * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (FILE* f = fopen(trace_path, "wb")) { fwrite(tr.data(), 8, trace_words, f); fclose(f); }
+    h->d_trace.release();
+  }
   CK(cudaMemcpyAsync(h->h_results, h->d_results.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   float f;

@@ -126,7 +126,8 @@ struct TtbDev {
   double* lh_partial;             // [tiles]
   unsigned long long* nd_slots;   // [1024]
   double* results;                // {total_lh, n_diff, n_diff of tips}
-  int dbg;   // measurement only (TTB_DBG): bit0 level kernels skip the arithmetic, bit1 skip the message copies (ttb_mma.cuh)
+  unsigned long long* trace;   // measurement only (TTB_TRACE=<file>, ttb_profile_marginal): per-block clock64 timelines of the level kernels, or null
+  int dbg;   // measurement only (TTB_DBG): bit0: the tensor-pipe level kernels skip the arithmetic, bit1: they skip the message copies (ttb_mma.cuh)
 };
 
 // ---------------------------------------------------------------------------------------

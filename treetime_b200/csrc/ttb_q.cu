@@ -79,19 +79,25 @@ int prepare_t(const TtbDev& d) {
 
 #if TTB_Q > 8
 // Tensor-pipe level kernels (ttb_mma.cuh): NW pattern warps per block, chosen at run time (TTB_MMA_NW, measurement knob).
-constexpr bool HAS_MMA = true;
-int mma_nw() {
-  static const int nw = [] {
-    const char* e = getenv("TTB_MMA_NW");
-    const int v = e ? atoi(e) : 8;
-    return (v == 4 || v == 8 || v == 16) ? v : 8;
-  }();
-  return nw;
+// Pattern warps per block (measurement knobs TTB_MMA_NW_POST / TTB_MMA_NW_PRE, TTB_MMA_NW for both).  Defaults from the
+// cfg4 sweep (profiles/R2p_mma_sweep.txt): postorder 8 warps x 2 blocks per SM, preorder 16 warps x 1 block.
+int mma_nw(bool pre) {
+  static const int nw[2] = {[] {
+                              const char* e = getenv("TTB_MMA_NW_POST") ? getenv("TTB_MMA_NW_POST") : getenv("TTB_MMA_NW");
+                              const int v = e ? atoi(e) : 8;
+                              return (v == 4 || v == 8 || v == 16) ? v : 8;
+                            }(),
+                            [] {
+                              const char* e = getenv("TTB_MMA_NW_PRE") ? getenv("TTB_MMA_NW_PRE") : getenv("TTB_MMA_NW");
+                              const int v = e ? atoi(e) : 16;
+                              return (v == 4 || v == 8 || v == 16) ? v : 16;
+                            }()};
+  return nw[pre ? 1 : 0];
 }
 template <int NW>
-size_t mma_post_smem(const TtbDev& d) { return MmaCfg<Q, NW>::PipeT::smem_bytes(Q, TTB_MMA_NF * 32, d.tu_stride); }
+size_t mma_post_smem(const TtbDev& d) { return MmaCfg<Q, NW>::PipeT::smem_bytes(Q, MmaQ<Q>::PFQ, d.tu_stride); }
 template <int NW>
-size_t mma_pre_smem(const TtbDev& d, bool tips) { return MmaCfg<Q, NW>::PipeT::smem_bytes(2 * Q, TTB_PF_STRIDE, tips ? d.tu_stride : 0); }
+size_t mma_pre_smem(const TtbDev& d, bool tips) { return MmaCfg<Q, NW>::PipeT::smem_bytes(2 * Q, 2 * MmaQ<Q>::PFQ, tips ? d.tu_stride : 0); }
 template <int NW>
 int prepare_mma(const TtbDev& d) {
   cudaError_t e;
@@ -119,8 +125,6 @@ void launch_pre_mma(const TtbPassPlan& pl, const TtbLevelLaunch& L, cudaStream_t
     launch_pdl(pre_level_mma_kernel<Q, NW, false>, grid, MmaCfg<Q, NW>::THREADS, mma_pre_smem<NW>(pl.d, false), s, pl.d, pl.d_pre_chunks,
                pl.d_pre_group_ptr + L.group_off, pl.tiles, pl.count_diff);
 }
-#else
-constexpr bool HAS_MMA = false;
 #endif
 
 int prepare_q(const TtbDev& d) {
@@ -153,7 +157,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
 #if TTB_Q > 8
   if constexpr (!SS && !MASK && sizeof(ST) == 8) {
     if (d.Pf) {
-      const long long nf = (long long)d.n_nodes * TTB_PF_STRIDE;
+      const long long nf = (long long)d.n_nodes * (2 * MmaQ<Q>::PFQ);
       pfrag_kernel<Q><<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(d, d.Pf);
       ++nk;
       use_mma = true;
@@ -185,7 +189,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
     constexpr bool CAN_DEP = !SS && !MASK && sizeof(ST) == 8;     // build_groups merges levels only for these
 #if TTB_Q > 8
     if (use_mma && !L.dep) {
-      switch (mma_nw()) {
+      switch (mma_nw(false)) {
         case 4: launch_post_mma<4>(pl, L, fbase, s); break;
         case 16: launch_post_mma<16>(pl, L, fbase, s); break;
         default: launch_post_mma<8>(pl, L, fbase, s); break;
@@ -226,7 +230,7 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
       constexpr bool CAN_DEP = !SS && !MASK && sizeof(ST) == 8;
 #if TTB_Q > 8
       if (use_mma && !L.dep) {
-        switch (mma_nw()) {
+        switch (mma_nw(true)) {
           case 4: launch_pre_mma<4>(pl, L, s); break;
           case 16: launch_pre_mma<16>(pl, L, s); break;
           default: launch_pre_mma<8>(pl, L, s); break;
