@@ -562,3 +562,85 @@ __global__ void __launch_bounds__(MmaCfg<Q, NW>::THREADS) __maxnreg__((MmaCfg<Q,
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------
+// Postorder level 1 (every child is a tip), see post_leaf_level_kernel: a pure write stream of q doubles per
+// (node, pattern) behind a table lookup per tip.  Same lane layout as the kernels above (four lanes per pattern, KS
+// states each): four times the threads of the one-thread-per-pattern kernel for the same bytes, 64-byte store segments.
+// Block = (run of nodes, 128-pattern tile), 16 warps x 8 patterns.
+// ---------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(512) post_leaf_mma_kernel(TtbDev p, const TtbChunk* __restrict__ chunks, const int* __restrict__ group_ptr,
+                                                            int tiles, int fbase) {
+  constexpr int KS = MmaQ<Q>::KS;
+  const int g_ = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c4 = lane & 3;
+  const long long a = (long long)tile * TTB_TILE + warp * 8 + g;
+  pdl_launch_dependents();
+  const int k0 = group_ptr[g_], k1 = group_ptr[g_ + 1];
+  const bool act = a < p.Lp;
+  const long long al = act ? a : 0;   // past the alignment: compute on pattern 0, store nothing
+  pdl_wait();   // the tip tables come from the preceding kernel
+  double X[KS];
+  double Facc = 0.0, Zprod = 1.0;
+  int scale = 0, seen = 0;
+  Chunk c = load_chunk_global(chunks + k0);
+  int code = __ldg(p.codes + (size_t)(-1 - c.src0) * p.ld + al);
+  for (int k = k0; k < k1; ++k) {
+    Chunk cn = c;
+    int ncode = 0;
+    if (k + 1 < k1) {   // descriptor and code byte of the next chunk are requested before this one is processed
+      cn = load_chunk_global(chunks + k + 1);
+      ncode = __ldg(p.codes + (size_t)(-1 - cn.src0) * p.ld + al);
+    }
+    if (c.flags & 1) {
+#pragma unroll
+      for (int s = 0; s < KS; ++s) X[s] = 1.0;
+      scale = 0;
+      seen = 0;
+    }
+    const double* tu = p.TU + (size_t)(-1 - c.src0) * p.tu_stride + code * Q;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      const int j = mma_state(s, c4);
+      X[s] *= (j < Q) ? __ldg(tu + j) : 0.0;
+    }
+    if (++seen > 2) {
+      double mx = X[0];
+#pragma unroll
+      for (int s = 1; s < KS; ++s) mx = fmax(mx, X[s]);
+      mx = quad_max(mx);
+      if (mx < 0x1p-256 && mx > 0.0) {
+#pragma unroll
+        for (int s = 0; s < KS; ++s) X[s] *= 0x1p+256;
+        ++scale;
+      }
+    }
+    if (c.flags & 2) {
+      const double Z = quad_sum(slot_sum<KS>(X));
+      const double inv = fast_rcp(Z);
+      if (act) {
+        double* __restrict__ so = p.S + msg_off<Q>(p, c.out, a);
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          const int j = mma_state(s, c4);
+          if (j < Q) so[j * TTB_TILE] = X[s] * inv;
+        }
+      }
+      if (scale) Facc -= scale * (256.0 * 0.693147180559945309417232121458);
+      if (Z < 1e-150 || Z > 1e150) {
+        Facc += log(Z);
+      } else {
+        Zprod *= Z;
+        if (Zprod < 1e-150 || Zprod > 1e150) {
+          Facc += log(Zprod);
+          Zprod = 1.0;
+        }
+      }
+    }
+    c = cn;
+    code = ncode;
+  }
+  if (act && c4 == 0) p.Fpart[(size_t)(fbase + g_) * p.ld + a] = Facc + log(Zprod);
+}

@@ -178,6 +178,12 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
         ++nk;
       }
     }
+#if TTB_Q > 8
+    if (use_mma)
+      launch_pdl(post_leaf_mma_kernel<Q>, (unsigned)((long long)L.n_groups * tiles), 512, 0, s, d, pl.d_post_chunks,
+                 pl.d_post_group_ptr + L.group_off, tiles, 0);
+    else
+#endif
     launch_pdl(post_leaf_level_kernel<Q, false, ST>, (unsigned)((long long)L.n_groups * tiles), TTB_BLOCK, 0, s, d, pl.d_post_chunks,
                pl.d_post_group_ptr + L.group_off, tiles, 0, pairs);
     ++nk;
