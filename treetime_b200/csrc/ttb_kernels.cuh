@@ -226,6 +226,16 @@ __device__ __forceinline__ double msg_ld(const double* base, size_t off, int f32
   return f32 ? (double)reinterpret_cast<const float*>(base)[off] : base[off];
 }
 
+// 1/a without the IEEE slow path: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps -> within 1 ulp for normal a;
+// 0 -> NaN like the exact quotient's inf * 0 in the reference's log-space form, so a vanished message surfaces the same way.
+__device__ __forceinline__ double fast_rcp(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  return fma(r, e, r);
+}
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -966,7 +976,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
       double Z = X[0];
 #pragma unroll
       for (int j = 1; j < Q; ++j) Z += X[j];
-      const double inv = 1.0 / Z;
+      const double inv = fast_rcp(Z);
       ST* __restrict__ so = msg_base<ST>(p.S) + msg_off<Q>(p, c.out, a);
 #pragma unroll
       for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = (ST)(X[j] * inv);
@@ -1014,7 +1024,7 @@ __global__ void leaf_pair_table_kernel(TtbDev p, const TtbChunk* __restrict__ ch
     double Z = X[0];
 #pragma unroll
     for (int j = 1; j < Q; ++j) Z += X[j];
-    const double inv = 1.0 / Z;
+    const double inv = fast_rcp(Z);
 #pragma unroll
     for (int j = 0; j < Q; ++j) out[(size_t)e * TTB_PAIR_STRIDE(Q) + j] = X[j] * inv;
     out[(size_t)e * TTB_PAIR_STRIDE(Q) + Q] = log(Z);
@@ -1115,7 +1125,7 @@ __global__ void __launch_bounds__(TTB_BLOCK) post_leaf_level_kernel(TtbDev p, co
       double Z = X[0];
 #pragma unroll
       for (int j = 1; j < Q; ++j) Z += X[j];
-      const double inv = 1.0 / Z;
+      const double inv = fast_rcp(Z);
       ST* __restrict__ so = msg_base<ST>(p.S) + msg_off<Q>(p, c.out, a);
 #pragma unroll
       for (int j = 0; j < Q; ++j) so[j * TTB_TILE] = (ST)(X[j] * inv);
@@ -1577,7 +1587,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
             msg[i] = ((MASK && mo) ? 1.0 : msg[i]) * Sc[i];
             z += msg[i];
           }
-          const double inv = 1.0 / z;
+          const double inv = fast_rcp(z);
           double bv = -1.0;
 #pragma unroll
           for (int i = 0; i < Q; ++i) {

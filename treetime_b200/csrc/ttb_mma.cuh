@@ -42,16 +42,6 @@ struct MmaQ {
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-// 1/a without the IEEE slow path: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps -> within 1 ulp for normal a;
-// 0 -> NaN like the exact quotient's inf * 0 further down, so a vanished message surfaces the same way.
-__device__ __forceinline__ double fast_rcp(double a) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-  double e = fma(-a, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-a, r, 1.0);
-  return fma(r, e, r);
-}
 __device__ __forceinline__ double quad_sum(double x) {   // sum over the four lanes that share a pattern
   x += __shfl_xor_sync(0xffffffffu, x, 1);
   x += __shfl_xor_sync(0xffffffffu, x, 2);
