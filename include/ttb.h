@@ -188,8 +188,9 @@ int ttb_fetch_all_seq_idx(ttb_handle h, uint8_t* out);
 
 /* Sparse form of the reconstructed sequences: root_idx[n_patterns] plus every (node, pattern, state) where
  * an internal node's state differs from its parent's (what `node.mutations` lists, treeanc.py:27-42, on
- * compressed patterns).  Up to max_n entries are written (unordered); *n receives the total count, so a
- * caller that passed too small a buffer can retry.  Synchronous. */
+ * compressed patterns).  The first max_n entries are written, ordered by (node, pattern) -- the device lays them out
+ * in that order (count per node, scan, ordered write; no sort anywhere); *n receives the total count, so a caller that
+ * passed too small a buffer can retry.  Synchronous. */
 int ttb_fetch_mutations(ttb_handle h, uint8_t* root_idx, int32_t max_n, int32_t* node, int32_t* pos, uint8_t* state,
                         int64_t* n);
 

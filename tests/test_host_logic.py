@@ -175,3 +175,49 @@ def test_vectorised_branch_length_floor_and_override():
     n2 = t2._flat().nodes
     assert np.array_equal(t2._branch_lengths_to_gtr(n2), np.array([t2._branch_length_to_gtr(n) for n in n2]))
     assert np.array_equal(t2._branch_lengths_to_gtr(n2)[1:], 2.0 * per_node[1:])
+
+
+def test_fastscan_equals_python_scans(monkeypatch):
+    """csrc/ttb_fastscan.c (optional host helper): the C loops over the nodes' dicts give what the numpy / map() forms
+    give, report 'cannot' on anything they do not handle, and the mirror's per-pass scans agree with and without them."""
+    import oracle_engine
+    from treetime_b200 import _fastscan
+    from treetime_b200.treeanc import TreeAnc
+    _fastscan.build()
+    assert _fastscan.load() is not None
+
+    class Node(object):
+        def __init__(self, i):
+            self.branch_length = 0.25 * i
+            self.mask = None
+    nodes = [Node(i) for i in range(1000)]
+    nodes[3].branch_length = 7                     # int
+    nodes[4].branch_length = np.float64(1.5)       # float subclass
+    dicts = [n.__dict__ for n in nodes]
+    out = np.full(1000, -1.0)
+    assert _fastscan.scan_float_attr(dicts, 'branch_length', out, 1)
+    assert out[0] == -1.0 and np.array_equal(out[1:], np.array([float(n.branch_length) for n in nodes[1:]]))
+    assert _fastscan.any_not_none(dicts, 'mask') is False
+    nodes[999].mask = np.zeros(3)
+    assert _fastscan.any_not_none(dicts, 'mask') is True
+    nodes[10].branch_length = None
+    assert not _fastscan.scan_float_attr(dicts, 'branch_length', out, 1)          # None: the caller's generic path decides
+    del nodes[10].__dict__['branch_length']
+    assert not _fastscan.scan_float_attr(dicts, 'branch_length', out, 1)          # missing attribute
+    assert not _fastscan.scan_float_attr(dicts, 'branch_length', np.zeros(1000, dtype=np.float32), 1)
+    assert _fastscan.any_not_none(tuple(dicts), 'mask') is None                     # not a list: cannot tell
+
+    tree = synth.random_tree(40, seed=5, mean_bl=1e-3, zero_frac=0.2)
+    g = util.nuc_gtr()
+    aln = {k: g.alphabet[v] for k, v in synth.evolve_alignment(tree, 90, g.Pi, g.W, seed=5).items()}
+    tt = TreeAnc(tree=tree.to_newick(), aln=aln, gtr=g, engine_factory=oracle_engine.factory)
+    flat_nodes = tt._flat().nodes
+    fast = tt._branch_lengths_to_gtr(flat_nodes)
+    monkeypatch.setattr(_fastscan, 'scan_float_attr', lambda *a, **k: False)
+    monkeypatch.setattr(_fastscan, 'any_not_none', lambda *a, **k: None)
+    assert np.array_equal(tt._branch_lengths_to_gtr(flat_nodes), fast)
+    tt.infer_ancestral_sequences(marginal=True)
+    lh = tt.tree.total_sequence_LH
+    monkeypatch.undo()
+    tt.infer_ancestral_sequences(marginal=True)
+    assert tt.tree.total_sequence_LH == lh

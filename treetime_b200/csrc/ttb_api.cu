@@ -155,6 +155,7 @@ struct ttb_engine {
   DBuf<int> d_seqrow, d_flag;
   long long aln_rows = 0, aln_L = 0;
   DBuf<int> d_mut_node, d_mut_pos, d_ent_row, d_ent_pos;
+  DBuf<long long> d_mut_offsets;
   DBuf<unsigned long long> d_mut_count;   // d_bstage: packed byte staging for contiguous H2D / D2H
   DBuf<unsigned long long> d_nd;
   DBuf<int> d_enodes, d_ekinds, d_pair_first;
@@ -647,7 +648,7 @@ int ttb_destroy(ttb_handle h) {
   h->d_bstage.release();
   h->d_TC.release(); h->d_Cx.release(); h->d_jpre_int.release(); h->d_jpre_all.release();
   h->d_mut_state.release(); h->d_mut_node.release(); h->d_mut_pos.release(); h->d_ent_row.release(); h->d_ent_pos.release();
-  h->d_mut_count.release();
+  h->d_mut_count.release(); h->d_mut_offsets.release();
   h->d_aln.release(); h->d_colstat.release(); h->d_lut.release(); h->d_constl.release(); h->d_firstpos.release();
   h->d_seqrow.release(); h->d_flag.release();
   h->d_nd.release();
@@ -1400,12 +1401,15 @@ int ttb_fetch_mutations(ttb_handle h, uint8_t* root_idx, int32_t max_n, int32_t*
   if ((rc = h->d_mut_pos.alloc(std::max(h->d_mut_pos.n, (size_t)std::max(max_n, 1))))) return rc;
   if ((rc = h->d_mut_state.alloc(std::max(h->d_mut_state.n, (size_t)std::max(max_n, 1))))) return rc;
   if ((rc = h->d_mut_count.alloc(1))) return rc;
+  if ((rc = h->d_mut_offsets.alloc((size_t)h->n_nodes))) return rc;
   cudaStream_t s = h->stream;
-  CK(cudaMemsetAsync(h->d_mut_count.p, 0, sizeof(unsigned long long), s));
-  const int chunks = std::max(1, std::min(h->n_nodes - 1, (h->n_sm * 16 + h->tiles() - 1) / h->tiles()));
-  mutations_kernel<<<dim3(h->tiles(), chunks), TTB_BLOCK, 0, s>>>(h->dev(), max_n, h->d_mut_node.p, h->d_mut_pos.p, h->d_mut_state.p,
-                                                                  h->d_mut_count.p);
-  h->launches += 1;
+  if (h->n_nodes > 1) {
+    mut_count_kernel<<<h->n_nodes - 1, 256, 0, s>>>(h->dev(), h->d_mut_offsets.p);
+    mut_scan_kernel<<<1, 1024, 0, s>>>(h->d_mut_offsets.p, h->n_nodes, h->d_mut_count.p);
+    mut_write_kernel<<<h->n_nodes - 1, 256, 0, s>>>(h->dev(), h->d_mut_offsets.p, (long long)max_n, h->d_mut_node.p, h->d_mut_pos.p, h->d_mut_state.p);
+    h->launches += 3;
+  } else
+    CK(cudaMemsetAsync(h->d_mut_count.p, 0, sizeof(unsigned long long), s));
   CK(cudaGetLastError());
   unsigned long long cnt = 0;
   CK(cudaMemcpyAsync(&cnt, h->d_mut_count.p, sizeof cnt, cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,54 @@
+/* ttb_fastscan.c -- host-side helper of the Python mirror, NOT part of the C-ABI (include/ttb.h): per-pass scans over
+ * the tree's node objects at C speed.  A pass needs every node's branch length (treeanc.py:752-760 reads
+ * node.branch_length / node.mutation_length per node) and has to know whether any node carries a mask (arg.py:128-133);
+ * on a 40 000-node tree the numpy.fromiter / map() forms of these scans cost 3.4 + 2 ms next to a 14 ms device pass.
+ * Loaded with ctypes.PyDLL (the GIL is held); every function works on a list of the nodes' instance dicts and reports
+ * "cannot" (-1) instead of guessing, so that the caller falls back to the generic Python path. */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+
+/* out[i] = float(dicts[i][key]) for start <= i < len(dicts).  Returns 0, or -1 if an entry is missing / not a number. */
+int ttb_scan_float_attr(PyObject* dicts, PyObject* key, double* out, Py_ssize_t start) {
+  if (!PyList_CheckExact(dicts)) return -1;
+  const Py_ssize_t n = PyList_GET_SIZE(dicts);
+  for (Py_ssize_t i = start; i < n; ++i) {
+    PyObject* d = PyList_GET_ITEM(dicts, i);
+    if (!PyDict_CheckExact(d)) return -1;
+    PyObject* v = PyDict_GetItemWithError(d, key); /* borrowed */
+    if (!v) {
+      PyErr_Clear();
+      return -1;
+    }
+    if (PyFloat_Check(v))
+      out[i] = PyFloat_AS_DOUBLE(v);
+    else if (PyLong_Check(v)) {
+      out[i] = PyLong_AsDouble(v);
+      if (out[i] == -1.0 && PyErr_Occurred()) {
+        PyErr_Clear();
+        return -1;
+      }
+    } else
+      return -1;
+  }
+  return 0;
+}
+
+/* 1 if dicts[i].get(key) is not None for some i, 0 if for none, -1 if the argument is not a list of dicts. */
+int ttb_any_not_none(PyObject* dicts, PyObject* key) {
+  if (!PyList_CheckExact(dicts)) return -1;
+  const Py_ssize_t n = PyList_GET_SIZE(dicts);
+  for (Py_ssize_t i = 0; i < n; ++i) {
+    PyObject* d = PyList_GET_ITEM(dicts, i);
+    if (!PyDict_CheckExact(d)) return -1;
+    PyObject* v = PyDict_GetItemWithError(d, key);
+    if (!v) {
+      if (PyErr_Occurred()) {
+        PyErr_Clear();
+        return -1;
+      }
+      continue;
+    }
+    if (v != Py_None) return 1;
+  }
+  return 0;
+}

@@ -1320,23 +1320,113 @@ static __global__ void scatter_codes_kernel(const int* __restrict__ row, const i
 // Sparse result: the reconstructed sequences as (node, pattern, state) wherever an internal node's
 // state differs from its parent's (the content of `node.mutations`, treeanc.py:27-42, on compressed
 // patterns) -- together with the root row this determines every sequence.  grid = (tiles, node chunks).
-static __global__ void mutations_kernel(TtbDev p, int max_n, int* __restrict__ out_node, int* __restrict__ out_pos,
-                                        uint8_t* __restrict__ out_state, unsigned long long* __restrict__ counter) {
-  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= p.Lp) return;
-  for (int n = 1 + blockIdx.y; n < p.n_nodes; n += gridDim.y) {
-    const int slot = p.int_slot[n];
-    if (slot < 0) continue;
-    const uint8_t s = p.idx[(size_t)slot * p.ld + a];
-    const uint8_t ps = p.idx[(size_t)p.int_slot[p.parent[n]] * p.ld + a];
-    if (s != ps) {
-      const unsigned long long k = atomicAdd(counter, 1ull);
-      if (k < (unsigned long long)max_n) {
-        out_node[k] = n;
-        out_pos[k] = (int)a;
-        out_state[k] = s;
-      }
+// Sparse form of the reconstructed sequences, ORDERED by (node, position) without a sort: one block per node counts
+// the positions whose state differs from the parent's (mut_count_kernel), a single-block scan turns the counts into
+// offsets (mut_scan_kernel), and the same walk writes every node's entries in position order (mut_write_kernel:
+// ballot-free block scan of the per-thread counts of 16 positions).  State rows are read as 16-byte words.
+__device__ __forceinline__ unsigned int mut_diff_mask(const uint4& x, const uint4& y, long long a, long long Lp) {
+  // bit i set: position a + i differs (positions >= Lp are padding)
+  const unsigned int w[4] = {__vcmpne4(x.x, y.x), __vcmpne4(x.y, y.y), __vcmpne4(x.z, y.z), __vcmpne4(x.w, y.w)};
+  unsigned int m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) m |= ((w[i] >> (8 * b)) & 1u) << (4 * i + b);
+  const long long left = Lp - a;
+  return left >= 16 ? m : (left <= 0 ? 0u : (m & ((1u << left) - 1u)));
+}
+static __global__ void __launch_bounds__(256) mut_count_kernel(TtbDev p, long long* __restrict__ counts) {
+  __shared__ int sred[8];
+  const int n = blockIdx.x + 1;
+  const int slot = p.int_slot[n];
+  if (n == 1 && threadIdx.x == 0) counts[0] = 0;   // the root has no parent
+  if (slot < 0) {
+    if (threadIdx.x == 0) counts[n] = 0;
+    return;
+  }
+  const uint4* row = reinterpret_cast<const uint4*>(p.idx + (size_t)slot * p.ld);
+  const uint4* prow = reinterpret_cast<const uint4*>(p.idx + (size_t)p.int_slot[p.parent[n]] * p.ld);
+  int c = 0;
+  for (long long a = 16LL * threadIdx.x; a < p.Lp; a += 16LL * 256) c += __popc(mut_diff_mask(row[a >> 4], prow[a >> 4], a, p.Lp));
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += sred[w];
+    counts[n] = t;
+  }
+}
+// exclusive scan of counts[0..n) in place; total -> *total.  One block of 1024 threads.
+static __global__ void __launch_bounds__(1024) mut_scan_kernel(long long* __restrict__ counts, int n, unsigned long long* __restrict__ total) {
+  __shared__ long long part[1024];
+  const int per = (n + 1023) / 1024, lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  long long s = 0;
+  for (int i = lo; i < hi; ++i) s += counts[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const long long v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  long long run = part[threadIdx.x] - s;
+  for (int i = lo; i < hi; ++i) {
+    const long long c = counts[i];
+    counts[i] = run;
+    run += c;
+  }
+  if (threadIdx.x == 1023) *total = (unsigned long long)part[1023];
+}
+static __global__ void __launch_bounds__(256) mut_write_kernel(TtbDev p, const long long* __restrict__ offsets, long long max_n,
+                                                               int* __restrict__ out_node, int* __restrict__ out_pos, uint8_t* __restrict__ out_state) {
+  __shared__ int wsum[8];
+  const int n = blockIdx.x + 1;
+  const int slot = p.int_slot[n];
+  if (slot < 0) return;
+  const uint8_t* rowb = p.idx + (size_t)slot * p.ld;
+  const uint4* row = reinterpret_cast<const uint4*>(rowb);
+  const uint4* prow = reinterpret_cast<const uint4*>(p.idx + (size_t)p.int_slot[p.parent[n]] * p.ld);
+  long long base = offsets[n];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long a0 = 0; a0 < p.Lp; a0 += 16LL * 256) {
+    const long long a = a0 + 16LL * threadIdx.x;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    unsigned int m = 0;
+    if (a < p.Lp) {
+      x = row[a >> 4];
+      m = mut_diff_mask(x, prow[a >> 4], a, p.Lp);
     }
+    const int c = __popc(m);
+    int inc = c;   // inclusive scan over the block, in thread (= position) order
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += v;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      before += w < warp ? wsum[w] : 0;
+      all += wsum[w];
+    }
+    long long k = base + before + inc - c;
+    const unsigned int xs[4] = {x.x, x.y, x.z, x.w};
+    while (m) {
+      const int i = __ffs(m) - 1;
+      m &= m - 1;
+      if (k < max_n) {
+        out_node[k] = n;
+        out_pos[k] = (int)(a + i);
+        out_state[k] = (uint8_t)(xs[i >> 2] >> (8 * (i & 3)));
+      }
+      ++k;
+    }
+    base += all;
+    __syncthreads();
   }
 }
 

@@ -9,6 +9,7 @@ import operator
 
 import numpy as np
 
+from . import _fastscan
 from . import config as ttconf
 from .brent import brent_lockstep
 from .dist import default_comm, shard_bounds
@@ -221,7 +222,9 @@ class DeviceMarginalMixin(object):
         n = len(nodes)
         vals = np.empty(n, dtype=np.float64)
         try:        # instance attributes straight from the nodes' dicts, no list of boxed floats in between
-            vals[1:] = np.fromiter(map(operator.itemgetter(attr), self._node_dicts(nodes)[1:]), dtype=np.float64, count=n - 1)
+            dicts = self._node_dicts(nodes)
+            if not _fastscan.scan_float_attr(dicts, attr, vals, 1):        # C loop over the dicts (3.4 -> 0.5 ms at 40 000 nodes)
+                vals[1:] = np.fromiter(map(operator.itemgetter(attr), dicts[1:]), dtype=np.float64, count=n - 1)
             root_val = nodes[0].__dict__.get(attr)
         except (KeyError, TypeError, ValueError):           # properties, slots, None on a non-root node
             vals = np.array(list(map(operator.attrgetter(attr), nodes)), dtype=np.float64)      # None -> nan
@@ -259,8 +262,13 @@ class DeviceMarginalMixin(object):
         """Per-branch masks (node.mask, set by arg.py:128-133): distinct 0/1 vectors over the patterns + one index per
         node.  Fractional masks have no device form (a masked message is dropped, not scaled)."""
         from itertools import repeat
-        node_masks = list(map(dict.get, self._node_dicts(topo.nodes), repeat('mask')))   # instance attribute on both clade classes
-        if not any(map(operator.is_not, node_masks, repeat(None))):      # identity, not ==: masks are arrays
+        dicts = self._node_dicts(topo.nodes)
+        # one lazy C-speed pass in the common case (no node has a mask); the list is only built otherwise
+        masked = _fastscan.any_not_none(dicts, 'mask')
+        if masked is None:
+            masked = any(map(operator.is_not, map(dict.get, dicts, repeat('mask')), repeat(None)))     # identity, not ==: masks are arrays
+        node_masks = list(map(dict.get, dicts, repeat('mask'))) if masked else None
+        if not masked:
             if self._device_masks is not None:
                 eng.set_branch_masks(None, None)
                 self._device_masks = None

@@ -244,8 +244,7 @@ class Engine(object):
                 break
             max_n = int(n.value)
         m = int(n.value)
-        order = np.lexsort((pos[:m], node[:m]))
-        return root, node[:m][order], pos[:m][order], st[:m][order]
+        return root, node[:m], pos[:m], st[:m]          # the library returns them ordered by (node, pos)
 
     def enqueue_site_lh(self, out):
         """Stream-ordered D2H of tree.sequence_LH into `out` (pinned); valid after sync()."""
