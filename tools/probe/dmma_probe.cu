@@ -30,6 +30,23 @@ __global__ void dmma884_kernel(double* out, int iters, double a, double b) {
   for (int k = 0; k < CH; ++k) s += c0[k] + c1[k];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// DMMA with distinct operand registers per instruction (the level kernels' situation: 15 fragments x m-tiles), not one
+// shared (a, b) pair: does operand collection cost pipe cycles?
+template <int CH>
+__global__ void dmma884_distinct_kernel(double* out, const double* in, int iters) {
+  double c0[CH], c1[CH], a[CH], b[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) { c0[k] = threadIdx.x + k; c1[k] = k; a[k] = in[threadIdx.x + 32 * k]; b[k] = in[threadIdx.x + 32 * k + 7]; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[k]), "+d"(c1[k]) : "d"(a[k]), "d"(b[(k + 3) % CH]));
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) s += c0[k] + c1[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 // dependent-issue latencies: one chain per warp, one warp per SMSP
 __global__ void lat_kernel(double* out, int iters, double a, double b, long long* clk) {
   double x = threadIdx.x, c0 = threadIdx.x, c1 = 1.0, r = threadIdx.x + 1.5;
@@ -117,6 +134,9 @@ int main() {
     fma = (double)blocks * (threads / 32) * 2.0 * iters * 256.0;
     printf("DMMA 884 (2 chains) warps/SM %2d: %.3f ms  %.2f TFLOP/s  -> latency %.1f clk per dependent mma at 1 warp/SMSP\n", wps, ms, 2 * fma / ms * 1e-9, ms * 1e-3 * 1.965e9 / (2.0 * iters) );
     if (wps == 16) {
+      ms = time_it([&] { dmma884_distinct_kernel<8><<<blocks, threads>>>(out, out + 4096, iters); });
+      fma = (double)blocks * (threads / 32) * 8.0 * iters * 256.0;
+      printf("DMMA 884 distinct operand registers, %d warps/SM: %.3f ms  %.2f TFLOP/s  (%.1f FMA/clk/SM)\n", wps, ms, 2 * fma / ms * 1e-9, fma / (ms * 1e-3) / sms / 1.965e9);
       ms = time_it([&] { mixed_kernel<2><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
       double per = ms * 1e-3 * 1.965e9 / (4.0 * iters) / (wps / 4);   // clocks per (1 DMMA + 2 DFMA) group per SMSP
       printf("MIXED 1 DMMA : 2 DFMA, %d warps/SM: %.3f ms -> %.1f clk per group per SMSP (DMMA alone 16, 2 DFMA alone ~4.4: shared pipe ~20.4)\n", wps, ms, per);

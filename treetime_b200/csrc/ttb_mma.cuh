@@ -422,18 +422,21 @@ __global__ void __launch_bounds__(MmaCfg<Q, NW>::THREADS) __maxnreg__((MmaCfg<Q,
     for (int mt = 0; mt < MT; ++mt) {
       const double z = quad_sum(slot_sum<KS>(pr[mt]));
       // first maximum of the unnormalised profile (the normaliser is positive), in parallel with the normaliser's chain
-      double bv = -1.0;
+      // (the entries are >= 0, so their order is the order of their bit patterns as integers: the compares run on the
+      // integer pipe instead of queueing behind the DMMAs on the fp64 pipe)
+      long long bv = -1;
       int best = 0;
 #pragma unroll
       for (int k = 0; k < KS; ++k) {   // slots are in increasing state order
         const int i = mma_state(k, c4);
-        const bool take = (i < Q) & (pr[mt][k] > bv);
-        bv = take ? pr[mt][k] : bv;
+        const long long v = __double_as_longlong(pr[mt][k]);
+        const bool take = (i < Q) & (v > bv);
+        bv = take ? v : bv;
         best = take ? i : best;
       }
 #pragma unroll
       for (int d = 1; d <= 2; d <<= 1) {       // over the four lanes of the pattern
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, d);
+        const long long ov = __shfl_xor_sync(0xffffffffu, bv, d);
         const int ob = __shfl_xor_sync(0xffffffffu, best, d);
         const bool take = (ov > bv) | ((ov == bv) & (ob < best));
         bv = take ? ov : bv;
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(MmaCfg<Q, NW>::THREADS) __maxnreg__((MmaCfg<Q,
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
         const int j = mma_state(k, c4);
-        U[mt][k] = (j < Q) ? Mp[mt][k] * fast_rcp(U[mt][k]) : 0.0;
+        U[mt][k] = (j < Q) ? Mp[mt][k] * fast_rcp1(U[mt][k]) : 0.0;   // 1e-12 relative: far inside the profiles' 1e-6
       }
     mma_product<MT, KS>(U, reinterpret_cast<const double2*>(pipe.P(s) + PFQ) + lane, pr);
 #pragma unroll
