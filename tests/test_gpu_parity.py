@@ -107,6 +107,58 @@ def test_other_alphabets(alphabet, q):
     compare_all(flat, g, eng, res, every=3)
 
 
+@pytest.mark.parametrize('alphabet,q,nw', [('aa_nogap', 20, None), ('aa', 22, None), ('aa_nogap', 20, '4'), ('aa_nogap', 20, '8'),
+                                           ('aa', 22, '16')])
+def test_large_alphabet_tensor_pipe_kernels(alphabet, q, nw, monkeypatch):
+    """q >= 20 level kernels on the fp64 tensor pipe (csrc/ttb_mma.cuh): polytomies up to a 40-child star (power-of-two
+    rescaling across the four lanes of a pattern), ambiguous characters, a ragged third tile, reconstructed tips, N_diff,
+    every compiled warp count, and agreement with the one-thread-per-pattern kernels (TTB_NO_MMA=1)."""
+    if nw:
+        monkeypatch.setenv('TTB_MMA_NW', nw)
+    gtr = util.random_gtr(alphabet, 21)
+    assert gtr.n_states == q
+    tree = synth.random_tree(90, seed=31, mean_bl=0.08, polytomy_frac=0.3)
+    topo, flat, g = util.make_flat(tree, gtr, 300, 31, amb_frac=0.03, amb_chars='X' if alphabet == 'aa_nogap' else 'X-')
+    Lp = flat['multiplicity'].shape[0]
+    assert 256 < Lp and Lp % 128 != 0
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    tot, nd = eng.results()
+    res = O.marginal(flat, g)
+    assert abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH) and nd == res.N_diff
+    compare_all(flat, g, eng, res, every=2)
+    eng.marginal()
+    assert eng.results() == (tot, 0)
+    eng.marginal(reconstruct_tips=True)
+    res_t = O.marginal(flat, g, reconstruct_tip_states=True)
+    compare_all(flat, g, eng, res_t, reconstruct_tips=True, every=3)
+    seq_mma, prof_mma = eng.all_seq_idx(), [eng.node_array(n, 2) for n in range(0, flat['parent'].shape[0], 7)]
+    monkeypatch.setenv('TTB_NO_MMA', '1')
+    old = util.engine_for(flat, g)
+    old.marginal(reconstruct_tips=True)
+    assert abs(old.results()[0] - tot) <= 1e-12 * abs(tot)
+    prof_old = [old.node_array(n, 2) for n in range(0, flat['parent'].shape[0], 7)]
+    assert max(np.abs(a - b).max() for a, b in zip(prof_mma, prof_old)) < 1e-10
+    differ = seq_mma != old.all_seq_idx()
+    assert differ.mean() < 1e-4          # exact ties aside, the two kernel families reconstruct the same sequences
+
+
+def test_large_alphabet_star_tree_rescaling():
+    """A 3 000-child star at q = 20: the running product of the up-messages leaves the double range many times; the
+    tensor-pipe postorder rescales by exact powers of two per pattern (max over the four lanes that share it)."""
+    from treetime_b200.tree import Node, Tree
+    gtr = util.random_gtr('aa_nogap', 5)
+    rng = np.random.default_rng(4)
+    tree = Tree(Node(clades=[Node(name='t%06d' % i, branch_length=float(b)) for i, b in enumerate(rng.exponential(0.5, 3000))]))
+    topo, flat, g = util.make_flat(tree, gtr, 140, 4)
+    eng = util.engine_for(flat, g)
+    eng.marginal()
+    tot, nd = eng.results()
+    res = O.marginal(flat, g)
+    assert np.isfinite(tot) and abs(tot - res.total_LH) <= LH_RTOL * abs(res.total_LH)
+    compare_all(flat, g, eng, res, every=500)
+
+
 @pytest.mark.parametrize('approximate', [True, False])
 def test_site_specific_gtr(approximate):
     """gtr_site_specific.py: per-site Pi/mu, interpolated (default) and exact exp(Qt)."""

@@ -81,18 +81,11 @@ int prepare_t(const TtbDev& d) {
 // Tensor-pipe level kernels (ttb_mma.cuh): NW pattern warps per block, chosen at run time (TTB_MMA_NW, measurement knob).
 // Pattern warps per block (measurement knobs TTB_MMA_NW_POST / TTB_MMA_NW_PRE, TTB_MMA_NW for both).  Defaults from the
 // cfg4 sweep (profiles/R2p_mma_sweep.txt): postorder 8 warps x 2 blocks per SM, preorder 16 warps x 1 block.
-int mma_nw(bool pre) {
-  static const int nw[2] = {[] {
-                              const char* e = getenv("TTB_MMA_NW_POST") ? getenv("TTB_MMA_NW_POST") : getenv("TTB_MMA_NW");
-                              const int v = e ? atoi(e) : 8;
-                              return (v == 4 || v == 8 || v == 16) ? v : 8;
-                            }(),
-                            [] {
-                              const char* e = getenv("TTB_MMA_NW_PRE") ? getenv("TTB_MMA_NW_PRE") : getenv("TTB_MMA_NW");
-                              const int v = e ? atoi(e) : 16;
-                              return (v == 4 || v == 8 || v == 16) ? v : 16;
-                            }()};
-  return nw[pre ? 1 : 0];
+int mma_nw(bool pre) {   // read at enqueue time (graph capture), so a test can select a variant per engine
+  const char* e = getenv(pre ? "TTB_MMA_NW_PRE" : "TTB_MMA_NW_POST");
+  if (!e) e = getenv("TTB_MMA_NW");
+  const int dflt = pre ? 16 : 8, v = e ? atoi(e) : dflt;
+  return (v == 4 || v == 8 || v == 16) ? v : dflt;
 }
 template <int NW>
 size_t mma_post_smem(const TtbDev& d) { return MmaCfg<Q, NW>::PipeT::smem_bytes(Q, MmaQ<Q>::PFQ, d.tu_stride); }
