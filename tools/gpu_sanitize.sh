@@ -16,7 +16,7 @@ def run(gtr, n, L, seed, mean_bl=0.01, **kw):
     eng.marginal(lh_only=True); eng.results()
     nodes=np.arange(1,flat['parent'].shape[0],dtype=np.int32)
     eng.branch_objective(nodes, np.full(nodes.shape[0],0.01)); eng.branch_hamming(nodes)
-    eng.node_array(3,1); eng.all_seq_idx()
+    eng.node_array(3,1); eng.all_seq_idx(); eng.mutations()
     if not g['site_specific']:
         eng.mutation_counts()
         eng.joint(); eng.results(); eng.joint(reconstruct_tips=True); eng.results(); eng.all_seq_idx()
