@@ -401,7 +401,10 @@ void site_counts_q(const TtbDev& d, int tiles, int chunks, int chunk, double* pa
     }
   }
   if (!done) site_counts_kernel<Q, false><<<dim3(tiles, chunks), TTB_BLOCK, 0, s>>>(d, chunk, partial);
-  site_counts_reduce_kernel<<<148 * 4, 256, 0, s>>>(partial, chunks, (long long)(Q * Q + Q) * d.ld, out);
+  int dev = 0, n_sm = 0;   // grid-stride reduction: four blocks per multiprocessor of the current device
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  site_counts_reduce_kernel<<<std::max(1, n_sm) * 4, 256, 0, s>>>(partial, chunks, (long long)(Q * Q + Q) * d.ld, out);
 }
 void sample_states_q(const TtbDev& d, int tiles, int n, const int* nodes, const double* uniforms, const uint8_t* prev_idx,
                      const uint8_t* prev_idxtip, unsigned long long* counts, cudaStream_t s) {
