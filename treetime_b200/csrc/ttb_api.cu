@@ -375,6 +375,11 @@ void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm
   // the postorder, one in the preorder -- so that a block's start-up (~2-4 us: barriers, descriptors, first bulk copy) is
   // paid once per level (cfg4 sweep, profiles/R2p_mma_sweep.txt: 888 -> 296 / 148 blocks: 1.76 -> 1.63 ms per pass)
   if (mma) target_blocks = post_order ? (long long)n_sm * 2 : (long long)n_sm;
+  // single-model kernels of the small alphabets: ONE whole wave of the 3 resident blocks per SM as well (cfg2 sweep,
+  // profiles/R2aa_cfg2_grouping.txt: 296 / 444 / 592 / 888 / 1332 blocks per level -> 0.80 / 0.71 / 0.81 / 0.73 / 0.77 ms:
+  // whole waves win, one beats two); big levels exceed it anyway through the run-length cap
+  const bool one_wave = mma || !site_specific;
+  if (!site_specific && !mma) target_blocks = (long long)n_sm * 3;
   if (const char* e = getenv("TTB_TARGET_BLOCKS")) target_blocks = std::max(1LL, atoll(e));   // tuning knobs (measurement only)
   if (const char* e = getenv("TTB_MAX_GROUP")) max_group = std::max(1LL, atoll(e));
   long long ss_waves = 4;
@@ -423,7 +428,9 @@ void build_groups(Sched& sc, int tiles, bool site_specific, int ss_blocks_per_sm
       }
     } else {
       G = ((long long)n * tiles + target_blocks - 1) / target_blocks;
-      if (mma) {   // never more blocks than one wave holds: a few blocks beyond it would double the level's duration
+      if (one_wave && !(post_order && l == 0 && !mma)) {
+        // never more blocks than one wave holds: a few blocks beyond it would double the level's duration (the leaf level
+        // of the small alphabets has its own, unpipelined kernel with 10 resident blocks per SM and keeps the plain rule)
         const long long groups_max = std::max(1LL, target_blocks / tiles);
         G = (n + groups_max - 1) / groups_max;
       }
