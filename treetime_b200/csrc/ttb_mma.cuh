@@ -16,8 +16,8 @@
 // operand -- no layout conversion between the two chained products of the preorder:
 //    U[pat][j]   = sum_i S[pat][i] P[i][j]     A = S (slot kap),  B1[kap][nt'] : lane (g,c) holds P[8nt+2c+r][8nt'+g]
 //    msg[pat][i] = sum_j O[pat][j] P[i][j]     A = O (slot kap),  B2[kap][nt'] : lane (g,c) holds P[8nt'+g][8nt+2c+r]
-// The B fragments of every branch are laid out in this order by pfrag_kernel (36 fragments x 32 lanes, zero-padded) so a
-// stage receives them with one bulk copy and a lane reads its element conflict-free.
+// The B fragments of every branch are laid out in this order by expqt_frag_kernel (pairs of fragments per lane,
+// zero-padded) so a stage receives them with one bulk copy and a lane reads its elements conflict-free.
 //
 // Reference semantics are those of post_level_kernel / pre_level_kernel (treeanc.py:857-930); summation order differs
 // (tolerances: log-LH 1e-9 relative, profiles 1e-6).  Single model, double storage, no masks, no joint pass: those keep
@@ -55,25 +55,61 @@ __device__ __forceinline__ double quad_max(double x) {
 // state held in register slot k by lane column c
 __device__ __forceinline__ int mma_state(int k, int c) { return k < 4 ? 8 * (k >> 1) + 2 * c + (k & 1) : 16 + 4 * (k - 4) + c; }
 
-// exp(Qt) of every branch in fragment order (see the header comment); thread = (node, fragment, lane).
+// A1 for the large alphabets in one kernel: exp(Qt) of a branch (same arithmetic and summation order as expqt_kernel, so
+// P is bit-identical) written in both layouts -- P[i][j] for the tip tables, the fetch / branch kernels, and the fragment
+// order above for the level kernels.  One warp per branch: the Q exponentials are taken once per branch (expqt_kernel
+// takes them once per row: 20x), e_k Vinv[k][j] is staged in shared memory, and both outputs are coalesced stores.
+// cfg4: expqt_kernel 45 us + pfrag_kernel 37 us -> one launch.
+#define TTB_EXPQT_WARPS 4
+#define TTB_EXPQT_NODES 2     // branches per warp (more would starve the SMs of warps at 10 000 branches): amortises the block's fragment-order index table
 template <int Q>
-__global__ void pfrag_kernel(TtbDev p, double* __restrict__ Pf) {
+__global__ void __launch_bounds__(TTB_EXPQT_WARPS * 32) expqt_frag_kernel(TtbDev p, double* __restrict__ Pf) {
   using MQ = MmaQ<Q>;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)p.n_nodes * (2 * MQ::PFQ)) return;
-  const int node = (int)(gid / (2 * MQ::PFQ)), rem2 = (int)(gid % (2 * MQ::PFQ));
-  const int which = rem2 / MQ::PFQ, rem = rem2 % MQ::PFQ;
-  // fragments are stored in pairs (one 16-byte load per lane for two fragments): rem = ((f/2)*32 + lane)*2 + f%2
-  const int f = (rem >> 6) * 2 + (rem & 1), lane = (rem >> 1) & 31, g = lane >> 2, c = lane & 3;
-  double v = 0.0;
-  if (f < MQ::NF) {
-    const int kap = f / TTB_MMA_NT, ntp = f % TTB_MMA_NT;
-    const int kidx = mma_state(kap, c);                          // contracted state of this lane in k-step kap
-    const int nidx = mma_state(2 * ntp + (g & 1), g >> 1);       // state of accumulator column 8*ntp + g
-    const int i = which ? nidx : kidx, j = which ? kidx : nidx;
-    if (i < Q && j < Q) v = p.P[(size_t)node * p.pq + i * Q + j];
+  __shared__ double sW[TTB_EXPQT_WARPS][Q * Q];   // e_k * Vinv[k][j]
+  __shared__ double sP[TTB_EXPQT_WARPS][Q * Q];
+  __shared__ double sE[TTB_EXPQT_WARPS][32];
+  __shared__ double sV[Q * Q];
+  __shared__ short sMap[2 * MQ::PFQ];             // fragment-order position -> i*Q + j of the source entry, -1 = padding
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = threadIdx.x; r < Q * Q; r += blockDim.x) sV[r] = p.v[r];
+  for (int rem2 = threadIdx.x; rem2 < 2 * MQ::PFQ; rem2 += blockDim.x) {
+    // rem2 = which * PFQ + ((f/2)*32 + lane)*2 + f%2
+    const int which = rem2 / MQ::PFQ, rem = rem2 % MQ::PFQ;
+    const int f = (rem >> 6) * 2 + (rem & 1), fl = (rem >> 1) & 31, fg = fl >> 2, fc = fl & 3;
+    int src = -1;
+    if (f < MQ::NF) {
+      const int kap = f / TTB_MMA_NT, ntp = f % TTB_MMA_NT;
+      const int kidx = mma_state(kap, fc), nidx = mma_state(2 * ntp + (fg & 1), fg >> 1);   // contracted state / state of accumulator column 8*ntp + fg
+      const int i = which ? nidx : kidx, j = which ? kidx : nidx;
+      if (i < Q && j < Q) src = i * Q + j;
+    }
+    sMap[rem2] = (short)src;
   }
-  Pf[(size_t)node * TTB_PF_STRIDE + rem2] = v;
+  __syncthreads();
+  const int node0 = (blockIdx.x * TTB_EXPQT_WARPS + warp) * TTB_EXPQT_NODES;
+  for (int node = node0; node < min(node0 + TTB_EXPQT_NODES, p.n_nodes); ++node) {
+    const double mt = p.mu[0] * p.t[node];
+    if (lane < Q) sE[warp][lane] = exp(mt * p.eig[lane]);
+    __syncwarp();
+    for (int r = lane; r < Q * Q; r += 32) sW[warp][r] = sE[warp][r / Q] * p.vinv[r];
+    __syncwarp();
+    for (int r = lane; r < Q * Q; r += 32) {
+      const int i = r / Q, j = r % Q;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < Q; ++k) acc = fma(sV[i * Q + k], sW[warp][k * Q + j], acc);
+      acc = fmax(0.0, acc);
+      sP[warp][r] = acc;
+      p.P[(size_t)node * p.pq + r] = acc;
+    }
+    __syncwarp();
+    double* __restrict__ out = Pf + (size_t)node * TTB_PF_STRIDE;
+    for (int rem2 = lane; rem2 < 2 * MQ::PFQ; rem2 += 32) {
+      const int src = sMap[rem2];
+      out[rem2] = src >= 0 ? sP[warp][src] : 0.0;
+    }
+    __syncwarp();
+  }
 }
 
 // C[mt][.] = A[mt][.] x B for the MT m-tiles of a warp; frag = this lane's column of the fragment pairs of one product.

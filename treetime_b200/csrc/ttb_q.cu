@@ -139,24 +139,24 @@ int enqueue_pass_t(const TtbPassPlan& pl, cudaStream_t s, cudaEvent_t* ev, int* 
   const int tiles = pl.tiles;
   int nk = 0;
   if (ev) cudaEventRecord(ev[0], s);
+  bool use_mma = false;   // large alphabets, single model, no masks: level kernels on the fp64 tensor pipe
+#if TTB_Q > 8
+  if constexpr (!SS && !MASK && sizeof(ST) == 8) use_mma = d.Pf != nullptr;
+#endif
   if (!SS) {
-    const int nthr = d.n_nodes * Q;
-    expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
+#if TTB_Q > 8
+    if (use_mma) {   // exp(Qt) in both layouts from one kernel
+      expqt_frag_kernel<Q><<<(d.n_nodes + TTB_EXPQT_WARPS * TTB_EXPQT_NODES - 1) / (TTB_EXPQT_WARPS * TTB_EXPQT_NODES), TTB_EXPQT_WARPS * 32, 0, s>>>(d, d.Pf);
+    } else
+#endif
+    {
+      const int nthr = d.n_nodes * Q;
+      expqt_kernel<Q><<<(nthr + 127) / 128, 128, 0, s>>>(d);
+    }
     const long long ntab = (long long)d.n_tips * d.n_codes * Q;
     tip_table_kernel<Q><<<(unsigned)((ntab + 255) / 256), 256, 0, s>>>(d, pl.d_tip_nodes);
     nk += 2;
   }
-  bool use_mma = false;   // large alphabets, single model, no masks: level kernels on the fp64 tensor pipe
-#if TTB_Q > 8
-  if constexpr (!SS && !MASK && sizeof(ST) == 8) {
-    if (d.Pf) {
-      const long long nf = (long long)d.n_nodes * (2 * MmaQ<Q>::PFQ);
-      pfrag_kernel<Q><<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(d, d.Pf);
-      ++nk;
-      use_mma = true;
-    }
-  }
-#endif
   if (ev) { cudaEventRecord(ev[1], s); pk[0] = nk; }
   const size_t psm = post_smem(d, SS, SYM);
   int l0 = 0;
