@@ -231,6 +231,21 @@ def test_branch_objective_hamming_counts():
     assert np.allclose(T_i, rT.sum(axis=-1), rtol=1e-10, atol=1e-12)
 
 
+def _check_mutation_order(flat, full, root_idx, mn, mp, ms):
+    """ttb_fetch_mutations returns exactly the (node, position, state) triples where an internal node differs from its
+    parent, ordered by (node, position) -- laid out that way by the device, no sort on either side."""
+    internal = np.nonzero(flat['tip_row'] < 0)[0]
+    slot = {int(n): k for k, n in enumerate(internal)}
+    en, ep, es = [], [], []
+    for k, n in enumerate(internal):
+        if n == 0:
+            continue
+        d = np.nonzero(full[k] != full[slot[int(flat['parent'][n])]])[0]
+        en.append(np.full(d.shape[0], n)); ep.append(d); es.append(full[k][d])
+    assert np.array_equal(root_idx, full[0])
+    assert np.array_equal(mn, np.concatenate(en)) and np.array_equal(mp, np.concatenate(ep)) and np.array_equal(ms, np.concatenate(es))
+
+
 def test_sparse_input_and_sparse_result():
     """ttb_set_patterns_sparse (reference row + differences) and ttb_fetch_mutations (root row +
     states that differ from the parent) carry the same information as the dense calls."""
@@ -258,6 +273,15 @@ def test_sparse_input_and_sparse_result():
     # a too small buffer is reported and retried
     r2, mn2, mp2, ms2 = sp.mutations(max_n=3)
     assert np.array_equal(mn2, mn) and np.array_equal(ms2, ms)
+    _check_mutation_order(flat, full, root_idx, mn, mp, ms)
+    # more patterns than one sweep of the ordered write covers (16 x 256 positions per block iteration), ragged tail
+    tree2 = synth.random_tree(30, seed=22, mean_bl=0.05)
+    topo2, flat2, g2 = util.make_flat(tree2, util.nuc_gtr(), 9000, 22, amb_frac=0.01)
+    assert flat2['multiplicity'].shape[0] > 4200 and flat2['multiplicity'].shape[0] % 16 != 0
+    e2 = util.engine_for(flat2, g2)
+    e2.marginal()
+    e2.results()
+    _check_mutation_order(flat2, e2.all_seq_idx(), *e2.mutations())
     from treetime_b200._lib import TTBError
     with pytest.raises(TTBError):
         sp.set_patterns_sparse(ref, np.array([10 ** 6], dtype=np.int32), np.array([0], dtype=np.int32), np.array([0], dtype=np.uint8),
