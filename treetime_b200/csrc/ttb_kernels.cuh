@@ -356,7 +356,9 @@ struct SiteModel {
     return (SYM ? p.ss_Ec : p.ss_E) + (size_t)(a / TTB_TILE) * ((size_t)p.ss_ngrid * Q * TTB_TILE) + (size_t)(a % TTB_TILE);
   }
   // level kernels: registers (REG) or the staged tile
-  __device__ __forceinline__ void init_level(const TtbDev& p, long long a, bool act, const double* smem_model, int tid) {
+  // `pre`: preorder kernel of the symmetric form -- rr[] then holds the clamp thresholds TINY * Pi_a[j] instead of 1 / Pi_a[j]
+  // (see up_pre / down_pre)
+  __device__ __forceinline__ void init_level(const TtbDev& p, long long a, bool act, const double* smem_model, int tid, bool pre = false) {
     lam = p.ss_eig + a; ld = p.ld; E = e_column(p, a);
     mu = act ? p.ss_mu[a] : 0.0;
     if constexpr (REG && SYM) {
@@ -365,7 +367,10 @@ struct SiteModel {
 #pragma unroll
       for (int r = 0; r < Q * Q; ++r) Vr[r] = act ? __ldg(p.ss_V + (size_t)r * p.ld + a) : 0.0;
 #pragma unroll
-      for (int j = 0; j < Q; ++j) rr[j] = act ? 1.0 / __ldg(p.ss_Pi + (size_t)j * p.ld + a) : 0.0;
+      for (int j = 0; j < Q; ++j) {
+        const double pi = act ? __ldg(p.ss_Pi + (size_t)j * p.ld + a) : 1.0;
+        rr[j] = pre ? TTB_TINY * pi : (act ? 1.0 / pi : 0.0);
+      }
     } else if constexpr (REG) {
       V = Vi = nullptr; vs = 0;
 #pragma unroll
@@ -455,6 +460,47 @@ struct SiteModel {
 #pragma unroll
       for (int k = 0; k < Q; ++k) acc = fma(wk[k], vi(k * Q + j), acc);
       U[j] = clamp ? at_least(acc, TTB_TINY) : acc;
+    }
+  }
+  // Symmetric form in the PREORDER: the factors r_j = 1 / Pi_a[j] cancel.  The up-message is U[j] = r_j u[j] with
+  // u = V (c e * (V^T S)), clamped: max(TINY, r_j u[j]) = r_j max(TINY Pi_j, u[j]); the outside message enters the way down
+  // as y[j] = r_j O[j] with O[j] = Mp[j] prod_{k != j} U[k], so y[j] = (prod_k r_k) Mp[j] prod_{k != j} max(TINY Pi_k, u[k]) --
+  // the constant prod_k r_k drops out in the final normalisation of the profile.  up_pre returns the clamped u (rr[] holds
+  // TINY Pi_j, see init_level), down_pre takes y: 2 Q multiplications fewer per child and pattern than up + down.
+  __device__ __forceinline__ void up_pre(const double (&S)[Q], const double (&e)[Q], double (&U)[Q]) const {
+    static_assert(REG && SYM, "symmetric register-resident form only");
+    double wk[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < Q; ++i) acc = fma(S[i], Vr[i * Q + k], acc);
+      wk[k] = acc * e[k];
+    }
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < Q; ++k) acc = fma(wk[k], Vr[j * Q + k], acc);
+      U[j] = at_least(acc, rr[j]);
+    }
+  }
+  __device__ __forceinline__ void down_pre(const double (&y)[Q], const double (&e)[Q], double (&msg)[Q]) const {
+    static_assert(REG && SYM, "symmetric register-resident form only");
+    double wk[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < Q; ++j) acc = fma(Vr[j * Q + k], y[j], acc);
+      wk[k] = acc * e[k];
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < Q; ++k) acc = fma(Vr[i * Q + k], wk[k], acc);
+      msg[i] = acc;
     }
   }
   // parent -> child: msg[i] = sum_j P[i][j] O[j]
@@ -1620,7 +1666,7 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
   }
   if (SS && !MREG) pipe.wait_model();
   SiteModel<Q, MREG, SYM> sm;
-  if constexpr (SS) sm.init_level(p, a, act, pipe.model, tid);
+  if constexpr (SS) sm.init_level(p, a, act, pipe.model, tid, SYM);
   pdl_wait();
 
   double Mp[Q];
@@ -1671,13 +1717,15 @@ __global__ void __launch_bounds__(TTB_LEVEL_THREADS) __maxnreg__((SS && Q <= TTB
             sm.efac_staged(rec.y, rec.x, pipe.P(s) + c.erow(b) * EROWS + tid, e);
           } else
             sm.efac(p, c.cnode(b), e);
-          sm.up(Sc, e, U);
+          if constexpr (SYM) sm.up_pre(Sc, e, U);   // u = U / r, clamped at TINY / r: the r_j cancel on the way down
+          else sm.up(Sc, e, U);
           if (MASK && mo) {
 #pragma unroll
             for (int j = 0; j < Q; ++j) U[j] = 1.0;
           }
           outgroup_message<Q, (Q > 8)>(Mp, U, O);
-          sm.down(O, e, msg);
+          if constexpr (SYM) sm.down_pre(O, e, msg);
+          else sm.down(O, e, msg);
           double z = 0.0;
 #pragma unroll
           for (int i = 0; i < Q; ++i) {
