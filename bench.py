@@ -737,7 +737,9 @@ def roofline_block(leg, phases, pass_ms, workload):
     dom_ms, dom_launches = phases[dom]
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9
     return {
-        'bound': 'hbm', 'kernel': '%s_level_kernel<%d> (%d level launches per pass)' % ('pre' if dom == 'preorder' else 'post', q, dom_launches),
+        'bound': 'hbm', 'kernel': '%s_level%s_kernel<%d> (%d level launches per pass)' % (
+            'pre' if dom == 'preorder' else 'post',
+            '_mma' if (q > 8 and not leg.g.get('site_specific') and not os.environ.get('TTB_NO_MMA')) else '', q, dom_launches),
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
         'peak_note': 'peak is a measured COPY bandwidth (1:1 read:write); the preorder kernel streams 2:1 read:write and can sit at or slightly above it',
         'algorithmic_bytes_per_pass': int(dom_bytes), 'kernel_ms_per_pass': dom_ms,
