@@ -303,8 +303,32 @@ class DeviceMarginalMixin(object):
             return None if m1 is None or m2 is None else np.asarray(m1) * np.asarray(m2)
         return getattr(node, 'mask', None)
 
+    def _shard_sizes(self):
+        """Pattern count of every rank's shard (shard_bounds is deterministic: no need to exchange them)."""
+        L, W = self.data.compressed_length, self.comm.world_size
+        return [hi - lo for lo, hi in (shard_bounds(L, r, W) for r in range(W))]
+
     def _gather_patterns(self, x, axis=0):
-        return x if self.comm.world_size == 1 else self.comm.allgather(x, axis=axis)
+        if self.comm.world_size == 1:
+            return x
+        sizes = self._shard_sizes()
+        return self.comm.allgather(x, axis=axis, sizes=sizes if np.shape(x)[axis] == sizes[self.comm.rank] else None)
+
+    def _gather_pass_results(self, site_lh, tot, nd):
+        """tree.sequence_LH of all shards plus the summed {total LH, N_diff} of a pass in ONE collective: every rank appends
+        its two scalars to its per-pattern likelihoods (the scalars are then added up in rank order on every rank: same
+        bits everywhere)."""
+        if self.comm.world_size == 1:
+            return site_lh, tot, nd
+        sizes = [k + 2 for k in self._shard_sizes()]
+        g = self.comm.allgather(np.concatenate([np.asarray(site_lh, dtype=np.float64), [float(tot), float(nd)]]), sizes=sizes)
+        parts, off, tot, nd = [], 0, 0.0, 0.0
+        for k in sizes:
+            parts.append(g[off:off + k - 2])
+            tot += g[off + k - 2]
+            nd += g[off + k - 1]
+            off += k
+        return np.concatenate(parts), tot, nd
 
     def _node_array(self, node, which):
         key = (node._fid, which)
@@ -367,11 +391,9 @@ class DeviceMarginalMixin(object):
         stale, self._stale_states = self._stale_states, None
         eng.marginal(reconstruct_tips=reconstruct_tip_states, keep_prev=other_sample)
         tot, nd = eng.results()
-        if self.comm.world_size > 1:
-            tot, nd = self.comm.allreduce_sum(np.array([tot, float(nd)]))
         self._cache = {}
         self._seq_cache = {}
-        self.tree.sequence_LH = self._gather_patterns(eng.site_lh())
+        self.tree.sequence_LH, tot, nd = self._gather_pass_results(eng.site_lh(), tot, nd)
         self.tree.total_sequence_LH = float(tot)
         self.tree.sequence_marginal_LH = self.tree.total_sequence_LH
         had_reconstruction, prev_tips = self.sequence_reconstruction, self.reconstructed_tip_sequences
@@ -491,11 +513,9 @@ class DeviceMarginalMixin(object):
         else:
             eng.joint(reconstruct_tips=reconstruct_tip_states)
         tot, nd = eng.results()
-        if self.comm.world_size > 1:
-            tot, nd = self.comm.allreduce_sum(np.array([tot, float(nd)]))
         self._cache = {}
         self._seq_cache = {}
-        self.tree.sequence_LH = self._gather_patterns(eng.site_lh())
+        self.tree.sequence_LH, tot, nd = self._gather_pass_results(eng.site_lh(), tot, nd)
         self.tree.sequence_joint_LH = float(tot)
         N_diff = self._n_diff(eng, topo, nd, reconstruct_tip_states, self.reconstructed_tip_sequences, stale=stale)
         self.tree.root._cseq_override = None

@@ -26,7 +26,7 @@ class SingleComm(object):
     def allreduce_sum(self, x):
         return np.asarray(x, dtype=np.float64)
 
-    def allgather(self, x, axis=0):
+    def allgather(self, x, axis=0, sizes=None):
         return np.asarray(x)
 
     def barrier(self):
@@ -54,24 +54,39 @@ class TorchComm(object):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
-    def allgather(self, x, axis=0):
-        """Concatenate per-rank arrays (possibly of different length along `axis`): two tensor collectives -- the
-        per-rank lengths, then the data padded to the longest shard -- no pickling (the per-pattern likelihoods are
-        gathered every pass, the q^2 L' site statistics per GTR inference)."""
+    def allgather(self, x, axis=0, sizes=None):
+        """Concatenate per-rank arrays (possibly of different length along `axis`).  Tensor collectives, no pickling:
+        the per-rank lengths (skipped when the caller knows them -- pattern shards follow shard_bounds -- and passes
+        `sizes`), then the data padded to the longest shard into ONE output tensor, so a gather costs one collective, one
+        host->device and one device->host copy whatever the world size (it runs every pass for tree.sequence_LH)."""
         torch = self.torch
         x = np.ascontiguousarray(np.moveaxis(np.asarray(x), axis, 0))
-        n = torch.tensor([x.shape[0]], dtype=torch.int64, device=self.device)
-        sizes = [torch.zeros_like(n) for _ in range(self.world_size)]
-        self.dist.all_gather(sizes, n, group=self.group)
-        sizes = [int(s.item()) for s in sizes]
+        W = self.world_size
+        if sizes is None:
+            n = torch.tensor([x.shape[0]], dtype=torch.int64, device=self.device)
+            got = self._gather_flat(n, W)
+            sizes = [int(v) for v in got.cpu().tolist()]
+        else:
+            sizes = [int(v) for v in sizes]
+            assert len(sizes) == W and sizes[self.rank] == x.shape[0], 'allgather: sizes do not match this rank\'s array'
         width = max(sizes)
         t = torch.zeros((width,) + x.shape[1:], dtype=torch.from_numpy(x[:0]).dtype, device=self.device)
         if x.shape[0]:
             t[:x.shape[0]] = torch.from_numpy(x).to(self.device)
-        parts = [torch.empty_like(t) for _ in range(self.world_size)]
-        self.dist.all_gather(parts, t, group=self.group)
-        out = np.concatenate([p[:k].cpu().numpy() for p, k in zip(parts, sizes)], axis=0)
+        host = self._gather_flat(t, W).cpu().numpy().reshape((W, width) + x.shape[1:])
+        out = np.concatenate([host[r, :k] for r, k in enumerate(sizes)], axis=0)
         return np.moveaxis(out, 0, axis)
+
+    def _gather_flat(self, t, W):
+        """all_gather of equally shaped tensors into one tensor of W times the leading extent."""
+        out = self.torch.empty((W * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        try:
+            self.dist.all_gather_into_tensor(out, t, group=self.group)
+        except (RuntimeError, NotImplementedError, AttributeError):      # a backend without the fused form
+            parts = [self.torch.empty_like(t) for _ in range(W)]
+            self.dist.all_gather(parts, t, group=self.group)
+            out = self.torch.cat(parts, dim=0)
+        return out
 
     def allreduce_sum_device(self, engine):
         """In-place sum over the ranks of n doubles at a device address (NCCL only): a callable (ptr, n) for
