@@ -6,6 +6,7 @@
 `reconstructed_tip_sequences`.
 """
 import operator
+import os
 
 import numpy as np
 
@@ -320,6 +321,9 @@ class DeviceMarginalMixin(object):
         bits everywhere)."""
         if self.comm.world_size == 1:
             return site_lh, tot, nd
+        if os.environ.get('TTB_TWO_COLLECTIVES'):      # measurement only: the earlier form (all-reduce + gather with size exchange)
+            tot, nd = self.comm.allreduce_sum(np.array([tot, float(nd)]))
+            return self.comm.allgather(site_lh), tot, nd
         sizes = [k + 2 for k in self._shard_sizes()]
         g = self.comm.allgather(np.concatenate([np.asarray(site_lh, dtype=np.float64), [float(tot), float(nd)]]), sizes=sizes)
         parts, off, tot, nd = [], 0, 0.0, 0.0
