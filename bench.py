@@ -728,6 +728,29 @@ def phase_profile(eng):
     return phases
 
 
+FP64_TENSOR_PEAK_TFLOPS = 37.0     # mma.sync.m8n8k4.f64 on this pool's B200s, measured: tools/probe/dmma_probe.cu, profiles/R2_dmma_probe.txt
+
+
+def fp64_pipe_block(leg, phases):
+    """q >= 20 (tensor-pipe level kernels): flops of the two matrix products against the measured fp64 tensor peak.  The
+    whole-pass HBM figure stays the headline bound; this block says how busy the pipe is that actually limits these
+    kernels (DESIGN.md par. 4).  useful = 2 q^2 per product, child and pattern; issued = what the padded mma tiles execute."""
+    q = leg.q
+    flat = leg.flat
+    n_int_children = int((flat['tip_row'][1:] < 0).sum())
+    Lp = int(flat['multiplicity'].shape[0])
+    ks = (q + 3) // 4
+    mtiles = -(-Lp // 128) * 16                      # m-tiles of 8 patterns, whole 128-pattern tiles
+    useful = {'postorder': 2.0 * q * q * n_int_children * Lp, 'preorder': 4.0 * q * q * n_int_children * Lp}
+    issued = {'postorder': 512.0 * ks * 3 * n_int_children * mtiles, 'preorder': 1024.0 * ks * 3 * n_int_children * mtiles}
+    out = {'peak_tflops': FP64_TENSOR_PEAK_TFLOPS, 'peak_source': 'measured (tools/probe/dmma_probe.cu; DFMA shares the pipe)'}
+    for k in ('postorder', 'preorder'):
+        sec = phases[k][0] / 1e3
+        out[k] = {'useful_tflops': useful[k] / sec / 1e12, 'issued_tflops': issued[k] / sec / 1e12,
+                  'frac_issued_of_peak': issued[k] / sec / 1e12 / FP64_TENSOR_PEAK_TFLOPS}
+    return out
+
+
 def roofline_block(leg, phases, pass_ms, workload):
     peak, peak_src = measured_peak()
     q = leg.q
@@ -736,10 +759,16 @@ def roofline_block(leg, phases, pass_ms, workload):
     dom_bytes = pre_b if dom == 'preorder' else post_b
     dom_ms, dom_launches = phases[dom]
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9
-    return {
+    mma = q > 8 and not leg.g.get('site_specific') and not os.environ.get('TTB_NO_MMA')
+    extra = {}
+    if mma:
+        try:
+            extra['fp64_tensor_pipe'] = fp64_pipe_block(leg, phases)
+        except Exception as e:      # an extra, never the reason a bench line is lost
+            extra['fp64_tensor_pipe'] = {'error': repr(e)}
+    return dict(extra, **{
         'bound': 'hbm', 'kernel': '%s_level%s_kernel<%d> (%d level launches per pass)' % (
-            'pre' if dom == 'preorder' else 'post',
-            '_mma' if (q > 8 and not leg.g.get('site_specific') and not os.environ.get('TTB_NO_MMA')) else '', q, dom_launches),
+            'pre' if dom == 'preorder' else 'post', '_mma' if mma else '', q, dom_launches),
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
         'peak_note': 'peak is a measured COPY bandwidth (1:1 read:write); the preorder kernel streams 2:1 read:write and can sit at or slightly above it',
         'algorithmic_bytes_per_pass': int(dom_bytes), 'kernel_ms_per_pass': dom_ms,
@@ -749,7 +778,7 @@ def roofline_block(leg, phases, pass_ms, workload):
                        'achieved_gbs': (post_b + pre_b) / (pass_ms / 1e3) / 1e9, 'frac': (post_b + pre_b) / (pass_ms / 1e3) / 1e9 / peak,
                        'survey_bytes_per_update': SURVEY_BYTES_PER_UPDATE.get(q),
                        'survey_frac': (SURVEY_BYTES_PER_UPDATE.get(q, 0) * leg.updates_local / (pass_ms / 1e3) / 1e9 / peak)
-                       if q in SURVEY_BYTES_PER_UPDATE else None}}
+                       if q in SURVEY_BYTES_PER_UPDATE else None}})
 
 
 def main():
