@@ -206,6 +206,16 @@ def test_fastscan_equals_python_scans(monkeypatch):
     assert not _fastscan.scan_float_attr(dicts, 'branch_length', out, 1)          # missing attribute
     assert not _fastscan.scan_float_attr(dicts, 'branch_length', np.zeros(1000, dtype=np.float32), 1)
     assert _fastscan.any_not_none(tuple(dicts), 'mask') is None                     # not a list: cannot tell
+    # both scans in one walk
+    for n in nodes:
+        n.branch_length = 0.5
+    nodes[999].mask = None
+    both = np.full(1000, -1.0)
+    assert _fastscan.scan_nodes(dicts, 'branch_length', 'mask', both, 1) is False and both[0] == -1.0 and (both[1:] == 0.5).all()
+    nodes[0].mask = np.ones(2)                                                     # the root's mask counts as well
+    assert _fastscan.scan_nodes(dicts, 'branch_length', 'mask', both, 1) is True
+    nodes[500].branch_length = 'x'
+    assert _fastscan.scan_nodes(dicts, 'branch_length', 'mask', both, 1) is None
 
     tree = synth.random_tree(40, seed=5, mean_bl=1e-3, zero_frac=0.2)
     g = util.nuc_gtr()
@@ -215,6 +225,7 @@ def test_fastscan_equals_python_scans(monkeypatch):
     fast = tt._branch_lengths_to_gtr(flat_nodes)
     monkeypatch.setattr(_fastscan, 'scan_float_attr', lambda *a, **k: False)
     monkeypatch.setattr(_fastscan, 'any_not_none', lambda *a, **k: None)
+    monkeypatch.setattr(_fastscan, 'scan_nodes', lambda *a, **k: None)
     assert np.array_equal(tt._branch_lengths_to_gtr(flat_nodes), fast)
     tt.infer_ancestral_sequences(marginal=True)
     lh = tt.tree.total_sequence_LH

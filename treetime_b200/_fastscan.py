@@ -35,6 +35,8 @@ def load():
         lib.ttb_scan_float_attr.restype = ctypes.c_int
         lib.ttb_any_not_none.argtypes = [ctypes.py_object, ctypes.py_object]
         lib.ttb_any_not_none.restype = ctypes.c_int
+        lib.ttb_scan_nodes.argtypes = [ctypes.py_object, ctypes.py_object, ctypes.py_object, ctypes.c_void_p, ctypes.c_ssize_t]
+        lib.ttb_scan_nodes.restype = ctypes.c_int
         _lib = lib
     except (OSError, AttributeError):
         _lib = None
@@ -56,3 +58,14 @@ def any_not_none(dicts, key):
         return None
     r = lib.ttb_any_not_none(dicts, key)
     return None if r < 0 else bool(r)
+
+
+def scan_nodes(dicts, float_key, mask_key, out, start=0):
+    """Both per-pass scans in one cache-friendly walk: fills out[start:] like scan_float_attr and returns whether any
+    dict has a non-None `mask_key` (True / False); None if the fast path cannot do it (nothing is guaranteed about `out`)."""
+    lib = load()
+    if lib is None or out.dtype.str != '<f8' or not out.flags.c_contiguous or out.shape[0] != len(dicts):
+        return None
+    r = lib.ttb_scan_nodes(dicts, float_key, mask_key, out.ctypes.data, start)
+    return None if r < 0 else bool(r)
+
